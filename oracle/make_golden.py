@@ -1,0 +1,170 @@
+"""TEST INFRASTRUCTURE ONLY -- regenerate tests/golden/*.npz from the REAL
+reference (``/root/reference`` executed under ``oracle/ref_shim.py``).
+
+    python -m oracle.make_golden            # in the build container
+
+The reference cannot travel to the GPU box, so its outputs on small seeded
+inputs are committed as fixtures together with this script.  Inputs are stored
+inside the fixtures so they stay self-contained.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from odin_b200 import synth  # noqa: E402
+from oracle import ref_shim  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _chain(sp, base, cfg):
+  steps = [
+      sp.AudioReader(remove_dc=True),
+      sp.PreEmphasis(0.97),
+      sp.STFTExtractor(cfg["frame_length"], cfg["step_length"], n_fft=cfg["n_fft"],
+                       window="hamm", energy=True),
+      sp.PowerSpecExtractor(2.0, output_name="spec"),
+      sp.MelsSpecExtractor(cfg["n_mels"], fmin=cfg["fmin"], fmax=cfg["fmax"]),
+      sp.MFCCsExtractor(cfg["n_ceps"], remove_first_coef=True, first_coef_energy=True),
+      base.DeltaExtractor("mfcc", order=(0, 1, 2)),
+      sp.SADgmm(3, smooth_window=3, input_name="stft_energy", output_name="sad_gmm"),
+      sp.SADthreshold(input_name="mfcc_energy", output_name="sad_thr"),
+  ]
+  return steps
+
+
+FE_CONFIGS = {
+    # SURVEY.md 8d config 1
+    "cfg1": dict(sr=16000, frame_length=0.025, step_length=0.010, n_fft=512, n_mels=40,
+                 fmin=64, fmax=8000, n_ceps=20, durations=[1.0, 0.64, 1.37]),
+    # config 3 front-end
+    "cfg3": dict(sr=16000, frame_length=0.025, step_length=0.010, n_fft=1024, n_mels=80,
+                 fmin=64, fmax=None, n_ceps=20, durations=[1.21]),
+    # config 5 (FSDD recipe, examples/fsdd_ivec.py:80-106)
+    "cfg5": dict(sr=8000, frame_length=0.025, step_length=0.005, n_fft=512, n_mels=24,
+                 fmin=64, fmax=4000, n_ceps=20, durations=[0.35, 0.8, 0.52]),
+}
+
+
+def frontend_fixtures():
+  pp, _ = ref_shim.load_frontend()
+  sp, base = pp.speech, pp.base
+  for name, cfg in FE_CONFIGS.items():
+    blob = {}
+    for i, dur in enumerate(cfg["durations"]):
+      raw = synth.speech_like(100 * len(name) + i, dur, cfg["sr"], seed=977)
+      X = ref_shim.run_pipeline(_chain(sp, base, cfg), {"raw": raw, "sr": cfg["sr"]})
+      blob["u%d_pcm" % i] = raw
+      blob["u%d_raw" % i] = X["raw"]                       # f32 after DC + pre-emphasis
+      blob["u%d_energy" % i] = X["stft_energy"]            # f32 [T,1]
+      blob["u%d_mspec" % i] = X["mspec"]                   # f64 [T,n_mels]
+      blob["u%d_mfcc" % i] = X["mfcc"]                     # f64 [T,60]
+      blob["u%d_c0" % i] = X["mfcc_energy"]                # f64 [T]
+      blob["u%d_spec_row0" % i] = X["spec"][0]             # f64 [n_bins]
+      blob["u%d_sad_gmm" % i] = X["sad_gmm"].astype(np.uint8)
+      blob["u%d_sad_gmm_threshold" % i] = np.float64(X["sad_gmm_threshold"])
+      blob["u%d_sad_thr" % i] = X["sad_thr"].astype(np.uint8)
+      blob["u%d_sad_thr_threshold" % i] = np.float64(X["sad_thr_threshold"])
+    blob["n_utt"] = np.int64(len(cfg["durations"]))
+    np.savez_compressed(os.path.join(OUT, "fe_%s.npz" % name), **blob)
+    print("wrote fe_%s.npz" % name)
+  # SURVEY.md Appendix B input (RNG-free)
+  n = np.arange(4800)
+  raw = np.round(10000 * np.sin(2 * np.pi * 440 * n / 16000) +
+                 3000 * np.sin(2 * np.pi * 1234.5 * n / 16000) * (n > 2400)).astype(np.int16)
+  X = ref_shim.run_pipeline(_chain(sp, base, FE_CONFIGS["cfg1"]), {"raw": raw, "sr": 16000})
+  np.savez_compressed(
+      os.path.join(OUT, "fe_appendix_b.npz"), pcm=raw, raw=X["raw"], energy=X["stft_energy"],
+      mspec=X["mspec"], mfcc=X["mfcc"], c0=X["mfcc_energy"],
+      sad_gmm=X["sad_gmm"].astype(np.uint8), sad_gmm_threshold=np.float64(X["sad_gmm_threshold"]),
+      sad_thr=X["sad_thr"].astype(np.uint8), sad_thr_threshold=np.float64(X["sad_thr_threshold"]))
+  print("wrote fe_appendix_b.npz")
+  # smoothing quirk: bool vs uint8 routes, reference smooth()
+  _, S = ref_shim.load_frontend()
+  rng = np.random.RandomState(5)
+  cases = [(rng.rand(n_) < p).astype(np.uint8) for n_ in (5, 6, 9, 17, 40) for p in (0.2, 0.5, 0.8)]
+  cases.append(np.array([0, 1, 1, 0, 0, 0, 0, 1, 1, 0], dtype=np.uint8))
+  blob = {"n": np.int64(len(cases))}
+  for i, x in enumerate(cases):
+    blob["x%d" % i] = x
+    blob["bool3_%d" % i] = (S.smooth(x.astype(bool), win=3, window="flat") >= 2. / 3).astype(np.uint8)
+    blob["u8_5_%d" % i] = (S.smooth(x, win=5, window="flat") >= 2. / 5).astype(np.uint8)
+  np.savez_compressed(os.path.join(OUT, "smooth.npz"), **blob)
+  print("wrote smooth.npz")
+
+
+def gmm_fixtures():
+  # (a) Appendix-B RNG-free case, both arithmetic modes of the reference
+  N, D, M = 1000, 6, 8
+  n = np.arange(N)[:, None]
+  d = np.arange(D)[None, :]
+  m = np.arange(M)[None, :]
+  dd = np.arange(D)[:, None]
+  X = (2 * np.sin(0.37 * n + 1.3 * d) + 0.5 * np.cos(0.011 * n * (d + 1))).astype("f")
+  mean = (1.5 * np.cos(0.5 * m + 0.2 * dd)).astype("f")
+  sigma = (0.5 + 0.25 * (1 + np.sin(m + dd))).astype("f")
+  w = ((1 + np.arange(M)) / 36)[None, :].astype("f")
+  blob = dict(X=X, mean=mean, sigma=sigma, w=w)
+  for tag, mode in (("np2", False), ("f32", True)):
+    g = ref_shim.make_ref_gmm(M, float32_mode=mode)
+    ref_shim.ref_gmm_initialize(g, X)
+    g.mean, g.sigma, g.w = mean.copy(), sigma.copy(), w.copy()
+    g._resfresh_cpu_posterior()
+    Z, F, S, L = g.expectation(X)
+    Zt, Ft = g.transform(X[:100])
+    g.maximization(Z, F, S)
+    blob.update({tag + "_Z": Z, tag + "_F": F, tag + "_S": S, tag + "_L": np.float64(L),
+                 tag + "_Zt": Zt, tag + "_Ft": Ft, tag + "_mean1": g.mean,
+                 tag + "_sigma1": g.sigma, tag + "_w1": g.w})
+  np.savez_compressed(os.path.join(OUT, "gmm_appendix_b.npz"), **blob)
+  print("wrote gmm_appendix_b.npz")
+
+  # (b) seeded D=60, M=64 E-step (config-2 shape, 3000 frames) with and without SAD
+  X = synth.gmm_features(3000, 60, 32, seed=11)
+  mean, sigma, w = synth.gmm_params(60, 64, seed=12)
+  sad = (np.random.RandomState(13).rand(3000) > 0.35).astype(np.uint8)
+  blob = dict(X=X, mean=mean, sigma=sigma, w=w, sad=sad)
+  for tag, mode in (("np2", False), ("f32", True)):
+    g = ref_shim.make_ref_gmm(64, float32_mode=mode)
+    ref_shim.ref_gmm_initialize(g, X)
+    g.mean, g.sigma, g.w = mean.copy(), sigma.copy(), w.copy()
+    g._resfresh_cpu_posterior()
+    Z, F, S, L = g.expectation(X)
+    Zs, Fs, Ss, Ls = g.expectation(X, sad=sad)
+    blob.update({tag + "_Z": Z, tag + "_F": F, tag + "_S": S, tag + "_L": np.float64(L),
+                 tag + "_Zsad": Zs, tag + "_Fsad": Fs, tag + "_Ssad": Ss,
+                 tag + "_Lsad": np.float64(Ls)})
+  # per-utterance statistics (transform) for three ragged "utterances"
+  g = ref_shim.make_ref_gmm(64)
+  ref_shim.ref_gmm_initialize(g, X)
+  g.mean, g.sigma, g.w = mean.copy(), sigma.copy(), w.copy()
+  g._resfresh_cpu_posterior()
+  bounds = [(0, 700), (700, 1900), (1900, 3000)]
+  Zs, Fs = zip(*[g.transform(X[s:e]) for s, e in bounds])
+  blob.update(utt_bounds=np.array(bounds), utt_Z=np.concatenate(Zs, 0), utt_Fhat=np.concatenate(Fs, 0))
+  np.savez_compressed(os.path.join(OUT, "gmm_d60_m64.npz"), **blob)
+  print("wrote gmm_d60_m64.npz")
+
+  # (c) full fit 1 -> 8 mixtures with the reference's split schedule (D=12)
+  X = synth.gmm_features(6000, 12, 8, seed=3)
+  g = ref_shim.make_ref_gmm(8, nmix_start=1, niter=4)
+  g.fit(X)
+  hist = dict(g._llk_hist)
+  np.savez_compressed(
+      os.path.join(OUT, "gmm_fit_d12_m8.npz"), X=X, mean=g.mean, sigma=g.sigma, w=g.w,
+      llk_last=np.array([float(hist[k][-1]) for k in (1, 2, 4, 8)]),
+      niters=np.array([len(hist[k]) for k in (1, 2, 4, 8)]))
+  print("wrote gmm_fit_d12_m8.npz")
+
+
+if __name__ == "__main__":
+  warnings.filterwarnings("ignore")
+  os.makedirs(OUT, exist_ok=True)
+  frontend_fixtures()
+  gmm_fixtures()

@@ -1,0 +1,86 @@
+"""CPU, build container only: the oracle against the REAL reference executed
+under oracle/ref_shim.py on fresh seeded inputs.  Skipped where the reference
+checkout is absent (the GPU box)."""
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import relmax
+from odin_b200 import synth
+from oracle import frontend as F
+from oracle import gmm as OG
+from oracle import ref_shim
+
+pytestmark = pytest.mark.skipif(not ref_shim.available(), reason="reference checkout absent")
+
+
+def _ref_chain(raw, sr, cfg):
+  from oracle.make_golden import _chain
+  pp, _ = ref_shim.load_frontend()
+  with warnings.catch_warnings():
+    warnings.simplefilter("ignore")
+    return ref_shim.run_pipeline(_chain(pp.speech, pp.base, cfg), {"raw": raw, "sr": sr})
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_frontend_matches_reference(seed):
+  from oracle.make_golden import FE_CONFIGS
+  name = ["cfg1", "cfg3", "cfg5", "cfg1"][seed]
+  cfg = FE_CONFIGS[name]
+  raw = synth.speech_like(seed, 0.9 + 0.4 * seed, cfg["sr"], seed=31)
+  R = _ref_chain(raw, cfg["sr"], cfg)
+  o = F.extract(raw, cfg["sr"], cfg["frame_length"], cfg["step_length"], cfg["n_fft"],
+                n_mels=cfg["n_mels"], fmin=cfg["fmin"], fmax=cfg["fmax"], vad="gmm")
+  assert o["mfcc"].shape == R["mfcc"].shape
+  assert np.array_equal(o["raw"], R["raw"])
+  assert np.array_equal(o["stft_energy"], R["stft_energy"])
+  assert relmax(o["mspec"], R["mspec"]) < 1e-12
+  assert relmax(o["mfcc"], R["mfcc"]) < 1e-12
+  assert np.array_equal(o["sad"], R["sad_gmm"])
+  assert abs(o["sad_threshold"] - R["sad_gmm_threshold"]) < 1e-9
+  s2, t2 = F.sad_threshold(o["mfcc_energy"])
+  assert np.array_equal(s2, R["sad_thr"]) and abs(t2 - R["sad_thr_threshold"]) < 1e-9
+
+
+def test_mel_and_dct_tables():
+  _, S = ref_shim.load_frontend()
+  for sr, n_fft, n_mels, fmin, fmax in [(16000, 512, 40, 64, 8000), (16000, 1024, 80, 64, 8000),
+                                        (8000, 512, 24, 64, 4000), (8000, 256, 24, 0, 3800)]:
+    assert np.allclose(F.mel_filterbank(sr, n_fft, n_mels, fmin, fmax),
+                       S.mel_filters(sr, n_fft, n_mels, fmin, fmax), rtol=0, atol=1e-15)
+  assert np.allclose(F.dct_basis(21, 40), S.dct_filters(21, 40), rtol=0, atol=1e-14)
+  for name in ("hamm", "hann"):
+    assert np.allclose(F.window_table(name, 400), S.get_window(name, 400), rtol=0, atol=1e-15)
+
+
+def test_smooth_exhaustive_short():
+  """every 0/1 sequence of length 5..9 through the reference smooth(), both
+  dtype routes."""
+  _, S = ref_shim.load_frontend()
+  for n in range(5, 10):
+    for code in range(2**n):
+      x = np.array([(code >> i) & 1 for i in range(n)], dtype=np.uint8)
+      for win, thr in ((3, 2. / 3), (5, 2. / 5)):
+        assert np.array_equal(S.smooth(x, win=win, window="flat") >= thr,
+                              F.smooth_flat(x, win) >= thr)
+        assert np.array_equal(S.smooth(x.astype(bool), win=win, window="flat") >= thr,
+                              F.smooth_flat(x.astype(bool), win) >= thr)
+
+
+def test_gmm_estep_and_fit_match_reference():
+  X = synth.gmm_features(5000, 20, 8, seed=77)
+  mean, sigma, w = synth.gmm_params(20, 16, seed=78)
+  for mode, dt in ((False, None), (True, np.float32)):
+    g = ref_shim.make_ref_gmm(16, float32_mode=mode)
+    ref_shim.ref_gmm_initialize(g, X)
+    g.mean, g.sigma, g.w = mean.copy(), sigma.copy(), w.copy()
+    g._resfresh_cpu_posterior()
+    Z, Fs, S, L = g.expectation(X)
+    z, f, s, l, _ = OG.expectation(X, mean, sigma, w, compute_dtype=dt)
+    assert np.array_equal(Z, z) and np.array_equal(Fs, f) and np.array_equal(S, s)
+    assert float(L) == float(l)
+  g = ref_shim.make_ref_gmm(4, nmix_start=1, niter=3)
+  g.fit(X)
+  m, s, ww, hist = OG.fit(X, 4, niter=3)
+  assert np.array_equal(g.mean, m) and np.array_equal(g.sigma, s) and np.array_equal(g.w, ww)
