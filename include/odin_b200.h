@@ -1,0 +1,192 @@
+/* odin_b200.h -- C-ABI of libodin_b200.so: the B200 (sm_100a) replacement for the
+ * arithmetic of odin-ai's speech front-end and GMM-UBM Baum-Welch hot path.
+ *
+ * The reference (trungnt13/odin-ai) is pure Python and has no FFI layer of its
+ * own; each entry point below names the reference function(s) whose arithmetic
+ * it replaces (file:line relative to the reference root).  The Python classes in
+ * odin_b200/preprocessing and odin_b200/ml keep the reference's Extractor /
+ * GMM surface and call these functions through ctypes (INTEGRATION.md shows the
+ * stub a reference maintainer would add).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / CUDA-runtime types in signatures
+ *    (`stream` is a cudaStream_t passed as void*; NULL = legacy default stream).
+ *  - pointers prefixed d_ are DEVICE pointers owned by the caller, h_ are HOST
+ *    pointers.  The library allocates only handle-internal tables / workspace.
+ *  - every function returns 0 on success or a negative ODIN_E* code and never
+ *    throws; odin_last_error() returns the message of the calling thread's last
+ *    failure.
+ *  - all kernels are launched on the caller's stream; functions are asynchronous
+ *    unless stated.  Handles are not thread-safe: one per GPU / stream.
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point
+ *    fails with ODIN_ENODEVICE.
+ */
+#ifndef ODIN_B200_H_
+#define ODIN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ODIN_OK 0
+#define ODIN_EINVAL (-1)    /* bad argument / unsupported configuration */
+#define ODIN_ENODEVICE (-2) /* no usable CUDA device */
+#define ODIN_ECUDA (-3)     /* CUDA runtime error (see odin_last_error) */
+#define ODIN_ENOMEM (-4)
+#define ODIN_ESHORT (-5)    /* an utterance is shorter than one frame (signal.py:1532-1538 raises) */
+
+const char* odin_last_error(void);
+int odin_version(void); /* 1000*major + minor */
+
+/* ------------------------------------------------------------------------- */
+/* Front-end: AudioReader DC removal -> PreEmphasis -> STFT(+energy) ->        */
+/* PowerSpec -> MelsSpec(+power2db) -> MFCCs -> Delta -> SADgmm / SADthreshold */
+/* ------------------------------------------------------------------------- */
+
+typedef struct odin_fe odin_fe_t;
+
+typedef struct {
+  int32_t sr;
+  int32_t frame_len;      /* samples; speech.py:207-220 resolves seconds -> samples */
+  int32_t hop;            /* samples */
+  int32_t n_fft;          /* power of two, 256..2048, >= frame_len (signal.py:1523-1524) */
+  int32_t window;         /* 0 = hann, 1 = hamming (periodic; signal.py:812-830) */
+  int32_t remove_dc;      /* speech.py:472-473 */
+  float preemph;          /* 0 disables; signal.py:955-967 */
+  int32_t n_mels;         /* <= 128 */
+  float fmin, fmax;       /* Hz, already int-truncated as signal.py:1672-1681 does */
+  float top_db;           /* < 0 disables the clip; signal.py:676-679 */
+  int32_t n_ceps;         /* cepstra kept AFTER dropping c0 (speech.py:821-831); 0 = no MFCC */
+  int32_t delta_width;    /* odd >= 3; signal.py:1002-1066 */
+  int32_t delta_order;    /* 0, 1 or 2: output = [mfcc, d1, d2][: order+1] concatenated */
+  int32_t vad_kind;       /* 0 none, 1 SADgmm on stft energy, 2 SADthreshold on c0 */
+  int32_t vad_nmix;       /* SADgmm nb_mixture (speech.py:1447), 2..4 */
+  int32_t vad_iters;      /* SADgmm nb_train_it */
+  int32_t vad_smooth;     /* smooth_window; < 3 disables (signal.py:986-987) */
+  float vad_mode;         /* signal.py:275-278, 2.0 = standard */
+  float thr_energy;       /* SADthreshold energy_threshold (speech.py:1392-1399) */
+  float thr_mean_scale;
+  float thr_proportion;
+  int32_t thr_context;
+} odin_fe_config;
+
+/* Builds the window / twiddle / sparse-mel / DCT tables (computed in fp64 on the
+ * host exactly as signal.py:682-810 does, stored fp32 + fp64 window) and uploads
+ * them.  Synchronous. */
+int odin_fe_create(const odin_fe_config* cfg, odin_fe_t** out);
+void odin_fe_destroy(odin_fe_t* fe);
+
+/* Output row width of `feat`: n_ceps * (1 + delta_order). */
+int odin_fe_feat_dim(const odin_fe_t* fe);
+
+/* HOST, integer-exact: frame_offsets[u+1]-frame_offsets[u] = 1+(n_u-L)//hop
+ * (signal.py:1532-1538).  Returns ODIN_ESHORT if any utterance has n_u < L
+ * (offsets are still written, with 0 frames for that utterance). */
+int odin_fe_frame_offsets(const odin_fe_t* fe, const int64_t* h_sample_offsets, int32_t n_utt,
+                          int64_t* h_frame_offsets);
+
+/* HOST mirrors of the device integer logic, for CPU-side tests.
+ * odin_host_smooth: signal.py:969-1000 with window='flat' followed by
+ * `>= 2/win`; wrap_u8 = 1 reproduces the uint8 route of SADthreshold
+ * (speech.py:1426-1431), 0 the bool route of SADgmm (speech.py:1465-1473). */
+int odin_host_smooth(const uint8_t* x, int32_t n, int32_t win, int32_t wrap_u8, uint8_t* out);
+/* np.mean / np.std of a float32 vector exactly as numpy evaluates them (pairwise
+ * float32 sums; signal.py:305), the standardisation the SADgmm kernel applies. */
+int odin_host_mean_std_f32(const float* e, int32_t n, float* mean, float* std_);
+/* Handle-free twin of odin_fe_frame_offsets. */
+int odin_host_frame_offsets(int32_t frame_len, int32_t hop, const int64_t* h_sample_offsets, int32_t n_utt,
+                            int64_t* h_frame_offsets);
+/* Dense fp64 tables as built for the device: which = 0 window [frame_len],
+ * 1 mel filterbank [n_mels, n_fft/2+1] (signal.py:735-810), 2 DCT [n_ceps+1, n_mels]
+ * (signal.py:682-733).  Returns the number of doubles written or a negative code. */
+int odin_fe_get_table(const odin_fe_t* fe, int32_t which, double* out, int64_t cap);
+
+/* The fused front-end over a ragged batch of utterances.
+ *   d_pcm            concatenated samples, int16 (pcm_dtype 0) or float32 (1); int16 is NOT
+ *                    rescaled (speech.py:453)
+ *   h_sample_offsets [n_utt+1] HOST, utterance u = samples [off[u], off[u+1])
+ * Outputs (device, any may be NULL except where noted), T = total frames:
+ *   d_mspec  [T, n_mels]  log-mel dB after the utterance-global top_db clip (signal.py:1650-1691)
+ *   d_feat   [T, feat_dim] MFCC (+deltas) (signal.py:1693-1716, 1002-1066; base.py:470-481)
+ *   d_energy [T]          log frame energy on the windowed frame (signal.py:1421-1440)
+ *   d_c0     [T]          DCT row 0 ("mfcc_energy", speech.py:829-830)
+ *   d_sad    [T] uint8    VAD mask; d_sad_thr [n_utt] double threshold (speech.py:1433-1477)
+ * d_mspec is required scratch whenever n_ceps > 0 or any output depends on it.
+ * Asynchronous on `stream` apart from a small pinned->device upload of the offsets. */
+int odin_fe_run(odin_fe_t* fe, const void* d_pcm, int32_t pcm_dtype, const int64_t* h_sample_offsets,
+                int32_t n_utt, float* d_mspec, float* d_feat, float* d_energy, float* d_c0,
+                uint8_t* d_sad, double* d_sad_thr, void* stream);
+
+/* ApplyingSAD (speech.py:1732-1756): order-preserving row compaction of `d_feat`
+ * [T, dim] by the mask.  d_out_offsets [n_utt+1] receives the compacted utterance
+ * boundaries (d_out_offsets[n_utt] = number of rows written).  keep_unvoiced = 1
+ * keeps every frame of an utterance whose mask is all zero. */
+int odin_fe_compact(odin_fe_t* fe, const uint8_t* d_sad, const int64_t* h_frame_offsets, int32_t n_utt,
+                    const float* d_feat, int32_t dim, int32_t keep_unvoiced, float* d_out,
+                    int64_t* d_out_offsets, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* GMM-UBM: odin/ml/gmm_tmat.py                                               */
+/* ------------------------------------------------------------------------- */
+
+typedef struct odin_gmm odin_gmm_t;
+
+/* D = feature dimension, max_nmix = largest mixture count the handle will see. */
+int odin_gmm_create(int32_t feat_dim, int32_t max_nmix, odin_gmm_t** out);
+void odin_gmm_destroy(odin_gmm_t* g);
+
+/* Number of doubles in a packed statistics buffer for `nmix` mixtures:
+ * Z[M] | F[D,M] | S[D,M] | L (sum of per-frame log-likelihood) | nframes. */
+int64_t odin_gmm_stats_size(const odin_gmm_t* g, int32_t nmix);
+
+/* Uploads the model and refreshes the cached posterior constants
+ * (gmm_tmat.py:493-504): precision = 1/(var+1e-6), mu*precision,
+ * C = sum mu^2 prec + sum log(var+1e-6) - 2 log(w+1e-6).
+ * d_mean, d_var: [D, M] row-major (the reference layout); d_w: [M]. */
+int odin_gmm_set_params(odin_gmm_t* g, int32_t nmix, const float* d_mean, const float* d_var,
+                        const float* d_w, void* stream);
+
+/* E-step over N frames (gmm_tmat.py:1012-1041): ACCUMULATES into the packed
+ * d_stats (caller zeroes it at the start of an EM iteration; several calls /
+ * batches may accumulate into the same buffer, which replaces the host-side sum
+ * of gmm_tmat.py:1148-1156,249-265).  d_sad (uint8 [N]) may be NULL; frames with
+ * sad == 0 are skipped (gmm_tmat.py:162-164).  want_second = 0 skips S.
+ * impl: 0 = auto, 1 = fp32 CUDA-core kernels, 2 = 3xTF32 tcgen05 kernels. */
+int odin_gmm_estep(odin_gmm_t* g, const float* d_X, const uint8_t* d_sad, int64_t n_frames,
+                   int32_t want_second, double* d_stats, int32_t impl, void* stream);
+
+/* M-step (gmm_tmat.py:1233-1276) from packed stats, in fp64 on device; writes the
+ * new model into the handle AND to d_mean/d_var/d_w (fp32, reference layout).
+ * If any variance < 0: allow_rollback = 1 keeps the previous model, 0 clips at 0;
+ * *d_rolled_back (int32 on device) is set to 1 in either case. */
+int odin_gmm_mstep(odin_gmm_t* g, const double* d_stats, int32_t allow_rollback, float* d_mean,
+                   float* d_var, float* d_w, int32_t* d_rolled_back, void* stream);
+
+/* Mixture split (gmm_tmat.py:1308-1338): M -> min(2M, new_nmix); reads and
+ * rewrites the caller's arrays, which must have room for new_nmix columns laid
+ * out as [D, new_nmix] AFTER the call (input is [D, M] packed). */
+int odin_gmm_mixup(odin_gmm_t* g, int32_t new_nmix, float* d_mean, float* d_var, float* d_w,
+                   void* stream);
+
+/* Per-utterance centred statistics (gmm_tmat.py:708-767, 769-913):
+ *   d_Z    [n_utt, M]     zeroth order
+ *   d_Fhat [n_utt, M*D]   (F - mean*Z) flattened column-major: index m*D + d
+ * h_frame_offsets [n_utt+1] HOST. */
+int odin_gmm_utt_stats(odin_gmm_t* g, const float* d_X, const uint8_t* d_sad,
+                       const int64_t* h_frame_offsets, int32_t n_utt, float* d_Z, float* d_Fhat,
+                       int32_t impl, void* stream);
+
+/* Per-frame quantities (gmm_tmat.py:916-995): d_llk [N] = logsumexp_m logprob;
+ * d_post [N, M] posteriors and d_logprob [N, M] component log-densities (either may be NULL). */
+int odin_gmm_score(odin_gmm_t* g, const float* d_X, int64_t n_frames, float* d_llk, float* d_post,
+                   float* d_logprob, void* stream);
+
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+int64_t odin_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ODIN_B200_H_ */

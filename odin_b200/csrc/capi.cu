@@ -1,0 +1,505 @@
+// extern "C" entry points of libodin_b200.so (see include/odin_b200.h) and the
+// host-side table construction for the front-end.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "fe.cuh"
+#include "fe_logic.cuh"
+#include "gmm.cuh"
+
+namespace odin {
+
+static thread_local std::string g_err;
+std::atomic<int64_t> g_launches{0};
+
+int set_error(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+int require_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    return set_error(ODIN_ENODEVICE, "no CUDA device available (%s); libodin_b200 has no CPU fallback",
+                     e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  }
+  return ODIN_OK;
+}
+
+int sm_count() {
+  static thread_local int cached_dev = -1, cached = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return cached;
+  if (dev != cached_dev) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) cached = v;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+// ---------------------------------------------------------------------------
+// front-end tables (fp64 on the host, as signal.py builds them)
+// ---------------------------------------------------------------------------
+static double hz2mel(double f) {  // signal.py:489-527
+  const double f_sp = 200.0 / 3.0;
+  if (f >= 1000.0) return 1000.0 / f_sp + log(f / 1000.0) / (log(6.4) / 27.0);
+  return f / f_sp;
+}
+static double mel2hz(double m) {  // signal.py:529-568
+  const double f_sp = 200.0 / 3.0, min_log_mel = 1000.0 / f_sp;
+  if (m >= min_log_mel) return 1000.0 * exp((log(6.4) / 27.0) * (m - min_log_mel));
+  return f_sp * m;
+}
+static std::vector<double> linspace(double a, double b, int n) {  // numpy: start + i*step, last = stop
+  std::vector<double> v(n);
+  if (n == 1) { v[0] = a; return v; }
+  double step = (b - a) / (n - 1);
+  for (int i = 0; i < n; ++i) v[i] = a + i * step;
+  v[n - 1] = b;
+  return v;
+}
+
+template <typename T>
+static int upload(T** dst, const std::vector<T>& src) {
+  size_t bytes = std::max<size_t>(1, src.size()) * sizeof(T);
+  ODIN_CUDA_CHECK(cudaMalloc(dst, bytes));
+  if (!src.empty()) ODIN_CUDA_CHECK(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return ODIN_OK;
+}
+
+int fe_build_tables(odin_fe* fe) {
+  const odin_fe_config& c = fe->cfg;
+  const int L = fe->L, N = fe->N, nb = fe->nbins, nm = fe->n_mels;
+  // window (scipy.signal.get_window(name, L, fftbins=True); signal.py:812-830)
+  fe->h_win.resize(L);
+  double wsum = 0.0;
+  for (int k = 0; k < L; ++k) {
+    double cs = cos(2.0 * M_PI * (double)k / (double)L);
+    fe->h_win[k] = c.window == 0 ? 0.5 - 0.5 * cs : 0.54 - 0.46 * cs;
+    wsum += fe->h_win[k];
+  }
+  double scale = sqrt(1.0 / (wsum * wsum));  // signal.py:1547
+  fe->scale2 = (float)(scale * scale);
+  std::vector<float> win32(L);
+  for (int k = 0; k < L; ++k) win32[k] = (float)fe->h_win[k];
+  std::vector<float2> tw(N);
+  for (int k = 0; k < N; ++k) {
+    double ang = -2.0 * M_PI * (double)k / (double)N;
+    tw[k] = make_float2((float)cos(ang), (float)sin(ang));
+  }
+  // mel filterbank (signal.py:735-810), dense fp64 -> CSR fp32
+  fe->h_mel.assign((size_t)nm * nb, 0.0);
+  std::vector<double> binhz = linspace(0.0, (double)c.sr / 2.0, nb);
+  std::vector<double> mels = linspace(hz2mel((double)c.fmin), hz2mel((double)c.fmax), nm + 2);
+  std::vector<double> edges(nm + 2);
+  for (int i = 0; i < nm + 2; ++i) edges[i] = mel2hz(mels[i]);
+  std::vector<int> mstart(nm), mcnt(nm), moff(nm);
+  std::vector<float> mw;
+  for (int i = 0; i < nm; ++i) {
+    double fd0 = edges[i + 1] - edges[i], fd1 = edges[i + 2] - edges[i + 1];
+    double enorm = 2.0 / (edges[i + 2] - edges[i]);
+    int first = -1, last = -1;
+    for (int k = 0; k < nb; ++k) {
+      double lower = -(edges[i] - binhz[k]) / fd0;
+      double upper = (edges[i + 2] - binhz[k]) / fd1;
+      double w = std::max(0.0, std::min(lower, upper)) * enorm;
+      fe->h_mel[(size_t)i * nb + k] = w;
+      if (w > 0.0) { if (first < 0) first = k; last = k; }
+    }
+    mstart[i] = first < 0 ? 0 : first;
+    mcnt[i] = first < 0 ? 0 : last - first + 1;
+    moff[i] = (int)mw.size();
+    for (int k = 0; k < mcnt[i]; ++k) mw.push_back((float)fe->h_mel[(size_t)i * nb + mstart[i] + k]);
+  }
+  fe->mel_nnz = (int)mw.size();
+  // DCT-II orthonormal rows (signal.py:682-733)
+  const int nc1 = fe->n_c1;
+  fe->h_dct.assign((size_t)std::max(1, nc1) * nm, 0.0);
+  std::vector<float> dct32((size_t)std::max(1, nc1) * nm, 0.f);
+  for (int i = 0; i < nc1; ++i)
+    for (int k = 0; k < nm; ++k) {
+      double v = i == 0 ? 1.0 / sqrt((double)nm)
+                        : cos((double)i * (double)(2 * k + 1) * M_PI / (2.0 * nm)) * sqrt(2.0 / nm);
+      fe->h_dct[(size_t)i * nm + k] = v;
+      dct32[(size_t)i * nm + k] = (float)v;
+    }
+  // delta taps (signal.py:1041-1045): (h, h-1, ..., -h) / sum m^2
+  const int W = c.delta_width, h = W / 2;
+  double norm = 0.0;
+  for (int m = -h; m <= h; ++m) norm += (double)m * m;
+  std::vector<float> taps(W);
+  for (int k = 0; k < W; ++k) taps[k] = (float)((double)(h - k) / norm);
+
+  int rc;
+  if ((rc = upload(&fe->d_win32, win32))) return rc;
+  if ((rc = upload(&fe->d_win64, fe->h_win))) return rc;
+  if ((rc = upload(&fe->d_tw, tw))) return rc;
+  if ((rc = upload(&fe->d_mel_start, mstart))) return rc;
+  if ((rc = upload(&fe->d_mel_cnt, mcnt))) return rc;
+  if ((rc = upload(&fe->d_mel_off, moff))) return rc;
+  if ((rc = upload(&fe->d_mel_w, mw))) return rc;
+  if ((rc = upload(&fe->d_dct, dct32))) return rc;
+  if ((rc = upload(&fe->d_taps, taps))) return rc;
+  return ODIN_OK;
+}
+
+int fe_reserve(odin_fe* fe, int n_utt) {
+  if (n_utt <= fe->cap_utt) return ODIN_OK;
+  int cap = n_utt + n_utt / 4 + 16;
+  auto freeall = [&]() {
+    if (fe->h_stage) cudaFreeHost(fe->h_stage);
+    cudaFree(fe->d_sample_off); cudaFree(fe->d_frame_off); cudaFree(fe->d_tile_off); cudaFree(fe->d_tile2_off);
+    cudaFree(fe->d_dcsum); cudaFree(fe->d_umax); cudaFree(fe->d_cnt);
+    fe->h_stage = nullptr;
+    fe->d_sample_off = fe->d_frame_off = fe->d_tile_off = fe->d_tile2_off = fe->d_cnt = nullptr;
+    fe->d_dcsum = nullptr; fe->d_umax = nullptr; fe->cap_utt = 0;
+  };
+  freeall();
+  size_t n1 = (size_t)cap + 1;
+  ODIN_CUDA_CHECK(cudaMallocHost(&fe->h_stage, 4 * n1 * sizeof(int64_t)));
+  ODIN_CUDA_CHECK(cudaMalloc(&fe->d_sample_off, 4 * n1 * sizeof(int64_t)));
+  fe->d_frame_off = fe->d_sample_off + n1;
+  fe->d_tile_off = fe->d_frame_off + n1;
+  fe->d_tile2_off = fe->d_tile_off + n1;
+  ODIN_CUDA_CHECK(cudaMalloc(&fe->d_dcsum, n1 * sizeof(double)));
+  ODIN_CUDA_CHECK(cudaMalloc(&fe->d_umax, n1 * sizeof(int)));
+  ODIN_CUDA_CHECK(cudaMalloc(&fe->d_cnt, n1 * sizeof(int64_t)));
+  fe->cap_utt = cap;
+  return ODIN_OK;
+}
+
+static int check_fe_config(const odin_fe_config& c) {
+  if (c.sr <= 0 || c.frame_len <= 0 || c.hop <= 0) return set_error(ODIN_EINVAL, "sr/frame_len/hop must be > 0");
+  if (c.n_fft != 256 && c.n_fft != 512 && c.n_fft != 1024 && c.n_fft != 2048)
+    return set_error(ODIN_EINVAL, "n_fft must be 256, 512, 1024 or 2048 (got %d)", c.n_fft);
+  if (c.n_fft < c.frame_len)
+    return set_error(ODIN_EINVAL, "n_fft must be >= frame_len (signal.py:1523-1524)");
+  if (c.window != 0 && c.window != 1) return set_error(ODIN_EINVAL, "window must be 0 (hann) or 1 (hamming)");
+  if (c.n_mels <= 0 || c.n_mels > ODIN_FE_MAX_MELS) return set_error(ODIN_EINVAL, "n_mels must be in 1..128");
+  if (!(c.fmin < c.fmax)) return set_error(ODIN_EINVAL, "fmin must < fmax (signal.py:1680-1682)");
+  if (c.n_ceps < 0 || c.n_ceps + 1 > c.n_mels) return set_error(ODIN_EINVAL, "n_ceps must be in 0..n_mels-1");
+  if (c.delta_order < 0 || c.delta_order > 2) return set_error(ODIN_EINVAL, "delta_order must be 0, 1 or 2");
+  if (c.delta_width < 3 || (c.delta_width & 1) == 0 || c.delta_width > 31)
+    return set_error(ODIN_EINVAL, "delta_width must be an odd integer in 3..31 (signal.py:1034-1035)");
+  if (c.vad_kind < 0 || c.vad_kind > 2) return set_error(ODIN_EINVAL, "vad_kind must be 0, 1 or 2");
+  if (c.vad_kind == 1 && (c.vad_nmix < 2 || c.vad_nmix > 4)) return set_error(ODIN_EINVAL, "vad_nmix must be 2..4");
+  if (c.vad_kind == 2 && c.n_ceps <= 0) return set_error(ODIN_EINVAL, "SADthreshold runs on c0: needs n_ceps > 0");
+  return ODIN_OK;
+}
+
+}  // namespace odin
+
+using namespace odin;
+
+extern "C" {
+
+const char* odin_last_error(void) { return g_err.c_str(); }
+int odin_version(void) { return 1000 * 0 + 1; }
+int64_t odin_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------- front-end ---------------------------------
+int odin_fe_create(const odin_fe_config* cfg, odin_fe_t** out) {
+  if (!cfg || !out) return set_error(ODIN_EINVAL, "null argument");
+  *out = nullptr;
+  int rc = check_fe_config(*cfg);
+  if (rc) return rc;
+  if ((rc = require_device())) return rc;
+  odin_fe* fe = new (std::nothrow) odin_fe();
+  if (!fe) return set_error(ODIN_ENOMEM, "out of host memory");
+  fe->cfg = *cfg;
+  fe->L = cfg->frame_len; fe->hop = cfg->hop; fe->N = cfg->n_fft; fe->nbins = cfg->n_fft / 2 + 1;
+  fe->n_mels = cfg->n_mels;
+  fe->n_c1 = cfg->n_ceps > 0 ? cfg->n_ceps + 1 : 0;
+  fe->feat_dim = cfg->n_ceps * (1 + cfg->delta_order);
+  rc = fe_build_tables(fe);
+  if (rc) { odin_fe_destroy(fe); return rc; }
+  *out = fe;
+  return ODIN_OK;
+}
+
+void odin_fe_destroy(odin_fe_t* fe) {
+  if (!fe) return;
+  cudaFree(fe->d_win32); cudaFree(fe->d_win64); cudaFree(fe->d_tw); cudaFree(fe->d_mel_start);
+  cudaFree(fe->d_mel_cnt); cudaFree(fe->d_mel_off); cudaFree(fe->d_mel_w); cudaFree(fe->d_dct);
+  cudaFree(fe->d_taps); cudaFree(fe->d_sample_off); cudaFree(fe->d_dcsum); cudaFree(fe->d_umax);
+  cudaFree(fe->d_cnt); cudaFree(fe->d_vad_scratch);
+  if (fe->h_stage) cudaFreeHost(fe->h_stage);
+  delete fe;
+}
+
+int odin_fe_feat_dim(const odin_fe_t* fe) { return fe ? fe->feat_dim : ODIN_EINVAL; }
+
+static int frame_offsets_impl(int L, int hop, const int64_t* so, int n_utt, int64_t* fo) {
+  int rc = ODIN_OK;
+  fo[0] = 0;
+  for (int u = 0; u < n_utt; ++u) {
+    int64_t n = so[u + 1] - so[u];
+    int64_t T = n < L ? 0 : 1 + (n - L) / hop;  // signal.py:1532-1538
+    if (n < L) rc = ODIN_ESHORT;
+    fo[u + 1] = fo[u] + T;
+  }
+  return rc;
+}
+
+int odin_fe_frame_offsets(const odin_fe_t* fe, const int64_t* h_sample_offsets, int32_t n_utt,
+                          int64_t* h_frame_offsets) {
+  if (!fe || !h_sample_offsets || !h_frame_offsets || n_utt < 0) return set_error(ODIN_EINVAL, "bad argument");
+  int rc = frame_offsets_impl(fe->L, fe->hop, h_sample_offsets, n_utt, h_frame_offsets);
+  if (rc == ODIN_ESHORT) set_error(rc, "an utterance is shorter than one frame (%d samples)", fe->L);
+  return rc;
+}
+
+int odin_host_frame_offsets(int32_t frame_len, int32_t hop, const int64_t* h_sample_offsets, int32_t n_utt,
+                            int64_t* h_frame_offsets) {
+  if (frame_len <= 0 || hop <= 0 || !h_sample_offsets || !h_frame_offsets || n_utt < 0)
+    return set_error(ODIN_EINVAL, "bad argument");
+  int rc = frame_offsets_impl(frame_len, hop, h_sample_offsets, n_utt, h_frame_offsets);
+  if (rc == ODIN_ESHORT) set_error(rc, "an utterance is shorter than one frame (%d samples)", frame_len);
+  return rc;
+}
+
+int odin_host_smooth(const uint8_t* x, int32_t n, int32_t win, int32_t wrap_u8, uint8_t* out) {
+  if (!x || !out || n < 0) return set_error(ODIN_EINVAL, "bad argument");
+  if (win < 3 || n < win) { for (int i = 0; i < n; ++i) out[i] = x[i]; return ODIN_OK; }
+  auto get = [x](int i) -> int { return x[i] ? 1 : 0; };
+  for (int t = 0; t < n; ++t) out[t] = (uint8_t)smooth_flat_ge_f(get, n, win, wrap_u8 != 0, t);
+  return ODIN_OK;
+}
+
+// numpy-exact float32 mean/std (signal.py:305), exposed for the CPU tests
+int odin_host_mean_std_f32(const float* e, int32_t n, float* mean, float* std_) {
+  if (!e || n <= 0 || !mean || !std_) return set_error(ODIN_EINVAL, "bad argument");
+  MeanStdF32 r = np_mean_std_f32(e, n);
+  *mean = r.mean;
+  *std_ = r.std;
+  return ODIN_OK;
+}
+
+// dense fp64 tables as built for the device (tests compare them with the oracle)
+int odin_fe_get_table(const odin_fe_t* fe, int32_t which, double* out, int64_t cap) {
+  if (!fe || !out) return set_error(ODIN_EINVAL, "bad argument");
+  const std::vector<double>* v = which == 0 ? &fe->h_win : which == 1 ? &fe->h_mel : which == 2 ? &fe->h_dct : nullptr;
+  if (!v) return set_error(ODIN_EINVAL, "which must be 0 (window), 1 (mel), 2 (dct)");
+  if ((int64_t)v->size() > cap) return set_error(ODIN_EINVAL, "buffer too small: need %zu", v->size());
+  memcpy(out, v->data(), v->size() * sizeof(double));
+  return (int)v->size();
+}
+
+int odin_fe_run(odin_fe_t* fe, const void* d_pcm, int32_t pcm_dtype, const int64_t* h_sample_offsets,
+                int32_t n_utt, float* d_mspec, float* d_feat, float* d_energy, float* d_c0, uint8_t* d_sad,
+                double* d_sad_thr, void* stream) {
+  if (!fe || !d_pcm || !h_sample_offsets || n_utt < 0) return set_error(ODIN_EINVAL, "bad argument");
+  if (pcm_dtype != 0 && pcm_dtype != 1) return set_error(ODIN_EINVAL, "pcm_dtype must be 0 (int16) or 1 (float32)");
+  if (!d_mspec) return set_error(ODIN_EINVAL, "d_mspec is required (scratch for the utterance pass)");
+  if (n_utt == 0) return ODIN_OK;
+  int rc = fe_reserve(fe, n_utt);
+  if (rc) return rc;
+  cudaStream_t st = as_stream(stream);
+  const size_t n1 = (size_t)fe->cap_utt + 1;
+  int64_t* so = fe->h_stage;
+  int64_t* fo = so + n1;
+  int64_t* t1 = fo + n1;
+  int64_t* t2 = t1 + n1;
+  // the pinned staging block may still be in flight from the previous call on this stream
+  ODIN_CUDA_CHECK(cudaStreamSynchronize(st));
+  memcpy(so, h_sample_offsets, sizeof(int64_t) * (n_utt + 1));
+  rc = frame_offsets_impl(fe->L, fe->hop, so, n_utt, fo);
+  if (rc == ODIN_ESHORT) return set_error(rc, "an utterance is shorter than one frame (%d samples)", fe->L);
+  t1[0] = t2[0] = 0;
+  for (int u = 0; u < n_utt; ++u) {
+    int64_t T = fo[u + 1] - fo[u];
+    t1[u + 1] = t1[u] + ceil_div<int64_t>(T, ODIN_FE_TILE);
+    t2[u + 1] = t2[u] + ceil_div<int64_t>(T, ODIN_FE_POST_TILE);
+  }
+  if (t1[n_utt] > 0x7fffffff) return set_error(ODIN_EINVAL, "batch too large (tiles)");
+  ODIN_CUDA_CHECK(cudaMemcpyAsync(fe->d_sample_off, fe->h_stage, 4 * n1 * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  return fe_launch(fe, d_pcm, pcm_dtype, n_utt, fo[n_utt], t1[n_utt], t2[n_utt], d_mspec, d_feat, d_energy, d_c0,
+                   d_sad, d_sad_thr, st);
+}
+
+int odin_fe_compact(odin_fe_t* fe, const uint8_t* d_sad, const int64_t* h_frame_offsets, int32_t n_utt,
+                    const float* d_feat, int32_t dim, int32_t keep_unvoiced, float* d_out, int64_t* d_out_offsets,
+                    void* stream) {
+  if (!fe || !d_sad || !h_frame_offsets || !d_feat || !d_out || !d_out_offsets || dim <= 0 || n_utt < 0)
+    return set_error(ODIN_EINVAL, "bad argument");
+  if (n_utt == 0) return ODIN_OK;
+  int rc = fe_reserve(fe, n_utt);
+  if (rc) return rc;
+  cudaStream_t st = as_stream(stream);
+  const size_t n1 = (size_t)fe->cap_utt + 1;
+  ODIN_CUDA_CHECK(cudaStreamSynchronize(st));
+  memcpy(fe->h_stage + n1, h_frame_offsets, sizeof(int64_t) * (n_utt + 1));
+  ODIN_CUDA_CHECK(cudaMemcpyAsync(fe->d_frame_off, fe->h_stage + n1, sizeof(int64_t) * (n_utt + 1),
+                                  cudaMemcpyHostToDevice, st));
+  return fe_compact_launch(fe, d_sad, n_utt, d_feat, dim, keep_unvoiced, d_out, d_out_offsets, st);
+}
+
+// --------------------------------- GMM --------------------------------------
+int odin_gmm_create(int32_t feat_dim, int32_t max_nmix, odin_gmm_t** out) {
+  if (!out || feat_dim <= 0 || feat_dim > 127 || max_nmix <= 0 || max_nmix > 65536)
+    return set_error(ODIN_EINVAL, "feat_dim must be 1..127 and max_nmix 1..65536");
+  *out = nullptr;
+  int rc = require_device();
+  if (rc) return rc;
+  odin_gmm* g = new (std::nothrow) odin_gmm();
+  if (!g) return set_error(ODIN_ENOMEM, "out of host memory");
+  g->D = feat_dim;
+  g->max_nmix = max_nmix;
+  cudaGetDevice(&g->device);
+  const size_t maxpad = (size_t)ceil_div(max_nmix, 128) * 128;
+  const size_t dm = (size_t)feat_dim * max_nmix;
+  auto fail = [&](cudaError_t e) {
+    odin_gmm_destroy(g);
+    return set_error(ODIN_ECUDA, "cudaMalloc: %s", cudaGetErrorString(e));
+  };
+  cudaError_t e;
+  if ((e = cudaMalloc(&g->d_mean, dm * sizeof(float))) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&g->d_var, dm * sizeof(float))) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&g->d_w, max_nmix * sizeof(float))) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&g->d_Wk, 2 * (size_t)feat_dim * maxpad * sizeof(float))) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&g->d_cst, maxpad * sizeof(float))) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&g->d_Whi, maxpad * 128 * sizeof(float))) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&g->d_Wlo, maxpad * 128 * sizeof(float))) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&g->d_prev, (2 * dm + max_nmix) * sizeof(float))) != cudaSuccess) return fail(e);
+  *out = g;
+  return ODIN_OK;
+}
+
+void odin_gmm_destroy(odin_gmm_t* g) {
+  if (!g) return;
+  cudaFree(g->d_mean); cudaFree(g->d_var); cudaFree(g->d_w); cudaFree(g->d_Wk); cudaFree(g->d_cst);
+  cudaFree(g->d_Whi); cudaFree(g->d_Wlo); cudaFree(g->d_lse); cudaFree(g->d_prev); cudaFree(g->d_off);
+  if (g->h_off) cudaFreeHost(g->h_off);
+  delete g;
+}
+
+int64_t odin_gmm_stats_size(const odin_gmm_t* g, int32_t nmix) {
+  if (!g || nmix <= 0) return ODIN_EINVAL;
+  return stats_size(g->D, nmix);
+}
+
+int odin_gmm_set_params(odin_gmm_t* g, int32_t nmix, const float* d_mean, const float* d_var, const float* d_w,
+                        void* stream) {
+  if (!g || !d_mean || !d_var || !d_w) return set_error(ODIN_EINVAL, "null argument");
+  if (nmix <= 0 || nmix > g->max_nmix) return set_error(ODIN_EINVAL, "nmix %d outside 1..%d", nmix, g->max_nmix);
+  cudaStream_t st = as_stream(stream);
+  g->M = nmix;
+  g->Mpad = ceil_div(nmix, 128) * 128;
+  const size_t dm = (size_t)g->D * nmix;
+  ODIN_CUDA_CHECK(cudaMemcpyAsync(g->d_mean, d_mean, dm * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  ODIN_CUDA_CHECK(cudaMemcpyAsync(g->d_var, d_var, dm * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  ODIN_CUDA_CHECK(cudaMemcpyAsync(g->d_w, d_w, nmix * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return gmm_refresh_constants(g, st);
+}
+
+static int pick_impl(odin_gmm* g, int impl, bool* use_tc) {
+  if (impl < 0 || impl > 2) return set_error(ODIN_EINVAL, "impl must be 0 (auto), 1 (fp32) or 2 (tcgen05)");
+  bool ok = gmm_tc_supported(g);
+  if (impl == 2 && !ok) return set_error(ODIN_EINVAL, "tcgen05 path unsupported for D=%d M=%d", g->D, g->M);
+  *use_tc = (impl == 2) || (impl == 0 && ok);
+  return ODIN_OK;
+}
+
+int odin_gmm_estep(odin_gmm_t* g, const float* d_X, const uint8_t* d_sad, int64_t n_frames, int32_t want_second,
+                   double* d_stats, int32_t impl, void* stream) {
+  if (!g || !d_X || !d_stats || n_frames < 0) return set_error(ODIN_EINVAL, "bad argument");
+  if (g->M <= 0) return set_error(ODIN_EINVAL, "odin_gmm_set_params has not been called");
+  if (n_frames == 0) return ODIN_OK;
+  bool tc;
+  int rc = pick_impl(g, impl, &tc);
+  if (rc) return rc;
+  cudaStream_t st = as_stream(stream);
+  if ((rc = gmm_reserve_lse(g, n_frames))) return rc;
+  if (tc) {
+    if ((rc = gmm_lse_tc(g, d_X, d_sad, n_frames, g->d_lse, d_stats, st))) return rc;
+    return gmm_stats_tc(g, d_X, d_sad, n_frames, g->d_lse, want_second, d_stats, st);
+  }
+  if ((rc = gmm_lse_ffma(g, d_X, d_sad, n_frames, g->d_lse, d_stats, st))) return rc;
+  return gmm_stats_ffma(g, d_X, d_sad, n_frames, g->d_lse, want_second, d_stats, st);
+}
+
+int odin_gmm_mstep(odin_gmm_t* g, const double* d_stats, int32_t allow_rollback, float* d_mean, float* d_var,
+                   float* d_w, int32_t* d_rolled_back, void* stream) {
+  if (!g || !d_stats) return set_error(ODIN_EINVAL, "null argument");
+  if (g->M <= 0) return set_error(ODIN_EINVAL, "odin_gmm_set_params has not been called");
+  cudaStream_t st = as_stream(stream);
+  int rc = gmm_mstep_launch(g, d_stats, allow_rollback, d_rolled_back, st);
+  if (rc) return rc;
+  const size_t dm = (size_t)g->D * g->M;
+  if (d_mean) ODIN_CUDA_CHECK(cudaMemcpyAsync(d_mean, g->d_mean, dm * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (d_var) ODIN_CUDA_CHECK(cudaMemcpyAsync(d_var, g->d_var, dm * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (d_w) ODIN_CUDA_CHECK(cudaMemcpyAsync(d_w, g->d_w, g->M * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return gmm_refresh_constants(g, st);
+}
+
+int odin_gmm_mixup(odin_gmm_t* g, int32_t new_nmix, float* d_mean, float* d_var, float* d_w, void* stream) {
+  if (!g) return set_error(ODIN_EINVAL, "null argument");
+  if (g->M <= 0) return set_error(ODIN_EINVAL, "odin_gmm_set_params has not been called");
+  if (new_nmix <= g->M || new_nmix > 2 * g->M || new_nmix > g->max_nmix)
+    return set_error(ODIN_EINVAL, "new_nmix %d must be in (%d, min(%d, %d)]", new_nmix, g->M, 2 * g->M, g->max_nmix);
+  cudaStream_t st = as_stream(stream);
+  int rc = gmm_mixup_launch(g, new_nmix, st);
+  if (rc) return rc;
+  g->M = new_nmix;
+  g->Mpad = ceil_div(new_nmix, 128) * 128;
+  const size_t dm = (size_t)g->D * g->M;
+  if (d_mean) ODIN_CUDA_CHECK(cudaMemcpyAsync(d_mean, g->d_mean, dm * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (d_var) ODIN_CUDA_CHECK(cudaMemcpyAsync(d_var, g->d_var, dm * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (d_w) ODIN_CUDA_CHECK(cudaMemcpyAsync(d_w, g->d_w, g->M * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return gmm_refresh_constants(g, st);
+}
+
+int odin_gmm_utt_stats(odin_gmm_t* g, const float* d_X, const uint8_t* d_sad, const int64_t* h_frame_offsets,
+                       int32_t n_utt, float* d_Z, float* d_Fhat, int32_t impl, void* stream) {
+  if (!g || !d_X || !h_frame_offsets || !d_Z || !d_Fhat || n_utt < 0) return set_error(ODIN_EINVAL, "bad argument");
+  if (g->M <= 0) return set_error(ODIN_EINVAL, "odin_gmm_set_params has not been called");
+  if (n_utt == 0) return ODIN_OK;
+  (void)impl;  // per-utterance statistics run on the fp32 kernels in this version
+  cudaStream_t st = as_stream(stream);
+  if (g->off_cap < n_utt + 1) {
+    if (g->h_off) cudaFreeHost(g->h_off);
+    cudaFree(g->d_off);
+    g->h_off = nullptr; g->d_off = nullptr; g->off_cap = 0;
+    int64_t cap = n_utt + n_utt / 4 + 16;
+    ODIN_CUDA_CHECK(cudaMallocHost(&g->h_off, cap * sizeof(int64_t)));
+    ODIN_CUDA_CHECK(cudaMalloc(&g->d_off, cap * sizeof(int64_t)));
+    g->off_cap = cap;
+  }
+  ODIN_CUDA_CHECK(cudaStreamSynchronize(st));
+  const int64_t f_lo = h_frame_offsets[0], f_hi = h_frame_offsets[n_utt];
+  for (int u = 0; u <= n_utt; ++u) g->h_off[u] = h_frame_offsets[u] - f_lo;
+  ODIN_CUDA_CHECK(cudaMemcpyAsync(g->d_off, g->h_off, (n_utt + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  const int64_t N = f_hi - f_lo;
+  int rc = gmm_reserve_lse(g, N);
+  if (rc) return rc;
+  const float* X = d_X + f_lo * g->D;
+  const uint8_t* sad = d_sad ? d_sad + f_lo : nullptr;
+  if ((rc = gmm_lse_ffma(g, X, sad, N, g->d_lse, nullptr, st))) return rc;
+  return gmm_utt_stats_ffma(g, X, sad, g->d_off, n_utt, g->d_lse, d_Z, d_Fhat, st);
+}
+
+int odin_gmm_score(odin_gmm_t* g, const float* d_X, int64_t n_frames, float* d_llk, float* d_post,
+                   float* d_logprob, void* stream) {
+  if (!g || !d_X || !d_llk || n_frames < 0) return set_error(ODIN_EINVAL, "bad argument");
+  if (g->M <= 0) return set_error(ODIN_EINVAL, "odin_gmm_set_params has not been called");
+  cudaStream_t st = as_stream(stream);
+  int rc = gmm_lse_ffma(g, d_X, nullptr, n_frames, d_llk, nullptr, st);
+  if (rc) return rc;
+  if (d_post || d_logprob) return gmm_post_ffma(g, d_X, n_frames, d_llk, d_post, d_logprob, st);
+  return ODIN_OK;
+}
+
+}  // extern "C"

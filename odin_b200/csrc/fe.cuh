@@ -1,0 +1,55 @@
+// Front-end handle: tables + per-run scratch.  Kernels live in fe_kernels.cu.
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+constexpr int ODIN_FE_TILE = 32;       // frames per CTA tile in the frame kernel
+constexpr int ODIN_FE_POST_TILE = 128; // frames per CTA tile in the utterance-pass kernel
+constexpr int ODIN_FE_MAX_MELS = 128;
+
+struct odin_fe {
+  odin_fe_config cfg;
+  int L = 0, hop = 0, N = 0, nbins = 0;
+  int n_mels = 0, n_c1 = 0 /* n_ceps+1 rows of the DCT */, feat_dim = 0;
+  float scale2 = 0.f;  // (1/sum w)^2  (signal.py:1547,1557-1558 applied to |S|^2)
+  // device tables
+  float* d_win32 = nullptr;    // [L]
+  double* d_win64 = nullptr;   // [L]
+  float2* d_tw = nullptr;      // [N] exp(-2 pi i k / N)
+  int* d_mel_start = nullptr;  // [n_mels] first bin with non-zero weight
+  int* d_mel_cnt = nullptr;    // [n_mels]
+  int* d_mel_off = nullptr;    // [n_mels] offset into d_mel_w
+  float* d_mel_w = nullptr;    // [nnz]
+  float* d_dct = nullptr;      // [n_c1, n_mels]
+  float* d_taps = nullptr;     // [delta_width]
+  int mel_nnz = 0;
+  // per-run scratch (capacity in utterances)
+  int cap_utt = 0;
+  int64_t* h_stage = nullptr;  // pinned [4*(cap+1)]: sample_off, frame_off, tile_off, tile2_off
+  int64_t* d_sample_off = nullptr;
+  int64_t* d_frame_off = nullptr;
+  int64_t* d_tile_off = nullptr;
+  int64_t* d_tile2_off = nullptr;
+  double* d_dcsum = nullptr;   // [cap] (int64 bit pattern for int16 input)
+  int* d_umax = nullptr;       // [cap] ordered-int encoded utterance max of log-mel dB
+  int64_t* d_cnt = nullptr;    // [cap+1] compaction counts / offsets
+  float* d_vad_scratch = nullptr;  // [frames] standardised energies
+  int64_t vad_scratch_cap = 0;
+  // host copies of the tables (tests, debugging)
+  std::vector<double> h_win;
+  std::vector<double> h_mel;   // dense [n_mels, nbins]
+  std::vector<double> h_dct;
+};
+
+namespace odin {
+
+int fe_build_tables(odin_fe* fe);           // host fp64 -> device
+int fe_reserve(odin_fe* fe, int n_utt);
+int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t total_frames,
+              int64_t n_tiles, int64_t n_tiles2, float* d_mspec, float* d_feat, float* d_energy,
+              float* d_c0, uint8_t* d_sad, double* d_sad_thr, cudaStream_t st);
+int fe_compact_launch(odin_fe* fe, const uint8_t* d_sad, int n_utt, const float* d_feat, int dim,
+                      int keep_unvoiced, float* d_out, int64_t* d_out_offsets, cudaStream_t st);
+
+}  // namespace odin

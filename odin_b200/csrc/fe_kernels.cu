@@ -1,0 +1,865 @@
+// Speech front-end kernels for sm_100a.
+//
+// Reference arithmetic (trungnt13/odin-ai, file:line):
+//   DC removal               odin/preprocessing/speech.py:453,472-473
+//   pre-emphasis             odin/preprocessing/signal.py:955-967
+//   framing/window/energy    signal.py:1442-1562, 1421-1440
+//   |rfft|^2 * scale^2       signal.py:1555-1558, 1623-1648
+//   mel filterbank + dB      signal.py:735-810, 1650-1691, 636-680
+//   DCT -> MFCC, c0          signal.py:682-733, 1693-1716; speech.py:821-831
+//   deltas                   signal.py:1002-1066; base.py:470-481
+//   SADgmm                   signal.py:293-331; speech.py:1459-1477
+//   SADthreshold             speech.py:1299-1324, 1415-1436
+//   ApplyingSAD              speech.py:1732-1756
+//
+// Kernel plan (one ragged batch of utterances per call):
+//   fe_dc_kernel     per-utterance sample sums (exact int64 for int16 PCM)
+//   fe_frame_kernel  one CTA per tile of 32 consecutive frames of ONE utterance:
+//                    PCM -> smem (DC removal + pre-emphasis fused into the
+//                    staging copy), then one warp per PAIR of frames: the two
+//                    real frames are packed as re/im of one complex n_fft-point
+//                    Stockham FFT held in shared memory (radix 8/16 butterflies
+//                    in registers, window multiply and the fp64 frame energy
+//                    fused into the first pass), spectra are split by symmetry,
+//                    |.|^2, sparse mel triangles, 10 log10 -> unclipped log-mel
+//                    rows + an atomic per-utterance max.  Spectra never touch HBM.
+//   fe_post_kernel   utterance pass: utterance-global top_db clip, DCT, c0,
+//                    delta / delta-delta with the reference's edge/latency quirks.
+//   fe_vad_*_kernel  one warp per utterance: standardise (numpy-exact float32
+//                    mean/std), 1-D EM in fp64, threshold, smoothing.
+//   fe_compact_*     ApplyingSAD row compaction.
+#include <float.h>
+#include <math.h>
+
+#include "fe.cuh"
+#include "fe_logic.cuh"
+
+namespace odin {
+
+constexpr int FT = ODIN_FE_TILE;
+constexpr int PT = ODIN_FE_POST_TILE;
+constexpr int FE_WARPS = 8;
+constexpr int FE_THREADS = FE_WARPS * 32;
+
+// ---------------------------------------------------------------------------
+// small complex helpers
+// ---------------------------------------------------------------------------
+template <typename T> struct C2 { T x, y; };
+template <typename T> __device__ __forceinline__ C2<T> cadd(C2<T> a, C2<T> b) { return {a.x + b.x, a.y + b.y}; }
+template <typename T> __device__ __forceinline__ C2<T> csub(C2<T> a, C2<T> b) { return {a.x - b.x, a.y - b.y}; }
+template <typename T> __device__ __forceinline__ C2<T> cmul(C2<T> a, C2<T> b) {
+  return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
+}
+template <typename T> __device__ __forceinline__ C2<T> cmul_negi(C2<T> a) { return {a.y, -a.x}; }  // a * (-i)
+
+// W_16^q = exp(-2 pi i q / 16), q = 0..7
+__device__ __forceinline__ constexpr double w16c(int q) {
+  return q == 0 ? 1.0 : q == 1 ? 0.92387953251128673848 : q == 2 ? 0.70710678118654752440
+       : q == 3 ? 0.38268343236508977173 : q == 4 ? 0.0 : q == 5 ? -0.38268343236508977173
+       : q == 6 ? -0.70710678118654752440 : -0.92387953251128673848;
+}
+__device__ __forceinline__ constexpr double w16s(int q) {  // -sin(2 pi q / 16)
+  return q == 0 ? 0.0 : q == 1 ? -0.38268343236508977173 : q == 2 ? -0.70710678118654752440
+       : q == 3 ? -0.92387953251128673848 : q == 4 ? -1.0 : q == 5 ? -0.92387953251128673848
+       : q == 6 ? -0.70710678118654752440 : -0.38268343236508977173;
+}
+
+// in-register forward DFT of size R (power of two <= 16), natural order in/out
+template <int R, typename T> struct Dft {
+  static __device__ __forceinline__ void run(C2<T> (&v)[R]) {
+    C2<T> e[R / 2], o[R / 2];
+#pragma unroll
+    for (int q = 0; q < R / 2; ++q) { e[q] = v[2 * q]; o[q] = v[2 * q + 1]; }
+    Dft<R / 2, T>::run(e);
+    Dft<R / 2, T>::run(o);
+#pragma unroll
+    for (int q = 0; q < R / 2; ++q) {
+      C2<T> t;
+      if (q == 0) t = o[q];
+      else if (4 * q == R) t = cmul_negi(o[q]);
+      else t = cmul(o[q], C2<T>{(T)w16c(q * (16 / R)), (T)w16s(q * (16 / R))});
+      v[q] = cadd(e[q], t);
+      v[q + R / 2] = csub(e[q], t);
+    }
+  }
+};
+template <typename T> struct Dft<1, T> {
+  static __device__ __forceinline__ void run(C2<T> (&)[1]) {}
+};
+
+template <int N> struct FftPlan;
+template <> struct FftPlan<256> { static constexpr int R0 = 8, R1 = 8, R2 = 4; };
+template <> struct FftPlan<512> { static constexpr int R0 = 8, R1 = 8, R2 = 8; };
+template <> struct FftPlan<1024> { static constexpr int R0 = 16, R1 = 8, R2 = 8; };
+template <> struct FftPlan<2048> { static constexpr int R0 = 16, R1 = 16, R2 = 8; };
+
+// one float2/double2 of padding every 16 elements keeps the strided Stockham
+// stores spread over the banks
+__device__ __forceinline__ int padi(int i) { return i + (i >> 4); }
+template <int N> constexpr int padded_len() { return N + (N >> 4) + 1; }
+
+// Stockham pass of radix R over a warp-private buffer, in place: every lane pulls
+// all of its butterfly inputs into registers, the warp syncs, results are written
+// back to the auto-sorted positions.  NS = product of the radices of earlier passes.
+template <int N, int R, int NS, typename T>
+__device__ __forceinline__ void fft_pass(C2<T>* buf, const C2<T>* __restrict__ tw, int lane) {
+  constexpr int NB = N / (32 * R);
+  C2<T> v[NB][R];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const int j = lane + 32 * b;
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[b][r] = buf[padi(j + r * (N / R))];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const int j = lane + 32 * b;
+    const int k = j % NS;
+    if (NS > 1) {
+      constexpr int stride = N / (NS * R);
+#pragma unroll
+      for (int r = 1; r < R; ++r) v[b][r] = cmul(v[b][r], tw[r * k * stride]);
+    }
+    Dft<R, T>::run(v[b]);
+    const int base = (j / NS) * (NS * R) + k;
+#pragma unroll
+    for (int r = 0; r < R; ++r) buf[padi(base + r * NS)] = v[b][r];
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------
+// fe_dc_kernel: per-utterance sums for the DC removal
+// ---------------------------------------------------------------------------
+constexpr int DC_CHUNK = 16384;
+
+template <typename PCM>
+__global__ void __launch_bounds__(256)
+fe_dc_kernel(const PCM* __restrict__ pcm, const int64_t* __restrict__ sample_off, int n_utt, int max_chunks,
+             double* __restrict__ dcsum) {
+  const int u = blockIdx.x / max_chunks, c = blockIdx.x % max_chunks;
+  if (u >= n_utt) return;
+  const int64_t s0 = sample_off[u], n = sample_off[u + 1] - s0;
+  const int64_t lo = (int64_t)c * DC_CHUNK;
+  if (lo >= n) return;
+  const int cnt = (int)min((int64_t)DC_CHUNK, n - lo);
+  const PCM* p = pcm + s0 + lo;
+  __shared__ double red[8];
+  if (sizeof(PCM) == 2) {
+    long long acc = 0;
+    for (int i = threadIdx.x; i < cnt; i += 256) acc += (long long)p[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __shared__ long long redi[8];
+    if ((threadIdx.x & 31) == 0) redi[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      long long t = 0;
+      for (int i = 0; i < 8; ++i) t += redi[i];
+      atomicAdd(reinterpret_cast<unsigned long long*>(dcsum) + u, (unsigned long long)t);
+    }
+  } else {
+    double acc = 0;
+    for (int i = threadIdx.x; i < cnt; i += 256) acc += (double)p[i];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0;
+      for (int i = 0; i < 8; ++i) t += red[i];
+      atomicAdd(dcsum + u, t);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// fe_frame_kernel
+// ---------------------------------------------------------------------------
+struct FrameArgs {
+  const void* pcm;
+  const int64_t* sample_off;
+  const int64_t* frame_off;
+  const int64_t* tile_off;
+  int n_utt;
+  int64_t n_tiles;
+  const double* dcsum;
+  int L, hop, remove_dc;
+  float preemph;
+  const float* win32;
+  const double* win64;
+  const void* tw;  // C2<T>[N]
+  const int* mel_start;
+  const int* mel_cnt;
+  const int* mel_off;
+  const float* mel_w;
+  int n_mels;
+  float scale2;
+  float* mspec;   // [T, n_mels] unclipped dB
+  float* energy;  // [T] nullable
+  int* umax;      // [n_utt]
+};
+
+__device__ __forceinline__ int find_segment(const int64_t* __restrict__ off, int n, int64_t v) {
+  // largest u in [0, n) with off[u] <= v   (off is non-decreasing, off[0] = 0)
+  int lo = 0, hi = n;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (off[mid] <= v) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+template <typename T> __device__ __forceinline__ T db10(T v);
+template <> __device__ __forceinline__ float db10<float>(float v) { return 10.f * log10f(fmaxf(v, 1e-10f)); }
+template <> __device__ __forceinline__ double db10<double>(double v) { return 10.0 * log10(fmax(v, 1e-10)); }
+
+template <int N, typename T, typename PCM>
+__global__ void __launch_bounds__(FE_THREADS) fe_frame_kernel(FrameArgs a) {
+  using P = FftPlan<N>;
+  constexpr int PL = padded_len<N>();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: win64 [L] | tw [N] | warp bufs [FE_WARPS][PL] | win32 [L] | sbuf [(FT-1)*hop + L]
+  double* win64 = reinterpret_cast<double*>(smem_raw);
+  C2<T>* tw = reinterpret_cast<C2<T>*>(win64 + a.L + (a.L & 1));
+  C2<T>* bufs = tw + N;
+  float* win32 = reinterpret_cast<float*>(bufs + FE_WARPS * PL);
+  float* sbuf = win32 + a.L;
+  __shared__ int cta_max;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int L = a.L, hop = a.hop;
+  for (int i = tid; i < L; i += FE_THREADS) { win64[i] = a.win64[i]; win32[i] = a.win32[i]; }
+  for (int i = tid; i < N; i += FE_THREADS) tw[i] = reinterpret_cast<const C2<T>*>(a.tw)[i];
+  C2<T>* buf = bufs + warp * PL;
+  const PCM* __restrict__ pcm = reinterpret_cast<const PCM*>(a.pcm);
+  const float coef = a.preemph;
+
+  for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    const int u = find_segment(a.tile_off, a.n_utt, tile);
+    const int64_t s0 = a.sample_off[u];
+    const int64_t n_u = a.sample_off[u + 1] - s0;
+    const int64_t fbase = a.frame_off[u];
+    const int T_u = (int)(a.frame_off[u + 1] - fbase);
+    const int t0 = (int)(tile - a.tile_off[u]) * FT;
+    const int nf = min(FT, T_u - t0);
+    float mean = 0.f;
+    if (a.remove_dc) {
+      double s = (sizeof(PCM) == 2) ? (double)reinterpret_cast<const long long*>(a.dcsum)[u] : a.dcsum[u];
+      mean = (float)(s / (double)n_u);
+    }
+    __syncthreads();  // previous tile done with sbuf / cta_max (and the table fill on the first trip)
+    if (tid == 0) cta_max = float_to_ordered(-FLT_MAX);
+    {
+      const int cnt = (nf - 1) * hop + L;
+      const int64_t g0 = (int64_t)t0 * hop;
+      const PCM* p = pcm + s0 + g0;
+      for (int i = tid; i < cnt; i += FE_THREADS) {
+        float cur = __fsub_rn((float)p[i], mean);
+        if (coef != 0.f && (g0 + i) > 0) {
+          float prev = __fsub_rn((float)p[i - 1], mean);
+          cur = __fsub_rn(cur, __fmul_rn(coef, prev));  // two roundings, like numpy (signal.py:965)
+        }
+        sbuf[i] = cur;
+      }
+    }
+    __syncthreads();
+
+    float wmax = -FLT_MAX;
+    for (int pair = warp; 2 * pair < nf; pair += FE_WARPS) {
+      const int fA = 2 * pair, fB = fA + 1;
+      const bool hasB = fB < nf;
+      const float* sA = sbuf + fA * hop;
+      const float* sB = sbuf + (hasB ? fB : fA) * hop;
+      // ---- pass 0 fused with windowing and the fp64 frame energy ----
+      {
+        constexpr int R = P::R0;
+        constexpr int NB = N / (32 * R);
+        double eA = 0.0, eB = 0.0;
+        C2<T> v[NB][R];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          const int j = lane + 32 * b;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const int i = j + r * (N / R);
+            C2<T> z = {(T)0, (T)0};
+            if (i < L) {
+              const float xa = sA[i], xb = hasB ? sB[i] : 0.f;
+              const double w = win64[i];
+              const double wa = w * (double)xa, wb = w * (double)xb;
+              eA = fma(wa, wa, eA);
+              eB = fma(wb, wb, eB);
+              if (sizeof(T) == 8) { z.x = (T)wa; z.y = (T)wb; }
+              else { const float wf = win32[i]; z.x = (T)(wf * xa); z.y = (T)(wf * xb); }
+            }
+            v[b][r] = z;
+          }
+        }
+        __syncwarp();  // previous pair's mel stage has finished reading buf
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          const int j = lane + 32 * b;
+          Dft<R, T>::run(v[b]);
+#pragma unroll
+          for (int r = 0; r < R; ++r) buf[padi(j * R + r)] = v[b][r];
+        }
+        __syncwarp();
+        if (a.energy != nullptr) {
+          eA = warp_sum(eA);
+          eB = warp_sum(eB);
+          if (lane == 0) {
+            if (eA == 0.0) eA = (double)FLT_EPSILON;  // signal.py:1436
+            a.energy[fbase + t0 + fA] = (float)log(eA);
+            if (hasB) {
+              if (eB == 0.0) eB = (double)FLT_EPSILON;
+              a.energy[fbase + t0 + fB] = (float)log(eB);
+            }
+          }
+        }
+      }
+      fft_pass<N, P::R1, P::R0, T>(buf, tw, lane);
+      fft_pass<N, P::R2, P::R0 * P::R1, T>(buf, tw, lane);
+      // ---- split the packed spectra: XA = (Z[k] + conj Z[N-k])/2, XB = (Z[k] - conj Z[N-k])/(2i) ----
+      constexpr int NK = (N / 2) / 32;  // bins per lane below N/2
+      T pa[NK + 1], pb[NK + 1];
+      const T q = (T)0.25 * (T)a.scale2;
+#pragma unroll
+      for (int i = 0; i < NK; ++i) {
+        const int k = lane + 32 * i;
+        const C2<T> z1 = buf[padi(k)], z2 = buf[padi((N - k) & (N - 1))];
+        const T ar = z1.x + z2.x, ai = z1.y - z2.y;
+        const T br = z1.y + z2.y, bi = z2.x - z1.x;
+        pa[i] = (ar * ar + ai * ai) * q;
+        pb[i] = (br * br + bi * bi) * q;
+      }
+      {
+        const C2<T> zn = buf[padi(N / 2)];
+        pa[NK] = (zn.x * zn.x) * (T)a.scale2;
+        pb[NK] = (zn.y * zn.y) * (T)a.scale2;
+      }
+      __syncwarp();
+      T* PA = reinterpret_cast<T*>(buf);
+      T* PB = PA + (N / 2 + 1);
+#pragma unroll
+      for (int i = 0; i < NK; ++i) { PA[lane + 32 * i] = pa[i]; PB[lane + 32 * i] = pb[i]; }
+      if (lane == 0) { PA[N / 2] = pa[NK]; PB[N / 2] = pb[NK]; }
+      __syncwarp();
+      // ---- sparse mel triangles, one filter per lane ----
+      for (int m = lane; m < a.n_mels; m += 32) {
+        const int st = a.mel_start[m], cn = a.mel_cnt[m];
+        const float* __restrict__ w = a.mel_w + a.mel_off[m];
+        T accA = 0, accB = 0;
+        for (int i = 0; i < cn; ++i) {
+          const T wi = (T)__ldg(w + i);
+          accA += wi * PA[st + i];
+          accB += wi * PB[st + i];
+        }
+        const float dA = (float)db10<T>(accA);
+        a.mspec[(fbase + t0 + fA) * a.n_mels + m] = dA;
+        wmax = fmaxf(wmax, dA);
+        if (hasB) {
+          const float dB = (float)db10<T>(accB);
+          a.mspec[(fbase + t0 + fB) * a.n_mels + m] = dB;
+          wmax = fmaxf(wmax, dB);
+        }
+      }
+    }
+    wmax = warp_max(wmax);
+    if (lane == 0) atomicMax(&cta_max, float_to_ordered(wmax));
+    __syncthreads();
+    if (tid == 0) atomicMax(a.umax + u, cta_max);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// fe_post_kernel: clip, DCT, deltas
+// ---------------------------------------------------------------------------
+struct PostArgs {
+  const int64_t* frame_off;
+  const int64_t* tile2_off;
+  int n_utt;
+  const int* umax;
+  float top_db;
+  int n_mels, n_c1, n_ceps, W, order;
+  const float* dct;   // [n_c1, n_mels]
+  const float* taps;  // [W]
+  float* mspec;       // in/out
+  int write_mspec;
+  float* feat;        // [T, n_ceps*(order+1)] nullable
+  float* c0;          // [T] nullable
+};
+
+__global__ void __launch_bounds__(256) fe_post_kernel(PostArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const int tid = threadIdx.x;
+  const int h = a.W / 2;
+  const int HL = (a.order >= 2) ? (a.W - 1 + h) : (a.order == 1 ? h : 0);
+  const int HR = (a.order >= 1) ? h : 0;
+  const int NR = PT + HL + HR;             // rows of mel / cepstra held
+  const int ND = PT + ((a.order >= 2) ? a.W - 1 : 0);  // rows of first-order deltas held
+  float* smel = sm;                         // [NR][n_mels]
+  float* scep = smel + NR * a.n_mels;       // [NR][n_c1]
+  float* sd1 = scep + NR * a.n_c1;          // [ND][n_ceps]
+  float* sdct = sd1 + ND * a.n_ceps;        // [n_c1][n_mels]
+  float* staps = sdct + a.n_c1 * a.n_mels;  // [W]
+
+  const int64_t tile = blockIdx.x;
+  const int u = find_segment(a.tile2_off, a.n_utt, tile);
+  const int64_t base = a.frame_off[u];
+  const int T = (int)(a.frame_off[u + 1] - base);
+  const int t0 = (int)(tile - a.tile2_off[u]) * PT;
+  const int nf = min(PT, T - t0);
+  const int lo = max(0, t0 - HL), hi = min(T, t0 + nf + HR);
+  const int nrows = hi - lo;
+  const float floor_db = (a.top_db >= 0.f) ? ordered_to_float(a.umax[u]) - a.top_db : -FLT_MAX;
+
+  for (int i = tid; i < a.n_c1 * a.n_mels; i += 256) sdct[i] = a.dct[i];
+  for (int i = tid; i < a.W; i += 256) staps[i] = a.taps[i];
+  for (int i = tid; i < nrows * a.n_mels; i += 256) {
+    const int r = i / a.n_mels;
+    const int64_t g = (base + lo) * a.n_mels + i;
+    float v = fmaxf(a.mspec[g], floor_db);
+    smel[i] = v;
+    const int t = lo + r;
+    if (a.write_mspec && t >= t0 && t < t0 + nf) a.mspec[g] = v;
+  }
+  __syncthreads();
+  if (a.n_ceps <= 0) return;
+  // DCT (signal.py:1711): cep[r][c] = sum_m dct[c][m] * mel[r][m]
+  for (int i = tid; i < nrows * a.n_c1; i += 256) {
+    const int r = i / a.n_c1, c = i - r * a.n_c1;
+    const float* mrow = smel + r * a.n_mels;
+    const float* drow = sdct + c * a.n_mels;
+    float acc = 0.f;
+    for (int m = 0; m < a.n_mels; ++m) acc = fmaf(drow[m], mrow[m], acc);
+    scep[i] = acc;
+    const int t = lo + r;
+    if (c == 0 && a.c0 != nullptr && t >= t0 && t < t0 + nf) a.c0[base + t] = acc;
+  }
+  __syncthreads();
+  if (a.feat == nullptr) return;
+  const int fd = a.n_ceps * (a.order + 1);
+  // first-order deltas D(u) for u in [ulo, t0+nf)
+  const int ulo = t0 - ((a.order >= 2) ? a.W - 1 : 0);
+  if (a.order >= 1) {
+    const int nd = t0 + nf - ulo;
+    for (int i = tid; i < nd * a.n_ceps; i += 256) {
+      const int r = i / a.n_ceps, c = i - r * a.n_ceps;
+      const int uu = ulo + r;
+      float acc = 0.f;
+      if (uu >= -(h + 1)) {
+        for (int k = 0; k < a.W; ++k) {
+          int t = min(max(uu + h - k, 0), T - 1);
+          acc = fmaf(staps[k], scep[(t - lo) * a.n_c1 + 1 + c], acc);
+        }
+      } else {  // zero initial state of the causal filter
+        const int j = uu + 2 * a.W - h - 1;
+        float ts = 0.f;
+        for (int k = 0; k <= j; ++k) ts += staps[k];
+        acc = ts * scep[(0 - lo) * a.n_c1 + 1 + c];
+      }
+      sd1[i] = acc;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < nf * fd; i += 256) {
+    const int r = i / fd, j = i - r * fd;
+    const int t = t0 + r;
+    const int o = j / a.n_ceps, c = j - o * a.n_ceps;
+    float v;
+    if (o == 0) {
+      v = scep[(t - lo) * a.n_c1 + 1 + c];
+    } else if (o == 1) {
+      v = sd1[(t - ulo) * a.n_ceps + c];
+    } else {
+      float acc = 0.f;
+      for (int k = 0; k < a.W; ++k) acc = fmaf(staps[k], sd1[(t - k - ulo) * a.n_ceps + c], acc);
+      v = acc;
+    }
+    a.feat[(base + t) * fd + j] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// VAD: one warp per utterance
+// ---------------------------------------------------------------------------
+struct VadArgs {
+  const int64_t* frame_off;
+  int n_utt;
+  const float* x;   // energy [T] (SADgmm) or c0 [T] (SADthreshold)
+  uint8_t* sad;     // [T]
+  double* thr_out;  // [n_utt] nullable
+  float* scratch;   // [T] standardised / normalised values
+  int nmix, iters, smooth;
+  double mode;
+  double thr_energy, thr_mean_scale, thr_proportion;
+  int thr_context;
+};
+
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+
+// 1-D EM of sklearn GaussianMixture with fixed inits (see oracle/frontend.py _em_1d).
+// Returns false where sklearn would raise ValueError.
+__device__ bool vad_em(const float* __restrict__ x, int n, int nc, int max_iter, int lane, double* mu_out,
+                       double* prec_out) {
+  constexpr int KMAX = 4;
+  if (n < max(nc, 2)) return false;
+  double w[KMAX], mu[KMAX], pch[KMAX];
+  for (int k = 0; k < nc; ++k) {
+    w[k] = 1.0 / nc;
+    mu[k] = -2.0 + 4.0 * k / (double)(nc - 1);
+    pch[k] = 1.0;
+  }
+  int bad = 0;
+  for (int i = lane; i < n; i += 32) if (!isfinite(x[i])) bad = 1;
+  if (__any_sync(0xffffffffu, bad)) return false;
+  const double LOG2PI = 1.8378770664093454835606594728112;
+  double lower = -INFINITY;
+  for (int it = 0; it < max_iter; ++it) {
+    double prec[KMAX], a0[KMAX], b0[KMAX], ld[KMAX], lw[KMAX];
+    for (int k = 0; k < nc; ++k) {
+      prec[k] = dmul(pch[k], pch[k]);
+      a0[k] = dmul(dmul(mu[k], mu[k]), prec[k]);
+      b0[k] = dmul(mu[k], prec[k]);
+      ld[k] = log(pch[k]);
+      lw[k] = log(w[k]);
+    }
+    double nk[KMAX] = {0, 0, 0, 0}, sx[KMAX] = {0, 0, 0, 0}, sxx[KMAX] = {0, 0, 0, 0}, lsum = 0.0;
+    for (int i = lane; i < n; i += 32) {
+      const float xf = x[i];
+      const double xd = (double)xf, x2 = (double)__fmul_rn(xf, xf);  // x*x is float32 in sklearn
+      double wl[KMAX], mx = -INFINITY;
+      for (int k = 0; k < nc; ++k) {
+        double lp = dadd(dadd(a0[k], -dmul(2.0, dmul(xd, b0[k]))), dmul(x2, prec[k]));
+        lp = dadd(dmul(-0.5, dadd(LOG2PI, lp)), ld[k]);
+        wl[k] = dadd(lp, lw[k]);
+        mx = fmax(mx, wl[k]);
+      }
+      double s = 0.0;
+      for (int k = 0; k < nc; ++k) s += exp(wl[k] - mx);
+      const double norm = mx + log(s);
+      lsum += norm;
+      for (int k = 0; k < nc; ++k) {
+        const double r = exp(wl[k] - norm);
+        nk[k] += r;
+        sx[k] = fma(r, xd, sx[k]);
+        sxx[k] = fma(r, x2, sxx[k]);
+      }
+    }
+    lsum = warp_sum(lsum);
+    double nksum = 0.0;
+    bool collapsed = false;
+    for (int k = 0; k < nc; ++k) {
+      nk[k] = warp_sum(nk[k]) + 10.0 * DBL_EPSILON;
+      sx[k] = warp_sum(sx[k]);
+      sxx[k] = warp_sum(sxx[k]);
+      nksum += nk[k];
+    }
+    for (int k = 0; k < nc; ++k) {
+      mu[k] = sx[k] / nk[k];
+      const double var = dadd(dadd(sxx[k] / nk[k], -dmul(mu[k], mu[k])), 1e-6);
+      if (!(var > 0.0)) collapsed = true;
+      pch[k] = 1.0 / sqrt(var);
+      w[k] = nk[k] / nksum;
+    }
+    if (collapsed) return false;
+    const double new_lower = lsum / (double)n;
+    const double change = new_lower - lower;
+    lower = new_lower;
+    if (fabs(change) < 1e-3) break;
+  }
+  for (int k = 0; k < nc; ++k) { mu_out[k] = mu[k]; prec_out[k] = dmul(pch[k], pch[k]); }
+  return true;
+}
+
+__global__ void __launch_bounds__(128) fe_vad_gmm_kernel(VadArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  for (int u = wid; u < a.n_utt; u += nw) {
+    const int64_t base = a.frame_off[u];
+    const int n = (int)(a.frame_off[u + 1] - base);
+    if (n <= 0) continue;
+    const float* e = a.x + base;
+    float* xs = a.scratch + base;
+    uint8_t* out = a.sad + base;
+    int nc = a.nmix;
+    bool ok = false;
+    double thr = 0.0;
+    const float* src = e;
+    while (true) {
+      // standardise in float32 exactly as numpy does (signal.py:305); the retry
+      // path of the reference re-standardises the already standardised vector
+      float mean = 0.f, sd = 0.f;
+      if (lane == 0) {
+        MeanStdF32 ms = np_mean_std_f32(src, n);
+        mean = ms.mean; sd = ms.std;
+      }
+      mean = __shfl_sync(0xffffffffu, mean, 0);
+      sd = __shfl_sync(0xffffffffu, sd, 0);
+      __syncwarp();
+      for (int i = lane; i < n; i += 32) xs[i] = __fdiv_rn(__fsub_rn(src[i], mean), sd);
+      __syncwarp();
+      src = xs;
+      double mu[4], prec[4];
+      if (vad_em(xs, n, nc, a.iters, lane, mu, prec)) {
+        int kb = 0;
+        for (int k = 1; k < nc; ++k) if (mu[k] > mu[kb]) kb = k;
+        thr = dadd(mu[kb], -dmul(a.mode, sqrt(1.0 / prec[kb])));
+        ok = true;
+        break;
+      }
+      if (nc - 1 >= 2) { --nc; continue; }
+      break;
+    }
+    if (a.thr_out != nullptr && lane == 0) a.thr_out[u] = ok ? thr : 0.0;
+    if (!ok) {
+      for (int i = lane; i < n; i += 32) out[i] = 0;
+      continue;
+    }
+    auto raw = [xs, thr](int i) -> int { return ((double)xs[i] > thr) ? 1 : 0; };
+    const bool do_smooth = a.smooth >= 3 && n >= a.smooth;
+    for (int i = lane; i < n; i += 32)
+      out[i] = do_smooth ? (uint8_t)smooth_flat_ge_f(raw, n, a.smooth, false, i) : (uint8_t)raw(i);
+  }
+}
+
+__global__ void __launch_bounds__(128) fe_vad_thr_kernel(VadArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  for (int u = wid; u < a.n_utt; u += nw) {
+    const int64_t base = a.frame_off[u];
+    const int n = (int)(a.frame_off[u + 1] - base);
+    if (n <= 0) continue;
+    const float* e = a.x + base;
+    float* en = a.scratch + base;
+    uint8_t* out = a.sad + base;
+    float lo = FLT_MAX, hi = -FLT_MAX;
+    for (int i = lane; i < n; i += 32) { lo = fminf(lo, e[i]); hi = fmaxf(hi, e[i]); }
+    lo = warp_min(lo);
+    hi = warp_max(hi);
+    const float range = __fsub_rn(hi, lo);
+    for (int i = lane; i < n; i += 32) en[i] = __fdiv_rn(__fsub_rn(e[i], lo), range);  // speech.py:1305-1307
+    __syncwarp();
+    double thr = a.thr_energy;
+    if (a.thr_mean_scale != 0.0) {
+      float s = 0.f;  // numba: sequential float32 accumulation (speech.py:1310,1328-1332)
+      if (lane == 0)
+        for (int i = 0; i < n; ++i) s = __fadd_rn(s, en[i]);
+      s = __shfl_sync(0xffffffffu, s, 0);
+      thr = dadd(thr, dmul(a.thr_mean_scale, (double)s) / (double)n);
+    }
+    if (a.thr_out != nullptr && lane == 0) a.thr_out[u] = thr;
+    // context vote (speech.py:1313-1324) -> uint8, then uint8-wrapping smooth (speech.py:1426-1431)
+    const int ctx = a.thr_context;
+    const double prop = a.thr_proportion;
+    auto vote = [en, n, thr, ctx, prop](int t) -> int {
+      int num = 0, den = 0;
+      for (int t2 = t - ctx; t2 <= t + ctx; ++t2)
+        if (t2 >= 0 && t2 < n) { ++den; if ((double)en[t2] > thr) ++num; }
+      return ((double)num >= (double)den * prop) ? 1 : 0;
+    };
+    const bool do_smooth = a.smooth >= 3 && n >= a.smooth;
+    for (int i = lane; i < n; i += 32)
+      out[i] = do_smooth ? (uint8_t)smooth_flat_ge_f(vote, n, a.smooth, true, i) : (uint8_t)vote(i);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// ApplyingSAD compaction
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+fe_count_kernel(const uint8_t* __restrict__ sad, const int64_t* __restrict__ frame_off, int n_utt,
+                int keep_unvoiced, int64_t* __restrict__ cnt) {
+  const int lane = threadIdx.x & 31;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  for (int u = wid; u < n_utt; u += nw) {
+    const int64_t b = frame_off[u], n = frame_off[u + 1] - b;
+    int c = 0;
+    for (int64_t i = lane; i < n; i += 32) c += sad[b + i] != 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) cnt[u] = (c == 0 && keep_unvoiced) ? -n : c;  // negative = keep all n frames
+  }
+}
+
+__global__ void fe_scan_kernel(const int64_t* __restrict__ cnt, int n_utt, int64_t* __restrict__ out_off) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;  // n_utt is small; a serial scan is microseconds
+  int64_t acc = 0;
+  for (int u = 0; u < n_utt; ++u) {
+    out_off[u] = acc;
+    int64_t c = cnt[u];
+    acc += c < 0 ? -c : c;
+  }
+  out_off[n_utt] = acc;
+}
+
+__global__ void __launch_bounds__(128)
+fe_compact_kernel(const uint8_t* __restrict__ sad, const int64_t* __restrict__ frame_off,
+                  const int64_t* __restrict__ cnt, const int64_t* __restrict__ out_off, int n_utt,
+                  const float* __restrict__ feat, int dim, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nw = (gridDim.x * blockDim.x) >> 5;
+  for (int u = wid; u < n_utt; u += nw) {
+    const int64_t b = frame_off[u], n = frame_off[u + 1] - b;
+    const bool all = cnt[u] < 0;
+    int64_t w = out_off[u];
+    for (int64_t i0 = 0; i0 < n; i0 += 32) {
+      const int64_t i = i0 + lane;
+      const bool keep = (i < n) && (all || sad[b + i] != 0);
+      const unsigned mask = __ballot_sync(0xffffffffu, keep);
+      // rows of this group that survive, in order
+      for (unsigned mm = mask; mm != 0; mm &= mm - 1) {
+        const int src_lane = __ffs(mm) - 1;
+        const int rank = __popc(mask & ((1u << src_lane) - 1));
+        const float* s = feat + (b + i0 + src_lane) * dim;
+        float* d = out + (w + rank) * dim;
+        for (int j = lane; j < dim; j += 32) d[j] = s[j];
+      }
+      w += __popc(mask);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host launcher
+// ---------------------------------------------------------------------------
+template <int N, typename T>
+static size_t frame_smem(int L, int hop) {
+  size_t b = (size_t)(L + (L & 1)) * sizeof(double);
+  b += (size_t)N * sizeof(C2<T>);
+  b += (size_t)FE_WARPS * padded_len<N>() * sizeof(C2<T>);
+  b += (size_t)L * sizeof(float);
+  b += (size_t)((FT - 1) * hop + L) * sizeof(float);
+  return b;
+}
+
+template <int N, typename T, typename PCM>
+static int launch_frame(const FrameArgs& a, cudaStream_t st) {
+  size_t smem = frame_smem<N, T>(a.L, a.hop);
+  if (smem > 227 * 1024) return set_error(ODIN_EINVAL, "frame kernel needs %zu B smem (hop too large)", smem);
+  auto k = fe_frame_kernel<N, T, PCM>;
+  ODIN_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (227 * 1024) / (smem + 1024)));
+  int64_t grid = std::min<int64_t>(a.n_tiles, (int64_t)sm_count() * per_sm);
+  k<<<(unsigned)grid, FE_THREADS, smem, st>>>(a);
+  ODIN_LAUNCH_CHECK("fe_frame_kernel");
+  return ODIN_OK;
+}
+
+template <typename T, typename PCM>
+static int dispatch_frame(int N, const FrameArgs& a, cudaStream_t st) {
+  switch (N) {
+    case 256: return launch_frame<256, T, PCM>(a, st);
+    case 512: return launch_frame<512, T, PCM>(a, st);
+    case 1024: return launch_frame<1024, T, PCM>(a, st);
+    case 2048: return launch_frame<2048, T, PCM>(a, st);
+  }
+  return set_error(ODIN_EINVAL, "n_fft %d unsupported (256/512/1024/2048)", N);
+}
+
+int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t total_frames, int64_t n_tiles,
+              int64_t n_tiles2, float* d_mspec, float* d_feat, float* d_energy, float* d_c0, uint8_t* d_sad,
+              double* d_sad_thr, cudaStream_t st) {
+  const odin_fe_config& c = fe->cfg;
+  if (total_frames <= 0) return ODIN_OK;
+  // 1. DC sums
+  if (c.remove_dc) {
+    ODIN_CUDA_CHECK(cudaMemsetAsync(fe->d_dcsum, 0, sizeof(double) * n_utt, st));
+    int64_t maxlen = 0;
+    for (int u = 0; u < n_utt; ++u) maxlen = std::max(maxlen, fe->h_stage[u + 1] - fe->h_stage[u]);
+    int max_chunks = (int)ceil_div<int64_t>(maxlen, DC_CHUNK);
+    int64_t grid = (int64_t)n_utt * max_chunks;
+    if (grid > 0x7fffffff) return set_error(ODIN_EINVAL, "batch too large for fe_dc_kernel");
+    if (pcm_dtype == 0)
+      fe_dc_kernel<int16_t><<<(unsigned)grid, 256, 0, st>>>((const int16_t*)d_pcm, fe->d_sample_off, n_utt,
+                                                            max_chunks, fe->d_dcsum);
+    else
+      fe_dc_kernel<float><<<(unsigned)grid, 256, 0, st>>>((const float*)d_pcm, fe->d_sample_off, n_utt,
+                                                          max_chunks, fe->d_dcsum);
+    ODIN_LAUNCH_CHECK("fe_dc_kernel");
+  }
+  // 2. frame kernel
+  {
+    // 0x80808080 decodes (ordered_to_float) to about -3.4e38: below any log-mel value
+    ODIN_CUDA_CHECK(cudaMemsetAsync(fe->d_umax, 0x80, sizeof(int) * n_utt, st));
+    FrameArgs a{};
+    a.pcm = d_pcm; a.sample_off = fe->d_sample_off; a.frame_off = fe->d_frame_off; a.tile_off = fe->d_tile_off;
+    a.n_utt = n_utt; a.n_tiles = n_tiles; a.dcsum = fe->d_dcsum; a.L = fe->L; a.hop = fe->hop;
+    a.remove_dc = c.remove_dc; a.preemph = c.preemph; a.win32 = fe->d_win32; a.win64 = fe->d_win64;
+    a.tw = fe->d_tw; a.mel_start = fe->d_mel_start; a.mel_cnt = fe->d_mel_cnt; a.mel_off = fe->d_mel_off;
+    a.mel_w = fe->d_mel_w; a.n_mels = fe->n_mels; a.scale2 = fe->scale2; a.mspec = d_mspec;
+    a.energy = d_energy; a.umax = fe->d_umax;
+    int rc = (pcm_dtype == 0) ? dispatch_frame<float, int16_t>(fe->N, a, st)
+                              : dispatch_frame<float, float>(fe->N, a, st);
+    if (rc) return rc;
+  }
+  // 3. utterance pass
+  {
+    PostArgs p{};
+    p.frame_off = fe->d_frame_off; p.tile2_off = fe->d_tile2_off; p.n_utt = n_utt; p.umax = fe->d_umax;
+    p.top_db = c.top_db; p.n_mels = fe->n_mels; p.n_c1 = fe->n_c1; p.n_ceps = c.n_ceps; p.W = c.delta_width;
+    p.order = c.delta_order; p.dct = fe->d_dct; p.taps = fe->d_taps; p.mspec = d_mspec; p.write_mspec = 1;
+    p.feat = d_feat; p.c0 = d_c0;
+    const int h = c.delta_width / 2;
+    const int HL = (c.delta_order >= 2) ? (c.delta_width - 1 + h) : (c.delta_order == 1 ? h : 0);
+    const int HR = (c.delta_order >= 1) ? h : 0;
+    const int NR = PT + HL + HR, ND = PT + ((c.delta_order >= 2) ? c.delta_width - 1 : 0);
+    size_t smem = sizeof(float) * ((size_t)NR * fe->n_mels + (size_t)NR * fe->n_c1 + (size_t)ND * c.n_ceps +
+                                   (size_t)fe->n_c1 * fe->n_mels + c.delta_width + 4);
+    if (smem > 227 * 1024) return set_error(ODIN_EINVAL, "post kernel needs %zu B smem", smem);
+    ODIN_CUDA_CHECK(cudaFuncSetAttribute(fe_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fe_post_kernel<<<(unsigned)n_tiles2, 256, smem, st>>>(p);
+    ODIN_LAUNCH_CHECK("fe_post_kernel");
+  }
+  // 4. VAD
+  if (c.vad_kind != 0 && d_sad != nullptr) {
+    VadArgs v{};
+    v.frame_off = fe->d_frame_off; v.n_utt = n_utt; v.sad = d_sad; v.thr_out = d_sad_thr;
+    v.nmix = c.vad_nmix; v.iters = c.vad_iters; v.smooth = c.vad_smooth; v.mode = (double)c.vad_mode;
+    v.thr_energy = (double)c.thr_energy; v.thr_mean_scale = (double)c.thr_mean_scale;
+    v.thr_proportion = (double)c.thr_proportion; v.thr_context = c.thr_context;
+    // scratch: reuse the per-frame part of the handle
+    if (fe->vad_scratch_cap < total_frames) {
+      if (fe->d_vad_scratch) ODIN_CUDA_CHECK(cudaFree(fe->d_vad_scratch));
+      fe->d_vad_scratch = nullptr; fe->vad_scratch_cap = 0;
+      ODIN_CUDA_CHECK(cudaMalloc(&fe->d_vad_scratch, sizeof(float) * (total_frames + total_frames / 8 + 256)));
+      fe->vad_scratch_cap = total_frames + total_frames / 8 + 256;
+    }
+    v.scratch = fe->d_vad_scratch;
+    int warps_per_cta = 4;
+    int grid = (int)std::min<int64_t>(ceil_div(n_utt, warps_per_cta), (int64_t)sm_count() * 8);
+    if (c.vad_kind == 1) {
+      if (d_energy == nullptr) return set_error(ODIN_EINVAL, "SADgmm needs d_energy");
+      v.x = d_energy;
+      fe_vad_gmm_kernel<<<grid, 128, 0, st>>>(v);
+      ODIN_LAUNCH_CHECK("fe_vad_gmm_kernel");
+    } else {
+      if (d_c0 == nullptr) return set_error(ODIN_EINVAL, "SADthreshold needs d_c0");
+      v.x = d_c0;
+      fe_vad_thr_kernel<<<grid, 128, 0, st>>>(v);
+      ODIN_LAUNCH_CHECK("fe_vad_thr_kernel");
+    }
+  }
+  return ODIN_OK;
+}
+
+int fe_compact_launch(odin_fe* fe, const uint8_t* d_sad, int n_utt, const float* d_feat, int dim,
+                      int keep_unvoiced, float* d_out, int64_t* d_out_offsets, cudaStream_t st) {
+  int grid = (int)std::min<int64_t>(ceil_div(n_utt, 4), (int64_t)sm_count() * 8);
+  fe_count_kernel<<<grid, 128, 0, st>>>(d_sad, fe->d_frame_off, n_utt, keep_unvoiced, fe->d_cnt);
+  ODIN_LAUNCH_CHECK("fe_count_kernel");
+  fe_scan_kernel<<<1, 32, 0, st>>>(fe->d_cnt, n_utt, d_out_offsets);
+  ODIN_LAUNCH_CHECK("fe_scan_kernel");
+  fe_compact_kernel<<<grid, 128, 0, st>>>(d_sad, fe->d_frame_off, fe->d_cnt, d_out_offsets, n_utt, d_feat, dim,
+                                          d_out);
+  ODIN_LAUNCH_CHECK("fe_compact_kernel");
+  return ODIN_OK;
+}
+
+}  // namespace odin

@@ -1,0 +1,66 @@
+// GMM-UBM handle shared by the fp32 CUDA-core kernels (gmm_kernels.cu) and the
+// 3xTF32 tcgen05 kernels (gmm_tc.cu).
+#pragma once
+#include "common.cuh"
+
+#define ODIN_GMM_EPS 1e-6  // gmm_tmat.py:27
+
+struct odin_gmm {
+  int D = 0;        // feature dimension
+  int max_nmix = 0;
+  int M = 0;        // current number of mixtures
+  int device = 0;
+  // current model, reference layout [D, M] row-major (fp32)
+  float* d_mean = nullptr;
+  float* d_var = nullptr;
+  float* d_w = nullptr;
+  // cached posterior constants (gmm_tmat.py:493-504), refreshed by set_params / mstep / mixup
+  //   Wk  [2D, Mpad]: rows 0..D-1 = -0.5*precision, rows D..2D-1 = mean*precision
+  //   cst [Mpad]    : -0.5*(C + D log 2pi); padding columns hold -1e30
+  float* d_Wk = nullptr;
+  float* d_cst = nullptr;
+  int Mpad = 0;  // M rounded up to 128
+  // tcgen05 operand images (gmm_tc.cu): [Mpad, 128] hi and lo TF32 splits of
+  // [-0.5*prec | mu*prec | 0 pad], K-major with the 128B swizzle applied.
+  float* d_Whi = nullptr;
+  float* d_Wlo = nullptr;
+  // per-frame log-sum-exp workspace (grows on demand)
+  float* d_lse = nullptr;
+  int64_t lse_cap = 0;
+  // scratch for M-step rollback
+  float* d_prev = nullptr;  // [3][D*max_nmix] (mean, var) + w
+  // pinned staging + device copy of frame offsets for utt_stats
+  int64_t* h_off = nullptr;
+  int64_t* d_off = nullptr;
+  int64_t off_cap = 0;
+};
+
+namespace odin {
+
+int gmm_refresh_constants(odin_gmm* g, cudaStream_t st);
+int gmm_reserve_lse(odin_gmm* g, int64_t n);
+
+// fp32 CUDA-core path
+int gmm_lse_ffma(odin_gmm* g, const float* X, const uint8_t* sad, int64_t N, float* lse,
+                 double* stats /*nullable: L, nframes accumulated*/, cudaStream_t st);
+int gmm_stats_ffma(odin_gmm* g, const float* X, const uint8_t* sad, int64_t N, const float* lse,
+                   int want_second, double* stats, cudaStream_t st);
+int gmm_utt_stats_ffma(odin_gmm* g, const float* X, const uint8_t* sad, const int64_t* d_off,
+                       int n_utt, const float* lse, float* Z, float* Fhat, cudaStream_t st);
+int gmm_post_ffma(odin_gmm* g, const float* X, int64_t N, const float* lse, float* post, float* logp,
+                  cudaStream_t st);
+
+// 3xTF32 tcgen05 path (gmm_tc.cu); returns ODIN_EINVAL when the shape is unsupported
+bool gmm_tc_supported(const odin_gmm* g);
+int gmm_tc_refresh(odin_gmm* g, cudaStream_t st);
+int gmm_lse_tc(odin_gmm* g, const float* X, const uint8_t* sad, int64_t N, float* lse, double* stats,
+               cudaStream_t st);
+int gmm_stats_tc(odin_gmm* g, const float* X, const uint8_t* sad, int64_t N, const float* lse,
+                 int want_second, double* stats, cudaStream_t st);
+
+int gmm_mstep_launch(odin_gmm* g, const double* stats, int allow_rollback, int* rolled_back, cudaStream_t st);
+int gmm_mixup_launch(odin_gmm* g, int newM, cudaStream_t st);
+
+inline int64_t stats_size(int D, int M) { return (int64_t)M * (2 * D + 1) + 2; }
+
+}  // namespace odin

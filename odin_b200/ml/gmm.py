@@ -1,0 +1,676 @@
+"""Diagonal GMM-UBM with the surface of ``odin.ml.GMM`` (reference:
+odin/ml/gmm_tmat.py:270-1338) over the B200 kernels of libodin_b200.
+
+Same constructor keywords, attributes (``mean [D,M]``, ``sigma [D,M]`` =
+VARIANCE, ``w [1,M]``), methods and pickle tuple as the reference, so a recipe
+switches by changing the import.  All arithmetic of the E-step / M-step / split
+runs in CUDA (``odin_gmm_*`` in include/odin_b200.h); this file is host logic
+only: argument handling, the split-and-train schedule (gmm_tmat.py:625-699),
+batch selection for ``downsample`` (gmm_tmat.py:135-168), host<->device staging
+and the NCCL all-reduce that replaces the reference's multiprocessing sum
+(gmm_tmat.py:249-265, 1199-1220).
+
+There is no CPU path: ``device`` is accepted for signature compatibility only.
+"""
+import os
+import pickle
+import random
+from collections import defaultdict
+from collections.abc import Mapping
+
+import numpy as np
+
+from .. import _lib
+
+EPS = 1e-6  # gmm_tmat.py:27
+
+_NITER_SCHEDULE = [1, 2, 4, 4, 4, 4, 6, 6, 10, 10, 10, 10, 10, 16, 16]  # gmm_tmat.py:677
+
+
+def _torch():
+  import torch
+  return torch
+
+
+def _dist():
+  td = _torch().distributed
+  if td.is_available() and td.is_initialized() and td.get_world_size() > 1:
+    return td
+  return None
+
+
+def minibatch(n, batch_size):
+  """odin.utils.minibatch: contiguous (start, end) ranges."""
+  batch_size = int(batch_size)
+  return [(s, min(s + batch_size, n)) for s in range(0, n, batch_size)]
+
+
+class _DeviceFrames(object):
+  """Feeds [N, D] float32 frames to the kernels: a CUDA tensor is used in place,
+  a host array is streamed through two pinned buffers on a copy stream so the
+  H2D copy of chunk i+1 overlaps the E-step of chunk i."""
+
+  def __init__(self, X, chunk_frames=1 << 20):
+    torch = _torch()
+    self.torch = torch
+    self.resident = None
+    self.host = None
+    if isinstance(X, torch.Tensor):
+      if not X.is_cuda:
+        X = X.numpy()
+      else:
+        if X.dtype != torch.float32 or not X.is_contiguous():
+          X = X.to(torch.float32).contiguous()
+        self.resident = X
+    if self.resident is None:
+      X = np.asarray(X) if not isinstance(X, np.memmap) else X
+      if X.ndim != 2:
+        raise ValueError("`X` must be a 2-D matrix [n_samples, feat_dim]")
+      self.host = X
+    self.n, self.dim = (self.resident.shape if self.resident is not None else self.host.shape)
+    self.chunk = int(chunk_frames)
+
+  def cache_on_device(self, reserve_bytes=2 << 30):
+    """Upload once if it fits (used by fit(): EM re-reads the data every iteration)."""
+    if self.resident is not None:
+      return True
+    torch = self.torch
+    need = self.n * self.dim * 4
+    free, _ = torch.cuda.mem_get_info()
+    if need + reserve_bytes > free:
+      return False
+    out = torch.empty((self.n, self.dim), dtype=torch.float32, device="cuda")
+    for dev, s, e in self.chunks():
+      out[s:e].copy_(dev)
+    self.resident, self.host = out, None
+    return True
+
+  def chunks(self):
+    """Yields (device tensor [n_i, D] float32, start, end)."""
+    torch = self.torch
+    if self.resident is not None:
+      yield self.resident, 0, self.n
+      return
+    n, D = self.n, self.dim
+    if n == 0:
+      return
+    ch = min(self.chunk, n)
+    pinned = [torch.empty((ch, D), dtype=torch.float32).pin_memory() for _ in range(2)]
+    dev = [torch.empty((ch, D), dtype=torch.float32, device="cuda") for _ in range(2)]
+    copy_stream = torch.cuda.Stream()
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    ranges = minibatch(n, ch)
+
+    def stage(i):
+      s, e = ranges[i]
+      b = i & 1
+      consumed[b].synchronize()  # kernels of chunk i-2 are done with dev[b]; pinned[b] was copied
+      np.copyto(pinned[b][:e - s].numpy(), self.host[s:e], casting="unsafe")
+      with torch.cuda.stream(copy_stream):
+        dev[b][:e - s].copy_(pinned[b][:e - s], non_blocking=True)
+        copied[b].record(copy_stream)
+
+    for b in range(2):
+      consumed[b].record()
+    stage(0)
+    for i, (s, e) in enumerate(ranges):
+      if i + 1 < len(ranges):
+        stage(i + 1)
+      b = i & 1
+      torch.cuda.current_stream().wait_event(copied[b])
+      yield dev[b][:e - s], s, e
+      consumed[b].record()
+
+
+class GMM(object):
+  r"""Gaussian Mixture Model with diagonal covariance (see module docstring).
+
+  Parameters follow gmm_tmat.py:341-346.  Extra keyword ``impl`` selects the
+  kernel family: 0 auto, 1 fp32 CUDA cores, 2 3xTF32 tcgen05.
+  """
+
+  STANDARD_CPU_BATCH_SIZE = 12 * 1024 * 1024  # gmm_tmat.py:338-339
+  STANDARD_GPU_BATCH_SIZE = 25 * 1024 * 1024
+
+  def __init__(self, nmix, nmix_start=1, niter=16, dtype='float32',
+               allow_rollback=True, exit_on_error=False,
+               batch_size_cpu='auto', batch_size_gpu='auto',
+               downsample=1, stochastic_downsample=True,
+               device='gpu', ncpu=1, gpu_factor=80,
+               seed=1234, path=None, name=None, impl=0):
+    self._path = path if isinstance(path, str) else None
+    nmix = int(nmix)
+    if nmix < 1:
+      raise ValueError("Number of Mixture must be greater than 1.")
+    self._nmix = nmix
+    self._curr_nmix = int(np.clip(int(nmix_start), 1, self._nmix))
+    self._feat_dim = None
+    self._niter = int(niter)
+    self.batch_size_cpu = batch_size_cpu
+    self.batch_size_gpu = batch_size_gpu
+    self.downsample = int(downsample)
+    self.stochastic_downsample = bool(stochastic_downsample)
+    self._seed = int(seed)
+    self.gpu_factor = int(gpu_factor)
+    self.ncpu = int(ncpu) if ncpu is not None else 1
+    self.set_device(device)
+    self._llk_hist = defaultdict(list)
+    self.allow_rollback = bool(allow_rollback)
+    self.exit_on_error = bool(exit_on_error)
+    self._stop_fitting = False
+    self._dtype = np.dtype(dtype)
+    self._name = ('GMM_%08x' % random.getrandbits(32)) if name is None else str(name)
+    self.impl = int(impl)
+    self._init_device_state()
+
+  # ------------------------------------------------------------------ state
+  def _init_device_state(self):
+    self._handle = None
+    self._d_mean = self._d_var = self._d_w = None
+    self._d_stats = None
+    self._d_flag = None
+    self._synced = (None, None, None)
+
+  def __getstate__(self):  # gmm_tmat.py:388-400 (same 21-tuple)
+    if not self.is_initialized:
+      raise RuntimeError("GMM hasn't been initialized, nothing to save")
+    return (self.mean, self.sigma, self.w,
+            self.allow_rollback, self.exit_on_error,
+            self._nmix, self._curr_nmix, self._feat_dim,
+            self._niter, self.batch_size_cpu, self.batch_size_gpu,
+            self.downsample, self.stochastic_downsample,
+            self._seed, self._llk_hist,
+            self.ncpu, self._device, self.gpu_factor,
+            self._dtype, self._path, self._name)
+
+  def __setstate__(self, states):
+    (self.mean, self.sigma, self.w,
+     self.allow_rollback, self.exit_on_error,
+     self._nmix, self._curr_nmix, self._feat_dim,
+     self._niter, self.batch_size_cpu, self.batch_size_gpu,
+     self.downsample, self.stochastic_downsample,
+     self._seed, self._llk_hist,
+     self.ncpu, self._device, self.gpu_factor,
+     self._dtype, self._path, self._name) = states
+    self._stop_fitting = False
+    self.impl = 0
+    self._feat_const = self._feat_dim * np.log(2 * np.pi)
+    self._init_device_state()
+
+  def __del__(self):
+    try:
+      if getattr(self, "_handle", None) is not None:
+        _lib.load().odin_gmm_destroy(self._handle)
+        self._handle = None
+    except Exception:
+      pass
+
+  def __str__(self):
+    if not self.is_initialized:
+      return '<"%s" nmix:%d initialized:False>' % (self.name, self._nmix)
+    return '<"%s" nmix:%s ndim:%s mean:%s std:%s w:%s>' % (
+        self.name, self._nmix, self._feat_dim, self.mean.shape, self.sigma.shape, self.w.shape)
+
+  # ------------------------------------------------------------- properties
+  def set_device(self, device):
+    device = str(device).lower()
+    if device not in ('cpu', 'gpu', 'mix'):
+      raise ValueError("`device` must be one of the following: 'cpu', 'gpu', or 'mix'")
+    self._device = device  # kept for pickle compatibility; compute is always CUDA
+    return self
+
+  device = property(lambda self: self._device)
+  path = property(lambda self: self._path)
+  name = property(lambda self: self._name)
+  is_initialized = property(lambda self: self._feat_dim is not None)
+  is_fitted = property(lambda self: self._curr_nmix == self._nmix)
+  nmix = property(lambda self: self._nmix)
+  dtype = property(lambda self: self._dtype)
+  history = property(lambda self: tuple(self._llk_hist))
+
+  @property
+  def feat_dim(self):
+    if not self.is_initialized:
+      raise RuntimeError("GMM has not been initialized on data.")
+    return self._feat_dim
+
+  def get_params(self, deep=True):
+    return dict(nmix=self._nmix, nmix_start=self._curr_nmix, niter=self._niter, dtype=self._dtype,
+                allow_rollback=self.allow_rollback, exit_on_error=self.exit_on_error,
+                batch_size_cpu=self.batch_size_cpu, batch_size_gpu=self.batch_size_gpu,
+                downsample=self.downsample, stochastic_downsample=self.stochastic_downsample,
+                device=self._device, ncpu=self.ncpu, gpu_factor=self.gpu_factor, seed=self._seed,
+                path=self._path, name=self._name)
+
+  # --------------------------------------------------------- device plumbing
+  def _ensure_handle(self):
+    _lib.require_cuda()
+    torch = _torch()
+    lib = _lib.load()
+    if self._handle is None:
+      import ctypes as C
+      h = C.c_void_p()
+      _lib.check(lib.odin_gmm_create(self._feat_dim, self._nmix, C.byref(h)))
+      self._handle = h
+      D, M = self._feat_dim, self._nmix
+      self._d_mean = torch.empty(D * M, dtype=torch.float32, device="cuda")
+      self._d_var = torch.empty(D * M, dtype=torch.float32, device="cuda")
+      self._d_w = torch.empty(M, dtype=torch.float32, device="cuda")
+      self._d_flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+      self._synced = (None, None, None)
+    return lib
+
+  def _upload_params(self, force=False):
+    """Host attributes -> device when they were replaced since the last sync."""
+    lib = self._ensure_handle()
+    if not force and self._synced[0] is self.mean and self._synced[1] is self.sigma \
+        and self._synced[2] is self.w:
+      return lib
+    torch = _torch()
+    D, M = self._feat_dim, self._curr_nmix
+    for dst, src, n in ((self._d_mean, self.mean, D * M), (self._d_var, self.sigma, D * M),
+                        (self._d_w, self.w, M)):
+      a = np.ascontiguousarray(np.asarray(src, dtype=np.float32)).reshape(-1)
+      if a.shape[0] != n:
+        raise ValueError("parameter has %d elements, expected %d" % (a.shape[0], n))
+      dst[:n].copy_(torch.from_numpy(a))
+    _lib.check(lib.odin_gmm_set_params(self._handle, M, _lib.ptr(self._d_mean), _lib.ptr(self._d_var),
+                                       _lib.ptr(self._d_w), _lib.current_stream()))
+    self._synced = (self.mean, self.sigma, self.w)
+    return lib
+
+  def _download_params(self):
+    D, M = self._feat_dim, self._curr_nmix
+    self.mean = self._d_mean[:D * M].cpu().numpy().reshape(D, M).astype(self._dtype, copy=False)
+    self.sigma = self._d_var[:D * M].cpu().numpy().reshape(D, M).astype(self._dtype, copy=False)
+    self.w = self._d_w[:M].cpu().numpy().reshape(1, M).astype(self._dtype, copy=False)
+    self._synced = (self.mean, self.sigma, self.w)
+
+  def _resfresh_cpu_posterior(self):
+    """Reference name (gmm_tmat.py:493-504): call after editing mean/sigma/w in
+    place; re-uploads the model and refreshes the cached constants on device."""
+    self._upload_params(force=True)
+
+  _refresh_gpu_posterior = _resfresh_cpu_posterior
+
+  def _stats_buffer(self):
+    torch = _torch()
+    n = (2 * self._feat_dim + 1) * self._curr_nmix + 2
+    if self._d_stats is None or self._d_stats.shape[0] != n:
+      self._d_stats = torch.zeros(n, dtype=torch.float64, device="cuda")
+    return self._d_stats
+
+  def _unpack_stats(self, stats_host, zero, first, second, llk):
+    D, M = self._feat_dim, self._curr_nmix
+    Z = stats_host[:M].reshape(1, M)
+    F = stats_host[M:M + D * M].reshape(D, M)
+    S = stats_host[M + D * M:M + 2 * D * M].reshape(D, M)
+    L, nfr = stats_host[-2], stats_host[-1]
+    out = []
+    if zero:
+      out.append(Z)
+    if first:
+      out.append(F)
+    if second:
+      out.append(S)
+    if llk:
+      out.append(np.array(L / nfr if nfr > 0 else 0.0))
+    return out[0] if len(out) == 1 else out
+
+  # --------------------------------------------------------- initialization
+  def initialize(self, X):  # gmm_tmat.py:562-622
+    indices = None
+    if isinstance(X, (tuple, list)):
+      tmp = [i for i in X if hasattr(i, 'shape')][0]
+      rest = [i for i in X if i is not tmp]
+      indices = rest[0] if rest else None
+      X = tmp
+    if isinstance(indices, Mapping):
+      indices = list(indices.items())
+    if not hasattr(X, 'shape') or len(X.shape) != 2:
+      raise ValueError("`X` must be a 2-D array [n_samples, feat_dim]")
+    feat_dim = int(X.shape[1])
+    if self.is_initialized:
+      if feat_dim != self._feat_dim:
+        raise RuntimeError("Input must be 2-D matrix with the 1st dimension equal to: %d" % self._feat_dim)
+      return X, indices
+    self._feat_dim = feat_dim
+    self._feat_const = self._feat_dim * np.log(2 * np.pi)
+    if isinstance(self.batch_size_cpu, str):
+      self.batch_size_cpu = int(GMM.STANDARD_CPU_BATCH_SIZE / (self._feat_dim * self._dtype.itemsize))
+    if isinstance(self.batch_size_gpu, str):
+      self.batch_size_gpu = int(GMM.STANDARD_GPU_BATCH_SIZE / (self._feat_dim * self._dtype.itemsize))
+    self.mean = np.zeros((feat_dim, self._curr_nmix), dtype=self._dtype)
+    self.sigma = np.ones((feat_dim, self._curr_nmix), dtype=self._dtype)
+    self.w = np.ones((1, self._curr_nmix), dtype=self._dtype)
+    return X, indices
+
+  # ---------------------------------------------------------------- E-step
+  def _selected_mask(self, n, sad, indices):
+    """Frame selection of gmm_tmat.py:135-232 as a uint8 mask (None = all)."""
+    mask = None
+    if indices is not None:
+      mask = np.zeros(n, dtype=np.uint8)
+      for _, (s, e) in indices:
+        mask[int(s):int(e)] = 1
+    if self.downsample > 1:
+      curr_niter = len(self._llk_hist[self._curr_nmix])
+      random.seed(int(self._seed + self._curr_nmix + curr_niter) if self.stochastic_downsample
+                  else int(self._seed))
+      if indices is None:
+        reduction = np.floor(np.power(2, self._curr_nmix / 1024))
+        units = minibatch(n, int(self.batch_size_cpu / reduction))
+      else:
+        units = [(int(s), int(e)) for _, (s, e) in indices]
+      random.shuffle(units)
+      keep = np.zeros(n, dtype=np.uint8)
+      for i, (s, e) in enumerate(units):
+        if i == 0 or random.random() <= 1. / self.downsample:
+          keep[s:e] = 1
+      mask = keep if mask is None else (mask & keep)
+    if sad is not None:
+      sad = (np.asarray(sad).reshape(-1) != 0).astype(np.uint8)
+      mask = sad if mask is None else (mask & sad)
+    return mask
+
+  def _estep_device(self, frames, mask, second=True):
+    """Runs the E-step kernels over `frames` (a _DeviceFrames); returns the packed
+    fp64 statistics tensor on device, all-reduced over ranks."""
+    torch = _torch()
+    lib = self._upload_params()
+    stats = self._stats_buffer()
+    stats.zero_()
+    d_mask = None
+    if mask is not None:
+      if isinstance(mask, torch.Tensor):
+        d_mask = mask.to(device="cuda", dtype=torch.uint8).contiguous()
+      else:
+        d_mask = torch.from_numpy(np.ascontiguousarray(mask)).cuda()
+    for dev, s, e in frames.chunks():
+      sad_ptr = None if d_mask is None else _lib.C.c_void_p(d_mask.data_ptr() + s)
+      _lib.check(lib.odin_gmm_estep(self._handle, _lib.ptr(dev), sad_ptr, e - s, 1 if second else 0,
+                                    _lib.ptr(stats), self.impl, _lib.current_stream()))
+    td = _dist()
+    if td is not None:
+      td.all_reduce(stats, op=td.ReduceOp.SUM)  # gmm_tmat.py:249-265 -> one NCCL all-reduce
+    return stats
+
+  def _fast_expectation(self, X, zero=True, first=True, second=True, llk=True, on_gpu=True):
+    """gmm_tmat.py:997-1041 (L is the SUM of frame log-likelihoods here, as in the reference)."""
+    self.initialize(X)
+    stats = self._estep_device(_DeviceFrames(X), None, second).cpu().numpy()
+    out = self._unpack_stats(stats, zero, first, second, False)
+    out = [out] if not isinstance(out, list) else out
+    if llk:
+      out.append(stats[-2])
+    return out if len(out) > 1 else out[0]
+
+  def expectation(self, X, sad=None, zero=True, first=True, second=True, llk=True,
+                  device=None, print_progress=True):
+    """gmm_tmat.py:1043-1231 -> Z [1,M], F [D,M], S [D,M], L (mean log-likelihood)."""
+    X, indices = self.initialize(X)
+    frames = X if isinstance(X, _DeviceFrames) else _DeviceFrames(X)
+    if sad is not None:
+      assert sad.shape[0] == frames.n, \
+          "Number of samples for X and sad mismatch X.shape=%s and sad.shape=%s" % ((frames.n, frames.dim), sad.shape)
+    mask = self._selected_mask(frames.n, sad, indices)
+    stats = self._estep_device(frames, mask, second).cpu().numpy()
+    return self._unpack_stats(stats, zero, first, second, llk)
+
+  # ---------------------------------------------------------------- M-step
+  def maximization(self, Z, F, S, floor_const=None):
+    """gmm_tmat.py:1233-1276 on device (fp64) from host statistics."""
+    torch = _torch()
+    D, M = self._feat_dim, self._curr_nmix
+    packed = np.concatenate([np.asarray(Z, dtype=np.float64).reshape(-1),
+                             np.asarray(F, dtype=np.float64).reshape(-1),
+                             np.asarray(S, dtype=np.float64).reshape(-1), [0.0, 0.0]])
+    assert packed.shape[0] == (2 * D + 1) * M + 2
+    self._upload_params()
+    stats = self._stats_buffer()
+    stats.copy_(torch.from_numpy(packed))
+    return self._maximization_device(stats, floor_const)
+
+  def _maximization_device(self, stats, floor_const=None):
+    lib = self._ensure_handle()
+    _lib.check(lib.odin_gmm_mstep(self._handle, _lib.ptr(stats), 1 if self.allow_rollback else 0,
+                                  _lib.ptr(self._d_mean), _lib.ptr(self._d_var), _lib.ptr(self._d_w),
+                                  _lib.ptr(self._d_flag), _lib.current_stream()))
+    self._download_params()
+    if floor_const is not None:  # gmm_tmat.py:1255-1257 (not used by fit)
+      vfloor = self.sigma.dot(self.w.T) * floor_const
+      self.sigma = self.sigma.clip(vfloor)
+      self._upload_params(force=True)
+    if int(self._d_flag.item()) != 0 and self.exit_on_error:
+      self._stop_fitting = True
+    return self
+
+  def expectation_maximization(self, X, sad=None, device=None, print_progress=True):
+    """gmm_tmat.py:1278-1306."""
+    X, indices = self.initialize(X)
+    frames = X if isinstance(X, _DeviceFrames) else _DeviceFrames(X)
+    curr_nmix = self._curr_nmix
+    mask = self._selected_mask(frames.n, sad, indices)
+    stats = self._estep_device(frames, mask, True)
+    tail = stats[-2:].cpu().numpy()
+    L = float(tail[0] / tail[1]) if tail[1] > 0 else 0.0
+    self._maximization_device(stats)
+    self._llk_hist[curr_nmix].append(L)
+    if print_progress:
+      print("#mix:%.2d #iter:%.2d llk:%.4f" % (curr_nmix, len(self._llk_hist[curr_nmix]), L))
+    self._checkpoint()
+    return self
+
+  def gmm_mixup(self):
+    """gmm_tmat.py:1308-1338 on device."""
+    if self._curr_nmix >= self._nmix:
+      return
+    lib = self._upload_params()
+    new_m = min(2 * self._curr_nmix, self._nmix)
+    _lib.check(lib.odin_gmm_mixup(self._handle, new_m, _lib.ptr(self._d_mean), _lib.ptr(self._d_var),
+                                  _lib.ptr(self._d_w), _lib.current_stream()))
+    self._curr_nmix = new_m
+    self._download_params()
+    self._checkpoint()
+    return self
+
+  def _checkpoint(self):
+    if self._path is not None:
+      td = _dist()
+      if td is None or td.get_rank() == 0:
+        with open(self._path, 'wb') as f:
+          pickle.dump(self, f)
+
+  # ------------------------------------------------------------------- fit
+  def fit(self, X, y=None, print_progress=False):
+    """gmm_tmat.py:625-699: split-and-train schedule.  `X` is an array (numpy or
+    CUDA tensor) or a tuple (X, sad) / (X, indices) / (X, sad, indices)."""
+    if not isinstance(X, (tuple, list)):
+      X = (X,)
+    sad = None
+    indices = None
+    if len(X) == 1:
+      data = X[0]
+    elif len(X) == 2:
+      if hasattr(X[1], 'shape') and X[0].shape[0] == X[1].shape[0]:
+        data, sad = X
+      else:
+        data, indices = X
+    elif len(X) == 3:
+      data, sad, indices = X
+    else:
+      raise ValueError("No support for `X` in type of list with length: %d" % len(X))
+    assert hasattr(data, 'shape') and len(data.shape) == 2, \
+        'Input data must be instance of 2-D ndarray but give: %s' % str(type(data))
+    if indices is not None:
+      if isinstance(indices, Mapping):
+        indices = list(indices.items())
+      indices = sorted(indices, key=lambda x: x[1][0])
+    self.initialize(data)
+    frames = _DeviceFrames(data)
+    frames.cache_on_device()
+    arg = frames if indices is None else (frames, indices)
+    niter = list(_NITER_SCHEDULE)
+    niter[int(np.log2(self._nmix))] = self._niter
+    self._stop_fitting = False
+    while True:
+      curr_nmix = self._curr_nmix
+      curr_niter = niter[int(np.log2(curr_nmix))] - len(self._llk_hist[curr_nmix])
+      for _ in range(max(curr_niter, 0)):
+        self._em_frames(frames, sad, indices, print_progress)
+        if self._stop_fitting:
+          return self
+      if curr_nmix < self._nmix:
+        self.gmm_mixup()
+      else:
+        break
+    return self
+
+  def _em_frames(self, frames, sad, indices, print_progress):
+    curr_nmix = self._curr_nmix
+    mask = self._selected_mask(frames.n, sad, indices)
+    stats = self._estep_device(frames, mask, True)
+    tail = stats[-2:].cpu().numpy()
+    L = float(tail[0] / tail[1]) if tail[1] > 0 else 0.0
+    self._maximization_device(stats)
+    self._llk_hist[curr_nmix].append(L)
+    if print_progress:
+      print("#mix:%.2d #iter:%.2d llk:%.4f" % (curr_nmix, len(self._llk_hist[curr_nmix]), L))
+    self._checkpoint()
+
+  # ------------------------------------------------------ scoring utilities
+  def _score_device(self, X, want_post, want_logprob):
+    torch = _torch()
+    self.initialize(X)
+    lib = self._upload_params()
+    frames = _DeviceFrames(X)
+    M = self._curr_nmix
+    llk = np.empty((frames.n, 1), dtype=np.float32)
+    post = np.empty((frames.n, M), dtype=np.float32) if want_post else None
+    logp = np.empty((frames.n, M), dtype=np.float32) if want_logprob else None
+    for dev, s, e in frames.chunks():
+      n = e - s
+      d_llk = torch.empty(n, dtype=torch.float32, device="cuda")
+      d_post = torch.empty((n, M), dtype=torch.float32, device="cuda") if want_post else None
+      d_logp = torch.empty((n, M), dtype=torch.float32, device="cuda") if want_logprob else None
+      _lib.check(lib.odin_gmm_score(self._handle, _lib.ptr(dev), n, _lib.ptr(d_llk), _lib.ptr(d_post),
+                                    _lib.ptr(d_logp), _lib.current_stream()))
+      llk[s:e, 0] = d_llk.cpu().numpy()
+      if want_post:
+        post[s:e] = d_post.cpu().numpy()
+      if want_logprob:
+        logp[s:e] = d_logp.cpu().numpy()
+    return llk, post, logp
+
+  def logprob(self, X):
+    """gmm_tmat.py:916-938 -> [batch, nmix]."""
+    return self._score_device(X, False, True)[2]
+
+  def postprob(self, X, gpu='auto'):
+    """gmm_tmat.py:940-966 -> [batch, nmix]."""
+    return self._score_device(X, True, False)[1]
+
+  def llk(self, X, gpu='auto'):
+    """gmm_tmat.py:968-995 -> [batch, 1]."""
+    return self._score_device(X, False, False)[0]
+
+  def score(self, X, y=None):
+    """gmm_tmat.py:701-706 -> [batch, 1]."""
+    return self.llk(X)
+
+  # ------------------------------------------------ per-utterance statistics
+  def _utt_stats_device(self, frames_dev, d_sad, offsets):
+    """offsets: int64 numpy [n_utt+1] into frames_dev. Returns (Z, Fhat) CUDA tensors."""
+    torch = _torch()
+    lib = self._upload_params()
+    n_utt = len(offsets) - 1
+    D, M = self._feat_dim, self._curr_nmix
+    Z = torch.empty((n_utt, M), dtype=torch.float32, device="cuda")
+    Fh = torch.empty((n_utt, M * D), dtype=torch.float32, device="cuda")
+    off = np.ascontiguousarray(offsets, dtype=np.int64)
+    _lib.check(lib.odin_gmm_utt_stats(self._handle, _lib.ptr(frames_dev), _lib.ptr(d_sad), _lib.as_i64_ptr(off),
+                                      n_utt, _lib.ptr(Z), _lib.ptr(Fh), self.impl, _lib.current_stream()))
+    return Z, Fh
+
+  def transform(self, X, zero=True, first=True, device=None):
+    """gmm_tmat.py:708-767 -> (Z [1,M], Fhat [1, D*M]), Fhat index = m*D + d."""
+    zero, first = bool(zero), bool(first)
+    if not zero and not first:
+      raise ValueError("One of `zero` or `first` must be True")
+    self.initialize(X)
+    assert X.ndim == 2 and X.shape[1] == self.feat_dim, \
+        "`X` must be 2-D matrix, with `X.shape[1]=%d`; but given: %s" % (self.feat_dim, str(X.shape))
+    frames = _DeviceFrames(X)
+    frames.cache_on_device(0)
+    Z, Fh = self._utt_stats_device(frames.resident, None, np.array([0, frames.n], dtype=np.int64))
+    Z, Fh = Z.cpu().numpy(), Fh.cpu().numpy()
+    if zero and first:
+      return Z, Fh
+    return Z if zero else Fh
+
+  def transform_to_disk(self, X, indices, sad=None, pathZ=None, pathF=None, name_path=None,
+                        dtype='float32', device='gpu', ncpu=None, override=True, utt_batch=256):
+    """gmm_tmat.py:769-913.  Z [n_utt, M] and Fhat [n_utt, M*D] are written as
+    .npy files (the reference's bigarray.MmapArray container is a third-party
+    format outside this path); returns the utterance names in processing order
+    (sorted by start, like the reference)."""
+    if isinstance(indices, Mapping):
+      indices = list(indices.items())
+    indices = sorted(indices, key=lambda x: x[1][0])
+    self.initialize(X)
+    torch = _torch()
+    frames = _DeviceFrames(X)
+    resident = frames.cache_on_device()
+    n_utt = len(indices)
+    D, M = self._feat_dim, self._nmix
+    for p in (pathZ, pathF):
+      if p is not None and os.path.exists(p) and override:
+        os.remove(p)
+    z_dat = np.lib.format.open_memmap(pathZ, mode='w+', dtype=np.dtype(dtype), shape=(n_utt, M)) \
+        if pathZ is not None else None
+    f_dat = np.lib.format.open_memmap(pathF, mode='w+', dtype=np.dtype(dtype), shape=(n_utt, M * D)) \
+        if pathF is not None else None
+    d_sad = None
+    if sad is not None:
+      assert sad.shape[0] == frames.n
+      d_sad_all = torch.from_numpy((np.asarray(sad).reshape(-1) != 0).astype(np.uint8)).cuda()
+    names = []
+    Zs, Fs = [], []
+    for b0 in range(0, n_utt, utt_batch):
+      batch = indices[b0:b0 + utt_batch]
+      lo, hi = int(batch[0][1][0]), max(int(e) for _, (_, e) in batch)
+      if resident:
+        dev = frames.resident[lo:hi]
+      else:
+        dev = torch.from_numpy(np.ascontiguousarray(frames.host[lo:hi], dtype=np.float32)).cuda()
+      # utterances may leave gaps: build offsets per utterance pair (start,end) via a mask
+      starts = np.array([int(s) - lo for _, (s, _) in batch], dtype=np.int64)
+      ends = np.array([int(e) - lo for _, (_, e) in batch], dtype=np.int64)
+      contiguous = np.all(starts[1:] == ends[:-1])
+      if sad is not None:
+        d_sad = d_sad_all[lo:hi]
+      if contiguous:
+        off = np.concatenate([starts, ends[-1:]])
+        Z, Fh = self._utt_stats_device(dev, d_sad, off)
+      else:
+        zs, fs = zip(*[self._utt_stats_device(dev, d_sad, np.array([s, e], dtype=np.int64))
+                       for s, e in zip(starts, ends)])
+        Z, Fh = torch.cat(zs, 0), torch.cat(fs, 0)
+      Z, Fh = Z.cpu().numpy(), Fh.cpu().numpy()
+      if z_dat is not None:
+        z_dat[b0:b0 + len(batch)] = Z
+      if f_dat is not None:
+        f_dat[b0:b0 + len(batch)] = Fh
+      if z_dat is None and f_dat is None:
+        Zs.append(Z)
+        Fs.append(Fh)
+      names += [n for n, _ in batch]
+    for d in (z_dat, f_dat):
+      if d is not None:
+        d.flush()
+    if isinstance(name_path, str):
+      np.savetxt(fname=name_path, X=names, fmt='%s')
+    if z_dat is None and f_dat is None:
+      self.last_utt_stats_ = (np.concatenate(Zs, 0), np.concatenate(Fs, 0))
+    return names

@@ -1,0 +1,556 @@
+"""Speech extractors with the constructor surface of ``odin.preprocessing.speech``
+(reference: speech.py:345-1756) executed as ONE fused, batched CUDA path.
+
+Every class keeps the reference's keyword arguments and feature-name wiring so
+recipe code builds the same pipeline; ``plan_fusion`` (called by
+``make_pipeline``) replaces the run
+
+  [AudioReader] [PreEmphasis] STFTExtractor PowerSpecExtractor MelsSpecExtractor
+  [MFCCsExtractor [DeltaExtractor]] [SADgmm | SADthreshold] [ApplyingSAD]
+
+by a ``FusedSpeechFrontEnd`` step which launches ``odin_fe_run`` /
+``odin_fe_compact`` over a ragged batch of utterances.  Intermediate spectra
+('stft', 'spec') are never materialised (they stay in shared memory), and 'raw'
+is passed through untouched; everything downstream ('stft_energy', 'mspec',
+'mfcc', 'mfcc_energy', 'sad', 'sad_threshold') carries the reference's names.
+Outputs are float32 (the reference's chained extractors return float64 for
+mspec/mfcc; recipes cast to float16 right after).
+
+A stand-alone speech extractor has no CPU implementation here and raises.
+"""
+import ctypes
+import os
+import wave
+from collections.abc import Mapping
+from numbers import Number
+
+import numpy as np
+
+from .. import _lib
+from .base import (DeltaExtractor, Extractor, ExtractorSignal, as_tuple)
+
+
+def _extract_frame_step_length(sr, frame_length, step_length):
+  """speech.py:207-220."""
+  if frame_length < 1.:
+    frame_length = int(sr * frame_length)
+  else:
+    frame_length = int(frame_length)
+  if step_length is None:
+    step_length = frame_length // 4
+  elif step_length < 1.:
+    step_length = int(sr * step_length)
+  else:
+    step_length = int(step_length)
+  return frame_length, step_length
+
+
+def _no_cpu(cls):
+  raise NotImplementedError(
+      "%s has no stand-alone implementation: build the chain with make_pipeline so it runs "
+      "fused on the GPU (odin_b200 has no CPU fallback)" % cls.__class__.__name__)
+
+
+def read_wav(path):
+  """16-bit PCM wav -> (int16 array [n] or [n, ch], sr).  (The reference decodes
+  through soundfile/sox, speech.py:127-170; only plain PCM is handled here.)"""
+  with wave.open(path, 'rb') as f:
+    if f.getsampwidth() != 2:
+      raise ValueError("only 16-bit PCM wav is supported: %s" % path)
+    sr, ch, n = f.getframerate(), f.getnchannels(), f.getnframes()
+    raw = np.frombuffer(f.readframes(n), dtype='<i2')
+  return (raw.reshape(-1, ch) if ch > 1 else raw), sr
+
+
+class AudioReader(Extractor):
+  """speech.py:345-491 -> {'raw', 'sr', 'duration', 'path'[, 'name']}.
+  DC removal (``remove_dc``) is applied inside the fused kernels."""
+
+  def __init__(self, sr=None, sr_new=None, best_resample=True, remove_dc=True, dataset=None):
+    super(AudioReader, self).__init__(is_input_layer=True)
+    self.sr = sr
+    self.sr_new = sr_new
+    self.best_resample = best_resample
+    self.remove_dc = bool(remove_dc)
+    self.dataset = dataset
+    if sr_new is not None:
+      raise NotImplementedError("resampling (sr_new) is outside the accelerated path")
+
+  def _load(self, path_or_array):
+    raw = sr = name = path = None
+    channel = None
+    if isinstance(path_or_array, Mapping):
+      if 'sr' in path_or_array:
+        sr = int(path_or_array['sr'])
+      if 'channel' in path_or_array:
+        channel = int(path_or_array['channel'])
+      if 'name' in path_or_array:
+        name = path_or_array['name']
+      if 'raw' in path_or_array:
+        raw = path_or_array['raw']
+      elif 'path' in path_or_array:
+        path = str(path_or_array['path'])
+        raw, sr = read_wav(path)
+      else:
+        raise ValueError('`path_or_array` can be a dictionary, contains following key: sr, raw, path.')
+    elif isinstance(path_or_array, str):
+      path = path_or_array
+      if not os.path.isfile(path):
+        raise ValueError("Cannot locate file at path: %s" % path_or_array)
+      raw, sr = read_wav(path)
+    elif isinstance(path_or_array, (tuple, list)) and len(path_or_array) == 2:
+      raw, sr = path_or_array
+      if isinstance(raw, str):
+        path = raw
+        raw, sr2 = read_wav(raw)
+        sr = sr2 if sr is None else sr
+    elif isinstance(path_or_array, np.ndarray):
+      raw = path_or_array
+    else:
+      raise ValueError("`path_or_array` can be: list, tuple, Mapping, string. But given: %s" %
+                       str(type(path_or_array)))
+    raw = np.asarray(raw)
+    if raw.ndim == 2:
+      if raw.shape[0] == 2:
+        raw = raw.T
+      if channel is not None:
+        raw = raw[:, channel]
+    if raw.ndim != 1:
+      raise ValueError("No support for %d-D signal from file: %s (select a `channel`)" % (raw.ndim, path))
+    if sr is None and self.sr is not None:
+      sr = int(self.sr)
+    ret = {'raw': raw, 'sr': sr, 'duration': (max(raw.shape) / sr) if sr is not None else None,
+           'path': os.path.abspath(path) if path is not None else None}
+    if name is not None:
+      ret['name'] = name
+    return ret
+
+  def _transform(self, X):
+    return self._load(X)
+
+
+class PreEmphasis(Extractor):
+  """speech.py:540-563."""
+
+  def __init__(self, coeff=0.97, input_name='raw', output_name='raw'):
+    super(PreEmphasis, self).__init__(input_name=str(input_name), output_name=str(output_name))
+    assert 0. < coeff < 1.
+    self.coeff = float(coeff)
+
+  def _transform(self, X):
+    _no_cpu(self)
+
+
+class STFTExtractor(Extractor):
+  """speech.py:655-745."""
+
+  def __init__(self, frame_length=None, step_length=None, n_fft=512, window='hamm', padding=False,
+               energy=True, scale=None, input_name=('raw', 'sr'), output_name='stft'):
+    if isinstance(input_name, str):
+      input_name = (input_name, 'sr')
+    assert isinstance(output_name, str), "`output_name` must be string"
+    super(STFTExtractor, self).__init__(input_name=input_name, output_name=output_name)
+    self.frame_length = frame_length
+    self.step_length = step_length
+    self.n_fft = n_fft
+    self.window = window
+    self.padding = bool(padding)
+    self.energy = bool(energy)
+    assert isinstance(scale, (str, Number, type(None)))
+    self.scale = scale
+
+  def _transform(self, X):
+    _no_cpu(self)
+
+
+class PowerSpecExtractor(Extractor):
+  """speech.py:748-763."""
+
+  def __init__(self, power=2.0, input_name='stft', output_name='spec'):
+    super(PowerSpecExtractor, self).__init__(input_name=input_name, output_name=output_name)
+    self.power = float(power)
+
+  def _transform(self, X):
+    _no_cpu(self)
+
+
+class MelsSpecExtractor(Extractor):
+  """speech.py:766-802."""
+
+  def __init__(self, n_mels, fmin=64, fmax=None, top_db=80.0, input_name=('spec', 'sr'),
+               output_name='mspec'):
+    if isinstance(input_name, str):
+      input_name = (input_name, 'sr')
+    super(MelsSpecExtractor, self).__init__(input_name=input_name, output_name=output_name)
+    self.n_mels = int(n_mels)
+    self.fmin = fmin
+    self.fmax = fmax
+    self.top_db = top_db
+
+  def _transform(self, X):
+    _no_cpu(self)
+
+
+class MFCCsExtractor(Extractor):
+  """speech.py:805-831."""
+
+  def __init__(self, n_ceps, remove_first_coef=True, first_coef_energy=False, input_name='mspec',
+               output_name='mfcc'):
+    super(MFCCsExtractor, self).__init__(input_name=input_name, output_name=output_name)
+    self.n_ceps = int(n_ceps)
+    self.remove_first_coef = bool(remove_first_coef)
+    self.first_coef_energy = bool(first_coef_energy)
+
+  def _transform(self, X):
+    _no_cpu(self)
+
+
+class SADthreshold(Extractor):
+  """speech.py:1335-1436."""
+
+  def __init__(self, energy_threshold=0.55, energy_mean_scale=0.5, frame_context=2,
+               proportion_threshold=0.12, smooth_window=5, input_name='energy', output_name='sad'):
+    super(SADthreshold, self).__init__(input_name=str(input_name), output_name=str(output_name))
+    self.energy_threshold = float(energy_threshold)
+    self.energy_mean_scale = float(energy_mean_scale)
+    self.proportion_threshold = float(proportion_threshold)
+    self.frame_context = int(frame_context)
+    self.smooth_window = int(smooth_window)
+    assert self.energy_mean_scale > 0, 'energy_mean_scale > 0, given: %.2f' % self.energy_mean_scale
+    assert self.frame_context >= 0, 'frame_context >= 0, given: %d' % self.frame_context
+    assert 0. < self.proportion_threshold < 1., \
+        '0 < proportion_threshold < 1, given: %.2f' % self.proportion_threshold
+
+  def _transform(self, X):
+    _no_cpu(self)
+
+
+class SADgmm(Extractor):
+  """speech.py:1439-1477."""
+
+  def __init__(self, nb_mixture=3, nb_train_it=24 + 1, smooth_window=3, input_name='energy',
+               output_name='sad'):
+    super(SADgmm, self).__init__(input_name=input_name, output_name=output_name)
+    self.nb_mixture = int(nb_mixture)
+    self.nb_train_it = int(nb_train_it)
+    self.smooth_window = int(smooth_window)
+
+  def _transform(self, X):
+    _no_cpu(self)
+
+
+class ApplyingSAD(Extractor):
+  """speech.py:1691-1756 (``threshold`` / ``smooth_window`` re-processing of a
+  continuous SAD is outside the accelerated path)."""
+
+  def __init__(self, input_name, output_name=None, sad_name='sad', threshold=None, smooth_window=None,
+               keep_unvoiced=False):
+    super(ApplyingSAD, self).__init__(input_name=as_tuple(input_name, t=str), output_name=output_name)
+    self.sad_name = str(sad_name)
+    if threshold is not None or smooth_window is not None:
+      raise NotImplementedError("ApplyingSAD(threshold=..., smooth_window=...) is not accelerated")
+    self.threshold = None
+    self.smooth_window = None
+    self.keep_unvoiced = bool(keep_unvoiced)
+
+  def _transform(self, X):
+    _no_cpu(self)
+
+
+# ---------------------------------------------------------------------------
+# fused execution
+# ---------------------------------------------------------------------------
+_WINDOWS = {'hann': 0, 'hanning': 0, 'hamm': 1, 'hamming': 1}
+
+
+class FusedSpeechFrontEnd(Extractor):
+  """The CUDA step standing in for a run of speech extractors (see module doc)."""
+
+  def __init__(self, reader, preemph, stft, power, mels, mfcc, delta, sad, apply_sad):
+    super(FusedSpeechFrontEnd, self).__init__(is_input_layer=reader is not None)
+    self.reader, self.preemph, self.stft, self.power = reader, preemph, stft, power
+    self.mels, self.mfcc, self.delta, self.sad, self.apply_sad = mels, mfcc, delta, sad, apply_sad
+    self._handles = {}
+    self._validate()
+
+  def _validate(self):
+    st, pw, ml, mf, dl, sd, ap = (self.stft, self.power, self.mels, self.mfcc, self.delta, self.sad,
+                                  self.apply_sad)
+    if st.window not in _WINDOWS:
+      raise NotImplementedError("window %r is not accelerated (hann / hamm only)" % (st.window,))
+    if st.padding or st.scale is not None or st.frame_length is None:
+      raise NotImplementedError("STFTExtractor(padding / scale / pre-framed input) is not accelerated")
+    if int(pw.power) != 2:
+      raise NotImplementedError("PowerSpecExtractor(power != 2) is not accelerated")
+    if pw.input_name != st.output_name or ml.input_name[0] != pw.output_name:
+      raise ValueError("feature names of STFT -> PowerSpec -> MelsSpec do not chain")
+    if self.preemph is not None and (self.preemph.input_name != st.input_name[0] or
+                                     self.preemph.output_name != st.input_name[0]):
+      raise ValueError("PreEmphasis must read and write the STFT input feature")
+    if mf is not None:
+      if mf.input_name != ml.output_name:
+        raise ValueError("MFCCsExtractor must read the MelsSpecExtractor output")
+      if not mf.remove_first_coef:
+        raise NotImplementedError("MFCCsExtractor(remove_first_coef=False) is not accelerated")
+    if dl is not None:
+      if mf is None or dl.input_name != (mf.output_name,) or dl.axis != 0:
+        raise NotImplementedError("DeltaExtractor is accelerated on the MFCC feature (axis=0) only")
+      if dl.order not in ((0,), (0, 1), (0, 1, 2)):
+        raise NotImplementedError("DeltaExtractor order must be (0,), (0,1) or (0,1,2)")
+    if sd is not None:
+      if isinstance(sd, SADgmm):
+        if sd.input_name != '%s_energy' % st.output_name or not st.energy:
+          raise NotImplementedError("SADgmm is accelerated on the STFT frame energy ('%s_energy')" %
+                                    st.output_name)
+      else:
+        if mf is None or not mf.first_coef_energy or sd.input_name != '%s_energy' % mf.output_name:
+          raise NotImplementedError("SADthreshold is accelerated on the first cepstral coefficient "
+                                    "('<mfcc>_energy', MFCCsExtractor(first_coef_energy=True))")
+    if ap is not None and (sd is None or ap.sad_name != sd.output_name):
+      raise ValueError("ApplyingSAD must use the SAD computed by the preceding SAD extractor")
+
+  # -- configuration ---------------------------------------------------------
+  def _config(self, sr):
+    st, ml, mf, dl, sd = self.stft, self.mels, self.mfcc, self.delta, self.sad
+    L, hop = _extract_frame_step_length(sr, st.frame_length, st.step_length)
+    fmax = sr // 2 if ml.fmax is None else int(ml.fmax)  # signal.py:1672-1681
+    fmin = int(ml.fmin)
+    if fmin >= fmax:
+      raise ValueError("fmin must < fmax, but fmin=%d and fmax=%d" % (fmin, fmax))
+    c = _lib.FeConfig()
+    c.sr, c.frame_len, c.hop, c.n_fft = int(sr), L, hop, int(st.n_fft)
+    c.window = _WINDOWS[st.window]
+    c.remove_dc = 1 if (self.reader is not None and self.reader.remove_dc) else 0
+    c.preemph = float(self.preemph.coeff) if self.preemph is not None else 0.0
+    c.n_mels, c.fmin, c.fmax = ml.n_mels, float(fmin), float(fmax)
+    c.top_db = -1.0 if ml.top_db is None else float(ml.top_db)
+    c.n_ceps = mf.n_ceps if mf is not None else 0
+    c.delta_width = dl.width if dl is not None else 9
+    c.delta_order = max(dl.order) if dl is not None else 0
+    c.vad_kind = 0 if sd is None else (1 if isinstance(sd, SADgmm) else 2)
+    c.vad_nmix = sd.nb_mixture if isinstance(sd, SADgmm) else 3
+    c.vad_iters = sd.nb_train_it if isinstance(sd, SADgmm) else 25
+    c.vad_smooth = sd.smooth_window if sd is not None else 0
+    c.vad_mode = 2.0  # signal.VAD_MODE_STANDARD
+    if isinstance(sd, SADthreshold):
+      c.thr_energy, c.thr_mean_scale = sd.energy_threshold, sd.energy_mean_scale
+      c.thr_proportion, c.thr_context = sd.proportion_threshold, sd.frame_context
+    return c
+
+  def _handle(self, sr):
+    if sr not in self._handles:
+      _lib.require_cuda()
+      lib = _lib.load()
+      cfg = self._config(sr)
+      h = ctypes.c_void_p()
+      _lib.check(lib.odin_fe_create(ctypes.byref(cfg), ctypes.byref(h)))
+      self._handles[sr] = (h, cfg)
+    return self._handles[sr]
+
+  def __del__(self):
+    try:
+      lib = _lib.load()
+      for h, _ in self._handles.values():
+        lib.odin_fe_destroy(h)
+      self._handles = {}
+    except Exception:
+      pass
+
+  # -- device run over packed PCM ---------------------------------------------
+  def run_packed(self, d_pcm, sample_offsets, sr, want=('mspec', 'feat', 'energy', 'c0', 'sad')):
+    """d_pcm: CUDA tensor int16 / float32 [sum n]; sample_offsets: int64 numpy
+    [n_utt+1].  Returns dict of CUDA tensors + 'frame_offsets' (numpy)."""
+    import torch
+    lib = _lib.load()
+    h, cfg = self._handle(int(sr))
+    n_utt = len(sample_offsets) - 1
+    so = np.ascontiguousarray(sample_offsets, dtype=np.int64)
+    fo = np.zeros(n_utt + 1, dtype=np.int64)
+    _lib.check(lib.odin_host_frame_offsets(cfg.frame_len, cfg.hop, _lib.as_i64_ptr(so), n_utt,
+                                           _lib.as_i64_ptr(fo)))
+    T = int(fo[-1])
+    fd = cfg.n_ceps * (1 + cfg.delta_order)
+    dev = d_pcm.device
+    out = {'frame_offsets': fo}
+    out['mspec'] = torch.empty((T, cfg.n_mels), dtype=torch.float32, device=dev)
+    out['feat'] = torch.empty((T, fd), dtype=torch.float32, device=dev) if fd > 0 and 'feat' in want else None
+    need_energy = ('energy' in want) or cfg.vad_kind == 1
+    out['energy'] = torch.empty(T, dtype=torch.float32, device=dev) if need_energy else None
+    need_c0 = cfg.n_ceps > 0 and (('c0' in want) or cfg.vad_kind == 2)
+    out['c0'] = torch.empty(T, dtype=torch.float32, device=dev) if need_c0 else None
+    has_sad = cfg.vad_kind != 0 and 'sad' in want
+    out['sad'] = torch.empty(T, dtype=torch.uint8, device=dev) if has_sad else None
+    out['sad_thr'] = torch.empty(n_utt, dtype=torch.float64, device=dev) if has_sad else None
+    if d_pcm.dtype == torch.int16:
+      pcm_dtype = 0
+    elif d_pcm.dtype == torch.float32:
+      pcm_dtype = 1
+    else:
+      raise ValueError("PCM must be int16 or float32")
+    _lib.check(lib.odin_fe_run(h, _lib.ptr(d_pcm), pcm_dtype, _lib.as_i64_ptr(so), n_utt,
+                               _lib.ptr(out['mspec']), _lib.ptr(out['feat']), _lib.ptr(out['energy']),
+                               _lib.ptr(out['c0']), _lib.ptr(out['sad']), _lib.ptr(out['sad_thr']),
+                               _lib.current_stream()))
+    return out
+
+  def compact(self, sr, d_sad, frame_offsets, d_feat, keep_unvoiced=False):
+    """ApplyingSAD on device -> (rows CUDA tensor [T, dim] (first n valid), offsets CUDA int64)."""
+    import torch
+    lib = _lib.load()
+    h, _ = self._handle(int(sr))
+    n_utt = len(frame_offsets) - 1
+    fo = np.ascontiguousarray(frame_offsets, dtype=np.int64)
+    out = torch.empty_like(d_feat)
+    off = torch.empty(n_utt + 1, dtype=torch.int64, device=d_feat.device)
+    _lib.check(lib.odin_fe_compact(h, _lib.ptr(d_sad), _lib.as_i64_ptr(fo), n_utt, _lib.ptr(d_feat),
+                                   int(d_feat.shape[1]), 1 if keep_unvoiced else 0, _lib.ptr(out),
+                                   _lib.ptr(off), _lib.current_stream()))
+    return out, off
+
+  # -- Extractor interface ---------------------------------------------------
+  def transform(self, X):
+    return self.transform_batch([X])[0]
+
+  def transform_batch(self, Xs):
+    _lib.require_cuda()
+    import torch
+    results = [None] * len(Xs)
+    loaded = {}
+    for i, X in enumerate(Xs):
+      sig = self._check_input(X)
+      if sig is not None:
+        results[i] = sig
+        continue
+      try:
+        d = self.reader._load(X) if self.reader is not None else X
+        raw_name, sr_name = self.stft.input_name
+        if raw_name not in d or sr_name not in d or d[sr_name] is None:
+          results[i] = ExtractorSignal().set_message(
+              self, "Cannot find features with name: %s / %s" % (raw_name, sr_name), X).set_action('error')
+          continue
+        raw = np.asarray(d[raw_name])
+        if raw.ndim != 1:
+          raise ValueError("Only 1-D signals are accelerated, given shape: %s" % str(raw.shape))
+        L, _ = _extract_frame_step_length(int(d[sr_name]), self.stft.frame_length, self.stft.step_length)
+        if raw.shape[0] < L:
+          raise ValueError("signal (%d samples) shorter than one frame (%d)" % (raw.shape[0], L))
+        loaded[i] = (d, raw, int(d[sr_name]))
+      except Exception as e:  # the reference's workers turn exceptions into signals (processor.py:656-671)
+        results[i] = ExtractorSignal().set_message(self, "%s: %s" % (type(e).__name__, e),
+                                                   X).set_action(self.robust_level)
+    # one ragged batch per (sample rate, dtype)
+    groups = {}
+    for i, (d, raw, sr) in loaded.items():
+      kind = 'i2' if raw.dtype == np.int16 else 'f4'
+      groups.setdefault((sr, kind), []).append(i)
+    for (sr, kind), idxs in groups.items():
+      raws = [loaded[i][1] if kind == 'i2' else loaded[i][1].astype(np.float32) for i in idxs]
+      off = np.zeros(len(raws) + 1, dtype=np.int64)
+      np.cumsum([len(r) for r in raws], out=off[1:])
+      pcm = torch.from_numpy(np.concatenate(raws)).pin_memory().cuda(non_blocking=True)
+      out = self.run_packed(pcm, off, sr)
+      fo = out['frame_offsets']
+      comp = None
+      if self.apply_sad is not None:
+        comp = {}
+        for name in self.apply_sad.input_name:
+          src = self._device_feature(out, name)
+          if src is None:
+            raise ValueError("ApplyingSAD: feature %r is not produced by the fused front-end" % name)
+          rows, coff = self.compact(sr, out['sad'], fo, src, self.apply_sad.keep_unvoiced)
+          comp[name] = (rows.cpu().numpy(), coff.cpu().numpy())
+      host = {k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in out.items()}
+      for j, i in enumerate(idxs):
+        results[i] = self._emit(loaded[i][0], Xs[i], host, comp, j, int(fo[j]), int(fo[j + 1]))
+    return results
+
+  def _device_feature(self, out, name):
+    if self.mfcc is not None and name == self._mfcc_out_name():
+      return out['feat']
+    if name == self.mels.output_name:
+      return out['mspec']
+    return None
+
+  def _mfcc_out_name(self):
+    if self.delta is not None:
+      on = self.delta.output_name
+      return on[0] if isinstance(on, tuple) else on
+    return self.mfcc.output_name
+
+  def _emit(self, base, X, host, comp, j, s, e):
+    y = dict(base) if self.reader is not None else {}
+    st, ml, mf, sd, ap = self.stft, self.mels, self.mfcc, self.sad, self.apply_sad
+    if st.energy and host.get('energy') is not None:
+      y['%s_energy' % st.output_name] = host['energy'][s:e, None].copy()
+    y[ml.output_name] = host['mspec'][s:e].copy()
+    if mf is not None:
+      feat = host['feat'][s:e]
+      if self.delta is None:
+        y[mf.output_name] = feat.copy()
+      else:
+        y[mf.output_name] = feat[:, :mf.n_ceps].copy()
+        y[self._mfcc_out_name()] = feat.copy()
+      if mf.first_coef_energy:
+        y['%s_energy' % mf.output_name] = host['c0'][s:e].copy()
+    if sd is not None:
+      sad = host['sad'][s:e]
+      y[sd.output_name] = sad.copy() if isinstance(sd, SADgmm) else sad.astype(bool)
+      y['%s_threshold' % sd.output_name] = float(host['sad_thr'][j])
+    if ap is not None:
+      names = as_tuple(ap.output_name, t=str)
+      for name, oname in zip(ap.input_name, names):
+        rows, coff = comp[name]
+        a, b = int(coff[j]), int(coff[j + 1])
+        if b - a == 0:  # speech.py:1739-1741: file dropped
+          return ExtractorSignal().set_message(ap, "`None` value is returned by the extractor: ApplyingSAD",
+                                               X).set_action(ap.robust_level)
+        y[oname] = rows[a:b].copy()
+    return self._merge_output(X if isinstance(X, Mapping) else None, y)
+
+
+def plan_fusion(extractors):
+  """Groups a flat list of extractors into execution steps, fusing the speech run."""
+  plan, i, n = [], 0, len(extractors)
+  speech_types = (PreEmphasis, STFTExtractor, PowerSpecExtractor, MelsSpecExtractor, MFCCsExtractor,
+                  SADgmm, SADthreshold, ApplyingSAD)
+  while i < n:
+    e = extractors[i]
+    j = i
+    reader = preemph = None
+    if isinstance(extractors[j], AudioReader) and j + 1 < n and \
+        isinstance(extractors[j + 1], (PreEmphasis, STFTExtractor)):
+      reader = extractors[j]
+      j += 1
+    if j < n and isinstance(extractors[j], PreEmphasis):
+      preemph = extractors[j]
+      j += 1
+    if j + 2 < n and isinstance(extractors[j], STFTExtractor) and \
+        isinstance(extractors[j + 1], PowerSpecExtractor) and isinstance(extractors[j + 2], MelsSpecExtractor):
+      stft, power, mels = extractors[j:j + 3]
+      j += 3
+      mfcc = delta = sad = apply_sad = None
+      if j < n and isinstance(extractors[j], MFCCsExtractor):
+        mfcc = extractors[j]
+        j += 1
+      # Delta and SAD may come in either order
+      for _ in range(2):
+        if j < n and delta is None and mfcc is not None and isinstance(extractors[j], DeltaExtractor):
+          delta = extractors[j]
+          j += 1
+        elif j < n and sad is None and isinstance(extractors[j], (SADgmm, SADthreshold)):
+          sad = extractors[j]
+          j += 1
+      if j < n and sad is not None and isinstance(extractors[j], ApplyingSAD):
+        apply_sad = extractors[j]
+        j += 1
+      plan.append(FusedSpeechFrontEnd(reader, preemph, stft, power, mels, mfcc, delta, sad, apply_sad))
+      i = j
+      continue
+    if isinstance(e, speech_types) or isinstance(e, DeltaExtractor):
+      raise NotImplementedError(
+          "%s at position %d is not part of a fusable run "
+          "([AudioReader] [PreEmphasis] STFT PowerSpec MelsSpec [MFCCs [Delta]] [SAD] [ApplyingSAD]); "
+          "odin_b200 has no CPU fallback" % (e.__class__.__name__, i))
+    plan.append(e)
+    i += 1
+  return plan
