@@ -183,6 +183,14 @@ int odin_gmm_utt_stats(odin_gmm_t* g, const float* d_X, const uint8_t* d_sad,
 int odin_gmm_score(odin_gmm_t* g, const float* d_X, int64_t n_frames, float* d_llk, float* d_post,
                    float* d_logprob, void* stream);
 
+/* Device time of the kernels of the most recent call, measured with CUDA events
+ * recorded on the caller's stream around each kernel (blocks until they complete).
+ * odin_gmm_last_estep_ms: log-sum-exp kernel and statistics kernel of the last
+ * odin_gmm_estep; *impl_used = 1 (fp32) or 2 (tcgen05).
+ * odin_fe_last_run_ms: ms4 = {DC sums, frame kernel, utterance pass, VAD}. */
+int odin_gmm_last_estep_ms(odin_gmm_t* g, float* lse_ms, float* stats_ms, int32_t* impl_used);
+int odin_fe_last_run_ms(odin_fe_t* fe, float* ms4);
+
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t odin_launch_count(void);
 

@@ -237,6 +237,7 @@ void odin_fe_destroy(odin_fe_t* fe) {
   cudaFree(fe->d_taps); cudaFree(fe->d_sample_off); cudaFree(fe->d_dcsum); cudaFree(fe->d_umax);
   cudaFree(fe->d_cnt); cudaFree(fe->d_vad_scratch);
   if (fe->h_stage) cudaFreeHost(fe->h_stage);
+  for (int i = 0; i < 5; ++i) if (fe->ev[i]) cudaEventDestroy(fe->ev[i]);
   delete fe;
 }
 
@@ -383,6 +384,7 @@ void odin_gmm_destroy(odin_gmm_t* g) {
   cudaFree(g->d_mean); cudaFree(g->d_var); cudaFree(g->d_w); cudaFree(g->d_Wk); cudaFree(g->d_cst);
   cudaFree(g->d_Whi); cudaFree(g->d_Wlo); cudaFree(g->d_lse); cudaFree(g->d_prev); cudaFree(g->d_off);
   if (g->h_off) cudaFreeHost(g->h_off);
+  for (int i = 0; i < 3; ++i) if (g->ev[i]) cudaEventDestroy(g->ev[i]);
   delete g;
 }
 
@@ -423,12 +425,38 @@ int odin_gmm_estep(odin_gmm_t* g, const float* d_X, const uint8_t* d_sad, int64_
   if (rc) return rc;
   cudaStream_t st = as_stream(stream);
   if ((rc = gmm_reserve_lse(g, n_frames))) return rc;
-  if (tc) {
-    if ((rc = gmm_lse_tc(g, d_X, d_sad, n_frames, g->d_lse, d_stats, st))) return rc;
-    return gmm_stats_tc(g, d_X, d_sad, n_frames, g->d_lse, want_second, d_stats, st);
-  }
-  if ((rc = gmm_lse_ffma(g, d_X, d_sad, n_frames, g->d_lse, d_stats, st))) return rc;
-  return gmm_stats_ffma(g, d_X, d_sad, n_frames, g->d_lse, want_second, d_stats, st);
+  if (g->ev[0] == nullptr)
+    for (int i = 0; i < 3; ++i) ODIN_CUDA_CHECK(cudaEventCreate(&g->ev[i]));
+  ODIN_CUDA_CHECK(cudaEventRecord(g->ev[0], st));
+  if (tc) rc = gmm_lse_tc(g, d_X, d_sad, n_frames, g->d_lse, d_stats, st);
+  else rc = gmm_lse_ffma(g, d_X, d_sad, n_frames, g->d_lse, d_stats, st);
+  if (rc) return rc;
+  ODIN_CUDA_CHECK(cudaEventRecord(g->ev[1], st));
+  if (tc) rc = gmm_stats_tc(g, d_X, d_sad, n_frames, g->d_lse, want_second, d_stats, st);
+  else rc = gmm_stats_ffma(g, d_X, d_sad, n_frames, g->d_lse, want_second, d_stats, st);
+  if (rc) return rc;
+  ODIN_CUDA_CHECK(cudaEventRecord(g->ev[2], st));
+  g->ev_valid = true;
+  g->last_impl = tc ? 2 : 1;
+  return ODIN_OK;
+}
+
+int odin_gmm_last_estep_ms(odin_gmm_t* g, float* lse_ms, float* stats_ms, int32_t* impl_used) {
+  if (!g || !lse_ms || !stats_ms) return set_error(ODIN_EINVAL, "null argument");
+  if (!g->ev_valid) return set_error(ODIN_EINVAL, "no E-step has been recorded");
+  ODIN_CUDA_CHECK(cudaEventSynchronize(g->ev[2]));
+  ODIN_CUDA_CHECK(cudaEventElapsedTime(lse_ms, g->ev[0], g->ev[1]));
+  ODIN_CUDA_CHECK(cudaEventElapsedTime(stats_ms, g->ev[1], g->ev[2]));
+  if (impl_used) *impl_used = g->last_impl;
+  return ODIN_OK;
+}
+
+int odin_fe_last_run_ms(odin_fe_t* fe, float* ms4) {
+  if (!fe || !ms4) return set_error(ODIN_EINVAL, "null argument");
+  if (!fe->ev_valid) return set_error(ODIN_EINVAL, "no run has been recorded");
+  ODIN_CUDA_CHECK(cudaEventSynchronize(fe->ev[4]));
+  for (int i = 0; i < 4; ++i) ODIN_CUDA_CHECK(cudaEventElapsedTime(ms4 + i, fe->ev[i], fe->ev[i + 1]));
+  return ODIN_OK;
 }
 
 int odin_gmm_mstep(odin_gmm_t* g, const double* d_stats, int32_t allow_rollback, float* d_mean, float* d_var,

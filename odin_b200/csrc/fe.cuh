@@ -36,6 +36,9 @@ struct odin_fe {
   int64_t* d_cnt = nullptr;    // [cap+1] compaction counts / offsets
   float* d_vad_scratch = nullptr;  // [frames] standardised energies
   int64_t vad_scratch_cap = 0;
+  // events bracketing dc | frame | post | vad kernels of the most recent run (odin_fe_last_run_ms)
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool ev_valid = false;
   // host copies of the tables (tests, debugging)
   std::vector<double> h_win;
   std::vector<double> h_mel;   // dense [n_mels, nbins]

@@ -768,6 +768,9 @@ int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t 
               double* d_sad_thr, cudaStream_t st) {
   const odin_fe_config& c = fe->cfg;
   if (total_frames <= 0) return ODIN_OK;
+  if (fe->ev[0] == nullptr)
+    for (int i = 0; i < 5; ++i) ODIN_CUDA_CHECK(cudaEventCreate(&fe->ev[i]));
+  ODIN_CUDA_CHECK(cudaEventRecord(fe->ev[0], st));
   // 1. DC sums
   if (c.remove_dc) {
     ODIN_CUDA_CHECK(cudaMemsetAsync(fe->d_dcsum, 0, sizeof(double) * n_utt, st));
@@ -784,6 +787,7 @@ int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t 
                                                           max_chunks, fe->d_dcsum);
     ODIN_LAUNCH_CHECK("fe_dc_kernel");
   }
+  ODIN_CUDA_CHECK(cudaEventRecord(fe->ev[1], st));
   // 2. frame kernel
   {
     // 0x80808080 decodes (ordered_to_float) to about -3.4e38: below any log-mel value
@@ -799,6 +803,7 @@ int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t 
                               : dispatch_frame<float, float>(fe->N, a, st);
     if (rc) return rc;
   }
+  ODIN_CUDA_CHECK(cudaEventRecord(fe->ev[2], st));
   // 3. utterance pass
   {
     PostArgs p{};
@@ -817,6 +822,7 @@ int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t 
     fe_post_kernel<<<(unsigned)n_tiles2, 256, smem, st>>>(p);
     ODIN_LAUNCH_CHECK("fe_post_kernel");
   }
+  ODIN_CUDA_CHECK(cudaEventRecord(fe->ev[3], st));
   // 4. VAD
   if (c.vad_kind != 0 && d_sad != nullptr) {
     VadArgs v{};
@@ -846,6 +852,8 @@ int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t 
       ODIN_LAUNCH_CHECK("fe_vad_thr_kernel");
     }
   }
+  ODIN_CUDA_CHECK(cudaEventRecord(fe->ev[4], st));
+  fe->ev_valid = true;
   return ODIN_OK;
 }
 

@@ -33,6 +33,10 @@ struct odin_gmm {
   int64_t* h_off = nullptr;
   int64_t* d_off = nullptr;
   int64_t off_cap = 0;
+  // events bracketing the two kernels of the most recent E-step (odin_gmm_last_estep_ms)
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  bool ev_valid = false;
+  int last_impl = 0;
 };
 
 namespace odin {

@@ -51,6 +51,7 @@ class _DeviceFrames(object):
   H2D copy of chunk i+1 overlaps the E-step of chunk i."""
 
   def __init__(self, X, chunk_frames=1 << 20):
+    _lib.require_cuda()
     torch = _torch()
     self.torch = torch
     self.resident = None
@@ -69,6 +70,9 @@ class _DeviceFrames(object):
       self.host = X
     self.n, self.dim = (self.resident.shape if self.resident is not None else self.host.shape)
     self.chunk = int(chunk_frames)
+
+  shape = property(lambda self: (self.n, self.dim))
+  ndim = 2
 
   def cache_on_device(self, reserve_bytes=2 << 30):
     """Upload once if it fits (used by fit(): EM re-reads the data every iteration)."""

@@ -1,0 +1,208 @@
+"""CPU: the C-ABI library loads and exports every declared symbol; the host
+mirrors of the device integer / float32 logic agree with numpy and the oracle;
+the Extractor contract behaves like the reference's (base.py:291-357)."""
+import ctypes as C
+import os
+import pickle
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from odin_b200 import _lib
+from odin_b200 import preprocessing as pp
+from odin_b200.ml import GMM
+from oracle import frontend as F
+
+
+@pytest.fixture(scope="module")
+def lib():
+  return _lib.load()
+
+
+def test_library_exports_every_header_symbol(lib):
+  header = open(os.path.join(ROOT, "include", "odin_b200.h")).read()
+  declared = set(re.findall(r"\b(odin_[a-z0-9_]+)\s*\(", header))
+  declared -= {"odin_fe_config"}
+  assert len(declared) >= 20
+  for name in sorted(declared):
+    assert hasattr(lib, name), "missing export %s" % name
+    assert name in _lib.SIGNATURES, "no ctypes signature for %s" % name
+  assert lib.odin_version() >= 1
+
+
+def test_no_device_fails_loudly(lib):
+  import torch
+  if torch.cuda.is_available():
+    pytest.skip("CUDA present")
+  h = C.c_void_p()
+  rc = lib.odin_gmm_create(60, 64, C.byref(h))
+  assert rc == _lib.ODIN_ENODEVICE
+  assert b"no CPU fallback" in lib.odin_last_error()
+  with pytest.raises(_lib.OdinError):
+    GMM(4).fit(np.zeros((10, 3), dtype=np.float32))
+  pipe = pp.make_pipeline([pp.AudioReader(), pp.STFTExtractor(0.025, 0.01), pp.PowerSpecExtractor(),
+                           pp.MelsSpecExtractor(24)])
+  with pytest.raises(_lib.OdinError):
+    pipe.transform({"raw": np.zeros(8000, dtype=np.int16), "sr": 8000})
+
+
+def test_frame_offsets_integer_exact(lib):
+  rng = np.random.RandomState(0)
+  for L, hop in ((400, 160), (200, 40), (512, 128), (400, 400)):
+    lens = np.concatenate([[L, L + 1, L + hop - 1, L + hop, 10 * L + 7], rng.randint(L, 200000, size=50)])
+    so = np.zeros(len(lens) + 1, dtype=np.int64)
+    np.cumsum(lens, out=so[1:])
+    fo = np.zeros_like(so)
+    assert lib.odin_host_frame_offsets(L, hop, _lib.as_i64_ptr(so), len(lens), _lib.as_i64_ptr(fo)) == 0
+    want = [F.num_frames(int(n), L, hop) for n in lens]
+    assert list(np.diff(fo)) == want == [1 + (int(n) - L) // hop for n in lens]
+  so = np.array([0, 399, 1000], dtype=np.int64)
+  fo = np.zeros(3, dtype=np.int64)
+  assert lib.odin_host_frame_offsets(400, 160, _lib.as_i64_ptr(so), 2, _lib.as_i64_ptr(fo)) == _lib.ODIN_ESHORT
+  assert list(fo) == [0, 0, 2]
+
+
+def _host_smooth(lib, x, win, wrap):
+  x = np.ascontiguousarray(x, dtype=np.uint8)
+  out = np.zeros_like(x)
+  p = C.POINTER(C.c_uint8)
+  assert lib.odin_host_smooth(x.ctypes.data_as(p), len(x), win, wrap, out.ctypes.data_as(p)) == 0
+  return out
+
+
+def test_smooth_matches_oracle_exhaustively(lib):
+  """signal.py:969-1000: every 0/1 sequence of length 5..11 for win 3 and 5, bool and
+  uint8-wrapping routes, plus random long ones and other windows."""
+  for n in range(5, 12):
+    for code in range(2**n):
+      x = np.array([(code >> i) & 1 for i in range(n)], dtype=np.uint8)
+      for win in (3, 5):
+        thr = 2.0 / win
+        assert np.array_equal(_host_smooth(lib, x, win, 0), F.smooth_flat(x.astype(bool), win) >= thr)
+        assert np.array_equal(_host_smooth(lib, x, win, 1), F.smooth_flat(x, win) >= thr)
+  rng = np.random.RandomState(1)
+  for win in (3, 4, 5, 7, 9):
+    for _ in range(20):
+      x = (rng.rand(rng.randint(win, 300)) < rng.rand()).astype(np.uint8)
+      thr = 2.0 / win
+      assert np.array_equal(_host_smooth(lib, x, win, 0), F.smooth_flat(x.astype(bool), win) >= thr)
+      assert np.array_equal(_host_smooth(lib, x, win, 1), F.smooth_flat(x, win) >= thr)
+  g = np.load(os.path.join(ROOT, "tests", "golden", "smooth.npz"))  # the REAL reference smooth()
+  for i in range(int(g["n"])):
+    assert np.array_equal(_host_smooth(lib, g["x%d" % i], 3, 0), g["bool3_%d" % i])
+    assert np.array_equal(_host_smooth(lib, g["x%d" % i], 5, 1), g["u8_5_%d" % i])
+
+
+def test_mean_std_bit_exact_with_numpy(lib):
+  """signal.py:305 standardises with np.mean/np.std on float32: numpy's pairwise sum."""
+  rng = np.random.RandomState(2)
+  pf = C.POINTER(C.c_float)
+  for n in list(range(1, 40)) + [127, 128, 129, 255, 256, 257, 298, 1000, 1023, 4097, 18001, 60000]:
+    e = (rng.randn(n) * 3 + 14).astype(np.float32)
+    m, s = C.c_float(), C.c_float()
+    assert lib.odin_host_mean_std_f32(e.ctypes.data_as(pf), n, C.byref(m), C.byref(s)) == 0
+    assert np.float32(m.value) == np.mean(e), n
+    assert np.float32(s.value) == np.std(e), n
+
+
+# ---------------------------------------------------------------------------
+# Extractor contract (base.py:291-357)
+# ---------------------------------------------------------------------------
+class _Double(pp.Extractor):
+
+  def __init__(self, input_name="x", output_name="y"):
+    super(_Double, self).__init__(input_name=input_name, output_name=output_name)
+
+  def _transform(self, X):
+    return X[self.input_name] * 2
+
+
+def test_extractor_contract():
+  e = _Double()
+  out = e.transform({"x": np.arange(3), "keep": 7})
+  assert set(out) == {"x", "y", "keep"} and list(out["y"]) == [0, 2, 4]      # merge keeps old keys
+  sig = e.transform({"z": 1})                                              # missing input name -> error signal
+  assert isinstance(sig, pp.ExtractorSignal) and sig.action == "error"
+  assert e.transform(sig) is sig                                             # signals pass through
+  assert isinstance(e.transform(None), pp.ExtractorSignal)                   # None -> signal (robust level)
+  assert e.transform(None).action == "ignore"
+  assert isinstance(e.transform([1, 2]), pp.ExtractorSignal)                 # non-dict on a non-input layer
+
+  class _Upper(pp.Extractor):
+
+    def _transform(self, X):
+      return {"Bad": 1}
+
+  assert _Upper().transform({"a": 1}).action == "error"                      # upper-case names rejected
+
+  class _Tup(pp.Extractor):
+
+    def __init__(self):
+      super(_Tup, self).__init__(input_name="x", output_name=("a", "b"))
+
+    def _transform(self, X):
+      return (1, None)
+
+  out = _Tup().transform({"x": 0})
+  assert out["a"] == 1 and "b" not in out                                    # None values dropped
+  assert pp.DeleteFeatures(["x"]).transform({"x": 1, "y": 2}) == {"y": 2}
+  assert pp.RenameFeatures("x", "z").transform({"x": 1}) == {"z": 1}
+  assert pp.DuplicateFeatures("x", "z").transform({"x": 1}) == {"x": 1, "z": 1}
+  out = pp.AsType("float16").transform({"mfcc": np.ones(3), "mfcc_sad": np.ones(3), "n": 3})
+  assert out["mfcc"].dtype == np.float16 and out["mfcc_sad"].dtype == np.float64
+  assert pp.speech._extract_frame_step_length(16000, 0.025, 0.010) == (400, 160)
+  assert pp.speech._extract_frame_step_length(8000, 0.025, 0.005) == (200, 40)
+  assert pp.speech._extract_frame_step_length(8000, 256, None) == (256, 64)
+
+
+def test_make_pipeline_and_fusion_plan():
+  steps = [pp.AudioReader(), pp.PreEmphasis(0.97), pp.STFTExtractor(0.025, 0.010, n_fft=512),
+           pp.PowerSpecExtractor(), pp.MelsSpecExtractor(40, fmin=64, fmax=8000),
+           pp.MFCCsExtractor(20, first_coef_energy=True), pp.DeltaExtractor("mfcc", order=(0, 1, 2)),
+           pp.SADgmm(input_name="stft_energy"), None, "junk", pp.DeleteFeatures(["raw"]), pp.AsType("float16")]
+  pipe = pp.make_pipeline(steps)
+  assert [n for n, _ in pipe.steps][:2] == ["AudioReader1", "PreEmphasis2"]      # base.py:112-121 naming
+  assert len(pipe.steps) == 10
+  assert [type(s).__name__ for s in pipe.plan] == ["FusedSpeechFrontEnd", "DeleteFeatures", "AsType"]
+  cfg = pipe.plan[0]._config(16000)
+  assert (cfg.frame_len, cfg.hop, cfg.n_fft, cfg.n_mels, cfg.n_ceps) == (400, 160, 512, 40, 20)
+  assert (cfg.delta_order, cfg.vad_kind, cfg.vad_smooth, cfg.window, cfg.remove_dc) == (2, 1, 3, 1, 1)
+  with pytest.raises(ValueError):
+    pp.make_pipeline([1, 2])
+  with pytest.raises(NotImplementedError):      # a lone speech extractor cannot run (no CPU fallback)
+    pp.make_pipeline([pp.PreEmphasis()])
+  with pytest.raises(NotImplementedError):
+    pp.PreEmphasis().transform({"raw": np.zeros(4)})
+  # FSDD recipe wiring (examples/fsdd_ivec.py:80-106): SADthreshold on the first cepstral coefficient
+  pipe = pp.make_pipeline([pp.AudioReader(), pp.PreEmphasis(), pp.STFTExtractor(0.025, 0.005, n_fft=512),
+                           pp.PowerSpecExtractor(), pp.MelsSpecExtractor(24, fmin=64, fmax=4000),
+                           pp.MFCCsExtractor(20, first_coef_energy=True),
+                           pp.SADthreshold(input_name="mfcc_energy"), pp.DeltaExtractor("mfcc", order=(0, 1, 2))])
+  cfg = pipe.plan[0]._config(8000)
+  assert (cfg.vad_kind, cfg.frame_len, cfg.hop, cfg.vad_smooth) == (2, 200, 40, 5)
+
+
+def test_gmm_host_surface():
+  g = GMM(nmix=8, nmix_start=1, niter=4, seed=7, name="ubm")
+  assert not g.is_initialized and not g.is_fitted and g.nmix == 8 and g.name == "ubm"
+  X = np.zeros((100, 60), dtype=np.float32)
+  g.initialize(X)
+  assert g.feat_dim == 60 and g.mean.shape == (60, 1) and g.sigma.shape == (60, 1) and g.w.shape == (1, 1)
+  assert g.batch_size_cpu == 52428 and g.batch_size_gpu == 109226          # gmm_tmat.py:602-607
+  g2 = pickle.loads(pickle.dumps(g))                                         # same 21-tuple state
+  assert len(g.__getstate__()) == 21
+  assert g2.feat_dim == 60 and g2.nmix == 8 and g2.name == "ubm" and np.array_equal(g2.sigma, g.sigma)
+  with pytest.raises(RuntimeError):
+    g.initialize(np.zeros((5, 3), dtype=np.float32))
+  # frame selection mask: indices + sad (gmm_tmat.py:162-164)
+  sad = np.ones(100, dtype=np.uint8)
+  sad[:10] = 0
+  m = g._selected_mask(100, sad, [("a", (5, 20)), ("b", (50, 60))])
+  assert int(m.sum()) == 10 + 10 and m[5:10].sum() == 0
+  assert g._selected_mask(100, None, None) is None
+  g.downsample = 4
+  m = g._selected_mask(200000, None, None)
+  assert 0 < int(m.sum()) < 200000 and m[:1].dtype == np.uint8
+  assert np.array_equal(m, g._selected_mask(200000, None, None))             # seeded => reproducible
