@@ -1,0 +1,436 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the accelerated path (see the driver contract).
+
+Metric (BASELINE.json): 2048-mix UBM Baum-Welch frames/s (+ MFCC frames/s in the
+`mfcc` object of the same JSON line) at N B200 vs the host CPU.
+
+One step = one EM iteration of the 2048-mix diagonal UBM over this rank's
+resident shard of frames: zero the statistics, E-step kernels (log-sum-exp +
+N/F/S accumulation), ONE all-reduce of the packed fp64 statistics over ranks
+(NCCL, N > 1), M-step kernel.  Weak scaling: every rank holds `--frames` frames.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+`--impl reference` times the reference's CPU implementation of the same step
+(the numpy restatement in oracle/gmm.py, float32-as-numpy-1 mode = the fastest
+mode of the reference, all BLAS threads) on a bounded sample, rank 0 only.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+D = 60
+NMIX = 2048
+
+
+def parse():
+  p = argparse.ArgumentParser()
+  p.add_argument("--gpus", type=int, default=1)
+  p.add_argument("--steps", type=int, default=5)
+  p.add_argument("--warmup", type=int, default=3)
+  p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+  p.add_argument("--frames", type=int, default=6_000_000, help="frames per GPU (60-dim fp32)")
+  p.add_argument("--nmix", type=int, default=NMIX)
+  p.add_argument("--kernel-impl", type=int, default=0, help="0 auto, 1 fp32 CUDA cores, 2 tcgen05")
+  p.add_argument("--mfcc-hours", type=float, default=2.0, help="hours of 16 kHz audio per GPU for the MFCC leg")
+  p.add_argument("--no-mfcc", action="store_true")
+  p.add_argument("--no-cpu-baseline", action="store_true")
+  p.add_argument("--cpu-sample", type=int, default=131072, help="frames in the CPU-baseline sample")
+  return p.parse_args()
+
+
+# ---------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------
+def measured_peaks():
+  path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  if os.path.isfile(path):
+    with open(path) as f:
+      d = json.load(f)
+    return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_burst=float(d["bf16_tflops"]),
+                bf16_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured")
+  return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+class ClockSampler(object):
+  """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+  Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+       "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+       "clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, gpu_index):
+    self.idx = gpu_index
+    self.rows = []
+    self.proc = None
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(
+          ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self.thread = threading.Thread(target=self._read, daemon=True)
+      self.thread.start()
+    except Exception:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.rows.append(line.strip())
+
+  def stop(self):
+    if self.proc is None:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=2)
+    except Exception:
+      self.proc.kill()
+    sm, smax, reasons = [], [], set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for r in self.rows:
+      f = [x.strip() for x in r.split(",")]
+      if len(f) < 8:
+        continue
+      try:
+        sm.append(float(f[1]))
+        smax.append(float(f[2]))
+      except ValueError:
+        continue
+      for n, v in zip(names, f[4:8]):
+        if v.lower().startswith("active"):
+          reasons.add(n)
+    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+            "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_ubm_and_frames(torch, n_frames, nmix, seed, device):
+  """Synthetic 60-dim features from a seeded 256-component diagonal mixture, generated
+  on the device; UBM initialised at perturbed data points so posteriors are neither
+  one-hot nor uniform."""
+  g = torch.Generator(device=device)
+  g.manual_seed(seed)
+  n_true = 256
+  mu = torch.randn(n_true, D, generator=g, device=device) * 3.0
+  sd = torch.sqrt(torch.rand(n_true, D, generator=g, device=device) + 0.5)
+  X = torch.empty((n_frames, D), dtype=torch.float32, device=device)
+  ch = 1 << 20
+  for s in range(0, n_frames, ch):
+    e = min(n_frames, s + ch)
+    comp = torch.randint(0, n_true, (e - s,), generator=g, device=device)
+    X[s:e] = mu[comp] + sd[comp] * torch.randn(e - s, D, generator=g, device=device)
+  g2 = torch.Generator(device="cpu")
+  g2.manual_seed(1234)  # the SAME model on every rank
+  mu_c = (torch.randn(n_true, D, generator=g2) * 3.0)
+  gen = torch.Generator(device="cpu")
+  gen.manual_seed(99)
+  pick = torch.randint(0, n_true, (nmix,), generator=gen)
+  mean = (mu_c[pick] + 0.7 * torch.randn(nmix, D, generator=gen)).t().contiguous().numpy().astype(np.float32)
+  sigma = (torch.rand(nmix, D, generator=gen) + 0.75).t().contiguous().numpy().astype(np.float32)
+  w = np.full((1, nmix), 1.0 / nmix, dtype=np.float32)
+  return X, mean, sigma, w
+
+
+def useful_flops_per_frame(nmix, second=True):
+  # loglik GEMM 2*(2D)*M + stats GEMM 2*M*(2D) + ~6*M for LSE/exp
+  return (240 + (240 if second else 120) + 6) * nmix
+
+
+# ---------------------------------------------------------------------------
+# reference arm (CPU)
+# ---------------------------------------------------------------------------
+def cpu_em_step(X, mean, sigma, w, nmix):
+  from oracle import gmm as OG
+  bs = OG.default_batch_size(D, nmix)
+  Z, F, S, L, n = OG.expectation(X, mean, sigma, w, batch_size=bs, compute_dtype=np.float32)
+  return OG.maximization(Z, F, S, (mean, sigma, w))
+
+
+def run_reference(args):
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return
+  import torch
+  n = min(args.cpu_sample, args.frames)
+  X, mean, sigma, w = make_ubm_and_frames(torch, n, args.nmix, 7, "cpu")
+  X = X.numpy()
+  cores = os.cpu_count()
+  for _ in range(args.warmup):
+    cpu_em_step(X[:8192], mean, sigma, w, args.nmix)
+  t0 = time.perf_counter()
+  for _ in range(args.steps):
+    cpu_em_step(X, mean, sigma, w, args.nmix)
+  dt = time.perf_counter() - t0
+  val = n * args.steps / dt
+  sample = "%d frames x %d-mix x %d steps, numpy float32 (numpy-1 semantics), BLAS threads" % (n, args.nmix, args.steps)
+  line = {
+      "impl": "reference", "metric": "ubm%d_baum_welch_frames_per_s" % args.nmix, "value": val, "unit": "frames/s",
+      "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+      "config": {"workload": "2048-mix diagonal UBM EM iteration (N/F/S + M-step), 60-dim MFCC+d+dd frames",
+                 "nmix": args.nmix, "feat_dim": D, "frames_per_step": n},
+      "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+      "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+  }
+  print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------
+# MFCC leg
+# ---------------------------------------------------------------------------
+def mfcc_leg(torch, args, rank, world, dist, peaks, do_cpu):
+  from odin_b200 import _lib, synth
+  from odin_b200 import preprocessing as pp
+  sr = 16000
+  pipe = pp.make_pipeline([
+      pp.AudioReader(), pp.PreEmphasis(0.97), pp.STFTExtractor(0.025, 0.010, n_fft=1024, window="hamm"),
+      pp.PowerSpecExtractor(), pp.MelsSpecExtractor(80, fmin=64, fmax=8000),
+      pp.MFCCsExtractor(20, first_coef_energy=True), pp.DeltaExtractor("mfcc", order=(0, 1, 2)),
+      pp.SADgmm(input_name="stft_energy")])
+  fe = pipe.plan[0]
+  pool = synth.utterance_batch(24, 5.0, 60.0, sr=sr, seed=4000 + rank)  # U[5,60] s utterances
+  pool_s = sum(len(u) for u in pool) / sr
+  reps = max(1, int(round(args.mfcc_hours * 3600.0 / pool_s)))
+  utts = [pool[i % len(pool)] for i in range(reps * len(pool))]
+  pcm_h, off = synth.pack_utterances(utts)
+  pcm_pinned = torch.from_numpy(pcm_h).pin_memory()
+  pcm = pcm_pinned.cuda()
+  lib = _lib.load()
+  h, _cfg = fe._handle(sr)
+
+  def step():
+    return fe.run_packed(pcm, off, sr)
+
+  for _ in range(max(3, args.warmup)):
+    out = step()
+  T = int(out["frame_offsets"][-1])
+  del out
+  torch.cuda.synchronize()
+  if dist is not None:
+    dist.barrier()
+  ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  kms = np.zeros(4)
+  torch.cuda.synchronize()
+  ev0.record()
+  for _ in range(args.steps):
+    out = step()
+    del out
+  ev1.record()
+  torch.cuda.synchronize()
+  ms = ev0.elapsed_time(ev1)
+  # per-kernel share of the last step
+  out = step()
+  buf = (C.c_float * 4)()
+  _lib.check(lib.odin_fe_last_run_ms(h, buf))
+  kms = np.array(list(buf))
+  # e2e: pinned host PCM -> device, features + VAD back to the host
+  t_e2e = []
+  for _ in range(2):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    d = pcm_pinned.cuda(non_blocking=True)
+    o = fe.run_packed(d, off, sr)
+    feat_h = o["feat"].cpu()
+    sad_h = o["sad"].cpu()
+    torch.cuda.synchronize()
+    t_e2e.append(time.perf_counter() - t0)
+  h2d = pcm_pinned.numel() * 2
+  d2h = feat_h.numel() * 4 + sad_h.numel()
+  t = torch.tensor([ms / 1e3 / args.steps, min(t_e2e)], dtype=torch.float64, device="cuda")
+  if dist is not None:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  step_s, e2e_s = float(t[0]), float(t[1])
+  total_T = T * world
+  bytes_per_frame = 320 + 240 + 320 + 5  # SURVEY.md 8d front-end cfg3: PCM in, feat, log-mel, energy+sad
+  frame_kernel_s = kms[1] / 1e3
+  res = {
+      "metric": "mfcc_frames_per_s", "value": total_T / step_s, "unit": "frames/s",
+      "ms_per_step": step_s * 1e3, "frames_per_gpu": T, "audio_hours_per_gpu": pcm_h.shape[0] / sr / 3600.0,
+      "config": {"workload": "config 3: 16 kHz, 25/10 ms, n_fft=1024, 80 mel + 20 MFCC + d/dd + SADgmm, U[5,60] s utterances",
+                 "n_utt_per_gpu": len(utts)},
+      "kernel_ms": {"dc": float(kms[0]), "frame": float(kms[1]), "post": float(kms[2]), "vad": float(kms[3])},
+      "roofline": {"bound": "hbm", "achieved": bytes_per_frame * T / frame_kernel_s / 1e9, "peak": peaks["hbm_gbs"],
+                   "unit": "GB/s", "frac": bytes_per_frame * T / frame_kernel_s / 1e9 / peaks["hbm_gbs"],
+                   "traffic": None, "kernel": "fe_frame_kernel", "peak_source": peaks["source"],
+                   "note": "algorithmic 885 B/frame; the kernel is FP32/shared-memory bound (SURVEY 8d), see DESIGN.md"},
+      "e2e": {"value": total_T / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d * world,
+              "d2h_bytes_per_step": d2h * world},
+  }
+  if do_cpu:
+    from oracle import frontend as F
+    t0 = time.perf_counter()
+    nfr = 0
+    for u in pool:
+      r = F.extract(u, sr, 0.025, 0.010, 1024, n_mels=80, fmin=64, fmax=8000, vad="gmm")
+      nfr += r["mfcc"].shape[0]
+      if time.perf_counter() - t0 > 15.0:
+        break
+    dt = time.perf_counter() - t0
+    res["cpu_baseline"] = {"value": nfr / dt, "unit": "frames/s", "cores": 1, "kind": "port",
+                           "sample": "%d frames of the same utterance pool, oracle/frontend.py, 1 process" % nfr}
+  return res
+
+
+# ---------------------------------------------------------------------------
+# main arm
+# ---------------------------------------------------------------------------
+def run_ours(args):
+  import torch
+  rank = int(os.environ.get("RANK", "0"))
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  torch.cuda.set_device(local)
+  dist = None
+  if world > 1:
+    import torch.distributed as td
+    td.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dist = td
+  from odin_b200 import _lib
+  from odin_b200.ml import GMM
+  lib = _lib.load()
+  peaks = measured_peaks()
+  N, M = args.frames, args.nmix
+  X, mean, sigma, w = make_ubm_and_frames(torch, N, M, 1000 + rank, "cuda")
+  g = GMM(nmix=M, nmix_start=M, impl=args.kernel_impl)
+  g.initialize(X)
+  g.mean, g.sigma, g.w = mean, sigma, w
+  stats_doubles = (2 * D + 1) * M + 2
+
+  def reset_model():
+    g.mean, g.sigma, g.w = mean, sigma, w
+    g._upload_params(force=True)
+
+  def step_resident():
+    stats = g._estep_device(X_frames, None, True)    # zero + E-step kernels + all-reduce
+    lib_rc = lib.odin_gmm_mstep(g._handle, _lib.ptr(stats), 1, _lib.ptr(g._d_mean), _lib.ptr(g._d_var),
+                                _lib.ptr(g._d_w), _lib.ptr(g._d_flag), _lib.current_stream())
+    _lib.check(lib_rc)
+
+  from odin_b200.ml.gmm import _DeviceFrames
+  X_frames = _DeviceFrames(X)
+  reset_model()
+  for _ in range(max(3, args.warmup)):
+    step_resident()
+  reset_model()
+  torch.cuda.synchronize()
+  if dist is not None:
+    dist.barrier()
+  sampler = ClockSampler(local)
+  if rank == 0:
+    sampler.start()
+  launches0 = lib.odin_launch_count()
+  ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  lse_ms, stats_ms = [], []
+  torch.cuda.synchronize()
+  ev0.record()
+  for _ in range(args.steps):
+    step_resident()
+  ev1.record()
+  torch.cuda.synchronize()
+  if dist is not None:
+    dist.barrier()
+  launches = lib.odin_launch_count() - launches0
+  clocks = sampler.stop() if rank == 0 else None
+  ms = ev0.elapsed_time(ev1)
+  # kernel durations of the last timed step (events recorded by the library on the launch stream)
+  a, b, im = C.c_float(), C.c_float(), C.c_int32()
+  _lib.check(lib.odin_gmm_last_estep_ms(g._handle, C.byref(a), C.byref(b), C.byref(im)))
+  lse_ms, stats_ms, impl_used = a.value, b.value, im.value
+
+  # ---- e2e: public API, pinned host frames -> device every step, parameters read back ----
+  Xh = torch.empty((N, D), dtype=torch.float32).pin_memory()
+  Xh.copy_(X)
+  reset_model()
+  e2e_times = []
+  for i in range(3):
+    torch.cuda.synchronize()
+    if dist is not None:
+      dist.barrier()
+    t0 = time.perf_counter()
+    g.expectation_maximization(Xh, print_progress=False)   # H2D chunks overlap the kernels; mean/var/w D2H
+    torch.cuda.synchronize()
+    e2e_times.append(time.perf_counter() - t0)
+  e2e_s = min(e2e_times[1:])
+  t = torch.tensor([ms / 1e3 / args.steps, e2e_s], dtype=torch.float64, device="cuda")
+  if dist is not None:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  step_s, e2e_s = float(t[0]), float(t[1])
+  del Xh
+
+  total_frames = N * world
+  value = total_frames / step_s
+  useful = useful_flops_per_frame(M) * N
+  # dominant kernel = statistics kernel; TF32 tensor peak = half the measured bf16 peak; a
+  # 3xTF32 product issues 3 MMAs per useful one
+  tf32_peak = peaks["bf16_sustained"] / 2.0
+  stats_useful = (240 + 240) * M * N  # its own logprob recompute + statistics GEMM
+  achieved = stats_useful / (stats_ms / 1e3) / 1e12
+  roofline = {
+      "bound": "tensor", "achieved": achieved, "peak": tf32_peak / 3.0, "unit": "TFLOP/s",
+      "frac": achieved / (tf32_peak / 3.0), "traffic": None,
+      "kernel": "gmm_stats_tc_kernel" if impl_used == 2 else "gmm_stats_kernel (fp32 CUDA cores)",
+      "kernel_ms": {"lse": lse_ms, "stats": stats_ms},
+      "peak_source": "%s bf16_tflops_sustained/2 (TF32 dense) /3 (3xTF32)" % peaks["source"],
+      "algorithmic_flops_per_frame": (240 + 240) * M,
+      "step_useful_tflops": useful / step_s / 1e12,
+  }
+  line = {
+      "metric": "ubm%d_baum_welch_frames_per_s" % M, "value": value, "unit": "frames/s", "n_gpus": world,
+      "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": step_s * 1e3, "higher_is_better": True,
+      "scaling": "weak", "vs_baseline": None, "dtype": "tf32x3" if impl_used == 2 else "f32", "data": "synthetic",
+      "config": {"workload": "config 4 shard: 2048-mix diagonal UBM EM iteration (N/F/S + NCCL all-reduce + M-step), "
+                             "60-dim frames resident in HBM",
+                 "nmix": M, "feat_dim": D, "frames_per_gpu": N, "parallelism": "dp%d" % world,
+                 "l2": "inputs (%.1f GB/GPU) exceed the 126 MB L2; no flush needed" % (N * D * 4 / 1e9),
+                 "kernel_impl": impl_used},
+      "roofline": roofline,
+      "e2e": {"value": total_frames / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": N * D * 4 * world,
+              "d2h_bytes_per_step": ((2 * D + 1) * M * 4 + 16) * world},
+      "gpu_launches": int(launches),
+      "clocks": clocks,
+  }
+  do_cpu = (rank == 0 and world == 1 and not args.no_cpu_baseline)
+  if do_cpu:
+    n = min(args.cpu_sample, N)
+    Xc = X[:n].cpu().numpy()
+    cpu_em_step(Xc[:8192], mean, sigma, w, M)
+    t0 = time.perf_counter()
+    cpu_em_step(Xc, mean, sigma, w, M)
+    dt = time.perf_counter() - t0
+    line["cpu_baseline"] = {"value": n / dt, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                            "sample": "%d frames of the same shard, one EM iteration, oracle/gmm.py in "
+                                      "float32 (numpy-1 semantics), BLAS threads" % n}
+  del X, X_frames
+  torch.cuda.empty_cache()
+  if not args.no_mfcc:
+    try:
+      line["mfcc"] = mfcc_leg(torch, args, rank, world, dist, peaks, do_cpu)
+    except Exception as e:  # the headline line must still be printed
+      line["mfcc"] = {"error": "%s: %s" % (type(e).__name__, e)}
+  if rank == 0:
+    print(json.dumps(line))
+  if dist is not None:
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def main():
+  args = parse()
+  if args.impl == "reference":
+    run_reference(args)
+  else:
+    run_ours(args)
+
+
+if __name__ == "__main__":
+  main()

@@ -56,8 +56,11 @@ class _DeviceFrames(object):
     self.torch = torch
     self.resident = None
     self.host = None
+    self.host_pinned = None
     if isinstance(X, torch.Tensor):
       if not X.is_cuda:
+        if X.is_pinned() and X.dtype == torch.float32 and X.is_contiguous() and X.dim() == 2:
+          self.host_pinned = X
         X = X.numpy()
       else:
         if X.dtype != torch.float32 or not X.is_contiguous():
@@ -86,7 +89,7 @@ class _DeviceFrames(object):
     out = torch.empty((self.n, self.dim), dtype=torch.float32, device="cuda")
     for dev, s, e in self.chunks():
       out[s:e].copy_(dev)
-    self.resident, self.host = out, None
+    self.resident, self.host, self.host_pinned = out, None, None
     return True
 
   def chunks(self):
@@ -99,7 +102,8 @@ class _DeviceFrames(object):
     if n == 0:
       return
     ch = min(self.chunk, n)
-    pinned = [torch.empty((ch, D), dtype=torch.float32).pin_memory() for _ in range(2)]
+    direct = self.host_pinned is not None  # pinned float32 tensor: DMA straight from the caller's buffer
+    pinned = None if direct else [torch.empty((ch, D), dtype=torch.float32).pin_memory() for _ in range(2)]
     dev = [torch.empty((ch, D), dtype=torch.float32, device="cuda") for _ in range(2)]
     copy_stream = torch.cuda.Stream()
     copied = [torch.cuda.Event() for _ in range(2)]
@@ -109,14 +113,20 @@ class _DeviceFrames(object):
     def stage(i):
       s, e = ranges[i]
       b = i & 1
-      consumed[b].synchronize()  # kernels of chunk i-2 are done with dev[b]; pinned[b] was copied
-      np.copyto(pinned[b][:e - s].numpy(), self.host[s:e], casting="unsafe")
+      if direct:
+        src = self.host_pinned[s:e]
+      else:
+        copied[b].synchronize()  # the previous DMA out of pinned[b] has finished
+        np.copyto(pinned[b][:e - s].numpy(), self.host[s:e], casting="unsafe")
+        src = pinned[b][:e - s]
       with torch.cuda.stream(copy_stream):
-        dev[b][:e - s].copy_(pinned[b][:e - s], non_blocking=True)
+        copy_stream.wait_event(consumed[b])  # kernels of chunk i-2 are done with dev[b]
+        dev[b][:e - s].copy_(src, non_blocking=True)
         copied[b].record(copy_stream)
 
     for b in range(2):
       consumed[b].record()
+      copied[b].record(copy_stream)
     stage(0)
     for i, (s, e) in enumerate(ranges):
       if i + 1 < len(ranges):

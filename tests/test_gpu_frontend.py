@@ -130,9 +130,14 @@ def test_ragged_edge_cases():
   outs = pipe.transform_batch([{"raw": utts[3], "sr": 16000}, {"raw": np.zeros(100, np.int16), "sr": 16000},
                                {"raw": np.zeros(16000, np.int16), "sr": 16000}])
   assert isinstance(outs[1], pp.ExtractorSignal) and outs[0]["mfcc"].shape == (2, 60)
-  # digital silence: energy falls back to float32 eps (signal.py:1436), VAD yields no speech
-  assert outs[2]["sad"].sum() == 0 and np.allclose(outs[2]["stft_energy"], np.log(np.finfo(np.float32).eps))
-  assert np.all(np.isfinite(outs[2]["mfcc"]))
+  # digital silence: energy falls back to float32 eps (signal.py:1436).  The reference's
+  # float32 mean of identical values is off by one ulp, so the standardised energy is a
+  # constant -1 and SADgmm marks EVERY frame as speech (threshold about -1.002): same here.
+  r = F.extract(np.zeros(16000, np.int16), 16000, vad="gmm", fmax=8000)
+  assert np.allclose(outs[2]["stft_energy"], np.log(np.finfo(np.float32).eps))
+  assert np.array_equal(outs[2]["sad"], r["sad"]) and r["sad"].sum() == 98
+  assert abs(outs[2]["sad_threshold"] - r["sad_threshold"]) < 1e-9
+  assert np.all(np.isfinite(outs[2]["mfcc"])) and relmax(outs[2]["mspec"], r["mspec"]) < TOL_FEAT
 
 
 def test_applying_sad_compaction_and_processor():
