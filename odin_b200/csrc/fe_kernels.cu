@@ -592,13 +592,8 @@ __global__ void __launch_bounds__(128) fe_vad_gmm_kernel(VadArgs a) {
     while (true) {
       // standardise in float32 exactly as numpy does (signal.py:305); the retry
       // path of the reference re-standardises the already standardised vector
-      float mean = 0.f, sd = 0.f;
-      if (lane == 0) {
-        MeanStdF32 ms = np_mean_std_f32(src, n);
-        mean = ms.mean; sd = ms.std;
-      }
-      mean = __shfl_sync(0xffffffffu, mean, 0);
-      sd = __shfl_sync(0xffffffffu, sd, 0);
+      const MeanStdF32 ms = warp_np_mean_std_f32(src, n, lane);
+      const float mean = ms.mean, sd = ms.std;
       __syncwarp();
       for (int i = lane; i < n; i += 32) xs[i] = __fdiv_rn(__fsub_rn(src[i], mean), sd);
       __syncwarp();

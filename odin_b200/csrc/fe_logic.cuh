@@ -98,6 +98,85 @@ __host__ __device__ inline MeanStdF32 np_mean_std_f32(const float* e, int n) {
   return r;
 }
 
+#ifdef __CUDACC__
+// Warp-cooperative, recursion-free twin of np_pairwise_sum_f32_gen (bit-identical
+// result, returned to every lane).  The recursion of numpy's pairwise_sum is
+// unrolled onto an explicit stack (depth <= log2(n/128)+2); inside a <=128
+// element leaf lanes 0..7 carry the eight strided accumulators and the fixed
+// combine tree ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) is an xor-butterfly (float
+// addition is commutative, so the butterfly reproduces the tree exactly).
+// Device recursion is avoided on purpose: its stack use is invisible to ptxas
+// and overflowed the 1 KB default stack for utterances beyond ~15 s.
+template <class F>
+__device__ inline float warp_np_pairwise_sum_f32(F f, int n, int lane) {
+  auto leaf = [&](int lo, int cnt) -> float {
+    if (cnt < 8) {
+      float res = 0.f;
+      for (int i = 0; i < cnt; ++i) res = __fadd_rn(res, f(lo + i));
+      return res;
+    }
+    const int body = cnt - (cnt % 8);
+    float r = 0.f;
+    if (lane < 8) {
+      r = f(lo + lane);
+      for (int i = 8; i < body; i += 8) r = __fadd_rn(r, f(lo + i + lane));
+    }
+    r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
+    r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
+    r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
+    float res = __shfl_sync(0xffffffffu, r, 0);
+    for (int i = body; i < cnt; ++i) res = __fadd_rn(res, f(lo + i));
+    return res;
+  };
+  constexpr int kDepth = 32;
+  int s_lo[kDepth], s_n[kDepth], s_stage[kDepth];
+  float s_left[kDepth];
+  int sp = 0;
+  s_lo[0] = 0; s_n[0] = n; s_stage[0] = 0; s_left[0] = 0.f;
+  sp = 1;
+  float ret = 0.f;
+  while (sp > 0) {
+    const int t = sp - 1;
+    const int lo = s_lo[t], cnt = s_n[t];
+    if (cnt <= 128) {
+      ret = leaf(lo, cnt);
+      --sp;
+      continue;
+    }
+    int n2 = cnt / 2;
+    n2 -= n2 % 8;
+    if (s_stage[t] == 0) {
+      s_stage[t] = 1;
+      s_lo[sp] = lo; s_n[sp] = n2; s_stage[sp] = 0; ++sp;
+    } else if (s_stage[t] == 1) {
+      s_left[t] = ret;
+      s_stage[t] = 2;
+      s_lo[sp] = lo + n2; s_n[sp] = cnt - n2; s_stage[sp] = 0; ++sp;
+    } else {
+      ret = __fadd_rn(s_left[t], ret);
+      --sp;
+    }
+  }
+  return ret;
+}
+
+// np.mean / np.std (float32) of e[0..n), warp-cooperative; same value on every lane.
+__device__ inline MeanStdF32 warp_np_mean_std_f32(const float* e, int n, int lane) {
+  MeanStdF32 r;
+  const float s = warp_np_pairwise_sum_f32([e](int i) { return e[i]; }, n, lane);
+  r.mean = (float)((double)s / (double)n);
+  const float mean = r.mean;
+  const float ss = warp_np_pairwise_sum_f32(
+      [e, mean](int i) {
+        const float d = __fadd_rn(e[i], -mean);
+        return __fmul_rn(d, d);
+      },
+      n, lane);
+  r.std = sqrtf((float)((double)ss / (double)n));
+  return r;
+}
+#endif  // __CUDACC__
+
 // signal.py:969-1000 smooth(x, win, 'flat') followed by `>= 2/win`, evaluated
 // for output element t.  x(i) -> 0/1 for i in [0, n).  wrap_u8 selects the
 // uint8 route of SADthreshold (speech.py:1426-1431) where 2*x[0]-x[k] wraps to
