@@ -382,7 +382,7 @@ int odin_gmm_create(int32_t feat_dim, int32_t max_nmix, odin_gmm_t** out) {
 void odin_gmm_destroy(odin_gmm_t* g) {
   if (!g) return;
   cudaFree(g->d_mean); cudaFree(g->d_var); cudaFree(g->d_w); cudaFree(g->d_Wk); cudaFree(g->d_cst);
-  cudaFree(g->d_Whi); cudaFree(g->d_Wlo); cudaFree(g->d_lse); cudaFree(g->d_prev); cudaFree(g->d_off);
+  cudaFree(g->d_Whi); cudaFree(g->d_Wlo); cudaFree(g->d_part); cudaFree(g->d_lse); cudaFree(g->d_prev); cudaFree(g->d_off);
   if (g->h_off) cudaFreeHost(g->h_off);
   for (int i = 0; i < 3; ++i) if (g->ev[i]) cudaEventDestroy(g->ev[i]);
   delete g;

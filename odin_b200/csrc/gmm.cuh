@@ -20,10 +20,14 @@ struct odin_gmm {
   float* d_Wk = nullptr;
   float* d_cst = nullptr;
   int Mpad = 0;  // M rounded up to 128
-  // tcgen05 operand images (gmm_tc.cu): [Mpad, 128] hi and lo TF32 splits of
-  // [-0.5*prec | mu*prec | 0 pad], K-major with the 128B swizzle applied.
+  // tcgen05 operand images (gmm_tc.cu): hi and lo TF32 splits of the [Mpad, 128]
+  // log2-domain weight rows; Whi plain (copied into TMEM), Wlo pre-swizzled per
+  // 128-mixture chunk as a K-major SWIZZLE_128B shared-memory tile.
   float* d_Whi = nullptr;
   float* d_Wlo = nullptr;
+  // pass-1 workspace of the tcgen05 path: per-chunk partial (max, sum) per frame
+  void* d_part = nullptr;
+  int64_t part_cap = 0;  // float2 elements
   // per-frame log-sum-exp workspace (grows on demand)
   float* d_lse = nullptr;
   int64_t lse_cap = 0;
