@@ -168,7 +168,8 @@ def test_ten_em_iterations_vs_oracle():
     om, os_, ow, rb = OG.maximization(z, f, s, (om, os_, ow))
     assert not rb
   assert relmax(gm.mean, om) < TOL_STATS and relmax(gm.sigma, os_) < TOL_STATS and relmax(gm.w, ow) < TOL_STATS
-  assert abs(gm._llk_hist[M][-1] - l) < 1e-3  # oracle L is already the per-frame mean
+  # oracle L is already the per-frame mean; fp32 parameters vs the fp64 oracle drift by ~1e-5 relative over 10 iterations
+  assert abs(gm._llk_hist[M][-1] - l) < 1e-4 * abs(l)
 
 
 def test_mixup_and_rollback():
@@ -207,7 +208,8 @@ def test_host_array_streaming_equals_resident():
   Zr, Fr, Sr, Lr = gm.expectation(torch.from_numpy(X).cuda())
   frames = G._DeviceFrames(X, chunk_frames=7000)
   Zh, Fh, Sh, Lh = gm.expectation(frames)
-  assert relmax(Zh, Zr) < 1e-9 and relmax(Fh, Fr) < 1e-9 and relmax(Sh, Sr) < 1e-9
+  # chunk boundaries regroup the fp32 partial sums that are flushed into the fp64 statistics
+  assert relmax(Zh, Zr) < 1e-6 and relmax(Fh, Fr) < 1e-6 and relmax(Sh, Sr) < 1e-6
   X16 = X.astype(np.float16)  # float16 stores are up-cast on load
   Z16, F16, S16, L16 = gm.expectation(X16)
   z, f, s, l, _ = OG.expectation(X16.astype(np.float32), mean, sigma, w, compute_dtype=np.float64)
