@@ -105,6 +105,18 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// one lane of a converged warp (keeps the surrounding control flow warp-uniform so
+// descriptors stay in uniform registers; a `lane == 0` branch makes ptxas wrap every
+// tcgen05.mma in an ELECT / R2UR waterfall loop and the issue rate collapses)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -415,7 +427,8 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gmm_tc_kernel(TcArgs a) {
     }
   } else if (warp == 4) {
     // ========================================================== MMA issuer
-    if (lane == 0 && my_tiles > 0) {
+    // The whole warp walks the (warp-uniform) schedule; one elected lane issues.
+    if (my_tiles > 0) {
       const uint32_t idesc1 = idesc_tf32(NF), idesc2 = idesc_tf32(CM);
       const uint32_t wlo_s = sbase + SM_WLO;
       bool acc = false, need_d2_empty = false;
@@ -425,20 +438,23 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gmm_tc_kernel(TcArgs a) {
         mbar_wait(bar(B_BT_FULL + s), (uint32_t)((it / BT_STAGES) & 1));
         mbar_wait(bar(B_D1_EMPTY + b), (uint32_t)(((it / D1_BUFS) & 1) ^ 1));
         tc_fence_after();
-        const uint32_t d = tmem + TM_D1 + 32 * b;
-        const uint32_t bt_hi = sbase + SM_BT + s * 32768, bt_lo = bt_hi + 16384;
+        if (elect_one()) {
+          const uint32_t d = tmem + TM_D1 + 32 * b;
+          const uint32_t bt_hi = sbase + SM_BT + s * 32768, bt_lo = bt_hi + 16384;
 #pragma unroll
-        for (int kk = 0; kk < K / 8; ++kk) {
-          const uint32_t a_hi = tmem + TM_WHI + kk * 8;
-          const uint64_t a_lo = desc_k_sw128(wlo_s + (kk >> 2) * 16384 + (kk & 3) * 32);
-          const uint64_t b_hi = desc_k_sw128(bt_hi + (kk >> 2) * 4096 + (kk & 3) * 32);
-          const uint64_t b_lo = desc_k_sw128(bt_lo + (kk >> 2) * 4096 + (kk & 3) * 32);
-          mma_ts(d, a_hi, b_hi, idesc1, kk > 0 ? 1u : 0u);
-          mma_ts(d, a_hi, b_lo, idesc1, 1u);
-          mma_ss(d, a_lo, b_hi, idesc1, 1u);
+          for (int kk = 0; kk < K / 8; ++kk) {
+            const uint32_t a_hi = tmem + TM_WHI + kk * 8;
+            const uint64_t a_lo = desc_k_sw128(wlo_s + (kk >> 2) * 16384 + (kk & 3) * 32);
+            const uint64_t b_hi = desc_k_sw128(bt_hi + (kk >> 2) * 4096 + (kk & 3) * 32);
+            const uint64_t b_lo = desc_k_sw128(bt_lo + (kk >> 2) * 4096 + (kk & 3) * 32);
+            mma_ts(d, a_hi, b_hi, idesc1, kk > 0 ? 1u : 0u);
+            mma_ts(d, a_hi, b_lo, idesc1, 1u);
+            mma_ss(d, a_lo, b_hi, idesc1, 1u);
+          }
+          tc_commit(bar(B_D1_FULL + b));
+          tc_commit(bar(B_BT_EMPTY + s));
         }
-        tc_commit(bar(B_D1_FULL + b));
-        tc_commit(bar(B_BT_EMPTY + s));
+        __syncwarp();
       };
       auto issue_g2 = [&](int64_t it) {
         const int pb = (int)(it % P_BUFS), ts = (int)(it % TT_BUFS);
@@ -450,24 +466,25 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gmm_tc_kernel(TcArgs a) {
           need_d2_empty = false;
         }
         tc_fence_after();
-        const uint32_t d = tmem + TM_D2;
-        const uint32_t p_hi = sbase + SM_P + pb * 32768, p_lo = p_hi + 16384;
+        const bool flush = ((it + 1) % a.flush_tiles) == 0 || it + 1 == my_tiles;
+        if (elect_one()) {
+          const uint32_t d = tmem + TM_D2;
+          const uint32_t p_hi = sbase + SM_P + pb * 32768, p_lo = p_hi + 16384;
 #pragma unroll
-        for (int ks = 0; ks < NF / 8; ++ks) {
-          const uint32_t t_hi = tmem + TM_TT + 64 * ts + ks * 8, t_lo = t_hi + 32;
-          const uint64_t b_hi = desc_k_sw128(p_hi + ks * 32), b_lo = desc_k_sw128(p_lo + ks * 32);
-          mma_ts(d, t_hi, b_hi, idesc2, (acc || ks > 0) ? 1u : 0u);
-          mma_ts(d, t_hi, b_lo, idesc2, 1u);
-          mma_ts(d, t_lo, b_hi, idesc2, 1u);
+          for (int ks = 0; ks < NF / 8; ++ks) {
+            const uint32_t t_hi = tmem + TM_TT + 64 * ts + ks * 8, t_lo = t_hi + 32;
+            const uint64_t b_hi = desc_k_sw128(p_hi + ks * 32), b_lo = desc_k_sw128(p_lo + ks * 32);
+            mma_ts(d, t_hi, b_hi, idesc2, (acc || ks > 0) ? 1u : 0u);
+            mma_ts(d, t_hi, b_lo, idesc2, 1u);
+            mma_ts(d, t_lo, b_hi, idesc2, 1u);
+          }
+          tc_commit(bar(B_P_EMPTY + pb));
+          tc_commit(bar(B_TT_EMPTY + ts));
+          if (flush) tc_commit(bar(B_D2_FULL));
         }
-        acc = true;
-        tc_commit(bar(B_P_EMPTY + pb));
-        tc_commit(bar(B_TT_EMPTY + ts));
-        if (((it + 1) % a.flush_tiles) == 0 || it + 1 == my_tiles) {
-          tc_commit(bar(B_D2_FULL));
-          acc = false;
-          need_d2_empty = true;
-        }
+        __syncwarp();
+        acc = !flush;
+        if (flush) need_d2_empty = true;
       };
       issue_g1(0);
       for (int64_t it = 0; it < my_tiles; ++it) {
