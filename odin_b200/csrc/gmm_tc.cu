@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gmm_tc_kernel(TcArgs a) {
     // The whole warp walks the (warp-uniform) schedule; one elected lane issues.
     if (my_tiles > 0) {
       const uint32_t idesc1 = idesc_tf32(NF), idesc2 = idesc_tf32(CM);
-      const uint32_t wlo_s = sbase + SM_WLO;
+      const uint64_t wlo_desc0 = desc_k_sw128(sbase + SM_WLO);
       bool acc = false, need_d2_empty = false;
       uint32_t d2_phase = 0;
       auto issue_g1 = [&](int64_t it) {
@@ -440,13 +440,14 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gmm_tc_kernel(TcArgs a) {
         tc_fence_after();
         if (elect_one()) {
           const uint32_t d = tmem + TM_D1 + 32 * b;
-          const uint32_t bt_hi = sbase + SM_BT + s * 32768, bt_lo = bt_hi + 16384;
+          // descriptors advance by adding the byte offset >> 4 to the start-address field
+          const uint64_t bt_hi0 = desc_k_sw128(sbase + SM_BT + s * 32768), bt_lo0 = bt_hi0 + (16384 >> 4);
 #pragma unroll
           for (int kk = 0; kk < K / 8; ++kk) {
             const uint32_t a_hi = tmem + TM_WHI + kk * 8;
-            const uint64_t a_lo = desc_k_sw128(wlo_s + (kk >> 2) * 16384 + (kk & 3) * 32);
-            const uint64_t b_hi = desc_k_sw128(bt_hi + (kk >> 2) * 4096 + (kk & 3) * 32);
-            const uint64_t b_lo = desc_k_sw128(bt_lo + (kk >> 2) * 4096 + (kk & 3) * 32);
+            const uint64_t a_lo = wlo_desc0 + (uint64_t)(((kk >> 2) * 16384 + (kk & 3) * 32) >> 4);
+            const uint64_t b_hi = bt_hi0 + (uint64_t)(((kk >> 2) * 4096 + (kk & 3) * 32) >> 4);
+            const uint64_t b_lo = bt_lo0 + (uint64_t)(((kk >> 2) * 4096 + (kk & 3) * 32) >> 4);
             mma_ts(d, a_hi, b_hi, idesc1, kk > 0 ? 1u : 0u);
             mma_ts(d, a_hi, b_lo, idesc1, 1u);
             mma_ss(d, a_lo, b_hi, idesc1, 1u);
@@ -469,11 +470,11 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gmm_tc_kernel(TcArgs a) {
         const bool flush = ((it + 1) % a.flush_tiles) == 0 || it + 1 == my_tiles;
         if (elect_one()) {
           const uint32_t d = tmem + TM_D2;
-          const uint32_t p_hi = sbase + SM_P + pb * 32768, p_lo = p_hi + 16384;
+          const uint64_t p_hi0 = desc_k_sw128(sbase + SM_P + pb * 32768), p_lo0 = p_hi0 + (16384 >> 4);
 #pragma unroll
           for (int ks = 0; ks < NF / 8; ++ks) {
             const uint32_t t_hi = tmem + TM_TT + 64 * ts + ks * 8, t_lo = t_hi + 32;
-            const uint64_t b_hi = desc_k_sw128(p_hi + ks * 32), b_lo = desc_k_sw128(p_lo + ks * 32);
+            const uint64_t b_hi = p_hi0 + (uint64_t)((ks * 32) >> 4), b_lo = p_lo0 + (uint64_t)((ks * 32) >> 4);
             mma_ts(d, t_hi, b_hi, idesc2, (acc || ks > 0) ? 1u : 0u);
             mma_ts(d, t_hi, b_lo, idesc2, 1u);
             mma_ts(d, t_lo, b_hi, idesc2, 1u);
