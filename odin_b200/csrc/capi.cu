@@ -373,6 +373,7 @@ int odin_gmm_create(int32_t feat_dim, int32_t max_nmix, odin_gmm_t** out) {
   if ((e = cudaMalloc(&g->d_Wk, 2 * (size_t)feat_dim * maxpad * sizeof(float))) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&g->d_cst, maxpad * sizeof(float))) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&g->d_Whi, maxpad * 128 * sizeof(float))) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&g->d_Whs, maxpad * 128 * sizeof(float))) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&g->d_Wlo, maxpad * 128 * sizeof(float))) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&g->d_prev, (2 * dm + max_nmix) * sizeof(float))) != cudaSuccess) return fail(e);
   *out = g;
@@ -382,7 +383,7 @@ int odin_gmm_create(int32_t feat_dim, int32_t max_nmix, odin_gmm_t** out) {
 void odin_gmm_destroy(odin_gmm_t* g) {
   if (!g) return;
   cudaFree(g->d_mean); cudaFree(g->d_var); cudaFree(g->d_w); cudaFree(g->d_Wk); cudaFree(g->d_cst);
-  cudaFree(g->d_Whi); cudaFree(g->d_Wlo); cudaFree(g->d_part); cudaFree(g->d_lse); cudaFree(g->d_prev); cudaFree(g->d_off);
+  cudaFree(g->d_Whi); cudaFree(g->d_Whs); cudaFree(g->d_Wlo); cudaFree(g->d_part); cudaFree(g->d_lse); cudaFree(g->d_prev); cudaFree(g->d_off);
   if (g->h_off) cudaFreeHost(g->h_off);
   for (int i = 0; i < 3; ++i) if (g->ev[i]) cudaEventDestroy(g->ev[i]);
   delete g;

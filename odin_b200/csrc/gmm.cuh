@@ -21,9 +21,10 @@ struct odin_gmm {
   float* d_cst = nullptr;
   int Mpad = 0;  // M rounded up to 128
   // tcgen05 operand images (gmm_tc.cu): hi and lo TF32 splits of the [Mpad, 128]
-  // log2-domain weight rows; Whi plain (copied into TMEM), Wlo pre-swizzled per
-  // 128-mixture chunk as a K-major SWIZZLE_128B shared-memory tile.
+  // log2-domain weight rows; Whi plain (copied into TMEM), Whs (hi) / Wlo (lo)
+  // pre-swizzled per 128-mixture chunk as K-major SWIZZLE_128B shared-memory tiles.
   float* d_Whi = nullptr;
+  float* d_Whs = nullptr;
   float* d_Wlo = nullptr;
   // pass-1 workspace of the tcgen05 path: per-chunk partial (max, sum) per frame
   void* d_part = nullptr;

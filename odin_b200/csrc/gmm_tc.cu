@@ -49,7 +49,6 @@ constexpr int BT_STAGES = 2;
 constexpr int D1_BUFS = 4;
 constexpr int TT_BUFS = 2;
 constexpr int P_BUFS = 2;
-constexpr int THREADS = 288;    // warps 0-3 epilogue, 4 MMA issuer, 5-8 producers
 constexpr int MAX_D = 60;       // 2*D + 2 <= 122 and D % 4 == 0
 
 constexpr uint32_t TM_WHI = 0, TM_D2 = 128, TM_D1 = 256, TM_TT = 384;
@@ -60,8 +59,7 @@ constexpr uint32_t SM_BT = 65536;                       // 2 x (hi 16 KB | lo 16
 constexpr uint32_t SM_P = SM_BT + BT_STAGES * 32768;    // 2 x (hi 16 KB | lo 16 KB)
 constexpr uint32_t SM_XRAW = SM_P + P_BUFS * 32768;     // 2 x 32 x 60 floats
 constexpr uint32_t SM_LSE = SM_XRAW + 2 * NF * MAX_D * 4;   // 2 x 32 floats
-constexpr uint32_t SM_PART = SM_LSE + 2 * NF * 4;       // 2 x 4 x 32 float2
-constexpr uint32_t SM_BAR = SM_PART + 2 * 4 * NF * 8;   // mbarriers
+constexpr uint32_t SM_BAR = SM_LSE + 2 * NF * 4;        // mbarriers
 constexpr uint32_t SM_TOTAL = SM_BAR + 256;
 constexpr uint32_t SMEM_BYTES = SM_TOTAL + 1024;        // alignment slack
 
@@ -152,22 +150,13 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
-__device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
-}
 __device__ __forceinline__ float ex2f(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
-#define ODIN_R32(v) \
-  v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15], v[16], \
-  v[17], v[18], v[19], v[20], v[21], v[22], v[23], v[24], v[25], v[26], v[27], v[28], v[29], v[30], v[31]
-
-// 32 consecutive TMEM columns of this thread's lane -> registers
+// 32 / 16 consecutive TMEM columns of this thread's lane <-> registers
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
   asm volatile(
@@ -184,6 +173,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
   uint32_t r[32];
 #pragma unroll
@@ -198,35 +200,73 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) 
         "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]), "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  uint32_t r[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(v[i]);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15};"
+      ::"r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc512(uint32_t dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(512) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc512(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(512) : "memory");
+}
+
+// 16-byte async copy global -> shared; src_bytes = 0 zero-fills the destination
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// x = hi + lo with hi the TF32 rounding of x (round half away, what cvt.rna.tf32.f32
+// does, but 2 integer ops instead of the 4-instruction sequence ptxas emits for it);
+// lo is exact in fp32 and is truncated to TF32 by the tensor core (error 2^-22 |x|).
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+  lo = x - hi;
+}
+__device__ __forceinline__ void split4(const float4& v, float4& h, float4& l) {
+  split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+}
+// byte offset of 16-byte chunk k4 (= k / 4) of row r inside a K-major SWIZZLE_128B
+// tile whose 32-element column blocks are `rows` rows tall
+__device__ __forceinline__ uint32_t sw128_off(int r, int k4, int rows) {
+  return (uint32_t)(k4 >> 3) * (uint32_t)(rows * 128) + (uint32_t)r * 128u + (uint32_t)(((k4 & 7) ^ (r & 7)) << 4);
+}
 
 }  // namespace tc
 
 // ---------------------------------------------------------------------------
 // operand images of the model (refreshed with the cached constants)
 // ---------------------------------------------------------------------------
-// Whi : [Mpad][128] plain rows (copied to TMEM by the kernels)
-// Wlo : per chunk of 128 mixtures the exact shared-memory image of a K-major
-//       SWIZZLE_128B tile: [kblock 4][row 128][16-byte chunk (q ^ (row & 7))][4]
+// Whi       : [Mpad][128] plain rows (pass 2 copies them into TMEM)
+// Whs / Wls : hi / lo parts, per chunk of 128 mixtures the exact shared-memory image of a
+//             K-major SWIZZLE_128B tile: [kblock 4][row 128][16-byte chunk (q ^ (row & 7))][4]
 __global__ void gmm_tc_prepare_kernel(const float* __restrict__ mean, const float* __restrict__ var,
                                       const float* __restrict__ w, int D, int M, int Mpad,
-                                      float* __restrict__ Whi, float* __restrict__ Wlo) {
+                                      float* __restrict__ Whi, float* __restrict__ Whs, float* __restrict__ Wls) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= Mpad) return;
   const double LOG2E = 1.4426950408889634074;
   const int chunk = m / tc::CM, row = m % tc::CM;
-  float* lo_base = Wlo + (size_t)chunk * tc::CM * tc::K;
+  const size_t cbase = (size_t)chunk * tc::CM * tc::K;
   auto put = [&](int k, double v) {
-    const float vf = (float)v;
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(vf));
-    const float h = __uint_as_float(u);
-    float l = vf - h;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(l));
-    l = __uint_as_float(u);
+    float h, l;
+    tc::split_tf32((float)v, h, l);
     Whi[(size_t)m * tc::K + k] = h;
-    const int kb = k >> 5, q = (k & 31) >> 2, e = k & 3;
-    lo_base[(size_t)kb * (tc::CM * 32) + row * 32 + ((q ^ (row & 7)) << 2) + e] = l;
+    const size_t o = cbase + (size_t)(k >> 5) * (tc::CM * 32) + row * 32 + ((((k & 31) >> 2) ^ (row & 7)) << 2) + (k & 3);
+    Whs[o] = h;
+    Wls[o] = l;
   };
   if (m >= M) {  // padding mixture: log-density -1e30 -> posterior exactly 0
     for (int k = 0; k < tc::K; ++k) put(k, k == tc::K_ONE ? -1e30 : 0.0);
@@ -247,16 +287,14 @@ __global__ void gmm_tc_prepare_kernel(const float* __restrict__ mean, const floa
   put(tc::K_LSE, 1.0);
 }
 
-// ---------------------------------------------------------------------------
-// the tensor-core kernel (STATS = false: pass 1 / LSE partials, true: pass 2)
-// ---------------------------------------------------------------------------
 struct TcArgs {
   const float* X;
   const uint8_t* sad;
   int64_t N;
   int D, M;
   const float* Whi;
-  const float* Wlo;
+  const float* Whs;
+  const float* Wls;
   const float* lse2;     // pass 2: per-frame log2-domain log-sum-exp
   float2* part;          // pass 1: [nchunks][part_stride] (max, sum) per frame
   int64_t part_stride;
@@ -265,8 +303,209 @@ struct TcArgs {
   int flush_tiles;
 };
 
-template <bool STATS>
-__global__ void __launch_bounds__(tc::THREADS, 1) gmm_tc_kernel(TcArgs a) {
+// ---------------------------------------------------------------------------
+// pass 1: per-chunk partial log-sum-exp.  Frames on the TMEM lanes.
+//   D1[128 frames, 128 mixtures] = Ahi*Whi + Alo*Whi + Ahi*Wlo      (K = 128)
+//   A (hi | lo) is written into TMEM by the producers one 32-column k-block at
+//   a time (single buffer, one full/empty mbarrier pair per k-block, so block
+//   kb of the next tile is refilled while the tensor core works on kb+1..3);
+//   W (hi | lo) sits in shared memory for the whole kernel; the epilogue runs an
+//   online max / sum over each thread's own 128-column row.
+// TMEM: [0,128) Ahi | [128,256) Alo | [256,384) D1[0] | [384,512) D1[1]
+// ---------------------------------------------------------------------------
+namespace tcl {
+constexpr int TF = 128;        // frames per tile
+constexpr int THREADS = 288;   // warps 0-3 epilogue, 4 MMA issuer, 5-8 producers
+constexpr uint32_t TM_AHI = 0, TM_ALO = 128, TM_D1 = 256;
+constexpr uint32_t SM_WHS = 0, SM_WLS = 65536, SM_XRAW = 131072;      // 2 x 128 x 60 floats
+constexpr uint32_t SM_BAR = SM_XRAW + 2 * TF * tc::MAX_D * 4;
+constexpr uint32_t SMEM_BYTES = SM_BAR + 256 + 1024;
+constexpr int B_A_FULL = 0, B_A_EMPTY = 4, B_D1_FULL = 8, B_D1_EMPTY = 10, B_TMEM_PTR = 16;
+}  // namespace tcl
+
+__global__ void __launch_bounds__(tcl::THREADS, 1) gmm_tc_lse_kernel(TcArgs a) {
+  using namespace tc;
+  using namespace tcl;
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t raw_addr = smem_u32(smem_dyn);
+  const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+  unsigned char* smem = smem_dyn + pad;
+  const uint32_t sbase = raw_addr + pad;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int chunk = blockIdx.x;
+  const int D = a.D, d4 = a.D >> 2;
+  const int64_t n_tiles = (a.N + TF - 1) / TF;
+  const int64_t my_tiles = (n_tiles > (int64_t)blockIdx.y) ? (n_tiles - blockIdx.y + gridDim.y - 1) / gridDim.y : 0;
+  auto bar = [&](int i) -> uint32_t { return sbase + tcl::SM_BAR + 8u * i; };
+  volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + tcl::SM_BAR + 8 * tcl::B_TMEM_PTR);
+
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int i = 0; i < 4; ++i) { mbar_init(bar(B_A_FULL + i), 128); mbar_init(bar(B_A_EMPTY + i), 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(bar(tcl::B_D1_FULL + i), 1); mbar_init(bar(tcl::B_D1_EMPTY + i), 128); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc512(bar(tcl::B_TMEM_PTR));
+  }
+  {  // W chunk images (hi | lo, already swizzled): global -> shared
+    const uint4* s0 = reinterpret_cast<const uint4*>(a.Whs + (size_t)chunk * CM * K);
+    const uint4* s1 = reinterpret_cast<const uint4*>(a.Wls + (size_t)chunk * CM * K);
+    uint4* d0 = reinterpret_cast<uint4*>(smem + SM_WHS);
+    uint4* d1 = reinterpret_cast<uint4*>(smem + SM_WLS);
+    for (int i = tid; i < CM * K / 4; i += tcl::THREADS) { d0[i] = __ldg(s0 + i); d1[i] = __ldg(s1 + i); }
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr_s;
+
+  if (warp >= 5) {
+    // =========================================================== producers
+    const int ptid = tid - 160;                 // 0..127
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;        // frame within the tile == TMEM lane
+    const uint32_t lane_field = (uint32_t)(quarter * 32) << 16;
+    const int items = TF * d4;                  // float4 items of one raw tile (<= 1920)
+    const float4* X4 = reinterpret_cast<const float4*>(a.X);
+    const int64_t total4 = a.N * d4;
+    auto fetch = [&](int64_t it) {
+      const int64_t tile = blockIdx.y + it * gridDim.y;
+      const int64_t base4 = tile * items;
+      const uint32_t dst = sbase + tcl::SM_XRAW + (uint32_t)(it & 1) * (TF * MAX_D * 4);
+      for (int idx = ptid; idx < items; idx += 128) {
+        const int64_t g = base4 + idx;
+        const bool ok = g < total4;
+        cp_async16(dst + idx * 16, X4 + (ok ? g : 0), ok ? 16u : 0u);
+      }
+      cp_async_commit();
+    };
+    if (my_tiles > 0) fetch(0);
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      cp_async_wait_all();
+      named_bar_sync(1, 128);   // tile `it` has landed; everyone is done with the other buffer
+      if (it + 1 < my_tiles) fetch(it + 1);
+      const float4* xr4 = reinterpret_cast<const float4*>(smem + tcl::SM_XRAW + (it & 1) * (TF * MAX_D * 4)) + row * d4;
+      for (int kb = 0; kb < 4; ++kb) {
+        float h[32], l[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const int k4 = 8 * kb + c;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (k4 < d4) {
+            const float4 x = xr4[k4];
+            v = make_float4(x.x * x.x, x.y * x.y, x.z * x.z, x.w * x.w);
+          } else if (k4 < 2 * d4) {
+            v = xr4[k4 - d4];
+          } else if (k4 == K_ONE / 4) {
+            v.x = 1.f;
+          }
+          float4 hh, ll;
+          split4(v, hh, ll);
+          h[4 * c] = hh.x; h[4 * c + 1] = hh.y; h[4 * c + 2] = hh.z; h[4 * c + 3] = hh.w;
+          l[4 * c] = ll.x; l[4 * c + 1] = ll.y; l[4 * c + 2] = ll.z; l[4 * c + 3] = ll.w;
+        }
+        mbar_wait(bar(B_A_EMPTY + kb), (uint32_t)((it & 1) ^ 1));
+        tc_fence_after();
+        tmem_st32(tmem + TM_AHI + 32 * kb + lane_field, h);
+        tmem_st32(tmem + TM_ALO + 32 * kb + lane_field, l);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(bar(B_A_FULL + kb));
+      }
+    }
+  } else if (warp == 4) {
+    // ========================================================== MMA issuer
+    if (my_tiles > 0) {
+      const uint32_t idesc = idesc_tf32(CM);
+      const uint64_t whi0 = desc_k_sw128(sbase + SM_WHS), wlo0 = desc_k_sw128(sbase + SM_WLS);
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        const int buf = (int)(it & 1);
+        mbar_wait(bar(tcl::B_D1_EMPTY + buf), (uint32_t)(((it >> 1) & 1) ^ 1));
+        const uint32_t d = tmem + tcl::TM_D1 + 128 * buf;
+        for (int kb = 0; kb < 4; ++kb) {
+          mbar_wait(bar(B_A_FULL + kb), (uint32_t)(it & 1));
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int kk = 4 * kb + q;
+              const uint32_t a_hi = tmem + TM_AHI + kk * 8, a_lo = tmem + TM_ALO + kk * 8;
+              const uint64_t off = (uint64_t)((kb * 16384 + q * 32) >> 4);
+              mma_ts(d, a_hi, whi0 + off, idesc, kk > 0 ? 1u : 0u);
+              mma_ts(d, a_lo, whi0 + off, idesc, 1u);
+              mma_ts(d, a_hi, wlo0 + off, idesc, 1u);
+            }
+            tc_commit(bar(B_A_EMPTY + kb));
+            if (kb == 3) tc_commit(bar(tcl::B_D1_FULL + buf));
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ============================================================ epilogue
+    const uint32_t lane_field = (uint32_t)(warp * 32) << 16;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int buf = (int)(it & 1);
+      mbar_wait(bar(tcl::B_D1_FULL + buf), (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      float m = 0.f, s = 0.f;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float v[32];
+        tmem_ld32(tmem + tcl::TM_D1 + 128 * buf + 32 * g + lane_field, v);
+        float mx = v[0];
+#pragma unroll
+        for (int i = 1; i < 32; ++i) mx = fmaxf(mx, v[i]);
+        float acc = 0.f;
+        if (g == 0) {
+          m = mx;
+        } else {
+          const float mn = fmaxf(m, mx);
+          acc = s * ex2f(m - mn);
+          m = mn;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc += ex2f(v[i] - m);
+        s = acc;
+      }
+      tc_fence_before();
+      mbar_arrive(bar(tcl::B_D1_EMPTY + buf));
+      const int64_t tile = blockIdx.y + it * gridDim.y;
+      const int64_t f = tile * TF + warp * 32 + lane;
+      if (f < a.N) a.part[(size_t)chunk * a.part_stride + f] = make_float2(m, s);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    __syncwarp();
+    tmem_dealloc512(tmem);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// pass 2: posteriors and statistics.  Mixtures on the TMEM lanes.
+//   D1[128 mix, 32 frames] = Whi*Bhi + Whi*Blo + Wlo*Bhi       (GEMM 1, K = 128;
+//       Whi in TMEM for the whole kernel, Wlo and the frame tile B in smem)
+//   P = ex2(D1)  (the -lse2 column of B makes D1 = lp2 - lse2)
+//   D2[128 j, 128 mix] += Thi*Phi + Thi*Plo + Tlo*Phi           (GEMM 2, K = 32 frames;
+//       T^T = [x^2 | x | 1] transposed, written into TMEM by the producers,
+//       P from a K-major SWIZZLE_128B smem tile written by the epilogue)
+//   every `flush_tiles` tiles D2 is drained into the fp64 statistics.
+// 17 warps: 0-7 epilogue, 8 MMA issuer, 9-16 producers (two warps per TMEM lane
+// quarter in each group: the roles are instruction-issue bound, not MMA bound,
+// with one warp per scheduler).
+// TMEM: [0,128) Whi | [128,256) D2 | [256,384) 4 x D1 | [384,512) 2 x (Thi | Tlo)
+// ---------------------------------------------------------------------------
+namespace tcs {
+constexpr int THREADS = 544;
+constexpr int NROLE = 256;     // threads per producer / epilogue group
+}
+
+__global__ void __launch_bounds__(tcs::THREADS, 1) gmm_tc_stats_kernel(TcArgs a) {
   using namespace tc;
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t raw_addr = smem_u32(smem_dyn);
@@ -283,42 +522,51 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gmm_tc_kernel(TcArgs a) {
   volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + SM_BAR + 8 * B_TMEM_PTR);
 
   // ------------------------------------------------------------- setup
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
-      for (int i = 0; i < BT_STAGES; ++i) { mbar_init(bar(B_BT_FULL + i), 128); mbar_init(bar(B_BT_EMPTY + i), 1); }
-      for (int i = 0; i < D1_BUFS; ++i) { mbar_init(bar(B_D1_FULL + i), 1); mbar_init(bar(B_D1_EMPTY + i), 128); }
-      for (int i = 0; i < TT_BUFS; ++i) { mbar_init(bar(B_TT_FULL + i), 128); mbar_init(bar(B_TT_EMPTY + i), 1); }
-      for (int i = 0; i < P_BUFS; ++i) { mbar_init(bar(B_P_FULL + i), 128); mbar_init(bar(B_P_EMPTY + i), 1); }
+      for (int i = 0; i < BT_STAGES; ++i) { mbar_init(bar(B_BT_FULL + i), tcs::NROLE); mbar_init(bar(B_BT_EMPTY + i), 1); }
+      for (int i = 0; i < D1_BUFS; ++i) { mbar_init(bar(B_D1_FULL + i), 1); mbar_init(bar(B_D1_EMPTY + i), tcs::NROLE); }
+      for (int i = 0; i < TT_BUFS; ++i) { mbar_init(bar(B_TT_FULL + i), tcs::NROLE); mbar_init(bar(B_TT_EMPTY + i), 1); }
+      for (int i = 0; i < P_BUFS; ++i) { mbar_init(bar(B_P_FULL + i), tcs::NROLE); mbar_init(bar(B_P_EMPTY + i), 1); }
       mbar_init(bar(B_D2_FULL), 1);
-      mbar_init(bar(B_D2_EMPTY), 128);
+      mbar_init(bar(B_D2_EMPTY), tcs::NROLE);
       fence_barrier_init();
     }
     __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bar(B_TMEM_PTR)), "r"(512)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    tmem_alloc512(bar(B_TMEM_PTR));
   }
   {  // Wlo chunk image: global -> shared (already swizzled)
-    const uint4* src = reinterpret_cast<const uint4*>(a.Wlo + (size_t)chunk * CM * K);
+    const uint4* src = reinterpret_cast<const uint4*>(a.Wls + (size_t)chunk * CM * K);
     uint4* dst = reinterpret_cast<uint4*>(smem + SM_WLO);
-    for (int i = tid; i < CM * K / 4; i += THREADS) dst[i] = __ldg(src + i);
+    for (int i = tid; i < CM * K / 4; i += tcs::THREADS) dst[i] = __ldg(src + i);
+    // constant columns 2D..127 of both frame-tile stages: zeros and the 1 of column 120
+    const int nconst = 32 - 2 * d4;
+    for (int i = tid; i < BT_STAGES * 2 * NF * nconst; i += tcs::THREADS) {
+      const int k4 = 2 * d4 + i % nconst;
+      int t = i / nconst;
+      const int r = t % NF; t /= NF;
+      const int part = t & 1, s = t >> 1;   // part 0 = hi, 1 = lo
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (part == 0 && k4 == K_ONE / 4) v.x = 1.f;
+      *reinterpret_cast<float4*>(smem + SM_BT + s * 32768 + part * 16384 + sw128_off(r, k4, NF)) = v;
+    }
     fence_proxy_async();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr_s;
-  if (warp < 4) {  // Whi rows -> TMEM columns [0,128): lane = mixture row
-    const int row = warp * 32 + lane;
-    const float4* src = reinterpret_cast<const float4*>(a.Whi + ((size_t)chunk * CM + row) * K);
-    for (int c = 0; c < 4; ++c) {
+  if (warp < 8) {  // Whi rows -> TMEM columns [0,128): lane = mixture row, 64 columns per warp
+    const int row = (warp & 3) * 32 + lane, half = warp >> 2;
+    const float4* src = reinterpret_cast<const float4*>(a.Whi + ((size_t)chunk * CM + row) * K + 64 * half);
+    for (int c = 0; c < 2; ++c) {
       float v[32];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float4 t = __ldg(src + c * 8 + i);
         v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
       }
-      tmem_st32(tmem + TM_WHI + 32 * c + ((uint32_t)(warp * 32) << 16), v);
+      tmem_st32(tmem + TM_WHI + 64 * half + 32 * c + ((uint32_t)((warp & 3) * 32) << 16), v);
     }
     tmem_st_wait();
   }
@@ -326,26 +574,42 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gmm_tc_kernel(TcArgs a) {
   __syncthreads();
   tc_fence_after();
 
-  if (warp >= 5) {
+  if (warp >= 9) {
     // =========================================================== producers
-    const int ptid = tid - 160;              // 0..127
-    const int quarter = warp & 3;            // TMEM lane quarter this warp may touch
-    const int j = quarter * 32 + lane;       // row of the transposed operand
-    const int items = NF * d4;               // float4 items of one raw tile
+    const int ptid = tid - 288;               // 0..255
+    const int quarter = warp & 3;             // TMEM lane quarter this warp may touch
+    const int half = (warp - 9) >> 2;         // which 16 frames of the transposed operand
+    const int j = quarter * 32 + lane;        // row of the transposed operand
+    const int items = NF * d4;                // float4 items of one raw tile (<= 480)
     const float4* X4 = reinterpret_cast<const float4*>(a.X);
     const int64_t total4 = a.N * d4;
-    float4 pre[4];
+    // item -> swizzled offsets of its x^2 and x chunks (the same for every tile)
+    uint32_t off_sq[2], off_x[2];
+    bool valid[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int idx = ptid + 256 * u;
+      valid[u] = idx < items;
+      const int r = valid[u] ? idx / d4 : 0, i = valid[u] ? idx - r * d4 : 0;
+      off_sq[u] = sw128_off(r, i, NF);
+      off_x[u] = sw128_off(r, d4 + i, NF);
+    }
+    const uint32_t off_lse = sw128_off(ptid & 31, K_ONE / 4, NF);
+    // transposed operand: which value this row carries
+    const bool t_sq = j < D, t_x = j >= D && j < 2 * D;
+    const int t_d = t_sq ? j : (t_x ? j - D : 0);
+    const float t_const = (j == K_ONE) ? 1.f : 0.f;
+    float4 pre[2];
     float lse_next = 0.f;
     auto prefetch = [&](int64_t it) {
       const int64_t tile = blockIdx.y + it * gridDim.y;
       const int64_t base4 = tile * items;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int idx = ptid + 128 * u;
-        const int64_t g = base4 + idx;
-        pre[u] = (idx < items && g < total4) ? __ldg(X4 + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int u = 0; u < 2; ++u) {
+        const int64_t g = base4 + ptid + 256 * u;
+        pre[u] = (valid[u] && g < total4) ? __ldg(X4 + g) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      if (STATS && ptid < NF) {
+      if (ptid < NF) {
         const int64_t f = tile * NF + ptid;
         const bool on = f < a.N && (a.sad == nullptr || a.sad[f] != 0);
         lse_next = on ? __ldg(a.lse2 + f) : 1e30f;   // 2^(lp - 1e30) = 0: masked / out of range
@@ -356,76 +620,61 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gmm_tc_kernel(TcArgs a) {
       const int buf = (int)(it & 1);
       float4* xr4 = reinterpret_cast<float4*>(smem + SM_XRAW + buf * (NF * MAX_D * 4));
       const float* xr = reinterpret_cast<const float*>(xr4);
-      float* lse_s = reinterpret_cast<float*>(smem + SM_LSE + buf * (NF * 4));
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int idx = ptid + 128 * u;
-        if (idx < items) xr4[idx] = pre[u];
-      }
-      if (STATS && ptid < NF) lse_s[ptid] = lse_next;
+      const float4 cur0 = pre[0], cur1 = pre[1];
+      const float lse_cur = lse_next;
+      if (valid[0]) xr4[ptid] = cur0;
+      if (valid[1]) xr4[ptid + 256] = cur1;
       if (it + 1 < my_tiles) prefetch(it + 1);
-      named_bar_sync(1, 128);
+      named_bar_sync(1, tcs::NROLE);
       // ---- (a) GEMM-1 operand tile: [frame r][k] K-major, SWIZZLE_128B, hi | lo
       {
         const int s = (int)(it % BT_STAGES);
         mbar_wait(bar(B_BT_EMPTY + s), (uint32_t)(((it / BT_STAGES) & 1) ^ 1));
         unsigned char* hi = smem + SM_BT + s * 32768;
         unsigned char* lo = hi + 16384;
-        auto put4 = [&](int r, int k4, float4 v) {   // k4 = k / 4
+        auto put = [&](uint32_t off, const float4& v) {
           float4 h, l;
-          h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-          l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
-          const uint32_t off = (uint32_t)(k4 >> 3) * 4096u + (uint32_t)r * 128u + (uint32_t)(((k4 & 7) ^ (r & 7)) << 4);
+          split4(v, h, l);
           *reinterpret_cast<float4*>(hi + off) = h;
           *reinterpret_cast<float4*>(lo + off) = l;
         };
-        for (int idx = ptid; idx < items; idx += 128) {
-          const int r = idx / d4, i = idx - r * d4;
-          const float4 x = xr4[idx];
-          put4(r, i, make_float4(x.x * x.x, x.y * x.y, x.z * x.z, x.w * x.w));
-          put4(r, d4 + i, x);
+        if (valid[0]) {
+          put(off_sq[0], make_float4(cur0.x * cur0.x, cur0.y * cur0.y, cur0.z * cur0.z, cur0.w * cur0.w));
+          put(off_x[0], cur0);
         }
-        // columns 2D .. 127: zeros, the constant 1 and -lse2
-        const int k4_first = 2 * d4;
-        for (int idx = ptid; idx < NF * (32 - k4_first); idx += 128) {
-          const int r = idx / (32 - k4_first), k4 = k4_first + (idx - r * (32 - k4_first));
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (k4 == K_ONE / 4) { v.x = 1.f; v.y = STATS ? -lse_s[r] : 0.f; }
-          put4(r, k4, v);
+        if (valid[1]) {
+          put(off_sq[1], make_float4(cur1.x * cur1.x, cur1.y * cur1.y, cur1.z * cur1.z, cur1.w * cur1.w));
+          put(off_x[1], cur1);
         }
+        if (ptid < NF) put(off_lse, make_float4(1.f, -lse_cur, 0.f, 0.f));
         fence_proxy_async();
         mbar_arrive(bar(B_BT_FULL + s));
       }
-      // ---- (b) GEMM-2 operand: T^T[j][frame] hi | lo -> TMEM (lane = j)
-      if (STATS) {
+      // ---- (b) GEMM-2 operand: T^T[j][frame] hi | lo -> TMEM (lane = j), 16 frames per warp
+      {
         const int ts = (int)(it % TT_BUFS);
-        mbar_wait(bar(B_TT_EMPTY + ts), (uint32_t)(((it / TT_BUFS) & 1) ^ 1));
-        tc_fence_after();
-        float h[32], l[32];
-        if (j < 2 * D) {
-          const bool sq = j < D;
-          const int d = sq ? j : j - D;
+        float h[16], l[16];
+        if (t_sq || t_x) {
 #pragma unroll
-          for (int b = 0; b < 32; ++b) {
-            const float x = xr[b * D + d];
-            const float v = sq ? x * x : x;
-            h[b] = tf32_rna(v);
-            l[b] = tf32_rna(v - h[b]);
+          for (int b = 0; b < 16; ++b) {
+            const float x = xr[(16 * half + b) * D + t_d];
+            split_tf32(t_sq ? x * x : x, h[b], l[b]);
           }
         } else {
-          const float v = (j == K_ONE) ? 1.f : 0.f;
 #pragma unroll
-          for (int b = 0; b < 32; ++b) { h[b] = v; l[b] = 0.f; }
+          for (int b = 0; b < 16; ++b) { h[b] = t_const; l[b] = 0.f; }
         }
-        const uint32_t taddr = tmem + TM_TT + 64 * ts + ((uint32_t)(quarter * 32) << 16);
-        tmem_st32(taddr, h);
-        tmem_st32(taddr + 32, l);
+        mbar_wait(bar(B_TT_EMPTY + ts), (uint32_t)(((it / TT_BUFS) & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t taddr = tmem + TM_TT + 64 * ts + 16 * half + ((uint32_t)(quarter * 32) << 16);
+        tmem_st16(taddr, h);
+        tmem_st16(taddr + 32, l);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(bar(B_TT_FULL + ts));
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // ========================================================== MMA issuer
     // The whole warp walks the (warp-uniform) schedule; one elected lane issues.
     if (my_tiles > 0) {
@@ -490,87 +739,62 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gmm_tc_kernel(TcArgs a) {
       issue_g1(0);
       for (int64_t it = 0; it < my_tiles; ++it) {
         if (it + 1 < my_tiles) issue_g1(it + 1);
-        if (STATS) issue_g2(it);
+        issue_g2(it);
       }
     }
   } else {
     // ============================================================ epilogue
-    const int row = warp * 32 + lane;                      // mixture within the chunk == TMEM lane
-    const uint32_t lane_field = (uint32_t)(warp * 32) << 16;
+    const int quarter = warp & 3, half = warp >> 2;
+    const int row = quarter * 32 + lane;                   // mixture within the chunk == TMEM lane
+    const uint32_t lane_field = (uint32_t)(quarter * 32) << 16;
+    uint32_t p_off[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) p_off[q] = sw128_off(row, 4 * half + q, CM);
     uint32_t d2_phase = 0;
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int b = (int)(it % D1_BUFS);
       mbar_wait(bar(B_D1_FULL + b), (uint32_t)((it / D1_BUFS) & 1));
       tc_fence_after();
-      float v[32];
-      tmem_ld32(tmem + TM_D1 + 32 * b + lane_field, v);
+      float v[16];
+      tmem_ld16(tmem + TM_D1 + 32 * b + 16 * half + lane_field, v);
       tc_fence_before();
       mbar_arrive(bar(B_D1_EMPTY + b));
-      if (STATS) {
+      float h[16], l[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = ex2f(v[i]);
-        const int pb = (int)(it % P_BUFS);
-        mbar_wait(bar(B_P_EMPTY + pb), (uint32_t)(((it / P_BUFS) & 1) ^ 1));
-        unsigned char* hi = smem + SM_P + pb * 32768 + row * 128;
-        unsigned char* lo = hi + 16384;
+      for (int i = 0; i < 16; ++i) split_tf32(ex2f(v[i]), h[i], l[i]);
+      const int pb = (int)(it % P_BUFS);
+      mbar_wait(bar(B_P_EMPTY + pb), (uint32_t)(((it / P_BUFS) & 1) ^ 1));
+      unsigned char* hi = smem + SM_P + pb * 32768;
+      unsigned char* lo = hi + 16384;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float4 h, l;
-          h.x = tf32_rna(v[4 * q]); h.y = tf32_rna(v[4 * q + 1]); h.z = tf32_rna(v[4 * q + 2]); h.w = tf32_rna(v[4 * q + 3]);
-          l.x = tf32_rna(v[4 * q] - h.x); l.y = tf32_rna(v[4 * q + 1] - h.y);
-          l.z = tf32_rna(v[4 * q + 2] - h.z); l.w = tf32_rna(v[4 * q + 3] - h.w);
-          const uint32_t off = (uint32_t)((q ^ (row & 7)) << 4);
-          *reinterpret_cast<float4*>(hi + off) = h;
-          *reinterpret_cast<float4*>(lo + off) = l;
-        }
-        fence_proxy_async();
-        mbar_arrive(bar(B_P_FULL + pb));
-        if (((it + 1) % a.flush_tiles) == 0 || it + 1 == my_tiles) {
-          // drain D2[j = row, mixture column] into the fp64 statistics
-          mbar_wait(bar(B_D2_FULL), d2_phase);
-          d2_phase ^= 1;
-          tc_fence_after();
-          double* dst = nullptr;
-          if (row < D) { if (a.want_second) dst = a.stats + a.M + (size_t)D * a.M + (size_t)row * a.M; }
-          else if (row < 2 * D) dst = a.stats + a.M + (size_t)(row - D) * a.M;
-          else if (row == K_ONE) dst = a.stats;
-          for (int c = 0; c < 4; ++c) {
-            float s[32];
-            tmem_ld32(tmem + TM_D2 + 32 * c + lane_field, s);
-            if (dst != nullptr) {
+      for (int q = 0; q < 4; ++q) {
+        *reinterpret_cast<float4*>(hi + p_off[q]) = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+        *reinterpret_cast<float4*>(lo + p_off[q]) = make_float4(l[4 * q], l[4 * q + 1], l[4 * q + 2], l[4 * q + 3]);
+      }
+      fence_proxy_async();
+      mbar_arrive(bar(B_P_FULL + pb));
+      if (((it + 1) % a.flush_tiles) == 0 || it + 1 == my_tiles) {
+        // drain D2[j = row, mixture column] into the fp64 statistics (64 columns per warp)
+        mbar_wait(bar(B_D2_FULL), d2_phase);
+        d2_phase ^= 1;
+        tc_fence_after();
+        double* dst = nullptr;
+        if (row < D) { if (a.want_second) dst = a.stats + a.M + (size_t)D * a.M + (size_t)row * a.M; }
+        else if (row < 2 * D) dst = a.stats + a.M + (size_t)(row - D) * a.M;
+        else if (row == K_ONE) dst = a.stats;
+        for (int c = 0; c < 2; ++c) {
+          float s[32];
+          tmem_ld32(tmem + TM_D2 + 64 * half + 32 * c + lane_field, s);
+          if (dst != nullptr) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const int m = chunk * CM + 32 * c + i;
-                if (m < a.M) atomicAdd(dst + m, (double)s[i]);
-              }
+            for (int i = 0; i < 32; ++i) {
+              const int m = chunk * CM + 64 * half + 32 * c + i;
+              if (m < a.M) atomicAdd(dst + m, (double)s[i]);
             }
           }
-          tc_fence_before();
-          mbar_arrive(bar(B_D2_EMPTY));
         }
-      } else {
-        // pass 1: max / sum over the 128 mixture lanes for each of the 32 frames
-        float pm = 0.f, ps = 0.f;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float mx;
-          asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(mx) : "f"(v[i]));
-          const float e = ex2f(v[i] - mx);                       // in [0, 1]
-          const uint32_t fx = __float2uint_rn(e * 67108864.f);   // 2^26 fixed point: warp sum < 2^31
-          uint32_t sum;
-          asm volatile("redux.sync.add.u32 %0, %1, 0xffffffff;" : "=r"(sum) : "r"(fx));
-          if (lane == i) { pm = mx; ps = (float)sum * (1.f / 67108864.f); }
-        }
-        float2* part_s = reinterpret_cast<float2*>(smem + SM_PART) + (it & 1) * (4 * NF);
-        part_s[warp * NF + lane] = make_float2(pm, ps);
-        named_bar_sync(2, 128);
-        if (warp == 0) {
-          float2 p0 = part_s[lane], p1 = part_s[NF + lane], p2 = part_s[2 * NF + lane], p3 = part_s[3 * NF + lane];
-          const float mx = fmaxf(fmaxf(p0.x, p1.x), fmaxf(p2.x, p3.x));
-          const float sm = p0.y * ex2f(p0.x - mx) + p1.y * ex2f(p1.x - mx) + p2.y * ex2f(p2.x - mx) + p3.y * ex2f(p3.x - mx);
-          const int64_t tile = blockIdx.y + it * gridDim.y;
-          a.part[(size_t)chunk * a.part_stride + tile * NF + lane] = make_float2(mx, sm);
-        }
+        tc_fence_before();
+        mbar_arrive(bar(B_D2_EMPTY));
       }
     }
   }
@@ -578,9 +802,9 @@ __global__ void __launch_bounds__(tc::THREADS, 1) gmm_tc_kernel(TcArgs a) {
   // ------------------------------------------------------------ teardown
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+    tmem_dealloc512(tmem);
   }
 }
 
@@ -624,7 +848,7 @@ bool gmm_tc_supported(const odin_gmm* g) {
 
 int gmm_tc_refresh(odin_gmm* g, cudaStream_t st) {
   gmm_tc_prepare_kernel<<<ceil_div(g->Mpad, 128), 128, 0, st>>>(g->d_mean, g->d_var, g->d_w, g->D, g->M, g->Mpad,
-                                                                g->d_Whi, g->d_Wlo);
+                                                                g->d_Whi, g->d_Whs, g->d_Wlo);
   ODIN_LAUNCH_CHECK("gmm_tc_prepare_kernel");
   return ODIN_OK;
 }
@@ -639,20 +863,14 @@ static int tc_flush_tiles() {
 static int64_t tc_sub_batch() {
   const char* e = getenv("ODIN_TC_SUB_BATCH");
   int64_t v = e ? atoll(e) : (int64_t)1 << 20;  // bounds the partial-LSE workspace
-  return v < tc::NF ? tc::NF : v;
+  return v < tcl::TF ? tcl::TF : v;
 }
 
-template <bool STATS>
-static int tc_launch(odin_gmm* g, TcArgs& a, cudaStream_t st) {
+static dim3 tc_grid(const odin_gmm* g, int64_t n_tiles) {
   const int nchunks = g->Mpad / tc::CM;
-  const int64_t n_tiles = ceil_div<int64_t>(a.N, tc::NF);
   int64_t splits = std::max<int64_t>(1, sm_count() / nchunks);
   splits = std::min<int64_t>(splits, n_tiles);
-  auto k = gmm_tc_kernel<STATS>;
-  ODIN_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
-  k<<<dim3(nchunks, (unsigned)splits), tc::THREADS, tc::SMEM_BYTES, st>>>(a);
-  ODIN_LAUNCH_CHECK(STATS ? "gmm_tc_kernel<stats>" : "gmm_tc_kernel<lse>");
-  return ODIN_OK;
+  return dim3(nchunks, (unsigned)splits);
 }
 
 int gmm_lse_tc(odin_gmm* g, const float* X, const uint8_t* sad, int64_t N, float* lse, double* stats,
@@ -660,7 +878,7 @@ int gmm_lse_tc(odin_gmm* g, const float* X, const uint8_t* sad, int64_t N, float
   if (N <= 0) return ODIN_OK;
   const int nchunks = g->Mpad / tc::CM;
   const int64_t sub = std::min<int64_t>(N, tc_sub_batch());
-  const int64_t stride = ceil_div<int64_t>(sub, tc::NF) * tc::NF;
+  const int64_t stride = ceil_div<int64_t>(sub, tcl::TF) * tcl::TF;
   const int64_t need = stride * nchunks;
   if (need > g->part_cap) {
     if (g->d_part) ODIN_CUDA_CHECK(cudaFree(g->d_part));
@@ -669,15 +887,17 @@ int gmm_lse_tc(odin_gmm* g, const float* X, const uint8_t* sad, int64_t N, float
     ODIN_CUDA_CHECK(cudaMalloc(&g->d_part, need * sizeof(float2)));
     g->part_cap = need;
   }
+  ODIN_CUDA_CHECK(cudaFuncSetAttribute(gmm_tc_lse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)tcl::SMEM_BYTES));
   double* statL = stats ? stats + (stats_size(g->D, g->M) - 2) : nullptr;
   for (int64_t s0 = 0; s0 < N; s0 += sub) {
     const int64_t n = std::min<int64_t>(sub, N - s0);
     TcArgs a{};
-    a.X = X + s0 * g->D; a.sad = nullptr; a.N = n; a.D = g->D; a.M = g->M;
-    a.Whi = g->d_Whi; a.Wlo = g->d_Wlo; a.part = reinterpret_cast<float2*>(g->d_part); a.part_stride = stride;
-    a.flush_tiles = 1 << 30;
-    int rc = tc_launch<false>(g, a, st);
-    if (rc) return rc;
+    a.X = X + s0 * g->D; a.N = n; a.D = g->D; a.M = g->M;
+    a.Whi = g->d_Whi; a.Whs = g->d_Whs; a.Wls = g->d_Wlo;
+    a.part = reinterpret_cast<float2*>(g->d_part); a.part_stride = stride;
+    gmm_tc_lse_kernel<<<tc_grid(g, ceil_div<int64_t>(n, tcl::TF)), tcl::THREADS, tcl::SMEM_BYTES, st>>>(a);
+    ODIN_LAUNCH_CHECK("gmm_tc_lse_kernel");
     gmm_tc_combine_kernel<<<(unsigned)ceil_div<int64_t>(n, 256), 256, 0, st>>>(
         reinterpret_cast<const float2*>(g->d_part), nchunks, stride, n, sad ? sad + s0 : nullptr, lse + s0, statL);
     ODIN_LAUNCH_CHECK("gmm_tc_combine_kernel");
@@ -690,9 +910,13 @@ int gmm_stats_tc(odin_gmm* g, const float* X, const uint8_t* sad, int64_t N, con
   if (N <= 0) return ODIN_OK;
   TcArgs a{};
   a.X = X; a.sad = sad; a.N = N; a.D = g->D; a.M = g->M;
-  a.Whi = g->d_Whi; a.Wlo = g->d_Wlo; a.lse2 = lse; a.stats = stats; a.want_second = want_second;
+  a.Whi = g->d_Whi; a.Whs = g->d_Whs; a.Wls = g->d_Wlo; a.lse2 = lse; a.stats = stats; a.want_second = want_second;
   a.flush_tiles = tc_flush_tiles();
-  return tc_launch<true>(g, a, st);
+  ODIN_CUDA_CHECK(cudaFuncSetAttribute(gmm_tc_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)tc::SMEM_BYTES));
+  gmm_tc_stats_kernel<<<tc_grid(g, ceil_div<int64_t>(N, tc::NF)), tcs::THREADS, tc::SMEM_BYTES, st>>>(a);
+  ODIN_LAUNCH_CHECK("gmm_tc_stats_kernel");
+  return ODIN_OK;
 }
 
 }  // namespace odin
