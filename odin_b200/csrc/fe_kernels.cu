@@ -398,8 +398,9 @@ __global__ void __launch_bounds__(256) fe_post_kernel(PostArgs a) {
   const int HR = (a.order >= 1) ? h : 0;
   const int NR = PT + HL + HR;             // rows of mel / cepstra held
   const int ND = PT + ((a.order >= 2) ? a.W - 1 : 0);  // rows of first-order deltas held
-  float* smel = sm;                         // [NR][n_mels]
-  float* scep = smel + NR * a.n_mels;       // [NR][n_c1]
+  const int MS = a.n_mels | 1;              // odd row stride: lanes walking rows hit distinct banks
+  float* smel = sm;                         // [NR][MS]
+  float* scep = smel + NR * MS;             // [NR][n_c1]
   float* sd1 = scep + NR * a.n_c1;          // [ND][n_ceps]
   float* sdct = sd1 + ND * a.n_ceps;        // [n_c1][n_mels]
   float* staps = sdct + a.n_c1 * a.n_mels;  // [W]
@@ -417,25 +418,40 @@ __global__ void __launch_bounds__(256) fe_post_kernel(PostArgs a) {
   for (int i = tid; i < a.n_c1 * a.n_mels; i += 256) sdct[i] = a.dct[i];
   for (int i = tid; i < a.W; i += 256) staps[i] = a.taps[i];
   for (int i = tid; i < nrows * a.n_mels; i += 256) {
-    const int r = i / a.n_mels;
+    const int r = i / a.n_mels, m = i - r * a.n_mels;
     const int64_t g = (base + lo) * a.n_mels + i;
     float v = fmaxf(a.mspec[g], floor_db);
-    smel[i] = v;
+    smel[r * MS + m] = v;
     const int t = lo + r;
     if (a.write_mspec && t >= t0 && t < t0 + nf) a.mspec[g] = v;
   }
   __syncthreads();
   if (a.n_ceps <= 0) return;
-  // DCT (signal.py:1711): cep[r][c] = sum_m dct[c][m] * mel[r][m]
-  for (int i = tid; i < nrows * a.n_c1; i += 256) {
-    const int r = i / a.n_c1, c = i - r * a.n_c1;
-    const float* mrow = smel + r * a.n_mels;
-    const float* drow = sdct + c * a.n_mels;
-    float acc = 0.f;
-    for (int m = 0; m < a.n_mels; ++m) acc = fmaf(drow[m], mrow[m], acc);
-    scep[i] = acc;
-    const int t = lo + r;
-    if (c == 0 && a.c0 != nullptr && t >= t0 && t < t0 + nf) a.c0[base + t] = acc;
+  // DCT (signal.py:1711): cep[r][c] = sum_m dct[c][m] * mel[r][m].  One work item = one row x
+  // a group of CG coefficients: the mel value is read once per CG FMAs and the DCT entries are
+  // warp-wide broadcasts (lanes of a warp share the coefficient group).
+  {
+    constexpr int CG = 8;
+    const int ncg = (a.n_c1 + CG - 1) / CG;
+    for (int i = tid; i < nrows * ncg; i += 256) {
+      const int g = i / nrows, r = i - g * nrows;
+      const int c0i = g * CG;
+      const float* mrow = smel + r * MS;
+      float acc[CG];
+#pragma unroll
+      for (int j = 0; j < CG; ++j) acc[j] = 0.f;
+      for (int m = 0; m < a.n_mels; ++m) {
+        const float x = mrow[m];
+#pragma unroll
+        for (int j = 0; j < CG; ++j)
+          if (c0i + j < a.n_c1) acc[j] = fmaf(sdct[(c0i + j) * a.n_mels + m], x, acc[j]);
+      }
+      const int t = lo + r;
+#pragma unroll
+      for (int j = 0; j < CG; ++j)
+        if (c0i + j < a.n_c1) scep[r * a.n_c1 + c0i + j] = acc[j];
+      if (g == 0 && a.c0 != nullptr && t >= t0 && t < t0 + nf) a.c0[base + t] = acc[0];
+    }
   }
   __syncthreads();
   if (a.feat == nullptr) return;
@@ -500,11 +516,20 @@ struct VadArgs {
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
 
-// 1-D EM of sklearn GaussianMixture with fixed inits (see oracle/frontend.py _em_1d).
-// Returns false where sklearn would raise ValueError.
-__device__ bool vad_em(const float* __restrict__ x, int n, int nc, int max_iter, int lane, double* mu_out,
-                       double* prec_out) {
-  constexpr int KMAX = 4;
+// 1-D EM of sklearn GaussianMixture with fixed inits (see oracle/frontend.py _em_1d),
+// block-cooperative: every thread of the CTA walks a strided share of the frames,
+// the ten sufficient statistics are reduced warp -> CTA in a fixed order and every
+// thread then runs the (tiny) M-step redundantly on identical numbers, so control
+// flow stays uniform.  Returns false where sklearn would raise ValueError.
+constexpr int VAD_THREADS = 256;
+constexpr int VAD_WARPS = VAD_THREADS / 32;
+constexpr int VAD_KMAX = 4;
+constexpr int VAD_NRED = 3 * VAD_KMAX + 1;
+
+__device__ bool vad_em(const float* __restrict__ x, int n, int nc, int max_iter, double (*red)[VAD_NRED],
+                       int* flag, double* mu_out, double* prec_out) {
+  constexpr int KMAX = VAD_KMAX;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (n < max(nc, 2)) return false;
   double w[KMAX], mu[KMAX], pch[KMAX];
   for (int k = 0; k < nc; ++k) {
@@ -512,9 +537,15 @@ __device__ bool vad_em(const float* __restrict__ x, int n, int nc, int max_iter,
     mu[k] = -2.0 + 4.0 * k / (double)(nc - 1);
     pch[k] = 1.0;
   }
+  if (tid == 0) *flag = 0;
+  __syncthreads();
   int bad = 0;
-  for (int i = lane; i < n; i += 32) if (!isfinite(x[i])) bad = 1;
-  if (__any_sync(0xffffffffu, bad)) return false;
+  for (int i = tid; i < n; i += VAD_THREADS) if (!isfinite(x[i])) bad = 1;
+  if (bad) *flag = 1;
+  __syncthreads();
+  bad = *flag;
+  __syncthreads();
+  if (bad) return false;
   const double LOG2PI = 1.8378770664093454835606594728112;
   double lower = -INFINITY;
   for (int it = 0; it < max_iter; ++it) {
@@ -527,7 +558,7 @@ __device__ bool vad_em(const float* __restrict__ x, int n, int nc, int max_iter,
       lw[k] = log(w[k]);
     }
     double nk[KMAX] = {0, 0, 0, 0}, sx[KMAX] = {0, 0, 0, 0}, sxx[KMAX] = {0, 0, 0, 0}, lsum = 0.0;
-    for (int i = lane; i < n; i += 32) {
+    for (int i = tid; i < n; i += VAD_THREADS) {
       const float xf = x[i];
       const double xd = (double)xf, x2 = (double)__fmul_rn(xf, xf);  // x*x is float32 in sklearn
       double wl[KMAX], mx = -INFINITY;
@@ -548,13 +579,25 @@ __device__ bool vad_em(const float* __restrict__ x, int n, int nc, int max_iter,
         sxx[k] = fma(r, x2, sxx[k]);
       }
     }
+    // CTA reduction (fixed order: lanes by xor butterfly, then warps 0..7)
     lsum = warp_sum(lsum);
+    for (int k = 0; k < nc; ++k) { nk[k] = warp_sum(nk[k]); sx[k] = warp_sum(sx[k]); sxx[k] = warp_sum(sxx[k]); }
+    if (lane == 0) {
+      red[warp][0] = lsum;
+      for (int k = 0; k < nc; ++k) { red[warp][1 + k] = nk[k]; red[warp][1 + KMAX + k] = sx[k]; red[warp][1 + 2 * KMAX + k] = sxx[k]; }
+    }
+    __syncthreads();
+    lsum = 0.0;
+    for (int k = 0; k < nc; ++k) { nk[k] = 0.0; sx[k] = 0.0; sxx[k] = 0.0; }
+    for (int wv = 0; wv < VAD_WARPS; ++wv) {
+      lsum += red[wv][0];
+      for (int k = 0; k < nc; ++k) { nk[k] += red[wv][1 + k]; sx[k] += red[wv][1 + KMAX + k]; sxx[k] += red[wv][1 + 2 * KMAX + k]; }
+    }
+    __syncthreads();  // red is rewritten in the next iteration
     double nksum = 0.0;
     bool collapsed = false;
     for (int k = 0; k < nc; ++k) {
-      nk[k] = warp_sum(nk[k]) + 10.0 * DBL_EPSILON;
-      sx[k] = warp_sum(sx[k]);
-      sxx[k] = warp_sum(sxx[k]);
+      nk[k] += 10.0 * DBL_EPSILON;
       nksum += nk[k];
     }
     for (int k = 0; k < nc; ++k) {
@@ -574,11 +617,13 @@ __device__ bool vad_em(const float* __restrict__ x, int n, int nc, int max_iter,
   return true;
 }
 
-__global__ void __launch_bounds__(128) fe_vad_gmm_kernel(VadArgs a) {
-  const int lane = threadIdx.x & 31;
-  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nw = (gridDim.x * blockDim.x) >> 5;
-  for (int u = wid; u < a.n_utt; u += nw) {
+// One CTA per utterance (grid-stride over utterances).
+__global__ void __launch_bounds__(VAD_THREADS) fe_vad_gmm_kernel(VadArgs a) {
+  __shared__ double red[VAD_WARPS][VAD_NRED];
+  __shared__ float s_ms[2];
+  __shared__ int s_flag;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int u = blockIdx.x; u < a.n_utt; u += gridDim.x) {
     const int64_t base = a.frame_off[u];
     const int n = (int)(a.frame_off[u + 1] - base);
     if (n <= 0) continue;
@@ -592,14 +637,18 @@ __global__ void __launch_bounds__(128) fe_vad_gmm_kernel(VadArgs a) {
     while (true) {
       // standardise in float32 exactly as numpy does (signal.py:305); the retry
       // path of the reference re-standardises the already standardised vector
-      const MeanStdF32 ms = warp_np_mean_std_f32(src, n, lane);
-      const float mean = ms.mean, sd = ms.std;
-      __syncwarp();
-      for (int i = lane; i < n; i += 32) xs[i] = __fdiv_rn(__fsub_rn(src[i], mean), sd);
-      __syncwarp();
+      __syncthreads();  // previous readers of xs / s_ms are done
+      if (warp == 0) {
+        const MeanStdF32 ms = warp_np_mean_std_f32(src, n, lane);
+        if (lane == 0) { s_ms[0] = ms.mean; s_ms[1] = ms.std; }
+      }
+      __syncthreads();
+      const float mean = s_ms[0], sd = s_ms[1];
+      for (int i = tid; i < n; i += VAD_THREADS) xs[i] = __fdiv_rn(__fsub_rn(src[i], mean), sd);
+      __syncthreads();
       src = xs;
       double mu[4], prec[4];
-      if (vad_em(xs, n, nc, a.iters, lane, mu, prec)) {
+      if (vad_em(xs, n, nc, a.iters, red, &s_flag, mu, prec)) {
         int kb = 0;
         for (int k = 1; k < nc; ++k) if (mu[k] > mu[kb]) kb = k;
         thr = dadd(mu[kb], -dmul(a.mode, sqrt(1.0 / prec[kb])));
@@ -609,14 +658,14 @@ __global__ void __launch_bounds__(128) fe_vad_gmm_kernel(VadArgs a) {
       if (nc - 1 >= 2) { --nc; continue; }
       break;
     }
-    if (a.thr_out != nullptr && lane == 0) a.thr_out[u] = ok ? thr : 0.0;
+    if (a.thr_out != nullptr && tid == 0) a.thr_out[u] = ok ? thr : 0.0;
     if (!ok) {
-      for (int i = lane; i < n; i += 32) out[i] = 0;
+      for (int i = tid; i < n; i += VAD_THREADS) out[i] = 0;
       continue;
     }
     auto raw = [xs, thr](int i) -> int { return ((double)xs[i] > thr) ? 1 : 0; };
     const bool do_smooth = a.smooth >= 3 && n >= a.smooth;
-    for (int i = lane; i < n; i += 32)
+    for (int i = tid; i < n; i += VAD_THREADS)
       out[i] = do_smooth ? (uint8_t)smooth_flat_ge_f(raw, n, a.smooth, false, i) : (uint8_t)raw(i);
   }
 }
@@ -810,7 +859,7 @@ int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t 
     const int HL = (c.delta_order >= 2) ? (c.delta_width - 1 + h) : (c.delta_order == 1 ? h : 0);
     const int HR = (c.delta_order >= 1) ? h : 0;
     const int NR = PT + HL + HR, ND = PT + ((c.delta_order >= 2) ? c.delta_width - 1 : 0);
-    size_t smem = sizeof(float) * ((size_t)NR * fe->n_mels + (size_t)NR * fe->n_c1 + (size_t)ND * c.n_ceps +
+    size_t smem = sizeof(float) * ((size_t)NR * (fe->n_mels | 1) + (size_t)NR * fe->n_c1 + (size_t)ND * c.n_ceps +
                                    (size_t)fe->n_c1 * fe->n_mels + c.delta_width + 4);
     if (smem > 227 * 1024) return set_error(ODIN_EINVAL, "post kernel needs %zu B smem", smem);
     ODIN_CUDA_CHECK(cudaFuncSetAttribute(fe_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -838,7 +887,8 @@ int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t 
     if (c.vad_kind == 1) {
       if (d_energy == nullptr) return set_error(ODIN_EINVAL, "SADgmm needs d_energy");
       v.x = d_energy;
-      fe_vad_gmm_kernel<<<grid, 128, 0, st>>>(v);
+      const int grid_gmm = (int)std::min<int64_t>(n_utt, (int64_t)sm_count() * 8);
+      fe_vad_gmm_kernel<<<grid_gmm, VAD_THREADS, 0, st>>>(v);
       ODIN_LAUNCH_CHECK("fe_vad_gmm_kernel");
     } else {
       if (d_c0 == nullptr) return set_error(ODIN_EINVAL, "SADthreshold needs d_c0");
