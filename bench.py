@@ -42,7 +42,7 @@ def parse():
   p.add_argument("--impl", default="ours", choices=["ours", "reference"])
   p.add_argument("--frames", type=int, default=6_000_000, help="frames per GPU (60-dim fp32)")
   p.add_argument("--nmix", type=int, default=NMIX)
-  p.add_argument("--kernel-impl", type=int, default=0, help="0 auto, 1 fp32 CUDA cores, 2 tcgen05")
+  p.add_argument("--kernel-impl", type=int, default=0, help="0 auto, 1 fp32 CUDA cores, 2 tcgen05 3xTF32, 3 tcgen05 3xFP16")
   p.add_argument("--mfcc-hours", type=float, default=2.0, help="hours of 16 kHz audio per GPU for the MFCC leg")
   p.add_argument("--no-mfcc", action="store_true")
   p.add_argument("--no-cpu-baseline", action="store_true")
@@ -374,24 +374,30 @@ def run_ours(args):
   total_frames = N * world
   value = total_frames / step_s
   useful = useful_flops_per_frame(M) * N
-  # dominant kernel = statistics kernel; TF32 tensor peak = half the measured bf16 peak; a
-  # 3xTF32 product issues 3 MMAs per useful one
-  tf32_peak = peaks["bf16_sustained"] / 2.0
-  stats_useful = (240 + 240) * M * N  # its own logprob recompute + statistics GEMM
+  # dominant kernel = statistics kernel (its own log-likelihood GEMM + the statistics GEMM).  Dense
+  # peak of the MMA kind: fp16 = the measured bf16 figure, tf32 = half of it; a split-precision
+  # product issues 3 MMAs per useful one, so the roofline is peak / 3.
+  lib.odin_gmm_last_estep_frames.restype = C.c_int64
+  n_timed = int(lib.odin_gmm_last_estep_frames(g._handle))   # frames covered by lse_ms / stats_ms
+  kind_peak = peaks["bf16_sustained"] if impl_used == 3 else peaks["bf16_sustained"] / 2.0
+  stats_useful = (240 + 240) * M * n_timed
   achieved = stats_useful / (stats_ms / 1e3) / 1e12
+  names = {1: "gmm_stats_kernel (fp32 CUDA cores)", 2: "gmm_tc_stats_kernel (3xTF32 tcgen05)",
+           3: "gmm_h_stats_kernel (3xFP16 tcgen05)"}
   roofline = {
-      "bound": "tensor", "achieved": achieved, "peak": tf32_peak / 3.0, "unit": "TFLOP/s",
-      "frac": achieved / (tf32_peak / 3.0), "traffic": None,
-      "kernel": "gmm_stats_tc_kernel" if impl_used == 2 else "gmm_stats_kernel (fp32 CUDA cores)",
-      "kernel_ms": {"lse": lse_ms, "stats": stats_ms},
-      "peak_source": "%s bf16_tflops_sustained/2 (TF32 dense) /3 (3xTF32)" % peaks["source"],
+      "bound": "tensor", "achieved": achieved, "peak": kind_peak / 3.0, "unit": "TFLOP/s",
+      "frac": achieved / (kind_peak / 3.0), "traffic": None,
+      "kernel": names.get(impl_used, str(impl_used)),
+      "kernel_ms": {"lse": lse_ms, "stats": stats_ms, "frames": n_timed},
+      "peak_source": "%s bf16_tflops_sustained%s / 3 (split precision)" % (
+          peaks["source"], " (= fp16 dense)" if impl_used == 3 else " / 2 (TF32 dense)"),
       "algorithmic_flops_per_frame": (240 + 240) * M,
       "step_useful_tflops": useful / step_s / 1e12,
   }
   line = {
       "metric": "ubm%d_baum_welch_frames_per_s" % M, "value": value, "unit": "frames/s", "n_gpus": world,
       "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": step_s * 1e3, "higher_is_better": True,
-      "scaling": "weak", "vs_baseline": None, "dtype": "tf32x3" if impl_used == 2 else "f32", "data": "synthetic",
+      "scaling": "weak", "vs_baseline": None, "dtype": {2: "tf32x3", 3: "f16x3"}.get(impl_used, "f32"), "data": "synthetic",
       "config": {"workload": "config 4 shard: 2048-mix diagonal UBM EM iteration (N/F/S + NCCL all-reduce + M-step), "
                              "60-dim frames resident in HBM",
                  "nmix": M, "feat_dim": D, "frames_per_gpu": N, "parallelism": "dp%d" % world,

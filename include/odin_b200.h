@@ -153,7 +153,8 @@ int odin_gmm_set_params(odin_gmm_t* g, int32_t nmix, const float* d_mean, const 
  * batches may accumulate into the same buffer, which replaces the host-side sum
  * of gmm_tmat.py:1148-1156,249-265).  d_sad (uint8 [N]) may be NULL; frames with
  * sad == 0 are skipped (gmm_tmat.py:162-164).  want_second = 0 skips S.
- * impl: 0 = auto, 1 = fp32 CUDA-core kernels, 2 = 3xTF32 tcgen05 kernels. */
+ * impl: 0 = auto, 1 = fp32 CUDA-core kernels, 2 = 3xTF32 tcgen05 kernels (M >= 96),
+ * 3 = 3xFP16 tcgen05 kernels (M >= 256; D % 4 == 0 and D <= 60 for both tensor paths). */
 int odin_gmm_estep(odin_gmm_t* g, const float* d_X, const uint8_t* d_sad, int64_t n_frames,
                    int32_t want_second, double* d_stats, int32_t impl, void* stream);
 
@@ -185,10 +186,12 @@ int odin_gmm_score(odin_gmm_t* g, const float* d_X, int64_t n_frames, float* d_l
 
 /* Device time of the kernels of the most recent call, measured with CUDA events
  * recorded on the caller's stream around each kernel (blocks until they complete).
- * odin_gmm_last_estep_ms: log-sum-exp kernel and statistics kernel of the last
- * odin_gmm_estep; *impl_used = 1 (fp32) or 2 (tcgen05).
+ * odin_gmm_last_estep_ms: log-sum-exp kernel(s) and statistics kernel of the last
+ * odin_gmm_estep; *impl_used = 1 (fp32), 2 (tcgen05 3xTF32) or 3 (tcgen05 3xFP16).
  * odin_fe_last_run_ms: ms4 = {DC sums, frame kernel, utterance pass, VAD}. */
 int odin_gmm_last_estep_ms(odin_gmm_t* g, float* lse_ms, float* stats_ms, int32_t* impl_used);
+/* Frames covered by those events (impl 3 times the last sub-batch only; others the whole call). */
+int64_t odin_gmm_last_estep_frames(const odin_gmm_t* g);
 int odin_fe_last_run_ms(odin_fe_t* fe, float* ms4);
 
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */

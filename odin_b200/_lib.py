@@ -62,6 +62,7 @@ SIGNATURES = {
     "odin_gmm_utt_stats": (C.c_int, [_vp, _vp, _vp, _pi64, _i32, _vp, _vp, _i32, _vp]),
     "odin_gmm_last_estep_ms": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                          C.POINTER(C.c_int32)]),
+    "odin_gmm_last_estep_frames": (_i64, [_vp]),
     "odin_fe_last_run_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "odin_gmm_score": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
 }

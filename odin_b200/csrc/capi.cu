@@ -384,6 +384,7 @@ void odin_gmm_destroy(odin_gmm_t* g) {
   if (!g) return;
   cudaFree(g->d_mean); cudaFree(g->d_var); cudaFree(g->d_w); cudaFree(g->d_Wk); cudaFree(g->d_cst);
   cudaFree(g->d_Whi); cudaFree(g->d_Whs); cudaFree(g->d_Wlo); cudaFree(g->d_part); cudaFree(g->d_lse); cudaFree(g->d_prev); cudaFree(g->d_off);
+  gmm_h_free(g);
   if (g->h_off) cudaFreeHost(g->h_off);
   for (int i = 0; i < 3; ++i) if (g->ev[i]) cudaEventDestroy(g->ev[i]);
   delete g;
@@ -408,11 +409,14 @@ int odin_gmm_set_params(odin_gmm_t* g, int32_t nmix, const float* d_mean, const 
   return gmm_refresh_constants(g, st);
 }
 
-static int pick_impl(odin_gmm* g, int impl, bool* use_tc) {
-  if (impl < 0 || impl > 2) return set_error(ODIN_EINVAL, "impl must be 0 (auto), 1 (fp32) or 2 (tcgen05)");
-  bool ok = gmm_tc_supported(g);
-  if (impl == 2 && !ok) return set_error(ODIN_EINVAL, "tcgen05 path unsupported for D=%d M=%d", g->D, g->M);
-  *use_tc = (impl == 2) || (impl == 0 && ok);
+// impl: 0 auto, 1 fp32 CUDA cores, 2 3xTF32 tcgen05, 3 3xFP16 tcgen05
+static int pick_impl(odin_gmm* g, int impl, int* use) {
+  if (impl < 0 || impl > 3)
+    return set_error(ODIN_EINVAL, "impl must be 0 (auto), 1 (fp32), 2 (tcgen05 3xTF32) or 3 (tcgen05 3xFP16)");
+  const bool ok2 = gmm_tc_supported(g), ok3 = gmm_h_supported(g);
+  if (impl == 2 && !ok2) return set_error(ODIN_EINVAL, "tcgen05 3xTF32 path unsupported for D=%d M=%d", g->D, g->M);
+  if (impl == 3 && !ok3) return set_error(ODIN_EINVAL, "tcgen05 3xFP16 path unsupported for D=%d M=%d", g->D, g->M);
+  *use = impl != 0 ? impl : (ok3 ? 3 : (ok2 ? 2 : 1));
   return ODIN_OK;
 }
 
@@ -421,13 +425,20 @@ int odin_gmm_estep(odin_gmm_t* g, const float* d_X, const uint8_t* d_sad, int64_
   if (!g || !d_X || !d_stats || n_frames < 0) return set_error(ODIN_EINVAL, "bad argument");
   if (g->M <= 0) return set_error(ODIN_EINVAL, "odin_gmm_set_params has not been called");
   if (n_frames == 0) return ODIN_OK;
-  bool tc;
-  int rc = pick_impl(g, impl, &tc);
+  int use;
+  int rc = pick_impl(g, impl, &use);
   if (rc) return rc;
+  const bool tc = use == 2;
   cudaStream_t st = as_stream(stream);
-  if ((rc = gmm_reserve_lse(g, n_frames))) return rc;
   if (g->ev[0] == nullptr)
     for (int i = 0; i < 3; ++i) ODIN_CUDA_CHECK(cudaEventCreate(&g->ev[i]));
+  if (use == 3) {
+    if ((rc = gmm_estep_h(g, d_X, d_sad, n_frames, want_second, d_stats, st))) return rc;
+    g->ev_valid = true;
+    g->last_impl = 3;
+    return ODIN_OK;
+  }
+  if ((rc = gmm_reserve_lse(g, n_frames))) return rc;
   ODIN_CUDA_CHECK(cudaEventRecord(g->ev[0], st));
   if (tc) rc = gmm_lse_tc(g, d_X, d_sad, n_frames, g->d_lse, d_stats, st);
   else rc = gmm_lse_ffma(g, d_X, d_sad, n_frames, g->d_lse, d_stats, st);
@@ -439,8 +450,11 @@ int odin_gmm_estep(odin_gmm_t* g, const float* d_X, const uint8_t* d_sad, int64_
   ODIN_CUDA_CHECK(cudaEventRecord(g->ev[2], st));
   g->ev_valid = true;
   g->last_impl = tc ? 2 : 1;
+  g->last_frames = n_frames;
   return ODIN_OK;
 }
+
+int64_t odin_gmm_last_estep_frames(const odin_gmm_t* g) { return g ? g->last_frames : ODIN_EINVAL; }
 
 int odin_gmm_last_estep_ms(odin_gmm_t* g, float* lse_ms, float* stats_ms, int32_t* impl_used) {
   if (!g || !lse_ms || !stats_ms) return set_error(ODIN_EINVAL, "null argument");

@@ -29,6 +29,17 @@ struct odin_gmm {
   // pass-1 workspace of the tcgen05 path: per-chunk partial (max, sum) per frame
   void* d_part = nullptr;
   int64_t part_cap = 0;  // float2 elements
+  // 3xFP16 tcgen05 path (gmm_h.cu): column scales, scaled model images, per-sub-batch frame
+  // operand images (A: rows = frames, T: rows = [x^2|x|1] transposed) and 14 - lse2 per frame
+  void* d_hscale = nullptr;
+  void* d_hWplain = nullptr;
+  void* d_hWimg = nullptr;
+  float* d_hdsc = nullptr;
+  void* d_himgA = nullptr;
+  void* d_himgT = nullptr;
+  float* d_hcb = nullptr;
+  int64_t h_cap = 0;       // frames the images hold
+  int64_t last_frames = 0; // frames covered by the events of the most recent E-step
   // per-frame log-sum-exp workspace (grows on demand)
   float* d_lse = nullptr;
   int64_t lse_cap = 0;
@@ -66,6 +77,12 @@ int gmm_lse_tc(odin_gmm* g, const float* X, const uint8_t* sad, int64_t N, float
                cudaStream_t st);
 int gmm_stats_tc(odin_gmm* g, const float* X, const uint8_t* sad, int64_t N, const float* lse,
                  int want_second, double* stats, cudaStream_t st);
+
+// 3xFP16 tcgen05 path (gmm_h.cu): both passes, records ev[0..2] itself
+bool gmm_h_supported(const odin_gmm* g);
+int gmm_estep_h(odin_gmm* g, const float* X, const uint8_t* sad, int64_t N, int want_second, double* stats,
+                cudaStream_t st);
+void gmm_h_free(odin_gmm* g);
 
 int gmm_mstep_launch(odin_gmm* g, const double* stats, int allow_rollback, int* rolled_back, cudaStream_t st);
 int gmm_mixup_launch(odin_gmm* g, int newM, cudaStream_t st);

@@ -1,0 +1,125 @@
+"""GPU parity of the 3xFP16 tcgen05 Baum-Welch kernels (odin_b200/csrc/gmm_h.cu, impl=3)
+against the fp64 oracle, the fp32 CUDA-core kernels (impl=1) and the 3xTF32 kernels
+(impl=2).  Tolerance (north_star): <= 1e-3 on N/F/S as max|a-b| / max|b|; the split
+keeps ~22 significant bits, which TIGHT pins."""
+import numpy as np
+import pytest
+
+from conftest import relmax
+from odin_b200 import synth
+from oracle import gmm as OG
+
+pytestmark = pytest.mark.gpu
+
+TOL_STATS = 1e-3
+TIGHT = 5e-5
+
+
+def _gmm(M, mean, sigma, w, impl):
+  from odin_b200.ml import GMM
+  g = GMM(nmix=M, nmix_start=M, impl=impl)
+  g.initialize(np.zeros((1, mean.shape[0]), dtype=np.float32))
+  g.mean, g.sigma, g.w = mean.copy(), sigma.copy(), w.copy()
+  return g
+
+
+def _check(X, mean, sigma, w, sad=None, tol=TIGHT):
+  M = mean.shape[1]
+  z, f, s, l, n = OG.expectation(X, mean, sigma, w, sad=sad, compute_dtype=np.float64)
+  Z, F, S, L = _gmm(M, mean, sigma, w, 3).expectation(X, sad=sad)
+  errs = (relmax(Z, z), relmax(F, f), relmax(S, s))
+  assert max(errs) < tol, errs
+  assert abs(float(L) - float(l)) < 1e-4 * max(1.0, abs(float(l))), (L, l)
+  assert abs(Z.sum() - n) < 1e-4 * max(n, 1)
+  return Z, F, S, L
+
+
+@pytest.mark.parametrize("D,M,N", [(60, 256, 32), (60, 256, 5000), (60, 512, 4099), (60, 2048, 3000),
+                                   (60, 300, 1000), (40, 384, 2049), (24, 300, 64), (4, 257, 500)])
+def test_h_estep_vs_oracle(D, M, N):
+  X = synth.gmm_features(N, D, 8, seed=D + M)
+  mean, sigma, w = synth.gmm_params(D, M, seed=M)
+  _check(X, mean, sigma, w)
+
+
+def test_h_wide_dynamic_range():
+  """fp16 halves only hold 5 exponent bits: features of very different scale per
+  dimension (1e-3 .. 1e3) and tight / loose variances must survive the exact
+  power-of-two column and row scaling."""
+  D, M, N = 60, 256, 6000
+  rng = np.random.RandomState(11)
+  scale = (10.0 ** rng.uniform(-3, 3, size=D)).astype(np.float32)
+  X = (synth.gmm_features(N, D, 8, seed=5) * scale[None, :]).astype(np.float32)
+  mean, sigma, w = synth.gmm_params(D, M, seed=6)
+  mean = (mean * scale[:, None]).astype(np.float32)
+  sigma = (sigma * (scale[:, None] ** 2) * (10.0 ** rng.uniform(-1, 1, size=(D, M)))).astype(np.float32)
+  _check(X, mean, sigma, w)
+
+
+def test_h_matches_other_kernels_and_mask():
+  D, M, N = 60, 512, 20000
+  X = synth.gmm_features(N, D, 32, seed=7)
+  mean, sigma, w = synth.gmm_params(D, M, seed=8)
+  rng = np.random.RandomState(3)
+  sad = (rng.rand(N) > 0.4).astype(np.uint8)
+  Z3, F3, S3, L3 = _check(X, mean, sigma, w, sad=sad)
+  for impl in (1, 2):
+    Z1, F1, S1, L1 = _gmm(M, mean, sigma, w, impl).expectation(X, sad=sad)
+    assert relmax(Z3, Z1) < TIGHT and relmax(F3, F1) < TIGHT and relmax(S3, S1) < TIGHT
+    assert abs(float(L1) - float(L3)) < 1e-4 * abs(float(L1))
+  # nothing selected -> exact zeros
+  Z, F, S, L = _gmm(M, mean, sigma, w, 3).expectation(X, sad=np.zeros(N, dtype=np.uint8))
+  assert np.all(Z == 0) and np.all(F == 0) and np.all(S == 0) and float(L) == 0.0
+
+
+def test_h_flush_interval_and_sub_batches(monkeypatch):
+  """the fp32 TMEM accumulator is drained into fp64 every ODIN_H_FLUSH_TILES tiles and the
+  operand images are rebuilt per ODIN_H_SUB_BATCH frames: neither may change the result."""
+  D, M, N = 60, 256, 150000
+  X = synth.gmm_features(N, D, 32, seed=17)
+  mean, sigma, w = synth.gmm_params(D, M, seed=18)
+  ref = None
+  for flush, sub in (("256", str(1 << 20)), ("7", "40000"), ("100000", "128")):
+    monkeypatch.setenv("ODIN_H_FLUSH_TILES", flush)
+    monkeypatch.setenv("ODIN_H_SUB_BATCH", sub)
+    out = _check(X, mean, sigma, w)
+    if ref is None:
+      ref = out
+    else:
+      assert relmax(out[0], ref[0]) < 1e-5 and relmax(out[1], ref[1]) < 1e-5 and relmax(out[2], ref[2]) < 1e-5
+
+
+def test_h_em_iterations_2048():
+  """config-4 protocol at reduced size: 3 EM iterations of a 2048-mix UBM."""
+  D, M, N = 60, 2048, 60000
+  X = synth.gmm_features(N, D, 64, seed=27)
+  rng = np.random.RandomState(5)
+  mean = X[rng.choice(N, M, replace=False)].T.copy()
+  sigma = np.tile(X.var(0)[:, None], (1, M)).astype(np.float32)
+  w = np.full((1, M), 1.0 / M, dtype=np.float32)
+  gm = _gmm(M, mean, sigma, w, 3)
+  om, os_, ow = mean.astype(np.float64), sigma.astype(np.float64), w.astype(np.float64)
+  for it in range(3):
+    gm.expectation_maximization(X, print_progress=False)
+    z, f, s, l, _ = OG.expectation(X, om, os_, ow, compute_dtype=np.float64)
+    om, os_, ow, rb = OG.maximization(z, f, s, (om, os_, ow))
+    assert not rb
+  assert relmax(gm.mean, om) < TOL_STATS and relmax(gm.sigma, os_) < TOL_STATS and relmax(gm.w, ow) < TOL_STATS
+  assert abs(gm._llk_hist[M][-1] - l) < 1e-3 * abs(l)
+
+
+def test_h_linearity_large():
+  """size-independent property on a 3 M-frame shard at 2048 mixtures: stats(whole) =
+  stats(first half) + stats(second half); sum(Z) = #frames."""
+  import torch
+  N, D, M = 3_000_000, 60, 2048
+  g = torch.Generator(device="cuda")
+  g.manual_seed(1)
+  X = torch.randn(N, D, generator=g, device="cuda") * 2.0
+  mean, sigma, w = synth.gmm_params(D, M, seed=22)
+  gm = _gmm(M, mean, sigma * 4.0, w, 3)
+  Z, F, S, L = gm.expectation(X)
+  Za, Fa, Sa, La = gm.expectation(X[:N // 2])
+  Zb, Fb, Sb, Lb = gm.expectation(X[N // 2:])
+  assert relmax(Za + Zb, Z) < 1e-5 and relmax(Fa + Fb, F) < 1e-5 and relmax(Sa + Sb, S) < 1e-5
+  assert abs(Z.sum() - N) < 1e-4 * N
