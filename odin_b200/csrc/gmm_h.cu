@@ -38,6 +38,7 @@
 //           D2[128 mix, 128 j]     += Phi*Thi + Phi*Tlo + Plo*Thi   (P' from TMEM, T' =
 //           transposed frame tile straight from the bulk-copied image)
 //           TMEM: [0,64) Whi | [64,128) Wlo | [128,256) D2 | [256,512) 4 x (D1 / P')
+//           smem: A ring 3 x 32 KB (freed by GEMM 1), T ring 3 x 32 KB (freed by GEMM 2)
 #include <math.h>
 #include <stdlib.h>
 
@@ -71,15 +72,14 @@ constexpr uint32_t L_SMEM = L_BAR + 256 + 1024;
 constexpr int LB_W = 0, LB_AFULL = 1, LB_AEMPTY = 4, LB_D1FULL = 7, LB_D1EMPTY = 9, LB_TMEM = 12;
 
 // ---- pass 2 shared memory map
-constexpr uint32_t S_A = 0;                       // 2 x 32 KB: [hi kb0 | hi kb1 | lo kb0 | lo kb1] x 64 rows
-constexpr int S_ASLOTS = 2;
-constexpr uint32_t S_T = S_A + S_ASLOTS * 32768;  // 4 x 32 KB: [Thi 16 KB | Tlo 16 KB]
-constexpr int S_TSLOTS = 4;
-constexpr uint32_t S_CB = S_T + S_TSLOTS * 32768; // 4 x 64 floats: 14 - lse2[b] (or -1e30)
-constexpr uint32_t S_DSJ = S_CB + S_TSLOTS * 256; // 128 doubles: 2^(-14 - ea[j])
+constexpr uint32_t S_A = 0;                       // 3 x 32 KB: [hi kb0 | hi kb1 | lo kb0 | lo kb1] x 64 rows
+constexpr int S_ASLOTS = 3;                       //   (freed by GEMM 1, so a slot turns around in ~5 MMA groups)
+constexpr uint32_t S_T = S_A + S_ASLOTS * 32768;  // 3 x 32 KB: [Thi 16 KB | Tlo 16 KB] (freed by GEMM 2)
+constexpr int S_TSLOTS = 3;
+constexpr uint32_t S_DSJ = S_T + S_TSLOTS * 32768; // 128 doubles: 2^(-14 - ea[j])
 constexpr uint32_t S_BAR = S_DSJ + 1024;
 constexpr uint32_t S_SMEM = S_BAR + 256 + 1024;
-constexpr int SB_AFULL = 0, SB_AEMPTY = 2, SB_TFULL = 4, SB_TEMPTY = 8, SB_D1FULL = 12, SB_PFULL = 16,
+constexpr int SB_AFULL = 0, SB_AEMPTY = 3, SB_TFULL = 6, SB_TEMPTY = 9, SB_D1FULL = 12, SB_PFULL = 16,
               SB_BUFEMPTY = 20, SB_D2FULL = 24, SB_D2EMPTY = 25, SB_TMEM = 28;
 constexpr uint32_t TM_WHI = 0, TM_WLO = 64, TM_D2 = 128, TM_BUF = 256;
 constexpr int NBUF = 4;
@@ -337,20 +337,21 @@ __global__ void __launch_bounds__(hk::THREADS, 1) gmm_h_lse_kernel(HArgs a) {
   } else if (warp == 8) {
     // ========================================================== MMA issuer
     if (my_tiles > 0) {
+      const uint32_t nt = (uint32_t)my_tiles;
       const uint32_t idesc = idesc_f16(CM1);
-      const uint64_t w0 = desc_k_sw128(sbase + L_W);
+      const uint32_t bar0 = sbase + L_BAR;
+      const uint64_t w0 = desc_k_sw128(sbase + L_W), descA = desc_k_sw128(sbase + L_A);
       mbar_wait(bar(LB_W), 0u);
-      int64_t pi = 0;
-      for (int64_t it = 0; it < my_tiles; ++it) {
-        const int buf = (int)(it & 1);
-        mbar_wait(bar(LB_D1EMPTY + buf), (uint32_t)(((it >> 1) & 1) ^ 1));
+      uint32_t slot = 0, spar = 0, buf = 0, bpar = 1;
+      for (uint32_t it = 0; it < nt; ++it) {
+        mbar_wait_fast(bar0 + 8u * (LB_D1EMPTY + buf), bpar);
         const uint32_t d = tmem + 256u * buf;
-        for (int kb = 0; kb < 2; ++kb, ++pi) {
-          const int slot = (int)(pi % L_ASLOTS);
-          mbar_wait(bar(LB_AFULL + slot), (uint32_t)((pi / L_ASLOTS) & 1));
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          mbar_wait_fast(bar0 + 8u * (LB_AFULL + slot), spar);
           tc_fence_after();
           if (elect_one()) {
-            const uint64_t a_hi0 = desc_k_sw128(sbase + L_A + slot * 32768), a_lo0 = a_hi0 + (16384 >> 4);
+            const uint64_t a_hi0 = descA + (uint64_t)(slot * (32768u >> 4)), a_lo0 = a_hi0 + (16384 >> 4);
             const uint64_t w_hi0 = w0 + (uint64_t)(((0 * 2 + kb) * 32768) >> 4);
             const uint64_t w_lo0 = w0 + (uint64_t)(((1 * 2 + kb) * 32768) >> 4);
 #pragma unroll
@@ -360,11 +361,13 @@ __global__ void __launch_bounds__(hk::THREADS, 1) gmm_h_lse_kernel(HArgs a) {
               mma_f16_ss(d, a_lo0 + o, w_hi0 + o, idesc, 1u);
               mma_f16_ss(d, a_hi0 + o, w_lo0 + o, idesc, 1u);
             }
-            tc_commit(bar(LB_AEMPTY + slot));
-            if (kb == 1) tc_commit(bar(LB_D1FULL + buf));
+            tc_commit(bar0 + 8u * (LB_AEMPTY + slot));
+            if (kb == 1) tc_commit(bar0 + 8u * (LB_D1FULL + buf));
           }
           __syncwarp();
+          if (++slot == L_ASLOTS) { slot = 0; spar ^= 1u; }
         }
+        if (++buf == 2u) { buf = 0; bpar ^= 1u; }
       }
     }
   } else {
@@ -530,26 +533,32 @@ __global__ void __launch_bounds__(hk::THREADS, 1) gmm_h_stats_kernel(HArgs a) {
         {
           const int s4 = (int)(it % S_TSLOTS);
           mbar_wait(bar(SB_TEMPTY + s4), (uint32_t)(((it / S_TSLOTS) & 1) ^ 1));
-          mbar_arrive_expect_tx(bar(SB_TFULL + s4), 32768u + 256u);
+          mbar_arrive_expect_tx(bar(SB_TFULL + s4), 32768u);
           bulk_g2s(sbase + S_T + s4 * 32768, a.imgT + (size_t)tile * TILE_T_BYTES, 32768u, bar(SB_TFULL + s4));
-          bulk_g2s(sbase + S_CB + s4 * 256, a.cb + (size_t)tile * TF2, 256u, bar(SB_TFULL + s4));
         }
       }
     }
   } else if (warp == 8) {
     // ========================================================== MMA issuer
+    // Everything between two groups of MMAs is kept to a handful of 32-bit instructions (ring
+    // cursors instead of div/mod, one try_wait per barrier): while this warp does bookkeeping the
+    // tensor pipe lives off its instruction queue.
     if (my_tiles > 0) {
+      const uint32_t nt = (uint32_t)my_tiles;
       const uint32_t idesc1 = idesc_f16(TF2), idesc2 = idesc_f16(K);
+      const uint32_t bar0 = sbase + S_BAR;
+      const uint64_t descA = desc_k_sw128(sbase + S_A), descT = desc_k_sw128(sbase + S_T);
+      uint32_t g1_b = 0, g1_bpar = 1, g1_a = 0, g1_apar = 0;     // cursors of GEMM 1: D1/P' buffer, A slot
+      uint32_t g2_b = 0, g2_bpar = 0, g2_t = 0, g2_tpar = 0;     // cursors of GEMM 2: P' buffer, T slot
+      uint32_t flush_left = (uint32_t)a.flush_tiles, d2_phase = 0;
       bool acc = false, need_d2_empty = false;
-      uint32_t d2_phase = 0;
-      auto issue_g1 = [&](int64_t it) {
-        const int b = (int)(it % NBUF), sa = (int)(it % S_ASLOTS);
-        mbar_wait(bar(SB_BUFEMPTY + b), (uint32_t)(((it / NBUF) & 1) ^ 1));
-        mbar_wait(bar(SB_AFULL + sa), (uint32_t)((it / S_ASLOTS) & 1));
+      auto issue_g1 = [&]() {
+        mbar_wait_fast(bar0 + 8u * (SB_BUFEMPTY + g1_b), g1_bpar);
+        mbar_wait_fast(bar0 + 8u * (SB_AFULL + g1_a), g1_apar);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t d = tmem + TM_BUF + 64u * b;
-          const uint64_t a0 = desc_k_sw128(sbase + S_A + sa * 32768);
+          const uint32_t d = tmem + TM_BUF + 64u * g1_b;
+          const uint64_t a0 = descA + (uint64_t)(g1_a * (32768u >> 4));
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
             const int kb = kk >> 2, ks = kk & 3;
@@ -559,26 +568,27 @@ __global__ void __launch_bounds__(hk::THREADS, 1) gmm_h_stats_kernel(HArgs a) {
             mma_f16_ts(d, tmem + TM_WHI + 8u * kk, b_lo, idesc1, 1u);
             mma_f16_ts(d, tmem + TM_WLO + 8u * kk, b_hi, idesc1, 1u);
           }
-          tc_commit(bar(SB_AEMPTY + sa));
-          tc_commit(bar(SB_D1FULL + b));
+          tc_commit(bar0 + 8u * (SB_AEMPTY + g1_a));
+          tc_commit(bar0 + 8u * (SB_D1FULL + g1_b));
         }
         __syncwarp();
+        if (++g1_b == NBUF) { g1_b = 0; g1_bpar ^= 1u; }
+        if (++g1_a == S_ASLOTS) { g1_a = 0; g1_apar ^= 1u; }
       };
-      auto issue_g2 = [&](int64_t it) {
-        const int b = (int)(it % NBUF), s4 = (int)(it % S_TSLOTS);
-        mbar_wait(bar(SB_PFULL + b), (uint32_t)((it / NBUF) & 1));
-        mbar_wait(bar(SB_TFULL + s4), (uint32_t)((it / S_TSLOTS) & 1));
+      auto issue_g2 = [&](bool last) {
+        mbar_wait_fast(bar0 + 8u * (SB_PFULL + g2_b), g2_bpar);
+        mbar_wait_fast(bar0 + 8u * (SB_TFULL + g2_t), g2_tpar);
         if (need_d2_empty) {
-          mbar_wait(bar(SB_D2EMPTY), d2_phase);
-          d2_phase ^= 1;
+          mbar_wait_fast(bar0 + 8u * SB_D2EMPTY, d2_phase);
+          d2_phase ^= 1u;
           need_d2_empty = false;
         }
         tc_fence_after();
-        const bool flush = ((it + 1) % a.flush_tiles) == 0 || it + 1 == my_tiles;
+        const bool flush = (--flush_left == 0u) || last;
         if (elect_one()) {
           const uint32_t d = tmem + TM_D2;
-          const uint32_t p0 = tmem + TM_BUF + 64u * b;
-          const uint64_t t_hi0 = desc_k_sw128(sbase + S_T + s4 * 32768), t_lo0 = t_hi0 + (16384 >> 4);
+          const uint32_t p0 = tmem + TM_BUF + 64u * g2_b;
+          const uint64_t t_hi0 = descT + (uint64_t)(g2_t * (32768u >> 4)), t_lo0 = t_hi0 + (16384 >> 4);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint32_t p_hi = p0 + 32u * (ks >> 1) + 8u * (ks & 1), p_lo = p_hi + 16u;
@@ -587,18 +597,21 @@ __global__ void __launch_bounds__(hk::THREADS, 1) gmm_h_stats_kernel(HArgs a) {
             mma_f16_ts(d, p_hi, t_lo0 + o, idesc2, 1u);
             mma_f16_ts(d, p_lo, t_hi0 + o, idesc2, 1u);
           }
-          tc_commit(bar(SB_TEMPTY + s4));
-          tc_commit(bar(SB_BUFEMPTY + b));
-          if (flush) tc_commit(bar(SB_D2FULL));
+          tc_commit(bar0 + 8u * (SB_TEMPTY + g2_t));
+          tc_commit(bar0 + 8u * (SB_BUFEMPTY + g2_b));
+          if (flush) tc_commit(bar0 + 8u * SB_D2FULL);
         }
         __syncwarp();
         acc = !flush;
-        if (flush) need_d2_empty = true;
+        if (flush) { need_d2_empty = true; flush_left = (uint32_t)a.flush_tiles; }
+        if (++g2_b == NBUF) { g2_b = 0; g2_bpar ^= 1u; }
+        if (++g2_t == S_TSLOTS) { g2_t = 0; g2_tpar ^= 1u; }
       };
-      for (int64_t it = 0; it < LOOKAHEAD && it < my_tiles; ++it) issue_g1(it);
-      for (int64_t it = 0; it < my_tiles; ++it) {
-        if (it + LOOKAHEAD < my_tiles) issue_g1(it + LOOKAHEAD);
-        issue_g2(it);
+      uint32_t issued = 0;
+      for (; issued < (uint32_t)LOOKAHEAD && issued < nt; ++issued) issue_g1();
+      for (uint32_t it = 0; it < nt; ++it) {
+        if (issued < nt) { issue_g1(); ++issued; }
+        issue_g2(it + 1 == nt);
       }
     }
   } else {
@@ -608,24 +621,26 @@ __global__ void __launch_bounds__(hk::THREADS, 1) gmm_h_stats_kernel(HArgs a) {
     const uint32_t lane_field = (uint32_t)(q * 32) << 16;
     const float dsc = a.dsc[chunk * CM2 + row];
     const double* dsj = reinterpret_cast<const double*>(smem + S_DSJ);
-    uint32_t d2_phase = 0;
+    uint32_t d2_phase = 0, flush_left = (uint32_t)a.flush_tiles;
     for (int64_t it = 0; it < my_tiles; ++it) {
-      const int b = (int)(it % NBUF), s4 = (int)(it % S_TSLOTS);
+      const int b = (int)(it % NBUF);
+      // 14 - lse2[b] of this warp's 32 frames (warp-uniform addresses: one broadcast line per load),
+      // issued before the wait so the latency hides behind GEMM 1
+      float cbv[32];
+      {
+        const int64_t tile = blockIdx.y + it * gridDim.y;
+        const float4* cb4 = reinterpret_cast<const float4*>(a.cb + (size_t)tile * TF2) + h * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 t = __ldg(cb4 + i);
+          cbv[4 * i] = t.x; cbv[4 * i + 1] = t.y; cbv[4 * i + 2] = t.z; cbv[4 * i + 3] = t.w;
+        }
+      }
       mbar_wait(bar(SB_D1FULL + b), (uint32_t)((it / NBUF) & 1));
-      mbar_wait(bar(SB_TFULL + s4), (uint32_t)((it / S_TSLOTS) & 1));   // cb[] of this tile has landed
       tc_fence_after();
       const uint32_t taddr = tmem + TM_BUF + 64u * b + 32u * h + lane_field;
       uint32_t r[32];
       tmem_ld32_nowait(taddr, r);
-      float cbv[32];
-      {
-        const float4* cb4 = reinterpret_cast<const float4*>(smem + S_CB + s4 * 256) + h * 8;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 t = cb4[i];
-          cbv[4 * i] = t.x; cbv[4 * i + 1] = t.y; cbv[4 * i + 2] = t.z; cbv[4 * i + 3] = t.w;
-        }
-      }
       tmem_ld_wait();
       uint32_t hi[16], lo[16];
 #pragma unroll
@@ -639,7 +654,8 @@ __global__ void __launch_bounds__(hk::THREADS, 1) gmm_h_stats_kernel(HArgs a) {
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(bar(SB_PFULL + b));
-      if (((it + 1) % a.flush_tiles) == 0 || it + 1 == my_tiles) {
+      if ((--flush_left == 0u) || it + 1 == my_tiles) {
+        flush_left = (uint32_t)a.flush_tiles;
         // drain D2[mixture = row, j] into the fp64 statistics (64 columns per warp)
         mbar_wait(bar(SB_D2FULL), d2_phase);
         d2_phase ^= 1;
