@@ -100,6 +100,16 @@ int fe_build_tables(odin_fe* fe) {
     double ang = -2.0 * M_PI * (double)k / (double)N;
     tw[k] = make_float2((float)cos(ang), (float)sin(ang));
   }
+  // four-step FFT twiddles for fe_frame4_kernel: N = G * 32, tw4[k1 * G + l] = exp(-2 pi i l k1 / N)
+  std::vector<float2> tw4(N);
+  {
+    const int G = N / 32;
+    for (int k1 = 0; k1 < 32; ++k1)
+      for (int l = 0; l < G; ++l) {
+        double ang = -2.0 * M_PI * (double)l * (double)k1 / (double)N;
+        tw4[(size_t)k1 * G + l] = make_float2((float)cos(ang), (float)sin(ang));
+      }
+  }
   // mel filterbank (signal.py:735-810), dense fp64 -> CSR fp32
   fe->h_mel.assign((size_t)nm * nb, 0.0);
   std::vector<double> binhz = linspace(0.0, (double)c.sr / 2.0, nb);
@@ -147,6 +157,7 @@ int fe_build_tables(odin_fe* fe) {
   if ((rc = upload(&fe->d_win32, win32))) return rc;
   if ((rc = upload(&fe->d_win64, fe->h_win))) return rc;
   if ((rc = upload(&fe->d_tw, tw))) return rc;
+  if ((rc = upload(&fe->d_tw4, tw4))) return rc;
   if ((rc = upload(&fe->d_mel_start, mstart))) return rc;
   if ((rc = upload(&fe->d_mel_cnt, mcnt))) return rc;
   if ((rc = upload(&fe->d_mel_off, moff))) return rc;
@@ -232,7 +243,7 @@ int odin_fe_create(const odin_fe_config* cfg, odin_fe_t** out) {
 
 void odin_fe_destroy(odin_fe_t* fe) {
   if (!fe) return;
-  cudaFree(fe->d_win32); cudaFree(fe->d_win64); cudaFree(fe->d_tw); cudaFree(fe->d_mel_start);
+  cudaFree(fe->d_win32); cudaFree(fe->d_win64); cudaFree(fe->d_tw); cudaFree(fe->d_tw4); cudaFree(fe->d_mel_start);
   cudaFree(fe->d_mel_cnt); cudaFree(fe->d_mel_off); cudaFree(fe->d_mel_w); cudaFree(fe->d_dct);
   cudaFree(fe->d_taps); cudaFree(fe->d_sample_off); cudaFree(fe->d_dcsum); cudaFree(fe->d_umax);
   cudaFree(fe->d_cnt); cudaFree(fe->d_vad_scratch);

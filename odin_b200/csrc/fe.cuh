@@ -17,6 +17,7 @@ struct odin_fe {
   float* d_win32 = nullptr;    // [L]
   double* d_win64 = nullptr;   // [L]
   float2* d_tw = nullptr;      // [N] exp(-2 pi i k / N)
+  float2* d_tw4 = nullptr;     // [32][N/32] four-step twiddles exp(-2 pi i l k1 / N)
   int* d_mel_start = nullptr;  // [n_mels] first bin with non-zero weight
   int* d_mel_cnt = nullptr;    // [n_mels]
   int* d_mel_off = nullptr;    // [n_mels] offset into d_mel_w

@@ -30,6 +30,7 @@
 //   fe_compact_*     ApplyingSAD row compaction.
 #include <float.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "fe.cuh"
 #include "fe_logic.cuh"
@@ -52,19 +53,25 @@ template <typename T> __device__ __forceinline__ C2<T> cmul(C2<T> a, C2<T> b) {
 }
 template <typename T> __device__ __forceinline__ C2<T> cmul_negi(C2<T> a) { return {a.y, -a.x}; }  // a * (-i)
 
-// W_16^q = exp(-2 pi i q / 16), q = 0..7
-__device__ __forceinline__ constexpr double w16c(int q) {
-  return q == 0 ? 1.0 : q == 1 ? 0.92387953251128673848 : q == 2 ? 0.70710678118654752440
-       : q == 3 ? 0.38268343236508977173 : q == 4 ? 0.0 : q == 5 ? -0.38268343236508977173
-       : q == 6 ? -0.70710678118654752440 : -0.92387953251128673848;
+// W_32^q = exp(-2 pi i q / 32), q = 0..15
+__device__ __forceinline__ constexpr double w32c(int q) {
+  return q == 0 ? 1.0 : q == 1 ? 0.98078528040323044913 : q == 2 ? 0.92387953251128675613
+       : q == 3 ? 0.83146961230254523708 : q == 4 ? 0.70710678118654752440 : q == 5 ? 0.55557023301960222474
+       : q == 6 ? 0.38268343236508977173 : q == 7 ? 0.19509032201612826785 : q == 8 ? 0.0
+       : q == 9 ? -0.19509032201612826785 : q == 10 ? -0.38268343236508977173 : q == 11 ? -0.55557023301960222474
+       : q == 12 ? -0.70710678118654752440 : q == 13 ? -0.83146961230254523708 : q == 14 ? -0.92387953251128675613
+       : -0.98078528040323044913;
 }
-__device__ __forceinline__ constexpr double w16s(int q) {  // -sin(2 pi q / 16)
-  return q == 0 ? 0.0 : q == 1 ? -0.38268343236508977173 : q == 2 ? -0.70710678118654752440
-       : q == 3 ? -0.92387953251128673848 : q == 4 ? -1.0 : q == 5 ? -0.92387953251128673848
-       : q == 6 ? -0.70710678118654752440 : -0.38268343236508977173;
+__device__ __forceinline__ constexpr double w32s(int q) {  // -sin(2 pi q / 32)
+  return q == 0 ? 0.0 : q == 1 ? -0.19509032201612826785 : q == 2 ? -0.38268343236508977173
+       : q == 3 ? -0.55557023301960222474 : q == 4 ? -0.70710678118654752440 : q == 5 ? -0.83146961230254523708
+       : q == 6 ? -0.92387953251128675613 : q == 7 ? -0.98078528040323044913 : q == 8 ? -1.0
+       : q == 9 ? -0.98078528040323044913 : q == 10 ? -0.92387953251128675613 : q == 11 ? -0.83146961230254523708
+       : q == 12 ? -0.70710678118654752440 : q == 13 ? -0.55557023301960222474 : q == 14 ? -0.38268343236508977173
+       : -0.19509032201612826785;
 }
 
-// in-register forward DFT of size R (power of two <= 16), natural order in/out
+// in-register forward DFT of size R (power of two <= 32), natural order in/out
 template <int R, typename T> struct Dft {
   static __device__ __forceinline__ void run(C2<T> (&v)[R]) {
     C2<T> e[R / 2], o[R / 2];
@@ -77,7 +84,7 @@ template <int R, typename T> struct Dft {
       C2<T> t;
       if (q == 0) t = o[q];
       else if (4 * q == R) t = cmul_negi(o[q]);
-      else t = cmul(o[q], C2<T>{(T)w16c(q * (16 / R)), (T)w16s(q * (16 / R))});
+      else t = cmul(o[q], C2<T>{(T)w32c(q * (32 / R)), (T)w32s(q * (32 / R))});
       v[q] = cadd(e[q], t);
       v[q + R / 2] = csub(e[q], t);
     }
@@ -188,7 +195,8 @@ struct FrameArgs {
   float preemph;
   const float* win32;
   const double* win64;
-  const void* tw;  // C2<T>[N]
+  const void* tw;  // C2<T>[N]: Stockham table exp(-2 pi i k / N), or the four-step table for fe_frame4_kernel
+  int mel_nnz;
   const int* mel_start;
   const int* mel_cnt;
   const int* mel_off;
@@ -362,6 +370,211 @@ __global__ void __launch_bounds__(FE_THREADS) fe_frame_kernel(FrameArgs a) {
           const float dB = (float)db10<T>(accB);
           a.mspec[(fbase + t0 + fB) * a.n_mels + m] = dB;
           wmax = fmaxf(wmax, dB);
+        }
+      }
+    }
+    wmax = warp_max(wmax);
+    if (lane == 0) atomicMax(&cta_max, float_to_ordered(wmax));
+    __syncthreads();
+    if (tid == 0) atomicMax(a.umax + u, cta_max);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// fe_frame4_kernel: same contract as fe_frame_kernel, four-step FFT.
+//
+// N = G * 32.  G lanes share one complex FFT (two real frames as re / im) and every
+// lane keeps 32 elements in registers:
+//   step A   lane l loads z[l + G r], r = 0..31 (window multiply and the fp64 frame
+//            energy fused), runs a 32-point DFT over r in registers
+//   twiddle  Y[l][k1] *= w_N^(l k1)                       (table tw4[k1][l])
+//   exchange through a warp-private padded smem tile [k1][G + 1] -- the ONLY round
+//            trip of the spectrum through shared memory (the Stockham kernel made three)
+//   step B   lane j runs the G-point DFT over l for its 32 / G values of k1 and writes
+//            X[k1 + 32 k2] in natural order for the split / mel stage
+// A warp therefore handles 32 / G frame pairs at once (1 at n_fft 1024, 2 at 512, 4 at
+// 256) in <= 128 registers, so two CTAs (16 warps) fit per SM instead of one.
+// ---------------------------------------------------------------------------
+template <int N> constexpr int f4_region() { return 32 * (N / 32 + 1); }   // float2 per pair
+
+template <int N, typename PCM>
+__global__ void __launch_bounds__(FE_THREADS, 2) fe_frame4_kernel(FrameArgs a) {
+  using T = float;
+  constexpr int G = N / 32, NP = 32 / G, RS = G + 1, REG = f4_region<N>();
+  static_assert(REG >= N, "pair region must hold the natural-order spectrum");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: win64 [L] | tw4 [N] | warp bufs [FE_WARPS][NP * REG] | win32 [L] | melw [nnz] |
+  //         mel start/cnt/off [3 n_mels] | sbuf [(FT-1)*hop + L]
+  double* win64 = reinterpret_cast<double*>(smem_raw);
+  C2<T>* tw4 = reinterpret_cast<C2<T>*>(win64 + a.L + (a.L & 1));
+  C2<T>* bufs = tw4 + N;
+  float* win32 = reinterpret_cast<float*>(bufs + FE_WARPS * NP * REG);
+  float* melw = win32 + a.L;
+  int* meli = reinterpret_cast<int*>(melw + a.mel_nnz);
+  float* sbuf = reinterpret_cast<float*>(meli + 3 * a.n_mels);
+  __shared__ int cta_max;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane / G, l = lane % G;
+  const int L = a.L, hop = a.hop;
+  for (int i = tid; i < L; i += FE_THREADS) { win64[i] = a.win64[i]; win32[i] = a.win32[i]; }
+  for (int i = tid; i < N; i += FE_THREADS) tw4[i] = reinterpret_cast<const C2<T>*>(a.tw)[i];
+  for (int i = tid; i < a.mel_nnz; i += FE_THREADS) melw[i] = a.mel_w[i];
+  for (int i = tid; i < a.n_mels; i += FE_THREADS) {
+    meli[i] = a.mel_start[i]; meli[a.n_mels + i] = a.mel_cnt[i]; meli[2 * a.n_mels + i] = a.mel_off[i];
+  }
+  C2<T>* wbuf = bufs + warp * (NP * REG);
+  const PCM* __restrict__ pcm = reinterpret_cast<const PCM*>(a.pcm);
+  const float coef = a.preemph;
+
+  for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    const int u = find_segment(a.tile_off, a.n_utt, tile);
+    const int64_t s0 = a.sample_off[u];
+    const int64_t n_u = a.sample_off[u + 1] - s0;
+    const int64_t fbase = a.frame_off[u];
+    const int T_u = (int)(a.frame_off[u + 1] - fbase);
+    const int t0 = (int)(tile - a.tile_off[u]) * FT;
+    const int nf = min(FT, T_u - t0);
+    float mean = 0.f;
+    if (a.remove_dc) {
+      double s = (sizeof(PCM) == 2) ? (double)reinterpret_cast<const long long*>(a.dcsum)[u] : a.dcsum[u];
+      mean = (float)(s / (double)n_u);
+    }
+    __syncthreads();  // previous tile done with sbuf / cta_max (and the table fill on the first trip)
+    if (tid == 0) cta_max = float_to_ordered(-FLT_MAX);
+    {
+      const int cnt = (nf - 1) * hop + L;
+      const int64_t g0 = (int64_t)t0 * hop;
+      const PCM* p = pcm + s0 + g0;
+      for (int i = tid; i < cnt; i += FE_THREADS) {
+        float cur = __fsub_rn((float)p[i], mean);
+        if (coef != 0.f && (g0 + i) > 0) {
+          float prev = __fsub_rn((float)p[i - 1], mean);
+          cur = __fsub_rn(cur, __fmul_rn(coef, prev));  // two roundings, like numpy (signal.py:965)
+        }
+        sbuf[i] = cur;
+      }
+    }
+    __syncthreads();
+
+    float wmax = -FLT_MAX;
+    const int npairs = (nf + 1) >> 1;
+    for (int base = warp * NP; base < npairs; base += FE_WARPS * NP) {
+      C2<T>* reg = wbuf + g * REG;
+      // ---------------- step A: load + window + energy, 32-point DFT over r, twiddle
+      {
+        const int pr = base + g;
+        const int fA = 2 * pr, fB = fA + 1;
+        const bool hasA = fA < nf, hasB = fB < nf;
+        const float* sA = sbuf + (hasA ? fA : 0) * hop;
+        const float* sB = sbuf + (hasB ? fB : 0) * hop;
+        double eA = 0.0, eB = 0.0;
+        C2<T> v[32];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          const int i = l + G * r;
+          C2<T> z = {0.f, 0.f};
+          if (i < L && hasA) {
+            const float xa = sA[i], xb = hasB ? sB[i] : 0.f;
+            const double w = win64[i];
+            const double wa = w * (double)xa, wb = w * (double)xb;
+            eA = fma(wa, wa, eA);
+            eB = fma(wb, wb, eB);
+            const float wf = win32[i];
+            z.x = wf * xa; z.y = wf * xb;
+          }
+          v[r] = z;
+        }
+        if (a.energy != nullptr) {
+#pragma unroll
+          for (int o = G / 2; o > 0; o >>= 1) {
+            eA += __shfl_xor_sync(0xffffffffu, eA, o);
+            eB += __shfl_xor_sync(0xffffffffu, eB, o);
+          }
+          if (l == 0 && hasA) {
+            if (eA == 0.0) eA = (double)FLT_EPSILON;  // signal.py:1436
+            a.energy[fbase + t0 + fA] = (float)log(eA);
+            if (hasB) {
+              if (eB == 0.0) eB = (double)FLT_EPSILON;
+              a.energy[fbase + t0 + fB] = (float)log(eB);
+            }
+          }
+        }
+        Dft<32, T>::run(v);
+#pragma unroll
+        for (int k1 = 1; k1 < 32; ++k1) v[k1] = cmul(v[k1], tw4[k1 * G + l]);
+        __syncwarp();  // the previous pass' mel stage has finished reading the regions
+#pragma unroll
+        for (int k1 = 0; k1 < 32; ++k1) reg[k1 * RS + l] = v[k1];
+      }
+      __syncwarp();
+      // ---------------- step B: G-point DFT over l for k1 = l + G t, natural-order store
+      {
+        C2<T> x[NP][G];
+#pragma unroll
+        for (int t = 0; t < NP; ++t) {
+          const int k1 = l + G * t;
+#pragma unroll
+          for (int i = 0; i < G; ++i) x[t][i] = reg[k1 * RS + i];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < NP; ++t) {
+          Dft<G, T>::run(x[t]);
+          const int k1 = l + G * t;
+#pragma unroll
+          for (int k2 = 0; k2 < G; ++k2) reg[k1 + 32 * k2] = x[t][k2];
+        }
+      }
+      __syncwarp();
+      // ---------------- split + |.|^2 + mel + dB, the whole warp on one pair at a time
+#pragma unroll 1
+      for (int pp = 0; pp < NP; ++pp) {
+        const int fA = 2 * (base + pp), fB = fA + 1;
+        if (fA >= nf) break;
+        const bool hasB = fB < nf;
+        C2<T>* buf = wbuf + pp * REG;
+        constexpr int NK = (N / 2) / 32;  // bins per lane below N/2
+        T pa[NK + 1], pb[NK + 1];
+        const T q = (T)0.25 * (T)a.scale2;
+#pragma unroll
+        for (int i = 0; i < NK; ++i) {
+          const int k = lane + 32 * i;
+          const C2<T> z1 = buf[k], z2 = buf[(N - k) & (N - 1)];
+          const T ar = z1.x + z2.x, ai = z1.y - z2.y;
+          const T br = z1.y + z2.y, bi = z2.x - z1.x;
+          pa[i] = (ar * ar + ai * ai) * q;
+          pb[i] = (br * br + bi * bi) * q;
+        }
+        {
+          const C2<T> zn = buf[N / 2];
+          pa[NK] = (zn.x * zn.x) * (T)a.scale2;
+          pb[NK] = (zn.y * zn.y) * (T)a.scale2;
+        }
+        __syncwarp();
+        T* PA = reinterpret_cast<T*>(buf);
+        T* PB = PA + (N / 2 + 1);
+#pragma unroll
+        for (int i = 0; i < NK; ++i) { PA[lane + 32 * i] = pa[i]; PB[lane + 32 * i] = pb[i]; }
+        if (lane == 0) { PA[N / 2] = pa[NK]; PB[N / 2] = pb[NK]; }
+        __syncwarp();
+        for (int m = lane; m < a.n_mels; m += 32) {
+          const int st = meli[m], cn = meli[a.n_mels + m];
+          const float* __restrict__ w = melw + meli[2 * a.n_mels + m];
+          T accA = 0, accB = 0;
+          for (int i = 0; i < cn; ++i) {
+            const T wi = w[i];
+            accA += wi * PA[st + i];
+            accB += wi * PB[st + i];
+          }
+          const float dA = db10<T>(accA);
+          a.mspec[(fbase + t0 + fA) * a.n_mels + m] = dA;
+          wmax = fmaxf(wmax, dA);
+          if (hasB) {
+            const float dB = db10<T>(accB);
+            a.mspec[(fbase + t0 + fB) * a.n_mels + m] = dB;
+            wmax = fmaxf(wmax, dB);
+          }
         }
       }
     }
@@ -807,6 +1020,32 @@ static int dispatch_frame(int N, const FrameArgs& a, cudaStream_t st) {
   return set_error(ODIN_EINVAL, "n_fft %d unsupported (256/512/1024/2048)", N);
 }
 
+template <int N, typename PCM>
+static int launch_frame4(const FrameArgs& a, cudaStream_t st) {
+  size_t smem = (size_t)(a.L + (a.L & 1)) * sizeof(double) + (size_t)N * sizeof(float2) +
+                (size_t)FE_WARPS * (32 / (N / 32)) * f4_region<N>() * sizeof(float2) + (size_t)a.L * sizeof(float) +
+                (size_t)a.mel_nnz * sizeof(float) + (size_t)3 * a.n_mels * sizeof(int) +
+                (size_t)((FT - 1) * a.hop + a.L) * sizeof(float);
+  if (smem > 227 * 1024) return set_error(ODIN_EINVAL, "frame kernel needs %zu B smem (hop too large)", smem);
+  auto k = fe_frame4_kernel<N, PCM>;
+  ODIN_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (227 * 1024) / (smem + 1024)));
+  int64_t grid = std::min<int64_t>(a.n_tiles, (int64_t)sm_count() * per_sm);
+  k<<<(unsigned)grid, FE_THREADS, smem, st>>>(a);
+  ODIN_LAUNCH_CHECK("fe_frame4_kernel");
+  return ODIN_OK;
+}
+
+template <typename PCM>
+static int dispatch_frame4(int N, const FrameArgs& a, cudaStream_t st) {
+  switch (N) {
+    case 256: return launch_frame4<256, PCM>(a, st);
+    case 512: return launch_frame4<512, PCM>(a, st);
+    case 1024: return launch_frame4<1024, PCM>(a, st);
+  }
+  return set_error(ODIN_EINVAL, "n_fft %d unsupported by the four-step kernel", N);
+}
+
 int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t total_frames, int64_t n_tiles,
               int64_t n_tiles2, float* d_mspec, float* d_feat, float* d_energy, float* d_c0, uint8_t* d_sad,
               double* d_sad_thr, cudaStream_t st) {
@@ -843,8 +1082,19 @@ int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t 
     a.tw = fe->d_tw; a.mel_start = fe->d_mel_start; a.mel_cnt = fe->d_mel_cnt; a.mel_off = fe->d_mel_off;
     a.mel_w = fe->d_mel_w; a.n_mels = fe->n_mels; a.scale2 = fe->scale2; a.mspec = d_mspec;
     a.energy = d_energy; a.umax = fe->d_umax;
-    int rc = (pcm_dtype == 0) ? dispatch_frame<float, int16_t>(fe->N, a, st)
-                              : dispatch_frame<float, float>(fe->N, a, st);
+    a.mel_nnz = fe->mel_nnz;
+    // four-step FFT kernel up to n_fft = 1024; the Stockham kernel keeps n_fft = 2048
+    // (ODIN_FE_STOCKHAM=1 forces it everywhere, for A/B runs)
+    const char* force = getenv("ODIN_FE_STOCKHAM");
+    const bool four = fe->N <= 1024 && !(force && force[0] == '1');
+    int rc;
+    if (four) {
+      a.tw = fe->d_tw4;
+      rc = (pcm_dtype == 0) ? dispatch_frame4<int16_t>(fe->N, a, st) : dispatch_frame4<float>(fe->N, a, st);
+    } else {
+      rc = (pcm_dtype == 0) ? dispatch_frame<float, int16_t>(fe->N, a, st)
+                            : dispatch_frame<float, float>(fe->N, a, st);
+    }
     if (rc) return rc;
   }
   ODIN_CUDA_CHECK(cudaEventRecord(fe->ev[2], st));
