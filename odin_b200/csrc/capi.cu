@@ -248,7 +248,8 @@ void odin_fe_destroy(odin_fe_t* fe) {
   cudaFree(fe->d_taps); cudaFree(fe->d_sample_off); cudaFree(fe->d_dcsum); cudaFree(fe->d_umax);
   cudaFree(fe->d_cnt); cudaFree(fe->d_vad_scratch);
   if (fe->h_stage) cudaFreeHost(fe->h_stage);
-  for (int i = 0; i < 5; ++i) if (fe->ev[i]) cudaEventDestroy(fe->ev[i]);
+  for (int i = 0; i < 7; ++i) if (fe->ev[i]) cudaEventDestroy(fe->ev[i]);
+  if (fe->aux) cudaStreamDestroy(fe->aux);
   delete fe;
 }
 
@@ -482,6 +483,7 @@ int odin_fe_last_run_ms(odin_fe_t* fe, float* ms4) {
   if (!fe->ev_valid) return set_error(ODIN_EINVAL, "no run has been recorded");
   ODIN_CUDA_CHECK(cudaEventSynchronize(fe->ev[4]));
   for (int i = 0; i < 4; ++i) ODIN_CUDA_CHECK(cudaEventElapsedTime(ms4 + i, fe->ev[i], fe->ev[i + 1]));
+  if (fe->vad_forked) ODIN_CUDA_CHECK(cudaEventElapsedTime(ms4 + 3, fe->ev[5], fe->ev[6]));
   return ODIN_OK;
 }
 

@@ -38,8 +38,10 @@ struct odin_fe {
   float* d_vad_scratch = nullptr;  // [frames] standardised energies
   int64_t vad_scratch_cap = 0;
   // events bracketing dc | frame | post | vad kernels of the most recent run (odin_fe_last_run_ms)
-  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool ev_valid = false;
+  bool vad_forked = false;      // last run had the SADgmm kernel on the auxiliary stream (ev[5] -> ev[6])
+  cudaStream_t aux = nullptr;   // SADgmm only needs the frame energies: it runs beside the utterance pass
   // host copies of the tables (tests, debugging)
   std::vector<double> h_win;
   std::vector<double> h_mel;   // dense [n_mels, nbins]

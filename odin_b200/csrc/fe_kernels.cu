@@ -32,8 +32,12 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <cooperative_groups.h>
+
 #include "fe.cuh"
 #include "fe_logic.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace odin {
 
@@ -729,20 +733,151 @@ struct VadArgs {
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
 
-// 1-D EM of sklearn GaussianMixture with fixed inits (see oracle/frontend.py _em_1d),
-// block-cooperative: every thread of the CTA walks a strided share of the frames,
-// the ten sufficient statistics are reduced warp -> CTA in a fixed order and every
-// thread then runs the (tiny) M-step redundantly on identical numbers, so control
-// flow stays uniform.  Returns false where sklearn would raise ValueError.
+// SADgmm: one thread-block CLUSTER of 1..8 CTAs per utterance (sized per launch so that the
+// clusters of a batch roughly fill the GPU: few long utterances get 8 CTAs each, hundreds get 1).
+//
+// The 1-D EM of sklearn's GaussianMixture is ~350 fp64 instructions per frame and iteration, so a
+// minute-long utterance on one SM is bound by that SM's fp64 pipe (the batch's longest utterance set
+// the kernel time).  The frames of an utterance are therefore spread over the CTAs of a cluster; the
+// thirteen sufficient statistics are reduced lanes -> warps -> CTA -> cluster (distributed shared
+// memory) in a FIXED order, and every thread of every CTA then runs the tiny M-step redundantly on
+// bit-identical numbers, so control flow (convergence test, component-drop retry) stays uniform.
 constexpr int VAD_THREADS = 256;
 constexpr int VAD_WARPS = VAD_THREADS / 32;
+constexpr int VAD_CL_MAX = 8;               // portable cluster size limit
 constexpr int VAD_KMAX = 4;
-constexpr int VAD_NRED = 3 * VAD_KMAX + 1;
+constexpr int VAD_NRED = 3 * VAD_KMAX + 2;   // lsum, nk[4], sx[4], sxx[4], #non-finite
+constexpr int VAD_MAXLEAF = 1024;            // leaves of numpy's pairwise sum held in smem (n <~ 58 000 frames)
 
-__device__ bool vad_em(const float* __restrict__ x, int n, int nc, int max_iter, double (*red)[VAD_NRED],
-                       int* flag, double* mu_out, double* prec_out) {
-  constexpr int KMAX = VAD_KMAX;
+struct VadShared {
+  double red[VAD_WARPS][VAD_NRED];
+  double part[VAD_NRED];
+  double tot[VAD_NRED];
+  float ms[2];
+  int nleaf;
+  int leaf_lo[VAD_MAXLEAF];
+  int leaf_cnt[VAD_MAXLEAF];
+  float leaf_sum[VAD_MAXLEAF];
+};
+
+// cluster-wide sums of v[0..VAD_NRED): same bits on every thread of every CTA
+__device__ __forceinline__ void vad_cluster_reduce(double (&v)[VAD_NRED], VadShared& sh, cg::cluster_group& cl) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int k = 0; k < VAD_NRED; ++k) v[k] = warp_sum(v[k]);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < VAD_NRED; ++k) sh.red[warp][k] = v[k];
+  }
+  __syncthreads();
+  if (tid < VAD_NRED) {
+    double t = 0.0;
+    for (int wv = 0; wv < VAD_WARPS; ++wv) t += sh.red[wv][tid];
+    sh.part[tid] = t;
+  }
+  cl.sync();
+  if (tid < VAD_NRED) {
+    double t = 0.0;
+    for (unsigned r = 0; r < cl.num_blocks(); ++r) t += *cl.map_shared_rank(&sh.part[tid], r);
+    sh.tot[tid] = t;
+  }
+  cl.sync();  // every CTA has read every part[]; tot[] is visible to the whole CTA
+#pragma unroll
+  for (int k = 0; k < VAD_NRED; ++k) v[k] = sh.tot[k];
+}
+
+// numpy's pairwise float32 sum of f(0..n) (see fe_logic.cuh), block-cooperative and bit-identical:
+// thread 0 lists the <= 128-element leaves of the recursion, 8-lane groups sum one leaf each with the
+// eight strided accumulators of numpy's unrolled loop, thread 0 folds the leaf sums along the same tree.
+template <class F>
+__device__ float block_np_pairwise_sum_f32(F f, int n, VadShared& sh) {
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    int s_lo[40], s_n[40], sp = 0, nl = 0;
+    s_lo[0] = 0; s_n[0] = n; sp = 1;
+    while (sp > 0 && nl >= 0) {
+      const int lo = s_lo[sp - 1], cnt = s_n[sp - 1];
+      --sp;
+      if (cnt <= 128) {
+        if (nl >= VAD_MAXLEAF) { nl = -1; break; }
+        sh.leaf_lo[nl] = lo; sh.leaf_cnt[nl] = cnt; ++nl;
+      } else {
+        int n2 = cnt / 2;
+        n2 -= n2 % 8;
+        s_lo[sp] = lo + n2; s_n[sp] = cnt - n2; ++sp;   // right half is visited after ...
+        s_lo[sp] = lo; s_n[sp] = n2; ++sp;              // ... the left half
+      }
+    }
+    sh.nleaf = nl;
+  }
+  __syncthreads();
+  const int nleaf = sh.nleaf;
+  if (nleaf < 0) {  // too long for the leaf table: warp 0 walks the tree on its own
+    if (tid < 32) {
+      const float r = warp_np_pairwise_sum_f32(f, n, tid);
+      if (tid == 0) sh.leaf_sum[0] = r;
+    }
+    __syncthreads();
+    const float r = sh.leaf_sum[0];
+    __syncthreads();
+    return r;
+  }
+  const int gid = tid >> 3, l8 = tid & 7;
+  for (int p0 = 0; p0 < nleaf; p0 += VAD_THREADS / 8) {
+    const int leaf = p0 + gid;
+    const bool active = leaf < nleaf;
+    const int lo = active ? sh.leaf_lo[leaf] : 0, cnt = active ? sh.leaf_cnt[leaf] : 0;
+    float r = 0.f;
+    const int body = cnt - (cnt % 8);
+    if (cnt >= 8) {
+      r = f(lo + l8);
+      for (int i = 8; i < body; i += 8) r = __fadd_rn(r, f(lo + i + l8));
+    }
+    __syncwarp();
+    r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
+    r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
+    r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
+    if (active && l8 == 0) {
+      float res = r;
+      if (cnt < 8) {
+        res = 0.f;
+        for (int i = 0; i < cnt; ++i) res = __fadd_rn(res, f(lo + i));
+      } else {
+        for (int i = body; i < cnt; ++i) res = __fadd_rn(res, f(lo + i));
+      }
+      sh.leaf_sum[leaf] = res;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    // fold: post-order evaluation of the same recursion, leaves consumed left to right
+    int s_n[40], s_stage[40], sp = 1, next = 0;
+    float s_left[40], ret = 0.f;
+    s_n[0] = n; s_stage[0] = 0; s_left[0] = 0.f;
+    while (sp > 0) {
+      const int t = sp - 1, cnt = s_n[t];
+      if (cnt <= 128) { ret = sh.leaf_sum[next++]; --sp; continue; }
+      int n2 = cnt / 2;
+      n2 -= n2 % 8;
+      if (s_stage[t] == 0) { s_stage[t] = 1; s_n[sp] = n2; s_stage[sp] = 0; ++sp; }
+      else if (s_stage[t] == 1) { s_left[t] = ret; s_stage[t] = 2; s_n[sp] = cnt - n2; s_stage[sp] = 0; ++sp; }
+      else { ret = __fadd_rn(s_left[t], ret); --sp; }
+    }
+    sh.leaf_sum[0] = ret;
+  }
+  __syncthreads();
+  const float r = sh.leaf_sum[0];
+  __syncthreads();
+  return r;
+}
+
+// 1-D EM of sklearn GaussianMixture with fixed inits (see oracle/frontend.py _em_1d).
+// Returns false where sklearn would raise ValueError.
+__device__ bool vad_em(const float* __restrict__ x, int n, int nc, int max_iter, VadShared& sh, cg::cluster_group& cl,
+                       double* mu_out, double* prec_out) {
+  constexpr int KMAX = VAD_KMAX;
+  const int gt = (int)cl.block_rank() * VAD_THREADS + threadIdx.x;
+  const int gstride = (int)cl.num_blocks() * VAD_THREADS;
   if (n < max(nc, 2)) return false;
   double w[KMAX], mu[KMAX], pch[KMAX];
   for (int k = 0; k < nc; ++k) {
@@ -750,15 +885,6 @@ __device__ bool vad_em(const float* __restrict__ x, int n, int nc, int max_iter,
     mu[k] = -2.0 + 4.0 * k / (double)(nc - 1);
     pch[k] = 1.0;
   }
-  if (tid == 0) *flag = 0;
-  __syncthreads();
-  int bad = 0;
-  for (int i = tid; i < n; i += VAD_THREADS) if (!isfinite(x[i])) bad = 1;
-  if (bad) *flag = 1;
-  __syncthreads();
-  bad = *flag;
-  __syncthreads();
-  if (bad) return false;
   const double LOG2PI = 1.8378770664093454835606594728112;
   double lower = -INFINITY;
   for (int it = 0; it < max_iter; ++it) {
@@ -770,9 +896,12 @@ __device__ bool vad_em(const float* __restrict__ x, int n, int nc, int max_iter,
       ld[k] = log(pch[k]);
       lw[k] = log(w[k]);
     }
-    double nk[KMAX] = {0, 0, 0, 0}, sx[KMAX] = {0, 0, 0, 0}, sxx[KMAX] = {0, 0, 0, 0}, lsum = 0.0;
-    for (int i = tid; i < n; i += VAD_THREADS) {
+    double acc[VAD_NRED];
+#pragma unroll
+    for (int k = 0; k < VAD_NRED; ++k) acc[k] = 0.0;
+    for (int i = gt; i < n; i += gstride) {
       const float xf = x[i];
+      if (!isfinite(xf)) acc[VAD_NRED - 1] += 1.0;
       const double xd = (double)xf, x2 = (double)__fmul_rn(xf, xf);  // x*x is float32 in sklearn
       double wl[KMAX], mx = -INFINITY;
       for (int k = 0; k < nc; ++k) {
@@ -781,47 +910,37 @@ __device__ bool vad_em(const float* __restrict__ x, int n, int nc, int max_iter,
         wl[k] = dadd(lp, lw[k]);
         mx = fmax(mx, wl[k]);
       }
-      double s = 0.0;
-      for (int k = 0; k < nc; ++k) s += exp(wl[k] - mx);
+      // responsibilities exp(wl - norm) = exp(wl - mx) / s: the exponentials of the log-sum-exp are
+      // reused instead of evaluated a second time (differs from sklearn's exp(wl - norm) by <= 1 ulp)
+      double ek[KMAX], s = 0.0;
+      for (int k = 0; k < nc; ++k) { ek[k] = exp(wl[k] - mx); s += ek[k]; }
       const double norm = mx + log(s);
-      lsum += norm;
+      const double inv = 1.0 / s;
+      acc[0] += norm;
       for (int k = 0; k < nc; ++k) {
-        const double r = exp(wl[k] - norm);
-        nk[k] += r;
-        sx[k] = fma(r, xd, sx[k]);
-        sxx[k] = fma(r, x2, sxx[k]);
+        const double r = ek[k] * inv;
+        acc[1 + k] += r;
+        acc[1 + KMAX + k] = fma(r, xd, acc[1 + KMAX + k]);
+        acc[1 + 2 * KMAX + k] = fma(r, x2, acc[1 + 2 * KMAX + k]);
       }
     }
-    // CTA reduction (fixed order: lanes by xor butterfly, then warps 0..7)
-    lsum = warp_sum(lsum);
-    for (int k = 0; k < nc; ++k) { nk[k] = warp_sum(nk[k]); sx[k] = warp_sum(sx[k]); sxx[k] = warp_sum(sxx[k]); }
-    if (lane == 0) {
-      red[warp][0] = lsum;
-      for (int k = 0; k < nc; ++k) { red[warp][1 + k] = nk[k]; red[warp][1 + KMAX + k] = sx[k]; red[warp][1 + 2 * KMAX + k] = sxx[k]; }
-    }
-    __syncthreads();
-    lsum = 0.0;
-    for (int k = 0; k < nc; ++k) { nk[k] = 0.0; sx[k] = 0.0; sxx[k] = 0.0; }
-    for (int wv = 0; wv < VAD_WARPS; ++wv) {
-      lsum += red[wv][0];
-      for (int k = 0; k < nc; ++k) { nk[k] += red[wv][1 + k]; sx[k] += red[wv][1 + KMAX + k]; sxx[k] += red[wv][1 + 2 * KMAX + k]; }
-    }
-    __syncthreads();  // red is rewritten in the next iteration
-    double nksum = 0.0;
+    vad_cluster_reduce(acc, sh, cl);
+    if (acc[VAD_NRED - 1] != 0.0) return false;   // sklearn rejects non-finite input
+    double nk[KMAX], nksum = 0.0;
     bool collapsed = false;
     for (int k = 0; k < nc; ++k) {
-      nk[k] += 10.0 * DBL_EPSILON;
+      nk[k] = acc[1 + k] + 10.0 * DBL_EPSILON;
       nksum += nk[k];
     }
     for (int k = 0; k < nc; ++k) {
-      mu[k] = sx[k] / nk[k];
-      const double var = dadd(dadd(sxx[k] / nk[k], -dmul(mu[k], mu[k])), 1e-6);
+      mu[k] = acc[1 + KMAX + k] / nk[k];
+      const double var = dadd(dadd(acc[1 + 2 * KMAX + k] / nk[k], -dmul(mu[k], mu[k])), 1e-6);
       if (!(var > 0.0)) collapsed = true;
       pch[k] = 1.0 / sqrt(var);
       w[k] = nk[k] / nksum;
     }
     if (collapsed) return false;
-    const double new_lower = lsum / (double)n;
+    const double new_lower = acc[0] / (double)n;
     const double change = new_lower - lower;
     lower = new_lower;
     if (fabs(change) < 1e-3) break;
@@ -830,13 +949,15 @@ __device__ bool vad_em(const float* __restrict__ x, int n, int nc, int max_iter,
   return true;
 }
 
-// One CTA per utterance (grid-stride over utterances).
-__global__ void __launch_bounds__(VAD_THREADS) fe_vad_gmm_kernel(VadArgs a) {
-  __shared__ double red[VAD_WARPS][VAD_NRED];
-  __shared__ float s_ms[2];
-  __shared__ int s_flag;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int u = blockIdx.x; u < a.n_utt; u += gridDim.x) {
+__global__ void __launch_bounds__(VAD_THREADS, 2) fe_vad_gmm_kernel(VadArgs a) {
+  __shared__ VadShared sh;
+  cg::cluster_group cl = cg::this_cluster();
+  const int tid = threadIdx.x;
+  const int gt = (int)cl.block_rank() * VAD_THREADS + tid;
+  const int ncta = (int)cl.num_blocks();       // cluster size, chosen per launch (1, 2, 4 or 8)
+  const int gstride = ncta * VAD_THREADS;
+  const int n_clusters = gridDim.x / ncta;
+  for (int u = blockIdx.x / ncta; u < a.n_utt; u += n_clusters) {
     const int64_t base = a.frame_off[u];
     const int n = (int)(a.frame_off[u + 1] - base);
     if (n <= 0) continue;
@@ -848,20 +969,21 @@ __global__ void __launch_bounds__(VAD_THREADS) fe_vad_gmm_kernel(VadArgs a) {
     double thr = 0.0;
     const float* src = e;
     while (true) {
-      // standardise in float32 exactly as numpy does (signal.py:305); the retry
-      // path of the reference re-standardises the already standardised vector
-      __syncthreads();  // previous readers of xs / s_ms are done
-      if (warp == 0) {
-        const MeanStdF32 ms = warp_np_mean_std_f32(src, n, lane);
-        if (lane == 0) { s_ms[0] = ms.mean; s_ms[1] = ms.std; }
-      }
-      __syncthreads();
-      const float mean = s_ms[0], sd = s_ms[1];
-      for (int i = tid; i < n; i += VAD_THREADS) xs[i] = __fdiv_rn(__fsub_rn(src[i], mean), sd);
-      __syncthreads();
+      // standardise in float32 exactly as numpy does (signal.py:305); the retry path of the
+      // reference re-standardises the already standardised vector.  Every CTA of the cluster
+      // evaluates mean / std redundantly (same bits), then writes its strided share of xs.
+      const float ssum = block_np_pairwise_sum_f32([src](int i) { return src[i]; }, n, sh);
+      const float mean = (float)((double)ssum / (double)n);
+      const float ss = block_np_pairwise_sum_f32(
+          [src, mean](int i) { const float d = __fadd_rn(src[i], -mean); return __fmul_rn(d, d); }, n, sh);
+      const float sd = sqrtf((float)((double)ss / (double)n));
+      cl.sync();  // every CTA is done reading src (== xs on the retry path) before it is overwritten
+      for (int i = gt; i < n; i += gstride) xs[i] = __fdiv_rn(__fsub_rn(src[i], mean), sd);
+      __threadfence();
+      cl.sync();
       src = xs;
       double mu[4], prec[4];
-      if (vad_em(xs, n, nc, a.iters, red, &s_flag, mu, prec)) {
+      if (vad_em(xs, n, nc, a.iters, sh, cl, mu, prec)) {
         int kb = 0;
         for (int k = 1; k < nc; ++k) if (mu[k] > mu[kb]) kb = k;
         thr = dadd(mu[kb], -dmul(a.mode, sqrt(1.0 / prec[kb])));
@@ -871,15 +993,16 @@ __global__ void __launch_bounds__(VAD_THREADS) fe_vad_gmm_kernel(VadArgs a) {
       if (nc - 1 >= 2) { --nc; continue; }
       break;
     }
-    if (a.thr_out != nullptr && tid == 0) a.thr_out[u] = ok ? thr : 0.0;
+    if (a.thr_out != nullptr && gt == 0) a.thr_out[u] = ok ? thr : 0.0;
     if (!ok) {
-      for (int i = tid; i < n; i += VAD_THREADS) out[i] = 0;
-      continue;
+      for (int i = gt; i < n; i += gstride) out[i] = 0;
+    } else {
+      auto raw = [xs, thr](int i) -> int { return ((double)xs[i] > thr) ? 1 : 0; };
+      const bool do_smooth = a.smooth >= 3 && n >= a.smooth;
+      for (int i = gt; i < n; i += gstride)
+        out[i] = do_smooth ? (uint8_t)smooth_flat_ge_f(raw, n, a.smooth, false, i) : (uint8_t)raw(i);
     }
-    auto raw = [xs, thr](int i) -> int { return ((double)xs[i] > thr) ? 1 : 0; };
-    const bool do_smooth = a.smooth >= 3 && n >= a.smooth;
-    for (int i = tid; i < n; i += VAD_THREADS)
-      out[i] = do_smooth ? (uint8_t)smooth_flat_ge_f(raw, n, a.smooth, false, i) : (uint8_t)raw(i);
+    cl.sync();  // xs / sh are reused by the cluster's next utterance
   }
 }
 
@@ -1051,8 +1174,10 @@ int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t 
               double* d_sad_thr, cudaStream_t st) {
   const odin_fe_config& c = fe->cfg;
   if (total_frames <= 0) return ODIN_OK;
-  if (fe->ev[0] == nullptr)
-    for (int i = 0; i < 5; ++i) ODIN_CUDA_CHECK(cudaEventCreate(&fe->ev[i]));
+  if (fe->ev[0] == nullptr) {
+    for (int i = 0; i < 7; ++i) ODIN_CUDA_CHECK(cudaEventCreate(&fe->ev[i]));
+    ODIN_CUDA_CHECK(cudaStreamCreateWithFlags(&fe->aux, cudaStreamNonBlocking));
+  }
   ODIN_CUDA_CHECK(cudaEventRecord(fe->ev[0], st));
   // 1. DC sums
   if (c.remove_dc) {
@@ -1098,6 +1223,68 @@ int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t 
     if (rc) return rc;
   }
   ODIN_CUDA_CHECK(cudaEventRecord(fe->ev[2], st));
+  // SADgmm reads only the frame energies, so it is forked onto the auxiliary stream and runs beside the
+  // utterance pass (its tail is a handful of long utterances); SADthreshold needs c0 and stays in line.
+  const bool has_vad = c.vad_kind != 0 && d_sad != nullptr;
+  // (measured: the fork only pays when the utterance pass is long; off unless ODIN_FE_VAD_FORK=1)
+  const char* wantfork = getenv("ODIN_FE_VAD_FORK");
+  const bool fork = has_vad && c.vad_kind == 1 && (wantfork && wantfork[0] == '1');
+  fe->vad_forked = fork;
+  auto launch_vad = [&](cudaStream_t vst) -> int {
+    {
+      VadArgs v{};
+      v.frame_off = fe->d_frame_off; v.n_utt = n_utt; v.sad = d_sad; v.thr_out = d_sad_thr;
+      v.nmix = c.vad_nmix; v.iters = c.vad_iters; v.smooth = c.vad_smooth; v.mode = (double)c.vad_mode;
+      v.thr_energy = (double)c.thr_energy; v.thr_mean_scale = (double)c.thr_mean_scale;
+      v.thr_proportion = (double)c.thr_proportion; v.thr_context = c.thr_context;
+      // scratch: reuse the per-frame part of the handle
+      if (fe->vad_scratch_cap < total_frames) {
+        if (fe->d_vad_scratch) ODIN_CUDA_CHECK(cudaFree(fe->d_vad_scratch));
+        fe->d_vad_scratch = nullptr; fe->vad_scratch_cap = 0;
+        ODIN_CUDA_CHECK(cudaMalloc(&fe->d_vad_scratch, sizeof(float) * (total_frames + total_frames / 8 + 256)));
+        fe->vad_scratch_cap = total_frames + total_frames / 8 + 256;
+      }
+      v.scratch = fe->d_vad_scratch;
+      int warps_per_cta = 4;
+      int grid = (int)std::min<int64_t>(ceil_div(n_utt, warps_per_cta), (int64_t)sm_count() * 8);
+      if (c.vad_kind == 1) {
+        if (d_energy == nullptr) return set_error(ODIN_EINVAL, "SADgmm needs d_energy");
+        v.x = d_energy;
+        // cluster size: the largest power of two such that all clusters of the batch are resident
+        // at once (2 CTAs of 256 threads per SM)
+        int ncta = 1;
+        while (ncta < VAD_CL_MAX && (int64_t)n_utt * (ncta * 2) <= (int64_t)sm_count() * 2) ncta *= 2;
+        const int64_t n_cl = std::min<int64_t>(n_utt, (int64_t)sm_count() * 4);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(n_cl * ncta));
+        cfg.blockDim = dim3(VAD_THREADS);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = vst;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)ncta;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        ODIN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, fe_vad_gmm_kernel, v));
+        ODIN_LAUNCH_CHECK("fe_vad_gmm_kernel");
+      } else {
+        if (d_c0 == nullptr) return set_error(ODIN_EINVAL, "SADthreshold needs d_c0");
+        v.x = d_c0;
+        fe_vad_thr_kernel<<<grid, 128, 0, vst>>>(v);
+        ODIN_LAUNCH_CHECK("fe_vad_thr_kernel");
+      }
+    }
+    return ODIN_OK;
+  };
+  if (fork) {
+    ODIN_CUDA_CHECK(cudaStreamWaitEvent(fe->aux, fe->ev[2], 0));
+    ODIN_CUDA_CHECK(cudaEventRecord(fe->ev[5], fe->aux));
+    int rc = launch_vad(fe->aux);
+    if (rc) return rc;
+    ODIN_CUDA_CHECK(cudaEventRecord(fe->ev[6], fe->aux));
+  }
   // 3. utterance pass
   {
     PostArgs p{};
@@ -1117,35 +1304,11 @@ int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t 
     ODIN_LAUNCH_CHECK("fe_post_kernel");
   }
   ODIN_CUDA_CHECK(cudaEventRecord(fe->ev[3], st));
-  // 4. VAD
-  if (c.vad_kind != 0 && d_sad != nullptr) {
-    VadArgs v{};
-    v.frame_off = fe->d_frame_off; v.n_utt = n_utt; v.sad = d_sad; v.thr_out = d_sad_thr;
-    v.nmix = c.vad_nmix; v.iters = c.vad_iters; v.smooth = c.vad_smooth; v.mode = (double)c.vad_mode;
-    v.thr_energy = (double)c.thr_energy; v.thr_mean_scale = (double)c.thr_mean_scale;
-    v.thr_proportion = (double)c.thr_proportion; v.thr_context = c.thr_context;
-    // scratch: reuse the per-frame part of the handle
-    if (fe->vad_scratch_cap < total_frames) {
-      if (fe->d_vad_scratch) ODIN_CUDA_CHECK(cudaFree(fe->d_vad_scratch));
-      fe->d_vad_scratch = nullptr; fe->vad_scratch_cap = 0;
-      ODIN_CUDA_CHECK(cudaMalloc(&fe->d_vad_scratch, sizeof(float) * (total_frames + total_frames / 8 + 256)));
-      fe->vad_scratch_cap = total_frames + total_frames / 8 + 256;
-    }
-    v.scratch = fe->d_vad_scratch;
-    int warps_per_cta = 4;
-    int grid = (int)std::min<int64_t>(ceil_div(n_utt, warps_per_cta), (int64_t)sm_count() * 8);
-    if (c.vad_kind == 1) {
-      if (d_energy == nullptr) return set_error(ODIN_EINVAL, "SADgmm needs d_energy");
-      v.x = d_energy;
-      const int grid_gmm = (int)std::min<int64_t>(n_utt, (int64_t)sm_count() * 8);
-      fe_vad_gmm_kernel<<<grid_gmm, VAD_THREADS, 0, st>>>(v);
-      ODIN_LAUNCH_CHECK("fe_vad_gmm_kernel");
-    } else {
-      if (d_c0 == nullptr) return set_error(ODIN_EINVAL, "SADthreshold needs d_c0");
-      v.x = d_c0;
-      fe_vad_thr_kernel<<<grid, 128, 0, st>>>(v);
-      ODIN_LAUNCH_CHECK("fe_vad_thr_kernel");
-    }
+  if (fork) {
+    ODIN_CUDA_CHECK(cudaStreamWaitEvent(st, fe->ev[6], 0));
+  } else if (has_vad) {
+    int rc = launch_vad(st);
+    if (rc) return rc;
   }
   ODIN_CUDA_CHECK(cudaEventRecord(fe->ev[4], st));
   fe->ev_valid = true;

@@ -21,6 +21,7 @@ from collections.abc import Mapping
 import numpy as np
 
 from .. import _lib
+from .. import sharding
 
 EPS = 1e-6  # gmm_tmat.py:27
 
@@ -405,9 +406,7 @@ class GMM(object):
       sad_ptr = None if d_mask is None else _lib.C.c_void_p(d_mask.data_ptr() + s)
       _lib.check(lib.odin_gmm_estep(self._handle, _lib.ptr(dev), sad_ptr, e - s, 1 if second else 0,
                                     _lib.ptr(stats), self.impl, _lib.current_stream()))
-    td = _dist()
-    if td is not None:
-      td.all_reduce(stats, op=td.ReduceOp.SUM)  # gmm_tmat.py:249-265 -> one NCCL all-reduce
+    sharding.allreduce_stats(stats)  # gmm_tmat.py:249-265 -> one NCCL all-reduce per EM iteration
     return stats
 
   def _fast_expectation(self, X, zero=True, first=True, second=True, llk=True, on_gpu=True):

@@ -1,0 +1,81 @@
+"""Multi-GPU plumbing of the hot path: one process per GPU, utterances
+sharded by rank, ONE sum all-reduce of the packed statistics per EM iteration.
+
+The reference fans the E-step out over forked workers and sums their partial
+(Z, F, S, L) through a multiprocessing queue (gmm_tmat.py:249-265, 1199-1220);
+here every rank accumulates its own frames on its GPU and the partials meet in a
+single `all_reduce(SUM)` of the packed fp64 buffer  Z[M] | F[D,M] | S[D,M] | L | n
+(NCCL over NVLink on GPUs; gloo in the CPU tests).  The M-step and the mixture
+split are deterministic functions of that buffer, so they are simply replicated.
+"""
+import numpy as np
+
+
+def shard_utterances(n_frames, world_size):
+  """Greedy longest-first assignment of whole utterances to ranks by frame count.
+
+  n_frames: sequence of per-utterance frame counts (job order).
+  Returns a list of `world_size` index lists; every list is in ascending job order
+  (the order in which a rank stores its rows), the assignment is deterministic
+  (ties broken by job index) and each utterance appears exactly once.
+  """
+  n_frames = np.asarray(n_frames, dtype=np.int64)
+  world_size = int(world_size)
+  if world_size < 1:
+    raise ValueError("world_size must be >= 1")
+  order = sorted(range(len(n_frames)), key=lambda i: (-int(n_frames[i]), i))
+  load = [0] * world_size
+  out = [[] for _ in range(world_size)]
+  for i in order:
+    r = min(range(world_size), key=lambda k: (load[k], k))
+    out[r].append(i)
+    load[r] += int(n_frames[i])
+  return [sorted(ix) for ix in out]
+
+
+def pack_stats(Z, F, S, L, n):
+  """Z [1,M] | F [D,M] | S [D,M] | sum-LLK | nframes -> the packed fp64 vector the kernels use."""
+  return np.concatenate([np.asarray(Z, np.float64).reshape(-1), np.asarray(F, np.float64).reshape(-1),
+                         np.asarray(S, np.float64).reshape(-1), [float(L), float(n)]])
+
+
+def unpack_stats(packed, D, M):
+  packed = np.asarray(packed, dtype=np.float64)
+  Z = packed[:M].reshape(1, M)
+  F = packed[M:M + D * M].reshape(D, M)
+  S = packed[M + D * M:M + 2 * D * M].reshape(D, M)
+  return Z, F, S, float(packed[-2]), float(packed[-1])
+
+
+def _dist():
+  import torch.distributed as td
+  if td.is_available() and td.is_initialized() and td.get_world_size() > 1:
+    return td
+  return None
+
+
+def allreduce_stats(stats):
+  """In-place sum over ranks of the packed statistics (torch tensor, CUDA -> NCCL,
+  CPU -> gloo).  No-op for a single process.  Returns `stats`."""
+  td = _dist()
+  if td is not None:
+    td.all_reduce(stats, op=td.ReduceOp.SUM)
+  return stats
+
+
+def gather_rows(local_rows, local_index, n_total):
+  """Per-utterance statistics (gmm_tmat.py:769-913) need no collective on the data path: each
+  rank owns the rows of its utterances.  This host-side helper assembles the [n_total, width]
+  matrix in JOB order on every rank from each rank's (rows, job indices)."""
+  local_rows = np.asarray(local_rows)
+  td = _dist()
+  if td is None:
+    out = np.zeros((n_total, local_rows.shape[1]), dtype=local_rows.dtype)
+    out[np.asarray(local_index, dtype=np.int64)] = local_rows
+    return out
+  parts = [None] * td.get_world_size()
+  td.all_gather_object(parts, (np.asarray(local_index, dtype=np.int64), local_rows))
+  out = np.zeros((n_total, local_rows.shape[1]), dtype=local_rows.dtype)
+  for idx, rows in parts:
+    out[idx] = rows
+  return out
