@@ -158,6 +158,18 @@ int odin_gmm_set_params(odin_gmm_t* g, int32_t nmix, const float* d_mean, const 
 int odin_gmm_estep(odin_gmm_t* g, const float* d_X, const uint8_t* d_sad, int64_t n_frames,
                    int32_t want_second, double* d_stats, int32_t impl, void* stream);
 
+/* Prepared frames (3xFP16 tensor path only).  The kernel-ready operand images of a frame matrix
+ * depend on the data alone, so for frames that stay resident across EM iterations
+ * (gmm_tmat.py:1278-1306 visits the same X every iteration) they can be built once: 1 KB of HBM
+ * per frame.  odin_gmm_estep_frames == odin_gmm_estep(impl 3) on the same frames, minus the image
+ * build.  ODIN_ENOMEM if the images do not fit (fall back to odin_gmm_estep). */
+typedef struct odin_gmm_frames odin_gmm_frames_t;
+int odin_gmm_frames_create(odin_gmm_t* g, const float* d_X, int64_t n_frames, odin_gmm_frames_t** out,
+                           void* stream);
+void odin_gmm_frames_destroy(odin_gmm_frames_t* f);
+int odin_gmm_estep_frames(odin_gmm_t* g, const odin_gmm_frames_t* f, const uint8_t* d_sad, int32_t want_second,
+                          double* d_stats, void* stream);
+
 /* M-step (gmm_tmat.py:1233-1276) from packed stats, in fp64 on device; writes the
  * new model into the handle AND to d_mean/d_var/d_w (fp32, reference layout).
  * If any variance < 0: allow_rollback = 1 keeps the previous model, 0 clips at 0;

@@ -466,6 +466,26 @@ int odin_gmm_estep(odin_gmm_t* g, const float* d_X, const uint8_t* d_sad, int64_
   return ODIN_OK;
 }
 
+int odin_gmm_frames_create(odin_gmm_t* g, const float* d_X, int64_t n_frames, odin_gmm_frames_t** out, void* stream) {
+  if (!g || !d_X || !out || n_frames <= 0) return set_error(ODIN_EINVAL, "bad argument");
+  return gmm_frames_create(g, d_X, n_frames, reinterpret_cast<void**>(out), as_stream(stream));
+}
+
+void odin_gmm_frames_destroy(odin_gmm_frames_t* f) { gmm_frames_destroy(f); }
+
+int odin_gmm_estep_frames(odin_gmm_t* g, const odin_gmm_frames_t* f, const uint8_t* d_sad, int32_t want_second,
+                          double* d_stats, void* stream) {
+  if (!g || !f || !d_stats) return set_error(ODIN_EINVAL, "bad argument");
+  if (g->M <= 0) return set_error(ODIN_EINVAL, "odin_gmm_set_params has not been called");
+  if (g->ev[0] == nullptr)
+    for (int i = 0; i < 3; ++i) ODIN_CUDA_CHECK(cudaEventCreate(&g->ev[i]));
+  int rc = gmm_estep_frames(g, f, d_sad, want_second, d_stats, as_stream(stream));
+  if (rc) return rc;
+  g->ev_valid = true;
+  g->last_impl = 3;
+  return ODIN_OK;
+}
+
 int64_t odin_gmm_last_estep_frames(const odin_gmm_t* g) { return g ? g->last_frames : ODIN_EINVAL; }
 
 int odin_gmm_last_estep_ms(odin_gmm_t* g, float* lse_ms, float* stats_ms, int32_t* impl_used) {

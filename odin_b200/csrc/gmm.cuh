@@ -39,6 +39,7 @@ struct odin_gmm {
   void* d_himgT = nullptr;
   float* d_hcb = nullptr;
   int64_t h_cap = 0;       // frames the images hold
+  int64_t h_cb_cap = 0;    // frames d_hcb holds
   int64_t last_frames = 0; // frames covered by the events of the most recent E-step
   // per-frame log-sum-exp workspace (grows on demand)
   float* d_lse = nullptr;
@@ -83,6 +84,11 @@ bool gmm_h_supported(const odin_gmm* g);
 int gmm_estep_h(odin_gmm* g, const float* X, const uint8_t* sad, int64_t N, int want_second, double* stats,
                 cudaStream_t st);
 void gmm_h_free(odin_gmm* g);
+// prepared frames (operand images of a resident frame matrix, built once)
+int gmm_frames_create(odin_gmm* g, const float* X, int64_t N, void** out, cudaStream_t st);
+void gmm_frames_destroy(void* f);
+int gmm_estep_frames(odin_gmm* g, const void* f, const uint8_t* sad, int want_second, double* stats,
+                     cudaStream_t st);
 
 int gmm_mstep_launch(odin_gmm* g, const double* stats, int allow_rollback, int* rolled_back, cudaStream_t st);
 int gmm_mixup_launch(odin_gmm* g, int newM, cudaStream_t st);

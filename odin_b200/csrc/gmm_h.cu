@@ -710,7 +710,7 @@ static int h_flush_tiles() {
   return v < 1 ? 1 : v;
 }
 
-static int h_reserve(odin_gmm* g, int64_t sub) {
+static int h_reserve(odin_gmm* g, int64_t sub, bool need_images) {
   const int64_t mpad = ceil_div<int64_t>(g->max_nmix, hk::CM1) * hk::CM1;
   if (g->d_hscale == nullptr) {
     ODIN_CUDA_CHECK(cudaMalloc(&g->d_hscale, sizeof(HScale)));
@@ -718,16 +718,20 @@ static int h_reserve(odin_gmm* g, int64_t sub) {
     ODIN_CUDA_CHECK(cudaMalloc(&g->d_hWimg, (size_t)(mpad / hk::CM1) * 131072));
     ODIN_CUDA_CHECK(cudaMalloc(&g->d_hdsc, (size_t)mpad * sizeof(float)));
   }
-  if (sub > g->h_cap) {
+  if (need_images && sub > g->h_cap) {
     if (g->d_himgA) ODIN_CUDA_CHECK(cudaFree(g->d_himgA));
     if (g->d_himgT) ODIN_CUDA_CHECK(cudaFree(g->d_himgT));
-    if (g->d_hcb) ODIN_CUDA_CHECK(cudaFree(g->d_hcb));
-    g->d_himgA = g->d_himgT = nullptr; g->d_hcb = nullptr; g->h_cap = 0;
+    g->d_himgA = g->d_himgT = nullptr; g->h_cap = 0;
     const int64_t nsuper = sub / hk::TF1;
     ODIN_CUDA_CHECK(cudaMalloc(&g->d_himgA, (size_t)nsuper * hk::SUPER_A_BYTES));
     ODIN_CUDA_CHECK(cudaMalloc(&g->d_himgT, (size_t)nsuper * 2 * hk::TILE_T_BYTES));
-    ODIN_CUDA_CHECK(cudaMalloc(&g->d_hcb, (size_t)sub * sizeof(float)));
     g->h_cap = sub;
+  }
+  if (sub > g->h_cb_cap) {
+    if (g->d_hcb) ODIN_CUDA_CHECK(cudaFree(g->d_hcb));
+    g->d_hcb = nullptr; g->h_cb_cap = 0;
+    ODIN_CUDA_CHECK(cudaMalloc(&g->d_hcb, (size_t)sub * sizeof(float)));
+    g->h_cb_cap = sub;
   }
   const int nparts = (int)(mpad / hk::CM1) * 2;
   const int64_t need = sub * nparts;
@@ -740,36 +744,86 @@ static int h_reserve(odin_gmm* g, int64_t sub) {
   return ODIN_OK;
 }
 
+static int h_launch_range(const float* X, int64_t N, int D, HScale* sc, cudaStream_t st) {
+  ODIN_CUDA_CHECK(cudaMemsetAsync(sc, 0, sizeof(unsigned) * 64, st));
+  const int threads = 16 * (D >> 2);
+  const int64_t total4 = N * (D >> 2);
+  const int grid = (int)std::min<int64_t>(ceil_div<int64_t>(total4, (int64_t)threads * 8), (int64_t)sm_count() * 8);
+  gmm_h_range_kernel<<<std::max(grid, 1), threads, 0, st>>>(X, N, D, sc);
+  ODIN_LAUNCH_CHECK("gmm_h_range_kernel");
+  gmm_h_scale_kernel<<<1, 128, 0, st>>>(D, sc);
+  ODIN_LAUNCH_CHECK("gmm_h_scale_kernel");
+  return ODIN_OK;
+}
+
+static int h_launch_prepare(odin_gmm* g, const HScale* sc, cudaStream_t st) {
+  const int mpad = ceil_div(g->M, hk::CM1) * hk::CM1;
+  gmm_h_prepare_kernel<<<ceil_div(mpad, 64), 64, 0, st>>>(g->d_mean, g->d_var, g->d_w, g->D, g->M, mpad, sc,
+                                                          reinterpret_cast<uint32_t*>(g->d_hWplain),
+                                                          reinterpret_cast<uint32_t*>(g->d_hWimg), g->d_hdsc);
+  ODIN_LAUNCH_CHECK("gmm_h_prepare_kernel");
+  ODIN_CUDA_CHECK(cudaFuncSetAttribute(gmm_h_lse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hk::L_SMEM));
+  ODIN_CUDA_CHECK(cudaFuncSetAttribute(gmm_h_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hk::S_SMEM));
+  return ODIN_OK;
+}
+
+// pass 1 + combine + pass 2 over n frames whose operand images start at imgA / imgT
+static int h_launch_passes(odin_gmm* g, const HScale* sc, const unsigned char* imgA, const unsigned char* imgT,
+                           int64_t n, int64_t part_stride, const uint8_t* sad, int want_second, double* stats,
+                           bool record, cudaStream_t st) {
+  const int D = g->D, M = g->M;
+  const int mpad = ceil_div(M, hk::CM1) * hk::CM1;
+  const int nch1 = mpad / hk::CM1, nch2 = mpad / hk::CM2;
+  const int64_t nsuper = ceil_div<int64_t>(n, hk::TF1);
+  double* statL = stats + (stats_size(D, M) - 2);
+  HArgs a{};
+  a.N = n; a.D = D; a.M = M;
+  a.imgA = imgA;
+  a.imgT = imgT;
+  a.Wplain = reinterpret_cast<const uint32_t*>(g->d_hWplain);
+  a.Wimg = reinterpret_cast<const unsigned char*>(g->d_hWimg);
+  a.dsc = g->d_hdsc;
+  a.dscale = sc->dscale;
+  a.cb = g->d_hcb;
+  a.part = reinterpret_cast<float2*>(g->d_part);
+  a.part_stride = part_stride;
+  a.stats = stats;
+  a.want_second = want_second;
+  a.flush_tiles = h_flush_tiles();
+  {
+    const int64_t splits = std::max<int64_t>(1, std::min<int64_t>(sm_count() / nch1, nsuper));
+    gmm_h_lse_kernel<<<dim3(nch1, (unsigned)splits), hk::THREADS, hk::L_SMEM, st>>>(a);
+    ODIN_LAUNCH_CHECK("gmm_h_lse_kernel");
+  }
+  const int64_t npad = nsuper * hk::TF1;
+  gmm_h_combine_kernel<<<(unsigned)ceil_div<int64_t>(npad, 256), 256, 0, st>>>(
+      reinterpret_cast<const float2*>(g->d_part), nch1 * 2, part_stride, n, npad, sad, g->d_hcb, statL);
+  ODIN_LAUNCH_CHECK("gmm_h_combine_kernel");
+  if (record) ODIN_CUDA_CHECK(cudaEventRecord(g->ev[1], st));
+  {
+    const int64_t splits = std::max<int64_t>(1, std::min<int64_t>(sm_count() / nch2, nsuper * 2));
+    gmm_h_stats_kernel<<<dim3(nch2, (unsigned)splits), hk::THREADS, hk::S_SMEM, st>>>(a);
+    ODIN_LAUNCH_CHECK("gmm_h_stats_kernel");
+  }
+  if (record) {
+    ODIN_CUDA_CHECK(cudaEventRecord(g->ev[2], st));
+    g->last_frames = n;
+  }
+  return ODIN_OK;
+}
+
 // Whole E-step (both passes) over N frames; events ev[0..2] bracket (image + pass 1 | pass 2)
 // of the LAST sub-batch, g->last_frames = its size.
 int gmm_estep_h(odin_gmm* g, const float* X, const uint8_t* sad, int64_t N, int want_second, double* stats,
                 cudaStream_t st) {
   if (N <= 0) return ODIN_OK;
   const int64_t sub = std::min<int64_t>(h_sub_batch(), ceil_div<int64_t>(N, hk::TF1) * hk::TF1);
-  int rc = h_reserve(g, sub);
+  int rc = h_reserve(g, sub, true);
   if (rc) return rc;
-  const int D = g->D, M = g->M;
-  const int mpad = ceil_div(M, hk::CM1) * hk::CM1;
+  const int D = g->D;
   HScale* sc = reinterpret_cast<HScale*>(g->d_hscale);
-  // 1. data range -> scales -> scaled model images
-  ODIN_CUDA_CHECK(cudaMemsetAsync(sc, 0, sizeof(unsigned) * 64, st));
-  {
-    const int threads = 16 * (D >> 2);
-    const int64_t total4 = N * (D >> 2);
-    const int grid = (int)std::min<int64_t>(ceil_div<int64_t>(total4, (int64_t)threads * 8), (int64_t)sm_count() * 8);
-    gmm_h_range_kernel<<<std::max(grid, 1), threads, 0, st>>>(X, N, D, sc);
-    ODIN_LAUNCH_CHECK("gmm_h_range_kernel");
-  }
-  gmm_h_scale_kernel<<<1, 128, 0, st>>>(D, sc);
-  ODIN_LAUNCH_CHECK("gmm_h_scale_kernel");
-  gmm_h_prepare_kernel<<<ceil_div(mpad, 64), 64, 0, st>>>(g->d_mean, g->d_var, g->d_w, D, M, mpad, sc,
-                                                          reinterpret_cast<uint32_t*>(g->d_hWplain),
-                                                          reinterpret_cast<uint32_t*>(g->d_hWimg), g->d_hdsc);
-  ODIN_LAUNCH_CHECK("gmm_h_prepare_kernel");
-  ODIN_CUDA_CHECK(cudaFuncSetAttribute(gmm_h_lse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hk::L_SMEM));
-  ODIN_CUDA_CHECK(cudaFuncSetAttribute(gmm_h_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hk::S_SMEM));
-  const int nch1 = mpad / hk::CM1, nch2 = mpad / hk::CM2;
-  double* statL = stats + (stats_size(D, M) - 2);
+  if ((rc = h_launch_range(X, N, D, sc, st))) return rc;   // data range -> exact power-of-two scales
+  if ((rc = h_launch_prepare(g, sc, st))) return rc;       // scaled model images
   for (int64_t s0 = 0; s0 < N; s0 += sub) {
     const int64_t n = std::min<int64_t>(sub, N - s0);
     const int64_t nsuper = ceil_div<int64_t>(n, hk::TF1);
@@ -779,39 +833,81 @@ int gmm_estep_h(odin_gmm* g, const float* X, const uint8_t* sad, int64_t N, int 
                                                           reinterpret_cast<unsigned char*>(g->d_himgA),
                                                           reinterpret_cast<unsigned char*>(g->d_himgT));
     ODIN_LAUNCH_CHECK("gmm_h_image_kernel");
-    HArgs a{};
-    a.N = n; a.D = D; a.M = M;
-    a.imgA = reinterpret_cast<const unsigned char*>(g->d_himgA);
-    a.imgT = reinterpret_cast<const unsigned char*>(g->d_himgT);
-    a.Wplain = reinterpret_cast<const uint32_t*>(g->d_hWplain);
-    a.Wimg = reinterpret_cast<const unsigned char*>(g->d_hWimg);
-    a.dsc = g->d_hdsc;
-    a.dscale = sc->dscale;
-    a.cb = g->d_hcb;
-    a.part = reinterpret_cast<float2*>(g->d_part);
-    a.part_stride = sub;
-    a.stats = stats;
-    a.want_second = want_second;
-    a.flush_tiles = h_flush_tiles();
-    {
-      const int64_t splits = std::max<int64_t>(1, std::min<int64_t>(sm_count() / nch1, nsuper));
-      gmm_h_lse_kernel<<<dim3(nch1, (unsigned)splits), hk::THREADS, hk::L_SMEM, st>>>(a);
-      ODIN_LAUNCH_CHECK("gmm_h_lse_kernel");
-    }
-    const int64_t npad = nsuper * hk::TF1;
-    gmm_h_combine_kernel<<<(unsigned)ceil_div<int64_t>(npad, 256), 256, 0, st>>>(
-        reinterpret_cast<const float2*>(g->d_part), nch1 * 2, sub, n, npad, sad ? sad + s0 : nullptr, g->d_hcb, statL);
-    ODIN_LAUNCH_CHECK("gmm_h_combine_kernel");
-    if (last) ODIN_CUDA_CHECK(cudaEventRecord(g->ev[1], st));
-    {
-      const int64_t splits = std::max<int64_t>(1, std::min<int64_t>(sm_count() / nch2, nsuper * 2));
-      gmm_h_stats_kernel<<<dim3(nch2, (unsigned)splits), hk::THREADS, hk::S_SMEM, st>>>(a);
-      ODIN_LAUNCH_CHECK("gmm_h_stats_kernel");
-    }
-    if (last) {
-      ODIN_CUDA_CHECK(cudaEventRecord(g->ev[2], st));
-      g->last_frames = n;
-    }
+    rc = h_launch_passes(g, sc, reinterpret_cast<const unsigned char*>(g->d_himgA),
+                         reinterpret_cast<const unsigned char*>(g->d_himgT), n, sub, sad ? sad + s0 : nullptr,
+                         want_second, stats, last, st);
+    if (rc) return rc;
+  }
+  return ODIN_OK;
+}
+
+// ---- prepared frames: the operand images depend on the data only, so a resident frame matrix
+// that is visited once per EM iteration gets them built ONCE (1 KB per frame)
+struct GmmFrames {
+  int D = 0, device = 0;
+  int64_t N = 0;
+  HScale* scale = nullptr;
+  unsigned char* imgA = nullptr;
+  unsigned char* imgT = nullptr;
+};
+
+void gmm_frames_destroy(void* p) {
+  GmmFrames* f = reinterpret_cast<GmmFrames*>(p);
+  if (!f) return;
+  cudaFree(f->scale); cudaFree(f->imgA); cudaFree(f->imgT);
+  delete f;
+}
+
+int gmm_frames_create(odin_gmm* g, const float* X, int64_t N, void** out, cudaStream_t st) {
+  *out = nullptr;
+  if (g->D % 4 != 0 || g->D > hk::MAX_D || g->D < 4)
+    return set_error(ODIN_EINVAL, "prepared frames need D %% 4 == 0 and D <= %d", hk::MAX_D);
+  GmmFrames* f = new (std::nothrow) GmmFrames();
+  if (!f) return set_error(ODIN_ENOMEM, "out of host memory");
+  f->D = g->D; f->N = N; f->device = g->device;
+  const int64_t nsuper = ceil_div<int64_t>(N, hk::TF1);
+  cudaError_t e;
+  if ((e = cudaMalloc(&f->scale, sizeof(HScale))) != cudaSuccess ||
+      (e = cudaMalloc(&f->imgA, (size_t)nsuper * hk::SUPER_A_BYTES)) != cudaSuccess ||
+      (e = cudaMalloc(&f->imgT, (size_t)nsuper * 2 * hk::TILE_T_BYTES)) != cudaSuccess) {
+    cudaGetLastError();
+    gmm_frames_destroy(f);
+    return set_error(ODIN_ENOMEM, "prepared frames: cudaMalloc of %lld MB failed: %s",
+                     (long long)(nsuper * 131072 >> 20), cudaGetErrorString(e));
+  }
+  int rc = h_launch_range(X, N, g->D, f->scale, st);
+  if (rc) { gmm_frames_destroy(f); return rc; }
+  const int64_t per = (int64_t)1 << 22;   // super-tiles per launch (grid.x limit is not a concern; keeps launches short)
+  for (int64_t s0 = 0; s0 < nsuper; s0 += per) {
+    const int64_t ns = std::min<int64_t>(per, nsuper - s0);
+    gmm_h_image_kernel<<<(unsigned)ns, 256, 0, st>>>(X + s0 * hk::TF1 * g->D, N - s0 * hk::TF1, g->D, f->scale,
+                                                      f->imgA + (size_t)s0 * hk::SUPER_A_BYTES,
+                                                      f->imgT + (size_t)s0 * 2 * hk::TILE_T_BYTES);
+    ODIN_LAUNCH_CHECK("gmm_h_image_kernel");
+  }
+  *out = f;
+  return ODIN_OK;
+}
+
+int gmm_estep_frames(odin_gmm* g, const void* pf, const uint8_t* sad, int want_second, double* stats,
+                     cudaStream_t st) {
+  const GmmFrames* f = reinterpret_cast<const GmmFrames*>(pf);
+  if (f->D != g->D) return set_error(ODIN_EINVAL, "prepared frames have D=%d, model has D=%d", f->D, g->D);
+  if (!gmm_h_supported(g)) return set_error(ODIN_EINVAL, "prepared frames need the 3xFP16 path (M >= 256)");
+  const int64_t N = f->N;
+  if (N <= 0) return ODIN_OK;
+  const int64_t sub = std::min<int64_t>(h_sub_batch(), ceil_div<int64_t>(N, hk::TF1) * hk::TF1);
+  int rc = h_reserve(g, sub, false);
+  if (rc) return rc;
+  if ((rc = h_launch_prepare(g, f->scale, st))) return rc;
+  for (int64_t s0 = 0; s0 < N; s0 += sub) {
+    const int64_t n = std::min<int64_t>(sub, N - s0);
+    const bool last = s0 + sub >= N;
+    if (last) ODIN_CUDA_CHECK(cudaEventRecord(g->ev[0], st));
+    rc = h_launch_passes(g, f->scale, f->imgA + (size_t)(s0 / hk::TF1) * hk::SUPER_A_BYTES,
+                         f->imgT + (size_t)(s0 / hk::TF2) * hk::TILE_T_BYTES, n, sub, sad ? sad + s0 : nullptr,
+                         want_second, stats, last, st);
+    if (rc) return rc;
   }
   return ODIN_OK;
 }

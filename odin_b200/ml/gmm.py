@@ -77,6 +77,33 @@ class _DeviceFrames(object):
 
   shape = property(lambda self: (self.n, self.dim))
   ndim = 2
+  _prepared = None
+  _prepared_failed = False
+  reuse = False   # set by callers that keep this object across EM iterations (fit, bench)
+
+  def prepared(self, gmm_handle):
+    """Tensor-core operand images of the RESIDENT frames (odin_gmm_frames_create), built on first
+    use and kept for the following EM iterations; None when they do not apply / do not fit."""
+    if self.resident is None or self._prepared_failed or self.n == 0:
+      return None
+    if self._prepared is None:
+      lib = _lib.load()
+      h = _lib.C.c_void_p()
+      rc = lib.odin_gmm_frames_create(gmm_handle, _lib.ptr(self.resident), self.n, _lib.C.byref(h),
+                                      _lib.current_stream())
+      if rc < 0:
+        self._prepared_failed = True   # ODIN_ENOMEM / unsupported D: fall back to odin_gmm_estep
+        return None
+      self._prepared = h
+    return self._prepared
+
+  def __del__(self):
+    try:
+      if self._prepared is not None:
+        _lib.load().odin_gmm_frames_destroy(self._prepared)
+        self._prepared = None
+    except Exception:
+      pass
 
   def cache_on_device(self, reserve_bytes=2 << 30):
     """Upload once if it fits (used by fit(): EM re-reads the data every iteration)."""
@@ -402,10 +429,18 @@ class GMM(object):
         d_mask = mask.to(device="cuda", dtype=torch.uint8).contiguous()
       else:
         d_mask = torch.from_numpy(np.ascontiguousarray(mask)).cuda()
-    for dev, s, e in frames.chunks():
-      sad_ptr = None if d_mask is None else _lib.C.c_void_p(d_mask.data_ptr() + s)
-      _lib.check(lib.odin_gmm_estep(self._handle, _lib.ptr(dev), sad_ptr, e - s, 1 if second else 0,
-                                    _lib.ptr(stats), self.impl, _lib.current_stream()))
+    prep = None
+    if self.impl in (0, 3) and self._curr_nmix >= 256 and self._feat_dim % 4 == 0 and self._feat_dim <= 60 \
+        and os.environ.get("ODIN_H_NO_PREPARED", "0") != "1":
+      prep = frames.prepared(self._handle) if frames.reuse else None
+    if prep is not None:
+      _lib.check(lib.odin_gmm_estep_frames(self._handle, prep, _lib.ptr(d_mask), 1 if second else 0,
+                                           _lib.ptr(stats), _lib.current_stream()))
+    else:
+      for dev, s, e in frames.chunks():
+        sad_ptr = None if d_mask is None else _lib.C.c_void_p(d_mask.data_ptr() + s)
+        _lib.check(lib.odin_gmm_estep(self._handle, _lib.ptr(dev), sad_ptr, e - s, 1 if second else 0,
+                                      _lib.ptr(stats), self.impl, _lib.current_stream()))
     sharding.allreduce_stats(stats)  # gmm_tmat.py:249-265 -> one NCCL all-reduce per EM iteration
     return stats
 
@@ -424,6 +459,7 @@ class GMM(object):
     """gmm_tmat.py:1043-1231 -> Z [1,M], F [D,M], S [D,M], L (mean log-likelihood)."""
     X, indices = self.initialize(X)
     frames = X if isinstance(X, _DeviceFrames) else _DeviceFrames(X)
+    frames.reuse = frames.reuse or isinstance(X, _DeviceFrames)
     if sad is not None:
       assert sad.shape[0] == frames.n, \
           "Number of samples for X and sad mismatch X.shape=%s and sad.shape=%s" % ((frames.n, frames.dim), sad.shape)
@@ -463,6 +499,7 @@ class GMM(object):
     """gmm_tmat.py:1278-1306."""
     X, indices = self.initialize(X)
     frames = X if isinstance(X, _DeviceFrames) else _DeviceFrames(X)
+    frames.reuse = frames.reuse or isinstance(X, _DeviceFrames)
     curr_nmix = self._curr_nmix
     mask = self._selected_mask(frames.n, sad, indices)
     stats = self._estep_device(frames, mask, True)
@@ -523,6 +560,7 @@ class GMM(object):
     self.initialize(data)
     frames = _DeviceFrames(data)
     frames.cache_on_device()
+    frames.reuse = True
     arg = frames if indices is None else (frames, indices)
     niter = list(_NITER_SCHEDULE)
     niter[int(np.log2(self._nmix))] = self._niter

@@ -123,3 +123,30 @@ def test_h_linearity_large():
   Zb, Fb, Sb, Lb = gm.expectation(X[N // 2:])
   assert relmax(Za + Zb, Z) < 1e-5 and relmax(Fa + Fb, F) < 1e-5 and relmax(Sa + Sb, S) < 1e-5
   assert abs(Z.sum() - N) < 1e-4 * N
+
+
+def test_h_prepared_frames_equal_per_call_images(monkeypatch):
+  """odin_gmm_estep_frames (operand images of resident frames built once, reused across EM
+  iterations) must give the statistics of odin_gmm_estep(impl 3) (to fp64 round-off), with and without a
+  SAD mask, and after the model changed (the images depend on the data only)."""
+  import torch
+  D, M, N = 60, 512, 70001
+  X = torch.from_numpy(synth.gmm_features(N, D, 32, seed=41)).cuda()
+  mean, sigma, w = synth.gmm_params(D, M, seed=42)
+  rng = np.random.RandomState(4)
+  sad = (rng.rand(N) > 0.3).astype(np.uint8)
+  from odin_b200.ml.gmm import _DeviceFrames
+  frames = _DeviceFrames(X)
+  g = _gmm(M, mean, sigma, w, 3)
+  for mask in (None, sad):
+    a = g.expectation(frames, sad=mask)
+    assert frames._prepared is not None
+    monkeypatch.setenv("ODIN_H_NO_PREPARED", "1")
+    b = g.expectation(X, sad=mask)
+    monkeypatch.delenv("ODIN_H_NO_PREPARED")
+    for u, v in zip(a, b):   # same operands and tiles; only the order of the fp64 atomic adds may differ
+      assert relmax(np.asarray(u), np.asarray(v)) < 1e-12
+  g.mean, g.sigma, g.w = mean * 1.01, sigma * 1.1, w
+  Z, F, S, L = g.expectation(frames)
+  z, f, s, l, n = OG.expectation(X.cpu().numpy(), g.mean, g.sigma, g.w, compute_dtype=np.float64)
+  assert max(relmax(Z, z), relmax(F, f), relmax(S, s)) < TIGHT
