@@ -268,8 +268,14 @@ def mfcc_leg(torch, args, rank, world, dist, peaks, do_cpu):
       "kernel_ms": {"dc": float(kms[0]), "frame": float(kms[1]), "post": float(kms[2]), "vad": float(kms[3])},
       "roofline": {"bound": "hbm", "achieved": bytes_per_frame * T / frame_kernel_s / 1e9, "peak": peaks["hbm_gbs"],
                    "unit": "GB/s", "frac": bytes_per_frame * T / frame_kernel_s / 1e9 / peaks["hbm_gbs"],
-                   "traffic": None, "kernel": "fe_frame_kernel", "peak_source": peaks["source"],
-                   "note": "algorithmic 885 B/frame; the kernel is FP32/shared-memory bound (SURVEY 8d), see DESIGN.md"},
+                   "traffic": 60.24e6 / 154696 * T, "kernel": "fe_frame4_kernel", "peak_source": peaks["source"],
+                   "note": "algorithmic 885 B/frame; traffic from profiles/r01_fe_frame4_ncu_full_keymetrics.csv (49.6 MB read + 10.6 MB written per 154 696-frame launch: the utterance pass writes the rest); the kernel is issue / FP32 bound (SURVEY 8d), see roofline_fp32 and DESIGN.md"},
+      # the binding resource is the SM, not HBM: algorithmic 35 kFLOP per frame against the
+      # FP32 pipe peak 148 SM x 128 lanes x 2 x max SM clock
+      "roofline_fp32": {"bound": "fp32", "achieved": 35.0e3 * T / frame_kernel_s / 1e12,
+                        "peak": 148 * 128 * 2 * 1.965e9 / 1e12, "unit": "TFLOP/s",
+                        "frac": 35.0e3 * T / frame_kernel_s / (148 * 128 * 2 * 1.965e9),
+                        "kernel": "fe_frame4_kernel", "peak_source": "nominal: 148 SMs x 128 FP32 lanes x 2 x 1.965 GHz"},
       "e2e": {"value": total_T / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d * world,
               "d2h_bytes_per_step": d2h * world},
   }
