@@ -127,6 +127,16 @@ int odin_fe_compact(odin_fe_t* fe, const uint8_t* d_sad, const int64_t* h_frame_
                     const float* d_feat, int32_t dim, int32_t keep_unvoiced, float* d_out,
                     int64_t* d_out_offsets, void* stream);
 
+/* AcousticNorm (speech.py:1536-1610) over a ragged batch: mean_var_norm -> signal.mvn(varnorm =
+ * var_norm) (signal.py:853-876), then windowed -> signal.wmvn(w = win_length, varnorm = False)
+ * (signal.py:878-924), statistics restricted to frames with d_sad != 0 when d_sad is given
+ * (an empty selection yields NaN, as numpy's mean of an empty slice does).
+ * d_x, d_y: [T, dim] float32 (dim <= 256); h_frame_offsets [n_utt+1] HOST; d_y may alias d_x only
+ * when windowed == 0.  The host copy of the offsets is consumed before the call returns. */
+int odin_fe_cmvn(const float* d_x, float* d_y, int32_t dim, const int64_t* h_frame_offsets, int32_t n_utt,
+                 const uint8_t* d_sad, int32_t mean_var_norm, int32_t var_norm, int32_t windowed,
+                 int32_t win_length, void* stream);
+
 /* ------------------------------------------------------------------------- */
 /* GMM-UBM: odin/ml/gmm_tmat.py                                               */
 /* ------------------------------------------------------------------------- */

@@ -52,6 +52,7 @@ SIGNATURES = {
     "odin_fe_get_table": (C.c_int, [_vp, _i32, C.POINTER(C.c_double), _i64]),
     "odin_fe_run": (C.c_int, [_vp, _vp, _i32, _pi64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "odin_fe_compact": (C.c_int, [_vp, _vp, _pi64, _i32, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "odin_fe_cmvn": (C.c_int, [_vp, _vp, _i32, _pi64, _i32, _vp, _i32, _i32, _i32, _i32, _vp]),
     "odin_gmm_create": (C.c_int, [_i32, _i32, C.POINTER(_vp)]),
     "odin_gmm_destroy": (None, [_vp]),
     "odin_gmm_stats_size": (_i64, [_vp, _i32]),

@@ -360,6 +360,27 @@ int odin_fe_compact(odin_fe_t* fe, const uint8_t* d_sad, const int64_t* h_frame_
   return fe_compact_launch(fe, d_sad, n_utt, d_feat, dim, keep_unvoiced, d_out, d_out_offsets, st);
 }
 
+int odin_fe_cmvn(const float* d_x, float* d_y, int32_t dim, const int64_t* h_frame_offsets, int32_t n_utt,
+                 const uint8_t* d_sad, int32_t mean_var_norm, int32_t var_norm, int32_t windowed, int32_t win_length,
+                 void* stream) {
+  if (!d_x || !d_y || !h_frame_offsets || dim <= 0 || dim > 256 || n_utt < 0)
+    return set_error(ODIN_EINVAL, "bad argument (dim must be 1..256)");
+  if (d_x == d_y && windowed) return set_error(ODIN_EINVAL, "windowed normalisation cannot run in place");
+  if (windowed && (win_length < 3 || (win_length & 1) == 0))
+    return set_error(ODIN_EINVAL, "Window length should be an odd integer >= 3");   // signal.py:896-897
+  int rc = require_device();
+  if (rc) return rc;
+  if (n_utt == 0) return ODIN_OK;
+  cudaStream_t st = as_stream(stream);
+  int64_t* d_off = nullptr;
+  ODIN_CUDA_CHECK(cudaMallocAsync(&d_off, sizeof(int64_t) * (n_utt + 1), st));
+  cudaError_t e = cudaMemcpyAsync(d_off, h_frame_offsets, sizeof(int64_t) * (n_utt + 1), cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) { cudaFreeAsync(d_off, st); return set_error(ODIN_ECUDA, "cudaMemcpyAsync: %s", cudaGetErrorString(e)); }
+  rc = fe_cmvn_launch(d_x, d_y, dim, d_off, n_utt, d_sad, mean_var_norm, var_norm, windowed, win_length, st);
+  cudaFreeAsync(d_off, st);
+  return rc;
+}
+
 // --------------------------------- GMM --------------------------------------
 int odin_gmm_create(int32_t feat_dim, int32_t max_nmix, odin_gmm_t** out) {
   if (!out || feat_dim <= 0 || feat_dim > 127 || max_nmix <= 0 || max_nmix > 65536)

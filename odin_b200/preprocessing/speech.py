@@ -263,11 +263,95 @@ class ApplyingSAD(Extractor):
 _WINDOWS = {'hann': 0, 'hanning': 0, 'hamm': 1, 'hamming': 1}
 
 
+class AcousticNorm(Extractor):
+  """speech.py:1536-1610: mean-variance normalisation (`signal.mvn`) followed by windowed mean
+  normalisation (`signal.wmvn(varnorm=False)`), optionally on SAD-selected statistics.  Runs on the
+  GPU (`odin_fe_cmvn`): `transform_batch` normalises a whole list of utterances with one launch per
+  feature.  Outputs are float32 (the reference keeps the input dtype, float64 in its chains)."""
+
+  def __init__(self, input_name, output_name=None, mean_var_norm=True, windowed_mean_var_norm=False,
+               win_length=301, var_norm=True, sad_name=None, ignore_sad_error=True):
+    self.sad_name = str(sad_name) if isinstance(sad_name, str) else None
+    self.ignore_sad_error = bool(ignore_sad_error)
+    super(AcousticNorm, self).__init__(input_name=as_tuple(input_name, t=str), output_name=output_name)
+    self.mean_var_norm = bool(mean_var_norm)
+    self.windowed_mean_var_norm = bool(windowed_mean_var_norm)
+    self.var_norm = bool(var_norm)
+    win_length = int(win_length)
+    if win_length % 2 == 0:
+      raise ValueError("win_length must be odd number")
+    if win_length < 3:
+      raise ValueError("win_length must >= 3")
+    self.win_length = win_length
+
+  def _transform(self, feat):
+    raise NotImplementedError  # transform / transform_batch below do the work
+
+  def transform(self, X):
+    return self.transform_batch([X])[0]
+
+  def transform_batch(self, Xs):
+    _lib.require_cuda()
+    import torch
+    lib = _lib.load()
+    results = list(Xs)
+    live = []
+    for i, X in enumerate(Xs):
+      sig = self._check_input(X)
+      if sig is not None:
+        results[i] = sig
+      else:
+        live.append(i)
+    if not live:
+      return results
+    outs = {i: {} for i in live}
+    for name in self.input_name:
+      mats, sads, use = [], [], []
+      for i in live:
+        x = np.asarray(Xs[i][name])
+        if x.ndim != 2:
+          raise ValueError("AcousticNorm expects [time, feature] matrices, %r has shape %s" % (name, x.shape))
+        sad = None
+        if self.sad_name is not None:
+          sad = np.asarray(Xs[i][self.sad_name]).astype(bool).reshape(-1)
+          if len(sad) != len(x):
+            if not self.ignore_sad_error:
+              raise RuntimeError("Features with name: '%s' have length %d, but given SAD has length %d" %
+                                 (name, len(x), len(sad)))
+            sad = None
+        mats.append(np.ascontiguousarray(x, dtype=np.float32))
+        sads.append(sad)
+        use.append(i)
+      # one launch per (has a usable SAD mask, feature width) group
+      groups = {}
+      for k in range(len(use)):
+        groups.setdefault((sads[k] is not None, mats[k].shape[1]), []).append(k)
+      for (with_sad, dim), idx in sorted(groups.items()):
+        off = np.zeros(len(idx) + 1, dtype=np.int64)
+        np.cumsum([mats[k].shape[0] for k in idx], out=off[1:])
+        d_x = torch.from_numpy(np.concatenate([mats[k] for k in idx], 0)).cuda()
+        d_y = torch.empty_like(d_x)
+        d_sad = torch.from_numpy(np.concatenate([sads[k] for k in idx]).astype(np.uint8)).cuda() if with_sad else None
+        _lib.check(lib.odin_fe_cmvn(_lib.ptr(d_x), _lib.ptr(d_y), dim, _lib.as_i64_ptr(off), len(idx),
+                                    _lib.ptr(d_sad), 1 if self.mean_var_norm else 0, 1 if self.var_norm else 0,
+                                    1 if self.windowed_mean_var_norm else 0, self.win_length,
+                                    _lib.current_stream()))
+        y = d_y.cpu().numpy()
+        for j, k in enumerate(idx):
+          outs[use[k]][name] = y[off[j]:off[j + 1]].copy()
+    out_names = as_tuple(self.output_name, t=str) if self.output_name is not None else self.input_name
+    for i in live:
+      y = {on: outs[i][n] for n, on in zip(self.input_name, out_names)}
+      results[i] = self._merge_output(Xs[i], y)
+    return results
+
+
 class FusedSpeechFrontEnd(Extractor):
   """The CUDA step standing in for a run of speech extractors (see module doc)."""
 
-  def __init__(self, reader, preemph, stft, power, mels, mfcc, delta, sad, apply_sad):
+  def __init__(self, reader, preemph, stft, power, mels, mfcc, delta, sad, apply_sad, alias=None):
     super(FusedSpeechFrontEnd, self).__init__(is_input_layer=reader is not None)
+    self.alias = dict(alias or {})   # feature renames deferred past this step (plan_fusion)
     self.reader, self.preemph, self.stft, self.power = reader, preemph, stft, power
     self.mels, self.mfcc, self.delta, self.sad, self.apply_sad = mels, mfcc, delta, sad, apply_sad
     self._handles = {}
@@ -298,12 +382,13 @@ class FusedSpeechFrontEnd(Extractor):
       if dl.order not in ((0,), (0, 1), (0, 1, 2)):
         raise NotImplementedError("DeltaExtractor order must be (0,), (0,1) or (0,1,2)")
     if sd is not None:
+      sd_in = self.alias.get(sd.input_name, sd.input_name)
       if isinstance(sd, SADgmm):
-        if sd.input_name != '%s_energy' % st.output_name or not st.energy:
+        if sd_in != '%s_energy' % st.output_name or not st.energy:
           raise NotImplementedError("SADgmm is accelerated on the STFT frame energy ('%s_energy')" %
                                     st.output_name)
       else:
-        if mf is None or not mf.first_coef_energy or sd.input_name != '%s_energy' % mf.output_name:
+        if mf is None or not mf.first_coef_energy or sd_in != '%s_energy' % mf.output_name:
           raise NotImplementedError("SADthreshold is accelerated on the first cepstral coefficient "
                                     "('<mfcc>_energy', MFCCsExtractor(first_coef_energy=True))")
     if ap is not None and (sd is None or ap.sad_name != sd.output_name):
@@ -509,41 +594,77 @@ class FusedSpeechFrontEnd(Extractor):
 
 
 def plan_fusion(extractors):
-  """Groups a flat list of extractors into execution steps, fusing the speech run."""
+  """Groups a flat list of extractors into execution steps, fusing the speech run.
+
+  Bookkeeping extractors that recipes interleave with the speech steps (Converter, RenameFeatures,
+  DuplicateFeatures -- e.g. examples/fsdd_ivec.py:83-98 renames `mfcc_energy` to `energy` right
+  before SADthreshold) do not break the run: they are deferred to just after the fused step, in
+  their original order, and a rename is taken into account when the SAD input name is resolved."""
+  from .base import Converter, RenameFeatures, DuplicateFeatures
   plan, i, n = [], 0, len(extractors)
   speech_types = (PreEmphasis, STFTExtractor, PowerSpecExtractor, MelsSpecExtractor, MFCCsExtractor,
                   SADgmm, SADthreshold, ApplyingSAD)
+  transparent = (Converter, RenameFeatures, DuplicateFeatures)
   while i < n:
     e = extractors[i]
     j = i
     reader = preemph = None
-    if isinstance(extractors[j], AudioReader) and j + 1 < n and \
-        isinstance(extractors[j + 1], (PreEmphasis, STFTExtractor)):
-      reader = extractors[j]
-      j += 1
+    deferred, alias = [], {}
+
+    def skip(j):
+      while j < n and isinstance(extractors[j], transparent):
+        t = extractors[j]
+        if isinstance(t, RenameFeatures):
+          for a, b in zip(t.input_name, t.output_name):
+            alias[b] = alias.get(a, a)
+        elif isinstance(t, DuplicateFeatures):
+          for a, b in zip(t.input_name, t.output_name):
+            alias[b] = alias.get(a, a)
+        deferred.append(t)
+        j += 1
+      return j
+
+    if isinstance(extractors[j], AudioReader):
+      k = skip(j + 1)
+      if k < n and isinstance(extractors[k], (PreEmphasis, STFTExtractor)):
+        reader = extractors[j]
+        j = k
+      else:
+        deferred, alias = [], {}
     if j < n and isinstance(extractors[j], PreEmphasis):
-      preemph = extractors[j]
-      j += 1
+      k = skip(j + 1)
+      if k < n and isinstance(extractors[k], STFTExtractor):
+        preemph = extractors[j]
+        j = k
     if j + 2 < n and isinstance(extractors[j], STFTExtractor) and \
         isinstance(extractors[j + 1], PowerSpecExtractor) and isinstance(extractors[j + 2], MelsSpecExtractor):
       stft, power, mels = extractors[j:j + 3]
       j += 3
       mfcc = delta = sad = apply_sad = None
-      if j < n and isinstance(extractors[j], MFCCsExtractor):
-        mfcc = extractors[j]
-        j += 1
+      k = skip(j)
+      if k < n and isinstance(extractors[k], MFCCsExtractor):
+        mfcc = extractors[k]
+        j = k + 1
       # Delta and SAD may come in either order
       for _ in range(2):
-        if j < n and delta is None and mfcc is not None and isinstance(extractors[j], DeltaExtractor):
-          delta = extractors[j]
-          j += 1
-        elif j < n and sad is None and isinstance(extractors[j], (SADgmm, SADthreshold)):
-          sad = extractors[j]
-          j += 1
-      if j < n and sad is not None and isinstance(extractors[j], ApplyingSAD):
-        apply_sad = extractors[j]
-        j += 1
-      plan.append(FusedSpeechFrontEnd(reader, preemph, stft, power, mels, mfcc, delta, sad, apply_sad))
+        k = skip(j)
+        if k < n and delta is None and mfcc is not None and isinstance(extractors[k], DeltaExtractor):
+          delta = extractors[k]
+          j = k + 1
+        elif k < n and sad is None and isinstance(extractors[k], (SADgmm, SADthreshold)):
+          sad = extractors[k]
+          j = k + 1
+      k = skip(j)
+      if k < n and sad is not None and isinstance(extractors[k], ApplyingSAD):
+        apply_sad = extractors[k]
+        j = k + 1
+      # transparent steps collected past the last fused extractor stay where they are
+      n_after = sum(1 for t in extractors[j:k] if isinstance(t, transparent)) if k > j else 0
+      if n_after:
+        deferred = deferred[:len(deferred) - n_after]
+      plan.append(FusedSpeechFrontEnd(reader, preemph, stft, power, mels, mfcc, delta, sad, apply_sad,
+                                      alias=dict(alias)))
+      plan.extend(deferred)
       i = j
       continue
     if isinstance(e, speech_types) or isinstance(e, DeltaExtractor):

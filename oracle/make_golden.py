@@ -163,8 +163,43 @@ def gmm_fixtures():
   print("wrote gmm_fit_d12_m8.npz")
 
 
+def cmvn_fixtures():
+  """AcousticNorm (speech.py:1536-1610) of the REAL reference on the MFCC / log-mel fixtures."""
+  pp, _ = ref_shim.load_frontend()
+  sp = pp.speech
+  blob = {}
+  k = 0
+  for name in ("cfg1", "cfg5"):
+    g = np.load(os.path.join(OUT, "fe_%s.npz" % name))
+    for i in range(int(g["n_utt"])):
+      feat = {"mfcc": g["u%d_mfcc" % i].astype(np.float64), "mspec": g["u%d_mspec" % i].astype(np.float64),
+              "sad": g["u%d_sad_gmm" % i].astype(bool)}
+      for tag, kw in (("mvn", dict(mean_var_norm=True, windowed_mean_var_norm=False)),
+                      ("mvn_novar", dict(mean_var_norm=True, windowed_mean_var_norm=False, var_norm=False)),
+                      ("wmvn", dict(mean_var_norm=True, windowed_mean_var_norm=True, win_length=51)),
+                      ("wonly", dict(mean_var_norm=False, windowed_mean_var_norm=True, win_length=31)),
+                      ("recipe", dict(mean_var_norm=True, windowed_mean_var_norm=True, win_length=301)),
+                      ("wmvn_sad", dict(mean_var_norm=True, windowed_mean_var_norm=True, win_length=51,
+                                        sad_name="sad"))):
+        e = sp.AcousticNorm(input_name=("mspec", "mfcc"), **kw)
+        out = e.transform(dict(feat))
+        blob["c%d_%s_mfcc" % (k, tag)] = np.asarray(out["mfcc"])
+        blob["c%d_%s_mspec" % (k, tag)] = np.asarray(out["mspec"])
+      blob["c%d_in_mfcc" % k] = feat["mfcc"]
+      blob["c%d_in_mspec" % k] = feat["mspec"]
+      blob["c%d_sad" % k] = feat["sad"]
+      k += 1
+  blob["n_case"] = np.array(k)
+  np.savez_compressed(os.path.join(OUT, "cmvn.npz"), **blob)
+  print("wrote cmvn.npz (%d cases)" % k)
+
+
 if __name__ == "__main__":
   warnings.filterwarnings("ignore")
   os.makedirs(OUT, exist_ok=True)
-  frontend_fixtures()
-  gmm_fixtures()
+  if len(sys.argv) > 1 and sys.argv[1] == "cmvn":
+    cmvn_fixtures()
+  else:
+    frontend_fixtures()
+    gmm_fixtures()
+    cmvn_fixtures()

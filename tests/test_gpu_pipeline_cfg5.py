@@ -78,3 +78,41 @@ def test_fsdd_style_pipeline(tmp_path):
   s0, e0 = indices["mfcc"][names[0]]
   z0, f0 = OG.transform(X[s0:e0], g.mean, g.sigma, g.w, compute_dtype=np.float64)
   assert relmax(Fu[0].reshape(M, 60), np.asarray(f0).reshape(M, 60)) < 1e-3
+
+
+def test_fsdd_recipe_with_normalisation_tail():
+  """The complete extractor list of examples/fsdd_ivec.py:80-106 (Converter / Rename / Delete /
+  AcousticNorm(mvn + wmvn) / AsType('float16') included) through make_pipeline, against the oracle."""
+  from odin_b200 import preprocessing as pp
+  cfg = FE_CONFIGS["cfg5"]
+  sr = cfg["sr"]
+  utts = synth.utterance_batch(10, 0.3, 2.2, sr=sr, seed=777)     # up to 2.2 s so that w = 301 slides (5 ms hop)
+  jobs = [{"raw": u, "sr": sr, "path": "/data/fsdd/%d_jackson_%d.wav" % (i % 10, i)} for i, u in enumerate(utts)]
+  pipe = pp.make_pipeline([
+      pp.AudioReader(remove_dc=True), pp.PreEmphasis(coeff=0.97),
+      pp.Converter(converter=lambda x: os.path.basename(x).split('.')[0], input_name='path', output_name='name'),
+      pp.STFTExtractor(frame_length=0.025, step_length=0.005, n_fft=512, window='hamm', energy=False),
+      pp.PowerSpecExtractor(power=2.0, output_name='spec'),
+      pp.MelsSpecExtractor(n_mels=24, fmin=64, fmax=4000, input_name=('spec', 'sr'), output_name='mspec'),
+      pp.MFCCsExtractor(n_ceps=20, remove_first_coef=True, first_coef_energy=True, input_name='mspec',
+                        output_name='mfcc'),
+      pp.DeltaExtractor(input_name='mfcc', order=(0, 1, 2)),
+      pp.RenameFeatures(input_name='mfcc_energy', output_name='energy'),
+      pp.SADthreshold(energy_threshold=0.55, smooth_window=5, input_name='energy', output_name='sad'),
+      pp.DeleteFeatures(input_name=('stft', 'spec', 'sad_threshold')),
+      pp.AcousticNorm(mean_var_norm=True, windowed_mean_var_norm=True, input_name=('mspec', 'mfcc')),
+      pp.AsType(dtype='float16')])
+  outs = pipe.transform_batch(jobs)
+  slid = 0
+  for j, u, o in zip(jobs, utts, outs):
+    r = F.extract(u, sr, 0.025, 0.005, 512, n_mels=24, fmin=64, fmax=4000, n_ceps=20, vad="threshold", vad_smooth=5)
+    assert o["name"] == os.path.basename(j["path"]).split('.')[0]
+    assert "stft" not in o and "spec" not in o and "sad_threshold" not in o
+    assert np.array_equal(np.asarray(o["sad"]).astype(np.uint8), r["sad"].astype(np.uint8))
+    for f in ("mspec", "mfcc"):
+      want = F.acoustic_norm(r[f], mean_var_norm=True, windowed_mean_var_norm=True, win_length=301)
+      assert o[f].dtype == np.float16 and o[f].shape == want.shape
+      # float16 storage: 2^-11 relative on top of the 1e-4 feature tolerance
+      assert np.max(np.abs(o[f].astype(np.float64) - want)) <= 1e-3 * max(1.0, float(np.max(np.abs(want))))
+    slid += int(r["mfcc"].shape[0] >= 301)
+  assert slid >= 3, "the test must exercise the sliding window"

@@ -206,3 +206,36 @@ def test_gmm_host_surface():
   m = g._selected_mask(200000, None, None)
   assert 0 < int(m.sum()) < 200000 and m[:1].dtype == np.uint8
   assert np.array_equal(m, g._selected_mask(200000, None, None))             # seeded => reproducible
+
+
+def test_fusion_plan_of_the_fsdd_recipe():
+  """examples/fsdd_ivec.py:80-106 interleaves Converter / RenameFeatures with the speech steps: the
+  run must still fuse, the bookkeeping steps are deferred behind the fused step in order, and the
+  renamed SAD input (`mfcc_energy` -> `energy`) is resolved."""
+  pipe = pp.make_pipeline([
+      pp.AudioReader(remove_dc=True), pp.PreEmphasis(coeff=0.97),
+      pp.Converter(converter=lambda x: os.path.basename(x).split('.')[0], input_name='path', output_name='name'),
+      pp.STFTExtractor(frame_length=0.025, step_length=0.005, n_fft=512, window='hamm', energy=False),
+      pp.PowerSpecExtractor(power=2.0, output_name='spec'),
+      pp.MelsSpecExtractor(n_mels=24, fmin=64, fmax=4000, input_name=('spec', 'sr'), output_name='mspec'),
+      pp.MFCCsExtractor(n_ceps=20, remove_first_coef=True, first_coef_energy=True, input_name='mspec',
+                        output_name='mfcc'),
+      pp.DeltaExtractor(input_name='mfcc', order=(0, 1, 2)),
+      pp.RenameFeatures(input_name='mfcc_energy', output_name='energy'),
+      pp.SADthreshold(energy_threshold=0.55, smooth_window=5, input_name='energy', output_name='sad'),
+      pp.DeleteFeatures(input_name=('stft', 'spec', 'sad_threshold')),
+      pp.AcousticNorm(mean_var_norm=True, windowed_mean_var_norm=True, input_name=('mspec', 'mfcc')),
+      pp.AsType(dtype='float16')])
+  assert [type(e).__name__ for e in pipe.plan] == ['FusedSpeechFrontEnd', 'Converter', 'RenameFeatures',
+                                                   'DeleteFeatures', 'AcousticNorm', 'AsType']
+  fused = pipe.plan[0]
+  assert fused.alias == {'energy': 'mfcc_energy'} and fused.sad is not None and fused.delta is not None
+  assert len(pipe.steps) == 13                                   # the user-visible step list is untouched
+  # a SAD on a feature the front-end does not produce is still refused
+  with pytest.raises(NotImplementedError):
+    pp.make_pipeline([pp.AudioReader(), pp.STFTExtractor(0.025, 0.01), pp.PowerSpecExtractor(),
+                      pp.MelsSpecExtractor(24), pp.MFCCsExtractor(20, first_coef_energy=True),
+                      pp.RenameFeatures('mspec', 'energy'), pp.SADthreshold(input_name='energy')])
+  # AcousticNorm argument checks (speech.py:1571-1579)
+  with pytest.raises(ValueError):
+    pp.AcousticNorm('mfcc', win_length=300)

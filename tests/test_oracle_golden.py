@@ -142,3 +142,27 @@ def test_minibatch_and_batch_size():
   assert OG.minibatch_ranges(10, 4) == [(0, 4), (4, 8), (8, 10)]
   assert OG.default_batch_size(60, 64) == 52428
   assert OG.default_batch_size(60, 2048) == 13107     # / floor(2^2)
+
+
+CMVN_TAGS = {
+    "mvn": dict(),
+    "mvn_novar": dict(var_norm=False),
+    "wmvn": dict(windowed_mean_var_norm=True, win_length=51),
+    "wonly": dict(mean_var_norm=False, windowed_mean_var_norm=True, win_length=31),
+    "recipe": dict(windowed_mean_var_norm=True, win_length=301),
+    "wmvn_sad": dict(windowed_mean_var_norm=True, win_length=51),
+}
+
+
+def test_cmvn_golden():
+  """oracle.acoustic_norm against AcousticNorm of the real reference (tests/golden/cmvn.npz)."""
+  g = np.load(os.path.join(GOLDEN, "cmvn.npz"))
+  for k in range(int(g["n_case"])):
+    for tag, kw in CMVN_TAGS.items():
+      for f in ("mfcc", "mspec"):
+        sad = g["c%d_sad" % k] if tag == "wmvn_sad" else None
+        y = F.acoustic_norm(g["c%d_in_%s" % (k, f)], sad=sad, **kw)
+        r = g["c%d_%s_%s" % (k, tag, f)]
+        assert np.array_equal(np.isnan(y), np.isnan(r))
+        ok = np.isfinite(r)
+        assert np.max(np.abs(y[ok] - r[ok])) < 1e-12
