@@ -180,11 +180,12 @@ int fe_reserve(odin_fe* fe, int n_utt) {
   };
   freeall();
   size_t n1 = (size_t)cap + 1;
-  ODIN_CUDA_CHECK(cudaMallocHost(&fe->h_stage, 4 * n1 * sizeof(int64_t)));
-  ODIN_CUDA_CHECK(cudaMalloc(&fe->d_sample_off, 4 * n1 * sizeof(int64_t)));
+  ODIN_CUDA_CHECK(cudaMallocHost(&fe->h_stage, 5 * n1 * sizeof(int64_t)));
+  ODIN_CUDA_CHECK(cudaMalloc(&fe->d_sample_off, 5 * n1 * sizeof(int64_t)));
   fe->d_frame_off = fe->d_sample_off + n1;
   fe->d_tile_off = fe->d_frame_off + n1;
   fe->d_tile2_off = fe->d_tile_off + n1;
+  fe->d_vad_order = fe->d_tile2_off + n1;
   ODIN_CUDA_CHECK(cudaMalloc(&fe->d_dcsum, n1 * sizeof(double)));
   ODIN_CUDA_CHECK(cudaMalloc(&fe->d_umax, n1 * sizeof(int)));
   ODIN_CUDA_CHECK(cudaMalloc(&fe->d_cnt, n1 * sizeof(int64_t)));
@@ -338,7 +339,21 @@ int odin_fe_run(odin_fe_t* fe, const void* d_pcm, int32_t pcm_dtype, const int64
     t2[u + 1] = t2[u] + ceil_div<int64_t>(T, ODIN_FE_POST_TILE);
   }
   if (t1[n_utt] > 0x7fffffff) return set_error(ODIN_EINVAL, "batch too large (tiles)");
-  ODIN_CUDA_CHECK(cudaMemcpyAsync(fe->d_sample_off, fe->h_stage, 4 * n1 * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  {
+    // Order in which the SADgmm kernel visits utterances (one CTA / cluster each, all resident at once,
+    // first wave placed round-robin over the SMs): the S longest ascending, then the rest descending, so
+    // the SMs that receive a second utterance pair a short one of the first group with a long one of the
+    // second and the longest utterances of the batch sit alone -- the kernel lasts as long as its most
+    // loaded SM.
+    int64_t* ord = t2 + n1;
+    std::vector<int> idx(n_utt);
+    for (int u = 0; u < n_utt; ++u) idx[u] = u;
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return fo[a + 1] - fo[a] > fo[b + 1] - fo[b]; });
+    const int S = std::min(n_utt, sm_count());
+    for (int i = 0; i < S; ++i) ord[i] = idx[S - 1 - i];
+    for (int i = S; i < n_utt; ++i) ord[i] = idx[i];
+  }
+  ODIN_CUDA_CHECK(cudaMemcpyAsync(fe->d_sample_off, fe->h_stage, 5 * n1 * sizeof(int64_t), cudaMemcpyHostToDevice, st));
   return fe_launch(fe, d_pcm, pcm_dtype, n_utt, fo[n_utt], t1[n_utt], t2[n_utt], d_mspec, d_feat, d_energy, d_c0,
                    d_sad, d_sad_thr, st);
 }

@@ -27,11 +27,12 @@ struct odin_fe {
   int mel_nnz = 0;
   // per-run scratch (capacity in utterances)
   int cap_utt = 0;
-  int64_t* h_stage = nullptr;  // pinned [4*(cap+1)]: sample_off, frame_off, tile_off, tile2_off
+  int64_t* h_stage = nullptr;  // pinned [5*(cap+1)]: sample_off, frame_off, tile_off, tile2_off, vad order
   int64_t* d_sample_off = nullptr;
   int64_t* d_frame_off = nullptr;
   int64_t* d_tile_off = nullptr;
   int64_t* d_tile2_off = nullptr;
+  int64_t* d_vad_order = nullptr;  // [cap] utterance visiting order of the SADgmm kernel
   double* d_dcsum = nullptr;   // [cap] (int64 bit pattern for int16 input)
   int* d_umax = nullptr;       // [cap] ordered-int encoded utterance max of log-mel dB
   int64_t* d_cnt = nullptr;    // [cap+1] compaction counts / offsets

@@ -718,6 +718,7 @@ __global__ void __launch_bounds__(256) fe_post_kernel(PostArgs a) {
 // VAD: one warp per utterance
 // ---------------------------------------------------------------------------
 struct VadArgs {
+  const int64_t* order;   // SADgmm: utterance visited by cluster i (nullable = identity)
   const int64_t* frame_off;
   int n_utt;
   const float* x;   // energy [T] (SADgmm) or c0 [T] (SADthreshold)
@@ -899,6 +900,16 @@ __device__ bool vad_em(const float* __restrict__ x, int n, int nc, int max_iter,
     double acc[VAD_NRED];
 #pragma unroll
     for (int k = 0; k < VAD_NRED; ++k) acc[k] = 0.0;
+    // The per-frame work is ~all fp64 transcendental code, so it is trimmed to what the sums need:
+    //  * exp(wl[k] - max) of the maximal component is exactly 1: with three components the two other
+    //    differences are picked with selects and only TWO exponentials are evaluated;
+    //  * log(s) only feeds the running sum of log-likelihoods: the s of a thread's frames are
+    //    multiplied (s in [1, nc], <= a few dozen frames per thread and iteration) and ONE log is
+    //    taken at the end;
+    //  * the responsibilities exp(wl - norm) are formed as exp(wl - max) / s.
+    // Each step differs from sklearn's expression by <= 1 ulp of a double.
+    double sprod = 1.0;
+    int nprod = 0;
     for (int i = gt; i < n; i += gstride) {
       const float xf = x[i];
       if (!isfinite(xf)) acc[VAD_NRED - 1] += 1.0;
@@ -910,13 +921,22 @@ __device__ bool vad_em(const float* __restrict__ x, int n, int nc, int max_iter,
         wl[k] = dadd(lp, lw[k]);
         mx = fmax(mx, wl[k]);
       }
-      // responsibilities exp(wl - norm) = exp(wl - mx) / s: the exponentials of the log-sum-exp are
-      // reused instead of evaluated a second time (differs from sklearn's exp(wl - norm) by <= 1 ulp)
       double ek[KMAX], s = 0.0;
-      for (int k = 0; k < nc; ++k) { ek[k] = exp(wl[k] - mx); s += ek[k]; }
-      const double norm = mx + log(s);
+      if (nc == 3) {
+        const bool am = wl[0] == mx, bm = wl[1] == mx, cm = wl[2] == mx;
+        const double dA = wl[0] - mx, dB = wl[1] - mx, dC = wl[2] - mx;
+        const double e1 = exp(am ? dB : dA), e2 = exp(cm ? dB : dC);
+        ek[0] = am ? 1.0 : e1;
+        ek[2] = cm ? 1.0 : e2;
+        ek[1] = bm ? 1.0 : (am ? e1 : e2);
+        s = (ek[0] + ek[1]) + ek[2];
+      } else {
+        for (int k = 0; k < nc; ++k) { ek[k] = exp(wl[k] - mx); s += ek[k]; }
+      }
       const double inv = 1.0 / s;
-      acc[0] += norm;
+      acc[0] += mx;
+      sprod *= s;
+      if (++nprod == 256) { acc[0] += log(sprod); sprod = 1.0; nprod = 0; }   // nc^256 stays finite
       for (int k = 0; k < nc; ++k) {
         const double r = ek[k] * inv;
         acc[1 + k] += r;
@@ -924,6 +944,7 @@ __device__ bool vad_em(const float* __restrict__ x, int n, int nc, int max_iter,
         acc[1 + 2 * KMAX + k] = fma(r, x2, acc[1 + 2 * KMAX + k]);
       }
     }
+    acc[0] += log(sprod);
     vad_cluster_reduce(acc, sh, cl);
     if (acc[VAD_NRED - 1] != 0.0) return false;   // sklearn rejects non-finite input
     double nk[KMAX], nksum = 0.0;
@@ -957,7 +978,8 @@ __global__ void __launch_bounds__(VAD_THREADS, 2) fe_vad_gmm_kernel(VadArgs a) {
   const int ncta = (int)cl.num_blocks();       // cluster size, chosen per launch (1, 2, 4 or 8)
   const int gstride = ncta * VAD_THREADS;
   const int n_clusters = gridDim.x / ncta;
-  for (int u = blockIdx.x / ncta; u < a.n_utt; u += n_clusters) {
+  for (int ci = blockIdx.x / ncta; ci < a.n_utt; ci += n_clusters) {
+    const int u = a.order ? (int)a.order[ci] : ci;
     const int64_t base = a.frame_off[u];
     const int n = (int)(a.frame_off[u + 1] - base);
     if (n <= 0) continue;
@@ -1234,6 +1256,7 @@ int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t 
     {
       VadArgs v{};
       v.frame_off = fe->d_frame_off; v.n_utt = n_utt; v.sad = d_sad; v.thr_out = d_sad_thr;
+      v.order = fe->d_vad_order;
       v.nmix = c.vad_nmix; v.iters = c.vad_iters; v.smooth = c.vad_smooth; v.mode = (double)c.vad_mode;
       v.thr_energy = (double)c.thr_energy; v.thr_mean_scale = (double)c.thr_mean_scale;
       v.thr_proportion = (double)c.thr_proportion; v.thr_context = c.thr_context;

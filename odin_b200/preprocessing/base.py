@@ -252,32 +252,32 @@ class DuplicateFeatures(Extractor):
 
 
 class RenameFeatures(Extractor):
-  """base.py:690-710."""
+  """base.py:675-700: renames only the features that exist; anything that is not a Mapping
+  (an ExtractorSignal, None) passes through untouched."""
 
   def __init__(self, input_name, output_name):
     super(RenameFeatures, self).__init__(input_name=as_tuple(input_name, t=str),
                                          output_name=as_tuple(output_name, t=str))
 
   def transform(self, X):
-    sig = self._check_input(X)
-    if sig is not None:
-      return sig
+    if not isinstance(X, Mapping):
+      return X
     X = dict(X)
     for inp, out in zip(self.input_name, self.output_name):
-      X[out] = X.pop(inp)
+      if inp in X:
+        X[out] = X.pop(inp)
     return X
 
 
 class DeleteFeatures(Extractor):
-  """base.py:713-721."""
+  """base.py:703-720: removes the named features that exist."""
 
   def __init__(self, input_name):
     super(DeleteFeatures, self).__init__(input_name=as_tuple(input_name, t=str))
 
   def transform(self, X):
-    sig = self._check_input(X)
-    if sig is not None:
-      return sig
+    if not isinstance(X, Mapping):
+      return X
     return {k: v for k, v in X.items() if k not in self.input_name}
 
 

@@ -86,7 +86,8 @@ def test_fsdd_recipe_with_normalisation_tail():
   from odin_b200 import preprocessing as pp
   cfg = FE_CONFIGS["cfg5"]
   sr = cfg["sr"]
-  utts = synth.utterance_batch(10, 0.3, 2.2, sr=sr, seed=777)     # up to 2.2 s so that w = 301 slides (5 ms hop)
+  utts = synth.utterance_batch(5, 0.3, 1.0, sr=sr, seed=777) + \
+      synth.utterance_batch(5, 1.7, 2.4, sr=sr, seed=778)          # > 1.53 s: w = 301 slides at a 5 ms hop
   jobs = [{"raw": u, "sr": sr, "path": "/data/fsdd/%d_jackson_%d.wav" % (i % 10, i)} for i, u in enumerate(utts)]
   pipe = pp.make_pipeline([
       pp.AudioReader(remove_dc=True), pp.PreEmphasis(coeff=0.97),
