@@ -349,7 +349,8 @@ int odin_fe_run(odin_fe_t* fe, const void* d_pcm, int32_t pcm_dtype, const int64
     std::vector<int> idx(n_utt);
     for (int u = 0; u < n_utt; ++u) idx[u] = u;
     std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return fo[a + 1] - fo[a] > fo[b + 1] - fo[b]; });
-    const int S = std::min(n_utt, sm_count());
+    const char* lpt = getenv("ODIN_FE_VAD_LPT");   // A/B runs: plain longest-first order
+    const int S = (lpt && lpt[0] == '1') ? 0 : std::min(n_utt, sm_count());
     for (int i = 0; i < S; ++i) ord[i] = idx[S - 1 - i];
     for (int i = S; i < n_utt; ++i) ord[i] = idx[i];
   }

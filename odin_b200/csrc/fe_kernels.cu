@@ -1277,6 +1277,10 @@ int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t 
         // at once (2 CTAs of 256 threads per SM)
         int ncta = 1;
         while (ncta < VAD_CL_MAX && (int64_t)n_utt * (ncta * 2) <= (int64_t)sm_count() * 2) ncta *= 2;
+        if (const char* ev = getenv("ODIN_FE_VAD_NCTA")) {   // A/B runs
+          const int v2 = atoi(ev);
+          if (v2 == 1 || v2 == 2 || v2 == 4 || v2 == 8) ncta = v2;
+        }
         const int64_t n_cl = std::min<int64_t>(n_utt, (int64_t)sm_count() * 4);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)(n_cl * ncta));
