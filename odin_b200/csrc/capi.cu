@@ -340,17 +340,15 @@ int odin_fe_run(odin_fe_t* fe, const void* d_pcm, int32_t pcm_dtype, const int64
   }
   if (t1[n_utt] > 0x7fffffff) return set_error(ODIN_EINVAL, "batch too large (tiles)");
   {
-    // Order in which the SADgmm kernel visits utterances (one CTA / cluster each, all resident at once,
-    // first wave placed round-robin over the SMs): the S longest ascending, then the rest descending, so
-    // the SMs that receive a second utterance pair a short one of the first group with a long one of the
-    // second and the longest utterances of the batch sit alone -- the kernel lasts as long as its most
-    // loaded SM.
+    // Order in which the SADgmm kernel visits utterances (one cluster each): longest first, so the
+    // hardware's in-order dispatch of clusters to freed SMs is longest-processing-time-first list scheduling
+    // (ODIN_FE_VAD_LPT=0 restores the earlier static pairing of long with short utterances for A/B runs).
     int64_t* ord = t2 + n1;
     std::vector<int> idx(n_utt);
     for (int u = 0; u < n_utt; ++u) idx[u] = u;
     std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return fo[a + 1] - fo[a] > fo[b + 1] - fo[b]; });
-    const char* lpt = getenv("ODIN_FE_VAD_LPT");   // A/B runs: plain longest-first order
-    const int S = (lpt && lpt[0] == '1') ? 0 : std::min(n_utt, sm_count());
+    const char* lpt = getenv("ODIN_FE_VAD_LPT");
+    const int S = (lpt && lpt[0] == '0') ? std::min(n_utt, sm_count()) : 0;
     for (int i = 0; i < S; ++i) ord[i] = idx[S - 1 - i];
     for (int i = S; i < n_utt; ++i) ord[i] = idx[i];
   }

@@ -431,8 +431,14 @@ __global__ void __launch_bounds__(FE_THREADS, 2) fe_frame4_kernel(FrameArgs a) {
   const PCM* __restrict__ pcm = reinterpret_cast<const PCM*>(a.pcm);
   const float coef = a.preemph;
 
-  for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-    const int u = find_segment(a.tile_off, a.n_utt, tile);
+  // contiguous range of tiles per CTA: one binary search, then the utterance index walks forward
+  const int64_t per = (a.n_tiles + gridDim.x - 1) / gridDim.x;
+  const int64_t tile_lo = per * blockIdx.x, tile_hi = min(a.n_tiles, tile_lo + per);
+  if (tile_lo >= tile_hi) return;
+  int u = find_segment(a.tile_off, a.n_utt, tile_lo);
+  int64_t u_end = a.tile_off[u + 1];
+  for (int64_t tile = tile_lo; tile < tile_hi; ++tile) {
+    while (tile >= u_end) { ++u; u_end = a.tile_off[u + 1]; }
     const int64_t s0 = a.sample_off[u];
     const int64_t n_u = a.sample_off[u + 1] - s0;
     const int64_t fbase = a.frame_off[u];
@@ -598,6 +604,7 @@ struct PostArgs {
   int n_utt;
   const int* umax;
   float top_db;
+  int64_t n_tiles;
   int n_mels, n_c1, n_ceps, W, order;
   const float* dct;   // [n_c1, n_mels]
   const float* taps;  // [W]
@@ -607,23 +614,64 @@ struct PostArgs {
   float* c0;          // [T] nullable
 };
 
-__global__ void __launch_bounds__(256) fe_post_kernel(PostArgs a) {
+// Division of small non-negative ints by a runtime constant: q = umulhi(n, M), M = floor((2^32-1)/d) + 1
+// (exact while n*d < 2^32; d == 1 wraps M to 0, which is the pass-through flag).
+__device__ __forceinline__ uint32_t fdiv_magic(int d) { return 0xFFFFFFFFu / (uint32_t)d + 1u; }
+__device__ __forceinline__ int fdiv(int n, uint32_t M) { return M ? (int)__umulhi((uint32_t)n, M) : n; }
+
+// Four consecutive outputs of a W-tap causal FIR down a strided column: out[j] = sum_k taps[k] x[(j + W-1 - k) * stride],
+// k ascending from a zero accumulator (the order of the one-row loops), the W + 3 inputs read once.
+template <int W>
+__device__ __forceinline__ void fir4(const float* __restrict__ x, int stride, const float* __restrict__ taps,
+                                     float (&out)[4]) {
+  float v[W + 3], tp[W];
+#pragma unroll
+  for (int q = 0; q < W + 3; ++q) v[q] = x[q * stride];
+#pragma unroll
+  for (int k = 0; k < W; ++k) tp[k] = taps[k];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < W; ++k) acc = fmaf(tp[k], v[j + W - 1 - k], acc);
+    out[j] = acc;
+  }
+}
+
+// Utterance pass.  Issue-bound (ncu: 72 % of issue slots at 728 warp-instructions per frame in its first
+// version), so the work is arranged to cost few instructions: runtime divisors go through fdiv, the DCT is
+// register-blocked 2 rows x 8 coefficients with the basis transposed and zero-padded to a multiple of 8
+// (two broadcast 16-byte loads per mel), rows of a thread are half a tile apart so lanes walk distinct banks.
+__global__ void __launch_bounds__(256, 3) fe_post_kernel(PostArgs a) {
   extern __shared__ __align__(16) float sm[];
   const int tid = threadIdx.x;
   const int h = a.W / 2;
   const int HL = (a.order >= 2) ? (a.W - 1 + h) : (a.order == 1 ? h : 0);
   const int HR = (a.order >= 1) ? h : 0;
   const int NR = PT + HL + HR;             // rows of mel / cepstra held
-  const int ND = PT + ((a.order >= 2) ? a.W - 1 : 0);  // rows of first-order deltas held
   const int MS = a.n_mels | 1;              // odd row stride: lanes walking rows hit distinct banks
-  float* smel = sm;                         // [NR][MS]
-  float* scep = smel + NR * MS;             // [NR][n_c1]
-  float* sd1 = scep + NR * a.n_c1;          // [ND][n_ceps]
-  float* sdct = sd1 + ND * a.n_ceps;        // [n_c1][n_mels]
-  float* staps = sdct + a.n_c1 * a.n_mels;  // [W]
+  const int C8 = (a.n_c1 + 7) & ~7;         // coefficients padded to whole groups of 8
+  float* sdct = sm;                         // [n_mels][C8]  transposed basis, 16-byte aligned rows
+  float* staps = sdct + a.n_mels * C8;      // [W] (+ pad to 4)
+  float* scep = staps + ((a.W + 3) & ~3);   // [NR][n_c1]
+  float* smel = scep + NR * a.n_c1;         // [NR][MS]
+  float* sd1 = smel;                        // [ND][n_ceps] first-order deltas: the mel rows are dead by then
+  const uint32_t mg_c8 = fdiv_magic(C8), mg_ceps = fdiv_magic(max(a.n_ceps, 1));
 
-  const int64_t tile = blockIdx.x;
-  const int u = find_segment(a.tile2_off, a.n_utt, tile);
+  // persistent CTA over a contiguous range of tiles: the tables are filled once and the utterance of a
+  // tile is found by walking forward from the previous one (one binary search per CTA)
+  for (int i = tid; i < a.n_mels * C8; i += 256) {
+    const int m = fdiv(i, mg_c8), c = i - m * C8;
+    sdct[i] = (c < a.n_c1) ? a.dct[c * a.n_mels + m] : 0.f;
+  }
+  for (int i = tid; i < a.W; i += 256) staps[i] = a.taps[i];
+  const int64_t per = (a.n_tiles + gridDim.x - 1) / gridDim.x;
+  const int64_t tile_lo = per * blockIdx.x, tile_hi = min(a.n_tiles, tile_lo + per);
+  if (tile_lo >= tile_hi) return;
+  int u = find_segment(a.tile2_off, a.n_utt, tile_lo);
+  int64_t u_end = a.tile2_off[u + 1];
+  for (int64_t tile = tile_lo; tile < tile_hi; ++tile) {
+  while (tile >= u_end) { ++u; u_end = a.tile2_off[u + 1]; }   // utterances shorter than a frame own no tile
   const int64_t base = a.frame_off[u];
   const int T = (int)(a.frame_off[u + 1] - base);
   const int t0 = (int)(tile - a.tile2_off[u]) * PT;
@@ -631,87 +679,167 @@ __global__ void __launch_bounds__(256) fe_post_kernel(PostArgs a) {
   const int lo = max(0, t0 - HL), hi = min(T, t0 + nf + HR);
   const int nrows = hi - lo;
   const float floor_db = (a.top_db >= 0.f) ? ordered_to_float(a.umax[u]) - a.top_db : -FLT_MAX;
-
-  for (int i = tid; i < a.n_c1 * a.n_mels; i += 256) sdct[i] = a.dct[i];
-  for (int i = tid; i < a.W; i += 256) staps[i] = a.taps[i];
-  for (int i = tid; i < nrows * a.n_mels; i += 256) {
-    const int r = i / a.n_mels, m = i - r * a.n_mels;
-    const int64_t g = (base + lo) * a.n_mels + i;
-    float v = fmaxf(a.mspec[g], floor_db);
-    smel[r * MS + m] = v;
-    const int t = lo + r;
-    if (a.write_mspec && t >= t0 && t < t0 + nf) a.mspec[g] = v;
-  }
-  __syncthreads();
-  if (a.n_ceps <= 0) return;
-  // DCT (signal.py:1711): cep[r][c] = sum_m dct[c][m] * mel[r][m].  One work item = one row x
-  // a group of CG coefficients: the mel value is read once per CG FMAs and the DCT entries are
-  // warp-wide broadcasts (lanes of a warp share the coefficient group).
+  __syncthreads();   // the previous tile is done with smel / scep / sd1 (and the table fill on the first trip)
   {
-    constexpr int CG = 8;
-    const int ncg = (a.n_c1 + CG - 1) / CG;
-    for (int i = tid; i < nrows * ncg; i += 256) {
-      const int g = i / nrows, r = i - g * nrows;
-      const int c0i = g * CG;
-      const float* mrow = smel + r * MS;
-      float acc[CG];
+    float* g0 = a.mspec + (base + lo) * a.n_mels;
+    if ((a.n_mels & 3) == 0 && (reinterpret_cast<uintptr_t>(a.mspec) & 15) == 0) {
+      const int nq = a.n_mels >> 2;
+      const uint32_t mg_nq = fdiv_magic(nq);
+      float4* g4 = reinterpret_cast<float4*>(g0);
+      // the rows are read and (clipped) written back through the same pointer, so the loads of a batch
+      // are issued before its stores by hand: 4 x 16 B in flight per thread
+      const int n4 = nrows * nq;
+      for (int i0 = tid; i0 < n4; i0 += 4 * 256) {
+        float4 vv[4];
 #pragma unroll
-      for (int j = 0; j < CG; ++j) acc[j] = 0.f;
-      for (int m = 0; m < a.n_mels; ++m) {
-        const float x = mrow[m];
-#pragma unroll
-        for (int j = 0; j < CG; ++j)
-          if (c0i + j < a.n_c1) acc[j] = fmaf(sdct[(c0i + j) * a.n_mels + m], x, acc[j]);
-      }
-      const int t = lo + r;
-#pragma unroll
-      for (int j = 0; j < CG; ++j)
-        if (c0i + j < a.n_c1) scep[r * a.n_c1 + c0i + j] = acc[j];
-      if (g == 0 && a.c0 != nullptr && t >= t0 && t < t0 + nf) a.c0[base + t] = acc[0];
-    }
-  }
-  __syncthreads();
-  if (a.feat == nullptr) return;
-  const int fd = a.n_ceps * (a.order + 1);
-  // first-order deltas D(u) for u in [ulo, t0+nf)
-  const int ulo = t0 - ((a.order >= 2) ? a.W - 1 : 0);
-  if (a.order >= 1) {
-    const int nd = t0 + nf - ulo;
-    for (int i = tid; i < nd * a.n_ceps; i += 256) {
-      const int r = i / a.n_ceps, c = i - r * a.n_ceps;
-      const int uu = ulo + r;
-      float acc = 0.f;
-      if (uu >= -(h + 1)) {
-        for (int k = 0; k < a.W; ++k) {
-          int t = min(max(uu + h - k, 0), T - 1);
-          acc = fmaf(staps[k], scep[(t - lo) * a.n_c1 + 1 + c], acc);
+        for (int k = 0; k < 4; ++k) {
+          const int i = i0 + k * 256;
+          vv[k] = (i < n4) ? g4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-      } else {  // zero initial state of the causal filter
-        const int j = uu + 2 * a.W - h - 1;
-        float ts = 0.f;
-        for (int k = 0; k <= j; ++k) ts += staps[k];
-        acc = ts * scep[(0 - lo) * a.n_c1 + 1 + c];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = i0 + k * 256;
+          if (i < n4) {
+            const int r = fdiv(i, mg_nq), q = i - r * nq;
+            float4 v = vv[k];
+            const bool clip = fminf(fminf(v.x, v.y), fminf(v.z, v.w)) < floor_db;
+            v.x = fmaxf(v.x, floor_db); v.y = fmaxf(v.y, floor_db);
+            v.z = fmaxf(v.z, floor_db); v.w = fmaxf(v.w, floor_db);
+            float* d = smel + r * MS + 4 * q;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            const int t = lo + r;
+            if (clip && a.write_mspec && t >= t0 && t < t0 + nf) g4[i] = v;   // unclipped rows are already final
+          }
+        }
       }
-      sd1[i] = acc;
+    } else {
+      const uint32_t mg_m = fdiv_magic(a.n_mels);
+      for (int i = tid; i < nrows * a.n_mels; i += 256) {
+        const int r = fdiv(i, mg_m), m = i - r * a.n_mels;
+        const float v = fmaxf(g0[i], floor_db);
+        smel[r * MS + m] = v;
+        const int t = lo + r;
+        if (a.write_mspec && t >= t0 && t < t0 + nf) g0[i] = v;
+      }
     }
   }
   __syncthreads();
-  for (int i = tid; i < nf * fd; i += 256) {
-    const int r = i / fd, j = i - r * fd;
-    const int t = t0 + r;
-    const int o = j / a.n_ceps, c = j - o * a.n_ceps;
-    float v;
-    if (o == 0) {
-      v = scep[(t - lo) * a.n_c1 + 1 + c];
-    } else if (o == 1) {
-      v = sd1[(t - ulo) * a.n_ceps + c];
-    } else {
-      float acc = 0.f;
-      for (int k = 0; k < a.W; ++k) acc = fmaf(staps[k], sd1[(t - k - ulo) * a.n_ceps + c], acc);
-      v = acc;
+  if (a.n_ceps <= 0) continue;
+  // DCT (signal.py:1711): cep[r][c] = sum_m dct[c][m] * mel[r][m], m ascending from a zero accumulator.
+  {
+    const int half = (nrows + 1) >> 1;
+    const int ncg = C8 >> 3;
+    const uint32_t mg_half = fdiv_magic(half);
+    for (int i = tid; i < half * ncg; i += 256) {
+      const int g = fdiv(i, mg_half), r0 = i - g * half;
+      const bool two = r0 + half < nrows;
+      const int r1 = two ? r0 + half : r0;
+      const float* m0 = smel + r0 * MS;
+      const float* m1 = smel + r1 * MS;
+      const float4* dq = reinterpret_cast<const float4*>(sdct + 8 * g);
+      const int dstride = C8 >> 2;
+      float acc0[8], acc1[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc0[j] = acc1[j] = 0.f;
+#pragma unroll 4
+      for (int m = 0; m < a.n_mels; ++m) {
+        const float x0 = m0[m], x1 = m1[m];
+        const float4 da = dq[m * dstride], db = dq[m * dstride + 1];
+        const float dv[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc0[j] = fmaf(dv[j], x0, acc0[j]);
+          acc1[j] = fmaf(dv[j], x1, acc1[j]);
+        }
+      }
+      const int c0i = 8 * g;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (c0i + j < a.n_c1) {
+          scep[r0 * a.n_c1 + c0i + j] = acc0[j];
+          if (two) scep[r1 * a.n_c1 + c0i + j] = acc1[j];
+        }
+      if (g == 0 && a.c0 != nullptr) {
+        const int ta = lo + r0, tb = lo + r1;
+        if (ta >= t0 && ta < t0 + nf) a.c0[base + ta] = acc0[0];
+        if (two && tb >= t0 && tb < t0 + nf) a.c0[base + tb] = acc1[0];
+      }
     }
-    a.feat[(base + t) * fd + j] = v;
   }
+  __syncthreads();   // scep complete; smel may now be overwritten by sd1
+  if (a.feat == nullptr) continue;
+  const int fd = a.n_ceps * (a.order + 1);
+  // first-order deltas D(u) for u in [ulo, t0+nf); a thread takes four consecutive rows of one coefficient
+  // so that the W + 3 inputs are read once (fir4, W == 9); rows that touch an utterance edge go one by one
+  const int ulo = t0 - ((a.order >= 2) ? a.W - 1 : 0);
+  const int nd = t0 + nf - ulo;
+  float* sd2 = sd1 + nd * a.n_ceps;   // [nf][n_ceps] second-order deltas
+  if (a.order >= 1) {
+    const int ng = (nd + 3) >> 2;
+    for (int i = tid; i < ng * a.n_ceps; i += 256) {
+      const int rg = fdiv(i, mg_ceps), c = i - rg * a.n_ceps;
+      const int r0 = 4 * rg, uu0 = ulo + r0;
+      if (a.W == 9 && r0 + 3 < nd && uu0 - h >= 0 && uu0 + 3 + h <= T - 1) {
+        float o4[4];
+        fir4<9>(scep + (uu0 - h - lo) * a.n_c1 + 1 + c, a.n_c1, staps, o4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sd1[(r0 + j) * a.n_ceps + c] = o4[j];
+        continue;
+      }
+      for (int r = r0; r < min(r0 + 4, nd); ++r) {
+        const int uu = ulo + r;
+        float acc = 0.f;
+        if (uu - h >= 0 && uu + h <= T - 1) {   // interior: no clamping
+          const float* p = scep + (uu + h - lo) * a.n_c1 + 1 + c;
+          for (int k = 0; k < a.W; ++k) acc = fmaf(staps[k], p[-k * a.n_c1], acc);
+        } else if (uu >= -(h + 1)) {
+          for (int k = 0; k < a.W; ++k) {
+            int t = min(max(uu + h - k, 0), T - 1);
+            acc = fmaf(staps[k], scep[(t - lo) * a.n_c1 + 1 + c], acc);
+          }
+        } else {  // zero initial state of the causal filter
+          const int j = uu + 2 * a.W - h - 1;
+          float ts = 0.f;
+          for (int k = 0; k <= j; ++k) ts += staps[k];
+          acc = ts * scep[(0 - lo) * a.n_c1 + 1 + c];
+        }
+        sd1[r * a.n_ceps + c] = acc;
+      }
+    }
+  }
+  if (a.order >= 2) {
+    __syncthreads();
+    // second-order deltas: DD(t) = sum_k taps[k] D(t - k), every input row is held (no edges)
+    const int ng = (nf + 3) >> 2;
+    for (int i = tid; i < ng * a.n_ceps; i += 256) {
+      const int rg = fdiv(i, mg_ceps), c = i - rg * a.n_ceps;
+      const int r0 = 4 * rg;   // row t = t0 + r0, its D row index is t - ulo = r0 + W - 1
+      if (a.W == 9 && r0 + 3 < nf) {
+        float o4[4];
+        fir4<9>(sd1 + r0 * a.n_ceps + c, a.n_ceps, staps, o4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sd2[(r0 + j) * a.n_ceps + c] = o4[j];
+        continue;
+      }
+      for (int r = r0; r < min(r0 + 4, nf); ++r) {
+        float acc = 0.f;
+        const float* p = sd1 + (r + a.W - 1) * a.n_ceps + c;
+        for (int k = 0; k < a.W; ++k) acc = fmaf(staps[k], p[-k * a.n_ceps], acc);
+        sd2[r * a.n_ceps + c] = acc;
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t mg_fd = fdiv_magic(fd);
+  float* fout = a.feat + (base + t0) * fd;
+  for (int i = tid; i < nf * fd; i += 256) {
+    const int r = fdiv(i, mg_fd), j = i - r * fd;
+    const int o = fdiv(j, mg_ceps), c = j - o * a.n_ceps;
+    const float* src = (o == 0) ? scep + (t0 + r - lo) * a.n_c1 + 1 + c
+                                : (o == 1 ? sd1 + (t0 + r - ulo) * a.n_ceps + c : sd2 + r * a.n_ceps + c);
+    fout[i] = *src;
+  }
+  }  // tile loop
 }
 
 // ---------------------------------------------------------------------------
@@ -735,7 +863,7 @@ __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a,
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
 
 // SADgmm: one thread-block CLUSTER of 1..8 CTAs per utterance (sized per launch so that the
-// clusters of a batch roughly fill the GPU: few long utterances get 8 CTAs each, hundreds get 1).
+// clusters of a batch roughly fill the GPU: few long utterances get 8 CTAs each, thousands get 1).
 //
 // The 1-D EM of sklearn's GaussianMixture is ~350 fp64 instructions per frame and iteration, so a
 // minute-long utterance on one SM is bound by that SM's fp64 pipe (the batch's longest utterance set
@@ -1275,8 +1403,12 @@ int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t 
         v.x = d_energy;
         // cluster size: the largest power of two such that all clusters of the batch are resident
         // at once (2 CTAs of 256 threads per SM)
+        // cluster size: the largest power of two that keeps the batch within ~3 CTAs per SM (2 are
+        // resident at once; measured on the config-3 shard, 216 utterances: 1 -> 0.82 ms, 2 -> 0.61,
+        // 4 -> 0.66, 8 -> 1.17); clusters start longest utterance first and the hardware hands the
+        // next one to whichever SMs free up
         int ncta = 1;
-        while (ncta < VAD_CL_MAX && (int64_t)n_utt * (ncta * 2) <= (int64_t)sm_count() * 2) ncta *= 2;
+        while (ncta < VAD_CL_MAX && (int64_t)n_utt * (ncta * 2) <= (int64_t)sm_count() * 3) ncta *= 2;
         if (const char* ev = getenv("ODIN_FE_VAD_NCTA")) {   // A/B runs
           const int v2 = atoi(ev);
           if (v2 == 1 || v2 == 2 || v2 == 4 || v2 == 8) ncta = v2;
@@ -1323,11 +1455,16 @@ int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t 
     const int HL = (c.delta_order >= 2) ? (c.delta_width - 1 + h) : (c.delta_order == 1 ? h : 0);
     const int HR = (c.delta_order >= 1) ? h : 0;
     const int NR = PT + HL + HR, ND = PT + ((c.delta_order >= 2) ? c.delta_width - 1 : 0);
-    size_t smem = sizeof(float) * ((size_t)NR * (fe->n_mels | 1) + (size_t)NR * fe->n_c1 + (size_t)ND * c.n_ceps +
-                                   (size_t)fe->n_c1 * fe->n_mels + c.delta_width + 4);
+    // sd1 ([ND][n_ceps]) and sd2 ([PT][n_ceps]) alias the mel rows
+    const size_t mel_or_d1 = std::max((size_t)NR * (fe->n_mels | 1), (size_t)(ND + PT) * c.n_ceps);
+    size_t smem = sizeof(float) * (mel_or_d1 + (size_t)NR * fe->n_c1 + (size_t)((fe->n_c1 + 7) & ~7) * fe->n_mels +
+                                   ((c.delta_width + 3) & ~3) + 4);
     if (smem > 227 * 1024) return set_error(ODIN_EINVAL, "post kernel needs %zu B smem", smem);
     ODIN_CUDA_CHECK(cudaFuncSetAttribute(fe_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fe_post_kernel<<<(unsigned)n_tiles2, 256, smem, st>>>(p);
+    p.n_tiles = n_tiles2;
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(3, (227 * 1024) / (smem + 1024)));
+    const int64_t pgrid = std::min<int64_t>(n_tiles2, (int64_t)sm_count() * per_sm);
+    fe_post_kernel<<<(unsigned)pgrid, 256, smem, st>>>(p);
     ODIN_LAUNCH_CHECK("fe_post_kernel");
   }
   ODIN_CUDA_CHECK(cudaEventRecord(fe->ev[3], st));
