@@ -135,6 +135,48 @@ int fe_build_tables(odin_fe* fe) {
     for (int k = 0; k < mcnt[i]; ++k) mw.push_back((float)fe->h_mel[(size_t)i * nb + mstart[i] + k]);
   }
   fe->mel_nnz = (int)mw.size();
+  // Lane-balanced form for fe_frame4_kernel.  Filter widths grow with frequency (4 taps at the bottom, ~60 at
+  // the top for n_fft 1024 / 80 mels), so "one filter per lane" makes every warp wait for its widest filter.
+  // Here each filter is cut into chunks of at most ceil(nnz / 32) taps, the chunks are dealt to the 32 lanes
+  // longest-first onto the least loaded lane, and a lane walks its own tap list; at the end of a chunk it
+  // drops the partial sum into the chunk's slot, and filter m adds its slots [ps[m], ps[m+1]) in bin order.
+  std::vector<float2> mtab;
+  std::vector<int> mps(nm + 1, 0);
+  {
+    const int cap = std::max(4, (fe->mel_nnz + 31) / 32);
+    struct Chunk { int m, start, cnt, slot; };
+    std::vector<Chunk> chunks;
+    for (int i = 0; i < nm; ++i) {
+      mps[i] = (int)chunks.size();
+      const int pieces = (mcnt[i] + cap - 1) / cap;
+      for (int p = 0; p < pieces; ++p) {
+        const int b0 = (int)((int64_t)mcnt[i] * p / pieces), b1 = (int)((int64_t)mcnt[i] * (p + 1) / pieces);
+        chunks.push_back({i, mstart[i] + b0, b1 - b0, (int)chunks.size()});
+      }
+    }
+    mps[nm] = (int)chunks.size();
+    std::vector<Chunk> order(chunks);
+    std::stable_sort(order.begin(), order.end(), [](const Chunk& x, const Chunk& y) { return x.cnt > y.cnt; });
+    std::vector<std::vector<float2>> lanes(32);
+    for (const Chunk& ch : order) {
+      int best = 0;
+      for (int l = 1; l < 32; ++l) if (lanes[l].size() < lanes[best].size()) best = l;
+      for (int k = 0; k < ch.cnt; ++k) {
+        const uint32_t meta = (uint32_t)(ch.start + k) | (k == ch.cnt - 1 ? 0x8000u : 0u) | ((uint32_t)ch.slot << 16);
+        float mf;
+        memcpy(&mf, &meta, 4);
+        lanes[best].push_back(make_float2((float)fe->h_mel[(size_t)ch.m * nb + ch.start + k], mf));
+      }
+    }
+    size_t trips = 0;
+    for (int l = 0; l < 32; ++l) trips = std::max(trips, lanes[l].size());
+    mtab.assign(std::max<size_t>(1, trips) * 32, make_float2(0.f, 0.f));   // padding: weight 0, bin 0, no flush
+    for (int l = 0; l < 32; ++l)
+      for (size_t t = 0; t < lanes[l].size(); ++t) mtab[t * 32 + l] = lanes[l][t];
+    fe->mel_trips = (int)trips;
+    fe->mel_chunks = (int)chunks.size();
+    if (nb > 0x7fff || chunks.size() > 0xffff) return set_error(ODIN_EINVAL, "filterbank too large for the packed table");
+  }
   // DCT-II orthonormal rows (signal.py:682-733)
   const int nc1 = fe->n_c1;
   fe->h_dct.assign((size_t)std::max(1, nc1) * nm, 0.0);
@@ -162,6 +204,8 @@ int fe_build_tables(odin_fe* fe) {
   if ((rc = upload(&fe->d_mel_cnt, mcnt))) return rc;
   if ((rc = upload(&fe->d_mel_off, moff))) return rc;
   if ((rc = upload(&fe->d_mel_w, mw))) return rc;
+  if ((rc = upload(&fe->d_mel_tab, mtab))) return rc;
+  if ((rc = upload(&fe->d_mel_ps, mps))) return rc;
   if ((rc = upload(&fe->d_dct, dct32))) return rc;
   if ((rc = upload(&fe->d_taps, taps))) return rc;
   return ODIN_OK;
@@ -246,6 +290,7 @@ void odin_fe_destroy(odin_fe_t* fe) {
   if (!fe) return;
   cudaFree(fe->d_win32); cudaFree(fe->d_win64); cudaFree(fe->d_tw); cudaFree(fe->d_tw4); cudaFree(fe->d_mel_start);
   cudaFree(fe->d_mel_cnt); cudaFree(fe->d_mel_off); cudaFree(fe->d_mel_w); cudaFree(fe->d_dct);
+  cudaFree(fe->d_mel_tab); cudaFree(fe->d_mel_ps);
   cudaFree(fe->d_taps); cudaFree(fe->d_sample_off); cudaFree(fe->d_dcsum); cudaFree(fe->d_umax);
   cudaFree(fe->d_cnt); cudaFree(fe->d_vad_scratch);
   if (fe->h_stage) cudaFreeHost(fe->h_stage);

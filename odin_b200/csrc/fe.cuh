@@ -25,6 +25,10 @@ struct odin_fe {
   float* d_dct = nullptr;      // [n_c1, n_mels]
   float* d_taps = nullptr;     // [delta_width]
   int mel_nnz = 0;
+  // lane-balanced form of the same filterbank for fe_frame4_kernel (see capi.cu: fe_build_tables)
+  float2* d_mel_tab = nullptr; // [mel_trips][32] {weight, bin | flush << 15 | slot << 16}
+  int* d_mel_ps = nullptr;     // [n_mels + 1] partial-sum slots of filter m: [ps[m], ps[m+1])
+  int mel_trips = 0, mel_chunks = 0;
   // per-run scratch (capacity in utterances)
   int cap_utt = 0;
   int64_t* h_stage = nullptr;  // pinned [5*(cap+1)]: sample_off, frame_off, tile_off, tile2_off, vad order

@@ -75,26 +75,33 @@ __device__ __forceinline__ constexpr double w32s(int q) {  // -sin(2 pi q / 32)
        : -0.19509032201612826785;
 }
 
-// in-register forward DFT of size R (power of two <= 32), natural order in/out
-template <int R, typename T> struct Dft {
+// in-register forward DFT of size R (power of two <= 32), natural order in/out.
+// NZ < R declares v[NZ..R) to be zero (a zero-padded frame: L <= n_fft / 2): the even / odd halves inherit
+// the zero tail, and a sub-transform with a single live input is a broadcast, so the leaf butterflies vanish.
+template <int R, typename T, int NZ = R> struct Dft {
   static __device__ __forceinline__ void run(C2<T> (&v)[R]) {
-    C2<T> e[R / 2], o[R / 2];
+    if constexpr (NZ <= 1) {
 #pragma unroll
-    for (int q = 0; q < R / 2; ++q) { e[q] = v[2 * q]; o[q] = v[2 * q + 1]; }
-    Dft<R / 2, T>::run(e);
-    Dft<R / 2, T>::run(o);
+      for (int q = 1; q < R; ++q) v[q] = v[0];
+    } else {
+      C2<T> e[R / 2], o[R / 2];
 #pragma unroll
-    for (int q = 0; q < R / 2; ++q) {
-      C2<T> t;
-      if (q == 0) t = o[q];
-      else if (4 * q == R) t = cmul_negi(o[q]);
-      else t = cmul(o[q], C2<T>{(T)w32c(q * (32 / R)), (T)w32s(q * (32 / R))});
-      v[q] = cadd(e[q], t);
-      v[q + R / 2] = csub(e[q], t);
+      for (int q = 0; q < R / 2; ++q) { e[q] = v[2 * q]; o[q] = v[2 * q + 1]; }
+      Dft<R / 2, T, (NZ + 1) / 2>::run(e);
+      Dft<R / 2, T, NZ / 2>::run(o);
+#pragma unroll
+      for (int q = 0; q < R / 2; ++q) {
+        C2<T> t;
+        if (q == 0) t = o[q];
+        else if (4 * q == R) t = cmul_negi(o[q]);
+        else t = cmul(o[q], C2<T>{(T)w32c(q * (32 / R)), (T)w32s(q * (32 / R))});
+        v[q] = cadd(e[q], t);
+        v[q + R / 2] = csub(e[q], t);
+      }
     }
   }
 };
-template <typename T> struct Dft<1, T> {
+template <typename T, int NZ> struct Dft<1, T, NZ> {
   static __device__ __forceinline__ void run(C2<T> (&)[1]) {}
 };
 
@@ -205,6 +212,9 @@ struct FrameArgs {
   const int* mel_cnt;
   const int* mel_off;
   const float* mel_w;
+  const float2* mel_tab;   // lane-balanced filterbank (fe_frame4_kernel)
+  const int* mel_ps;
+  int mel_trips, mel_chunks;
   int n_mels;
   float scale2;
   float* mspec;   // [T, n_mels] unclipped dB
@@ -401,32 +411,31 @@ __global__ void __launch_bounds__(FE_THREADS) fe_frame_kernel(FrameArgs a) {
 // ---------------------------------------------------------------------------
 template <int N> constexpr int f4_region() { return 32 * (N / 32 + 1); }   // float2 per pair
 
-template <int N, typename PCM>
+template <int N, typename PCM, bool ZH>   // ZH: L <= N / 2, rows r >= 16 of step A are zero padding
 __global__ void __launch_bounds__(FE_THREADS, 2) fe_frame4_kernel(FrameArgs a) {
   using T = float;
   constexpr int G = N / 32, NP = 32 / G, RS = G + 1, REG = f4_region<N>();
   static_assert(REG >= N, "pair region must hold the natural-order spectrum");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: win64 [L] | tw4 [N] | warp bufs [FE_WARPS][NP * REG] | win32 [L] | melw [nnz] |
-  //         mel start/cnt/off [3 n_mels] | sbuf [(FT-1)*hop + L]
+  // layout: win64 [L] | tw4 [N] | warp bufs [FE_WARPS][NP * REG] | mel table [trips][32] float2 | win32 [L] |
+  //         mel slots [n_mels + 1] | sbuf [(FT-1)*hop + L]
   double* win64 = reinterpret_cast<double*>(smem_raw);
   C2<T>* tw4 = reinterpret_cast<C2<T>*>(win64 + a.L + (a.L & 1));
   C2<T>* bufs = tw4 + N;
-  float* win32 = reinterpret_cast<float*>(bufs + FE_WARPS * NP * REG);
-  float* melw = win32 + a.L;
-  int* meli = reinterpret_cast<int*>(melw + a.mel_nnz);
-  float* sbuf = reinterpret_cast<float*>(meli + 3 * a.n_mels);
+  float2* mtab = reinterpret_cast<float2*>(bufs + FE_WARPS * NP * REG);
+  float* win32 = reinterpret_cast<float*>(mtab + a.mel_trips * 32);
+  int* mps = reinterpret_cast<int*>(win32 + a.L);
+  float* sbuf = reinterpret_cast<float*>(mps + a.n_mels + 1);
   __shared__ int cta_max;
+  __shared__ double s_en[FT];   // frame energies of the tile; their logs are taken by one warp at the end
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane / G, l = lane % G;
   const int L = a.L, hop = a.hop;
   for (int i = tid; i < L; i += FE_THREADS) { win64[i] = a.win64[i]; win32[i] = a.win32[i]; }
   for (int i = tid; i < N; i += FE_THREADS) tw4[i] = reinterpret_cast<const C2<T>*>(a.tw)[i];
-  for (int i = tid; i < a.mel_nnz; i += FE_THREADS) melw[i] = a.mel_w[i];
-  for (int i = tid; i < a.n_mels; i += FE_THREADS) {
-    meli[i] = a.mel_start[i]; meli[a.n_mels + i] = a.mel_cnt[i]; meli[2 * a.n_mels + i] = a.mel_off[i];
-  }
+  for (int i = tid; i < a.mel_trips * 32; i += FE_THREADS) mtab[i] = a.mel_tab[i];
+  for (int i = tid; i <= a.n_mels; i += FE_THREADS) mps[i] = a.mel_ps[i];
   C2<T>* wbuf = bufs + warp * (NP * REG);
   const PCM* __restrict__ pcm = reinterpret_cast<const PCM*>(a.pcm);
   const float coef = a.preemph;
@@ -484,7 +493,7 @@ __global__ void __launch_bounds__(FE_THREADS, 2) fe_frame4_kernel(FrameArgs a) {
         for (int r = 0; r < 32; ++r) {
           const int i = l + G * r;
           C2<T> z = {0.f, 0.f};
-          if (i < L && hasA) {
+          if ((!ZH || r < 16) && i < L && hasA) {
             const float xa = sA[i], xb = hasB ? sB[i] : 0.f;
             const double w = win64[i];
             const double wa = w * (double)xa, wb = w * (double)xb;
@@ -502,15 +511,11 @@ __global__ void __launch_bounds__(FE_THREADS, 2) fe_frame4_kernel(FrameArgs a) {
             eB += __shfl_xor_sync(0xffffffffu, eB, o);
           }
           if (l == 0 && hasA) {
-            if (eA == 0.0) eA = (double)FLT_EPSILON;  // signal.py:1436
-            a.energy[fbase + t0 + fA] = (float)log(eA);
-            if (hasB) {
-              if (eB == 0.0) eB = (double)FLT_EPSILON;
-              a.energy[fbase + t0 + fB] = (float)log(eB);
-            }
+            s_en[fA] = eA;
+            if (hasB) s_en[fB] = eB;
           }
         }
-        Dft<32, T>::run(v);
+        Dft<32, T, ZH ? 16 : 32>::run(v);
 #pragma unroll
         for (int k1 = 1; k1 < 32; ++k1) v[k1] = cmul(v[k1], tw4[k1 * G + l]);
         __syncwarp();  // the previous pass' mel stage has finished reading the regions
@@ -568,15 +573,29 @@ __global__ void __launch_bounds__(FE_THREADS, 2) fe_frame4_kernel(FrameArgs a) {
         for (int i = 0; i < NK; ++i) { PA[lane + 32 * i] = pa[i]; PB[lane + 32 * i] = pb[i]; }
         if (lane == 0) { PA[N / 2] = pa[NK]; PB[N / 2] = pb[NK]; }
         __syncwarp();
-        for (int m = lane; m < a.n_mels; m += 32) {
-          const int st = meli[m], cn = meli[a.n_mels + m];
-          const float* __restrict__ w = melw + meli[2 * a.n_mels + m];
+        // lane-balanced sparse projection: every lane walks its own list of (weight, bin) taps and drops a
+        // partial sum into the chunk's slot at the end of each chunk; slots live behind PA | PB in the region
+        T* QA = PB + (N / 2 + 1);
+        T* QB = QA + a.mel_chunks;
+        {
           T accA = 0, accB = 0;
-          for (int i = 0; i < cn; ++i) {
-            const T wi = w[i];
-            accA += wi * PA[st + i];
-            accB += wi * PB[st + i];
+          for (int i = 0; i < a.mel_trips; ++i) {
+            const float2 e = mtab[i * 32 + lane];
+            const uint32_t meta = __float_as_uint(e.y);
+            const int bin = meta & 0x7fff;
+            accA = fmaf(e.x, PA[bin], accA);
+            accB = fmaf(e.x, PB[bin], accB);
+            if (meta & 0x8000u) {
+              QA[meta >> 16] = accA; QB[meta >> 16] = accB;
+              accA = 0; accB = 0;
+            }
           }
+        }
+        __syncwarp();
+        for (int m = lane; m < a.n_mels; m += 32) {
+          const int s0 = mps[m], s1 = mps[m + 1];
+          T accA = 0, accB = 0;
+          for (int i = s0; i < s1; ++i) { accA += QA[i]; accB += QB[i]; }
           const float dA = db10<T>(accA);
           a.mspec[(fbase + t0 + fA) * a.n_mels + m] = dA;
           wmax = fmaxf(wmax, dA);
@@ -592,6 +611,11 @@ __global__ void __launch_bounds__(FE_THREADS, 2) fe_frame4_kernel(FrameArgs a) {
     if (lane == 0) atomicMax(&cta_max, float_to_ordered(wmax));
     __syncthreads();
     if (tid == 0) atomicMax(a.umax + u, cta_max);
+    if (a.energy != nullptr && tid < nf) {
+      double e = s_en[tid];
+      if (e == 0.0) e = (double)FLT_EPSILON;  // signal.py:1436
+      a.energy[fbase + t0 + tid] = (float)log(e);
+    }
   }
 }
 
@@ -876,12 +900,17 @@ constexpr int VAD_WARPS = VAD_THREADS / 32;
 constexpr int VAD_CL_MAX = 8;               // portable cluster size limit
 constexpr int VAD_KMAX = 4;
 constexpr int VAD_NRED = 3 * VAD_KMAX + 2;   // lsum, nk[4], sx[4], sxx[4], #non-finite
+constexpr int VAD_XR = 16;                  // frames per thread staged in shared memory by the EM
 constexpr int VAD_MAXLEAF = 1024;            // leaves of numpy's pairwise sum held in smem (n <~ 58 000 frames)
 
 struct VadShared {
   double red[VAD_WARPS][VAD_NRED];
-  double part[VAD_NRED];
+  double part[2][VAD_CL_MAX][VAD_NRED];   // [parity][source CTA]: every CTA pushes its partials to every CTA
   double tot[VAD_NRED];
+  double par[VAD_KMAX][8];                // per component: prec, a0, b0, ld, lw, mu, pch, w
+  int bad[VAD_KMAX];                      // M-step outcome per component: variance collapsed
+  int parity;
+  float xs[VAD_XR * VAD_THREADS];         // [j][tid]: the j-th frame of thread tid (standardised energies)
   float ms[2];
   int nleaf;
   int leaf_lo[VAD_MAXLEAF];
@@ -889,7 +918,10 @@ struct VadShared {
   float leaf_sum[VAD_MAXLEAF];
 };
 
-// cluster-wide sums of v[0..VAD_NRED): same bits on every thread of every CTA
+// cluster-wide sums of v[0..VAD_NRED) -> sh.tot (same bits in every CTA; visible after the caller's next
+// __syncthreads).  Every CTA pushes its partials into every CTA's shared memory (DSMEM stores), so ONE
+// cluster barrier per reduction is enough; the slots alternate with the call parity, which keeps a fast CTA's
+// next push away from the slots a slow CTA is still reading (it cannot be two reductions ahead).
 __device__ __forceinline__ void vad_cluster_reduce(double (&v)[VAD_NRED], VadShared& sh, cg::cluster_group& cl) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #pragma unroll
@@ -899,29 +931,29 @@ __device__ __forceinline__ void vad_cluster_reduce(double (&v)[VAD_NRED], VadSha
     for (int k = 0; k < VAD_NRED; ++k) sh.red[warp][k] = v[k];
   }
   __syncthreads();
+  const int par = sh.parity;
+  const unsigned nb = cl.num_blocks(), me = cl.block_rank();
   if (tid < VAD_NRED) {
     double t = 0.0;
     for (int wv = 0; wv < VAD_WARPS; ++wv) t += sh.red[wv][tid];
-    sh.part[tid] = t;
+    for (unsigned r = 0; r < nb; ++r) *cl.map_shared_rank(&sh.part[par][me][tid], r) = t;
   }
   cl.sync();
   if (tid < VAD_NRED) {
     double t = 0.0;
-    for (unsigned r = 0; r < cl.num_blocks(); ++r) t += *cl.map_shared_rank(&sh.part[tid], r);
+    for (unsigned r = 0; r < nb; ++r) t += sh.part[par][r][tid];
     sh.tot[tid] = t;
   }
-  cl.sync();  // every CTA has read every part[]; tot[] is visible to the whole CTA
-#pragma unroll
-  for (int k = 0; k < VAD_NRED; ++k) v[k] = sh.tot[k];
+  if (tid == 32) sh.parity = par ^ 1;   // read by everybody before the barrier above, next read after the caller's
 }
 
 // numpy's pairwise float32 sum of f(0..n) (see fe_logic.cuh), block-cooperative and bit-identical:
 // thread 0 lists the <= 128-element leaves of the recursion, 8-lane groups sum one leaf each with the
 // eight strided accumulators of numpy's unrolled loop, thread 0 folds the leaf sums along the same tree.
 template <class F>
-__device__ float block_np_pairwise_sum_f32(F f, int n, VadShared& sh) {
+__device__ float block_np_pairwise_sum_f32(F f, int n, VadShared& sh, bool reuse_leaves = false) {
   const int tid = threadIdx.x;
-  if (tid == 0) {
+  if (tid == 0 && !reuse_leaves) {   // (the table depends on n only)
     int s_lo[40], s_n[40], sp = 0, nl = 0;
     s_lo[0] = 0; s_n[0] = n; sp = 1;
     while (sp > 0 && nl >= 0) {
@@ -1002,28 +1034,50 @@ __device__ float block_np_pairwise_sum_f32(F f, int n, VadShared& sh) {
 
 // 1-D EM of sklearn GaussianMixture with fixed inits (see oracle/frontend.py _em_1d).
 // Returns false where sklearn would raise ValueError.
+//
+// Who computes what: the per-frame E-step is spread over all threads of the cluster (a thread's frames
+// are staged in shared memory across iterations when there are <= VAD_XR of them); the sufficient statistics are
+// reduced in a fixed order (vad_cluster_reduce); the M-step and the derived constants of component k
+// (two fp64 logs, divisions, a square root: ~1 000 instructions when every thread replayed them) are
+// computed by thread k of every CTA and broadcast through shared memory.  All CTAs see identical bits, so
+// the convergence test and the component-drop retry stay uniform across the cluster.
+enum { VP_PREC = 0, VP_A0, VP_B0, VP_LD, VP_LW, VP_MU, VP_PCH, VP_W };
+
+__device__ __forceinline__ void vad_store_params(VadShared& sh, int k, double mu, double pch, double w) {
+  const double prec = dmul(pch, pch);
+  sh.par[k][VP_PREC] = prec;
+  sh.par[k][VP_A0] = dmul(dmul(mu, mu), prec);
+  sh.par[k][VP_B0] = dmul(mu, prec);
+  sh.par[k][VP_LD] = log(pch);
+  sh.par[k][VP_LW] = log(w);
+  sh.par[k][VP_MU] = mu;
+  sh.par[k][VP_PCH] = pch;
+  sh.par[k][VP_W] = w;
+}
+
 __device__ bool vad_em(const float* __restrict__ x, int n, int nc, int max_iter, VadShared& sh, cg::cluster_group& cl,
                        double* mu_out, double* prec_out) {
   constexpr int KMAX = VAD_KMAX;
-  const int gt = (int)cl.block_rank() * VAD_THREADS + threadIdx.x;
+  const int tid = threadIdx.x;
+  const int gt = (int)cl.block_rank() * VAD_THREADS + tid;
   const int gstride = (int)cl.num_blocks() * VAD_THREADS;
   if (n < max(nc, 2)) return false;
-  double w[KMAX], mu[KMAX], pch[KMAX];
-  for (int k = 0; k < nc; ++k) {
-    w[k] = 1.0 / nc;
-    mu[k] = -2.0 + 4.0 * k / (double)(nc - 1);
-    pch[k] = 1.0;
+  const bool staged = n <= VAD_XR * gstride;   // this thread's frames fit its column of sh.xs
+  if (staged) {
+    for (int j = 0, i = gt; i < n; ++j, i += gstride) sh.xs[j * VAD_THREADS + tid] = x[i];
   }
+  if (tid < nc) {
+    vad_store_params(sh, tid, -2.0 + 4.0 * tid / (double)(nc - 1), 1.0, 1.0 / nc);
+    sh.bad[tid] = 0;
+  }
+  __syncthreads();
   const double LOG2PI = 1.8378770664093454835606594728112;
   double lower = -INFINITY;
   for (int it = 0; it < max_iter; ++it) {
     double prec[KMAX], a0[KMAX], b0[KMAX], ld[KMAX], lw[KMAX];
     for (int k = 0; k < nc; ++k) {
-      prec[k] = dmul(pch[k], pch[k]);
-      a0[k] = dmul(dmul(mu[k], mu[k]), prec[k]);
-      b0[k] = dmul(mu[k], prec[k]);
-      ld[k] = log(pch[k]);
-      lw[k] = log(w[k]);
+      prec[k] = sh.par[k][VP_PREC]; a0[k] = sh.par[k][VP_A0]; b0[k] = sh.par[k][VP_B0];
+      ld[k] = sh.par[k][VP_LD]; lw[k] = sh.par[k][VP_LW];
     }
     double acc[VAD_NRED];
 #pragma unroll
@@ -1038,8 +1092,7 @@ __device__ bool vad_em(const float* __restrict__ x, int n, int nc, int max_iter,
     // Each step differs from sklearn's expression by <= 1 ulp of a double.
     double sprod = 1.0;
     int nprod = 0;
-    for (int i = gt; i < n; i += gstride) {
-      const float xf = x[i];
+    auto frame = [&](const float xf) {
       if (!isfinite(xf)) acc[VAD_NRED - 1] += 1.0;
       const double xd = (double)xf, x2 = (double)__fmul_rn(xf, xf);  // x*x is float32 in sklearn
       double wl[KMAX], mx = -INFINITY;
@@ -1071,30 +1124,45 @@ __device__ bool vad_em(const float* __restrict__ x, int n, int nc, int max_iter,
         acc[1 + KMAX + k] = fma(r, xd, acc[1 + KMAX + k]);
         acc[1 + 2 * KMAX + k] = fma(r, x2, acc[1 + 2 * KMAX + k]);
       }
+    };
+    if (staged) {
+      for (int j = 0, i = gt; i < n; ++j, i += gstride) frame(sh.xs[j * VAD_THREADS + tid]);
+    } else {
+      for (int i = gt; i < n; i += gstride) frame(x[i]);
     }
     acc[0] += log(sprod);
     vad_cluster_reduce(acc, sh, cl);
-    if (acc[VAD_NRED - 1] != 0.0) return false;   // sklearn rejects non-finite input
-    double nk[KMAX], nksum = 0.0;
+    // M-step (sklearn _estimate_gaussian_parameters, 1-D): component k by lane k of warp 0 -- the same warp
+    // that wrote sh.tot, so a warp barrier orders the two
+    if (tid < 32) {
+      __syncwarp();
+      if (tid < nc) {
+        double nk[KMAX], nksum = 0.0;
+        for (int k = 0; k < nc; ++k) {
+          nk[k] = sh.tot[1 + k] + 10.0 * DBL_EPSILON;
+          nksum += nk[k];
+        }
+        const int k = tid;
+        const double mu = sh.tot[1 + KMAX + k] / nk[k];
+        const double var = dadd(dadd(sh.tot[1 + 2 * KMAX + k] / nk[k], -dmul(mu, mu)), 1e-6);
+        sh.bad[k] = !(var > 0.0);
+        vad_store_params(sh, k, mu, 1.0 / sqrt(var), nk[k] / nksum);
+      }
+    }
+    __syncthreads();
+    if (sh.tot[VAD_NRED - 1] != 0.0) return false;   // sklearn rejects non-finite input
     bool collapsed = false;
-    for (int k = 0; k < nc; ++k) {
-      nk[k] = acc[1 + k] + 10.0 * DBL_EPSILON;
-      nksum += nk[k];
-    }
-    for (int k = 0; k < nc; ++k) {
-      mu[k] = acc[1 + KMAX + k] / nk[k];
-      const double var = dadd(dadd(acc[1 + 2 * KMAX + k] / nk[k], -dmul(mu[k], mu[k])), 1e-6);
-      if (!(var > 0.0)) collapsed = true;
-      pch[k] = 1.0 / sqrt(var);
-      w[k] = nk[k] / nksum;
-    }
+    for (int k = 0; k < nc; ++k) collapsed |= sh.bad[k] != 0;
     if (collapsed) return false;
-    const double new_lower = acc[0] / (double)n;
+    const double new_lower = sh.tot[0] / (double)n;
     const double change = new_lower - lower;
     lower = new_lower;
     if (fabs(change) < 1e-3) break;
   }
-  for (int k = 0; k < nc; ++k) { mu_out[k] = mu[k]; prec_out[k] = dmul(pch[k], pch[k]); }
+  for (int k = 0; k < nc; ++k) {
+    mu_out[k] = sh.par[k][VP_MU];
+    prec_out[k] = dmul(sh.par[k][VP_PCH], sh.par[k][VP_PCH]);
+  }
   return true;
 }
 
@@ -1106,6 +1174,8 @@ __global__ void __launch_bounds__(VAD_THREADS, 2) fe_vad_gmm_kernel(VadArgs a) {
   const int ncta = (int)cl.num_blocks();       // cluster size, chosen per launch (1, 2, 4 or 8)
   const int gstride = ncta * VAD_THREADS;
   const int n_clusters = gridDim.x / ncta;
+  if (tid == 0) sh.parity = 0;
+  __syncthreads();
   for (int ci = blockIdx.x / ncta; ci < a.n_utt; ci += n_clusters) {
     const int u = a.order ? (int)a.order[ci] : ci;
     const int64_t base = a.frame_off[u];
@@ -1125,7 +1195,7 @@ __global__ void __launch_bounds__(VAD_THREADS, 2) fe_vad_gmm_kernel(VadArgs a) {
       const float ssum = block_np_pairwise_sum_f32([src](int i) { return src[i]; }, n, sh);
       const float mean = (float)((double)ssum / (double)n);
       const float ss = block_np_pairwise_sum_f32(
-          [src, mean](int i) { const float d = __fadd_rn(src[i], -mean); return __fmul_rn(d, d); }, n, sh);
+          [src, mean](int i) { const float d = __fadd_rn(src[i], -mean); return __fmul_rn(d, d); }, n, sh, true);
       const float sd = sqrtf((float)((double)ss / (double)n));
       cl.sync();  // every CTA is done reading src (== xs on the retry path) before it is overwritten
       for (int i = gt; i < n; i += gstride) xs[i] = __fdiv_rn(__fsub_rn(src[i], mean), sd);
@@ -1297,10 +1367,10 @@ template <int N, typename PCM>
 static int launch_frame4(const FrameArgs& a, cudaStream_t st) {
   size_t smem = (size_t)(a.L + (a.L & 1)) * sizeof(double) + (size_t)N * sizeof(float2) +
                 (size_t)FE_WARPS * (32 / (N / 32)) * f4_region<N>() * sizeof(float2) + (size_t)a.L * sizeof(float) +
-                (size_t)a.mel_nnz * sizeof(float) + (size_t)3 * a.n_mels * sizeof(int) +
+                (size_t)a.mel_trips * 32 * sizeof(float2) + (size_t)(a.n_mels + 1) * sizeof(int) +
                 (size_t)((FT - 1) * a.hop + a.L) * sizeof(float);
   if (smem > 227 * 1024) return set_error(ODIN_EINVAL, "frame kernel needs %zu B smem (hop too large)", smem);
-  auto k = fe_frame4_kernel<N, PCM>;
+  auto k = (a.L <= N / 2) ? fe_frame4_kernel<N, PCM, true> : fe_frame4_kernel<N, PCM, false>;
   ODIN_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (227 * 1024) / (smem + 1024)));
   int64_t grid = std::min<int64_t>(a.n_tiles, (int64_t)sm_count() * per_sm);
@@ -1358,10 +1428,13 @@ int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t 
     a.mel_w = fe->d_mel_w; a.n_mels = fe->n_mels; a.scale2 = fe->scale2; a.mspec = d_mspec;
     a.energy = d_energy; a.umax = fe->d_umax;
     a.mel_nnz = fe->mel_nnz;
+    a.mel_tab = fe->d_mel_tab; a.mel_ps = fe->d_mel_ps; a.mel_trips = fe->mel_trips; a.mel_chunks = fe->mel_chunks;
     // four-step FFT kernel up to n_fft = 1024; the Stockham kernel keeps n_fft = 2048
     // (ODIN_FE_STOCKHAM=1 forces it everywhere, for A/B runs)
     const char* force = getenv("ODIN_FE_STOCKHAM");
-    const bool four = fe->N <= 1024 && !(force && force[0] == '1');
+    // (the chunk slots of the balanced filterbank sit behind the two power spectra in a pair region)
+    const bool slots_fit = fe->N + 2 + 2 * fe->mel_chunks <= 2 * 32 * (fe->N / 32 + 1);
+    const bool four = fe->N <= 1024 && slots_fit && !(force && force[0] == '1');
     int rc;
     if (four) {
       a.tw = fe->d_tw4;
