@@ -70,6 +70,7 @@ typedef struct {
   float thr_mean_scale;
   float thr_proportion;
   int32_t thr_context;
+  int32_t padding;        /* stft(padding=True): frame_len/2 zeros on both sides (signal.py:1529-1530) */
 } odin_fe_config;
 
 /* Builds the window / twiddle / sparse-mel / DCT tables (computed in fp64 on the
@@ -82,7 +83,7 @@ void odin_fe_destroy(odin_fe_t* fe);
 int odin_fe_feat_dim(const odin_fe_t* fe);
 
 /* HOST, integer-exact: frame_offsets[u+1]-frame_offsets[u] = 1+(n_u-L)//hop
- * (signal.py:1532-1538).  Returns ODIN_ESHORT if any utterance has n_u < L
+ * (signal.py:1532-1538; n_u counts the padding when cfg.padding is set).  Returns ODIN_ESHORT if any utterance has n_u < L
  * (offsets are still written, with 0 frames for that utterance). */
 int odin_fe_frame_offsets(const odin_fe_t* fe, const int64_t* h_sample_offsets, int32_t n_utt,
                           int64_t* h_frame_offsets);
@@ -118,6 +119,15 @@ int odin_fe_get_table(const odin_fe_t* fe, int32_t which, double* out, int64_t c
 int odin_fe_run(odin_fe_t* fe, const void* d_pcm, int32_t pcm_dtype, const int64_t* h_sample_offsets,
                 int32_t n_utt, float* d_mspec, float* d_feat, float* d_energy, float* d_c0,
                 uint8_t* d_sad, double* d_sad_thr, void* stream);
+
+/* odin_fe_run plus the power spectrum itself as an output -- the all-in-one SpectraExtractor
+ * (speech.py:849-929 -> signal.spectra, signal.py:1718-1832):
+ *   d_spec [T, n_fft/2+1]  |rfft|^2 / (sum w)^2; spec_log != 0 converts it with power2db and clips it at
+ *                          (utterance max - top_db) like signal.py:636-680 (spectra() passes top_db = 80).
+ * d_spec == NULL makes this call identical to odin_fe_run. */
+int odin_fe_run_spectra(odin_fe_t* fe, const void* d_pcm, int32_t pcm_dtype, const int64_t* h_sample_offsets,
+                        int32_t n_utt, float* d_mspec, float* d_feat, float* d_energy, float* d_c0,
+                        uint8_t* d_sad, double* d_sad_thr, float* d_spec, int32_t spec_log, void* stream);
 
 /* ApplyingSAD (speech.py:1732-1756): order-preserving row compaction of `d_feat`
  * [T, dim] by the mask.  d_out_offsets [n_utt+1] receives the compacted utterance

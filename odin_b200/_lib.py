@@ -30,6 +30,7 @@ class FeConfig(C.Structure):
       ("vad_kind", C.c_int32), ("vad_nmix", C.c_int32), ("vad_iters", C.c_int32),
       ("vad_smooth", C.c_int32), ("vad_mode", C.c_float), ("thr_energy", C.c_float),
       ("thr_mean_scale", C.c_float), ("thr_proportion", C.c_float), ("thr_context", C.c_int32),
+      ("padding", C.c_int32),
   ]
 
 
@@ -51,6 +52,7 @@ SIGNATURES = {
     "odin_host_frame_offsets": (C.c_int, [_i32, _i32, _pi64, _i32, _pi64]),
     "odin_fe_get_table": (C.c_int, [_vp, _i32, C.POINTER(C.c_double), _i64]),
     "odin_fe_run": (C.c_int, [_vp, _vp, _i32, _pi64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "odin_fe_run_spectra": (C.c_int, [_vp, _vp, _i32, _pi64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "odin_fe_compact": (C.c_int, [_vp, _vp, _pi64, _i32, _vp, _i32, _i32, _vp, _vp, _vp]),
     "odin_fe_cmvn": (C.c_int, [_vp, _vp, _i32, _pi64, _i32, _vp, _i32, _i32, _i32, _i32, _vp]),
     "odin_gmm_create": (C.c_int, [_i32, _i32, C.POINTER(_vp)]),

@@ -231,7 +231,7 @@ int fe_reserve(odin_fe* fe, int n_utt) {
   fe->d_tile2_off = fe->d_tile_off + n1;
   fe->d_vad_order = fe->d_tile2_off + n1;
   ODIN_CUDA_CHECK(cudaMalloc(&fe->d_dcsum, n1 * sizeof(double)));
-  ODIN_CUDA_CHECK(cudaMalloc(&fe->d_umax, n1 * sizeof(int)));
+  ODIN_CUDA_CHECK(cudaMalloc(&fe->d_umax, 2 * n1 * sizeof(int)));
   ODIN_CUDA_CHECK(cudaMalloc(&fe->d_cnt, n1 * sizeof(int64_t)));
   fe->cap_utt = cap;
   return ODIN_OK;
@@ -277,6 +277,7 @@ int odin_fe_create(const odin_fe_config* cfg, odin_fe_t** out) {
   if (!fe) return set_error(ODIN_ENOMEM, "out of host memory");
   fe->cfg = *cfg;
   fe->L = cfg->frame_len; fe->hop = cfg->hop; fe->N = cfg->n_fft; fe->nbins = cfg->n_fft / 2 + 1;
+  fe->pad = cfg->padding ? cfg->frame_len / 2 : 0;
   fe->n_mels = cfg->n_mels;
   fe->n_c1 = cfg->n_ceps > 0 ? cfg->n_ceps + 1 : 0;
   fe->feat_dim = cfg->n_ceps * (1 + cfg->delta_order);
@@ -301,11 +302,11 @@ void odin_fe_destroy(odin_fe_t* fe) {
 
 int odin_fe_feat_dim(const odin_fe_t* fe) { return fe ? fe->feat_dim : ODIN_EINVAL; }
 
-static int frame_offsets_impl(int L, int hop, const int64_t* so, int n_utt, int64_t* fo) {
+static int frame_offsets_impl(int L, int hop, const int64_t* so, int n_utt, int64_t* fo, int pad = 0) {
   int rc = ODIN_OK;
   fo[0] = 0;
   for (int u = 0; u < n_utt; ++u) {
-    int64_t n = so[u + 1] - so[u];
+    int64_t n = so[u + 1] - so[u] + 2 * (int64_t)pad;   // signal.py:1529-1530
     int64_t T = n < L ? 0 : 1 + (n - L) / hop;  // signal.py:1532-1538
     if (n < L) rc = ODIN_ESHORT;
     fo[u + 1] = fo[u] + T;
@@ -316,7 +317,7 @@ static int frame_offsets_impl(int L, int hop, const int64_t* so, int n_utt, int6
 int odin_fe_frame_offsets(const odin_fe_t* fe, const int64_t* h_sample_offsets, int32_t n_utt,
                           int64_t* h_frame_offsets) {
   if (!fe || !h_sample_offsets || !h_frame_offsets || n_utt < 0) return set_error(ODIN_EINVAL, "bad argument");
-  int rc = frame_offsets_impl(fe->L, fe->hop, h_sample_offsets, n_utt, h_frame_offsets);
+  int rc = frame_offsets_impl(fe->L, fe->hop, h_sample_offsets, n_utt, h_frame_offsets, fe->pad);
   if (rc == ODIN_ESHORT) set_error(rc, "an utterance is shorter than one frame (%d samples)", fe->L);
   return rc;
 }
@@ -360,6 +361,13 @@ int odin_fe_get_table(const odin_fe_t* fe, int32_t which, double* out, int64_t c
 int odin_fe_run(odin_fe_t* fe, const void* d_pcm, int32_t pcm_dtype, const int64_t* h_sample_offsets,
                 int32_t n_utt, float* d_mspec, float* d_feat, float* d_energy, float* d_c0, uint8_t* d_sad,
                 double* d_sad_thr, void* stream) {
+  return odin_fe_run_spectra(fe, d_pcm, pcm_dtype, h_sample_offsets, n_utt, d_mspec, d_feat, d_energy, d_c0, d_sad,
+                             d_sad_thr, nullptr, 0, stream);
+}
+
+int odin_fe_run_spectra(odin_fe_t* fe, const void* d_pcm, int32_t pcm_dtype, const int64_t* h_sample_offsets,
+                        int32_t n_utt, float* d_mspec, float* d_feat, float* d_energy, float* d_c0, uint8_t* d_sad,
+                        double* d_sad_thr, float* d_spec, int32_t spec_log, void* stream) {
   if (!fe || !d_pcm || !h_sample_offsets || n_utt < 0) return set_error(ODIN_EINVAL, "bad argument");
   if (pcm_dtype != 0 && pcm_dtype != 1) return set_error(ODIN_EINVAL, "pcm_dtype must be 0 (int16) or 1 (float32)");
   if (!d_mspec) return set_error(ODIN_EINVAL, "d_mspec is required (scratch for the utterance pass)");
@@ -375,7 +383,7 @@ int odin_fe_run(odin_fe_t* fe, const void* d_pcm, int32_t pcm_dtype, const int64
   // the pinned staging block may still be in flight from the previous call on this stream
   ODIN_CUDA_CHECK(cudaStreamSynchronize(st));
   memcpy(so, h_sample_offsets, sizeof(int64_t) * (n_utt + 1));
-  rc = frame_offsets_impl(fe->L, fe->hop, so, n_utt, fo);
+  rc = frame_offsets_impl(fe->L, fe->hop, so, n_utt, fo, fe->pad);
   if (rc == ODIN_ESHORT) return set_error(rc, "an utterance is shorter than one frame (%d samples)", fe->L);
   t1[0] = t2[0] = 0;
   for (int u = 0; u < n_utt; ++u) {
@@ -399,7 +407,7 @@ int odin_fe_run(odin_fe_t* fe, const void* d_pcm, int32_t pcm_dtype, const int64
   }
   ODIN_CUDA_CHECK(cudaMemcpyAsync(fe->d_sample_off, fe->h_stage, 5 * n1 * sizeof(int64_t), cudaMemcpyHostToDevice, st));
   return fe_launch(fe, d_pcm, pcm_dtype, n_utt, fo[n_utt], t1[n_utt], t2[n_utt], d_mspec, d_feat, d_energy, d_c0,
-                   d_sad, d_sad_thr, st);
+                   d_sad, d_sad_thr, d_spec, spec_log, st);
 }
 
 int odin_fe_compact(odin_fe_t* fe, const uint8_t* d_sad, const int64_t* h_frame_offsets, int32_t n_utt,

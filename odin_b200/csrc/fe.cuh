@@ -11,6 +11,7 @@ constexpr int ODIN_FE_MAX_MELS = 128;
 struct odin_fe {
   odin_fe_config cfg;
   int L = 0, hop = 0, N = 0, nbins = 0;
+  int pad = 0;   // zeros on both sides of every utterance (cfg.padding ? L / 2 : 0)
   int n_mels = 0, n_c1 = 0 /* n_ceps+1 rows of the DCT */, feat_dim = 0;
   float scale2 = 0.f;  // (1/sum w)^2  (signal.py:1547,1557-1558 applied to |S|^2)
   // device tables
@@ -38,7 +39,7 @@ struct odin_fe {
   int64_t* d_tile2_off = nullptr;
   int64_t* d_vad_order = nullptr;  // [cap] utterance visiting order of the SADgmm kernel
   double* d_dcsum = nullptr;   // [cap] (int64 bit pattern for int16 input)
-  int* d_umax = nullptr;       // [cap] ordered-int encoded utterance max of log-mel dB
+  int* d_umax = nullptr;       // [2 cap] ordered-int encoded utterance max of log-mel dB | of the dB spectrum
   int64_t* d_cnt = nullptr;    // [cap+1] compaction counts / offsets
   float* d_vad_scratch = nullptr;  // [frames] standardised energies
   int64_t vad_scratch_cap = 0;
@@ -58,8 +59,8 @@ namespace odin {
 int fe_build_tables(odin_fe* fe);           // host fp64 -> device
 int fe_reserve(odin_fe* fe, int n_utt);
 int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t total_frames,
-              int64_t n_tiles, int64_t n_tiles2, float* d_mspec, float* d_feat, float* d_energy,
-              float* d_c0, uint8_t* d_sad, double* d_sad_thr, cudaStream_t st);
+              int64_t n_tiles, int64_t n_tiles2, float* d_mspec, float* d_feat, float* d_energy, float* d_c0,
+              uint8_t* d_sad, double* d_sad_thr, float* d_spec, int spec_log, cudaStream_t st);
 int fe_cmvn_launch(const float* d_x, float* d_y, int dim, const int64_t* d_frame_off, int n_utt,
                    const uint8_t* d_sad, int mean_var_norm, int var_norm, int windowed, int win_length,
                    cudaStream_t st);

@@ -220,7 +220,31 @@ struct FrameArgs {
   float* mspec;   // [T, n_mels] unclipped dB
   float* energy;  // [T] nullable
   int* umax;      // [n_utt]
+  int pad;        // zeros virtually prepended / appended to every utterance (stft(padding=True), signal.py:1529-1530)
+  float* spec;    // [T, N/2+1] nullable: power spectrum (SpectraExtractor, signal.py:1718-1832), dB when spec_log
+  int spec_log;
+  int* umax_spec; // [n_utt] ordered-int max of the dB spectrum
 };
+
+// PCM tile -> shared memory with DC removal and pre-emphasis fused (speech.py:472-473, signal.py:955-967);
+// virtual sample v of the (padded) utterance is real sample v - pad, zeros outside (signal.py:1529-1530:
+// the padding is applied to the processed signal, so padded samples are exact zeros).
+template <typename PCM>
+__device__ __forceinline__ void stage_pcm(float* __restrict__ sbuf, const PCM* __restrict__ pu, int64_t n_u,
+                                          int64_t v0, int cnt, float mean, float coef, int pad, int tid, int nthr) {
+  for (int i = tid; i < cnt; i += nthr) {
+    const int64_t g = v0 + i - pad;
+    float cur = 0.f;
+    if (g >= 0 && g < n_u) {
+      cur = __fsub_rn((float)pu[g], mean);
+      if (coef != 0.f && g > 0) {
+        const float prev = __fsub_rn((float)pu[g - 1], mean);
+        cur = __fsub_rn(cur, __fmul_rn(coef, prev));  // two roundings, like numpy (signal.py:965)
+      }
+    }
+    sbuf[i] = cur;
+  }
+}
 
 __device__ __forceinline__ int find_segment(const int64_t* __restrict__ off, int n, int64_t v) {
   // largest u in [0, n) with off[u] <= v   (off is non-decreasing, off[0] = 0)
@@ -247,7 +271,7 @@ __global__ void __launch_bounds__(FE_THREADS) fe_frame_kernel(FrameArgs a) {
   C2<T>* bufs = tw + N;
   float* win32 = reinterpret_cast<float*>(bufs + FE_WARPS * PL);
   float* sbuf = win32 + a.L;
-  __shared__ int cta_max;
+  __shared__ int cta_max, cta_max_spec;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int L = a.L, hop = a.hop;
@@ -271,23 +295,11 @@ __global__ void __launch_bounds__(FE_THREADS) fe_frame_kernel(FrameArgs a) {
       mean = (float)(s / (double)n_u);
     }
     __syncthreads();  // previous tile done with sbuf / cta_max (and the table fill on the first trip)
-    if (tid == 0) cta_max = float_to_ordered(-FLT_MAX);
-    {
-      const int cnt = (nf - 1) * hop + L;
-      const int64_t g0 = (int64_t)t0 * hop;
-      const PCM* p = pcm + s0 + g0;
-      for (int i = tid; i < cnt; i += FE_THREADS) {
-        float cur = __fsub_rn((float)p[i], mean);
-        if (coef != 0.f && (g0 + i) > 0) {
-          float prev = __fsub_rn((float)p[i - 1], mean);
-          cur = __fsub_rn(cur, __fmul_rn(coef, prev));  // two roundings, like numpy (signal.py:965)
-        }
-        sbuf[i] = cur;
-      }
-    }
+    if (tid == 0) { cta_max = float_to_ordered(-FLT_MAX); cta_max_spec = float_to_ordered(-FLT_MAX); }
+    stage_pcm<PCM>(sbuf, pcm + s0, n_u, (int64_t)t0 * hop, (nf - 1) * hop + L, mean, coef, a.pad, tid, FE_THREADS);
     __syncthreads();
 
-    float wmax = -FLT_MAX;
+    float wmax = -FLT_MAX, smax = -FLT_MAX;
     for (int pair = warp; 2 * pair < nf; pair += FE_WARPS) {
       const int fA = 2 * pair, fB = fA + 1;
       const bool hasB = fB < nf;
@@ -360,6 +372,24 @@ __global__ void __launch_bounds__(FE_THREADS) fe_frame_kernel(FrameArgs a) {
         pa[NK] = (zn.x * zn.x) * (T)a.scale2;
         pb[NK] = (zn.y * zn.y) * (T)a.scale2;
       }
+      if (a.spec != nullptr) {   // SpectraExtractor: the power spectrum itself is an output
+        constexpr int NBIN = N / 2 + 1;
+        float* rowA = a.spec + (fbase + t0 + fA) * NBIN;
+        float* rowB = rowA + NBIN;
+#pragma unroll
+        for (int i = 0; i <= NK; ++i) {
+          if (i == NK && lane != 0) break;
+          const int k = (i == NK) ? N / 2 : lane + 32 * i;
+          const float va = a.spec_log ? (float)db10<T>(pa[i]) : (float)pa[i];
+          rowA[k] = va;
+          smax = fmaxf(smax, va);
+          if (hasB) {
+            const float vb = a.spec_log ? (float)db10<T>(pb[i]) : (float)pb[i];
+            rowB[k] = vb;
+            smax = fmaxf(smax, vb);
+          }
+        }
+      }
       __syncwarp();
       T* PA = reinterpret_cast<T*>(buf);
       T* PB = PA + (N / 2 + 1);
@@ -389,8 +419,15 @@ __global__ void __launch_bounds__(FE_THREADS) fe_frame_kernel(FrameArgs a) {
     }
     wmax = warp_max(wmax);
     if (lane == 0) atomicMax(&cta_max, float_to_ordered(wmax));
+    if (a.spec != nullptr && a.spec_log) {
+      smax = warp_max(smax);
+      if (lane == 0) atomicMax(&cta_max_spec, float_to_ordered(smax));
+    }
     __syncthreads();
-    if (tid == 0) atomicMax(a.umax + u, cta_max);
+    if (tid == 0) {
+      atomicMax(a.umax + u, cta_max);
+      if (a.spec != nullptr && a.spec_log) atomicMax(a.umax_spec + u, cta_max_spec);
+    }
   }
 }
 
@@ -426,7 +463,7 @@ __global__ void __launch_bounds__(FE_THREADS, 2) fe_frame4_kernel(FrameArgs a) {
   float* win32 = reinterpret_cast<float*>(mtab + a.mel_trips * 32);
   int* mps = reinterpret_cast<int*>(win32 + a.L);
   float* sbuf = reinterpret_cast<float*>(mps + a.n_mels + 1);
-  __shared__ int cta_max;
+  __shared__ int cta_max, cta_max_spec;
   __shared__ double s_en[FT];   // frame energies of the tile; their logs are taken by one warp at the end
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -460,23 +497,11 @@ __global__ void __launch_bounds__(FE_THREADS, 2) fe_frame4_kernel(FrameArgs a) {
       mean = (float)(s / (double)n_u);
     }
     __syncthreads();  // previous tile done with sbuf / cta_max (and the table fill on the first trip)
-    if (tid == 0) cta_max = float_to_ordered(-FLT_MAX);
-    {
-      const int cnt = (nf - 1) * hop + L;
-      const int64_t g0 = (int64_t)t0 * hop;
-      const PCM* p = pcm + s0 + g0;
-      for (int i = tid; i < cnt; i += FE_THREADS) {
-        float cur = __fsub_rn((float)p[i], mean);
-        if (coef != 0.f && (g0 + i) > 0) {
-          float prev = __fsub_rn((float)p[i - 1], mean);
-          cur = __fsub_rn(cur, __fmul_rn(coef, prev));  // two roundings, like numpy (signal.py:965)
-        }
-        sbuf[i] = cur;
-      }
-    }
+    if (tid == 0) { cta_max = float_to_ordered(-FLT_MAX); cta_max_spec = float_to_ordered(-FLT_MAX); }
+    stage_pcm<PCM>(sbuf, pcm + s0, n_u, (int64_t)t0 * hop, (nf - 1) * hop + L, mean, coef, a.pad, tid, FE_THREADS);
     __syncthreads();
 
-    float wmax = -FLT_MAX;
+    float wmax = -FLT_MAX, smax = -FLT_MAX;
     const int npairs = (nf + 1) >> 1;
     for (int base = warp * NP; base < npairs; base += FE_WARPS * NP) {
       C2<T>* reg = wbuf + g * REG;
@@ -566,6 +591,24 @@ __global__ void __launch_bounds__(FE_THREADS, 2) fe_frame4_kernel(FrameArgs a) {
           pa[NK] = (zn.x * zn.x) * (T)a.scale2;
           pb[NK] = (zn.y * zn.y) * (T)a.scale2;
         }
+        if (a.spec != nullptr) {   // SpectraExtractor: the power spectrum itself is an output
+          constexpr int NBIN = N / 2 + 1;
+          float* rowA = a.spec + (fbase + t0 + fA) * NBIN;
+          float* rowB = rowA + NBIN;
+#pragma unroll
+          for (int i = 0; i <= NK; ++i) {
+            if (i == NK && lane != 0) break;
+            const int k = (i == NK) ? N / 2 : lane + 32 * i;
+            const float va = a.spec_log ? (float)db10<T>(pa[i]) : (float)pa[i];
+            rowA[k] = va;
+            smax = fmaxf(smax, va);
+            if (hasB) {
+              const float vb = a.spec_log ? (float)db10<T>(pb[i]) : (float)pb[i];
+              rowB[k] = vb;
+              smax = fmaxf(smax, vb);
+            }
+          }
+        }
         __syncwarp();
         T* PA = reinterpret_cast<T*>(buf);
         T* PB = PA + (N / 2 + 1);
@@ -609,8 +652,15 @@ __global__ void __launch_bounds__(FE_THREADS, 2) fe_frame4_kernel(FrameArgs a) {
     }
     wmax = warp_max(wmax);
     if (lane == 0) atomicMax(&cta_max, float_to_ordered(wmax));
+    if (a.spec != nullptr && a.spec_log) {
+      smax = warp_max(smax);
+      if (lane == 0) atomicMax(&cta_max_spec, float_to_ordered(smax));
+    }
     __syncthreads();
-    if (tid == 0) atomicMax(a.umax + u, cta_max);
+    if (tid == 0) {
+      atomicMax(a.umax + u, cta_max);
+      if (a.spec != nullptr && a.spec_log) atomicMax(a.umax_spec + u, cta_max_spec);
+    }
     if (a.energy != nullptr && tid < nf) {
       double e = s_en[tid];
       if (e == 0.0) e = (double)FLT_EPSILON;  // signal.py:1436
@@ -642,6 +692,24 @@ struct PostArgs {
 // (exact while n*d < 2^32; d == 1 wraps M to 0, which is the pass-through flag).
 __device__ __forceinline__ uint32_t fdiv_magic(int d) { return 0xFFFFFFFFu / (uint32_t)d + 1u; }
 __device__ __forceinline__ int fdiv(int n, uint32_t M) { return M ? (int)__umulhi((uint32_t)n, M) : n; }
+
+// SpectraExtractor's dB spectrum: clip at (utterance max - top_db) (signal.py:676-679), in place, tiles of PT frames
+__global__ void __launch_bounds__(256) fe_spec_clip_kernel(float* __restrict__ spec, const int64_t* __restrict__ frame_off,
+                                                           const int64_t* __restrict__ tile2_off, int n_utt,
+                                                           int64_t n_tiles, const int* __restrict__ umax_spec,
+                                                           float top_db, int nb) {
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int u = find_segment(tile2_off, n_utt, tile);
+    const int64_t base = frame_off[u];
+    const int T = (int)(frame_off[u + 1] - base);
+    const int t0 = (int)(tile - tile2_off[u]) * PT;
+    const int nf = min(PT, T - t0);
+    const float floor_db = ordered_to_float(umax_spec[u]) - top_db;
+    float* p = spec + (base + t0) * nb;
+    for (int i = threadIdx.x; i < nf * nb; i += 256)
+      if (p[i] < floor_db) p[i] = floor_db;
+  }
+}
 
 // Four consecutive outputs of a W-tap causal FIR down a strided column: out[j] = sum_k taps[k] x[(j + W-1 - k) * stride],
 // k ascending from a zero accumulator (the order of the one-row loops), the W + 3 inputs read once.
@@ -1391,7 +1459,7 @@ static int dispatch_frame4(int N, const FrameArgs& a, cudaStream_t st) {
 
 int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t total_frames, int64_t n_tiles,
               int64_t n_tiles2, float* d_mspec, float* d_feat, float* d_energy, float* d_c0, uint8_t* d_sad,
-              double* d_sad_thr, cudaStream_t st) {
+              double* d_sad_thr, float* d_spec, int spec_log, cudaStream_t st) {
   const odin_fe_config& c = fe->cfg;
   if (total_frames <= 0) return ODIN_OK;
   if (fe->ev[0] == nullptr) {
@@ -1419,7 +1487,7 @@ int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t 
   // 2. frame kernel
   {
     // 0x80808080 decodes (ordered_to_float) to about -3.4e38: below any log-mel value
-    ODIN_CUDA_CHECK(cudaMemsetAsync(fe->d_umax, 0x80, sizeof(int) * n_utt, st));
+    ODIN_CUDA_CHECK(cudaMemsetAsync(fe->d_umax, 0x80, sizeof(int) * 2 * ((size_t)fe->cap_utt + 1), st));
     FrameArgs a{};
     a.pcm = d_pcm; a.sample_off = fe->d_sample_off; a.frame_off = fe->d_frame_off; a.tile_off = fe->d_tile_off;
     a.n_utt = n_utt; a.n_tiles = n_tiles; a.dcsum = fe->d_dcsum; a.L = fe->L; a.hop = fe->hop;
@@ -1427,6 +1495,7 @@ int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t 
     a.tw = fe->d_tw; a.mel_start = fe->d_mel_start; a.mel_cnt = fe->d_mel_cnt; a.mel_off = fe->d_mel_off;
     a.mel_w = fe->d_mel_w; a.n_mels = fe->n_mels; a.scale2 = fe->scale2; a.mspec = d_mspec;
     a.energy = d_energy; a.umax = fe->d_umax;
+    a.pad = fe->pad; a.spec = d_spec; a.spec_log = spec_log; a.umax_spec = fe->d_umax + fe->cap_utt + 1;
     a.mel_nnz = fe->mel_nnz;
     a.mel_tab = fe->d_mel_tab; a.mel_ps = fe->d_mel_ps; a.mel_trips = fe->mel_trips; a.mel_chunks = fe->mel_chunks;
     // four-step FFT kernel up to n_fft = 1024; the Stockham kernel keeps n_fft = 2048
@@ -1444,6 +1513,12 @@ int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t 
                             : dispatch_frame<float, float>(fe->N, a, st);
     }
     if (rc) return rc;
+  }
+  if (d_spec != nullptr && spec_log && c.top_db >= 0.f) {
+    const int64_t grid = std::min<int64_t>(n_tiles2, (int64_t)sm_count() * 8);
+    fe_spec_clip_kernel<<<(unsigned)grid, 256, 0, st>>>(d_spec, fe->d_frame_off, fe->d_tile2_off, n_utt, n_tiles2,
+                                                        fe->d_umax + fe->cap_utt + 1, c.top_db, fe->nbins);
+    ODIN_LAUNCH_CHECK("fe_spec_clip_kernel");
   }
   ODIN_CUDA_CHECK(cudaEventRecord(fe->ev[2], st));
   // SADgmm reads only the frame energies, so it is forked onto the auxiliary stream and runs beside the

@@ -99,6 +99,42 @@ def frontend_fixtures():
   print("wrote smooth.npz")
 
 
+SPECTRA_CASES = [
+    # (sr, duration, SpectraExtractor kwargs, AudioReader + PreEmphasis in front)
+    (16000, 0.9, dict(frame_length=0.025, step_length=0.010, n_fft=512, window="hann", n_mels=40, n_ceps=13), True),
+    (16000, 0.5, dict(frame_length=0.025, step_length=0.010, n_fft=1024, window="hamm", log=False, padding=True),
+     False),
+    (8000, 0.7, dict(frame_length=0.025, step_length=0.005, n_fft=256, window="hann", n_ceps=20, padding=True,
+                     fmin=100, fmax=3000), True),
+]
+
+
+def spectra_fixtures():
+  """SpectraExtractor (speech.py:849-929) and STFTExtractor(padding=True) from the reference."""
+  pp, _ = ref_shim.load_frontend()
+  sp, base = pp.speech, pp.base
+  blob = {"n": np.int64(len(SPECTRA_CASES))}
+  for i, (sr, dur, kw, front) in enumerate(SPECTRA_CASES):
+    raw = synth.speech_like(700 + i, dur, sr, seed=311)
+    steps = ([sp.AudioReader(remove_dc=True), sp.PreEmphasis(0.97)] if front else []) + [sp.SpectraExtractor(**kw)]
+    X = ref_shim.run_pipeline(steps, {"raw": raw if front else raw.astype(np.float32), "sr": sr})
+    blob["c%d_pcm" % i] = raw
+    for k in ("spec", "energy", "mspec", "mfcc"):
+      if X.get(k) is not None:
+        blob["c%d_%s" % (i, k)] = X[k]
+  # the chained extractors with stft(padding=True)
+  cfg = FE_CONFIGS["cfg1"]
+  raw = synth.speech_like(731, 0.6, 16000, seed=311)
+  steps = _chain(sp, base, cfg)
+  steps[2] = sp.STFTExtractor(cfg["frame_length"], cfg["step_length"], n_fft=cfg["n_fft"], window="hamm",
+                              energy=True, padding=True)
+  X = ref_shim.run_pipeline(steps, {"raw": raw, "sr": 16000})
+  blob.update(pad_pcm=raw, pad_energy=X["stft_energy"], pad_mspec=X["mspec"], pad_mfcc=X["mfcc"],
+              pad_sad_gmm=X["sad_gmm"].astype(np.uint8))
+  np.savez_compressed(os.path.join(OUT, "spectra.npz"), **blob)
+  print("wrote spectra.npz")
+
+
 def gmm_fixtures():
   # (a) Appendix-B RNG-free case, both arithmetic modes of the reference
   N, D, M = 1000, 6, 8
@@ -199,7 +235,10 @@ if __name__ == "__main__":
   os.makedirs(OUT, exist_ok=True)
   if len(sys.argv) > 1 and sys.argv[1] == "cmvn":
     cmvn_fixtures()
+  elif len(sys.argv) > 1 and sys.argv[1] == "spectra":
+    spectra_fixtures()
   else:
+    spectra_fixtures()
     frontend_fixtures()
     gmm_fixtures()
     cmvn_fixtures()

@@ -213,3 +213,45 @@ def test_round_trip_properties_large():
   for i in range(8):        # utterance-global top_db clip: min >= max - 80 exactly
     m = mspec[fo[i]:fo[i + 1]]
     assert m.min() >= m.max() - 80.0 - 1e-4
+
+
+def test_spectra_extractor_and_padding():
+  """SpectraExtractor and STFTExtractor(padding=True) against the reference's golden outputs."""
+  from odin_b200 import preprocessing as pp
+  from oracle.make_golden import SPECTRA_CASES
+  g = np.load(os.path.join(GOLDEN, "spectra.npz"))
+  for i, (sr, _, kw, front) in enumerate(SPECTRA_CASES):
+    pcm = g["c%d_pcm" % i]
+    steps = ([pp.AudioReader(remove_dc=True), pp.PreEmphasis(0.97)] if front else []) + [pp.SpectraExtractor(**kw)]
+    pipe = pp.make_pipeline(steps)
+    X = pipe.transform({"raw": pcm if front else pcm.astype(np.float32), "sr": sr})
+    for k in ("spec", "energy", "mspec", "mfcc"):
+      key = "c%d_%s" % (i, k)
+      if key in g.files:
+        assert X[k].dtype == np.float32 and X[k].shape == g[key].shape, (i, k, X[k].shape)
+        assert relmax(X[k], g[key]) < TOL_FEAT, (i, k, relmax(X[k], g[key]))
+      else:
+        assert k not in X
+    assert "stft_energy" not in X and X["sr"] == sr
+  # chained extractors with centred frames
+  cfg = FE_CONFIGS["cfg1"]
+  steps = [pp.AudioReader(remove_dc=True), pp.PreEmphasis(0.97),
+           pp.STFTExtractor(cfg["frame_length"], cfg["step_length"], n_fft=cfg["n_fft"], window="hamm", energy=True,
+                            padding=True),
+           pp.PowerSpecExtractor(2.0, output_name="spec"),
+           pp.MelsSpecExtractor(cfg["n_mels"], fmin=cfg["fmin"], fmax=cfg["fmax"]),
+           pp.MFCCsExtractor(cfg["n_ceps"], remove_first_coef=True, first_coef_energy=True),
+           pp.DeltaExtractor("mfcc", order=(0, 1, 2)), pp.SADgmm(3, smooth_window=3, input_name="stft_energy")]
+  X = pp.make_pipeline(steps).transform({"raw": g["pad_pcm"], "sr": 16000})
+  assert X["mfcc"].shape == g["pad_mfcc"].shape
+  assert relmax(X["stft_energy"], g["pad_energy"]) < 1e-6
+  assert relmax(X["mspec"], g["pad_mspec"]) < TOL_FEAT and relmax(X["mfcc"], g["pad_mfcc"]) < TOL_FEAT
+  assert np.array_equal(X["sad"], g["pad_sad_gmm"])
+  # batch of ragged utterances, spectrum vs the oracle (dB clip is per utterance)
+  utts = synth.utterance_batch(5, 0.2, 1.1, sr=16000, seed=77)
+  ex = pp.SpectraExtractor(0.025, 0.010, n_fft=512, n_mels=40, n_ceps=13, padding=True)
+  outs = ex.transform_batch([{"raw": u.astype(np.float32), "sr": 16000} for u in utts])
+  for u, o in zip(utts, outs):
+    r = F.spectra(u.astype(np.float32), 16000, 0.025, 0.010, n_fft=512, n_mels=40, n_ceps=13, padding=True)
+    for k in ("spec", "mspec", "mfcc"):
+      assert o[k].shape == r[k].shape and relmax(o[k], r[k]) < TOL_FEAT, k

@@ -166,3 +166,32 @@ def test_cmvn_golden():
         assert np.array_equal(np.isnan(y), np.isnan(r))
         ok = np.isfinite(r)
         assert np.max(np.abs(y[ok] - r[ok])) < 1e-12
+
+
+def _spectra_inputs(g, i):
+  """The signal SpectraExtractor saw in fixture case i (oracle/make_golden.py SPECTRA_CASES)."""
+  from oracle.make_golden import SPECTRA_CASES
+  sr, _, kw, front = SPECTRA_CASES[i]
+  pcm = g["c%d_pcm" % i]
+  y = F.pre_emphasis(F.read_audio(pcm, True), 0.97) if front else pcm.astype(np.float32)
+  return sr, kw, front, pcm, y
+
+
+def test_spectra_golden():
+  """SpectraExtractor (speech.py:849-929) and stft(padding=True): oracle vs the reference's outputs."""
+  g = np.load(os.path.join(GOLDEN, "spectra.npz"))
+  for i in range(int(g["n"])):
+    sr, kw, _, _, y = _spectra_inputs(g, i)
+    o = F.spectra(y, sr, **kw)
+    for k in ("spec", "energy", "mspec", "mfcc"):
+      key = "c%d_%s" % (i, k)
+      if key in g.files:
+        assert o[k].dtype == np.float32 and o[k].shape == g[key].shape, (i, k)
+        assert relmax(o[k], g[key]) < 1e-6, (i, k)   # f32 casts of f64 pipelines
+      else:
+        assert o[k] is None
+  o = F.extract(g["pad_pcm"], 16000, vad="gmm", fmax=8000, padding=True)
+  assert o["mfcc"].shape == g["pad_mfcc"].shape == (1 + (9600 + 2 * 200 - 400) // 160, 60)
+  assert np.array_equal(o["stft_energy"], g["pad_energy"])
+  assert relmax(o["mspec"], g["pad_mspec"]) < 1e-12 and relmax(o["mfcc"], g["pad_mfcc"]) < 1e-12
+  assert np.array_equal(o["sad"], g["pad_sad_gmm"])

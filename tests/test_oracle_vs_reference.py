@@ -84,3 +84,18 @@ def test_gmm_estep_and_fit_match_reference():
   g.fit(X)
   m, s, ww, hist = OG.fit(X, 4, niter=3)
   assert np.array_equal(g.mean, m) and np.array_equal(g.sigma, s) and np.array_equal(g.w, ww)
+
+
+@pytest.mark.parametrize("padding", [False, True])
+def test_spectra_matches_reference(padding):
+  """oracle.spectra against the reference's SpectraExtractor (speech.py:849-929) on fresh audio."""
+  pp, _ = ref_shim.load_frontend()
+  raw = synth.speech_like(5, 0.8, 16000, seed=41).astype(np.float32)
+  kw = dict(frame_length=0.025, step_length=0.010, n_fft=512, window="hann", n_mels=30, n_ceps=12, padding=padding)
+  with warnings.catch_warnings():
+    warnings.simplefilter("ignore")
+    R = ref_shim.run_pipeline([pp.speech.SpectraExtractor(**kw)], {"raw": raw, "sr": 16000})
+  o = F.spectra(raw, 16000, **kw)
+  for k in ("spec", "energy", "mspec", "mfcc"):
+    assert o[k].shape == R[k].shape and o[k].dtype == R[k].dtype
+    assert relmax(o[k], R[k]) < 1e-6, k
