@@ -230,6 +230,48 @@ def cmvn_fixtures():
   print("wrote cmvn.npz (%d cases)" % k)
 
 
+def _tmat_problem(seed=3, D=6, M=8, n_files=40):
+  """Synthetic per-utterance statistics shaped like GMM.transform output (gmm_tmat.py:708-767)."""
+  rng = np.random.RandomState(seed)
+  sigma = (0.5 + rng.rand(D, M)).astype(np.float64)
+  Z = (rng.gamma(2.0, 15.0, size=(n_files, M))).astype(np.float64)
+  load = rng.randn(3, M * D) * 0.3                       # a low-rank speaker / session subspace
+  F = (rng.randn(n_files, 3).dot(load) * np.repeat(Z, D, axis=1) +
+       rng.randn(n_files, M * D) * np.sqrt(np.repeat(Z, D, axis=1))).astype(np.float64)
+  return sigma, Z, F
+
+
+def make_ref_tmatrix(tv_dim, sigma, niter=3):
+  """The reference Tmatrix on a stand-in for a fitted GMM (only feat_dim / nmix / sigma are read,
+  gmm_tmat.py:1419-1468)."""
+  G = ref_shim.load_gmm()
+  D, M = sigma.shape
+  g = G.GMM(nmix=M, nmix_start=M, niter=1, device="cpu", ncpu=1)
+  g._feat_dim, g._is_initialized, g._is_fitted = D, True, True
+  g.sigma = sigma
+  if not hasattr(G, "defaultdictkey"):
+    raise RuntimeError("reference helper defaultdictkey missing")
+  G.Tmatrix._refresh_gpu = lambda self: None
+  return G.Tmatrix(tv_dim=tv_dim, gmm=g, niter=niter, dtype="float64", device="cpu", ncpu=1)
+
+
+def tmat_fixtures():
+  sigma, Z, F = _tmat_problem()
+  tv = 5
+  t = make_ref_tmatrix(tv, sigma)
+  blob = dict(sigma=sigma, Z=Z, F=F, tv_dim=np.int64(tv), T0=t.Tm.copy(), T_invS0=t.T_invS.copy(),
+              T_invS_Tt0=t.T_invS_Tt.copy())
+  LU, RU, llk, nframes = t.expectation(Z, F, device="cpu", print_progress=False)
+  blob.update(LU0=LU, RU0=RU, llk0=np.float64(llk), nframes0=np.float64(nframes))
+  for it in range(3):
+    t.expectation_maximization(Z, F, device="cpu", print_progress=False)
+    blob["T%d" % (it + 1)] = t.Tm.copy()
+  blob["llk_hist"] = np.array(t._llk_hist, dtype=np.float64)
+  blob["ivec"] = np.concatenate([t.transform((Z[i:i + 1], F[i:i + 1])) for i in range(Z.shape[0])], 0)
+  np.savez_compressed(os.path.join(OUT, "tmat.npz"), **blob)
+  print("wrote tmat.npz")
+
+
 if __name__ == "__main__":
   warnings.filterwarnings("ignore")
   os.makedirs(OUT, exist_ok=True)
@@ -237,7 +279,10 @@ if __name__ == "__main__":
     cmvn_fixtures()
   elif len(sys.argv) > 1 and sys.argv[1] == "spectra":
     spectra_fixtures()
+  elif len(sys.argv) > 1 and sys.argv[1] == "tmat":
+    tmat_fixtures()
   else:
+    tmat_fixtures()
     spectra_fixtures()
     frontend_fixtures()
     gmm_fixtures()

@@ -195,3 +195,24 @@ def test_spectra_golden():
   assert np.array_equal(o["stft_energy"], g["pad_energy"])
   assert relmax(o["mspec"], g["pad_mspec"]) < 1e-12 and relmax(o["mfcc"], g["pad_mfcc"]) < 1e-12
   assert np.array_equal(o["sad"], g["pad_sad_gmm"])
+
+
+def test_tmatrix_golden():
+  """oracle/tmatrix.py against the reference's Tmatrix (gmm_tmat.py:1343-2090): initial statistics, one
+  E-step, three EM iterations and the i-vectors of the training files."""
+  from oracle import tmatrix as OT
+  g = np.load(os.path.join(GOLDEN, "tmat.npz"))
+  sigma, Z, F, tv = g["sigma"], g["Z"], g["F"], int(g["tv_dim"])
+  D = sigma.shape[0]
+  Sigma = OT.sigma_row(sigma)
+  T0 = OT.init_T(tv, Sigma)
+  assert np.array_equal(T0, g["T0"])
+  T_invS, T_invS_Tt = OT.refresh(T0, Sigma, D)
+  assert relmax(T_invS, g["T_invS0"]) < 1e-14 and relmax(T_invS_Tt, g["T_invS_Tt0"]) < 1e-14
+  LU, RU, llk, nframes = OT.expectation(Z, F, T_invS, T_invS_Tt)
+  assert relmax(LU, g["LU0"]) < 1e-12 and relmax(RU, g["RU0"]) < 1e-12
+  assert abs(llk - float(g["llk0"])) < 1e-9 * abs(float(g["llk0"])) and nframes == float(g["nframes0"])
+  Tm, T_invS, T_invS_Tt, hist = OT.fit(Z, F, tv, sigma, 3)
+  assert relmax(Tm, g["T3"]) < 1e-9
+  assert np.allclose(hist, g["llk_hist"], rtol=1e-9)
+  assert relmax(OT.ivector(Z, F, T_invS, T_invS_Tt), g["ivec"]) < 1e-9

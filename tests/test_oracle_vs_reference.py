@@ -99,3 +99,21 @@ def test_spectra_matches_reference(padding):
   for k in ("spec", "energy", "mspec", "mfcc"):
     assert o[k].shape == R[k].shape and o[k].dtype == R[k].dtype
     assert relmax(o[k], R[k]) < 1e-6, k
+
+
+def test_tmatrix_matches_reference():
+  """oracle/tmatrix.py against the reference class on a fresh problem (tv 7, 5 mixtures, 2 EM iterations)."""
+  from oracle import tmatrix as OT
+  from oracle.make_golden import _tmat_problem, make_ref_tmatrix
+  sigma, Z, F = _tmat_problem(seed=11, D=4, M=5, n_files=25)
+  t = make_ref_tmatrix(7, sigma, niter=2)
+  with warnings.catch_warnings():
+    warnings.simplefilter("ignore")
+    for _ in range(2):
+      t.expectation_maximization(Z, F, device="cpu", print_progress=False)
+  Tm, T_invS, T_invS_Tt, hist = OT.fit(Z, F, 7, sigma, 2)
+  assert relmax(Tm, t.Tm) < 1e-9 and relmax(T_invS_Tt, t.T_invS_Tt) < 1e-9
+  assert np.allclose(hist, t._llk_hist, rtol=1e-9)
+  iv = OT.ivector(Z[:3], F[:3], T_invS, T_invS_Tt)
+  ref = np.concatenate([t.transform((Z[i:i + 1], F[i:i + 1])) for i in range(3)], 0)
+  assert relmax(iv, ref) < 1e-9
