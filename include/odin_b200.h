@@ -36,6 +36,7 @@ extern "C" {
 #define ODIN_ECUDA (-3)     /* CUDA runtime error (see odin_last_error) */
 #define ODIN_ENOMEM (-4)
 #define ODIN_ESHORT (-5)    /* an utterance is shorter than one frame (signal.py:1532-1538 raises) */
+#define ODIN_ENUMERIC (-6)  /* a linear system was not positive definite (T-matrix path) */
 
 const char* odin_last_error(void);
 int odin_version(void); /* 1000*major + minor */
@@ -228,6 +229,44 @@ int odin_fe_last_run_ms(odin_fe_t* fe, float* ms4);
 
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t odin_launch_count(void);
+
+/* ------------------------------------------------------------------------- */
+/* Total-variability model / i-vectors: odin/ml/gmm_tmat.py class Tmatrix      */
+/* (fp64 like the reference's default dtype, gmm_tmat.py:1412)    */
+/* ------------------------------------------------------------------------- */
+typedef struct odin_tmat odin_tmat_t;
+
+/* tv_dim <= 128, feat_dim <= 64 in this version (the tv x tv systems are factorised in shared memory). */
+int odin_tmat_create(int32_t tv_dim, int32_t nmix, int32_t feat_dim, odin_tmat_t** out);
+void odin_tmat_destroy(odin_tmat_t* t);
+
+/* Number of doubles in the packed E-step statistics:
+ *   LU [nmix, tv(tv+1)/2] | RU [tv, nmix*feat_dim] | llk | nframes        (gmm_tmat.py:1694-1725)
+ * One buffer so that ranks holding different files can all-reduce it in one collective. */
+int64_t odin_tmat_acc_size(const odin_tmat_t* t);
+
+/* d_Tm [tv, nmix*feat_dim] (column m*feat_dim + d), d_Sigma [nmix*feat_dim] = GMM variances mixture-major
+ * (gmm_tmat.py:1466-1468).  Rebuilds T_invS and T_invS_Tt (gmm_tmat.py:1578-1589).  d_Sigma may be NULL to
+ * keep the current one. */
+int odin_tmat_set_model(odin_tmat_t* t, const double* d_Tm, const double* d_Sigma, void* stream);
+/* Copies out any of Tm [tv, MD], T_invS [tv, MD], T_invS_Tt [nmix, t2] (NULL = skip). */
+int odin_tmat_get_model(odin_tmat_t* t, double* d_Tm, double* d_T_invS, double* d_T_invS_Tt, void* stream);
+
+/* E-step over n_files utterances: d_Z [n, nmix], d_F [n, nmix*feat_dim] (centred first-order statistics
+ * of odin_gmm_utt_stats, as doubles); ACCUMULATES into d_acc (zero it before the first call of an iteration). */
+int odin_tmat_estep(odin_tmat_t* t, const double* d_Z, const double* d_F, int64_t n_files, double* d_acc,
+                    void* stream);
+
+/* M-step from the (all-reduced) statistics: per-mixture solve, minimum-divergence re-estimation and
+ * orthogonalisation (gmm_tmat.py:1818-1865), then the cached statistics are rebuilt.  The orthogonalised
+ * T equals the reference's diag(s) V^T up to the sign of each row (the SVD's sign convention).
+ * Synchronises the stream; returns ODIN_ENUMERIC when a system was not positive definite. */
+int odin_tmat_mstep(odin_tmat_t* t, const double* d_acc, int32_t min_div_est, int32_t orthogonalize,
+                    void* stream);
+
+/* i-vectors (gmm_tmat.py:1898-1942): d_out [n_files, tv]. */
+int odin_tmat_ivector(odin_tmat_t* t, const double* d_Z, const double* d_F, int64_t n_files, double* d_out,
+                      void* stream);
 
 #ifdef __cplusplus
 }

@@ -53,6 +53,14 @@ SIGNATURES = {
     "odin_fe_get_table": (C.c_int, [_vp, _i32, C.POINTER(C.c_double), _i64]),
     "odin_fe_run": (C.c_int, [_vp, _vp, _i32, _pi64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "odin_fe_run_spectra": (C.c_int, [_vp, _vp, _i32, _pi64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "odin_tmat_create": (C.c_int, [_i32, _i32, _i32, C.POINTER(_vp)]),
+    "odin_tmat_destroy": (None, [_vp]),
+    "odin_tmat_acc_size": (_i64, [_vp]),
+    "odin_tmat_set_model": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "odin_tmat_get_model": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "odin_tmat_estep": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "odin_tmat_mstep": (C.c_int, [_vp, _vp, _i32, _i32, _vp]),
+    "odin_tmat_ivector": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "odin_fe_compact": (C.c_int, [_vp, _vp, _pi64, _i32, _vp, _i32, _i32, _vp, _vp, _vp]),
     "odin_fe_cmvn": (C.c_int, [_vp, _vp, _i32, _pi64, _i32, _vp, _i32, _i32, _i32, _i32, _vp]),
     "odin_gmm_create": (C.c_int, [_i32, _i32, C.POINTER(_vp)]),

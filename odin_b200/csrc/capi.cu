@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "fe.cuh"
+#include "tmat.cuh"
 #include "fe_logic.cuh"
 #include "gmm.cuh"
 
@@ -664,6 +665,103 @@ int odin_gmm_score(odin_gmm_t* g, const float* d_X, int64_t n_frames, float* d_l
   if (rc) return rc;
   if (d_post || d_logprob) return gmm_post_ffma(g, d_X, n_frames, d_llk, d_post, d_logprob, st);
   return ODIN_OK;
+}
+
+// --------------------------------- T-matrix ---------------------------------
+int odin_tmat_create(int32_t tv_dim, int32_t nmix, int32_t feat_dim, odin_tmat_t** out) {
+  if (!out || tv_dim <= 0 || nmix <= 0 || feat_dim <= 0) return set_error(ODIN_EINVAL, "bad argument");
+  *out = nullptr;
+  if (tv_dim > TMAT_MAX_TV || feat_dim > TMAT_MAX_D)
+    return set_error(ODIN_EINVAL, "tv_dim must be <= %d and feat_dim <= %d in this version", TMAT_MAX_TV, TMAT_MAX_D);
+  int rc = require_device();
+  if (rc) return rc;
+  odin_tmat* t = new (std::nothrow) odin_tmat();
+  if (!t) return set_error(ODIN_ENOMEM, "out of host memory");
+  t->tv = tv_dim; t->M = nmix; t->D = feat_dim; t->t2 = tv_dim * (tv_dim + 1) / 2;
+  t->MD = (int64_t)nmix * feat_dim;
+  auto fail = [&](cudaError_t e) {
+    odin_tmat_destroy(t);
+    return set_error(ODIN_ENOMEM, "T-matrix buffers: %s", cudaGetErrorString(e));
+  };
+  cudaError_t e;
+  const size_t big = sizeof(double) * (size_t)t->tv * t->MD;
+  if ((e = cudaMalloc(&t->d_Tm, big)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&t->d_TinvS, big)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&t->d_Sigma, sizeof(double) * t->MD)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&t->d_TinvSTt, sizeof(double) * (size_t)t->M * t->t2)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&t->d_U, sizeof(double) * (size_t)t->tv * t->tv)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&t->d_perm, sizeof(int) * t->tv)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&t->d_flag, sizeof(int))) != cudaSuccess) return fail(e);
+  if ((e = cudaMemset(t->d_flag, 0, sizeof(int))) != cudaSuccess) return fail(e);
+  *out = t;
+  return ODIN_OK;
+}
+
+void odin_tmat_destroy(odin_tmat_t* t) {
+  if (!t) return;
+  cudaFree(t->d_Tm); cudaFree(t->d_TinvS); cudaFree(t->d_Sigma); cudaFree(t->d_TinvSTt); cudaFree(t->d_U);
+  cudaFree(t->d_perm); cudaFree(t->d_flag); cudaFree(t->d_L1); cudaFree(t->d_B1); cudaFree(t->d_Ex); cudaFree(t->d_llk);
+  delete t;
+}
+
+int64_t odin_tmat_acc_size(const odin_tmat_t* t) {
+  if (!t) return ODIN_EINVAL;
+  return (int64_t)t->M * t->t2 + (int64_t)t->tv * t->MD + 2;
+}
+
+int odin_tmat_set_model(odin_tmat_t* t, const double* d_Tm, const double* d_Sigma, void* stream) {
+  if (!t || !d_Tm) return set_error(ODIN_EINVAL, "bad argument");
+  cudaStream_t st = as_stream(stream);
+  ODIN_CUDA_CHECK(cudaMemcpyAsync(t->d_Tm, d_Tm, sizeof(double) * (size_t)t->tv * t->MD, cudaMemcpyDeviceToDevice, st));
+  if (d_Sigma) ODIN_CUDA_CHECK(cudaMemcpyAsync(t->d_Sigma, d_Sigma, sizeof(double) * t->MD, cudaMemcpyDeviceToDevice, st));
+  return tmat_refresh(t, st);
+}
+
+int odin_tmat_get_model(odin_tmat_t* t, double* d_Tm, double* d_T_invS, double* d_T_invS_Tt, void* stream) {
+  if (!t) return set_error(ODIN_EINVAL, "bad argument");
+  cudaStream_t st = as_stream(stream);
+  const size_t big = sizeof(double) * (size_t)t->tv * t->MD;
+  if (d_Tm) ODIN_CUDA_CHECK(cudaMemcpyAsync(d_Tm, t->d_Tm, big, cudaMemcpyDeviceToDevice, st));
+  if (d_T_invS) ODIN_CUDA_CHECK(cudaMemcpyAsync(d_T_invS, t->d_TinvS, big, cudaMemcpyDeviceToDevice, st));
+  if (d_T_invS_Tt)
+    ODIN_CUDA_CHECK(cudaMemcpyAsync(d_T_invS_Tt, t->d_TinvSTt, sizeof(double) * (size_t)t->M * t->t2, cudaMemcpyDeviceToDevice, st));
+  return ODIN_OK;
+}
+
+static int tmat_check_flag(odin_tmat* t, cudaStream_t st) {
+  int flag = 0;
+  ODIN_CUDA_CHECK(cudaMemcpyAsync(&flag, t->d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  ODIN_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (flag != 0) {
+    ODIN_CUDA_CHECK(cudaMemsetAsync(t->d_flag, 0, sizeof(int), st));
+    return set_error(ODIN_ENUMERIC, "T-matrix: %s not positive definite",
+                     flag == 1 ? "a posterior precision I + sum Z T' S^-1 T is" : flag == 2 ? "an M-step system sym(LU_m) is"
+                                                                                            : "the minimum-divergence matrix is");
+  }
+  return ODIN_OK;
+}
+
+int odin_tmat_estep(odin_tmat_t* t, const double* d_Z, const double* d_F, int64_t n_files, double* d_acc, void* stream) {
+  if (!t || !d_Z || !d_F || !d_acc || n_files < 0) return set_error(ODIN_EINVAL, "bad argument");
+  if (n_files == 0) return ODIN_OK;
+  return tmat_estep(t, d_Z, d_F, n_files, d_acc, as_stream(stream));
+}
+
+int odin_tmat_mstep(odin_tmat_t* t, const double* d_acc, int32_t min_div_est, int32_t orthogonalize, void* stream) {
+  if (!t || !d_acc) return set_error(ODIN_EINVAL, "bad argument");
+  cudaStream_t st = as_stream(stream);
+  int rc = tmat_mstep(t, d_acc, min_div_est, orthogonalize, 12, st);
+  if (rc) return rc;
+  return tmat_check_flag(t, st);
+}
+
+int odin_tmat_ivector(odin_tmat_t* t, const double* d_Z, const double* d_F, int64_t n_files, double* d_out, void* stream) {
+  if (!t || !d_Z || !d_F || !d_out || n_files < 0) return set_error(ODIN_EINVAL, "bad argument");
+  if (n_files == 0) return ODIN_OK;
+  cudaStream_t st = as_stream(stream);
+  int rc = tmat_ivector(t, d_Z, d_F, n_files, d_out, st);
+  if (rc) return rc;
+  return tmat_check_flag(t, st);
 }
 
 }  // extern "C"

@@ -1,0 +1,558 @@
+// Total-variability model (i-vector extractor) on sm_100a, fp64 throughout.
+//
+// Reference arithmetic (trungnt13/odin-ai, odin/ml/gmm_tmat.py):
+//   cached statistics        :1578-1589   T_invS = T / (Sigma + EPS); T_invS_Tt[m] = tril(T2_m T2_m^T),
+//                                         T2 = T / (sqrt(Sigma) + EPS)
+//   E-step                   :1694-1725   L1 = Z T_invS_Tt, B1 = F T_invS^T, per file: L = I + sym(L1),
+//                                         Cxx = L^-1, Ex = Cxx B, llk, Exx = tril(Cxx + Ex Ex^T);
+//                                         RU = Ex^T F, LU = Z^T Exx
+//   M-step                   :1818-1865   per mixture solve(sym(LU_m), RU_m); minimum-divergence
+//                                         T <- chol_upper(sym(sum LU / nframes)) T; orthogonalise T <- diag(s) V^T
+//   i-vector                 :1898-1942
+//
+// Layout: Tm / T_invS / RU [tv, M*D] row-major (column m*D + d), T_invS_Tt / LU [M, t2] with
+// t2 = tv (tv + 1) / 2 in np.tril_indices order (index a (a + 1) / 2 + b for a >= b), Z [n, M], F [n, M*D].
+//
+// Kernels
+//   tmat_refresh_kernel   one CTA per mixture (T2 block in smem)
+//   tmat_gemm_kernel      64x64x16 register-blocked fp64 GEMM with generic strides (all four products)
+//   tmat_file_kernel      one CTA per file: the tv x tv system lives in ONE padded smem square --
+//                         Cholesky factor in the lower triangle, its inverse written transposed into the
+//                         upper triangle, Cxx = G^-T G^-1 back into the lower triangle -- so tv = 128 fits
+//   tmat_solve_kernel     one CTA per mixture: Cholesky + forward / backward substitution, one thread per column
+//   tmat_mindiv_kernel    sum of LU over mixtures / nframes -> upper Cholesky factor
+//   tmat_jacobi_kernel    one-sided (Hestenes) Jacobi on the ROWS of T: rotating rows until they are mutually
+//                         orthogonal yields U^T T = diag(s) V^T directly, without forming T T^T or U; one launch
+//                         per round of a round-robin tournament (tv / 2 disjoint pairs per round)
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "tmat.cuh"
+
+namespace odin {
+
+constexpr double TM_EPS = 1e-6;  // gmm_tmat.py:27
+
+__device__ __forceinline__ int tril_idx(int a, int b) { return a * (a + 1) / 2 + b; }  // a >= b
+
+// ---------------------------------------------------------------------------
+// cached statistics
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tmat_refresh_kernel(const double* __restrict__ Tm, const double* __restrict__ Sigma,
+                                                           int tv, int D, int64_t MD, double* __restrict__ T_invS,
+                                                           double* __restrict__ T_invS_Tt) {
+  extern __shared__ double sm[];   // T2 block [tv][D + 1]
+  const int m = blockIdx.x, tid = threadIdx.x;
+  const int P = D + 1;
+  for (int i = tid; i < tv * D; i += 256) {
+    const int r = i / D, d = i - r * D;
+    const int64_t g = (int64_t)r * MD + (int64_t)m * D + d;
+    const double t = Tm[g], s = Sigma[(int64_t)m * D + d];
+    T_invS[g] = t / (s + TM_EPS);
+    sm[r * P + d] = t / (sqrt(s) + TM_EPS);
+  }
+  __syncthreads();
+  const int t2 = tv * (tv + 1) / 2;
+  for (int i = tid; i < tv * tv; i += 256) {
+    const int a = i / tv, b = i - a * tv;
+    if (b > a) continue;
+    double acc = 0.0;
+    for (int d = 0; d < D; ++d) acc = fma(sm[a * P + d], sm[b * P + d], acc);
+    T_invS_Tt[(int64_t)m * t2 + tril_idx(a, b)] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// C[M, N] = beta C + sum_k A(i, k) B(k, j);  A(i, k) = A[i sai + k sak],  B(k, j) = B[k sbk + j sbj]
+// ---------------------------------------------------------------------------
+constexpr int GB = 64, GK = 16;
+
+__global__ void __launch_bounds__(256) tmat_gemm_kernel(int M, int N, int K, const double* __restrict__ A, int64_t sai,
+                                                        int64_t sak, const double* __restrict__ B, int64_t sbk,
+                                                        int64_t sbj, double* __restrict__ C, int64_t ldc, double beta) {
+  __shared__ double As[GK][GB + 1];
+  __shared__ double Bs[GK][GB + 1];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int i0 = blockIdx.y * GB, j0 = blockIdx.x * GB;
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+  for (int k0 = 0; k0 < K; k0 += GK) {
+    // tile loads: consecutive threads walk the unit-stride dimension of each operand
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = tid + e * 256;   // 0 .. 1023
+      int ii, kk;
+      if (sak == 1) { kk = idx & (GK - 1); ii = idx >> 4; } else { ii = idx & (GB - 1); kk = idx >> 6; }
+      const int gi = i0 + ii, gk = k0 + kk;
+      As[kk][ii] = (gi < M && gk < K) ? A[(int64_t)gi * sai + (int64_t)gk * sak] : 0.0;
+      int jj, kb;
+      if (sbk == 1) { kb = idx & (GK - 1); jj = idx >> 4; } else { jj = idx & (GB - 1); kb = idx >> 6; }
+      const int gj = j0 + jj, gkb = k0 + kb;
+      Bs[kb][jj] = (gj < N && gkb < K) ? B[(int64_t)gkb * sbk + (int64_t)gj * sbj] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GK; ++kk) {
+      double av[4], bv[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) av[a] = As[kk][ty + 16 * a];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) bv[b] = Bs[kk][tx + 16 * b];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int gi = i0 + ty + 16 * a;
+    if (gi >= M) continue;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int gj = j0 + tx + 16 * b;
+      if (gj >= N) continue;
+      double* c = C + (int64_t)gi * ldc + gj;
+      *c = (beta == 0.0) ? acc[a][b] : fma(beta, *c, acc[a][b]);
+    }
+  }
+}
+
+static int gemm(int M, int N, int K, const double* A, int64_t sai, int64_t sak, const double* B, int64_t sbk, int64_t sbj,
+                double* C, int64_t ldc, double beta, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return ODIN_OK;
+  dim3 grid((unsigned)ceil_div(N, GB), (unsigned)ceil_div(M, GB));
+  tmat_gemm_kernel<<<grid, 256, 0, st>>>(M, N, K, A, sai, sak, B, sbk, sbj, C, ldc, beta);
+  ODIN_LAUNCH_CHECK("tmat_gemm_kernel");
+  return ODIN_OK;
+}
+
+// ---------------------------------------------------------------------------
+// in-place Cholesky of the lower triangle of S [n][P] (A = G G^T); returns false on a non-positive pivot
+// ---------------------------------------------------------------------------
+__device__ bool chol_lower(double* S, int n, int P, int* s_flag) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int k = 0; k < n; ++k) {
+    __syncthreads();
+    const double akk = S[k * P + k];
+    if (!(akk > 0.0)) {   // uniform: every thread reads the same value
+      if (tid == 0) *s_flag = 1;
+      return false;
+    }
+    const double g = sqrt(akk);
+    __syncthreads();
+    if (tid == 0) S[k * P + k] = g;
+    for (int i = k + 1 + tid; i < n; i += nt) S[i * P + k] /= g;
+    __syncthreads();
+    const int r = n - k - 1;
+    for (int e = tid; e < r * r; e += nt) {
+      const int ii = e / r, jj = e - ii * r;
+      if (jj > ii) continue;
+      const int i = k + 1 + ii, j = k + 1 + jj;
+      S[i * P + j] = fma(-S[i * P + k], S[j * P + k], S[i * P + j]);
+    }
+  }
+  __syncthreads();
+  return true;
+}
+
+// ---------------------------------------------------------------------------
+// per-file posterior of the latent factor
+// ---------------------------------------------------------------------------
+struct FileArgs {
+  int tv;
+  int64_t n;
+  double* L1;        // [n, t2] in: Z T_invS_Tt; out: Exx (when want_exx)
+  const double* B1;  // [n, tv]
+  double* Ex;        // [n, tv]
+  double* llk;       // [n] nullable
+  int want_exx;
+  int* flag;
+};
+
+__global__ void __launch_bounds__(256) tmat_file_kernel(FileArgs a) {
+  extern __shared__ double sm[];
+  const int n = a.tv, P = n + 1, tid = threadIdx.x;
+  double* S = sm;              // [n][P]
+  double* dg = S + n * P;      // [n] diagonal of the Cholesky factor, later diagonal of Cxx
+  double* Bv = dg + n;         // [n]
+  double* Ev = Bv + n;         // [n]
+  __shared__ int s_flag;
+  __shared__ double s_red[8];
+  const int t2 = n * (n + 1) / 2;
+  for (int64_t f = blockIdx.x; f < a.n; f += gridDim.x) {
+    __syncthreads();
+    if (tid == 0) s_flag = 0;
+    double* row = a.L1 + f * t2;
+    for (int e = tid; e < n * n; e += 256) {
+      const int i = e / n, j = e - i * n;
+      if (j > i) continue;
+      S[i * P + j] = row[tril_idx(i, j)] + (i == j ? 1.0 : 0.0);   // L = I + sym(L1)
+    }
+    for (int i = tid; i < n; i += 256) Bv[i] = a.B1[f * n + i];
+    if (!chol_lower(S, n, P, &s_flag)) {
+      if (tid == 0) atomicExch(a.flag, 1);
+      continue;
+    }
+    // G^-1 by forward substitution, one thread per column j; entry (i, j) is stored TRANSPOSED at S[j][i]
+    // (strict upper triangle), the diagonal of G moves to dg[] and 1 / G[j][j] takes its place
+    for (int i = tid; i < n; i += 256) dg[i] = S[i * P + i];
+    __syncthreads();
+    if (tid < n) {
+      const int j = tid;
+      S[j * P + j] = 1.0 / dg[j];
+      for (int i = j + 1; i < n; ++i) {
+        double acc = 0.0;
+        for (int k = j; k < i; ++k) acc = fma(S[i * P + k], S[j * P + k], acc);   // G[i][k] * Ginv[k][j]
+        S[j * P + i] = -acc / dg[i];
+      }
+    }
+    // careful: thread j reads G[i][k] for k in [j, i) -- strictly lower entries and never the diagonal slot of
+    // another column (k < i), except k == j where S[j][j] holds Ginv[j][j]: that IS Ginv[k][j] for k == j, and the
+    // G factor G[i][j] is read from S[i][j] (lower) -- distinct slots, so the loop above is hazard-free.
+    __syncthreads();
+    // Cxx = G^-T G^-1: Cxx[p][q] = sum_{i >= p} Ginv[i][p] Ginv[i][q] (p >= q) = row p . row q of the upper storage
+    for (int e = tid; e < n * n; e += 256) {
+      const int p = e / n, q = e - p * n;
+      if (q > p) continue;
+      double acc = 0.0;
+      for (int i = p; i < n; ++i) acc = fma(S[p * P + i], S[q * P + i], acc);
+      if (p == q) dg[p] = acc; else S[p * P + q] = acc;   // lower triangle is free again (G is consumed)
+    }
+    __syncthreads();
+    // Ex = Cxx B
+    for (int p = tid; p < n; p += 256) {
+      double acc = 0.0;
+      for (int q = 0; q < n; ++q) {
+        const double c = (q == p) ? dg[p] : (q < p ? S[p * P + q] : S[q * P + p]);
+        acc = fma(c, Bv[q], acc);
+      }
+      Ev[p] = acc;
+      a.Ex[f * n + p] = acc;
+    }
+    __syncthreads();
+    if (a.llk != nullptr) {   // -0.5 Ex^T (B - Ex) + Ex^T B   (gmm_tmat.py:1719)
+      double part = 0.0;
+      for (int p = tid; p < n; p += 256) part += -0.5 * Ev[p] * (Bv[p] - Ev[p]) + Ev[p] * Bv[p];
+      part = warp_sum(part);
+      if ((tid & 31) == 0) s_red[tid >> 5] = part;
+      __syncthreads();
+      if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += s_red[w];
+        a.llk[f] = t;
+      }
+    }
+    if (a.want_exx) {
+      for (int e = tid; e < n * n; e += 256) {
+        const int p = e / n, q = e - p * n;
+        if (q > p) continue;
+        const double c = (p == q) ? dg[p] : S[p * P + q];
+        row[tril_idx(p, q)] = fma(Ev[p], Ev[q], c);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// M-step, per mixture: Tm[:, m-block] = sym(LU_m)^-1 RU[:, m-block]
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tmat_solve_kernel(int tv, int D, int64_t MD, const double* __restrict__ LU,
+                                                         const double* __restrict__ RU, double* __restrict__ Tm,
+                                                         int* flag) {
+  extern __shared__ double sm[];
+  const int n = tv, P = n + 1, Q = D + 1, tid = threadIdx.x, m = blockIdx.x;
+  double* S = sm;            // [n][P]
+  double* R = S + n * P;     // [n][Q]
+  __shared__ int s_flag;
+  const int t2 = n * (n + 1) / 2;
+  if (tid == 0) s_flag = 0;
+  for (int e = tid; e < n * n; e += 256) {
+    const int i = e / n, j = e - i * n;
+    if (j > i) continue;
+    S[i * P + j] = LU[(int64_t)m * t2 + tril_idx(i, j)];
+  }
+  for (int e = tid; e < n * D; e += 256) {
+    const int i = e / D, d = e - i * D;
+    R[i * Q + d] = RU[(int64_t)i * MD + (int64_t)m * D + d];
+  }
+  if (!chol_lower(S, n, P, &s_flag)) {
+    if (tid == 0) atomicExch(flag, 2);
+    return;
+  }
+  if (tid < D) {
+    const int d = tid;
+    for (int i = 0; i < n; ++i) {            // G y = r
+      double acc = R[i * Q + d];
+      for (int k = 0; k < i; ++k) acc = fma(-S[i * P + k], R[k * Q + d], acc);
+      R[i * Q + d] = acc / S[i * P + i];
+    }
+    for (int i = n - 1; i >= 0; --i) {       // G^T x = y
+      double acc = R[i * Q + d];
+      for (int k = i + 1; k < n; ++k) acc = fma(-S[k * P + i], R[k * Q + d], acc);
+      R[i * Q + d] = acc / S[i * P + i];
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < n * D; e += 256) {
+    const int i = e / D, d = e - i * D;
+    Tm[(int64_t)i * MD + (int64_t)m * D + d] = R[i * Q + d];
+  }
+}
+
+// minimum-divergence factor: U upper with sym(sum_m LU_m / nframes) = U^T U (scipy.linalg.cholesky default)
+__global__ void __launch_bounds__(256) tmat_mindiv_kernel(int tv, int nmix, const double* __restrict__ LU,
+                                                          const double* __restrict__ nframes, double* __restrict__ U,
+                                                          int* flag) {
+  extern __shared__ double sm[];
+  const int n = tv, P = n + 1, tid = threadIdx.x;
+  double* S = sm;
+  __shared__ int s_flag;
+  const int t2 = n * (n + 1) / 2;
+  const double nf = *nframes;
+  if (tid == 0) s_flag = 0;
+  for (int e = tid; e < n * n; e += 256) {
+    const int i = e / n, j = e - i * n;
+    if (j > i) continue;
+    double acc = 0.0;
+    for (int m = 0; m < nmix; ++m) acc += LU[(int64_t)m * t2 + tril_idx(i, j)];   // LU.sum(0), mixture order
+    S[i * P + j] = acc / nf;
+  }
+  if (!chol_lower(S, n, P, &s_flag)) {
+    if (tid == 0) atomicExch(flag, 3);
+    return;
+  }
+  for (int e = tid; e < n * n; e += 256) {
+    const int i = e / n, j = e - i * n;
+    U[i * n + j] = (j >= i) ? S[j * P + i] : 0.0;   // U = G^T
+  }
+}
+
+// ---------------------------------------------------------------------------
+// one-sided Jacobi on the rows of W [tv, MD]: round `r` of a round-robin tournament over `np` players
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tmat_jacobi_kernel(double* __restrict__ W, int tv, int64_t MD, int np, int r) {
+  const int tid = threadIdx.x, i = blockIdx.x;   // pair index 0 .. np/2 - 1
+  int p, q;
+  if (i == 0) { p = np - 1; q = r; }
+  else { p = (r + i) % (np - 1); q = (r - i + (np - 1)) % (np - 1); }
+  if (p >= tv || q >= tv) return;   // the bye of an odd tournament
+  if (p > q) { const int t = p; p = q; q = t; }
+  double* wp = W + (int64_t)p * MD;
+  double* wq = W + (int64_t)q * MD;
+  double al = 0.0, be = 0.0, ga = 0.0;
+  for (int64_t j = tid; j < MD; j += 256) {
+    const double x = wp[j], y = wq[j];
+    al = fma(x, x, al); be = fma(y, y, be); ga = fma(x, y, ga);
+  }
+  __shared__ double red[3][8];
+  al = warp_sum(al); be = warp_sum(be); ga = warp_sum(ga);
+  if ((tid & 31) == 0) { red[0][tid >> 5] = al; red[1][tid >> 5] = be; red[2][tid >> 5] = ga; }
+  __syncthreads();
+  al = be = ga = 0.0;
+  for (int w = 0; w < 8; ++w) { al += red[0][w]; be += red[1][w]; ga += red[2][w]; }
+  if (fabs(ga) <= 1e-15 * sqrt(al * be) || ga == 0.0) return;   // already orthogonal to working precision
+  const double zeta = (be - al) / (2.0 * ga);
+  const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+  const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+  for (int64_t j = tid; j < MD; j += 256) {
+    const double x = wp[j], y = wq[j];
+    wp[j] = c * x - s * y;
+    wq[j] = s * x + c * y;
+  }
+}
+
+// singular values (row norms) -> descending order (stable), one CTA
+__global__ void __launch_bounds__(256) tmat_order_kernel(const double* __restrict__ W, int tv, int64_t MD,
+                                                         int* __restrict__ perm) {
+  __shared__ double nrm[TMAT_MAX_TV];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int p = warp; p < tv; p += 8) {
+    double a = 0.0;
+    for (int64_t j = lane; j < MD; j += 32) { const double x = W[(int64_t)p * MD + j]; a = fma(x, x, a); }
+    a = warp_sum(a);
+    if (lane == 0) nrm[p] = a;
+  }
+  __syncthreads();
+  if (tid < tv) {   // rank of row tid = #rows with a larger norm (ties: lower index first)
+    int rank = 0;
+    for (int p = 0; p < tv; ++p) rank += (nrm[p] > nrm[tid]) || (nrm[p] == nrm[tid] && p < tid);
+    perm[rank] = tid;
+  }
+}
+
+__global__ void __launch_bounds__(256) tmat_gather_rows_kernel(const double* __restrict__ W, double* __restrict__ out,
+                                                               const int* __restrict__ perm, int64_t MD) {
+  const int r = blockIdx.y;
+  const double* src = W + (int64_t)perm[r] * MD;
+  for (int64_t j = blockIdx.x * 256 + threadIdx.x; j < MD; j += (int64_t)gridDim.x * 256) out[(int64_t)r * MD + j] = src[j];
+}
+
+// nframes and llk totals of a chunk, one CTA, fixed order, accumulated into the packed statistics.
+// The reference takes nframes = ceil(sum Z) PER BATCH of its expectation() (gmm_tmat.py:1695, batches of
+// 64 MiB / ((D M + M) itemsize) files, :1444-1449) and adds the batches up, so the ceil is applied per
+// `rows_per_batch` files here as well.
+__global__ void __launch_bounds__(256) tmat_totals_kernel(const double* __restrict__ Z, int64_t n, int M,
+                                                          int64_t rows_per_batch, const double* __restrict__ llk,
+                                                          double* __restrict__ acc_llk, double* __restrict__ acc_nframes) {
+  __shared__ double red[8];
+  __shared__ double total;
+  const int tid = threadIdx.x;
+  auto block_sum = [&](double v) -> double {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += red[w];
+      total = t;
+    }
+    __syncthreads();
+    return total;
+  };
+  double nfr = 0.0;
+  for (int64_t s = 0; s < n; s += rows_per_batch) {
+    const int64_t e = min(n, s + rows_per_batch);
+    double a = 0.0;
+    for (int64_t i = s * M + tid; i < e * M; i += 256) a += Z[i];
+    nfr += ceil(block_sum(a));
+  }
+  double b = 0.0;
+  for (int64_t i = tid; i < n; i += 256) b += llk[i];
+  b = block_sum(b);
+  if (tid == 0) {
+    *acc_nframes += nfr;
+    *acc_llk += b;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static size_t square_smem(int tv, int extra_doubles) {
+  return sizeof(double) * ((size_t)tv * (tv + 1) + extra_doubles);
+}
+
+int tmat_refresh(odin_tmat* t, cudaStream_t st) {
+  const size_t smem = sizeof(double) * (size_t)t->tv * (t->D + 1);
+  ODIN_CUDA_CHECK(cudaFuncSetAttribute(tmat_refresh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tmat_refresh_kernel<<<t->M, 256, smem, st>>>(t->d_Tm, t->d_Sigma, t->tv, t->D, t->MD, t->d_TinvS, t->d_TinvSTt);
+  ODIN_LAUNCH_CHECK("tmat_refresh_kernel");
+  return ODIN_OK;
+}
+
+static int reserve_files(odin_tmat* t, int64_t n) {
+  if (n <= t->cap_files) return ODIN_OK;
+  cudaFree(t->d_L1); cudaFree(t->d_B1); cudaFree(t->d_Ex); cudaFree(t->d_llk);
+  t->d_L1 = t->d_B1 = t->d_Ex = t->d_llk = nullptr;
+  t->cap_files = 0;
+  ODIN_CUDA_CHECK(cudaMalloc(&t->d_L1, sizeof(double) * (size_t)n * t->t2));
+  ODIN_CUDA_CHECK(cudaMalloc(&t->d_B1, sizeof(double) * (size_t)n * t->tv));
+  ODIN_CUDA_CHECK(cudaMalloc(&t->d_Ex, sizeof(double) * (size_t)n * t->tv));
+  ODIN_CUDA_CHECK(cudaMalloc(&t->d_llk, sizeof(double) * (size_t)n));
+  t->cap_files = n;
+  return ODIN_OK;
+}
+
+// posterior of a chunk of files: fills d_Ex (and d_L1 <- Exx, d_llk when training)
+static int posterior_chunk(odin_tmat* t, const double* d_Z, const double* d_F, int64_t n, bool training, double* d_ex_out,
+                           cudaStream_t st) {
+  int rc;
+  // L1 = Z T_invS_Tt  [n, t2]
+  if ((rc = gemm((int)n, t->t2, t->M, d_Z, t->M, 1, t->d_TinvSTt, t->t2, 1, t->d_L1, t->t2, 0.0, st))) return rc;
+  // B1 = F T_invS^T   [n, tv]
+  if ((rc = gemm((int)n, t->tv, (int)t->MD, d_F, t->MD, 1, t->d_TinvS, 1, t->MD, t->d_B1, t->tv, 0.0, st))) return rc;
+  FileArgs a{};
+  a.tv = t->tv; a.n = n; a.L1 = t->d_L1; a.B1 = t->d_B1; a.Ex = d_ex_out; a.llk = training ? t->d_llk : nullptr;
+  a.want_exx = training ? 1 : 0; a.flag = t->d_flag;
+  const size_t smem = square_smem(t->tv, 3 * t->tv);
+  ODIN_CUDA_CHECK(cudaFuncSetAttribute(tmat_file_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (227 * 1024) / (smem + 1024)));
+  const int64_t grid = std::min<int64_t>(n, (int64_t)sm_count() * per_sm);
+  tmat_file_kernel<<<(unsigned)grid, 256, smem, st>>>(a);
+  ODIN_LAUNCH_CHECK("tmat_file_kernel");
+  return ODIN_OK;
+}
+
+int tmat_estep(odin_tmat* t, const double* d_Z, const double* d_F, int64_t n_files, double* d_acc, cudaStream_t st) {
+  double* d_LU = d_acc;
+  double* d_RU = d_LU + (size_t)t->M * t->t2;
+  double* d_llk = d_RU + (size_t)t->tv * t->MD;
+  double* d_nframes = d_llk + 1;
+  // files per chunk: a multiple of the reference's batch (see tmat_totals_kernel) within ~256 MiB of Exx rows
+  const int64_t ref_batch = std::max<int64_t>(1, (int64_t)(64u << 20) / ((t->MD + t->M) * (int64_t)sizeof(double)));
+  const int64_t cap = std::max<int64_t>(1, (int64_t)(256u << 20) / ((int64_t)sizeof(double) * t->t2));
+  const int64_t chunk = std::max<int64_t>(1, cap / ref_batch) * ref_batch;
+  int rc = reserve_files(t, std::min(chunk, n_files));
+  if (rc) return rc;
+  for (int64_t s = 0; s < n_files; s += chunk) {
+    const int64_t n = std::min(chunk, n_files - s);
+    const double* Z = d_Z + s * t->M;
+    const double* F = d_F + s * t->MD;
+    if ((rc = posterior_chunk(t, Z, F, n, true, t->d_Ex, st))) return rc;
+    // RU += Ex^T F  [tv, MD];  LU += Z^T Exx  [M, t2]
+    if ((rc = gemm(t->tv, (int)t->MD, (int)n, t->d_Ex, 1, t->tv, F, t->MD, 1, d_RU, t->MD, 1.0, st))) return rc;
+    if ((rc = gemm(t->M, t->t2, (int)n, Z, 1, t->M, t->d_L1, t->t2, 1, d_LU, t->t2, 1.0, st))) return rc;
+    tmat_totals_kernel<<<1, 256, 0, st>>>(Z, n, t->M, ref_batch, t->d_llk, d_llk, d_nframes);
+    ODIN_LAUNCH_CHECK("tmat_totals_kernel");
+  }
+  return ODIN_OK;
+}
+
+int tmat_ivector(odin_tmat* t, const double* d_Z, const double* d_F, int64_t n_files, double* d_out, cudaStream_t st) {
+  const int64_t chunk = std::max<int64_t>(64, std::min<int64_t>(n_files, (int64_t)(256u << 20) / (sizeof(double) * t->t2)));
+  int rc = reserve_files(t, std::min(chunk, n_files));
+  if (rc) return rc;
+  for (int64_t s = 0; s < n_files; s += chunk) {
+    const int64_t n = std::min(chunk, n_files - s);
+    if ((rc = posterior_chunk(t, d_Z + s * t->M, d_F + s * t->MD, n, false, d_out + s * t->tv, st))) return rc;
+  }
+  return ODIN_OK;
+}
+
+int tmat_mstep(odin_tmat* t, const double* d_acc, int min_div, int orthogonalize, int sweeps, cudaStream_t st) {
+  const double* d_LU = d_acc;
+  const double* d_RU = d_LU + (size_t)t->M * t->t2;
+  const double* d_nframes = d_RU + (size_t)t->tv * t->MD + 1;
+  int rc;
+  {
+    const size_t smem = square_smem(t->tv, t->tv * (t->D + 1));
+    if (smem > 227 * 1024) return set_error(ODIN_EINVAL, "T-matrix M-step needs %zu B of shared memory", smem);
+    ODIN_CUDA_CHECK(cudaFuncSetAttribute(tmat_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tmat_solve_kernel<<<t->M, 256, smem, st>>>(t->tv, t->D, t->MD, d_LU, d_RU, t->d_Tm, t->d_flag);
+    ODIN_LAUNCH_CHECK("tmat_solve_kernel");
+  }
+  if (min_div) {
+    const size_t smem = square_smem(t->tv, 0);
+    ODIN_CUDA_CHECK(cudaFuncSetAttribute(tmat_mindiv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tmat_mindiv_kernel<<<1, 256, smem, st>>>(t->tv, t->M, d_LU, d_nframes, t->d_U, t->d_flag);
+    ODIN_LAUNCH_CHECK("tmat_mindiv_kernel");
+    // Tm <- U Tm (through the T_invS buffer, which is rebuilt by the refresh below)
+    if ((rc = gemm(t->tv, (int)t->MD, t->tv, t->d_U, t->tv, 1, t->d_Tm, t->MD, 1, t->d_TinvS, t->MD, 0.0, st))) return rc;
+    ODIN_CUDA_CHECK(cudaMemcpyAsync(t->d_Tm, t->d_TinvS, sizeof(double) * (size_t)t->tv * t->MD, cudaMemcpyDeviceToDevice, st));
+  }
+  if (orthogonalize && t->tv > 1) {
+    const int np = t->tv + (t->tv & 1);
+    for (int sweep = 0; sweep < sweeps; ++sweep)
+      for (int r = 0; r < np - 1; ++r) {
+        tmat_jacobi_kernel<<<np / 2, 256, 0, st>>>(t->d_Tm, t->tv, t->MD, np, r);
+        ODIN_LAUNCH_CHECK("tmat_jacobi_kernel");
+      }
+    tmat_order_kernel<<<1, 256, 0, st>>>(t->d_Tm, t->tv, t->MD, t->d_perm);
+    ODIN_LAUNCH_CHECK("tmat_order_kernel");
+    dim3 grid((unsigned)std::min<int64_t>(ceil_div<int64_t>(t->MD, 256), 64), (unsigned)t->tv);
+    tmat_gather_rows_kernel<<<grid, 256, 0, st>>>(t->d_Tm, t->d_TinvS, t->d_perm, t->MD);
+    ODIN_LAUNCH_CHECK("tmat_gather_rows_kernel");
+    ODIN_CUDA_CHECK(cudaMemcpyAsync(t->d_Tm, t->d_TinvS, sizeof(double) * (size_t)t->tv * t->MD, cudaMemcpyDeviceToDevice, st));
+  }
+  return tmat_refresh(t, st);
+}
+
+}  // namespace odin
