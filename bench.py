@@ -48,6 +48,8 @@ def parse():
   p.add_argument("--kernel-impl", type=int, default=0, help="0 auto, 1 fp32 CUDA cores, 2 tcgen05 3xTF32, 3 tcgen05 3xFP16")
   p.add_argument("--mfcc-hours", type=float, default=2.0, help="hours of 16 kHz audio per GPU for the MFCC leg")
   p.add_argument("--no-mfcc", action="store_true")
+  p.add_argument("--no-tmat", action="store_true")
+  p.add_argument("--tmat-files", type=int, default=3000, help="files per GPU in the T-matrix leg")
   p.add_argument("--no-cpu-baseline", action="store_true")
   p.add_argument("--cpu-sample", type=int, default=131072, help="frames in the CPU-baseline sample")
   return p.parse_args()
@@ -295,6 +297,94 @@ def mfcc_leg(torch, args, rank, world, dist, peaks, do_cpu):
 
 
 # ---------------------------------------------------------------------------
+# T-matrix / i-vector leg (SURVEY 8f-2, config-5 scale)
+# ---------------------------------------------------------------------------
+def tmat_leg(torch, args, rank, world, dist, do_cpu):
+  """One EM iteration of the total-variability model on per-utterance statistics resident in HBM:
+  512-mix UBM, 60-dim features, tv_dim 64 (examples/fsdd_ivec.py default), `--tmat-files` files per GPU."""
+  from odin_b200 import _lib
+  from odin_b200.ml import GMM, Tmatrix
+  Dm, M, tv, n = 60, 512, 64, args.tmat_files
+  rng = np.random.RandomState(77 + rank)
+  sigma = (0.5 + rng.rand(Dm, M))
+  g = GMM(nmix=M, nmix_start=M)
+  g.initialize(np.zeros((4, Dm), dtype=np.float32))
+  g.sigma = sigma
+  t = Tmatrix(tv, g, niter=1)
+  gen = torch.Generator(device="cuda").manual_seed(99 + rank)
+  Z = torch.empty((n, M), dtype=torch.float64, device="cuda").uniform_(0.0, 40.0, generator=gen)
+  F = torch.randn((n, M * Dm), dtype=torch.float64, device="cuda", generator=gen) * Z.repeat_interleave(Dm, 1).sqrt()
+  lib = _lib.load()
+  acc = torch.zeros(t._acc_size, dtype=torch.float64, device="cuda")
+  T0 = t.Tm
+
+  def step(timing=None):
+    acc.zero_()
+    if timing:
+      timing[0].record()
+    _lib.check(lib.odin_tmat_estep(t._h, _lib.ptr(Z), _lib.ptr(F), n, _lib.ptr(acc), _lib.current_stream()))
+    if dist is not None:
+      dist.all_reduce(acc)
+    if timing:
+      timing[1].record()
+    t._mstep_device(acc, True, True)
+    if timing:
+      timing[2].record()
+
+  for _ in range(2):
+    step()
+  t._upload(T0)
+  torch.cuda.synchronize()
+  if dist is not None:
+    dist.barrier()
+  ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+  l0 = lib.odin_launch_count()
+  reps = max(2, min(args.steps, 3))
+  te = tm = 0.0
+  for _ in range(reps):
+    step(ev)
+    torch.cuda.synchronize()
+    te += ev[0].elapsed_time(ev[1])
+    tm += ev[1].elapsed_time(ev[2])
+  launches = lib.odin_launch_count() - l0
+  tt = torch.tensor([(te + tm) / reps / 1e3], dtype=torch.float64, device="cuda")
+  if dist is not None:
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+  step_s = float(tt[0])
+  t2 = tv * (tv + 1) // 2
+  flops_file = 2 * M * t2 * 2 + 2 * M * Dm * tv * 2 + tv ** 3          # L1 + LU, B1 + RU, factorise / invert / product
+  res = {
+      "metric": "tmatrix_em_files_per_s", "value": n * world / step_s, "unit": "files/s", "ms_per_step": step_s * 1e3,
+      "config": {"workload": "config 5 scale: T-matrix EM iteration (E-step + all-reduce + M-step with minimum divergence "
+                             "and orthogonalisation) on resident statistics", "nmix": M, "feat_dim": Dm, "tv_dim": tv,
+                 "files_per_gpu": n}, "dtype": "f64",
+      "kernel_ms": {"estep": te / reps, "mstep": tm / reps}, "gpu_launches": int(launches // reps),
+      "roofline": {"bound": "fp64", "achieved": flops_file * n / (te / reps / 1e3) / 1e12, "peak": 40.0, "unit": "TFLOP/s",
+                   "frac": flops_file * n / (te / reps / 1e3) / 1e12 / 40.0, "traffic": None,
+                   "kernel": "E-step (tmat_gemm_kernel x4 + tmat_file_kernel)", "peak_source": "nominal B200 fp64 (40 TFLOP/s)",
+                   "algorithmic_flops_per_file": flops_file},
+  }
+  if do_cpu:
+    from oracle import tmatrix as OT
+    ns = min(n, 256)
+    Zc, Fc = Z[:ns].cpu().numpy(), F[:ns].cpu().numpy()
+    Sigma = OT.sigma_row(sigma)
+    T_invS, T_invS_Tt = OT.refresh(T0, Sigma, Dm)
+    t0 = time.perf_counter()
+    LU, RU, _, nfr = OT.expectation(Zc, Fc, T_invS, T_invS_Tt)
+    t_e = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    OT.maximization(LU, RU, nfr, Dm)
+    t_m = time.perf_counter() - t0
+    res["cpu_baseline"] = {"value": n / (t_e * n / ns + t_m), "unit": "files/s", "cores": os.cpu_count(), "kind": "port",
+                           "sample": "oracle/tmatrix.py: E-step on %d files (%.2f s, scaled to %d files) + one M-step (%.2f s), "
+                                     "numpy/scipy with BLAS threads" % (ns, t_e, n, t_m)}
+  del Z, F, acc, t
+  torch.cuda.empty_cache()
+  return res
+
+
+# ---------------------------------------------------------------------------
 # main arm
 # ---------------------------------------------------------------------------
 def run_ours(args):
@@ -442,6 +532,11 @@ def run_ours(args):
       line["mfcc"] = mfcc_leg(torch, args, rank, world, dist, peaks, do_cpu)
     except Exception as e:  # the headline line must still be printed
       line["mfcc"] = {"error": "%s: %s" % (type(e).__name__, e)}
+  if not args.no_tmat:
+    try:
+      line["tmatrix"] = tmat_leg(torch, args, rank, world, dist, do_cpu)
+    except Exception as e:
+      line["tmatrix"] = {"error": "%s: %s" % (type(e).__name__, e)}
   if rank == 0:
     print(json.dumps(line))
   if dist is not None:

@@ -691,8 +691,8 @@ int odin_tmat_create(int32_t tv_dim, int32_t nmix, int32_t feat_dim, odin_tmat_t
   if ((e = cudaMalloc(&t->d_TinvSTt, sizeof(double) * (size_t)t->M * t->t2)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&t->d_U, sizeof(double) * (size_t)t->tv * t->tv)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&t->d_perm, sizeof(int) * t->tv)) != cudaSuccess) return fail(e);
-  if ((e = cudaMalloc(&t->d_flag, sizeof(int))) != cudaSuccess) return fail(e);
-  if ((e = cudaMemset(t->d_flag, 0, sizeof(int))) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&t->d_flag, 2 * sizeof(int))) != cudaSuccess) return fail(e);   // status | Jacobi rotation counter
+  if ((e = cudaMemset(t->d_flag, 0, 2 * sizeof(int))) != cudaSuccess) return fail(e);
   *out = t;
   return ODIN_OK;
 }
@@ -750,7 +750,7 @@ int odin_tmat_estep(odin_tmat_t* t, const double* d_Z, const double* d_F, int64_
 int odin_tmat_mstep(odin_tmat_t* t, const double* d_acc, int32_t min_div_est, int32_t orthogonalize, void* stream) {
   if (!t || !d_acc) return set_error(ODIN_EINVAL, "bad argument");
   cudaStream_t st = as_stream(stream);
-  int rc = tmat_mstep(t, d_acc, min_div_est, orthogonalize, 12, st);
+  int rc = tmat_mstep(t, d_acc, min_div_est, orthogonalize, 30, st);
   if (rc) return rc;
   return tmat_check_flag(t, st);
 }

@@ -337,7 +337,10 @@ __global__ void __launch_bounds__(256) tmat_mindiv_kernel(int tv, int nmix, cons
 // ---------------------------------------------------------------------------
 // one-sided Jacobi on the rows of W [tv, MD]: round `r` of a round-robin tournament over `np` players
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) tmat_jacobi_kernel(double* __restrict__ W, int tv, int64_t MD, int np, int r) {
+constexpr int JT = 1024;   // threads per pair: the three dot products are latency-bound, so use the whole SM
+
+__global__ void __launch_bounds__(JT) tmat_jacobi_kernel(double* __restrict__ W, int tv, int64_t MD, int np, int r,
+                                                         int* __restrict__ n_rot) {
   const int tid = threadIdx.x, i = blockIdx.x;   // pair index 0 .. np/2 - 1
   int p, q;
   if (i == 0) { p = np - 1; q = r; }
@@ -347,21 +350,22 @@ __global__ void __launch_bounds__(256) tmat_jacobi_kernel(double* __restrict__ W
   double* wp = W + (int64_t)p * MD;
   double* wq = W + (int64_t)q * MD;
   double al = 0.0, be = 0.0, ga = 0.0;
-  for (int64_t j = tid; j < MD; j += 256) {
+  for (int64_t j = tid; j < MD; j += JT) {
     const double x = wp[j], y = wq[j];
     al = fma(x, x, al); be = fma(y, y, be); ga = fma(x, y, ga);
   }
-  __shared__ double red[3][8];
+  __shared__ double red[3][JT / 32];
   al = warp_sum(al); be = warp_sum(be); ga = warp_sum(ga);
   if ((tid & 31) == 0) { red[0][tid >> 5] = al; red[1][tid >> 5] = be; red[2][tid >> 5] = ga; }
   __syncthreads();
   al = be = ga = 0.0;
-  for (int w = 0; w < 8; ++w) { al += red[0][w]; be += red[1][w]; ga += red[2][w]; }
+  for (int w = 0; w < JT / 32; ++w) { al += red[0][w]; be += red[1][w]; ga += red[2][w]; }
   if (fabs(ga) <= 1e-15 * sqrt(al * be) || ga == 0.0) return;   // already orthogonal to working precision
+  if (tid == 0) atomicAdd(n_rot, 1);
   const double zeta = (be - al) / (2.0 * ga);
   const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
   const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
-  for (int64_t j = tid; j < MD; j += 256) {
+  for (int64_t j = tid; j < MD; j += JT) {
     const double x = wp[j], y = wq[j];
     wp[j] = c * x - s * y;
     wq[j] = s * x + c * y;
@@ -540,11 +544,20 @@ int tmat_mstep(odin_tmat* t, const double* d_acc, int min_div, int orthogonalize
   }
   if (orthogonalize && t->tv > 1) {
     const int np = t->tv + (t->tv & 1);
-    for (int sweep = 0; sweep < sweeps; ++sweep)
+    // sweeps until one of them rotates nothing (quadratic convergence: 6-9 sweeps in fp64), at most `sweeps`;
+    // the rotation counter is read back once per sweep (the M-step runs once per EM iteration)
+    int* d_rot = t->d_flag + 1;
+    for (int sweep = 0; sweep < sweeps; ++sweep) {
+      ODIN_CUDA_CHECK(cudaMemsetAsync(d_rot, 0, sizeof(int), st));
       for (int r = 0; r < np - 1; ++r) {
-        tmat_jacobi_kernel<<<np / 2, 256, 0, st>>>(t->d_Tm, t->tv, t->MD, np, r);
+        tmat_jacobi_kernel<<<np / 2, JT, 0, st>>>(t->d_Tm, t->tv, t->MD, np, r, d_rot);
         ODIN_LAUNCH_CHECK("tmat_jacobi_kernel");
       }
+      int h_rot = 0;
+      ODIN_CUDA_CHECK(cudaMemcpyAsync(&h_rot, d_rot, sizeof(int), cudaMemcpyDeviceToHost, st));
+      ODIN_CUDA_CHECK(cudaStreamSynchronize(st));
+      if (h_rot == 0) break;
+    }
     tmat_order_kernel<<<1, 256, 0, st>>>(t->d_Tm, t->tv, t->MD, t->d_perm);
     ODIN_LAUNCH_CHECK("tmat_order_kernel");
     dim3 grid((unsigned)std::min<int64_t>(ceil_div<int64_t>(t->MD, 256), 64), (unsigned)t->tv);
