@@ -229,21 +229,49 @@ struct FrameArgs {
 // PCM tile -> shared memory with DC removal and pre-emphasis fused (speech.py:472-473, signal.py:955-967);
 // virtual sample v of the (padded) utterance is real sample v - pad, zeros outside (signal.py:1529-1530:
 // the padding is applied to the processed signal, so padded samples are exact zeros).
+//
+// ncu put 31 % of the frame kernel's stall samples on the scalar 2-byte loads of the first version, so the
+// tile is read as 16-byte vectors aligned in GLOBAL memory (8 int16 / 4 float samples per load) and written as
+// 16-byte shared-memory stores: element i of the tile lands at sbase[i + mis], where mis (0..7) is the
+// misalignment of the tile's first sample; the function returns sbase + mis, the tile origin for the readers.
+// sbase must be 32-byte aligned and hold cnt + 16 floats.
 template <typename PCM>
-__device__ __forceinline__ void stage_pcm(float* __restrict__ sbuf, const PCM* __restrict__ pu, int64_t n_u,
-                                          int64_t v0, int cnt, float mean, float coef, int pad, int tid, int nthr) {
-  for (int i = tid; i < cnt; i += nthr) {
-    const int64_t g = v0 + i - pad;
-    float cur = 0.f;
-    if (g >= 0 && g < n_u) {
-      cur = __fsub_rn((float)pu[g], mean);
-      if (coef != 0.f && g > 0) {
-        const float prev = __fsub_rn((float)pu[g - 1], mean);
-        cur = __fsub_rn(cur, __fmul_rn(coef, prev));  // two roundings, like numpy (signal.py:965)
+__device__ __forceinline__ float* stage_pcm(float* __restrict__ sbase, const PCM* __restrict__ pu, int64_t n_u,
+                                            int64_t v0, int cnt, float mean, float coef, int pad, int tid, int nthr) {
+  constexpr int V = 16 / (int)sizeof(PCM);
+  const int64_t gstart = v0 - pad;   // utterance index of tile element 0 (negative inside the left padding)
+  const int mis = (int)((reinterpret_cast<uintptr_t>(pu + gstart) & 15) / sizeof(PCM));
+  const int n_chunks = (cnt + mis + V - 1) / V;
+  for (int c = tid; c < n_chunks; c += nthr) {
+    const int64_t g0 = gstart + (int64_t)c * V - mis;   // utterance index of the chunk's first sample
+    float x[V], prev0 = 0.f;
+    if (g0 >= 0 && g0 + V <= n_u) {
+      union { uint4 u; PCM e[V]; } raw;
+      raw.u = *reinterpret_cast<const uint4*>(pu + g0);
+#pragma unroll
+      for (int e = 0; e < V; ++e) x[e] = __fsub_rn((float)raw.e[e], mean);
+      if (g0 > 0) prev0 = __fsub_rn((float)pu[g0 - 1], mean);
+    } else {
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        const int64_t g = g0 + e;
+        x[e] = (g >= 0 && g < n_u) ? __fsub_rn((float)pu[g], mean) : 0.f;
       }
+      if (g0 > 0 && g0 - 1 < n_u) prev0 = __fsub_rn((float)pu[g0 - 1], mean);
     }
-    sbuf[i] = cur;
+    float y[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      const int64_t g = g0 + e;
+      float cur = x[e];
+      if (coef != 0.f && g > 0) cur = __fsub_rn(cur, __fmul_rn(coef, e == 0 ? prev0 : x[e - 1]));  // two roundings, like numpy (signal.py:965)
+      y[e] = (g >= 0 && g < n_u) ? cur : 0.f;
+    }
+    float4* dst = reinterpret_cast<float4*>(sbase + c * V);
+#pragma unroll
+    for (int q = 0; q < V / 4; ++q) dst[q] = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
   }
+  return sbase + mis;
 }
 
 __device__ __forceinline__ int find_segment(const int64_t* __restrict__ off, int n, int64_t v) {
@@ -257,7 +285,12 @@ __device__ __forceinline__ int find_segment(const int64_t* __restrict__ off, int
 }
 
 template <typename T> __device__ __forceinline__ T db10(T v);
-template <> __device__ __forceinline__ float db10<float>(float v) { return 10.f * log10f(fmaxf(v, 1e-10f)); }
+// 10 log10(max(v, 1e-10)) (signal.py:636-680) through the SFU: MUFU.LG2 is within 2 ulp of log2 (absolute error
+// < 1e-5 dB over the range of a log-mel value, against a 1e-4 x 80 dB tolerance) and replaces ~20 instructions
+// of log10f by two -- it was 4 % of the frame kernel's instructions.
+template <> __device__ __forceinline__ float db10<float>(float v) {
+  return 3.0102999566398120f * __log2f(fmaxf(v, 1e-10f));
+}
 template <> __device__ __forceinline__ double db10<double>(double v) { return 10.0 * log10(fmax(v, 1e-10)); }
 
 template <int N, typename T, typename PCM>
@@ -265,12 +298,12 @@ __global__ void __launch_bounds__(FE_THREADS) fe_frame_kernel(FrameArgs a) {
   using P = FftPlan<N>;
   constexpr int PL = padded_len<N>();
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: win64 [L] | tw [N] | warp bufs [FE_WARPS][PL] | win32 [L] | sbuf [(FT-1)*hop + L]
+  // layout: win64 [L] | tw [N] | warp bufs [FE_WARPS][PL] | win32 [L] | sbuf [(FT-1)*hop + L + 16]
   double* win64 = reinterpret_cast<double*>(smem_raw);
   C2<T>* tw = reinterpret_cast<C2<T>*>(win64 + a.L + (a.L & 1));
   C2<T>* bufs = tw + N;
   float* win32 = reinterpret_cast<float*>(bufs + FE_WARPS * PL);
-  float* sbuf = win32 + a.L;
+  float* sbuf = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(win32 + a.L) + 15) & ~uintptr_t(15));   // 16-byte stores
   __shared__ int cta_max, cta_max_spec;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -296,15 +329,16 @@ __global__ void __launch_bounds__(FE_THREADS) fe_frame_kernel(FrameArgs a) {
     }
     __syncthreads();  // previous tile done with sbuf / cta_max (and the table fill on the first trip)
     if (tid == 0) { cta_max = float_to_ordered(-FLT_MAX); cta_max_spec = float_to_ordered(-FLT_MAX); }
-    stage_pcm<PCM>(sbuf, pcm + s0, n_u, (int64_t)t0 * hop, (nf - 1) * hop + L, mean, coef, a.pad, tid, FE_THREADS);
+    const float* stile = stage_pcm<PCM>(sbuf, pcm + s0, n_u, (int64_t)t0 * hop, (nf - 1) * hop + L, mean, coef, a.pad,
+                                        tid, FE_THREADS);
     __syncthreads();
 
     float wmax = -FLT_MAX, smax = -FLT_MAX;
     for (int pair = warp; 2 * pair < nf; pair += FE_WARPS) {
       const int fA = 2 * pair, fB = fA + 1;
       const bool hasB = fB < nf;
-      const float* sA = sbuf + fA * hop;
-      const float* sB = sbuf + (hasB ? fB : fA) * hop;
+      const float* sA = stile + fA * hop;
+      const float* sB = stile + (hasB ? fB : fA) * hop;
       // ---- pass 0 fused with windowing and the fp64 frame energy ----
       {
         constexpr int R = P::R0;
@@ -455,14 +489,14 @@ __global__ void __launch_bounds__(FE_THREADS, 2) fe_frame4_kernel(FrameArgs a) {
   static_assert(REG >= N, "pair region must hold the natural-order spectrum");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // layout: win64 [L] | tw4 [N] | warp bufs [FE_WARPS][NP * REG] | mel table [trips][32] float2 | win32 [L] |
-  //         mel slots [n_mels + 1] | sbuf [(FT-1)*hop + L]
+  //         mel slots [n_mels + 1] | sbuf [(FT-1)*hop + L + 16]
   double* win64 = reinterpret_cast<double*>(smem_raw);
   C2<T>* tw4 = reinterpret_cast<C2<T>*>(win64 + a.L + (a.L & 1));
   C2<T>* bufs = tw4 + N;
   float2* mtab = reinterpret_cast<float2*>(bufs + FE_WARPS * NP * REG);
   float* win32 = reinterpret_cast<float*>(mtab + a.mel_trips * 32);
   int* mps = reinterpret_cast<int*>(win32 + a.L);
-  float* sbuf = reinterpret_cast<float*>(mps + a.n_mels + 1);
+  float* sbuf = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(mps + a.n_mels + 1) + 15) & ~uintptr_t(15));   // 16-byte stores
   __shared__ int cta_max, cta_max_spec;
   __shared__ double s_en[FT];   // frame energies of the tile; their logs are taken by one warp at the end
 
@@ -498,7 +532,8 @@ __global__ void __launch_bounds__(FE_THREADS, 2) fe_frame4_kernel(FrameArgs a) {
     }
     __syncthreads();  // previous tile done with sbuf / cta_max (and the table fill on the first trip)
     if (tid == 0) { cta_max = float_to_ordered(-FLT_MAX); cta_max_spec = float_to_ordered(-FLT_MAX); }
-    stage_pcm<PCM>(sbuf, pcm + s0, n_u, (int64_t)t0 * hop, (nf - 1) * hop + L, mean, coef, a.pad, tid, FE_THREADS);
+    const float* stile = stage_pcm<PCM>(sbuf, pcm + s0, n_u, (int64_t)t0 * hop, (nf - 1) * hop + L, mean, coef, a.pad,
+                                        tid, FE_THREADS);
     __syncthreads();
 
     float wmax = -FLT_MAX, smax = -FLT_MAX;
@@ -510,8 +545,8 @@ __global__ void __launch_bounds__(FE_THREADS, 2) fe_frame4_kernel(FrameArgs a) {
         const int pr = base + g;
         const int fA = 2 * pr, fB = fA + 1;
         const bool hasA = fA < nf, hasB = fB < nf;
-        const float* sA = sbuf + (hasA ? fA : 0) * hop;
-        const float* sB = sbuf + (hasB ? fB : 0) * hop;
+        const float* sA = stile + (hasA ? fA : 0) * hop;
+        const float* sB = stile + (hasB ? fB : 0) * hop;
         double eA = 0.0, eB = 0.0;
         C2<T> v[32];
 #pragma unroll
@@ -1403,7 +1438,7 @@ static size_t frame_smem(int L, int hop) {
   b += (size_t)N * sizeof(C2<T>);
   b += (size_t)FE_WARPS * padded_len<N>() * sizeof(C2<T>);
   b += (size_t)L * sizeof(float);
-  b += (size_t)((FT - 1) * hop + L) * sizeof(float);
+  b += (size_t)((FT - 1) * hop + L + 16 + 4) * sizeof(float);   // + misalignment slots and the 16-byte round-up (stage_pcm)
   return b;
 }
 
@@ -1436,7 +1471,7 @@ static int launch_frame4(const FrameArgs& a, cudaStream_t st) {
   size_t smem = (size_t)(a.L + (a.L & 1)) * sizeof(double) + (size_t)N * sizeof(float2) +
                 (size_t)FE_WARPS * (32 / (N / 32)) * f4_region<N>() * sizeof(float2) + (size_t)a.L * sizeof(float) +
                 (size_t)a.mel_trips * 32 * sizeof(float2) + (size_t)(a.n_mels + 1) * sizeof(int) +
-                (size_t)((FT - 1) * a.hop + a.L) * sizeof(float);
+                (size_t)((FT - 1) * a.hop + a.L + 16 + 4) * sizeof(float);   // + stage_pcm's misalignment slots / round-up
   if (smem > 227 * 1024) return set_error(ODIN_EINVAL, "frame kernel needs %zu B smem (hop too large)", smem);
   auto k = (a.L <= N / 2) ? fe_frame4_kernel<N, PCM, true> : fe_frame4_kernel<N, PCM, false>;
   ODIN_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
