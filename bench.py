@@ -48,6 +48,7 @@ def parse():
   p.add_argument("--kernel-impl", type=int, default=0, help="0 auto, 1 fp32 CUDA cores, 2 tcgen05 3xTF32, 3 tcgen05 3xFP16")
   p.add_argument("--mfcc-hours", type=float, default=2.0, help="hours of 16 kHz audio per GPU for the MFCC leg")
   p.add_argument("--no-mfcc", action="store_true")
+  p.add_argument("--mfcc-chunks", type=int, default=4, help="pipeline depth of the MFCC end-to-end call")
   p.add_argument("--no-tmat", action="store_true")
   p.add_argument("--tmat-files", type=int, default=3000, help="files per GPU in the T-matrix leg")
   p.add_argument("--no-cpu-baseline", action="store_true")
@@ -238,21 +239,18 @@ def mfcc_leg(torch, args, rank, world, dist, peaks, do_cpu):
   buf = (C.c_float * 4)()
   _lib.check(lib.odin_fe_last_run_ms(h, buf))
   kms = np.array(list(buf))
-  # e2e: pinned host PCM -> device, features + VAD back to the host
+  # e2e: pinned host PCM -> device, features + VAD back to pinned host memory, through the public host-buffer
+  # call (chunks of whole utterances pipelined over copy-in / kernel / copy-out streams)
   t_e2e = []
-  feat_h = torch.empty(out["feat"].shape, dtype=out["feat"].dtype).pin_memory()
-  sad_h = torch.empty(out["sad"].shape, dtype=out["sad"].dtype).pin_memory()
   del out
-  for _ in range(3):
+  host_out = None
+  for _ in range(4):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    d = pcm_pinned.cuda(non_blocking=True)
-    o = fe.run_packed(d, off, sr)
-    feat_h.copy_(o["feat"], non_blocking=True)   # MFCC+d+dd and the VAD mask back to pinned host memory
-    sad_h.copy_(o["sad"], non_blocking=True)
+    host_out = fe.run_host_packed(pcm_pinned, off, sr, want=("feat", "sad"), n_chunks=args.mfcc_chunks, out=host_out)
     torch.cuda.synchronize()
     t_e2e.append(time.perf_counter() - t0)
-    del o, d
+  feat_h, sad_h = host_out["feat"], host_out["sad"]
   h2d = pcm_pinned.numel() * 2
   d2h = feat_h.numel() * 4 + sad_h.numel()
   t = torch.tensor([ms / 1e3 / args.steps, min(t_e2e[1:])], dtype=torch.float64, device="cuda")

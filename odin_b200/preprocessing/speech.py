@@ -482,6 +482,88 @@ class FusedSpeechFrontEnd(Extractor):
                                        _lib.ptr(out['spec']), 1 if spec_log else 0, _lib.current_stream()))
     return out
 
+  def run_host_packed(self, pcm_pinned, sample_offsets, sr, want=("feat", "sad"), n_chunks=4, out=None):
+    """End-to-end variant of `run_packed` for HOST buffers: `pcm_pinned` is a pinned CPU tensor (int16 /
+    float32) of concatenated utterances; the batch is cut into `n_chunks` groups of whole utterances and
+    pipelined over three streams -- H2D copy of chunk i+1, kernels of chunk i and D2H copy of chunk i-1 run
+    concurrently (PCIe is full duplex) -- into pinned host outputs.  Returns a dict of pinned CPU tensors
+    for the names in `want` (from 'mspec', 'feat', 'energy', 'c0', 'sad') + 'frame_offsets'; valid after
+    the call returns (it synchronises).  Measured on the config-3 shard of bench.py (223 MB in, 168 MB out):
+    1 chunk 9.5 ms, 2 -> 7.2, 4 -> 6.1, 8 -> 6.7, 16 -> 8.9 (every chunk pays the SADgmm critical path of its
+    longest utterance once; tools/fe_e2e_sweep.py)."""
+    import torch
+    lib = _lib.load()
+    h, cfg = self._handle(int(sr))
+    so = np.ascontiguousarray(sample_offsets, dtype=np.int64)
+    n_utt = len(so) - 1
+    fo = np.zeros(n_utt + 1, dtype=np.int64)
+    _lib.check(lib.odin_fe_frame_offsets(h, _lib.as_i64_ptr(so), n_utt, _lib.as_i64_ptr(fo)))
+    T = int(fo[-1])
+    fd = cfg.n_ceps * (1 + cfg.delta_order)
+    widths = {'mspec': (cfg.n_mels, torch.float32), 'feat': (fd, torch.float32), 'energy': (0, torch.float32),
+              'c0': (0, torch.float32), 'sad': (0, torch.uint8)}
+    want = tuple(w for w in want if w in widths)
+    if out is None:
+      out = {}
+    for name in want:
+      wd, dt = widths[name]
+      if name not in out:
+        out[name] = torch.empty((T, wd) if wd else (T,), dtype=dt).pin_memory()
+    out['frame_offsets'] = fo
+    # chunk boundaries: whole utterances, about equal numbers of samples
+    n_chunks = max(1, min(int(n_chunks), n_utt))
+    targets = so[0] + (so[-1] - so[0]) * np.arange(1, n_chunks) / n_chunks
+    cuts = [0] + sorted(set(int(c) for c in np.searchsorted(so, targets) if 0 < c < n_utt)) + [n_utt]
+    chunks = [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+    max_s = max(int(so[b] - so[a]) for a, b in chunks)
+    dev = torch.device('cuda', torch.cuda.current_device())
+    main = torch.cuda.current_stream()
+    # the streams and the two PCM buffers are kept: the caching allocator hands blocks back per stream, so
+    # fresh streams on every call would turn each chunk's output tensors into cudaMalloc calls
+    pipe = getattr(self, '_pipe', None)
+    if pipe is None or pipe['dev'] != dev:
+      pipe = self._pipe = {'dev': dev, 'streams': [torch.cuda.Stream() for _ in range(3)], 'pcm': None}
+    s_in, s_run, s_out = pipe['streams']
+    for st in (s_in, s_run, s_out):
+      st.wait_stream(main)
+    if pipe['pcm'] is None or pipe['pcm'][0].numel() < max_s or pipe['pcm'][0].dtype != pcm_pinned.dtype:
+      pipe['pcm'] = [torch.empty(max_s, dtype=pcm_pinned.dtype, device=dev) for _ in range(2)]
+    d_pcm = pipe['pcm']
+    ev_in = [torch.cuda.Event() for _ in chunks]
+    ev_run = [torch.cuda.Event() for _ in chunks]
+    ev_out = [torch.cuda.Event() for _ in chunks]
+    dev_want = tuple(w for w in ('mspec', 'feat', 'energy', 'c0', 'sad') if w in want)
+
+    def copy_in(i):
+      a, b = chunks[i]
+      with torch.cuda.stream(s_in):
+        if i >= 2:
+          s_in.wait_event(ev_run[i - 2])          # the kernels of chunk i-2 are done with this PCM buffer
+        d_pcm[i % 2][:int(so[b] - so[a])].copy_(pcm_pinned[int(so[a]):int(so[b])], non_blocking=True)
+        ev_in[i].record(s_in)
+
+    copy_in(0)
+    keep = []
+    for i, (a, b) in enumerate(chunks):
+      if i + 1 < len(chunks):
+        copy_in(i + 1)
+      with torch.cuda.stream(s_run):
+        s_run.wait_event(ev_in[i])
+        o = self.run_packed(d_pcm[i % 2][:int(so[b] - so[a])], so[a:b + 1] - so[a], sr, want=dev_want)
+        ev_run[i].record(s_run)
+      with torch.cuda.stream(s_out):
+        s_out.wait_event(ev_run[i])
+        f0, f1 = int(fo[a]), int(fo[b])
+        for name in want:
+          out[name][f0:f1].copy_(o[name], non_blocking=True)
+        ev_out[i].record(s_out)
+      keep.append(o)   # device outputs stay referenced until their D2H copy has been issued and finished
+    for st in (s_in, s_run, s_out):
+      main.wait_stream(st)
+    main.synchronize()
+    del keep
+    return out
+
   def compact(self, sr, d_sad, frame_offsets, d_feat, keep_unvoiced=False):
     """ApplyingSAD on device -> (rows CUDA tensor [T, dim] (first n valid), offsets CUDA int64)."""
     import torch

@@ -255,3 +255,21 @@ def test_spectra_extractor_and_padding():
     r = F.spectra(u.astype(np.float32), 16000, 0.025, 0.010, n_fft=512, n_mels=40, n_ceps=13, padding=True)
     for k in ("spec", "mspec", "mfcc"):
       assert o[k].shape == r[k].shape and relmax(o[k], r[k]) < TOL_FEAT, k
+
+
+def test_run_host_packed_matches_run_packed():
+  """The pipelined host-buffer call (chunks of whole utterances over three streams) returns exactly what one
+  resident call does: per-utterance results do not depend on how the batch is cut."""
+  import torch
+  from odin_b200 import preprocessing as pp
+  cfg = FE_CONFIGS["cfg1"]
+  fe = _pipeline(cfg, vad="gmm").plan[0]
+  utts = synth.utterance_batch(23, 0.3, 2.5, sr=16000, seed=5)
+  pcm, off = synth.pack_utterances(utts)
+  ref = fe.run_packed(torch.from_numpy(pcm).cuda(), off, 16000)
+  pinned = torch.from_numpy(pcm).pin_memory()
+  for n_chunks in (1, 4, 50):
+    out = fe.run_host_packed(pinned, off, 16000, want=("feat", "sad", "mspec", "energy", "c0"), n_chunks=n_chunks)
+    assert np.array_equal(out["frame_offsets"], ref["frame_offsets"])
+    for k in ("feat", "sad", "mspec", "energy", "c0"):
+      assert torch.equal(out[k], ref[k].cpu()), (n_chunks, k)
