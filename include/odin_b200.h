@@ -130,6 +130,26 @@ int odin_fe_run_spectra(odin_fe_t* fe, const void* d_pcm, int32_t pcm_dtype, con
                         int32_t n_utt, float* d_mspec, float* d_feat, float* d_energy, float* d_c0,
                         uint8_t* d_sad, double* d_sad_thr, float* d_spec, int32_t spec_log, void* stream);
 
+/* Framing (speech.py:569-620) [+ CalculateEnergy, speech.py:623-649]: d_frames [T, frame_len] = window * signal
+ * (float32; the reference keeps float64), d_energy [T] = log sum (windowed frame)^2; either may be NULL.  DC removal,
+ * pre-emphasis and padding follow the handle's configuration, like odin_fe_run. */
+int odin_fe_frames(odin_fe_t* fe, const void* d_pcm, int32_t pcm_dtype, const int64_t* h_sample_offsets,
+                   int32_t n_utt, float* d_frames, float* d_energy, void* stream);
+
+/* Feature-matrix extractors over a ragged batch ([T, dim] float32, h_frame_offsets [n_utt+1] HOST):
+ *   odin_feat_stack      StackFeatures (base.py:724-771 = signal.stack_frames(keep_length=True), signal.py:1225-1294):
+ *                        d_y [T, (2 n_context + 1) dim], row t = rows t-c .. t+c, zeros outside the utterance
+ *   odin_feat_rasta_sdc  RASTAfilter (speech.py:1483-1533): rasta != 0 applies signal.rastafilt (signal.py:926-953) along
+ *                        time; sdc >= 1 appends signal.shifted_deltas(N = k = dim, d = sdc, P = 3) (signal.py:1068-1090):
+ *                        d_y [T, dim] or [T, dim + dim*dim]
+ *   odin_feat_energy     CalculateEnergy on explicit frames (signal.py:1421-1440): d_energy [n_frames] */
+int odin_feat_stack(const float* d_x, float* d_y, int32_t dim, const int64_t* h_frame_offsets, int32_t n_utt,
+                    int32_t n_context, void* stream);
+int odin_feat_rasta_sdc(const float* d_x, float* d_y, int32_t dim, const int64_t* h_frame_offsets, int32_t n_utt,
+                        int32_t rasta, int32_t sdc, void* stream);
+int odin_feat_energy(const float* d_frames, float* d_energy, int64_t n_frames, int32_t frame_len, int32_t take_log,
+                     void* stream);
+
 /* ApplyingSAD (speech.py:1732-1756): order-preserving row compaction of `d_feat`
  * [T, dim] by the mask.  d_out_offsets [n_utt+1] receives the compacted utterance
  * boundaries (d_out_offsets[n_utt] = number of rows written).  keep_unvoiced = 1

@@ -61,6 +61,10 @@ SIGNATURES = {
     "odin_tmat_estep": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "odin_tmat_mstep": (C.c_int, [_vp, _vp, _i32, _i32, _vp]),
     "odin_tmat_ivector": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "odin_fe_frames": (C.c_int, [_vp, _vp, _i32, _pi64, _i32, _vp, _vp, _vp]),
+    "odin_feat_stack": (C.c_int, [_vp, _vp, _i32, _pi64, _i32, _i32, _vp]),
+    "odin_feat_rasta_sdc": (C.c_int, [_vp, _vp, _i32, _pi64, _i32, _i32, _i32, _vp]),
+    "odin_feat_energy": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp]),
     "odin_fe_compact": (C.c_int, [_vp, _vp, _pi64, _i32, _vp, _i32, _i32, _vp, _vp, _vp]),
     "odin_fe_cmvn": (C.c_int, [_vp, _vp, _i32, _pi64, _i32, _vp, _i32, _i32, _i32, _i32, _vp]),
     "odin_gmm_create": (C.c_int, [_i32, _i32, C.POINTER(_vp)]),

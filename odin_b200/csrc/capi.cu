@@ -366,16 +366,12 @@ int odin_fe_run(odin_fe_t* fe, const void* d_pcm, int32_t pcm_dtype, const int64
                              d_sad_thr, nullptr, 0, stream);
 }
 
-int odin_fe_run_spectra(odin_fe_t* fe, const void* d_pcm, int32_t pcm_dtype, const int64_t* h_sample_offsets,
-                        int32_t n_utt, float* d_mspec, float* d_feat, float* d_energy, float* d_c0, uint8_t* d_sad,
-                        double* d_sad_thr, float* d_spec, int32_t spec_log, void* stream) {
-  if (!fe || !d_pcm || !h_sample_offsets || n_utt < 0) return set_error(ODIN_EINVAL, "bad argument");
-  if (pcm_dtype != 0 && pcm_dtype != 1) return set_error(ODIN_EINVAL, "pcm_dtype must be 0 (int16) or 1 (float32)");
-  if (!d_mspec) return set_error(ODIN_EINVAL, "d_mspec is required (scratch for the utterance pass)");
-  if (n_utt == 0) return ODIN_OK;
+// Host prelude shared by the entry points that walk a ragged batch of PCM: frame / tile offsets (integer exact,
+// signal.py:1532-1538) and the SADgmm visiting order into the pinned staging block, one upload.
+static int fe_prepare(odin_fe_t* fe, const int64_t* h_sample_offsets, int32_t n_utt, cudaStream_t st,
+                      int64_t* total_frames, int64_t* n_tiles, int64_t* n_tiles2) {
   int rc = fe_reserve(fe, n_utt);
   if (rc) return rc;
-  cudaStream_t st = as_stream(stream);
   const size_t n1 = (size_t)fe->cap_utt + 1;
   int64_t* so = fe->h_stage;
   int64_t* fo = so + n1;
@@ -407,8 +403,36 @@ int odin_fe_run_spectra(odin_fe_t* fe, const void* d_pcm, int32_t pcm_dtype, con
     for (int i = S; i < n_utt; ++i) ord[i] = idx[i];
   }
   ODIN_CUDA_CHECK(cudaMemcpyAsync(fe->d_sample_off, fe->h_stage, 5 * n1 * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-  return fe_launch(fe, d_pcm, pcm_dtype, n_utt, fo[n_utt], t1[n_utt], t2[n_utt], d_mspec, d_feat, d_energy, d_c0,
-                   d_sad, d_sad_thr, d_spec, spec_log, st);
+  *total_frames = fo[n_utt]; *n_tiles = t1[n_utt]; *n_tiles2 = t2[n_utt];
+  return ODIN_OK;
+}
+
+int odin_fe_run_spectra(odin_fe_t* fe, const void* d_pcm, int32_t pcm_dtype, const int64_t* h_sample_offsets,
+                        int32_t n_utt, float* d_mspec, float* d_feat, float* d_energy, float* d_c0, uint8_t* d_sad,
+                        double* d_sad_thr, float* d_spec, int32_t spec_log, void* stream) {
+  if (!fe || !d_pcm || !h_sample_offsets || n_utt < 0) return set_error(ODIN_EINVAL, "bad argument");
+  if (pcm_dtype != 0 && pcm_dtype != 1) return set_error(ODIN_EINVAL, "pcm_dtype must be 0 (int16) or 1 (float32)");
+  if (!d_mspec) return set_error(ODIN_EINVAL, "d_mspec is required (scratch for the utterance pass)");
+  if (n_utt == 0) return ODIN_OK;
+  cudaStream_t st = as_stream(stream);
+  int64_t T = 0, nt1 = 0, nt2 = 0;
+  int rc = fe_prepare(fe, h_sample_offsets, n_utt, st, &T, &nt1, &nt2);
+  if (rc) return rc;
+  return fe_launch(fe, d_pcm, pcm_dtype, n_utt, T, nt1, nt2, d_mspec, d_feat, d_energy, d_c0, d_sad, d_sad_thr, d_spec,
+                   spec_log, st);
+}
+
+int odin_fe_frames(odin_fe_t* fe, const void* d_pcm, int32_t pcm_dtype, const int64_t* h_sample_offsets, int32_t n_utt,
+                   float* d_frames, float* d_energy, void* stream) {
+  if (!fe || !d_pcm || !h_sample_offsets || n_utt < 0 || (!d_frames && !d_energy))
+    return set_error(ODIN_EINVAL, "bad argument");
+  if (pcm_dtype != 0 && pcm_dtype != 1) return set_error(ODIN_EINVAL, "pcm_dtype must be 0 (int16) or 1 (float32)");
+  if (n_utt == 0) return ODIN_OK;
+  cudaStream_t st = as_stream(stream);
+  int64_t T = 0, nt1 = 0, nt2 = 0;
+  int rc = fe_prepare(fe, h_sample_offsets, n_utt, st, &T, &nt1, &nt2);
+  if (rc) return rc;
+  return fe_frames_launch(fe, d_pcm, pcm_dtype, n_utt, T, nt1, d_frames, d_energy, st);
 }
 
 int odin_fe_compact(odin_fe_t* fe, const uint8_t* d_sad, const int64_t* h_frame_offsets, int32_t n_utt,

@@ -61,6 +61,8 @@ int fe_reserve(odin_fe* fe, int n_utt);
 int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t total_frames,
               int64_t n_tiles, int64_t n_tiles2, float* d_mspec, float* d_feat, float* d_energy, float* d_c0,
               uint8_t* d_sad, double* d_sad_thr, float* d_spec, int spec_log, cudaStream_t st);
+int fe_frames_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t total_frames, int64_t n_tiles,
+                     float* d_frames, float* d_energy, cudaStream_t st);
 int fe_cmvn_launch(const float* d_x, float* d_y, int dim, const int64_t* d_frame_off, int n_utt,
                    const uint8_t* d_sad, int mean_var_norm, int var_norm, int windowed, int win_length,
                    cudaStream_t st);

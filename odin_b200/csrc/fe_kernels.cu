@@ -1662,6 +1662,88 @@ int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t 
   return ODIN_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Framing (speech.py:569-620): windowed frames [T, L] as float32 and their log energy (get_energy on the
+// windowed frame, signal.py:1421-1440); same tiles and staging as the frame kernels
+// ---------------------------------------------------------------------------
+template <typename PCM>
+__global__ void __launch_bounds__(FE_THREADS) fe_frames_kernel(FrameArgs a, float* __restrict__ frames) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* win64 = reinterpret_cast<double*>(smem_raw);
+  float* sbuf = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(win64 + a.L) + 15) & ~uintptr_t(15));
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int L = a.L, hop = a.hop;
+  for (int i = tid; i < L; i += FE_THREADS) win64[i] = a.win64[i];
+  const PCM* __restrict__ pcm = reinterpret_cast<const PCM*>(a.pcm);
+  for (int64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    const int u = find_segment(a.tile_off, a.n_utt, tile);
+    const int64_t s0 = a.sample_off[u];
+    const int64_t n_u = a.sample_off[u + 1] - s0;
+    const int64_t fbase = a.frame_off[u];
+    const int T_u = (int)(a.frame_off[u + 1] - fbase);
+    const int t0 = (int)(tile - a.tile_off[u]) * FT;
+    const int nf = min(FT, T_u - t0);
+    float mean = 0.f;
+    if (a.remove_dc) {
+      double s = (sizeof(PCM) == 2) ? (double)reinterpret_cast<const long long*>(a.dcsum)[u] : a.dcsum[u];
+      mean = (float)(s / (double)n_u);
+    }
+    __syncthreads();
+    const float* stile = stage_pcm<PCM>(sbuf, pcm + s0, n_u, (int64_t)t0 * hop, (nf - 1) * hop + L, mean, a.preemph, a.pad,
+                                        tid, FE_THREADS);
+    __syncthreads();
+    for (int f = warp; f < nf; f += FE_WARPS) {
+      const float* sf = stile + f * hop;
+      double e = 0.0;
+      for (int i = lane; i < L; i += 32) {
+        const double v = win64[i] * (double)sf[i];
+        e = fma(v, v, e);
+        if (frames != nullptr) frames[(fbase + t0 + f) * L + i] = (float)v;
+      }
+      e = warp_sum(e);
+      if (lane == 0 && a.energy != nullptr) {
+        if (e == 0.0) e = (double)FLT_EPSILON;
+        a.energy[fbase + t0 + f] = (float)log(e);
+      }
+    }
+  }
+}
+
+int fe_frames_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t total_frames, int64_t n_tiles,
+                     float* d_frames, float* d_energy, cudaStream_t st) {
+  const odin_fe_config& c = fe->cfg;
+  if (total_frames <= 0) return ODIN_OK;
+  if (c.remove_dc) {
+    ODIN_CUDA_CHECK(cudaMemsetAsync(fe->d_dcsum, 0, sizeof(double) * n_utt, st));
+    int64_t maxlen = 0;
+    for (int u = 0; u < n_utt; ++u) maxlen = std::max(maxlen, fe->h_stage[u + 1] - fe->h_stage[u]);
+    int max_chunks = (int)ceil_div<int64_t>(maxlen, DC_CHUNK);
+    int64_t grid = (int64_t)n_utt * max_chunks;
+    if (grid > 0x7fffffff) return set_error(ODIN_EINVAL, "batch too large for fe_dc_kernel");
+    if (pcm_dtype == 0)
+      fe_dc_kernel<int16_t><<<(unsigned)grid, 256, 0, st>>>((const int16_t*)d_pcm, fe->d_sample_off, n_utt, max_chunks, fe->d_dcsum);
+    else
+      fe_dc_kernel<float><<<(unsigned)grid, 256, 0, st>>>((const float*)d_pcm, fe->d_sample_off, n_utt, max_chunks, fe->d_dcsum);
+    ODIN_LAUNCH_CHECK("fe_dc_kernel");
+  }
+  FrameArgs a{};
+  a.pcm = d_pcm; a.sample_off = fe->d_sample_off; a.frame_off = fe->d_frame_off; a.tile_off = fe->d_tile_off;
+  a.n_utt = n_utt; a.n_tiles = n_tiles; a.dcsum = fe->d_dcsum; a.L = fe->L; a.hop = fe->hop;
+  a.remove_dc = c.remove_dc; a.preemph = c.preemph; a.win64 = fe->d_win64; a.energy = d_energy; a.pad = fe->pad;
+  const size_t smem = sizeof(double) * fe->L + sizeof(float) * ((size_t)(FT - 1) * fe->hop + fe->L + 16 + 4) + 16;
+  if (smem > 227 * 1024) return set_error(ODIN_EINVAL, "framing kernel needs %zu B smem (hop too large)", smem);
+  const int64_t grid = std::min<int64_t>(n_tiles, (int64_t)sm_count() * 4);
+  if (pcm_dtype == 0) {
+    ODIN_CUDA_CHECK(cudaFuncSetAttribute(fe_frames_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fe_frames_kernel<int16_t><<<(unsigned)grid, FE_THREADS, smem, st>>>(a, d_frames);
+  } else {
+    ODIN_CUDA_CHECK(cudaFuncSetAttribute(fe_frames_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fe_frames_kernel<float><<<(unsigned)grid, FE_THREADS, smem, st>>>(a, d_frames);
+  }
+  ODIN_LAUNCH_CHECK("fe_frames_kernel");
+  return ODIN_OK;
+}
+
 int fe_compact_launch(odin_fe* fe, const uint8_t* d_sad, int n_utt, const float* d_feat, int dim,
                       int keep_unvoiced, float* d_out, int64_t* d_out_offsets, cudaStream_t st) {
   int grid = (int)std::min<int64_t>(ceil_div(n_utt, 4), (int64_t)sm_count() * 8);

@@ -1,0 +1,191 @@
+// Feature-matrix extractors that sit beside the fused front-end, over ragged batches
+// [T, dim] with host frame offsets:
+//   StackFeatures   base.py:724-771 -> signal.stack_frames(keep_length=True)  signal.py:1225-1294
+//   RASTAfilter     speech.py:1483-1533 -> signal.rastafilt (signal.py:926-953) + signal.shifted_deltas
+//                   (signal.py:1068-1090, deltas of signal.py:1002-1066)
+//   CalculateEnergy speech.py:623-649 -> signal.get_energy (signal.py:1421-1440)
+// All are HBM-bound copies / short recurrences; the arithmetic that the reference does in float64 (RASTA,
+// deltas, energy sums) is done in fp64 here and cast to float32 where the reference casts.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace odin {
+
+__device__ __forceinline__ int feat_find(const int64_t* __restrict__ off, int n, int64_t v) {
+  int lo = 0, hi = n;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (off[mid] <= v) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// y[t] = [x[t-c], ..., x[t+c]] flattened, zeros outside the utterance
+__global__ void __launch_bounds__(256) feat_stack_kernel(const float* __restrict__ x, float* __restrict__ y, int dim,
+                                                         const int64_t* __restrict__ off, int n_utt, int c) {
+  const int64_t T = off[n_utt];
+  const int w = (2 * c + 1) * dim;
+  for (int64_t t = blockIdx.x; t < T; t += gridDim.x) {
+    const int u = feat_find(off, n_utt, t);
+    const int64_t lo = off[u], hi = off[u + 1];
+    for (int j = threadIdx.x; j < w; j += 256) {
+      const int k = j / dim, d = j - k * dim;
+      const int64_t s = t + k - c;
+      y[t * w + j] = (s >= lo && s < hi) ? x[s * dim + d] : 0.f;
+    }
+  }
+}
+
+// RASTA along time, one thread per (utterance, column): scipy's transposed direct-form II recurrence with the
+// reference's warm-up (the first four outputs are zero; the FIR run over them only leaves the filter state).
+// y64 [T, dim] keeps the fp64 result for the delta pass, y32 (row stride ld) receives the float32 cast.
+__global__ void __launch_bounds__(128) feat_rasta_kernel(const float* __restrict__ x, double* __restrict__ y64,
+                                                         float* __restrict__ y32, int ld, int dim,
+                                                         const int64_t* __restrict__ off, int n_utt, int rasta) {
+  const int64_t id = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (id >= (int64_t)n_utt * dim) return;
+  const int u = (int)(id / dim), d = (int)(id - (int64_t)u * dim);
+  const int64_t lo = off[u], hi = off[u + 1];
+  const double b0 = 0.2, b1 = 0.1, b2 = -0.0, b3 = -0.1, b4 = -0.2;   // -arange(-2, 3) / 10
+  double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;
+  for (int64_t t = lo; t < hi; ++t) {
+    const double xn = (double)x[t * dim + d];
+    double yn;
+    if (!rasta) {
+      yn = xn;
+    } else if (t - lo < 4) {
+      yn = 0.0;
+      z0 = __dadd_rn(__dmul_rn(b1, xn), z1); z1 = __dadd_rn(__dmul_rn(b2, xn), z2);
+      z2 = __dadd_rn(__dmul_rn(b3, xn), z3); z3 = __dmul_rn(b4, xn);
+    } else {
+      yn = __dadd_rn(__dmul_rn(b0, xn), z0);
+      z0 = __dadd_rn(__dadd_rn(__dmul_rn(b1, xn), z1), __dmul_rn(0.94, yn));
+      z1 = __dadd_rn(__dmul_rn(b2, xn), z2);
+      z2 = __dadd_rn(__dmul_rn(b3, xn), z3);
+      z3 = __dmul_rn(b4, xn);
+    }
+    y64[t * dim + d] = yn;
+    y32[t * ld + d] = (float)yn;
+  }
+}
+
+// shifted delta coefficients: block ix of row t = first-order delta (width 2 sdc + 1, clamped edges, cast to
+// float32 like signal.delta) of frame min(t + 3 ix, T_u - 1); written behind the dim leading columns
+__global__ void __launch_bounds__(256) feat_sdc_kernel(const double* __restrict__ y64, float* __restrict__ out, int ld,
+                                                       int dim, const int64_t* __restrict__ off, int n_utt, int sdc) {
+  const int64_t T = off[n_utt];
+  const int w = dim * dim;
+  const int h = sdc, W = 2 * sdc + 1;
+  double norm = 0.0;
+  for (int m = -h; m <= h; ++m) norm += (double)m * m;
+  for (int64_t t = blockIdx.x; t < T; t += gridDim.x) {
+    const int u = feat_find(off, n_utt, t);
+    const int64_t lo = off[u], hi = off[u + 1];
+    for (int j = threadIdx.x; j < w; j += 256) {
+      const int ix = j / dim, d = j - ix * dim;
+      int64_t f = t + 3 * (int64_t)ix;
+      if (f > hi - 1) f = hi - 1;
+      double acc = 0.0;
+      for (int k = 0; k < W; ++k) {                      // taps (h - k) / norm on frame f + h - k, k ascending
+        int64_t s = f + h - k;
+        s = s < lo ? lo : (s > hi - 1 ? hi - 1 : s);
+        acc = __dadd_rn(acc, __dmul_rn((double)(h - k) / norm, y64[s * dim + d]));
+      }
+      out[t * ld + dim + j] = (float)acc;
+    }
+  }
+}
+
+// log sum x^2 per row (fp64 accumulation), exact zero -> float32 eps (signal.py:1436)
+__global__ void __launch_bounds__(256) feat_energy_kernel(const float* __restrict__ x, float* __restrict__ e, int64_t T,
+                                                          int L, int take_log) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * 256) >> 5;
+  for (int64_t t = row0; t < T; t += nw) {
+    double acc = 0.0;
+    for (int i = lane; i < L; i += 32) { const double v = (double)x[t * L + i]; acc = fma(v, v, acc); }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      if (acc == 0.0) acc = 1.1920928955078125e-07;
+      e[t] = (float)(take_log ? log(acc) : acc);
+    }
+  }
+}
+
+static int upload_offsets(const int64_t* h_off, int n_utt, int64_t** d_off, cudaStream_t st) {
+  ODIN_CUDA_CHECK(cudaMallocAsync(d_off, sizeof(int64_t) * (n_utt + 1), st));
+  cudaError_t e = cudaMemcpyAsync(*d_off, h_off, sizeof(int64_t) * (n_utt + 1), cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) { cudaFreeAsync(*d_off, st); return set_error(ODIN_ECUDA, "cudaMemcpyAsync: %s", cudaGetErrorString(e)); }
+  return ODIN_OK;
+}
+
+}  // namespace odin
+
+using namespace odin;
+
+extern "C" {
+
+int odin_feat_stack(const float* d_x, float* d_y, int32_t dim, const int64_t* h_frame_offsets, int32_t n_utt,
+                    int32_t n_context, void* stream) {
+  if (!d_x || !d_y || !h_frame_offsets || dim <= 0 || n_utt < 0 || n_context <= 0)
+    return set_error(ODIN_EINVAL, "bad argument");
+  int rc = require_device();
+  if (rc) return rc;
+  const int64_t T = n_utt ? h_frame_offsets[n_utt] : 0;
+  if (T == 0) return ODIN_OK;
+  cudaStream_t st = as_stream(stream);
+  int64_t* d_off = nullptr;
+  if ((rc = upload_offsets(h_frame_offsets, n_utt, &d_off, st))) return rc;
+  const unsigned grid = (unsigned)std::min<int64_t>(T, (int64_t)sm_count() * 16);
+  feat_stack_kernel<<<grid, 256, 0, st>>>(d_x, d_y, dim, d_off, n_utt, n_context);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(d_off, st);
+  if (e != cudaSuccess) return set_error(ODIN_ECUDA, "launch feat_stack_kernel: %s", cudaGetErrorString(e));
+  return ODIN_OK;
+}
+
+int odin_feat_rasta_sdc(const float* d_x, float* d_y, int32_t dim, const int64_t* h_frame_offsets, int32_t n_utt,
+                        int32_t rasta, int32_t sdc, void* stream) {
+  if (!d_x || !d_y || !h_frame_offsets || dim <= 0 || n_utt < 0 || sdc < 0) return set_error(ODIN_EINVAL, "bad argument");
+  int rc = require_device();
+  if (rc) return rc;
+  const int64_t T = n_utt ? h_frame_offsets[n_utt] : 0;
+  if (T == 0) return ODIN_OK;
+  cudaStream_t st = as_stream(stream);
+  int64_t* d_off = nullptr;
+  if ((rc = upload_offsets(h_frame_offsets, n_utt, &d_off, st))) return rc;
+  double* d_y64 = nullptr;
+  cudaError_t e = cudaMallocAsync(&d_y64, sizeof(double) * (size_t)T * dim, st);
+  if (e != cudaSuccess) { cudaFreeAsync(d_off, st); return set_error(ODIN_ENOMEM, "RASTA scratch: %s", cudaGetErrorString(e)); }
+  const int ld = sdc >= 1 ? dim + dim * dim : dim;
+  const int64_t nthr = (int64_t)n_utt * dim;
+  feat_rasta_kernel<<<(unsigned)ceil_div<int64_t>(nthr, 128), 128, 0, st>>>(d_x, d_y64, d_y, ld, dim, d_off, n_utt, rasta);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (sdc >= 1) {
+    const unsigned grid = (unsigned)std::min<int64_t>(T, (int64_t)sm_count() * 16);
+    feat_sdc_kernel<<<grid, 256, 0, st>>>(d_y64, d_y, ld, dim, d_off, n_utt, sdc);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
+  e = cudaGetLastError();
+  cudaFreeAsync(d_y64, st);
+  cudaFreeAsync(d_off, st);
+  if (e != cudaSuccess) return set_error(ODIN_ECUDA, "launch feat_rasta/sdc kernel: %s", cudaGetErrorString(e));
+  return ODIN_OK;
+}
+
+int odin_feat_energy(const float* d_frames, float* d_energy, int64_t n_frames, int32_t frame_len, int32_t take_log,
+                     void* stream) {
+  if (!d_frames || !d_energy || n_frames < 0 || frame_len <= 0) return set_error(ODIN_EINVAL, "bad argument");
+  int rc = require_device();
+  if (rc) return rc;
+  if (n_frames == 0) return ODIN_OK;
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(n_frames, 8), (int64_t)sm_count() * 16);
+  feat_energy_kernel<<<grid, 256, 0, as_stream(stream)>>>(d_frames, d_energy, n_frames, frame_len, take_log);
+  ODIN_LAUNCH_CHECK("feat_energy_kernel");
+  return ODIN_OK;
+}
+
+}  // extern "C"

@@ -284,6 +284,46 @@ class DeleteFeatures(Extractor):
 # ---------------------------------------------------------------------------
 # pipeline
 # ---------------------------------------------------------------------------
+class StackFeatures(Extractor):
+  """base.py:724-771: splice `n_context` frames of left and right context into every row
+  (signal.stack_frames(frame_length=2c+1, step_length=1, keep_length=True), zeros outside the utterance)."""
+
+  def __init__(self, n_context, input_name=None):
+    super(StackFeatures, self).__init__(input_name=as_tuple(input_name, t=str) if input_name is not None else None)
+    self.n_context = int(n_context)
+    assert self.n_context > 0
+
+  def transform_batch(self, Xs):
+    from .. import _lib
+    from .speech import _ragged_feature_call
+    import torch
+    _lib.require_cuda()
+    lib = _lib.load()
+    Xs = list(Xs)
+    checked = [self._check_input(x) for x in Xs]
+
+    def fn(d_x, dim, off):
+      y = torch.empty((d_x.shape[0], (2 * self.n_context + 1) * dim), dtype=torch.float32, device='cuda')
+      _lib.check(lib.odin_feat_stack(_lib.ptr(d_x), _lib.ptr(y), dim, _lib.as_i64_ptr(off), len(off) - 1,
+                                     self.n_context, _lib.current_stream()))
+      return y
+
+    res = list(checked)
+    live = [i for i, c in enumerate(checked) if c is None]
+    if self.input_name is None:   # every 2-D array of the dictionary, per input
+      for i in live:
+        names = [k for k, v in Xs[i].items() if isinstance(v, np.ndarray) and v.ndim == 2]
+        res[i] = _ragged_feature_call([Xs[i]], names, fn)[0]
+    else:
+      outs = _ragged_feature_call([Xs[i] for i in live], self.input_name, fn)
+      for i, o in zip(live, outs):
+        res[i] = o
+    return res
+
+  def transform(self, X):
+    return self.transform_batch([X])[0]
+
+
 class Pipeline(object):
   """What ``make_pipeline`` returns (base.py:96-136 returns an sklearn Pipeline;
   sklearn >= 1.x refuses ``transform`` on an unfitted pipeline, so the chain is

@@ -755,15 +755,15 @@ def plan_fusion(extractors):
       plan.extend(deferred)
       i = j
       continue
-    # [AudioReader] [PreEmphasis] SpectraExtractor: the all-in-one extractor takes the reader's DC removal
+    # [AudioReader] [PreEmphasis] SpectraExtractor | Framing: the extractor takes the reader's DC removal
     # and the pre-emphasis into its own fused run
-    if isinstance(e, (AudioReader, PreEmphasis, SpectraExtractor)):
+    if isinstance(e, (AudioReader, PreEmphasis, SpectraExtractor, Framing)):
       j, rd, pe, deferred, alias = i, None, None, [], {}
       if isinstance(extractors[j], AudioReader):
         rd, j = extractors[j], skip(j + 1)
       if j < n and isinstance(extractors[j], PreEmphasis):
         pe, j = extractors[j], skip(j + 1)
-      if j < n and isinstance(extractors[j], SpectraExtractor):
+      if j < n and isinstance(extractors[j], (SpectraExtractor, Framing)):
         extractors[j].bind(rd, pe)
         plan.append(extractors[j])
         plan.extend(deferred)
@@ -862,6 +862,165 @@ class SpectraExtractor(Extractor):
       base = {k: v for k, v in o.items() if k not in ('stft_energy', 'spec', 'mspec', 'mfcc')}
       results[i] = self._merge_output(base, y)
     return results
+
+  def transform(self, X):
+    return self.transform_batch([X])[0]
+
+  def _transform(self, X):
+    _no_cpu(self)
+
+
+class Framing(Extractor):
+  """speech.py:569-620: windowed frames `[T, frame_length]` (float32 here, float64 in the reference) and
+  the STFT `scale`.  An AudioReader / PreEmphasis in front of it is taken into its kernel by `plan_fusion`
+  (DC removal and pre-emphasis run in the staging copy, like the fused front-end)."""
+
+  def __init__(self, frame_length, step_length=None, window='hamm', padding=False, input_name=('raw', 'sr'),
+               output_name='frames'):
+    if isinstance(input_name, str):
+      input_name = (input_name, 'sr')
+    assert isinstance(output_name, str), "`output_name` must be string"
+    super(Framing, self).__init__(input_name=input_name, output_name=output_name)
+    if step_length is None:
+      step_length = frame_length // 4
+    self.frame_length = frame_length
+    self.step_length = step_length
+    self.window = window
+    self.padding = bool(padding)
+    self._reader = self._preemph = None
+    self._handles = {}
+    if window not in _WINDOWS:
+      raise NotImplementedError("window %r is not accelerated (hann / hamm only)" % (window,))
+
+  def bind(self, reader, preemph):
+    if preemph is not None and (preemph.input_name != self.input_name[0] or preemph.output_name != self.input_name[0]):
+      raise ValueError("PreEmphasis must read and write the Framing input feature")
+    self._reader, self._preemph, self._handles = reader, preemph, {}
+    self._is_input_layer = reader is not None
+
+  def _handle(self, sr):
+    if sr not in self._handles:
+      _lib.require_cuda()
+      L, hop = _extract_frame_step_length(sr, self.frame_length, self.step_length)
+      c = _lib.FeConfig()
+      c.sr, c.frame_len, c.hop = int(sr), L, hop
+      c.n_fft = max(256, 1 << int(np.ceil(np.log2(L))))
+      c.window = _WINDOWS[self.window]
+      c.remove_dc = 1 if (self._reader is not None and self._reader.remove_dc) else 0
+      c.preemph = float(self._preemph.coeff) if self._preemph is not None else 0.0
+      c.n_mels, c.fmin, c.fmax, c.top_db = 8, 0.0, float(sr // 2), 80.0
+      c.n_ceps, c.delta_width, c.delta_order, c.vad_kind = 0, 9, 0, 0
+      c.vad_nmix, c.vad_iters, c.vad_smooth, c.vad_mode = 3, 25, 0, 2.0
+      c.padding = 1 if self.padding else 0
+      h = ctypes.c_void_p()
+      _lib.check(_lib.load().odin_fe_create(ctypes.byref(c), ctypes.byref(h)))
+      self._handles[sr] = (h, c)
+    return self._handles[sr]
+
+  def __del__(self):
+    try:
+      for h, _ in self._handles.values():
+        _lib.load().odin_fe_destroy(h)
+      self._handles = {}
+    except Exception:
+      pass
+
+  def transform(self, X):
+    import torch
+    if isinstance(X, ExtractorSignal) or X is None or self._reader is None:
+      sig = self._check_input(X)
+      if sig is not None:
+        return sig
+    d = self._reader._load(X) if self._reader is not None else X
+    raw, sr = np.asarray(d[self.input_name[0]]), int(d[self.input_name[1]])
+    lib = _lib.load()
+    h, cfg = self._handle(sr)
+    pcm = torch.from_numpy(np.ascontiguousarray(raw if raw.dtype == np.int16 else raw.astype(np.float32))).cuda()
+    so = np.array([0, raw.shape[0]], dtype=np.int64)
+    fo = np.zeros(2, dtype=np.int64)
+    _lib.check(lib.odin_fe_frame_offsets(h, _lib.as_i64_ptr(so), 1, _lib.as_i64_ptr(fo)))
+    frames = torch.empty((int(fo[1]), cfg.frame_len), dtype=torch.float32, device='cuda')
+    _lib.check(lib.odin_fe_frames(h, _lib.ptr(pcm), 0 if raw.dtype == np.int16 else 1, _lib.as_i64_ptr(so), 1,
+                                  _lib.ptr(frames), None, _lib.current_stream()))
+    win = (ctypes.c_double * cfg.frame_len)()
+    _lib.check(lib.odin_fe_get_table(h, 0, win, cfg.frame_len))
+    scale = float(np.sqrt(1.0 / np.sum(np.frombuffer(win, dtype=np.float64))**2))
+    return self._merge_output(d if isinstance(d, Mapping) else None, {self.output_name: frames.cpu().numpy(), 'scale': scale})
+
+  def _transform(self, X):
+    _no_cpu(self)
+
+
+class CalculateEnergy(Extractor):
+  """speech.py:623-649: `[T, 1]` float32 (log) energy of explicit frames (signal.get_energy, signal.py:1421-1440)."""
+
+  def __init__(self, log=True, input_name='frames', output_name='energy'):
+    super(CalculateEnergy, self).__init__(input_name=str(input_name), output_name=str(output_name))
+    self.log = bool(log)
+
+  def _transform(self, X):
+    import torch
+    _lib.require_cuda()
+    frames = torch.from_numpy(np.ascontiguousarray(X[self.input_name], dtype=np.float32)).cuda()
+    e = torch.empty(frames.shape[0], dtype=torch.float32, device='cuda')
+    _lib.check(_lib.load().odin_feat_energy(_lib.ptr(frames), _lib.ptr(e), frames.shape[0], frames.shape[1],
+                                            1 if self.log else 0, _lib.current_stream()))
+    return {self.output_name: e.cpu().numpy()[:, None]}
+
+
+def _ragged_feature_call(Xs, names, fn):
+  """Packs feature `name` of every live input into one ragged [T, dim] batch per (name, dim), runs
+  `fn(d_x, dim, frame_offsets) -> CUDA tensor [T, out_dim]` and scatters the rows back."""
+  import torch
+  results = [dict(x) if isinstance(x, Mapping) else x for x in Xs]
+  live = [i for i, x in enumerate(Xs) if isinstance(x, Mapping)]
+  for name in names:
+    groups = {}
+    for i in live:
+      groups.setdefault(np.asarray(Xs[i][name]).shape[1], []).append(i)
+    for dim, idxs in groups.items():
+      mats = [np.ascontiguousarray(Xs[i][name], dtype=np.float32) for i in idxs]
+      off = np.zeros(len(mats) + 1, dtype=np.int64)
+      np.cumsum([m.shape[0] for m in mats], out=off[1:])
+      y = fn(torch.from_numpy(np.concatenate(mats, 0)).cuda(), dim, off).cpu().numpy()
+      for j, i in enumerate(idxs):
+        results[i][name] = y[off[j]:off[j + 1]].copy()
+  return results
+
+
+class RASTAfilter(Extractor):
+  """speech.py:1483-1533: RASTA band-pass along time (signal.rastafilt) and, when `sdc >= 1`, shifted delta
+  coefficients appended (signal.shifted_deltas with N = k = n_ceps, P = 3) -> float32."""
+
+  def __init__(self, rasta=True, sdc=1, input_name='mfcc', output_name=None):
+    super(RASTAfilter, self).__init__(input_name=as_tuple(input_name, t=str), output_name=output_name)
+    self.rasta = bool(rasta)
+    self.sdc = int(sdc)
+
+  def transform_batch(self, Xs):
+    _lib.require_cuda()
+    import torch
+    lib = _lib.load()
+    Xs = list(Xs)
+    checked = [self._check_input(x) for x in Xs]
+
+    def fn(d_x, dim, off):
+      w = dim + dim * dim if self.sdc >= 1 else dim
+      y = torch.empty((d_x.shape[0], w), dtype=torch.float32, device='cuda')
+      _lib.check(lib.odin_feat_rasta_sdc(_lib.ptr(d_x), _lib.ptr(y), dim, _lib.as_i64_ptr(off), len(off) - 1,
+                                         1 if self.rasta else 0, max(self.sdc, 0), _lib.current_stream()))
+      return y
+
+    live = [x if c is None else None for x, c in zip(Xs, checked)]
+    outs = _ragged_feature_call(live, self.input_name, fn)
+    names = as_tuple(self.output_name, t=str) if self.output_name is not None else self.input_name
+    res = []
+    for x, c, o in zip(Xs, checked, outs):
+      if c is not None:
+        res.append(c)
+        continue
+      res.append(self._merge_output(x, {on: o[n] for n, on in zip(self.input_name, names)}))
+    return res
 
   def transform(self, X):
     return self.transform_batch([X])[0]

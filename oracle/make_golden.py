@@ -230,6 +230,34 @@ def cmvn_fixtures():
   print("wrote cmvn.npz (%d cases)" % k)
 
 
+def variants_fixtures():
+  """Framing + CalculateEnergy, RASTAfilter (+ shifted deltas) and StackFeatures from the reference
+  (speech.py:569-649, 1483-1533; base.py:724-771)."""
+  pp, _ = ref_shim.load_frontend()
+  sp, base = pp.speech, pp.base
+  blob = {}
+  raw = synth.speech_like(801, 0.45, 16000, seed=19)
+  for tag, padding in (("nopad", False), ("pad", True)):
+    X = ref_shim.run_pipeline([sp.AudioReader(remove_dc=True), sp.PreEmphasis(0.97),
+                               sp.Framing(0.025, 0.010, window="hamm", padding=padding), sp.CalculateEnergy(log=True)],
+                              {"raw": raw, "sr": 16000})
+    blob["fr_%s_frames" % tag] = X["frames"].astype(np.float32)
+    blob["fr_%s_energy" % tag] = X["energy"]
+    blob["fr_%s_scale" % tag] = np.float64(X["scale"])
+  blob["fr_pcm"] = raw
+  rng = np.random.RandomState(23)
+  for i, (T, F_) in enumerate([(61, 20), (5, 7), (200, 13)]):
+    x = np.cumsum(rng.randn(T, F_), axis=0).astype(np.float32) * 0.3 + rng.randn(T, F_).astype(np.float32)
+    blob["m%d_x" % i] = x
+    blob["m%d_rasta_sdc" % i] = sp.RASTAfilter(rasta=True, sdc=1, input_name="mfcc").transform({"mfcc": x})["mfcc"]
+    blob["m%d_rasta" % i] = sp.RASTAfilter(rasta=True, sdc=0, input_name="mfcc").transform({"mfcc": x})["mfcc"]
+    blob["m%d_sdc2" % i] = sp.RASTAfilter(rasta=False, sdc=2, input_name="mfcc").transform({"mfcc": x})["mfcc"]
+    blob["m%d_stack3" % i] = base.StackFeatures(3, input_name="mfcc").transform({"mfcc": x.copy()})["mfcc"]
+  blob["n_mat"] = np.int64(3)
+  np.savez_compressed(os.path.join(OUT, "variants.npz"), **blob)
+  print("wrote variants.npz")
+
+
 def _tmat_problem(seed=3, D=6, M=8, n_files=40):
   """Synthetic per-utterance statistics shaped like GMM.transform output (gmm_tmat.py:708-767)."""
   rng = np.random.RandomState(seed)
@@ -281,7 +309,10 @@ if __name__ == "__main__":
     spectra_fixtures()
   elif len(sys.argv) > 1 and sys.argv[1] == "tmat":
     tmat_fixtures()
+  elif len(sys.argv) > 1 and sys.argv[1] == "variants":
+    variants_fixtures()
   else:
+    variants_fixtures()
     tmat_fixtures()
     spectra_fixtures()
     frontend_fixtures()

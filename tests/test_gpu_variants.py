@@ -1,0 +1,55 @@
+"""GPU parity of the feature-matrix extractors of SURVEY 8f-3 (Framing, CalculateEnergy, RASTAfilter with
+shifted deltas, StackFeatures) against the reference's golden outputs (tests/golden/variants.npz) and the
+oracle on ragged batches."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, relmax
+from oracle import frontend as F
+
+pytestmark = pytest.mark.gpu
+
+
+def test_framing_and_energy_golden():
+  from odin_b200 import preprocessing as pp
+  g = np.load(os.path.join(GOLDEN, "variants.npz"))
+  for tag, padding in (("nopad", False), ("pad", True)):
+    pipe = pp.make_pipeline([pp.AudioReader(remove_dc=True), pp.PreEmphasis(0.97),
+                             pp.Framing(0.025, 0.010, window="hamm", padding=padding), pp.CalculateEnergy(log=True)])
+    X = pipe.transform({"raw": g["fr_pcm"], "sr": 16000})
+    assert X["frames"].shape == g["fr_%s_frames" % tag].shape and X["frames"].dtype == np.float32
+    assert relmax(X["frames"], g["fr_%s_frames" % tag]) < 1e-6
+    assert abs(X["scale"] - float(g["fr_%s_scale" % tag])) < 1e-15
+    assert X["energy"].shape == g["fr_%s_energy" % tag].shape
+    assert relmax(X["energy"], g["fr_%s_energy" % tag]) < 1e-6
+  # the fused kernel's own energy output (odin_fe_frames with d_energy) agrees with CalculateEnergy
+  lin = pp.CalculateEnergy(log=False).transform({"frames": g["fr_nopad_frames"]})["energy"]
+  assert relmax(np.log(lin), g["fr_nopad_energy"]) < 1e-6
+
+
+def test_rasta_sdc_stack_golden_and_ragged():
+  from odin_b200 import preprocessing as pp
+  g = np.load(os.path.join(GOLDEN, "variants.npz"))
+  n = int(g["n_mat"])
+  xs = [g["m%d_x" % i] for i in range(n)]
+  for key, ex in (("rasta_sdc", pp.RASTAfilter(True, 1, "mfcc")), ("rasta", pp.RASTAfilter(True, 0, "mfcc")),
+                  ("sdc2", pp.RASTAfilter(False, 2, "mfcc")), ("stack3", pp.StackFeatures(3, "mfcc"))):
+    # one at a time and as one ragged batch (matrices of different widths go to different launches)
+    single = [ex.transform({"mfcc": x})["mfcc"] for x in xs]
+    batch = [o["mfcc"] for o in ex.transform_batch([{"mfcc": x} for x in xs])]
+    for i in range(n):
+      ref = g["m%d_%s" % (i, key)]
+      assert single[i].shape == ref.shape and single[i].dtype == np.float32, (key, i)
+      assert relmax(single[i], ref) < 1e-6, (key, i, relmax(single[i], ref))
+      assert np.array_equal(single[i], batch[i]), (key, i)
+  # same width, ragged lengths, against the oracle
+  rng = np.random.RandomState(4)
+  mats = [rng.randn(T, 12).astype(np.float32) for T in (1, 2, 4, 5, 9, 150, 33)]
+  outs = pp.RASTAfilter(True, 1, "mfcc").transform_batch([{"mfcc": m} for m in mats])
+  for m, o in zip(mats, outs):
+    assert relmax(o["mfcc"], F.rasta_sdc(m, True, 1)) < 1e-6
+  outs = pp.StackFeatures(2, "mfcc").transform_batch([{"mfcc": m} for m in mats])
+  for m, o in zip(mats, outs):
+    assert np.array_equal(o["mfcc"], F.stack_context(m, 2))

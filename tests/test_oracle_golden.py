@@ -216,3 +216,20 @@ def test_tmatrix_golden():
   assert relmax(Tm, g["T3"]) < 1e-9
   assert np.allclose(hist, g["llk_hist"], rtol=1e-9)
   assert relmax(OT.ivector(Z, F, T_invS, T_invS_Tt), g["ivec"]) < 1e-9
+
+
+def test_feature_variants_golden():
+  """Framing / CalculateEnergy / RASTAfilter (+ shifted deltas) / StackFeatures: oracle vs the reference's outputs."""
+  g = np.load(os.path.join(GOLDEN, "variants.npz"))
+  y = F.pre_emphasis(F.read_audio(g["fr_pcm"], True), 0.97)
+  for tag, padding in (("nopad", False), ("pad", True)):
+    fr, scale = F.framing(y, 16000, 0.025, 0.010, "hamm", padding)
+    assert fr.shape == g["fr_%s_frames" % tag].shape
+    assert relmax(fr, g["fr_%s_frames" % tag]) < 1e-6 and abs(scale - float(g["fr_%s_scale" % tag])) < 1e-15
+    assert np.array_equal(F.frame_energy(fr), g["fr_%s_energy" % tag])
+  for i in range(int(g["n_mat"])):
+    x = g["m%d_x" % i]
+    assert relmax(F.rasta_sdc(x, True, 1), g["m%d_rasta_sdc" % i]) < 1e-6
+    assert relmax(F.rasta_sdc(x, True, 0), g["m%d_rasta" % i]) < 1e-6
+    assert relmax(F.rasta_sdc(x, False, 2), g["m%d_sdc2" % i]) < 1e-6
+    assert np.array_equal(F.stack_context(x, 3), g["m%d_stack3" % i])
