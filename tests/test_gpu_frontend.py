@@ -273,3 +273,25 @@ def test_run_host_packed_matches_run_packed():
     assert np.array_equal(out["frame_offsets"], ref["frame_offsets"])
     for k in ("feat", "sad", "mspec", "energy", "c0"):
       assert torch.equal(out[k], ref[k].cpu()), (n_chunks, k)
+
+
+@pytest.mark.parametrize("n_fft,frame_length,force_stockham", [(2048, 0.064, False), (512, 0.025, True), (256, 0.016, False)])
+def test_other_fft_sizes_vs_oracle(n_fft, frame_length, force_stockham, monkeypatch):
+  """n_fft 2048 runs on the three-pass Stockham kernel (also forced at 512 for an A/B of the two FFT kernels),
+  256 on the four-step kernel with four frame pairs per warp."""
+  from odin_b200 import preprocessing as pp
+  if force_stockham:
+    monkeypatch.setenv("ODIN_FE_STOCKHAM", "1")
+  pipe = pp.make_pipeline([pp.AudioReader(remove_dc=True), pp.PreEmphasis(0.97),
+                           pp.STFTExtractor(frame_length, 0.010, n_fft=n_fft, window="hamm", energy=True),
+                           pp.PowerSpecExtractor(2.0), pp.MelsSpecExtractor(40, fmin=64, fmax=8000),
+                           pp.MFCCsExtractor(20, first_coef_energy=True), pp.DeltaExtractor("mfcc", order=(0, 1, 2)),
+                           pp.SADgmm(3, smooth_window=3, input_name="stft_energy")])
+  utts = synth.utterance_batch(7, 0.4, 1.6, sr=16000, seed=91)
+  outs = pipe.transform_batch([{"raw": u, "sr": 16000} for u in utts])
+  for u, o in zip(utts, outs):
+    r = F.extract(u, 16000, frame_length, 0.010, n_fft, n_mels=40, fmin=64, fmax=8000, vad="gmm")
+    assert o["mfcc"].shape == r["mfcc"].shape
+    assert relmax(o["mspec"], r["mspec"]) < TOL_FEAT and relmax(o["mfcc"], r["mfcc"]) < TOL_FEAT
+    assert relmax(o["stft_energy"], r["stft_energy"]) < 1e-6
+    assert np.array_equal(o["sad"], r["sad"])
