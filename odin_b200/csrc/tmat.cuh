@@ -22,6 +22,8 @@ struct odin_tmat {
   double* d_B1 = nullptr;      // [cap, tv]
   double* d_Ex = nullptr;      // [cap, tv]
   double* d_llk = nullptr;     // [cap]
+  double* d_ws = nullptr;      // split-K workspace of the skinny B1 product
+  int64_t ws_cap = 0;
 };
 
 namespace odin {

@@ -69,6 +69,8 @@ __global__ void __launch_bounds__(256) tmat_refresh_kernel(const double* __restr
 // ---------------------------------------------------------------------------
 constexpr int GB = 64, GK = 16;
 
+// gridDim.z > 1: split-K -- slice z of the K range writes its partial product (beta ignored) to C + z * M * ldc of a
+// workspace; tmat_splitk_reduce_kernel adds the slices in a fixed order.
 __global__ void __launch_bounds__(256) tmat_gemm_kernel(int M, int N, int K, const double* __restrict__ A, int64_t sai,
                                                         int64_t sak, const double* __restrict__ B, int64_t sbk,
                                                         int64_t sbj, double* __restrict__ C, int64_t ldc, double beta) {
@@ -81,7 +83,15 @@ __global__ void __launch_bounds__(256) tmat_gemm_kernel(int M, int N, int K, con
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-  for (int k0 = 0; k0 < K; k0 += GK) {
+  int kbeg = 0, kend = K;
+  if (gridDim.z > 1) {
+    const int per = ((K + (int)gridDim.z - 1) / (int)gridDim.z + GK - 1) / GK * GK;
+    kbeg = (int)blockIdx.z * per;
+    kend = min(K, kbeg + per);
+    C += (int64_t)blockIdx.z * M * ldc;
+    beta = 0.0;
+  }
+  for (int k0 = kbeg; k0 < kend; k0 += GK) {
     // tile loads: consecutive threads walk the unit-stride dimension of each operand
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -89,11 +99,11 @@ __global__ void __launch_bounds__(256) tmat_gemm_kernel(int M, int N, int K, con
       int ii, kk;
       if (sak == 1) { kk = idx & (GK - 1); ii = idx >> 4; } else { ii = idx & (GB - 1); kk = idx >> 6; }
       const int gi = i0 + ii, gk = k0 + kk;
-      As[kk][ii] = (gi < M && gk < K) ? A[(int64_t)gi * sai + (int64_t)gk * sak] : 0.0;
+      As[kk][ii] = (gi < M && gk < kend) ? A[(int64_t)gi * sai + (int64_t)gk * sak] : 0.0;
       int jj, kb;
       if (sbk == 1) { kb = idx & (GK - 1); jj = idx >> 4; } else { jj = idx & (GB - 1); kb = idx >> 6; }
       const int gj = j0 + jj, gkb = k0 + kb;
-      Bs[kb][jj] = (gj < N && gkb < K) ? B[(int64_t)gkb * sbk + (int64_t)gj * sbj] : 0.0;
+      Bs[kb][jj] = (gj < N && gkb < kend) ? B[(int64_t)gkb * sbk + (int64_t)gj * sbj] : 0.0;
     }
     __syncthreads();
 #pragma unroll
@@ -124,12 +134,40 @@ __global__ void __launch_bounds__(256) tmat_gemm_kernel(int M, int N, int K, con
   }
 }
 
+__global__ void __launch_bounds__(256) tmat_splitk_reduce_kernel(const double* __restrict__ ws, int splits, int64_t MN,
+                                                                 int N, double* __restrict__ C, int64_t ldc, double beta) {
+  for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < MN; e += (int64_t)gridDim.x * 256) {
+    double acc = 0.0;
+    for (int z = 0; z < splits; ++z) acc += ws[(int64_t)z * MN + e];
+    double* c = C + (e / N) * ldc + (e % N);
+    *c = (beta == 0.0) ? acc : fma(beta, *c, acc);
+  }
+}
+
+// ws / ws_cap: optional split-K workspace (doubles).  Split-K is used when the output has too few tiles to fill
+// the GPU and K is long (B1 = F T_invS^T: 47 tiles, K = M D = 30 720 at the config-5 scale).
 static int gemm(int M, int N, int K, const double* A, int64_t sai, int64_t sak, const double* B, int64_t sbk, int64_t sbj,
-                double* C, int64_t ldc, double beta, cudaStream_t st) {
+                double* C, int64_t ldc, double beta, cudaStream_t st, double* ws = nullptr, int64_t ws_cap = 0) {
   if (M <= 0 || N <= 0) return ODIN_OK;
   dim3 grid((unsigned)ceil_div(N, GB), (unsigned)ceil_div(M, GB));
-  tmat_gemm_kernel<<<grid, 256, 0, st>>>(M, N, K, A, sai, sak, B, sbk, sbj, C, ldc, beta);
+  const int64_t tiles = (int64_t)grid.x * grid.y;
+  int splits = 1;
+  if (ws != nullptr && tiles < 2 * sm_count() && K >= 1024) {
+    splits = (int)std::min<int64_t>(std::min<int64_t>(4 * sm_count() / tiles, K / 256), 32);
+    while (splits > 1 && (int64_t)splits * M * N > ws_cap) --splits;
+  }
+  if (splits <= 1) {
+    tmat_gemm_kernel<<<grid, 256, 0, st>>>(M, N, K, A, sai, sak, B, sbk, sbj, C, ldc, beta);
+    ODIN_LAUNCH_CHECK("tmat_gemm_kernel");
+    return ODIN_OK;
+  }
+  grid.z = (unsigned)splits;
+  tmat_gemm_kernel<<<grid, 256, 0, st>>>(M, N, K, A, sai, sak, B, sbk, sbj, ws, N, 0.0);
   ODIN_LAUNCH_CHECK("tmat_gemm_kernel");
+  const int64_t MN = (int64_t)M * N;
+  tmat_splitk_reduce_kernel<<<(unsigned)std::min<int64_t>(ceil_div<int64_t>(MN, 256), sm_count() * 8), 256, 0, st>>>(
+      ws, splits, MN, N, C, ldc, beta);
+  ODIN_LAUNCH_CHECK("tmat_splitk_reduce_kernel");
   return ODIN_OK;
 }
 
@@ -454,13 +492,15 @@ int tmat_refresh(odin_tmat* t, cudaStream_t st) {
 
 static int reserve_files(odin_tmat* t, int64_t n) {
   if (n <= t->cap_files) return ODIN_OK;
-  cudaFree(t->d_L1); cudaFree(t->d_B1); cudaFree(t->d_Ex); cudaFree(t->d_llk);
-  t->d_L1 = t->d_B1 = t->d_Ex = t->d_llk = nullptr;
+  cudaFree(t->d_L1); cudaFree(t->d_B1); cudaFree(t->d_Ex); cudaFree(t->d_llk); cudaFree(t->d_ws);
+  t->d_L1 = t->d_B1 = t->d_Ex = t->d_llk = t->d_ws = nullptr;
   t->cap_files = 0;
   ODIN_CUDA_CHECK(cudaMalloc(&t->d_L1, sizeof(double) * (size_t)n * t->t2));
   ODIN_CUDA_CHECK(cudaMalloc(&t->d_B1, sizeof(double) * (size_t)n * t->tv));
   ODIN_CUDA_CHECK(cudaMalloc(&t->d_Ex, sizeof(double) * (size_t)n * t->tv));
   ODIN_CUDA_CHECK(cudaMalloc(&t->d_llk, sizeof(double) * (size_t)n));
+  t->ws_cap = (int64_t)16 * n * t->tv;
+  ODIN_CUDA_CHECK(cudaMalloc(&t->d_ws, sizeof(double) * (size_t)t->ws_cap));
   t->cap_files = n;
   return ODIN_OK;
 }
@@ -472,7 +512,8 @@ static int posterior_chunk(odin_tmat* t, const double* d_Z, const double* d_F, i
   // L1 = Z T_invS_Tt  [n, t2]
   if ((rc = gemm((int)n, t->t2, t->M, d_Z, t->M, 1, t->d_TinvSTt, t->t2, 1, t->d_L1, t->t2, 0.0, st))) return rc;
   // B1 = F T_invS^T   [n, tv]
-  if ((rc = gemm((int)n, t->tv, (int)t->MD, d_F, t->MD, 1, t->d_TinvS, 1, t->MD, t->d_B1, t->tv, 0.0, st))) return rc;
+  if ((rc = gemm((int)n, t->tv, (int)t->MD, d_F, t->MD, 1, t->d_TinvS, 1, t->MD, t->d_B1, t->tv, 0.0, st, t->d_ws, t->ws_cap)))
+    return rc;
   FileArgs a{};
   a.tv = t->tv; a.n = n; a.L1 = t->d_L1; a.B1 = t->d_B1; a.Ex = d_ex_out; a.llk = training ? t->d_llk : nullptr;
   a.want_exx = training ? 1 : 0; a.flag = t->d_flag;

@@ -2,7 +2,7 @@
 8 kHz synthetic digits -> MFCC (+c0 energy, deltas, SADthreshold, recipe of
 examples/fsdd_ivec.py:80-106 minus AcousticNorm / AsType) -> FeatureProcessor store with
 name -> (start, end) indices -> 512-mix UBM statistics -> per-utterance Z [n, 512] and
-F-hat [n, 512*60] (the i-vector input of gmm_tmat.py:769-913).
+F-hat [n, 512*60] (the i-vector input of gmm_tmat.py:769-913) -> T-matrix EM and i-vectors (gmm_tmat.py:1343-2090).
 Bit-exact: frame counts, `sad`, indices.  <= 1e-4 on MFCC, <= 1e-3 on Z / F-hat."""
 import os
 
@@ -78,6 +78,21 @@ def test_fsdd_style_pipeline(tmp_path):
   s0, e0 = indices["mfcc"][names[0]]
   z0, f0 = OG.transform(X[s0:e0], g.mean, g.sigma, g.w, compute_dtype=np.float64)
   assert relmax(Fu[0].reshape(M, 60), np.asarray(f0).reshape(M, 60)) < 1e-3
+  # ---- i-vector extractor on those statistics (examples/fsdd_ivec.py:229-240: Tmatrix.fit on (Z, F), then
+  # transform): 3 EM iterations of a tv = 16 model on the GPU vs the oracle ON THE SAME statistics; rows of T
+  # and i-vector coordinates are compared up to the sign the orthogonalisation leaves open
+  from odin_b200.ml import Tmatrix
+  from oracle import tmatrix as OT
+  t = Tmatrix(16, g, niter=3)
+  t.fit((Zu, Fu))
+  Tm, T_invS, T_invS_Tt, hist = OT.fit(Zu.astype(np.float64), Fu.astype(np.float64), 16, np.asarray(g.sigma), 3)
+  assert np.allclose(t._llk_hist, hist, rtol=1e-6)
+  a, sa = OT.sign_normalise(t.Tm)
+  b, sb = OT.sign_normalise(Tm)
+  assert relmax(a, b) < 1e-5, relmax(a, b)
+  iv = t.transform((Zu, Fu))
+  ref_iv = OT.ivector(Zu.astype(np.float64), Fu.astype(np.float64), T_invS, T_invS_Tt)
+  assert iv.shape == (n_utt, 16) and relmax(iv * sa[None, :], ref_iv * sb[None, :]) < 1e-5
 
 
 def test_fsdd_recipe_with_normalisation_tail():
