@@ -726,6 +726,7 @@ void odin_tmat_destroy(odin_tmat_t* t) {
   cudaFree(t->d_Tm); cudaFree(t->d_TinvS); cudaFree(t->d_Sigma); cudaFree(t->d_TinvSTt); cudaFree(t->d_U);
   cudaFree(t->d_perm); cudaFree(t->d_flag); cudaFree(t->d_L1); cudaFree(t->d_B1); cudaFree(t->d_Ex); cudaFree(t->d_llk);
   cudaFree(t->d_ws);
+  if (t->sweep_graph) cudaGraphExecDestroy((cudaGraphExec_t)t->sweep_graph);
   delete t;
 }
 

@@ -23,13 +23,18 @@
 //   tmat_mindiv_kernel    sum of LU over mixtures / nframes -> upper Cholesky factor
 //   tmat_jacobi_kernel    one-sided (Hestenes) Jacobi on the ROWS of T: rotating rows until they are mutually
 //                         orthogonal yields U^T T = diag(s) V^T directly, without forming T T^T or U; one launch
-//                         per round of a round-robin tournament (tv / 2 disjoint pairs per round)
+//                         per round of a round-robin tournament (tv / 2 disjoint pairs per round, a 4-CTA
+//                         cluster per pair with the dot products reduced through distributed shared memory)
 #include <algorithm>
 #include <new>
 #include <vector>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "tmat.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace odin {
 
@@ -375,35 +380,55 @@ __global__ void __launch_bounds__(256) tmat_mindiv_kernel(int tv, int nmix, cons
 // ---------------------------------------------------------------------------
 // one-sided Jacobi on the rows of W [tv, MD]: round `r` of a round-robin tournament over `np` players
 // ---------------------------------------------------------------------------
-constexpr int JT = 1024;   // threads per pair: the three dot products are latency-bound, so use the whole SM
+constexpr int JT = 1024;   // threads per CTA: the three dot products are latency-bound, so use the whole SM
+constexpr int JC = 4;      // CTAs (one cluster) per row pair: each takes a quarter of the columns
 
+// One CLUSTER of JC CTAs per row pair: every CTA forms the three partial dot products over its slice of the
+// columns, the partials meet through distributed shared memory (each CTA reads the JC slots in rank order, so
+// all CTAs of the cluster hold bit-identical sums and take the same decision), then every CTA rotates its slice.
 __global__ void __launch_bounds__(JT) tmat_jacobi_kernel(double* __restrict__ W, int tv, int64_t MD, int np, int r,
                                                          int* __restrict__ n_rot) {
-  const int tid = threadIdx.x, i = blockIdx.x;   // pair index 0 .. np/2 - 1
+  cg::cluster_group cl = cg::this_cluster();
+  const int nc = (int)cl.num_blocks(), rank = (int)cl.block_rank();
+  const int tid = threadIdx.x, i = blockIdx.x / nc;   // pair index 0 .. np/2 - 1
   int p, q;
   if (i == 0) { p = np - 1; q = r; }
   else { p = (r + i) % (np - 1); q = (r - i + (np - 1)) % (np - 1); }
-  if (p >= tv || q >= tv) return;   // the bye of an odd tournament
+  const bool bye = (p >= tv || q >= tv);   // the bye of an odd tournament (uniform over the cluster)
   if (p > q) { const int t = p; p = q; q = t; }
+  const int64_t per = (MD + nc - 1) / nc;
+  const int64_t j0 = per * rank, j1 = min(MD, j0 + per);
   double* wp = W + (int64_t)p * MD;
   double* wq = W + (int64_t)q * MD;
   double al = 0.0, be = 0.0, ga = 0.0;
-  for (int64_t j = tid; j < MD; j += JT) {
-    const double x = wp[j], y = wq[j];
-    al = fma(x, x, al); be = fma(y, y, be); ga = fma(x, y, ga);
-  }
+  if (!bye)
+    for (int64_t j = j0 + tid; j < j1; j += JT) {
+      const double x = wp[j], y = wq[j];
+      al = fma(x, x, al); be = fma(y, y, be); ga = fma(x, y, ga);
+    }
   __shared__ double red[3][JT / 32];
+  __shared__ double part[3];
   al = warp_sum(al); be = warp_sum(be); ga = warp_sum(ga);
   if ((tid & 31) == 0) { red[0][tid >> 5] = al; red[1][tid >> 5] = be; red[2][tid >> 5] = ga; }
   __syncthreads();
+  if (tid < 3) {
+    double t = 0.0;
+    for (int w = 0; w < JT / 32; ++w) t += red[tid][w];
+    part[tid] = t;
+  }
+  cl.sync();
   al = be = ga = 0.0;
-  for (int w = 0; w < JT / 32; ++w) { al += red[0][w]; be += red[1][w]; ga += red[2][w]; }
-  if (fabs(ga) <= 1e-15 * sqrt(al * be) || ga == 0.0) return;   // already orthogonal to working precision
-  if (tid == 0) atomicAdd(n_rot, 1);
+  for (int c = 0; c < nc; ++c) {
+    const double* rp = cl.map_shared_rank(part, c);
+    al += rp[0]; be += rp[1]; ga += rp[2];
+  }
+  cl.sync();   // nobody leaves (or overwrites part) while a neighbour still reads it
+  if (bye || fabs(ga) <= 1e-15 * sqrt(al * be) || ga == 0.0) return;   // already orthogonal to working precision
+  if (tid == 0 && rank == 0) atomicAdd(n_rot, 1);
   const double zeta = (be - al) / (2.0 * ga);
   const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
   const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
-  for (int64_t j = tid; j < MD; j += JT) {
+  for (int64_t j = j0 + tid; j < j1; j += JT) {
     const double x = wp[j], y = wq[j];
     wp[j] = c * x - s * y;
     wq[j] = s * x + c * y;
@@ -586,14 +611,47 @@ int tmat_mstep(odin_tmat* t, const double* d_acc, int min_div, int orthogonalize
   if (orthogonalize && t->tv > 1) {
     const int np = t->tv + (t->tv & 1);
     // sweeps until one of them rotates nothing (quadratic convergence: 6-9 sweeps in fp64), at most `sweeps`;
-    // the rotation counter is read back once per sweep (the M-step runs once per EM iteration)
+    // the rotation counter is read back once per sweep (the M-step runs once per EM iteration).  A sweep is
+    // np - 1 dependent launches of a few microseconds each, i.e. launch-bound: it is captured ONCE into a CUDA
+    // graph (the launches differ only in the round number) and replayed.
     int* d_rot = t->d_flag + 1;
-    for (int sweep = 0; sweep < sweeps; ++sweep) {
-      ODIN_CUDA_CHECK(cudaMemsetAsync(d_rot, 0, sizeof(int), st));
-      for (int r = 0; r < np - 1; ++r) {
-        tmat_jacobi_kernel<<<np / 2, JT, 0, st>>>(t->d_Tm, t->tv, t->MD, np, r, d_rot);
-        ODIN_LAUNCH_CHECK("tmat_jacobi_kernel");
+    if (t->sweep_graph == nullptr) {
+      cudaGraph_t graph = nullptr;
+      cudaStream_t cs = nullptr;   // the caller's stream may be the legacy default stream, which cannot be captured
+      ODIN_CUDA_CHECK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+      cudaError_t e_beg = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+      if (e_beg != cudaSuccess) {
+        cudaStreamDestroy(cs);
+        return set_error(ODIN_ECUDA, "cudaStreamBeginCapture: %s", cudaGetErrorString(e_beg));
       }
+      cudaError_t e_cap = cudaMemsetAsync(d_rot, 0, sizeof(int), cs);
+      for (int r = 0; r < np - 1 && e_cap == cudaSuccess; ++r) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(np / 2 * JC));
+        cfg.blockDim = dim3(JT);
+        cfg.stream = cs;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = JC; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        e_cap = cudaLaunchKernelEx(&cfg, tmat_jacobi_kernel, t->d_Tm, t->tv, t->MD, np, r, d_rot);
+      }
+      cudaError_t e_end = cudaStreamEndCapture(cs, &graph);
+      cudaStreamDestroy(cs);
+      if (e_cap != cudaSuccess || e_end != cudaSuccess || graph == nullptr) {
+        if (graph) cudaGraphDestroy(graph);
+        return set_error(ODIN_ECUDA, "capturing the Jacobi sweep: %s", cudaGetErrorString(e_cap != cudaSuccess ? e_cap : e_end));
+      }
+      cudaGraphExec_t exec = nullptr;
+      cudaError_t e_inst = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e_inst != cudaSuccess) return set_error(ODIN_ECUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e_inst));
+      t->sweep_graph = exec;
+    }
+    for (int sweep = 0; sweep < sweeps; ++sweep) {
+      ODIN_CUDA_CHECK(cudaGraphLaunch((cudaGraphExec_t)t->sweep_graph, st));
+      g_launches.fetch_add(np - 1, std::memory_order_relaxed);
       int h_rot = 0;
       ODIN_CUDA_CHECK(cudaMemcpyAsync(&h_rot, d_rot, sizeof(int), cudaMemcpyDeviceToHost, st));
       ODIN_CUDA_CHECK(cudaStreamSynchronize(st));
