@@ -3,3 +3,4 @@ Tmatrix, Ivector, PLDA, Scorer; the GMM-UBM half and the T-matrix / i-vector ext
 path)."""
 from .gmm import GMM  # noqa: F401
 from .tmat import Tmatrix  # noqa: F401
+from .ivector import Ivector  # noqa: F401

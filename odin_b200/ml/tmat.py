@@ -148,7 +148,7 @@ class Tmatrix(object):
     torch = _torch()
     if isinstance(A, torch.Tensor):
       return A.to(device='cuda', dtype=torch.float64).contiguous()
-    return torch.as_tensor(np.ascontiguousarray(A)).cuda().to(torch.float64)
+    return torch.from_numpy(np.array(A, copy=True)).cuda().to(torch.float64)   # (memmaps may be read-only)
 
   def _estep_device(self, Z, F):
     """-> packed CUDA statistics LU | RU | llk | nframes, all-reduced over the ranks."""

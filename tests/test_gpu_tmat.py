@@ -109,3 +109,37 @@ def test_limits_fail_loudly():
   sigma, _, _ = _problem(1, 4, 3, 5)
   with pytest.raises(_lib.OdinError):
     Tmatrix(129, _gmm_stub(sigma))
+
+
+def test_ivector_wrapper(tmp_path):
+  """odin.ml.Ivector surface (ivector.py:83-520): fit trains UBM + T-matrix and stores the models, transform returns
+  the i-vectors of new files; the numbers equal driving GMM and Tmatrix by hand."""
+  from odin_b200.ml import GMM, Ivector, Tmatrix
+  rng = np.random.RandomState(3)
+  D, n_utt = 8, 30
+  cents = rng.randn(4, D) * 3
+  lens = rng.randint(40, 90, size=n_utt)
+  off = np.concatenate([[0], np.cumsum(lens)])
+  X = np.concatenate([cents[rng.randint(0, 4, size=n)] + rng.randn(n, D) + 0.3 * rng.randn(1, D) for n in lens]).astype(np.float32)
+  indices = [("utt%02d" % i, (int(off[i]), int(off[i + 1]))) for i in range(n_utt)]
+  iv = Ivector(str(tmp_path / "ivec"), nmix=4, tv_dim=3, niter_gmm=3, niter_tmat=2)
+  iv.fit(X, indices=indices, extract_ivecs=True, keep_stats=False)
+  assert iv.is_fitted and os.path.exists(iv.gmm_path) and os.path.exists(iv.tmat_path)
+  assert not os.path.exists(iv.z_path) and os.path.exists(iv.ivec_path)
+  train_iv = np.load(iv.ivec_path)
+  out = np.asarray(iv.transform(X, indices=indices, name="again", save_ivecs=True))
+  assert out.shape == (n_utt, 3) and np.allclose(out, train_iv, rtol=1e-5, atol=1e-6)
+  assert os.path.exists(iv.get_i_path("again"))
+  # by hand: the same UBM schedule, statistics, T-matrix EM and extraction
+  g = GMM(nmix=4, nmix_start=1, niter=3)
+  g.fit((X, indices))
+  pz, pf = str(tmp_path / "z.npy"), str(tmp_path / "f.npy")
+  g.transform_to_disk(X, indices, pathZ=pz, pathF=pf)
+  t = Tmatrix(3, g, niter=2)
+  t.fit((np.load(pz), np.load(pf)))
+  ref = t.transform((np.load(pz), np.load(pf)))
+  assert np.allclose(out, ref.astype(np.float32), rtol=1e-4, atol=1e-5)
+  # a reloaded wrapper finds its pickled models
+  iv2 = Ivector(str(tmp_path / "ivec"), nmix=4, tv_dim=3)
+  assert iv2.is_fitted
+  assert np.allclose(np.asarray(iv2.transform(X, indices=indices)), out, rtol=1e-5, atol=1e-6)
