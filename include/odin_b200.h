@@ -256,7 +256,8 @@ int64_t odin_launch_count(void);
 /* ------------------------------------------------------------------------- */
 typedef struct odin_tmat odin_tmat_t;
 
-/* tv_dim <= 128, feat_dim <= 64 in this version (the tv x tv systems are factorised in shared memory). */
+/* tv_dim <= 1024, feat_dim <= 256.  Up to tv_dim ~ 150 the tv x tv systems are factorised in shared memory; larger
+ * ones run from per-CTA slabs of global memory with the same (unblocked) algorithms, i.e. correct but slow. */
 int odin_tmat_create(int32_t tv_dim, int32_t nmix, int32_t feat_dim, odin_tmat_t** out);
 void odin_tmat_destroy(odin_tmat_t* t);
 

@@ -696,7 +696,7 @@ int odin_tmat_create(int32_t tv_dim, int32_t nmix, int32_t feat_dim, odin_tmat_t
   if (!out || tv_dim <= 0 || nmix <= 0 || feat_dim <= 0) return set_error(ODIN_EINVAL, "bad argument");
   *out = nullptr;
   if (tv_dim > TMAT_MAX_TV || feat_dim > TMAT_MAX_D)
-    return set_error(ODIN_EINVAL, "tv_dim must be <= %d and feat_dim <= %d in this version", TMAT_MAX_TV, TMAT_MAX_D);
+    return set_error(ODIN_EINVAL, "tv_dim must be <= %d and feat_dim <= %d", TMAT_MAX_TV, TMAT_MAX_D);
   int rc = require_device();
   if (rc) return rc;
   odin_tmat* t = new (std::nothrow) odin_tmat();
@@ -725,7 +725,7 @@ void odin_tmat_destroy(odin_tmat_t* t) {
   if (!t) return;
   cudaFree(t->d_Tm); cudaFree(t->d_TinvS); cudaFree(t->d_Sigma); cudaFree(t->d_TinvSTt); cudaFree(t->d_U);
   cudaFree(t->d_perm); cudaFree(t->d_flag); cudaFree(t->d_L1); cudaFree(t->d_B1); cudaFree(t->d_Ex); cudaFree(t->d_llk);
-  cudaFree(t->d_ws);
+  cudaFree(t->d_ws); cudaFree(t->d_gws);
   if (t->sweep_graph) cudaGraphExecDestroy((cudaGraphExec_t)t->sweep_graph);
   delete t;
 }

@@ -3,8 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-constexpr int TMAT_MAX_TV = 128;   // the tv x tv systems live in one shared-memory square (fp64)
-constexpr int TMAT_MAX_D = 64;
+constexpr int TMAT_MAX_TV = 1024;  // tv <= ~150: the tv x tv systems live in one shared-memory square (fp64); larger ones
+                                   // in per-CTA slabs of global memory (unblocked, slow: DESIGN.md 4.3)
+constexpr int TMAT_MAX_D = 256;
 
 struct odin_tmat {
   int tv = 0, M = 0, D = 0, t2 = 0;
@@ -25,6 +26,8 @@ struct odin_tmat {
   double* d_llk = nullptr;     // [cap]
   double* d_ws = nullptr;      // split-K workspace of the skinny B1 product
   int64_t ws_cap = 0;
+  double* d_gws = nullptr;     // per-CTA squares in global memory for sizes beyond shared memory
+  size_t gws_cap = 0;
 };
 
 namespace odin {

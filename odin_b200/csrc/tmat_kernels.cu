@@ -46,11 +46,14 @@ __device__ __forceinline__ int tril_idx(int a, int b) { return a * (a + 1) / 2 +
 // cached statistics
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) tmat_refresh_kernel(const double* __restrict__ Tm, const double* __restrict__ Sigma,
-                                                           int tv, int D, int64_t MD, double* __restrict__ T_invS,
-                                                           double* __restrict__ T_invS_Tt) {
-  extern __shared__ double sm[];   // T2 block [tv][D + 1]
-  const int m = blockIdx.x, tid = threadIdx.x;
+                                                           int tv, int D, int64_t MD, int M, double* __restrict__ T_invS,
+                                                           double* __restrict__ T_invS_Tt, double* __restrict__ gws) {
+  extern __shared__ double dyn_sm[];   // T2 block [tv][D + 1] (or in the global workspace for large tv)
+  const int tid = threadIdx.x;
   const int P = D + 1;
+  double* sm = gws ? gws + (size_t)blockIdx.x * tv * P : dyn_sm;
+  for (int m = blockIdx.x; m < M; m += gridDim.x) {
+  __syncthreads();
   for (int i = tid; i < tv * D; i += 256) {
     const int r = i / D, d = i - r * D;
     const int64_t g = (int64_t)r * MD + (int64_t)m * D + d;
@@ -67,6 +70,7 @@ __global__ void __launch_bounds__(256) tmat_refresh_kernel(const double* __restr
     for (int d = 0; d < D; ++d) acc = fma(sm[a * P + d], sm[b * P + d], acc);
     T_invS_Tt[(int64_t)m * t2 + tril_idx(a, b)] = acc;
   }
+  }  // mixture loop
 }
 
 // ---------------------------------------------------------------------------
@@ -217,12 +221,14 @@ struct FileArgs {
   double* llk;       // [n] nullable
   int want_exx;
   int* flag;
+  double* gws;       // nullable: per-CTA squares in global memory (large tv)
 };
 
 __global__ void __launch_bounds__(256) tmat_file_kernel(FileArgs a) {
-  extern __shared__ double sm[];
+  extern __shared__ double dyn_sm[];
   const int n = a.tv, P = n + 1, tid = threadIdx.x;
-  double* S = sm;              // [n][P]
+  // the square lives in shared memory up to tv ~ 160 and in a per-CTA slab of global memory (L2) beyond
+  double* S = a.gws ? a.gws + (size_t)blockIdx.x * ((size_t)n * P + 3 * n) : dyn_sm;   // [n][P]
   double* dg = S + n * P;      // [n] diagonal of the Cholesky factor, later diagonal of Cxx
   double* Bv = dg + n;         // [n]
   double* Ev = Bv + n;         // [n]
@@ -247,8 +253,7 @@ __global__ void __launch_bounds__(256) tmat_file_kernel(FileArgs a) {
     // (strict upper triangle), the diagonal of G moves to dg[] and 1 / G[j][j] takes its place
     for (int i = tid; i < n; i += 256) dg[i] = S[i * P + i];
     __syncthreads();
-    if (tid < n) {
-      const int j = tid;
+    for (int j = tid; j < n; j += 256) {
       S[j * P + j] = 1.0 / dg[j];
       for (int i = j + 1; i < n; ++i) {
         double acc = 0.0;
@@ -308,13 +313,15 @@ __global__ void __launch_bounds__(256) tmat_file_kernel(FileArgs a) {
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) tmat_solve_kernel(int tv, int D, int64_t MD, const double* __restrict__ LU,
                                                          const double* __restrict__ RU, double* __restrict__ Tm,
-                                                         int* flag) {
-  extern __shared__ double sm[];
-  const int n = tv, P = n + 1, Q = D + 1, tid = threadIdx.x, m = blockIdx.x;
-  double* S = sm;            // [n][P]
+                                                         int* flag, int M, double* __restrict__ gws) {
+  extern __shared__ double dyn_sm[];
+  const int n = tv, P = n + 1, Q = D + 1, tid = threadIdx.x;
+  double* S = gws ? gws + (size_t)blockIdx.x * ((size_t)n * P + (size_t)n * Q) : dyn_sm;   // [n][P]
   double* R = S + n * P;     // [n][Q]
   __shared__ int s_flag;
   const int t2 = n * (n + 1) / 2;
+  for (int m = blockIdx.x; m < M; m += gridDim.x) {
+  __syncthreads();
   if (tid == 0) s_flag = 0;
   for (int e = tid; e < n * n; e += 256) {
     const int i = e / n, j = e - i * n;
@@ -327,10 +334,9 @@ __global__ void __launch_bounds__(256) tmat_solve_kernel(int tv, int D, int64_t 
   }
   if (!chol_lower(S, n, P, &s_flag)) {
     if (tid == 0) atomicExch(flag, 2);
-    return;
+    continue;
   }
-  if (tid < D) {
-    const int d = tid;
+  for (int d = tid; d < D; d += 256) {
     for (int i = 0; i < n; ++i) {            // G y = r
       double acc = R[i * Q + d];
       for (int k = 0; k < i; ++k) acc = fma(-S[i * P + k], R[k * Q + d], acc);
@@ -347,20 +353,21 @@ __global__ void __launch_bounds__(256) tmat_solve_kernel(int tv, int D, int64_t 
     const int i = e / D, d = e - i * D;
     Tm[(int64_t)i * MD + (int64_t)m * D + d] = R[i * Q + d];
   }
+  }  // mixture loop
 }
 
 // minimum-divergence factor: U upper with sym(sum_m LU_m / nframes) = U^T U (scipy.linalg.cholesky default)
-__global__ void __launch_bounds__(256) tmat_mindiv_kernel(int tv, int nmix, const double* __restrict__ LU,
+__global__ void __launch_bounds__(1024) tmat_mindiv_kernel(int tv, int nmix, const double* __restrict__ LU,
                                                           const double* __restrict__ nframes, double* __restrict__ U,
-                                                          int* flag) {
-  extern __shared__ double sm[];
+                                                          int* flag, double* __restrict__ gws) {
+  extern __shared__ double dyn_sm[];
   const int n = tv, P = n + 1, tid = threadIdx.x;
-  double* S = sm;
+  double* S = gws ? gws : dyn_sm;
   __shared__ int s_flag;
   const int t2 = n * (n + 1) / 2;
   const double nf = *nframes;
   if (tid == 0) s_flag = 0;
-  for (int e = tid; e < n * n; e += 256) {
+  for (int e = tid; e < n * n; e += blockDim.x) {
     const int i = e / n, j = e - i * n;
     if (j > i) continue;
     double acc = 0.0;
@@ -371,7 +378,7 @@ __global__ void __launch_bounds__(256) tmat_mindiv_kernel(int tv, int nmix, cons
     if (tid == 0) atomicExch(flag, 3);
     return;
   }
-  for (int e = tid; e < n * n; e += 256) {
+  for (int e = tid; e < n * n; e += blockDim.x) {
     const int i = e / n, j = e - i * n;
     U[i * n + j] = (j >= i) ? S[j * P + i] : 0.0;   // U = G^T
   }
@@ -438,7 +445,7 @@ __global__ void __launch_bounds__(JT) tmat_jacobi_kernel(double* __restrict__ W,
 // singular values (row norms) -> descending order (stable), one CTA
 __global__ void __launch_bounds__(256) tmat_order_kernel(const double* __restrict__ W, int tv, int64_t MD,
                                                          int* __restrict__ perm) {
-  __shared__ double nrm[TMAT_MAX_TV];
+  __shared__ double nrm[TMAT_MAX_TV];   // (8 KB)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int p = warp; p < tv; p += 8) {
     double a = 0.0;
@@ -447,10 +454,10 @@ __global__ void __launch_bounds__(256) tmat_order_kernel(const double* __restric
     if (lane == 0) nrm[p] = a;
   }
   __syncthreads();
-  if (tid < tv) {   // rank of row tid = #rows with a larger norm (ties: lower index first)
+  for (int q = tid; q < tv; q += 256) {   // rank of row q = #rows with a larger norm (ties: lower index first)
     int rank = 0;
-    for (int p = 0; p < tv; ++p) rank += (nrm[p] > nrm[tid]) || (nrm[p] == nrm[tid] && p < tid);
-    perm[rank] = tid;
+    for (int p = 0; p < tv; ++p) rank += (nrm[p] > nrm[q]) || (nrm[p] == nrm[q] && p < q);
+    perm[rank] = q;
   }
 }
 
@@ -507,10 +514,36 @@ static size_t square_smem(int tv, int extra_doubles) {
   return sizeof(double) * ((size_t)tv * (tv + 1) + extra_doubles);
 }
 
+constexpr size_t SMEM_LIMIT = 200 * 1024;   // beyond this a kernel's matrices move to a per-CTA slab of global memory
+
+// per-CTA global slabs for the sizes whose systems do not fit shared memory (tv > ~150): `ctas` slabs of
+// `doubles_per_cta`; the data stay L2-resident while a CTA works on them, but the factorisations are not blocked,
+// so this route is much slower per FLOP than the shared-memory one
+static int reserve_gws(odin_tmat* t, size_t doubles_per_cta, int ctas) {
+  const size_t need = doubles_per_cta * (size_t)ctas;
+  if (need <= t->gws_cap) return ODIN_OK;
+  cudaFree(t->d_gws);
+  t->d_gws = nullptr; t->gws_cap = 0;
+  cudaError_t e = cudaMalloc(&t->d_gws, sizeof(double) * need);
+  if (e != cudaSuccess) return set_error(ODIN_ENOMEM, "T-matrix workspace (%zu MB): %s", need >> 17, cudaGetErrorString(e));
+  t->gws_cap = need;
+  return ODIN_OK;
+}
+
 int tmat_refresh(odin_tmat* t, cudaStream_t st) {
-  const size_t smem = sizeof(double) * (size_t)t->tv * (t->D + 1);
-  ODIN_CUDA_CHECK(cudaFuncSetAttribute(tmat_refresh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tmat_refresh_kernel<<<t->M, 256, smem, st>>>(t->d_Tm, t->d_Sigma, t->tv, t->D, t->MD, t->d_TinvS, t->d_TinvSTt);
+  const size_t per = (size_t)t->tv * (t->D + 1);
+  const size_t smem = sizeof(double) * per;
+  if (smem <= SMEM_LIMIT) {
+    ODIN_CUDA_CHECK(cudaFuncSetAttribute(tmat_refresh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tmat_refresh_kernel<<<t->M, 256, smem, st>>>(t->d_Tm, t->d_Sigma, t->tv, t->D, t->MD, t->M, t->d_TinvS, t->d_TinvSTt,
+                                                 nullptr);
+  } else {
+    const int ctas = std::min(t->M, sm_count() * 4);
+    int rc = reserve_gws(t, per, ctas);
+    if (rc) return rc;
+    tmat_refresh_kernel<<<ctas, 256, 0, st>>>(t->d_Tm, t->d_Sigma, t->tv, t->D, t->MD, t->M, t->d_TinvS, t->d_TinvSTt,
+                                              t->d_gws);
+  }
   ODIN_LAUNCH_CHECK("tmat_refresh_kernel");
   return ODIN_OK;
 }
@@ -543,10 +576,18 @@ static int posterior_chunk(odin_tmat* t, const double* d_Z, const double* d_F, i
   a.tv = t->tv; a.n = n; a.L1 = t->d_L1; a.B1 = t->d_B1; a.Ex = d_ex_out; a.llk = training ? t->d_llk : nullptr;
   a.want_exx = training ? 1 : 0; a.flag = t->d_flag;
   const size_t smem = square_smem(t->tv, 3 * t->tv);
-  ODIN_CUDA_CHECK(cudaFuncSetAttribute(tmat_file_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (227 * 1024) / (smem + 1024)));
-  const int64_t grid = std::min<int64_t>(n, (int64_t)sm_count() * per_sm);
-  tmat_file_kernel<<<(unsigned)grid, 256, smem, st>>>(a);
+  if (smem <= SMEM_LIMIT) {
+    ODIN_CUDA_CHECK(cudaFuncSetAttribute(tmat_file_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (227 * 1024) / (smem + 1024)));
+    const int64_t grid = std::min<int64_t>(n, (int64_t)sm_count() * per_sm);
+    a.gws = nullptr;
+    tmat_file_kernel<<<(unsigned)grid, 256, smem, st>>>(a);
+  } else {
+    const int64_t grid = std::min<int64_t>(n, (int64_t)sm_count() * 4);
+    if ((rc = reserve_gws(t, smem / sizeof(double), (int)grid))) return rc;
+    a.gws = t->d_gws;
+    tmat_file_kernel<<<(unsigned)grid, 256, 0, st>>>(a);
+  }
   ODIN_LAUNCH_CHECK("tmat_file_kernel");
   return ODIN_OK;
 }
@@ -594,15 +635,25 @@ int tmat_mstep(odin_tmat* t, const double* d_acc, int min_div, int orthogonalize
   int rc;
   {
     const size_t smem = square_smem(t->tv, t->tv * (t->D + 1));
-    if (smem > 227 * 1024) return set_error(ODIN_EINVAL, "T-matrix M-step needs %zu B of shared memory", smem);
-    ODIN_CUDA_CHECK(cudaFuncSetAttribute(tmat_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tmat_solve_kernel<<<t->M, 256, smem, st>>>(t->tv, t->D, t->MD, d_LU, d_RU, t->d_Tm, t->d_flag);
+    if (smem <= SMEM_LIMIT) {
+      ODIN_CUDA_CHECK(cudaFuncSetAttribute(tmat_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      tmat_solve_kernel<<<t->M, 256, smem, st>>>(t->tv, t->D, t->MD, d_LU, d_RU, t->d_Tm, t->d_flag, t->M, nullptr);
+    } else {
+      const int ctas = std::min(t->M, sm_count() * 4);
+      if ((rc = reserve_gws(t, smem / sizeof(double), ctas))) return rc;
+      tmat_solve_kernel<<<ctas, 256, 0, st>>>(t->tv, t->D, t->MD, d_LU, d_RU, t->d_Tm, t->d_flag, t->M, t->d_gws);
+    }
     ODIN_LAUNCH_CHECK("tmat_solve_kernel");
   }
   if (min_div) {
     const size_t smem = square_smem(t->tv, 0);
-    ODIN_CUDA_CHECK(cudaFuncSetAttribute(tmat_mindiv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tmat_mindiv_kernel<<<1, 256, smem, st>>>(t->tv, t->M, d_LU, d_nframes, t->d_U, t->d_flag);
+    if (smem <= SMEM_LIMIT) {
+      ODIN_CUDA_CHECK(cudaFuncSetAttribute(tmat_mindiv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      tmat_mindiv_kernel<<<1, 256, smem, st>>>(t->tv, t->M, d_LU, d_nframes, t->d_U, t->d_flag, nullptr);
+    } else {
+      if ((rc = reserve_gws(t, smem / sizeof(double), 1))) return rc;
+      tmat_mindiv_kernel<<<1, 1024, 0, st>>>(t->tv, t->M, d_LU, d_nframes, t->d_U, t->d_flag, t->d_gws);
+    }
     ODIN_LAUNCH_CHECK("tmat_mindiv_kernel");
     // Tm <- U Tm (through the T_invS buffer, which is rebuilt by the refresh below)
     if ((rc = gemm(t->tv, (int)t->MD, t->tv, t->d_U, t->tv, 1, t->d_Tm, t->MD, 1, t->d_TinvS, t->MD, 0.0, st))) return rc;

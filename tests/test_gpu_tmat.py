@@ -59,10 +59,12 @@ def test_golden_reference_run():
   assert relmax(iv * sg_ours[None, :], g["ivec"] * sg_ref[None, :]) < 1e-6
 
 
-@pytest.mark.parametrize("tv,D,M,n_files", [(16, 12, 20, 150), (64, 60, 32, 300), (128, 20, 8, 90), (33, 7, 5, 70)])
+@pytest.mark.parametrize("tv,D,M,n_files", [(16, 12, 20, 150), (64, 60, 32, 300), (128, 20, 8, 90), (33, 7, 5, 70),
+                                            (176, 24, 10, 230)])
 def test_em_iteration_vs_oracle(tv, D, M, n_files):
-  """One full EM iteration and i-vector extraction on fresh statistics, including the largest supported
-  tv_dim (128) and an odd one (a bye in the Jacobi tournament)."""
+  """One full EM iteration and i-vector extraction on fresh statistics, including tv_dim 128 (the largest whose
+  systems fit shared memory next to the M-step's right-hand sides), an odd one (a bye in the Jacobi tournament) and
+  176 (every factorisation on the global-memory route)."""
   from odin_b200.ml import Tmatrix
   sigma, Z, F = _problem(tv + D, D, M, n_files)
   t = Tmatrix(tv, _gmm_stub(sigma), niter=1)
@@ -108,7 +110,7 @@ def test_limits_fail_loudly():
   from odin_b200.ml import Tmatrix
   sigma, _, _ = _problem(1, 4, 3, 5)
   with pytest.raises(_lib.OdinError):
-    Tmatrix(129, _gmm_stub(sigma))
+    Tmatrix(1025, _gmm_stub(sigma))
 
 
 def test_ivector_wrapper(tmp_path):
