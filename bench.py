@@ -268,16 +268,21 @@ def mfcc_leg(torch, args, rank, world, dist, peaks, do_cpu):
       "kernel_ms": {"dc": float(kms[0]), "frame": float(kms[1]), "post": float(kms[2]), "vad": float(kms[3])},
       "roofline": {"bound": "hbm", "achieved": bytes_per_frame * T / frame_kernel_s / 1e9, "peak": peaks["hbm_gbs"],
                    "unit": "GB/s", "frac": bytes_per_frame * T / frame_kernel_s / 1e9 / peaks["hbm_gbs"],
-                   "traffic": 60.24e6 / 154696 * T, "kernel": "fe_frame4_kernel", "peak_source": peaks["source"],
-                   "note": "algorithmic 885 B/frame; traffic from profiles/r01_fe_frame4_ncu_full_keymetrics.csv (49.6 MB read + 10.6 MB written per 154 696-frame launch: the utterance pass writes the rest); the kernel is issue / FP32 bound (SURVEY 8d), see roofline_fp32 and DESIGN.md"},
+                   "traffic": 408.5e6 / 696132 * T, "kernel": "fe_frame4_kernel", "peak_source": peaks["source"],
+                   "note": "algorithmic 885 B/frame; traffic from profiles/r01_fe_ncu_s7_keymetrics.csv (223.2 MB read + 185.3 MB written per 696 132-frame launch: PCM in, unclipped log-mel + energies out; the utterance pass writes the rest); the kernel is issue / FP32 bound (SURVEY 8d), see roofline_fp32 and DESIGN.md"},
       # the binding resource is the SM, not HBM: algorithmic 35 kFLOP per frame against the
       # FP32 pipe peak 148 SM x 128 lanes x 2 x max SM clock
       "roofline_fp32": {"bound": "fp32", "achieved": 35.0e3 * T / frame_kernel_s / 1e12,
                         "peak": 148 * 128 * 2 * 1.965e9 / 1e12, "unit": "TFLOP/s",
                         "frac": 35.0e3 * T / frame_kernel_s / (148 * 128 * 2 * 1.965e9),
                         "kernel": "fe_frame4_kernel", "peak_source": "nominal: 148 SMs x 128 FP32 lanes x 2 x 1.965 GHz"},
+      # what actually binds the frame kernel: warp-instruction issue slots (4 per SM per cycle).  Not measurable
+      # without a profiler, so the figures of the committed capture are quoted, not re-measured per run.
+      "roofline_issue": {"bound": "issue", "frac": 0.591, "warp_instructions_per_frame": 1451, "kernel": "fe_frame4_kernel",
+                         "peak_source": "ncu smsp__issue_active / smsp__inst_executed of profiles/r01_fe_ncu_s7_keymetrics.csv "
+                                        "(same workload); utterance pass 0.62, SADgmm 0.31 (latency / barrier bound)"},
       "e2e": {"value": total_T / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d * world,
-              "d2h_bytes_per_step": d2h * world},
+              "d2h_bytes_per_step": d2h * world, "call": "FusedSpeechFrontEnd.run_host_packed (%d chunks)" % args.mfcc_chunks},
   }
   if do_cpu:
     from oracle import frontend as F
