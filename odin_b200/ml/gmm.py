@@ -51,7 +51,7 @@ class _DeviceFrames(object):
   a host array is streamed through two pinned buffers on a copy stream so the
   H2D copy of chunk i+1 overlaps the E-step of chunk i."""
 
-  def __init__(self, X, chunk_frames=1 << 20):
+  def __init__(self, X, chunk_frames=1 << 18):
     _lib.require_cuda()
     torch = _torch()
     self.torch = torch
@@ -73,7 +73,7 @@ class _DeviceFrames(object):
         raise ValueError("`X` must be a 2-D matrix [n_samples, feat_dim]")
       self.host = X
     self.n, self.dim = (self.resident.shape if self.resident is not None else self.host.shape)
-    self.chunk = int(chunk_frames)
+    self.chunk = int(os.environ.get('ODIN_GMM_CHUNK_FRAMES', chunk_frames))   # (env: A/B runs of the streaming depth)
 
   shape = property(lambda self: (self.n, self.dim))
   ndim = 2
@@ -136,6 +136,9 @@ class _DeviceFrames(object):
     copy_stream = torch.cuda.Stream()
     copied = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
+    # Chunk size: the first copy and the last E-step cannot overlap anything, so smaller chunks shorten the exposed
+    # ends until per-chunk overheads win (6 M frames at 2048 mixtures, tools/gmm_e2e_sweep.py: 1 M-frame chunks
+    # 29.7 ms per EM iteration, 512 k 28.5, 256 k 27.7, 128 k 29.6; ramped sizes were no better than fixed ones).
     ranges = minibatch(n, ch)
 
     def stage(i):
