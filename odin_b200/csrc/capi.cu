@@ -217,10 +217,10 @@ int fe_reserve(odin_fe* fe, int n_utt) {
   int cap = n_utt + n_utt / 4 + 16;
   auto freeall = [&]() {
     if (fe->h_stage) cudaFreeHost(fe->h_stage);
-    cudaFree(fe->d_sample_off); cudaFree(fe->d_frame_off); cudaFree(fe->d_tile_off); cudaFree(fe->d_tile2_off);
+    cudaFree(fe->d_sample_off);   // one block: d_frame_off / d_tile_off / d_tile2_off / d_vad_order point into it
     cudaFree(fe->d_dcsum); cudaFree(fe->d_umax); cudaFree(fe->d_cnt);
     fe->h_stage = nullptr;
-    fe->d_sample_off = fe->d_frame_off = fe->d_tile_off = fe->d_tile2_off = fe->d_cnt = nullptr;
+    fe->d_sample_off = fe->d_frame_off = fe->d_tile_off = fe->d_tile2_off = fe->d_vad_order = fe->d_cnt = nullptr;
     fe->d_dcsum = nullptr; fe->d_umax = nullptr; fe->cap_utt = 0;
   };
   freeall();

@@ -1592,6 +1592,14 @@ int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t 
         // next one to whichever SMs free up
         int ncta = 1;
         while (ncta < VAD_CL_MAX && (int64_t)n_utt * (ncta * 2) <= (int64_t)sm_count() * 3) ncta *= 2;
+        {
+          // ... but never more CTAs than the longest utterance can feed (>= 4 frames per thread): short utterances
+          // (config 1: 298 frames) only pay the cluster barriers
+          int64_t max_T = 0;
+          const int64_t* fo = fe->h_stage + ((size_t)fe->cap_utt + 1);
+          for (int u = 0; u < n_utt; ++u) max_T = std::max(max_T, fo[u + 1] - fo[u]);
+          while (ncta > 1 && max_T < (int64_t)4 * VAD_THREADS * ncta) ncta /= 2;
+        }
         if (const char* ev = getenv("ODIN_FE_VAD_NCTA")) {   // A/B runs
           const int v2 = atoi(ev);
           if (v2 == 1 || v2 == 2 || v2 == 4 || v2 == 8) ncta = v2;

@@ -295,3 +295,17 @@ def test_other_fft_sizes_vs_oracle(n_fft, frame_length, force_stockham, monkeypa
     assert relmax(o["mspec"], r["mspec"]) < TOL_FEAT and relmax(o["mfcc"], r["mfcc"]) < TOL_FEAT
     assert relmax(o["stft_energy"], r["stft_energy"]) < 1e-6
     assert np.array_equal(o["sad"], r["sad"])
+
+
+def test_growing_batches_on_one_handle():
+  """The per-call staging of a handle grows with the batch: a second, larger batch (more utterances, more frames)
+  on the same pipeline must give the same per-utterance results as the first."""
+  cfg = FE_CONFIGS["cfg1"]
+  pipe = _pipeline(cfg, vad="gmm")
+  utts = synth.utterance_batch(40, 0.3, 0.9, sr=16000, seed=321)
+  small = pipe.transform_batch([{"raw": u, "sr": 16000} for u in utts[:3]])
+  big = pipe.transform_batch([{"raw": u, "sr": 16000} for u in utts])
+  again = pipe.transform_batch([{"raw": u, "sr": 16000} for u in utts[:3]])
+  for a, b, c in zip(small, big[:3], again):
+    for k in ("mfcc", "mspec", "sad", "stft_energy"):
+      assert np.array_equal(a[k], b[k]) and np.array_equal(a[k], c[k]), k
