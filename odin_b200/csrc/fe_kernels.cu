@@ -1004,6 +1004,7 @@ constexpr int VAD_CL_MAX = 8;               // portable cluster size limit
 constexpr int VAD_KMAX = 4;
 constexpr int VAD_NRED = 3 * VAD_KMAX + 2;   // lsum, nk[4], sx[4], sxx[4], #non-finite
 constexpr int VAD_XR = 16;                  // frames per thread staged in shared memory by the EM
+constexpr int VAD_WARP_MAX_T = 512;          // utterances up to this many frames: one warp each (fe_vad_gmm_warp_kernel)
 constexpr int VAD_MAXLEAF = 1024;            // leaves of numpy's pairwise sum held in smem (n <~ 58 000 frames)
 
 struct VadShared {
@@ -1158,6 +1159,46 @@ __device__ __forceinline__ void vad_store_params(VadShared& sh, int k, double mu
   sh.par[k][VP_W] = w;
 }
 
+// E-step of one frame (sklearn _estimate_log_prob_resp, 1-D) accumulated into acc[] = lsum | nk | sx | sxx | #non-finite
+__device__ __forceinline__ void vad_frame(const float xf, const int nc, const double (&prec)[VAD_KMAX],
+                                          const double (&a0)[VAD_KMAX], const double (&b0)[VAD_KMAX],
+                                          const double (&ld)[VAD_KMAX], const double (&lw)[VAD_KMAX],
+                                          double (&acc)[VAD_NRED], double& sprod, int& nprod) {
+  constexpr int KMAX = VAD_KMAX;
+  const double LOG2PI = 1.8378770664093454835606594728112;
+  if (!isfinite(xf)) acc[VAD_NRED - 1] += 1.0;
+  const double xd = (double)xf, x2 = (double)__fmul_rn(xf, xf);  // x*x is float32 in sklearn
+  double wl[KMAX], mx = -INFINITY;
+  for (int k = 0; k < nc; ++k) {
+    double lp = dadd(dadd(a0[k], -dmul(2.0, dmul(xd, b0[k]))), dmul(x2, prec[k]));
+    lp = dadd(dmul(-0.5, dadd(LOG2PI, lp)), ld[k]);
+    wl[k] = dadd(lp, lw[k]);
+    mx = fmax(mx, wl[k]);
+  }
+  double ek[KMAX], s = 0.0;
+  if (nc == 3) {
+    const bool am = wl[0] == mx, bm = wl[1] == mx, cm = wl[2] == mx;
+    const double dA = wl[0] - mx, dB = wl[1] - mx, dC = wl[2] - mx;
+    const double e1 = exp(am ? dB : dA), e2 = exp(cm ? dB : dC);
+    ek[0] = am ? 1.0 : e1;
+    ek[2] = cm ? 1.0 : e2;
+    ek[1] = bm ? 1.0 : (am ? e1 : e2);
+    s = (ek[0] + ek[1]) + ek[2];
+  } else {
+    for (int k = 0; k < nc; ++k) { ek[k] = exp(wl[k] - mx); s += ek[k]; }
+  }
+  const double inv = 1.0 / s;
+  acc[0] += mx;
+  sprod *= s;
+  if (++nprod == 256) { acc[0] += log(sprod); sprod = 1.0; nprod = 0; }   // nc^256 stays finite
+  for (int k = 0; k < nc; ++k) {
+    const double r = ek[k] * inv;
+    acc[1 + k] += r;
+    acc[1 + KMAX + k] = fma(r, xd, acc[1 + KMAX + k]);
+    acc[1 + 2 * KMAX + k] = fma(r, x2, acc[1 + 2 * KMAX + k]);
+  }
+}
+
 __device__ bool vad_em(const float* __restrict__ x, int n, int nc, int max_iter, VadShared& sh, cg::cluster_group& cl,
                        double* mu_out, double* prec_out) {
   constexpr int KMAX = VAD_KMAX;
@@ -1174,7 +1215,6 @@ __device__ bool vad_em(const float* __restrict__ x, int n, int nc, int max_iter,
     sh.bad[tid] = 0;
   }
   __syncthreads();
-  const double LOG2PI = 1.8378770664093454835606594728112;
   double lower = -INFINITY;
   for (int it = 0; it < max_iter; ++it) {
     double prec[KMAX], a0[KMAX], b0[KMAX], ld[KMAX], lw[KMAX];
@@ -1195,39 +1235,7 @@ __device__ bool vad_em(const float* __restrict__ x, int n, int nc, int max_iter,
     // Each step differs from sklearn's expression by <= 1 ulp of a double.
     double sprod = 1.0;
     int nprod = 0;
-    auto frame = [&](const float xf) {
-      if (!isfinite(xf)) acc[VAD_NRED - 1] += 1.0;
-      const double xd = (double)xf, x2 = (double)__fmul_rn(xf, xf);  // x*x is float32 in sklearn
-      double wl[KMAX], mx = -INFINITY;
-      for (int k = 0; k < nc; ++k) {
-        double lp = dadd(dadd(a0[k], -dmul(2.0, dmul(xd, b0[k]))), dmul(x2, prec[k]));
-        lp = dadd(dmul(-0.5, dadd(LOG2PI, lp)), ld[k]);
-        wl[k] = dadd(lp, lw[k]);
-        mx = fmax(mx, wl[k]);
-      }
-      double ek[KMAX], s = 0.0;
-      if (nc == 3) {
-        const bool am = wl[0] == mx, bm = wl[1] == mx, cm = wl[2] == mx;
-        const double dA = wl[0] - mx, dB = wl[1] - mx, dC = wl[2] - mx;
-        const double e1 = exp(am ? dB : dA), e2 = exp(cm ? dB : dC);
-        ek[0] = am ? 1.0 : e1;
-        ek[2] = cm ? 1.0 : e2;
-        ek[1] = bm ? 1.0 : (am ? e1 : e2);
-        s = (ek[0] + ek[1]) + ek[2];
-      } else {
-        for (int k = 0; k < nc; ++k) { ek[k] = exp(wl[k] - mx); s += ek[k]; }
-      }
-      const double inv = 1.0 / s;
-      acc[0] += mx;
-      sprod *= s;
-      if (++nprod == 256) { acc[0] += log(sprod); sprod = 1.0; nprod = 0; }   // nc^256 stays finite
-      for (int k = 0; k < nc; ++k) {
-        const double r = ek[k] * inv;
-        acc[1 + k] += r;
-        acc[1 + KMAX + k] = fma(r, xd, acc[1 + KMAX + k]);
-        acc[1 + 2 * KMAX + k] = fma(r, x2, acc[1 + 2 * KMAX + k]);
-      }
-    };
+    auto frame = [&](const float xf) { vad_frame(xf, nc, prec, a0, b0, ld, lw, acc, sprod, nprod); };
     if (staged) {
       for (int j = 0, i = gt; i < n; ++j, i += gstride) frame(sh.xs[j * VAD_THREADS + tid]);
     } else {
@@ -1326,6 +1334,104 @@ __global__ void __launch_bounds__(VAD_THREADS, 2) fe_vad_gmm_kernel(VadArgs a) {
         out[i] = do_smooth ? (uint8_t)smooth_flat_ge_f(raw, n, a.smooth, false, i) : (uint8_t)raw(i);
     }
     cl.sync();  // xs / sh are reused by the cluster's next utterance
+  }
+}
+
+// SADgmm for SHORT utterances: one WARP per utterance, eight independent utterances per CTA, no block or cluster
+// barrier anywhere.  A 3 s utterance (298 frames) leaves a 256-thread CTA with one frame per thread and ~25 EM
+// iterations of pure barrier / M-step latency (ncu on 2 000 such utterances: 22 % of the instructions were the
+// warp shuffles of the 14-value reduction, most stall samples sat on barriers); here every lane takes ~10 frames,
+// the statistics are reduced with one xor-butterfly (bit-identical on all lanes, so every lane replays the tiny
+// M-step on the same numbers) and the eight warps of a CTA hide each other's latency.
+// Utterances [first, n_utt) of the visiting order (longest first) are handled here.
+__global__ void __launch_bounds__(VAD_THREADS, 2) fe_vad_gmm_warp_kernel(VadArgs a, int first) {
+  constexpr int KMAX = VAD_KMAX;
+  const int lane = threadIdx.x & 31;
+  const int wid = (blockIdx.x * VAD_THREADS + threadIdx.x) >> 5;
+  const int nw = (gridDim.x * VAD_THREADS) >> 5;
+  for (int ci = first + wid; ci < a.n_utt; ci += nw) {
+    const int u = a.order ? (int)a.order[ci] : ci;
+    const int64_t base = a.frame_off[u];
+    const int n = (int)(a.frame_off[u + 1] - base);
+    if (n <= 0) continue;
+    const float* e = a.x + base;
+    float* xs = a.scratch + base;
+    uint8_t* out = a.sad + base;
+    int nc = a.nmix;
+    bool ok = false;
+    double thr = 0.0;
+    const float* src = e;
+    while (true) {
+      // standardise in float32 exactly as numpy does (signal.py:305)
+      const float ssum = warp_np_pairwise_sum_f32([src](int i) { return src[i]; }, n, lane);
+      const float mean = (float)((double)ssum / (double)n);
+      const float ss = warp_np_pairwise_sum_f32(
+          [src, mean](int i) { const float d = __fadd_rn(src[i], -mean); return __fmul_rn(d, d); }, n, lane);
+      const float sd = sqrtf((float)((double)ss / (double)n));
+      __syncwarp();
+      for (int i = lane; i < n; i += 32) xs[i] = __fdiv_rn(__fsub_rn(src[i], mean), sd);
+      __syncwarp();
+      src = xs;
+      // ---- EM (same arithmetic as vad_em; reductions by butterfly) ----
+      bool fitted = n >= max(nc, 2);
+      double w[KMAX], mu[KMAX], pch[KMAX];
+      for (int k = 0; k < nc; ++k) { w[k] = 1.0 / nc; mu[k] = -2.0 + 4.0 * k / (double)(nc - 1); pch[k] = 1.0; }
+      double lower = -INFINITY;
+      for (int it = 0; fitted && it < a.iters; ++it) {
+        double prec[KMAX], a0[KMAX], b0[KMAX], ld[KMAX], lw[KMAX];
+        for (int k = 0; k < nc; ++k) {
+          prec[k] = dmul(pch[k], pch[k]);
+          a0[k] = dmul(dmul(mu[k], mu[k]), prec[k]);
+          b0[k] = dmul(mu[k], prec[k]);
+          ld[k] = log(pch[k]);
+          lw[k] = log(w[k]);
+        }
+        double acc[VAD_NRED];
+#pragma unroll
+        for (int k = 0; k < VAD_NRED; ++k) acc[k] = 0.0;
+        double sprod = 1.0;
+        int nprod = 0;
+        for (int i = lane; i < n; i += 32) vad_frame(xs[i], nc, prec, a0, b0, ld, lw, acc, sprod, nprod);
+        acc[0] += log(sprod);
+#pragma unroll
+        for (int k = 0; k < VAD_NRED; ++k) acc[k] = warp_sum(acc[k]);
+        if (acc[VAD_NRED - 1] != 0.0) { fitted = false; break; }   // sklearn rejects non-finite input
+        double nk[KMAX], nksum = 0.0;
+        bool collapsed = false;
+        for (int k = 0; k < nc; ++k) { nk[k] = acc[1 + k] + 10.0 * DBL_EPSILON; nksum += nk[k]; }
+        for (int k = 0; k < nc; ++k) {
+          mu[k] = acc[1 + KMAX + k] / nk[k];
+          const double var = dadd(dadd(acc[1 + 2 * KMAX + k] / nk[k], -dmul(mu[k], mu[k])), 1e-6);
+          if (!(var > 0.0)) collapsed = true;
+          pch[k] = 1.0 / sqrt(var);
+          w[k] = nk[k] / nksum;
+        }
+        if (collapsed) { fitted = false; break; }
+        const double new_lower = acc[0] / (double)n;
+        const double change = new_lower - lower;
+        lower = new_lower;
+        if (fabs(change) < 1e-3) break;
+      }
+      if (fitted) {
+        int kb = 0;
+        for (int k = 1; k < nc; ++k) if (mu[k] > mu[kb]) kb = k;
+        thr = dadd(mu[kb], -dmul(a.mode, sqrt(1.0 / dmul(pch[kb], pch[kb]))));
+        ok = true;
+        break;
+      }
+      if (nc - 1 >= 2) { --nc; continue; }
+      break;
+    }
+    if (a.thr_out != nullptr && lane == 0) a.thr_out[u] = ok ? thr : 0.0;
+    if (!ok) {
+      for (int i = lane; i < n; i += 32) out[i] = 0;
+    } else {
+      auto raw = [xs, thr](int i) -> int { return ((double)xs[i] > thr) ? 1 : 0; };
+      const bool do_smooth = a.smooth >= 3 && n >= a.smooth;
+      for (int i = lane; i < n; i += 32)
+        out[i] = do_smooth ? (uint8_t)smooth_flat_ge_f(raw, n, a.smooth, false, i) : (uint8_t)raw(i);
+    }
+    __syncwarp();
   }
 }
 
@@ -1584,41 +1690,59 @@ int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t 
       if (c.vad_kind == 1) {
         if (d_energy == nullptr) return set_error(ODIN_EINVAL, "SADgmm needs d_energy");
         v.x = d_energy;
-        // cluster size: the largest power of two such that all clusters of the batch are resident
-        // at once (2 CTAs of 256 threads per SM)
-        // cluster size: the largest power of two that keeps the batch within ~3 CTAs per SM (2 are
-        // resident at once; measured on the config-3 shard, 216 utterances: 1 -> 0.82 ms, 2 -> 0.61,
-        // 4 -> 0.66, 8 -> 1.17); clusters start longest utterance first and the hardware hands the
-        // next one to whichever SMs free up
-        int ncta = 1;
-        while (ncta < VAD_CL_MAX && (int64_t)n_utt * (ncta * 2) <= (int64_t)sm_count() * 3) ncta *= 2;
-        {
-          // ... but never more CTAs than the longest utterance can feed (>= 4 frames per thread): short utterances
-          // (config 1: 298 frames) only pay the cluster barriers
-          int64_t max_T = 0;
-          const int64_t* fo = fe->h_stage + ((size_t)fe->cap_utt + 1);
-          for (int u = 0; u < n_utt; ++u) max_T = std::max(max_T, fo[u + 1] - fo[u]);
+        // Utterances of up to VAD_WARP_MAX_T frames go to the warp-per-utterance kernel, longer ones to the
+        // cluster kernel.  The visiting order is longest first, so the long ones are its first n_long entries.
+        const int64_t* fo = fe->h_stage + ((size_t)fe->cap_utt + 1);
+        const char* lpt = getenv("ODIN_FE_VAD_LPT");
+        const char* nowarp = getenv("ODIN_FE_VAD_NOWARP");   // A/B runs
+        int n_long = n_utt;
+        int64_t max_T = 0;
+        for (int u = 0; u < n_utt; ++u) max_T = std::max(max_T, fo[u + 1] - fo[u]);
+        if (!(lpt && lpt[0] == '0') && !(nowarp && nowarp[0] == '1')) {
+          n_long = 0;
+          for (int u = 0; u < n_utt; ++u) n_long += (fo[u + 1] - fo[u]) > VAD_WARP_MAX_T;
+          // a warp takes ~2x longer over ONE utterance than a CTA does, so the warp kernel only pays once there are
+          // enough short utterances to fill the SMs with warps (measured: 100 x 3 s 0.13 ms on CTAs vs 0.24 on warps;
+          // 2 000 x 3 s 0.84 vs 0.29)
+          if (n_utt - n_long < 4 * sm_count()) n_long = n_utt;
+        }
+        if (n_long > 0) {
+          // cluster size: the largest power of two that keeps the batch within ~3 CTAs per SM (2 are
+          // resident at once; measured on the config-3 shard, 216 utterances: 1 -> 0.82 ms, 2 -> 0.61,
+          // 4 -> 0.66, 8 -> 1.17); clusters start longest utterance first and the hardware hands the
+          // next one to whichever SMs free up
+          int ncta = 1;
+          while (ncta < VAD_CL_MAX && (int64_t)n_long * (ncta * 2) <= (int64_t)sm_count() * 3) ncta *= 2;
+          // ... but never more CTAs than the longest utterance can feed (>= 4 frames per thread)
           while (ncta > 1 && max_T < (int64_t)4 * VAD_THREADS * ncta) ncta /= 2;
+          if (const char* ev = getenv("ODIN_FE_VAD_NCTA")) {   // A/B runs
+            const int v2 = atoi(ev);
+            if (v2 == 1 || v2 == 2 || v2 == 4 || v2 == 8) ncta = v2;
+          }
+          VadArgs vl = v;
+          vl.n_utt = n_long;
+          const int64_t n_cl = std::min<int64_t>(n_long, (int64_t)sm_count() * 4);
+          cudaLaunchConfig_t cfg = {};
+          cfg.gridDim = dim3((unsigned)(n_cl * ncta));
+          cfg.blockDim = dim3(VAD_THREADS);
+          cfg.dynamicSmemBytes = 0;
+          cfg.stream = vst;
+          cudaLaunchAttribute attr[1];
+          attr[0].id = cudaLaunchAttributeClusterDimension;
+          attr[0].val.clusterDim.x = (unsigned)ncta;
+          attr[0].val.clusterDim.y = 1;
+          attr[0].val.clusterDim.z = 1;
+          cfg.attrs = attr;
+          cfg.numAttrs = 1;
+          ODIN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, fe_vad_gmm_kernel, vl));
+          ODIN_LAUNCH_CHECK("fe_vad_gmm_kernel");
         }
-        if (const char* ev = getenv("ODIN_FE_VAD_NCTA")) {   // A/B runs
-          const int v2 = atoi(ev);
-          if (v2 == 1 || v2 == 2 || v2 == 4 || v2 == 8) ncta = v2;
+        if (n_long < n_utt) {
+          const int n_short = n_utt - n_long;
+          const int wgrid = (int)std::min<int64_t>(ceil_div(n_short, VAD_WARPS), (int64_t)sm_count() * 8);
+          fe_vad_gmm_warp_kernel<<<wgrid, VAD_THREADS, 0, vst>>>(v, n_long);
+          ODIN_LAUNCH_CHECK("fe_vad_gmm_warp_kernel");
         }
-        const int64_t n_cl = std::min<int64_t>(n_utt, (int64_t)sm_count() * 4);
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)(n_cl * ncta));
-        cfg.blockDim = dim3(VAD_THREADS);
-        cfg.dynamicSmemBytes = 0;
-        cfg.stream = vst;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = (unsigned)ncta;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        ODIN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, fe_vad_gmm_kernel, v));
-        ODIN_LAUNCH_CHECK("fe_vad_gmm_kernel");
       } else {
         if (d_c0 == nullptr) return set_error(ODIN_EINVAL, "SADthreshold needs d_c0");
         v.x = d_c0;

@@ -309,3 +309,24 @@ def test_growing_batches_on_one_handle():
   for a, b, c in zip(small, big[:3], again):
     for k in ("mfcc", "mspec", "sad", "stft_energy"):
       assert np.array_equal(a[k], b[k]) and np.array_equal(a[k], c[k]), k
+
+
+def test_sadgmm_many_short_utterances_warp_kernel():
+  """More than 4 x SM-count short utterances switch SADgmm to the warp-per-utterance kernel (and a few long ones in the
+  same batch stay on the cluster kernel): masks must still equal the oracle's bit for bit, and equal what the cluster
+  kernel gives for the same utterances in a small batch."""
+  cfg = FE_CONFIGS["cfg1"]
+  pipe = _pipeline(cfg, vad="gmm")
+  short = synth.utterance_batch(30, 0.3, 2.0, sr=16000, seed=777)
+  long_ = synth.utterance_batch(2, 6.0, 8.0, sr=16000, seed=778)
+  utts = [short[i % 30] for i in range(700)] + long_
+  outs = pipe.transform_batch([{"raw": u, "sr": 16000} for u in utts])
+  small = pipe.transform_batch([{"raw": u, "sr": 16000} for u in short + long_])
+  for i in range(30):
+    r = F.extract(short[i], 16000, vad="gmm", fmax=8000)
+    assert np.array_equal(outs[i]["sad"], r["sad"]), i
+    assert abs(outs[i]["sad_threshold"] - r["sad_threshold"]) < 1e-9
+    assert np.array_equal(outs[i]["sad"], small[i]["sad"]) and np.array_equal(outs[i + 30]["sad"], small[i]["sad"])
+  for j in range(2):
+    assert np.array_equal(outs[700 + j]["sad"], small[30 + j]["sad"])
+    assert np.array_equal(outs[700 + j]["sad"], F.extract(long_[j], 16000, vad="gmm", fmax=8000)["sad"])
