@@ -508,7 +508,7 @@ int odin_gmm_create(int32_t feat_dim, int32_t max_nmix, odin_gmm_t** out) {
 void odin_gmm_destroy(odin_gmm_t* g) {
   if (!g) return;
   cudaFree(g->d_mean); cudaFree(g->d_var); cudaFree(g->d_w); cudaFree(g->d_Wk); cudaFree(g->d_cst);
-  cudaFree(g->d_Whi); cudaFree(g->d_Whs); cudaFree(g->d_Wlo); cudaFree(g->d_part); cudaFree(g->d_lse); cudaFree(g->d_prev); cudaFree(g->d_off);
+  cudaFree(g->d_Whi); cudaFree(g->d_Whs); cudaFree(g->d_Wlo); cudaFree(g->d_part); cudaFree(g->d_utt_acc); cudaFree(g->d_lse); cudaFree(g->d_prev); cudaFree(g->d_off);
   gmm_h_free(g);
   if (g->h_off) cudaFreeHost(g->h_off);
   for (int i = 0; i < 3; ++i) if (g->ev[i]) cudaEventDestroy(g->ev[i]);
@@ -656,8 +656,23 @@ int odin_gmm_utt_stats(odin_gmm_t* g, const float* d_X, const uint8_t* d_sad, co
   if (!g || !d_X || !h_frame_offsets || !d_Z || !d_Fhat || n_utt < 0) return set_error(ODIN_EINVAL, "bad argument");
   if (g->M <= 0) return set_error(ODIN_EINVAL, "odin_gmm_set_params has not been called");
   if (n_utt == 0) return ODIN_OK;
-  (void)impl;  // per-utterance statistics run on the fp32 kernels in this version
   cudaStream_t st = as_stream(stream);
+  {
+    // Long utterances at tensor-core-sized models go through the tcgen05 3xFP16 E-step, one accumulator per
+    // utterance (gmm_utt_stats_h); short ones stay on the batched fp32 kernels, where a launch covers every
+    // utterance at once (a 100-frame digit does not fill one tensor-core launch).
+    int use = 1;
+    if (impl == 0 || impl == 3) {
+      int rc = pick_impl(g, impl, &use);
+      if (rc) return rc;
+    }
+    const int64_t total = h_frame_offsets[n_utt] - h_frame_offsets[0];
+    if (use == 3 && (impl == 3 || total >= (int64_t)1024 * n_utt)) {
+      ODIN_CUDA_CHECK(cudaStreamSynchronize(st));
+      return gmm_utt_stats_h(g, d_X + h_frame_offsets[0] * g->D, d_sad ? d_sad + h_frame_offsets[0] : nullptr,
+                             h_frame_offsets, n_utt, d_Z, d_Fhat, st);
+    }
+  }
   if (g->off_cap < n_utt + 1) {
     if (g->h_off) cudaFreeHost(g->h_off);
     cudaFree(g->d_off);

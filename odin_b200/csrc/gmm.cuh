@@ -29,6 +29,8 @@ struct odin_gmm {
   // pass-1 workspace of the tcgen05 path: per-chunk partial (max, sum) per frame
   void* d_part = nullptr;
   int64_t part_cap = 0;  // float2 elements
+  double* d_utt_acc = nullptr;   // per-utterance statistics of a group of utterances (gmm_utt_stats_h)
+  int64_t utt_acc_cap = 0;
   // 3xFP16 tcgen05 path (gmm_h.cu): column scales, scaled model images, per-sub-batch frame
   // operand images (A: rows = frames, T: rows = [x^2|x|1] transposed) and 14 - lse2 per frame
   void* d_hscale = nullptr;
@@ -87,6 +89,8 @@ void gmm_h_free(odin_gmm* g);
 // prepared frames (operand images of a resident frame matrix, built once)
 int gmm_frames_create(odin_gmm* g, const float* X, int64_t N, void** out, cudaStream_t st);
 void gmm_frames_destroy(void* f);
+int gmm_utt_stats_h(odin_gmm* g, const float* X, const uint8_t* sad, const int64_t* h_off, int n_utt, float* d_Z,
+                    float* d_Fhat, cudaStream_t st);
 int gmm_estep_frames(odin_gmm* g, const void* f, const uint8_t* sad, int want_second, double* stats,
                      cudaStream_t st);
 

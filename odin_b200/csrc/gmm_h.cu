@@ -841,6 +841,73 @@ int gmm_estep_h(odin_gmm* g, const float* X, const uint8_t* sad, int64_t N, int 
   return ODIN_OK;
 }
 
+// ---- per-utterance statistics (gmm_tmat.py:708-767, 769-913) on the tensor-core E-step ----
+// acc holds, per utterance of a group, the packed statistics the E-step accumulates (Z [M] | F [D, M] | ...);
+// Z and the centred first-order statistics F-hat[m * D + d] = F[d, m] - mean[d, m] Z[m] go out as float32 rows.
+__global__ void __launch_bounds__(256) gmm_h_centre_kernel(const double* __restrict__ acc, int64_t stride, int D, int M,
+                                                           const float* __restrict__ mean, float* __restrict__ Z,
+                                                           float* __restrict__ Fhat) {
+  const double* a = acc + (int64_t)blockIdx.x * stride;
+  float* z = Z + (int64_t)blockIdx.x * M;
+  float* f = Fhat + (int64_t)blockIdx.x * M * D;
+  for (int m = threadIdx.x; m < M; m += 256) z[m] = (float)a[m];
+  for (int i = threadIdx.x; i < M * D; i += 256) {
+    const int m = i / D, d = i - m * D;
+    f[i] = (float)(a[M + (int64_t)d * M + m] - (double)mean[(int64_t)d * M + m] * a[m]);
+  }
+}
+
+int gmm_utt_stats_h(odin_gmm* g, const float* X, const uint8_t* sad, const int64_t* h_off, int n_utt, float* d_Z,
+                    float* d_Fhat, cudaStream_t st) {
+  const int D = g->D, M = g->M;
+  const int64_t base = h_off[0], N = h_off[n_utt] - base;
+  int64_t maxlen = 0;
+  for (int u = 0; u < n_utt; ++u) maxlen = std::max(maxlen, h_off[u + 1] - h_off[u]);
+  if (N <= 0) {
+    ODIN_CUDA_CHECK(cudaMemsetAsync(d_Z, 0, sizeof(float) * (size_t)n_utt * M, st));
+    ODIN_CUDA_CHECK(cudaMemsetAsync(d_Fhat, 0, sizeof(float) * (size_t)n_utt * M * D, st));
+    return ODIN_OK;
+  }
+  const int64_t sub = std::min<int64_t>(h_sub_batch(), ceil_div<int64_t>(maxlen, hk::TF1) * hk::TF1);
+  int rc = h_reserve(g, sub, true);
+  if (rc) return rc;
+  HScale* sc = reinterpret_cast<HScale*>(g->d_hscale);
+  // one data range (-> exact power-of-two scales) and one set of scaled model images for the whole batch
+  if ((rc = h_launch_range(X, N, D, sc, st))) return rc;
+  if ((rc = h_launch_prepare(g, sc, st))) return rc;
+  const int64_t SD = stats_size(D, M);
+  const int G = 32;
+  if (g->utt_acc_cap < G * SD) {
+    cudaFree(g->d_utt_acc);
+    g->d_utt_acc = nullptr; g->utt_acc_cap = 0;
+    ODIN_CUDA_CHECK(cudaMalloc(&g->d_utt_acc, sizeof(double) * (size_t)(G * SD)));
+    g->utt_acc_cap = G * SD;
+  }
+  for (int u0 = 0; u0 < n_utt; u0 += G) {
+    const int cnt = std::min(G, n_utt - u0);
+    ODIN_CUDA_CHECK(cudaMemsetAsync(g->d_utt_acc, 0, sizeof(double) * (size_t)(cnt * SD), st));
+    for (int j = 0; j < cnt; ++j) {
+      const int64_t lo = h_off[u0 + j] - base, n_u = h_off[u0 + j + 1] - h_off[u0 + j];
+      for (int64_t s0 = 0; s0 < n_u; s0 += sub) {
+        const int64_t n = std::min<int64_t>(sub, n_u - s0);
+        const int64_t nsuper = ceil_div<int64_t>(n, hk::TF1);
+        gmm_h_image_kernel<<<(unsigned)nsuper, 256, 0, st>>>(X + (lo + s0) * D, n, D, sc,
+                                                              reinterpret_cast<unsigned char*>(g->d_himgA),
+                                                              reinterpret_cast<unsigned char*>(g->d_himgT));
+        ODIN_LAUNCH_CHECK("gmm_h_image_kernel");
+        rc = h_launch_passes(g, sc, reinterpret_cast<const unsigned char*>(g->d_himgA),
+                             reinterpret_cast<const unsigned char*>(g->d_himgT), n, sub, sad ? sad + lo + s0 : nullptr, 0,
+                             g->d_utt_acc + (int64_t)j * SD, false, st);
+        if (rc) return rc;
+      }
+    }
+    gmm_h_centre_kernel<<<cnt, 256, 0, st>>>(g->d_utt_acc, SD, D, M, g->d_mean, d_Z + (int64_t)u0 * M,
+                                             d_Fhat + (int64_t)u0 * M * D);
+    ODIN_LAUNCH_CHECK("gmm_h_centre_kernel");
+  }
+  return ODIN_OK;
+}
+
 // ---- prepared frames: the operand images depend on the data only, so a resident frame matrix
 // that is visited once per EM iteration gets them built ONCE (1 KB per frame)
 struct GmmFrames {

@@ -2,6 +2,8 @@
 against the fp64 oracle, the fp32 CUDA-core kernels (impl=1) and the 3xTF32 kernels
 (impl=2).  Tolerance (north_star): <= 1e-3 on N/F/S as max|a-b| / max|b|; the split
 keeps ~22 significant bits, which TIGHT pins."""
+import os
+
 import numpy as np
 import pytest
 
@@ -150,3 +152,36 @@ def test_h_prepared_frames_equal_per_call_images(monkeypatch):
   Z, F, S, L = g.expectation(frames)
   z, f, s, l, n = OG.expectation(X.cpu().numpy(), g.mean, g.sigma, g.w, compute_dtype=np.float64)
   assert max(relmax(Z, z), relmax(F, f), relmax(S, s)) < TIGHT
+
+
+def test_h_per_utterance_statistics():
+  """GMM.transform_to_disk on long utterances at a tensor-core-sized model: per-utterance Z / F-hat through the
+  tcgen05 E-step (one accumulator per utterance, odin_gmm_utt_stats -> gmm_utt_stats_h) vs the oracle, with a SAD
+  mask, an empty utterance and lengths that are not multiples of the 128-frame operand tile."""
+  import tempfile
+  from odin_b200.ml import GMM
+  from oracle import gmm as OG
+  rng = np.random.RandomState(21)
+  D, M = 60, 256
+  lens = [1500, 3001, 0, 1277, 2048, 4100, 1030]
+  off = np.concatenate([[0], np.cumsum(lens)])
+  cents = rng.randn(M, D).astype(np.float32) * 2
+  X = (cents[rng.randint(0, M, size=off[-1])] + rng.randn(off[-1], D)).astype(np.float32)
+  mean = cents.T.copy()
+  sigma = (0.6 + rng.rand(D, M)).astype(np.float32)
+  w = (rng.rand(1, M) + 0.5).astype(np.float32)
+  w /= w.sum()
+  g = GMM(nmix=M, nmix_start=M)
+  g.initialize(X)
+  g.mean, g.sigma, g.w = mean, sigma, w
+  sad = (rng.rand(off[-1]) > 0.3).astype(np.uint8)
+  indices = [("u%d" % i, (int(off[i]), int(off[i + 1]))) for i in range(len(lens)) if lens[i] > 0]
+  for mask in (None, sad):
+    with tempfile.TemporaryDirectory() as d:
+      pz, pf = os.path.join(d, "z.npy"), os.path.join(d, "f.npy")
+      names = g.transform_to_disk(X, indices, sad=mask, pathZ=pz, pathF=pf)
+      Zu, Fu = np.load(pz), np.load(pf)
+    nr, zr, fr = OG.utterance_stats(X, [(n, dict(indices)[n]) for n in names], mean, sigma, w, sad=mask,
+                                    compute_dtype=np.float64)
+    assert nr == names and Zu.shape == zr.shape and Fu.shape == fr.shape
+    assert relmax(Zu, zr) < 5e-5 and relmax(Fu, fr) < 5e-5, (relmax(Zu, zr), relmax(Fu, fr))
