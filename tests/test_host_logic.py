@@ -239,3 +239,24 @@ def test_fusion_plan_of_the_fsdd_recipe():
   # AcousticNorm argument checks (speech.py:1571-1579)
   with pytest.raises(ValueError):
     pp.AcousticNorm('mfcc', win_length=300)
+
+
+def test_plan_fusion_variants():
+  """Planning is host logic: which extractor runs take the reader's DC removal / the pre-emphasis into their kernels."""
+  from odin_b200 import preprocessing as pp
+  from odin_b200.preprocessing.speech import FusedSpeechFrontEnd
+  p = pp.make_pipeline([pp.AudioReader(), pp.PreEmphasis(0.97), pp.SpectraExtractor(0.025, 0.010, n_mels=40, n_ceps=13)])
+  assert [type(x).__name__ for x in p.plan] == ["SpectraExtractor"]
+  assert p.plan[0]._reader is not None and p.plan[0]._preemph.coeff == 0.97 and p.plan[0].is_input_layer
+  p = pp.make_pipeline([pp.AudioReader(), pp.Framing(0.025, 0.010), pp.CalculateEnergy(), pp.StackFeatures(2, "frames")])
+  assert [type(x).__name__ for x in p.plan] == ["Framing", "CalculateEnergy", "StackFeatures"]
+  assert p.plan[0]._reader is not None and p.plan[0]._preemph is None
+  p = pp.make_pipeline([pp.AudioReader(), pp.PreEmphasis(0.97), pp.STFTExtractor(0.025, 0.010, padding=True),
+                        pp.PowerSpecExtractor(), pp.MelsSpecExtractor(24), pp.MFCCsExtractor(13),
+                        pp.SADgmm(input_name="stft_energy"), pp.RASTAfilter(True, 1, "mfcc")])
+  assert isinstance(p.plan[0], FusedSpeechFrontEnd) and p.plan[0]._config(16000).padding == 1
+  assert [type(x).__name__ for x in p.plan[1:]] == ["RASTAfilter"]
+  # DC removal only exists inside the kernels: a reader that nothing fuses with must not silently skip it
+  with pytest.raises(NotImplementedError):
+    pp.make_pipeline([pp.AudioReader(remove_dc=True), pp.StackFeatures(2, "raw")])
+  assert len(pp.make_pipeline([pp.AudioReader(remove_dc=False), pp.StackFeatures(2, "x")]).plan) == 2
