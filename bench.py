@@ -40,7 +40,7 @@ NMIX = 2048
 def parse():
   p = argparse.ArgumentParser()
   p.add_argument("--gpus", type=int, default=1)
-  p.add_argument("--steps", type=int, default=5)
+  p.add_argument("--steps", type=int, default=20)
   p.add_argument("--warmup", type=int, default=3)
   p.add_argument("--impl", default="ours", choices=["ours", "reference"])
   p.add_argument("--frames", type=int, default=6_000_000, help="frames per GPU (60-dim fp32)")

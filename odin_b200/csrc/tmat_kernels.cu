@@ -15,7 +15,7 @@
 //
 // Kernels
 //   tmat_refresh_kernel   one CTA per mixture (T2 block in smem)
-//   tmat_gemm_kernel      64x64x16 register-blocked fp64 GEMM with generic strides (all four products)
+//   tmat_gemm_kernel      128x64x16 register-blocked (8x4 per thread) fp64 GEMM with generic strides (all products)
 //   tmat_file_kernel      one CTA per file: the tv x tv system lives in ONE padded smem square --
 //                         Cholesky factor in the lower triangle, its inverse written transposed into the
 //                         upper triangle, Cxx = G^-T G^-1 back into the lower triangle -- so tv = 128 fits
@@ -76,20 +76,22 @@ __global__ void __launch_bounds__(256) tmat_refresh_kernel(const double* __restr
 // ---------------------------------------------------------------------------
 // C[M, N] = beta C + sum_k A(i, k) B(k, j);  A(i, k) = A[i sai + k sak],  B(k, j) = B[k sbk + j sbj]
 // ---------------------------------------------------------------------------
-constexpr int GB = 64, GK = 16;
+constexpr int GBM = 128, GBN = 64, GK = 16;   // CTA tile 128 x 64, 256 threads, 8 x 4 outputs per thread
 
 // gridDim.z > 1: split-K -- slice z of the K range writes its partial product (beta ignored) to C + z * M * ldc of a
 // workspace; tmat_splitk_reduce_kernel adds the slices in a fixed order.
-__global__ void __launch_bounds__(256) tmat_gemm_kernel(int M, int N, int K, const double* __restrict__ A, int64_t sai,
-                                                        int64_t sak, const double* __restrict__ B, int64_t sbk,
-                                                        int64_t sbj, double* __restrict__ C, int64_t ldc, double beta) {
-  __shared__ double As[GK][GB + 1];
-  __shared__ double Bs[GK][GB + 1];
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int i0 = blockIdx.y * GB, j0 = blockIdx.x * GB;
-  double acc[4][4];
+// Per k step a thread reads 8 + 4 operands (16-byte shared loads, the A operands of a warp are two broadcast rows)
+// for 32 DFMAs: the first version's 4 x 4 tile spent as many shared-memory wavefronts as fp64 issue cycles.
+__global__ void __launch_bounds__(256, 2) tmat_gemm_kernel(int M, int N, int K, const double* __restrict__ A, int64_t sai,
+                                                           int64_t sak, const double* __restrict__ B, int64_t sbk,
+                                                           int64_t sbj, double* __restrict__ C, int64_t ldc, double beta) {
+  __shared__ __align__(16) double As[GK][GBM + 2];
+  __shared__ __align__(16) double Bs[GK][GBN + 2];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;   // thread: rows 8 ty .. 8 ty + 7, cols 4 tx .. 4 tx + 3
+  const int i0 = blockIdx.y * GBM, j0 = blockIdx.x * GBN;
+  double acc[8][4];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int a = 0; a < 8; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
   int kbeg = 0, kend = K;
@@ -103,39 +105,45 @@ __global__ void __launch_bounds__(256) tmat_gemm_kernel(int M, int N, int K, con
   for (int k0 = kbeg; k0 < kend; k0 += GK) {
     // tile loads: consecutive threads walk the unit-stride dimension of each operand
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int idx = tid + e * 256;   // 0 .. 1023
+    for (int e = 0; e < (GBM * GK) / 256; ++e) {
+      const int idx = tid + e * 256;
       int ii, kk;
-      if (sak == 1) { kk = idx & (GK - 1); ii = idx >> 4; } else { ii = idx & (GB - 1); kk = idx >> 6; }
+      if (sak == 1) { kk = idx & (GK - 1); ii = idx >> 4; } else { ii = idx & (GBM - 1); kk = idx >> 7; }
       const int gi = i0 + ii, gk = k0 + kk;
       As[kk][ii] = (gi < M && gk < kend) ? A[(int64_t)gi * sai + (int64_t)gk * sak] : 0.0;
+    }
+#pragma unroll
+    for (int e = 0; e < (GBN * GK) / 256; ++e) {
+      const int idx = tid + e * 256;
       int jj, kb;
-      if (sbk == 1) { kb = idx & (GK - 1); jj = idx >> 4; } else { jj = idx & (GB - 1); kb = idx >> 6; }
+      if (sbk == 1) { kb = idx & (GK - 1); jj = idx >> 4; } else { jj = idx & (GBN - 1); kb = idx >> 6; }
       const int gj = j0 + jj, gkb = k0 + kb;
       Bs[kb][jj] = (gj < N && gkb < kend) ? B[(int64_t)gkb * sbk + (int64_t)gj * sbj] : 0.0;
     }
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < GK; ++kk) {
-      double av[4], bv[4];
+      double av[8], bv[4];
+      const double2* ap = reinterpret_cast<const double2*>(&As[kk][8 * ty]);
+      const double2* bp = reinterpret_cast<const double2*>(&Bs[kk][4 * tx]);
 #pragma unroll
-      for (int a = 0; a < 4; ++a) av[a] = As[kk][ty + 16 * a];
+      for (int a = 0; a < 4; ++a) { const double2 t = ap[a]; av[2 * a] = t.x; av[2 * a + 1] = t.y; }
 #pragma unroll
-      for (int b = 0; b < 4; ++b) bv[b] = Bs[kk][tx + 16 * b];
+      for (int b = 0; b < 2; ++b) { const double2 t = bp[b]; bv[2 * b] = t.x; bv[2 * b + 1] = t.y; }
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < 8; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const int gi = i0 + ty + 16 * a;
+  for (int a = 0; a < 8; ++a) {
+    const int gi = i0 + 8 * ty + a;
     if (gi >= M) continue;
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
-      const int gj = j0 + tx + 16 * b;
+      const int gj = j0 + 4 * tx + b;
       if (gj >= N) continue;
       double* c = C + (int64_t)gi * ldc + gj;
       *c = (beta == 0.0) ? acc[a][b] : fma(beta, *c, acc[a][b]);
@@ -158,7 +166,7 @@ __global__ void __launch_bounds__(256) tmat_splitk_reduce_kernel(const double* _
 static int gemm(int M, int N, int K, const double* A, int64_t sai, int64_t sak, const double* B, int64_t sbk, int64_t sbj,
                 double* C, int64_t ldc, double beta, cudaStream_t st, double* ws = nullptr, int64_t ws_cap = 0) {
   if (M <= 0 || N <= 0) return ODIN_OK;
-  dim3 grid((unsigned)ceil_div(N, GB), (unsigned)ceil_div(M, GB));
+  dim3 grid((unsigned)ceil_div(N, GBN), (unsigned)ceil_div(M, GBM));
   const int64_t tiles = (int64_t)grid.x * grid.y;
   int splits = 1;
   if (ws != nullptr && tiles < 2 * sm_count() && K >= 1024) {

@@ -159,8 +159,8 @@ class Tmatrix(object):
     dist = _dist()
     lo, hi = 0, n
     if dist is not None:
-      w, r = dist.get_world_size(), dist.get_rank()
-      lo, hi = (n * r) // w, (n * (r + 1)) // w
+      from ..sharding import file_shard
+      lo, hi = file_shard(n, dist.get_rank(), dist.get_world_size())
     acc = torch.zeros(self._acc_size, dtype=torch.float64, device='cuda')
     # stream the shard through the device in slabs (F is the large operand: nmix * feat_dim doubles per file)
     slab = max(1, int((1 << 30) // (8 * self.nmix * self.feat_dim)))

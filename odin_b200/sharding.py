@@ -47,6 +47,28 @@ def unpack_stats(packed, D, M):
   return Z, F, S, float(packed[-2]), float(packed[-1])
 
 
+def file_shard(n_files, rank, world_size):
+  """Contiguous [lo, hi) range of the files rank `rank` owns in the T-matrix E-step (Tmatrix._estep_device):
+  files are equal-cost there (one tv x tv system each), so an even contiguous split is balanced."""
+  n_files, rank, world_size = int(n_files), int(rank), int(world_size)
+  return (n_files * rank) // world_size, (n_files * (rank + 1)) // world_size
+
+
+def pack_tmat_stats(LU, RU, llk, nframes):
+  """LU [M, t2] | RU [tv, M*D] | llk | nframes -> the packed fp64 vector of odin_tmat_estep (odin_tmat_acc_size)."""
+  return np.concatenate([np.asarray(LU, np.float64).reshape(-1), np.asarray(RU, np.float64).reshape(-1),
+                         [float(llk), float(nframes)]])
+
+
+def unpack_tmat_stats(packed, nmix, tv_dim, feat_dim):
+  packed = np.asarray(packed, dtype=np.float64)
+  t2 = tv_dim * (tv_dim + 1) // 2
+  nLU = nmix * t2
+  LU = packed[:nLU].reshape(nmix, t2)
+  RU = packed[nLU:nLU + tv_dim * nmix * feat_dim].reshape(tv_dim, nmix * feat_dim)
+  return LU, RU, float(packed[-2]), float(packed[-1])
+
+
 def _dist():
   import torch.distributed as td
   if td.is_available() and td.is_initialized() and td.get_world_size() > 1:

@@ -108,3 +108,77 @@ def test_two_ranks_allreduce_matches_single_process():
                   for i in range(N_UTT)])
   assert np.array_equal(got[0][5], got[1][5]) and np.allclose(got[0][5], ref, rtol=1e-12)
   assert sorted(got[0][6] + got[1][6]) == list(range(N_UTT))
+
+
+# ---------------------------------------------------------------------------
+# T-matrix E-step: contiguous file shards, one all-reduce of LU | RU | llk | nframes
+# ---------------------------------------------------------------------------
+def _tmat_data():
+  from oracle import tmatrix as OT
+  from oracle.make_golden import _tmat_problem
+  sigma, Z, F = _tmat_problem(seed=17, D=5, M=6, n_files=31)
+  Z = np.round(Z)                       # integer frame counts: ceil(sum Z) is then shard-independent
+  Sigma = OT.sigma_row(sigma)
+  T0 = OT.init_T(4, Sigma)
+  T_invS, T_invS_Tt = OT.refresh(T0, Sigma, 5)
+  return sigma, Z, F, T_invS, T_invS_Tt
+
+
+def _tmat_worker(rank, world, port, q):
+  import torch
+  import torch.distributed as td
+  from oracle import tmatrix as OT
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  td.init_process_group("gloo", rank=rank, world_size=world)
+  try:
+    sigma, Z, F, T_invS, T_invS_Tt = _tmat_data()
+    lo, hi = sharding.file_shard(Z.shape[0], rank, world)
+    LU, RU, llk, nfr = OT.expectation(Z[lo:hi], F[lo:hi], T_invS, T_invS_Tt)
+    stats = torch.from_numpy(sharding.pack_tmat_stats(LU, RU, llk, nfr))
+    sharding.allreduce_stats(stats)
+    LU, RU, llk, nfr = sharding.unpack_tmat_stats(stats.numpy(), 6, 4, 5)
+    T1 = OT.maximization(LU, RU, nfr, 5)                      # replicated M-step
+    q.put((rank, stats.numpy().copy(), T1, (lo, hi)))
+  finally:
+    td.destroy_process_group()
+
+
+def test_file_shard_properties():
+  for n in (0, 1, 7, 31, 1000):
+    for world in (1, 2, 3, 8):
+      parts = [sharding.file_shard(n, r, world) for r in range(world)]
+      assert parts[0][0] == 0 and parts[-1][1] == n
+      assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))           # contiguous partition
+      sizes = [hi - lo for lo, hi in parts]
+      assert max(sizes) - min(sizes) <= 1
+  rng = np.random.RandomState(2)
+  LU, RU = rng.rand(6, 10), rng.rand(4, 30)
+  p = sharding.pack_tmat_stats(LU, RU, -3.5, 1234)
+  assert p.shape[0] == 6 * 10 + 4 * 30 + 2
+  a, b, c, d = sharding.unpack_tmat_stats(p, 6, 4, 5)
+  assert np.array_equal(a, LU) and np.array_equal(b, RU) and c == -3.5 and d == 1234
+
+
+@pytest.mark.timeout(120)
+def test_two_ranks_tmatrix_estep_matches_single_process():
+  import torch.multiprocessing as mp
+  from oracle import tmatrix as OT
+  ctx = mp.get_context("spawn")
+  q = ctx.Queue()
+  port = _free_port()
+  procs = [ctx.Process(target=_tmat_worker, args=(r, 2, port, q)) for r in range(2)]
+  for p in procs:
+    p.start()
+  got = [q.get(timeout=100) for _ in procs]
+  for p in procs:
+    p.join(timeout=30)
+    assert p.exitcode == 0
+  got.sort(key=lambda t: t[0])
+  sigma, Z, F, T_invS, T_invS_Tt = _tmat_data()
+  LU, RU, llk, nfr = OT.expectation(Z, F, T_invS, T_invS_Tt)
+  whole = sharding.pack_tmat_stats(LU, RU, llk, nfr)
+  for rank, stats, T1, (lo, hi) in got:
+    assert np.allclose(stats, whole, rtol=1e-11, atol=1e-11)
+  assert np.array_equal(got[0][2], got[1][2])                    # bit-identical replicated M-step
+  assert got[0][3][1] == got[1][3][0] and got[1][3][1] == Z.shape[0]
