@@ -150,6 +150,19 @@ int odin_feat_rasta_sdc(const float* d_x, float* d_y, int32_t dim, const int64_t
 int odin_feat_energy(const float* d_frames, float* d_energy, int64_t n_frames, int32_t frame_len, int32_t take_log,
                      void* stream);
 
+/* The two SAD extractors on ANY per-frame energy feature of a ragged batch (d_energy [T] float32, h_frame_offsets
+ * [n_utt+1] HOST), without a front-end handle -- the same kernels odin_fe_run uses on the STFT energy / c0:
+ *   odin_vad_gmm        SADgmm._transform = signal.vad_energy + smooth (speech.py:1439-1477, signal.py:293-331, 969-1000);
+ *                       mode = 2.0 is VAD_MODE_STANDARD (signal.py:275-278)
+ *   odin_vad_threshold  SADthreshold._transform (speech.py:1299-1332, 1415-1436)
+ * d_sad [T] uint8, d_threshold [n_utt] double (nullable). */
+int odin_vad_gmm(const float* d_energy, const int64_t* h_frame_offsets, int32_t n_utt, int32_t nb_mixture,
+                 int32_t nb_train_it, int32_t smooth_window, float mode, uint8_t* d_sad, double* d_threshold,
+                 void* stream);
+int odin_vad_threshold(const float* d_energy, const int64_t* h_frame_offsets, int32_t n_utt, float energy_threshold,
+                       float energy_mean_scale, int32_t frame_context, float proportion_threshold,
+                       int32_t smooth_window, uint8_t* d_sad, double* d_threshold, void* stream);
+
 /* ApplyingSAD (speech.py:1732-1756): order-preserving row compaction of `d_feat`
  * [T, dim] by the mask.  d_out_offsets [n_utt+1] receives the compacted utterance
  * boundaries (d_out_offsets[n_utt] = number of rows written).  keep_unvoiced = 1

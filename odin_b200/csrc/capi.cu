@@ -435,6 +435,30 @@ int odin_fe_frames(odin_fe_t* fe, const void* d_pcm, int32_t pcm_dtype, const in
   return fe_frames_launch(fe, d_pcm, pcm_dtype, n_utt, T, nt1, d_frames, d_energy, st);
 }
 
+int odin_vad_gmm(const float* d_energy, const int64_t* h_frame_offsets, int32_t n_utt, int32_t nb_mixture,
+                 int32_t nb_train_it, int32_t smooth_window, float mode, uint8_t* d_sad, double* d_threshold,
+                 void* stream) {
+  if (!d_energy || !h_frame_offsets || !d_sad || n_utt < 0) return set_error(ODIN_EINVAL, "bad argument");
+  if (nb_mixture < 2 || nb_mixture > 4) return set_error(ODIN_EINVAL, "nb_mixture must be 2..4");
+  int rc = require_device();
+  if (rc) return rc;
+  if (n_utt == 0) return ODIN_OK;
+  return fe_vad_standalone(1, d_energy, h_frame_offsets, n_utt, nb_mixture, nb_train_it, smooth_window, (double)mode, 0, 0,
+                           0, 0, d_sad, d_threshold, as_stream(stream));
+}
+
+int odin_vad_threshold(const float* d_energy, const int64_t* h_frame_offsets, int32_t n_utt, float energy_threshold,
+                       float energy_mean_scale, int32_t frame_context, float proportion_threshold,
+                       int32_t smooth_window, uint8_t* d_sad, double* d_threshold, void* stream) {
+  if (!d_energy || !h_frame_offsets || !d_sad || n_utt < 0) return set_error(ODIN_EINVAL, "bad argument");
+  int rc = require_device();
+  if (rc) return rc;
+  if (n_utt == 0) return ODIN_OK;
+  return fe_vad_standalone(2, d_energy, h_frame_offsets, n_utt, 3, 25, smooth_window, 2.0, (double)energy_threshold,
+                           (double)energy_mean_scale, (double)proportion_threshold, frame_context, d_sad, d_threshold,
+                           as_stream(stream));
+}
+
 int odin_fe_compact(odin_fe_t* fe, const uint8_t* d_sad, const int64_t* h_frame_offsets, int32_t n_utt,
                     const float* d_feat, int32_t dim, int32_t keep_unvoiced, float* d_out, int64_t* d_out_offsets,
                     void* stream) {

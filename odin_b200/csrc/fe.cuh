@@ -63,6 +63,9 @@ int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t 
               uint8_t* d_sad, double* d_sad_thr, float* d_spec, int spec_log, cudaStream_t st);
 int fe_frames_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t total_frames, int64_t n_tiles,
                      float* d_frames, float* d_energy, cudaStream_t st);
+int fe_vad_standalone(int kind, const float* d_x, const int64_t* h_fo, int n_utt, int nmix, int iters, int smooth,
+                      double mode, double thr_energy, double thr_mean_scale, double thr_proportion, int thr_context,
+                      uint8_t* d_sad, double* d_thr, cudaStream_t st);
 int fe_cmvn_launch(const float* d_x, float* d_y, int dim, const int64_t* d_frame_off, int n_utt,
                    const uint8_t* d_sad, int mean_var_norm, int var_norm, int windowed, int win_length,
                    cudaStream_t st);

@@ -32,6 +32,9 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <algorithm>
+#include <vector>
+
 #include <cooperative_groups.h>
 
 #include "fe.cuh"
@@ -1598,6 +1601,112 @@ static int dispatch_frame4(int N, const FrameArgs& a, cudaStream_t st) {
   return set_error(ODIN_EINVAL, "n_fft %d unsupported by the four-step kernel", N);
 }
 
+// Launches the SAD kernels for a ragged batch: kind 1 = SADgmm (cluster kernel for long utterances, warp kernel for
+// many short ones), otherwise SADthreshold.  `fo` = HOST frame offsets [n_utt + 1]; v.order must list the
+// utterances longest first (or be null when the legacy order is forced).
+static int vad_dispatch(const VadArgs& v, int kind, const int64_t* fo, int n_utt, cudaStream_t vst) {
+    {
+      int warps_per_cta = 4;
+      int grid = (int)std::min<int64_t>(ceil_div(n_utt, warps_per_cta), (int64_t)sm_count() * 8);
+      if (kind == 1) {
+        // Utterances of up to VAD_WARP_MAX_T frames go to the warp-per-utterance kernel, longer ones to the
+        // cluster kernel.  The visiting order is longest first, so the long ones are its first n_long entries.
+        const char* lpt = getenv("ODIN_FE_VAD_LPT");
+        const char* nowarp = getenv("ODIN_FE_VAD_NOWARP");   // A/B runs
+        int n_long = n_utt;
+        int64_t max_T = 0;
+        for (int u = 0; u < n_utt; ++u) max_T = std::max(max_T, fo[u + 1] - fo[u]);
+        if (!(lpt && lpt[0] == '0') && !(nowarp && nowarp[0] == '1')) {
+          n_long = 0;
+          for (int u = 0; u < n_utt; ++u) n_long += (fo[u + 1] - fo[u]) > VAD_WARP_MAX_T;
+          // a warp takes ~2x longer over ONE utterance than a CTA does, so the warp kernel only pays once there are
+          // enough short utterances to fill the SMs with warps (measured: 100 x 3 s 0.13 ms on CTAs vs 0.24 on warps;
+          // 2 000 x 3 s 0.84 vs 0.29)
+          if (n_utt - n_long < 4 * sm_count()) n_long = n_utt;
+        }
+        if (n_long > 0) {
+          // cluster size: the largest power of two that keeps the batch within ~3 CTAs per SM (2 are
+          // resident at once; measured on the config-3 shard, 216 utterances: 1 -> 0.82 ms, 2 -> 0.61,
+          // 4 -> 0.66, 8 -> 1.17); clusters start longest utterance first and the hardware hands the
+          // next one to whichever SMs free up
+          int ncta = 1;
+          while (ncta < VAD_CL_MAX && (int64_t)n_long * (ncta * 2) <= (int64_t)sm_count() * 3) ncta *= 2;
+          // ... but never more CTAs than the longest utterance can feed (>= 4 frames per thread)
+          while (ncta > 1 && max_T < (int64_t)4 * VAD_THREADS * ncta) ncta /= 2;
+          if (const char* ev = getenv("ODIN_FE_VAD_NCTA")) {   // A/B runs
+            const int v2 = atoi(ev);
+            if (v2 == 1 || v2 == 2 || v2 == 4 || v2 == 8) ncta = v2;
+          }
+          VadArgs vl = v;
+          vl.n_utt = n_long;
+          const int64_t n_cl = std::min<int64_t>(n_long, (int64_t)sm_count() * 4);
+          cudaLaunchConfig_t cfg = {};
+          cfg.gridDim = dim3((unsigned)(n_cl * ncta));
+          cfg.blockDim = dim3(VAD_THREADS);
+          cfg.dynamicSmemBytes = 0;
+          cfg.stream = vst;
+          cudaLaunchAttribute attr[1];
+          attr[0].id = cudaLaunchAttributeClusterDimension;
+          attr[0].val.clusterDim.x = (unsigned)ncta;
+          attr[0].val.clusterDim.y = 1;
+          attr[0].val.clusterDim.z = 1;
+          cfg.attrs = attr;
+          cfg.numAttrs = 1;
+          ODIN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, fe_vad_gmm_kernel, vl));
+          ODIN_LAUNCH_CHECK("fe_vad_gmm_kernel");
+        }
+        if (n_long < n_utt) {
+          const int n_short = n_utt - n_long;
+          const int wgrid = (int)std::min<int64_t>(ceil_div(n_short, VAD_WARPS), (int64_t)sm_count() * 8);
+          fe_vad_gmm_warp_kernel<<<wgrid, VAD_THREADS, 0, vst>>>(v, n_long);
+          ODIN_LAUNCH_CHECK("fe_vad_gmm_warp_kernel");
+        }
+      } else {
+        fe_vad_thr_kernel<<<grid, 128, 0, vst>>>(v);
+        ODIN_LAUNCH_CHECK("fe_vad_thr_kernel");
+      }
+    }
+  return ODIN_OK;
+}
+
+// SAD on given per-frame energies, without a front-end handle (SADgmm / SADthreshold applied to any energy
+// feature of a pipeline, signal.vad_split_audio): temporaries are stream-ordered allocations.
+int fe_vad_standalone(int kind, const float* d_x, const int64_t* h_fo, int n_utt, int nmix, int iters, int smooth,
+                      double mode, double thr_energy, double thr_mean_scale, double thr_proportion, int thr_context,
+                      uint8_t* d_sad, double* d_thr, cudaStream_t st) {
+  const int64_t T = h_fo[n_utt] - h_fo[0];
+  if (T <= 0) return ODIN_OK;
+  std::vector<int64_t> host(2 * (size_t)n_utt + 1);
+  for (int u = 0; u <= n_utt; ++u) host[u] = h_fo[u] - h_fo[0];
+  {
+    std::vector<int> idx(n_utt);
+    for (int u = 0; u < n_utt; ++u) idx[u] = u;
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return host[a + 1] - host[a] > host[b + 1] - host[b]; });
+    for (int i = 0; i < n_utt; ++i) host[n_utt + 1 + i] = idx[i];
+  }
+  int64_t* d_meta = nullptr;
+  float* d_scratch = nullptr;
+  ODIN_CUDA_CHECK(cudaMallocAsync(&d_meta, sizeof(int64_t) * host.size(), st));
+  cudaError_t e = cudaMallocAsync(&d_scratch, sizeof(float) * (size_t)(T + T / 8 + 256), st);
+  if (e != cudaSuccess) { cudaFreeAsync(d_meta, st); return set_error(ODIN_ENOMEM, "SAD scratch: %s", cudaGetErrorString(e)); }
+  // pageable source: the copy is staged before the call returns, so `host` may go out of scope
+  e = cudaMemcpyAsync(d_meta, host.data(), sizeof(int64_t) * host.size(), cudaMemcpyHostToDevice, st);
+  int rc = ODIN_OK;
+  if (e != cudaSuccess) rc = set_error(ODIN_ECUDA, "cudaMemcpyAsync: %s", cudaGetErrorString(e));
+  if (rc == ODIN_OK) {
+    VadArgs v{};
+    v.frame_off = d_meta; v.order = d_meta + n_utt + 1; v.n_utt = n_utt;
+    v.x = d_x + h_fo[0]; v.sad = d_sad + h_fo[0]; v.thr_out = d_thr; v.scratch = d_scratch;
+    v.nmix = nmix; v.iters = iters; v.smooth = smooth; v.mode = mode;
+    v.thr_energy = thr_energy; v.thr_mean_scale = thr_mean_scale; v.thr_proportion = thr_proportion;
+    v.thr_context = thr_context;
+    rc = vad_dispatch(v, kind, host.data(), n_utt, st);
+  }
+  cudaFreeAsync(d_scratch, st);
+  cudaFreeAsync(d_meta, st);
+  return rc;
+}
+
 int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t total_frames, int64_t n_tiles,
               int64_t n_tiles2, float* d_mspec, float* d_feat, float* d_energy, float* d_c0, uint8_t* d_sad,
               double* d_sad_thr, float* d_spec, int spec_log, cudaStream_t st) {
@@ -1685,70 +1794,11 @@ int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t 
         fe->vad_scratch_cap = total_frames + total_frames / 8 + 256;
       }
       v.scratch = fe->d_vad_scratch;
-      int warps_per_cta = 4;
-      int grid = (int)std::min<int64_t>(ceil_div(n_utt, warps_per_cta), (int64_t)sm_count() * 8);
-      if (c.vad_kind == 1) {
-        if (d_energy == nullptr) return set_error(ODIN_EINVAL, "SADgmm needs d_energy");
-        v.x = d_energy;
-        // Utterances of up to VAD_WARP_MAX_T frames go to the warp-per-utterance kernel, longer ones to the
-        // cluster kernel.  The visiting order is longest first, so the long ones are its first n_long entries.
-        const int64_t* fo = fe->h_stage + ((size_t)fe->cap_utt + 1);
-        const char* lpt = getenv("ODIN_FE_VAD_LPT");
-        const char* nowarp = getenv("ODIN_FE_VAD_NOWARP");   // A/B runs
-        int n_long = n_utt;
-        int64_t max_T = 0;
-        for (int u = 0; u < n_utt; ++u) max_T = std::max(max_T, fo[u + 1] - fo[u]);
-        if (!(lpt && lpt[0] == '0') && !(nowarp && nowarp[0] == '1')) {
-          n_long = 0;
-          for (int u = 0; u < n_utt; ++u) n_long += (fo[u + 1] - fo[u]) > VAD_WARP_MAX_T;
-          // a warp takes ~2x longer over ONE utterance than a CTA does, so the warp kernel only pays once there are
-          // enough short utterances to fill the SMs with warps (measured: 100 x 3 s 0.13 ms on CTAs vs 0.24 on warps;
-          // 2 000 x 3 s 0.84 vs 0.29)
-          if (n_utt - n_long < 4 * sm_count()) n_long = n_utt;
-        }
-        if (n_long > 0) {
-          // cluster size: the largest power of two that keeps the batch within ~3 CTAs per SM (2 are
-          // resident at once; measured on the config-3 shard, 216 utterances: 1 -> 0.82 ms, 2 -> 0.61,
-          // 4 -> 0.66, 8 -> 1.17); clusters start longest utterance first and the hardware hands the
-          // next one to whichever SMs free up
-          int ncta = 1;
-          while (ncta < VAD_CL_MAX && (int64_t)n_long * (ncta * 2) <= (int64_t)sm_count() * 3) ncta *= 2;
-          // ... but never more CTAs than the longest utterance can feed (>= 4 frames per thread)
-          while (ncta > 1 && max_T < (int64_t)4 * VAD_THREADS * ncta) ncta /= 2;
-          if (const char* ev = getenv("ODIN_FE_VAD_NCTA")) {   // A/B runs
-            const int v2 = atoi(ev);
-            if (v2 == 1 || v2 == 2 || v2 == 4 || v2 == 8) ncta = v2;
-          }
-          VadArgs vl = v;
-          vl.n_utt = n_long;
-          const int64_t n_cl = std::min<int64_t>(n_long, (int64_t)sm_count() * 4);
-          cudaLaunchConfig_t cfg = {};
-          cfg.gridDim = dim3((unsigned)(n_cl * ncta));
-          cfg.blockDim = dim3(VAD_THREADS);
-          cfg.dynamicSmemBytes = 0;
-          cfg.stream = vst;
-          cudaLaunchAttribute attr[1];
-          attr[0].id = cudaLaunchAttributeClusterDimension;
-          attr[0].val.clusterDim.x = (unsigned)ncta;
-          attr[0].val.clusterDim.y = 1;
-          attr[0].val.clusterDim.z = 1;
-          cfg.attrs = attr;
-          cfg.numAttrs = 1;
-          ODIN_CUDA_CHECK(cudaLaunchKernelEx(&cfg, fe_vad_gmm_kernel, vl));
-          ODIN_LAUNCH_CHECK("fe_vad_gmm_kernel");
-        }
-        if (n_long < n_utt) {
-          const int n_short = n_utt - n_long;
-          const int wgrid = (int)std::min<int64_t>(ceil_div(n_short, VAD_WARPS), (int64_t)sm_count() * 8);
-          fe_vad_gmm_warp_kernel<<<wgrid, VAD_THREADS, 0, vst>>>(v, n_long);
-          ODIN_LAUNCH_CHECK("fe_vad_gmm_warp_kernel");
-        }
-      } else {
-        if (d_c0 == nullptr) return set_error(ODIN_EINVAL, "SADthreshold needs d_c0");
-        v.x = d_c0;
-        fe_vad_thr_kernel<<<grid, 128, 0, vst>>>(v);
-        ODIN_LAUNCH_CHECK("fe_vad_thr_kernel");
-      }
+      if (c.vad_kind == 1 && d_energy == nullptr) return set_error(ODIN_EINVAL, "SADgmm needs d_energy");
+      if (c.vad_kind != 1 && d_c0 == nullptr) return set_error(ODIN_EINVAL, "SADthreshold needs d_c0");
+      v.x = (c.vad_kind == 1) ? d_energy : d_c0;
+      int rc_v = vad_dispatch(v, c.vad_kind, fe->h_stage + ((size_t)fe->cap_utt + 1), n_utt, vst);
+      if (rc_v) return rc_v;
     }
     return ODIN_OK;
   };

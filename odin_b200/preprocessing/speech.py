@@ -222,7 +222,10 @@ class SADthreshold(Extractor):
         '0 < proportion_threshold < 1, given: %.2f' % self.proportion_threshold
 
   def _transform(self, X):
-    _no_cpu(self)
+    return _standalone_sad(self, [X])[0]
+
+  def transform_batch(self, Xs):
+    return _standalone_sad_batch(self, Xs)
 
 
 class SADgmm(Extractor):
@@ -236,7 +239,51 @@ class SADgmm(Extractor):
     self.smooth_window = int(smooth_window)
 
   def _transform(self, X):
-    _no_cpu(self)
+    return _standalone_sad(self, [X])[0]
+
+  def transform_batch(self, Xs):
+    return _standalone_sad_batch(self, Xs)
+
+
+def _standalone_sad(ex, Xs):
+  """SADgmm / SADthreshold on an energy feature that is already in the dictionary (not fused behind an STFT):
+  one ragged batch through odin_vad_gmm / odin_vad_threshold.  Returns the output dicts (not merged)."""
+  import torch
+  _lib.require_cuda()
+  lib = _lib.load()
+  es = [np.ascontiguousarray(np.asarray(X[ex.input_name], dtype=np.float32).reshape(-1)) for X in Xs]
+  off = np.zeros(len(es) + 1, dtype=np.int64)
+  np.cumsum([len(e) for e in es], out=off[1:])
+  if off[-1] == 0:
+    return [{ex.output_name: np.zeros(0, np.uint8), '%s_threshold' % ex.output_name: 0.0} for _ in es]
+  d_e = torch.from_numpy(np.concatenate(es)).cuda()
+  d_sad = torch.zeros(int(off[-1]), dtype=torch.uint8, device='cuda')
+  d_thr = torch.zeros(len(es), dtype=torch.float64, device='cuda')
+  if isinstance(ex, SADgmm):
+    _lib.check(lib.odin_vad_gmm(_lib.ptr(d_e), _lib.as_i64_ptr(off), len(es), ex.nb_mixture, ex.nb_train_it,
+                                ex.smooth_window, 2.0, _lib.ptr(d_sad), _lib.ptr(d_thr), _lib.current_stream()))
+  else:
+    _lib.check(lib.odin_vad_threshold(_lib.ptr(d_e), _lib.as_i64_ptr(off), len(es), ex.energy_threshold,
+                                      ex.energy_mean_scale, ex.frame_context, ex.proportion_threshold,
+                                      ex.smooth_window, _lib.ptr(d_sad), _lib.ptr(d_thr), _lib.current_stream()))
+  sad, thr = d_sad.cpu().numpy(), d_thr.cpu().numpy()
+  outs = []
+  for j in range(len(es)):
+    m = sad[off[j]:off[j + 1]]
+    outs.append({ex.output_name: m.copy() if isinstance(ex, SADgmm) else m.astype(bool),
+                 '%s_threshold' % ex.output_name: float(thr[j])})
+  return outs
+
+
+def _standalone_sad_batch(ex, Xs):
+  Xs = list(Xs)
+  checked = [ex._check_input(x) for x in Xs]
+  live = [i for i, c in enumerate(checked) if c is None]
+  outs = _standalone_sad(ex, [Xs[i] for i in live]) if live else []
+  res = list(checked)
+  for i, o in zip(live, outs):
+    res[i] = ex._merge_output(Xs[i], o)
+  return res
 
 
 class ApplyingSAD(Extractor):
@@ -773,7 +820,7 @@ def plan_fusion(extractors):
         raise NotImplementedError(
             "AudioReader(remove_dc=True) at position %d is not followed by a fusable speech step: DC removal "
             "runs inside the fused kernels; odin_b200 has no CPU fallback" % i)
-    if isinstance(e, speech_types) or isinstance(e, DeltaExtractor):
+    if (isinstance(e, speech_types) and not isinstance(e, (SADgmm, SADthreshold))) or isinstance(e, DeltaExtractor):
       raise NotImplementedError(
           "%s at position %d is not part of a fusable run "
           "([AudioReader] [PreEmphasis] STFT PowerSpec MelsSpec [MFCCs [Delta]] [SAD] [ApplyingSAD]); "

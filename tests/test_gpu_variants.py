@@ -53,3 +53,29 @@ def test_rasta_sdc_stack_golden_and_ragged():
   outs = pp.StackFeatures(2, "mfcc").transform_batch([{"mfcc": m} for m in mats])
   for m, o in zip(mats, outs):
     assert np.array_equal(o["mfcc"], F.stack_context(m, 2))
+
+
+def test_standalone_sad_extractors():
+  """SADgmm / SADthreshold on an energy feature that is not produced by the fused STFT (here: CalculateEnergy on
+  explicit frames, and a c0-like feature): bit-exact masks vs the oracle, single and ragged batch."""
+  from odin_b200 import preprocessing as pp
+  from odin_b200 import synth
+  utts = synth.utterance_batch(9, 0.4, 2.2, sr=16000, seed=31)
+  pipe = pp.make_pipeline([pp.AudioReader(remove_dc=True), pp.PreEmphasis(0.97), pp.Framing(0.025, 0.010, window="hamm"),
+                           pp.CalculateEnergy(log=True), pp.SADgmm(3, smooth_window=3, input_name="energy")])
+  assert [type(x).__name__ for x in pipe.plan] == ["Framing", "CalculateEnergy", "SADgmm"]
+  outs = pipe.transform_batch([{"raw": u, "sr": 16000} for u in utts])
+  for u, o in zip(utts, outs):
+    r = F.extract(u, 16000, vad="gmm", fmax=8000)
+    assert relmax(o["energy"], r["stft_energy"]) < 1e-6
+    sad, thr = F.sad_gmm(o["energy"], 3, 25, 3)            # the oracle on the energies the extractor saw
+    assert np.array_equal(o["sad"], sad) and abs(o["sad_threshold"] - thr) < 1e-9
+    one = pp.SADgmm(3, smooth_window=3, input_name="energy").transform({"energy": o["energy"]})
+    assert np.array_equal(one["sad"], o["sad"])
+  rng = np.random.RandomState(8)
+  es = [np.cumsum(rng.randn(n)).astype(np.float32) for n in (7, 60, 333, 5, 1200)]
+  th = pp.SADthreshold(input_name="e", output_name="v")
+  outs = th.transform_batch([{"e": e} for e in es])
+  for e, o in zip(es, outs):
+    s2, t2 = F.sad_threshold(e)
+    assert o["v"].dtype == bool and np.array_equal(o["v"], s2.astype(bool)) and abs(o["v_threshold"] - t2) < 1e-7
