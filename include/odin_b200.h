@@ -149,6 +149,8 @@ int odin_feat_rasta_sdc(const float* d_x, float* d_y, int32_t dim, const int64_t
                         int32_t rasta, int32_t sdc, void* stream);
 int odin_feat_energy(const float* d_frames, float* d_energy, int64_t n_frames, int32_t frame_len, int32_t take_log,
                      void* stream);
+/* signal.smooth(x, win, window='flat') of a 0/1 vector (signal.py:969-1000), float64 out; win >= 3, n >= win. */
+int odin_feat_smooth(const uint8_t* d_x, double* d_y, int64_t n, int32_t win, void* stream);
 
 /* The two SAD extractors on ANY per-frame energy feature of a ragged batch (d_energy [T] float32, h_frame_offsets
  * [n_utt+1] HOST), without a front-end handle -- the same kernels odin_fe_run uses on the STFT energy / c0:

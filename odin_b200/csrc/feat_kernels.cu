@@ -114,6 +114,26 @@ __global__ void __launch_bounds__(256) feat_energy_kernel(const float* __restric
   }
 }
 
+// signal.smooth(x, win, 'flat') (signal.py:969-1000) of a 0/1 vector: mirror extension 2 x[0] - x[win-1::-1] | x |
+// 2 x[-1] - x[-1:-win:-1], np.convolve(w / win, s, 'same')[win : -win + 1].  Output t averages s[t + c .. t + c + win)
+// with c = (win - 1) / 2 + 1; all terms are small integers, so the double result is exact.
+__global__ void __launch_bounds__(256) feat_smooth_kernel(const uint8_t* __restrict__ x, double* __restrict__ y, int64_t n,
+                                                          int win) {
+  const int64_t c = (win - 1) / 2 + 1;
+  for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < n; t += (int64_t)gridDim.x * 256) {
+    long long acc = 0;
+    for (int j = 0; j < win; ++j) {
+      const int64_t i = t + c + j;          // index into the extended vector s
+      int v;
+      if (i < win) v = 2 * (int)(x[0] != 0) - (int)(x[win - 1 - i] != 0);
+      else if (i < win + n) v = (int)(x[i - win] != 0);
+      else v = 2 * (int)(x[n - 1] != 0) - (int)(x[n - 1 - (i - win - n)] != 0);
+      acc += v;
+    }
+    y[t] = (double)acc / (double)win;
+  }
+}
+
 static int upload_offsets(const int64_t* h_off, int n_utt, int64_t** d_off, cudaStream_t st) {
   ODIN_CUDA_CHECK(cudaMallocAsync(d_off, sizeof(int64_t) * (n_utt + 1), st));
   cudaError_t e = cudaMemcpyAsync(*d_off, h_off, sizeof(int64_t) * (n_utt + 1), cudaMemcpyHostToDevice, st);
@@ -185,6 +205,16 @@ int odin_feat_energy(const float* d_frames, float* d_energy, int64_t n_frames, i
   const unsigned grid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(n_frames, 8), (int64_t)sm_count() * 16);
   feat_energy_kernel<<<grid, 256, 0, as_stream(stream)>>>(d_frames, d_energy, n_frames, frame_len, take_log);
   ODIN_LAUNCH_CHECK("feat_energy_kernel");
+  return ODIN_OK;
+}
+
+int odin_feat_smooth(const uint8_t* d_x, double* d_y, int64_t n, int32_t win, void* stream) {
+  if (!d_x || !d_y || n < 0 || win < 3 || n < win) return set_error(ODIN_EINVAL, "bad argument (need win >= 3 and n >= win)");
+  int rc = require_device();
+  if (rc) return rc;
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(n, 256), (int64_t)sm_count() * 8);
+  feat_smooth_kernel<<<grid, 256, 0, as_stream(stream)>>>(d_x, d_y, n, win);
+  ODIN_LAUNCH_CHECK("feat_smooth_kernel");
   return ODIN_OK;
 }
 

@@ -79,3 +79,18 @@ def test_standalone_sad_extractors():
   for e, o in zip(es, outs):
     s2, t2 = F.sad_threshold(e)
     assert o["v"].dtype == bool and np.array_equal(o["v"], s2.astype(bool)) and abs(o["v_threshold"] - t2) < 1e-7
+
+
+@pytest.mark.parametrize("seed,mx,mn,thr", [(5, 5, None, 0.6), (6, 3, 1.0, 0.5), (7, 4, None, 0.8)])
+def test_vad_split_audio(seed, mx, mn, thr):
+  """signal.vad_split_audio (signal.py:341-478) on the GPU kernels vs the oracle (itself checked against the
+  reference in tests/test_oracle_vs_reference.py): identical segments, smoothed VAD curve, voiced and cut indicators."""
+  from odin_b200 import synth
+  from odin_b200.preprocessing import signal
+  s = np.concatenate(synth.utterance_batch(3, 4.0, 6.0, sr=8000, seed=seed)).astype(np.float32)
+  segs, vad, voices, cut = signal.vad_split_audio(s, 8000, mx, mn, 128, 3, thr, return_vad=True, return_voices=True,
+                                                  return_cut=True)
+  o_segs, o_vad, o_voices, o_cut = F.vad_split_audio(s, 8000, mx, mn, 128, 3, thr)
+  assert np.array_equal(vad, o_vad) and np.array_equal(voices, o_voices) and np.array_equal(cut, o_cut)
+  assert len(segs) == len(o_segs) and all(np.array_equal(a, b) for a, b in zip(segs, o_segs))
+  assert signal.vad_split_audio(s[:8000], 8000, 5) [0] is not None and len(signal.vad_split_audio(s[:8000], 8000, 5)) == 1

@@ -117,3 +117,17 @@ def test_tmatrix_matches_reference():
   iv = OT.ivector(Z[:3], F[:3], T_invS, T_invS_Tt)
   ref = np.concatenate([t.transform((Z[i:i + 1], F[i:i + 1])) for i in range(3)], 0)
   assert relmax(iv, ref) < 1e-9
+
+
+@pytest.mark.parametrize("seed,mx,mn,thr", [(5, 5, None, 0.6), (6, 3, 1.0, 0.5)])
+def test_vad_split_audio_matches_reference(seed, mx, mn, thr):
+  _, S = ref_shim.load_frontend()
+  s = np.concatenate(synth.utterance_batch(3, 4.0, 6.0, sr=8000, seed=seed)).astype(np.float32)
+  with warnings.catch_warnings():
+    warnings.simplefilter("ignore")
+    segs, vad, voices, cut = S.vad_split_audio(s, 8000, maximum_duration=mx, minimum_duration=mn, frame_length=128,
+                                               nb_mixtures=3, threshold=thr, return_vad=True, return_voices=True,
+                                               return_cut=True)
+  o = F.vad_split_audio(s, 8000, mx, mn, 128, 3, thr)
+  assert len(segs) == len(o[0]) and all(np.array_equal(a, b) for a, b in zip(segs, o[0]))
+  assert np.array_equal(vad, o[1]) and np.array_equal(voices, o[2]) and np.array_equal(cut, o[3])
