@@ -183,8 +183,10 @@ def run_reference(args):
       "impl": "reference", "metric": "ubm%d_baum_welch_frames_per_s" % args.nmix, "value": val, "unit": "frames/s",
       "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-      "config": {"workload": "2048-mix diagonal UBM EM iteration (N/F/S + M-step), 60-dim MFCC+d+dd frames",
-                 "nmix": args.nmix, "feat_dim": D, "frames_per_step": n},
+      "config": {"workload": "config 4 shard: 2048-mix diagonal UBM EM iteration (N/F/S + NCCL all-reduce + M-step), "
+                             "60-dim frames resident in HBM",
+                 "nmix": args.nmix, "feat_dim": D, "frames_per_step": n,
+                 "note": "the reference's CPU arithmetic (numpy port) on a bounded sample of the same frames"},
       "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
       "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
   }
