@@ -695,7 +695,12 @@ __global__ void __launch_bounds__(hk::THREADS, 1) gmm_h_stats_kernel(HArgs a) {
 // host side
 // ---------------------------------------------------------------------------
 bool gmm_h_supported(const odin_gmm* g) {
-  return g->D % 4 == 0 && g->D <= hk::MAX_D && g->D >= 4 && g->M >= 256;
+  // The kernels pad the mixtures to their 256 / 128-wide tiles, so they run at any M; measured on 1 M frames
+  // (tools/gmm_small_m_sweep.py) the padded tensor-core E-step takes 0.70-0.79 ms for M = 1 .. 256 where the fp32
+  // CUDA-core kernels take 1.7 ms (M <= 64), 3.1 ms (128), 6.0 ms (256) -- so the early stages of the split-and-train
+  // schedule (M = 1, 2, 4, ...) use it too.  ODIN_GMM_H_MIN_M restores a threshold for A/B runs.
+  static const int min_m = [] { const char* e = getenv("ODIN_GMM_H_MIN_M"); return e ? atoi(e) : 1; }();
+  return g->D % 4 == 0 && g->D <= hk::MAX_D && g->D >= 4 && g->M >= min_m;
 }
 
 static int64_t h_sub_batch() {

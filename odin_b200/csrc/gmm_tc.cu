@@ -843,7 +843,8 @@ gmm_tc_combine_kernel(const float2* __restrict__ part, int nchunks, int64_t stri
 // host side
 // ---------------------------------------------------------------------------
 bool gmm_tc_supported(const odin_gmm* g) {
-  return g->D % 4 == 0 && g->D <= tc::MAX_D && g->D >= 4 && g->M >= 96;
+  static const int min_m = [] { const char* e = getenv("ODIN_GMM_TC_MIN_M"); return e ? atoi(e) : 96; }();
+  return g->D % 4 == 0 && g->D <= tc::MAX_D && g->D >= 4 && g->M >= min_m;
 }
 
 int gmm_tc_refresh(odin_gmm* g, cudaStream_t st) {

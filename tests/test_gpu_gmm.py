@@ -117,7 +117,9 @@ def test_linearity_of_statistics_full_size():
   Z, F, S, L = gm.expectation(X)
   Za, Fa, Sa, La = gm.expectation(X[:N // 2])
   Zb, Fb, Sb, Lb = gm.expectation(X[N // 2:])
-  assert relmax(Za + Zb, Z) < 1e-6 and relmax(Fa + Fb, F) < 1e-6 and relmax(Sa + Sb, S) < 1e-6
+  # (each call picks its own power-of-two operand scales on the tensor-core path, which auto-dispatch now uses at every
+  # mixture count: regrouping is exact to its split precision, ~2e-6, not to fp32 rounding)
+  assert relmax(Za + Zb, Z) < 1e-5 and relmax(Fa + Fb, F) < 1e-5 and relmax(Sa + Sb, S) < 1e-5
   assert abs(0.5 * (float(La) + float(Lb)) - float(L)) < 1e-6 * abs(float(L))
   assert abs(Z.sum() - N) < 1e-4 * N
 
@@ -209,7 +211,8 @@ def test_host_array_streaming_equals_resident():
   frames = G._DeviceFrames(X, chunk_frames=7000)
   Zh, Fh, Sh, Lh = gm.expectation(frames)
   # chunk boundaries regroup the fp32 partial sums that are flushed into the fp64 statistics
-  assert relmax(Zh, Zr) < 1e-6 and relmax(Fh, Fr) < 1e-6 and relmax(Sh, Sr) < 1e-6
+  # (and, on the tensor-core path, every chunk gets its own operand scales: equal to its split precision, ~2e-6)
+  assert relmax(Zh, Zr) < 1e-5 and relmax(Fh, Fr) < 1e-5 and relmax(Sh, Sr) < 1e-5
   X16 = X.astype(np.float16)  # float16 stores are up-cast on load
   Z16, F16, S16, L16 = gm.expectation(X16)
   z, f, s, l, _ = OG.expectation(X16.astype(np.float32), mean, sigma, w, compute_dtype=np.float64)
