@@ -271,7 +271,7 @@ def mfcc_leg(torch, args, rank, world, dist, peaks, do_cpu):
       "roofline": {"bound": "hbm", "achieved": bytes_per_frame * T / frame_kernel_s / 1e9, "peak": peaks["hbm_gbs"],
                    "unit": "GB/s", "frac": bytes_per_frame * T / frame_kernel_s / 1e9 / peaks["hbm_gbs"],
                    "traffic": 408.5e6 / 696132 * T, "kernel": "fe_frame4_kernel", "peak_source": peaks["source"],
-                   "note": "algorithmic 885 B/frame; traffic from profiles/r01_fe_ncu_s7_keymetrics.csv (223.2 MB read + 185.3 MB written per 696 132-frame launch: PCM in, unclipped log-mel + energies out; the utterance pass writes the rest); the kernel is issue / FP32 bound (SURVEY 8d), see roofline_fp32 and DESIGN.md"},
+                   "note": "algorithmic 885 B/frame; traffic from profiles/r01_fe_ncu_s10_keymetrics.csv (223.2 MB read + 185.3 MB written per 696 132-frame launch: PCM in, unclipped log-mel + energies out; the utterance pass writes the rest); the kernel is issue / FP32 bound (SURVEY 8d), see roofline_fp32 and DESIGN.md"},
       # the binding resource is the SM, not HBM: algorithmic 35 kFLOP per frame against the
       # FP32 pipe peak 148 SM x 128 lanes x 2 x max SM clock
       "roofline_fp32": {"bound": "fp32", "achieved": 35.0e3 * T / frame_kernel_s / 1e12,
@@ -281,7 +281,7 @@ def mfcc_leg(torch, args, rank, world, dist, peaks, do_cpu):
       # what actually binds the frame kernel: warp-instruction issue slots (4 per SM per cycle).  Not measurable
       # without a profiler, so the figures of the committed capture are quoted, not re-measured per run.
       "roofline_issue": {"bound": "issue", "frac": 0.591, "warp_instructions_per_frame": 1451, "kernel": "fe_frame4_kernel",
-                         "peak_source": "ncu smsp__issue_active / smsp__inst_executed of profiles/r01_fe_ncu_s7_keymetrics.csv "
+                         "peak_source": "ncu smsp__issue_active / smsp__inst_executed of profiles/r01_fe_ncu_s10_keymetrics.csv "
                                         "(same workload); utterance pass 0.62, SADgmm 0.31 (latency / barrier bound)"},
       "e2e": {"value": total_T / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d * world,
               "d2h_bytes_per_step": d2h * world, "call": "FusedSpeechFrontEnd.run_host_packed (%d chunks)" % args.mfcc_chunks},
@@ -455,6 +455,9 @@ def run_ours(args):
   a, b, im = C.c_float(), C.c_float(), C.c_int32()
   _lib.check(lib.odin_gmm_last_estep_ms(g._handle, C.byref(a), C.byref(b), C.byref(im)))
   lse_ms, stats_ms, impl_used = a.value, b.value, im.value
+  lib.odin_gmm_last_estep_frames.restype = C.c_int64
+  n_timed = int(lib.odin_gmm_last_estep_frames(g._handle))   # frames covered by lse_ms / stats_ms (read before the
+                                                             # end-to-end runs below issue their own E-steps)
 
   # ---- e2e: public API, pinned host frames -> device every step, parameters read back ----
   Xh = torch.empty((N, D), dtype=torch.float32).pin_memory()
@@ -482,8 +485,6 @@ def run_ours(args):
   # dominant kernel = statistics kernel (its own log-likelihood GEMM + the statistics GEMM).  Dense
   # peak of the MMA kind: fp16 = the measured bf16 figure, tf32 = half of it; a split-precision
   # product issues 3 MMAs per useful one, so the roofline is peak / 3.
-  lib.odin_gmm_last_estep_frames.restype = C.c_int64
-  n_timed = int(lib.odin_gmm_last_estep_frames(g._handle))   # frames covered by lse_ms / stats_ms
   kind_peak = peaks["bf16_sustained"] if impl_used == 3 else peaks["bf16_sustained"] / 2.0
   stats_useful = (240 + 240) * M * n_timed
   achieved = stats_useful / (stats_ms / 1e3) / 1e12
