@@ -1774,7 +1774,9 @@ int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t 
   // SADgmm reads only the frame energies, so it is forked onto the auxiliary stream and runs beside the
   // utterance pass (its tail is a handful of long utterances); SADthreshold needs c0 and stays in line.
   const bool has_vad = c.vad_kind != 0 && d_sad != nullptr;
-  // (measured: the fork only pays when the utterance pass is long; off unless ODIN_FE_VAD_FORK=1)
+  // (measured again with the current kernels on the config-3 shard: forked 2.59 ms per batch, in line 2.45 -- the
+  // SADgmm CTAs hold every register of an SM, so the utterance pass cannot fill in beside them; off unless
+  // ODIN_FE_VAD_FORK=1)
   const char* wantfork = getenv("ODIN_FE_VAD_FORK");
   const bool fork = has_vad && c.vad_kind == 1 && (wantfork && wantfork[0] == '1');
   fe->vad_forked = fork;
