@@ -33,9 +33,8 @@ def main(n_files=600, nmix=128, tv_dim=64):
       pp.DeltaExtractor(input_name="mfcc", order=(0, 1, 2)),
       pp.RenameFeatures(input_name="mfcc_energy", output_name="energy"),
       pp.SADthreshold(energy_threshold=0.55, smooth_window=5, input_name="energy", output_name="sad"),
-      pp.AcousticNorm(mean_var_norm=True, windowed_mean_var_norm=True, sad_name=None, ignore_sad_error=True,
-                      input_name=("spec", "mspec", "mfcc")),
       pp.DeleteFeatures(input_name=("stft", "spec", "sad_threshold", "sr_copy")),
+      pp.AcousticNorm(mean_var_norm=True, windowed_mean_var_norm=True, input_name=("mspec", "mfcc")),
       pp.AsType(dtype="float16"),
   ])
   t0 = time.perf_counter()
