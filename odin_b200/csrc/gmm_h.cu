@@ -965,7 +965,7 @@ int gmm_estep_frames(odin_gmm* g, const void* pf, const uint8_t* sad, int want_s
                      cudaStream_t st) {
   const GmmFrames* f = reinterpret_cast<const GmmFrames*>(pf);
   if (f->D != g->D) return set_error(ODIN_EINVAL, "prepared frames have D=%d, model has D=%d", f->D, g->D);
-  if (!gmm_h_supported(g)) return set_error(ODIN_EINVAL, "prepared frames need the 3xFP16 path (M >= 256)");
+  if (!gmm_h_supported(g)) return set_error(ODIN_EINVAL, "prepared frames need the 3xFP16 path (D a multiple of 4, M above ODIN_GMM_H_MIN_M)");
   const int64_t N = f->N;
   if (N <= 0) return ODIN_OK;
   const int64_t sub = std::min<int64_t>(h_sub_batch(), ceil_div<int64_t>(N, hk::TF1) * hk::TF1);

@@ -433,8 +433,8 @@ class GMM(object):
       else:
         d_mask = torch.from_numpy(np.ascontiguousarray(mask)).cuda()
     prep = None
-    if self.impl in (0, 3) and self._curr_nmix >= 256 and self._feat_dim % 4 == 0 and self._feat_dim <= 60 \
-        and os.environ.get("ODIN_H_NO_PREPARED", "0") != "1":
+    if self.impl in (0, 3) and self._feat_dim % 4 == 0 and self._feat_dim <= 60 \
+        and os.environ.get("ODIN_H_NO_PREPARED", "0") != "1":   # (the images depend on the data only: every stage of fit)
       prep = frames.prepared(self._handle) if frames.reuse else None
     if prep is not None:
       _lib.check(lib.odin_gmm_estep_frames(self._handle, prep, _lib.ptr(d_mask), 1 if second else 0,
