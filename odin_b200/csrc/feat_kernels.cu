@@ -21,18 +21,38 @@ __device__ __forceinline__ int feat_find(const int64_t* __restrict__ off, int n,
   return lo;
 }
 
+// Frames are walked in contiguous per-CTA ranges: the utterance of the first frame is found by one binary search,
+// after that the index only moves forward (a per-frame search was 11 dependent loads in front of every row and
+// held StackFeatures at 0.9 TB/s).
+struct FrameWalk {
+  int u;
+  int64_t lo, hi;
+  __device__ FrameWalk(const int64_t* __restrict__ off, int n_utt, int64_t t) {
+    u = feat_find(off, n_utt, t);
+    lo = off[u]; hi = off[u + 1];
+  }
+  __device__ __forceinline__ void to(const int64_t* __restrict__ off, int64_t t) {
+    while (t >= hi) { ++u; lo = hi; hi = off[u + 1]; }
+  }
+};
+
 // y[t] = [x[t-c], ..., x[t+c]] flattened, zeros outside the utterance
 __global__ void __launch_bounds__(256) feat_stack_kernel(const float* __restrict__ x, float* __restrict__ y, int dim,
                                                          const int64_t* __restrict__ off, int n_utt, int c) {
   const int64_t T = off[n_utt];
   const int w = (2 * c + 1) * dim;
-  for (int64_t t = blockIdx.x; t < T; t += gridDim.x) {
-    const int u = feat_find(off, n_utt, t);
-    const int64_t lo = off[u], hi = off[u + 1];
+  const int64_t per = (T + gridDim.x - 1) / gridDim.x;
+  const int64_t t_lo = per * blockIdx.x, t_hi = min(T, t_lo + per);
+  if (t_lo >= t_hi) return;
+  FrameWalk fw(off, n_utt, t_lo);
+  const uint32_t mg = 0xFFFFFFFFu / (uint32_t)dim + 1u;   // j / dim by multiply-high (dim > 1; exact for j < 2^16)
+  for (int64_t t = t_lo; t < t_hi; ++t) {
+    fw.to(off, t);
+    float* row = y + t * w;
     for (int j = threadIdx.x; j < w; j += 256) {
-      const int k = j / dim, d = j - k * dim;
+      const int k = (dim == 1) ? j : (int)__umulhi((uint32_t)j, mg), d = j - k * dim;
       const int64_t s = t + k - c;
-      y[t * w + j] = (s >= lo && s < hi) ? x[s * dim + d] : 0.f;
+      row[j] = (s >= fw.lo && s < fw.hi) ? x[s * dim + d] : 0.f;
     }
   }
 }
@@ -40,6 +60,7 @@ __global__ void __launch_bounds__(256) feat_stack_kernel(const float* __restrict
 // RASTA along time, one thread per (utterance, column): scipy's transposed direct-form II recurrence with the
 // reference's warm-up (the first four outputs are zero; the FIR run over them only leaves the filter state).
 // y64 [T, dim] keeps the fp64 result for the delta pass, y32 (row stride ld) receives the float32 cast.
+// The recurrence is sequential in time, so the loads are issued eight rows ahead of the dependent chain.
 __global__ void __launch_bounds__(128) feat_rasta_kernel(const float* __restrict__ x, double* __restrict__ y64,
                                                          float* __restrict__ y32, int ld, int dim,
                                                          const int64_t* __restrict__ off, int n_utt, int rasta) {
@@ -49,50 +70,85 @@ __global__ void __launch_bounds__(128) feat_rasta_kernel(const float* __restrict
   const int64_t lo = off[u], hi = off[u + 1];
   const double b0 = 0.2, b1 = 0.1, b2 = -0.0, b3 = -0.1, b4 = -0.2;   // -arange(-2, 3) / 10
   double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;
-  for (int64_t t = lo; t < hi; ++t) {
-    const double xn = (double)x[t * dim + d];
-    double yn;
-    if (!rasta) {
-      yn = xn;
-    } else if (t - lo < 4) {
-      yn = 0.0;
-      z0 = __dadd_rn(__dmul_rn(b1, xn), z1); z1 = __dadd_rn(__dmul_rn(b2, xn), z2);
-      z2 = __dadd_rn(__dmul_rn(b3, xn), z3); z3 = __dmul_rn(b4, xn);
-    } else {
-      yn = __dadd_rn(__dmul_rn(b0, xn), z0);
-      z0 = __dadd_rn(__dadd_rn(__dmul_rn(b1, xn), z1), __dmul_rn(0.94, yn));
-      z1 = __dadd_rn(__dmul_rn(b2, xn), z2);
-      z2 = __dadd_rn(__dmul_rn(b3, xn), z3);
-      z3 = __dmul_rn(b4, xn);
+  constexpr int PF = 8;
+  for (int64_t t0 = lo; t0 < hi; t0 += PF) {
+    float xv[PF];
+#pragma unroll
+    for (int q = 0; q < PF; ++q) xv[q] = (t0 + q < hi) ? x[(t0 + q) * dim + d] : 0.f;
+#pragma unroll
+    for (int q = 0; q < PF; ++q) {
+      const int64_t t = t0 + q;
+      if (t < hi) {
+        const double xn = (double)xv[q];
+        double yn;
+        if (!rasta) {
+          yn = xn;
+        } else {
+          // one formula for both phases: during the four warm-up frames the output is zero and the pole is off
+          const bool warm = (t - lo) < 4;
+          const double yr = __dadd_rn(__dmul_rn(b0, xn), z0);
+          yn = warm ? 0.0 : yr;
+          const double fb = warm ? 0.0 : __dmul_rn(0.94, yr);
+          z0 = __dadd_rn(__dadd_rn(__dmul_rn(b1, xn), z1), fb);
+          z1 = __dadd_rn(__dmul_rn(b2, xn), z2);
+          z2 = __dadd_rn(__dmul_rn(b3, xn), z3);
+          z3 = __dmul_rn(b4, xn);
+        }
+        y64[t * dim + d] = yn;
+        y32[t * ld + d] = (float)yn;
+      }
     }
-    y64[t * dim + d] = yn;
-    y32[t * ld + d] = (float)yn;
   }
 }
 
-// shifted delta coefficients: block ix of row t = first-order delta (width 2 sdc + 1, clamped edges, cast to
-// float32 like signal.delta) of frame min(t + 3 ix, T_u - 1); written behind the dim leading columns
-__global__ void __launch_bounds__(256) feat_sdc_kernel(const double* __restrict__ y64, float* __restrict__ out, int ld,
-                                                       int dim, const int64_t* __restrict__ off, int n_utt, int sdc) {
+// first-order delta of every frame (width 2 sdc + 1, clamped edges, fp64, cast to float32 like signal.delta)
+__global__ void __launch_bounds__(256) feat_delta1_kernel(const double* __restrict__ y64, float* __restrict__ dx, int dim,
+                                                          const int64_t* __restrict__ off, int n_utt, int sdc) {
   const int64_t T = off[n_utt];
-  const int w = dim * dim;
   const int h = sdc, W = 2 * sdc + 1;
   double norm = 0.0;
   for (int m = -h; m <= h; ++m) norm += (double)m * m;
-  for (int64_t t = blockIdx.x; t < T; t += gridDim.x) {
-    const int u = feat_find(off, n_utt, t);
-    const int64_t lo = off[u], hi = off[u + 1];
+  const int64_t per = (T + gridDim.x - 1) / gridDim.x;
+  const int64_t t_lo = per * blockIdx.x, t_hi = min(T, t_lo + per);
+  if (t_lo >= t_hi) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;   // one warp per frame, lanes over the columns
+  if (t_lo + warp >= t_hi) return;
+  FrameWalk fw(off, n_utt, t_lo + warp);
+  for (int64_t t = t_lo + warp; t < t_hi; t += 8) {
+    fw.to(off, t);
+    const int64_t lo = fw.lo, hi = fw.hi;
+    for (int d = lane; d < dim; d += 32) {
+      double acc = 0.0;
+      for (int k = 0; k < W; ++k) {                      // taps (h - k) / norm on frame t + h - k, k ascending
+        int64_t s2 = t + h - k;
+        s2 = s2 < lo ? lo : (s2 > hi - 1 ? hi - 1 : s2);
+        acc = __dadd_rn(acc, __dmul_rn((double)(h - k) / norm, y64[s2 * dim + d]));
+      }
+      dx[t * dim + d] = (float)acc;
+    }
+  }
+}
+
+// shifted delta coefficients: block ix of row t = delta of frame min(t + 3 ix, T_u - 1), written behind the dim
+// leading columns -- a pure gather of the float32 deltas (the fused version re-read three fp64 values per output)
+__global__ void __launch_bounds__(256) feat_sdc_kernel(const float* __restrict__ dx, float* __restrict__ out, int ld,
+                                                       int dim, const int64_t* __restrict__ off, int n_utt) {
+  const int64_t T = off[n_utt];
+  const int w = dim * dim;
+  const int64_t per = (T + gridDim.x - 1) / gridDim.x;
+  const int64_t t_lo = per * blockIdx.x, t_hi = min(T, t_lo + per);
+  if (t_lo >= t_hi) return;
+  FrameWalk fw(off, n_utt, t_lo);
+  const uint32_t mg = 0xFFFFFFFFu / (uint32_t)dim + 1u;
+  for (int64_t t = t_lo; t < t_hi; ++t) {
+    fw.to(off, t);
+    const int64_t hi = fw.hi;
+    float* row = out + t * ld + dim;
     for (int j = threadIdx.x; j < w; j += 256) {
-      const int ix = j / dim, d = j - ix * dim;
+      const int ix = (dim == 1) ? j : (int)__umulhi((uint32_t)j, mg), d = j - ix * dim;
       int64_t f = t + 3 * (int64_t)ix;
       if (f > hi - 1) f = hi - 1;
-      double acc = 0.0;
-      for (int k = 0; k < W; ++k) {                      // taps (h - k) / norm on frame f + h - k, k ascending
-        int64_t s = f + h - k;
-        s = s < lo ? lo : (s > hi - 1 ? hi - 1 : s);
-        acc = __dadd_rn(acc, __dmul_rn((double)(h - k) / norm, y64[s * dim + d]));
-      }
-      out[t * ld + dim + j] = (float)acc;
+      row[j] = dx[f * dim + d];
     }
   }
 }
@@ -184,12 +240,18 @@ int odin_feat_rasta_sdc(const float* d_x, float* d_y, int32_t dim, const int64_t
   const int64_t nthr = (int64_t)n_utt * dim;
   feat_rasta_kernel<<<(unsigned)ceil_div<int64_t>(nthr, 128), 128, 0, st>>>(d_x, d_y64, d_y, ld, dim, d_off, n_utt, rasta);
   g_launches.fetch_add(1, std::memory_order_relaxed);
+  float* d_dx = nullptr;
   if (sdc >= 1) {
-    const unsigned grid = (unsigned)std::min<int64_t>(T, (int64_t)sm_count() * 16);
-    feat_sdc_kernel<<<grid, 256, 0, st>>>(d_y64, d_y, ld, dim, d_off, n_utt, sdc);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    e = cudaMallocAsync(&d_dx, sizeof(float) * (size_t)T * dim, st);
+    if (e == cudaSuccess) {
+      const unsigned grid = (unsigned)std::min<int64_t>(T, (int64_t)sm_count() * 16);
+      feat_delta1_kernel<<<grid, 256, 0, st>>>(d_y64, d_dx, dim, d_off, n_utt, sdc);
+      feat_sdc_kernel<<<grid, 256, 0, st>>>(d_dx, d_y, ld, dim, d_off, n_utt);
+      g_launches.fetch_add(2, std::memory_order_relaxed);
+    }
   }
-  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (d_dx) cudaFreeAsync(d_dx, st);
   cudaFreeAsync(d_y64, st);
   cudaFreeAsync(d_off, st);
   if (e != cudaSuccess) return set_error(ODIN_ECUDA, "launch feat_rasta/sdc kernel: %s", cudaGetErrorString(e));
