@@ -558,8 +558,12 @@ class FusedSpeechFrontEnd(Extractor):
         out[name] = torch.empty((T, wd) if wd else (T,), dtype=dt).pin_memory()
     out['frame_offsets'] = fo
     # chunk boundaries: whole utterances, about equal numbers of samples
-    n_chunks = max(1, min(int(n_chunks), n_utt))
-    targets = so[0] + (so[-1] - so[0]) * np.arange(1, n_chunks) / n_chunks
+    if isinstance(n_chunks, (tuple, list)):   # explicit fractions of the samples per chunk (they are normalised)
+      fr = np.cumsum(np.asarray(n_chunks, dtype=np.float64))
+      targets = so[0] + (so[-1] - so[0]) * fr[:-1] / fr[-1]
+    else:
+      n_chunks = max(1, min(int(n_chunks), n_utt))
+      targets = so[0] + (so[-1] - so[0]) * np.arange(1, n_chunks) / n_chunks
     cuts = [0] + sorted(set(int(c) for c in np.searchsorted(so, targets) if 0 < c < n_utt)) + [n_utt]
     chunks = [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
     max_s = max(int(so[b] - so[a]) for a, b in chunks)

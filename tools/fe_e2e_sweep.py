@@ -13,7 +13,7 @@ pool = synth.utterance_batch(24, 5.0, 60.0, sr=sr, seed=4000)
 utts = [pool[i % len(pool)] for i in range(9 * len(pool))]
 pcm_h, off = synth.pack_utterances(utts)
 pinned = torch.from_numpy(pcm_h).pin_memory()
-for nc in (1, 2, 4, 6, 8, 12, 16, 24):
+for nc in (1, 4, 6, (1, 3, 3, 2, 1), (1, 2, 3, 3, 2, 1), (1, 2, 2, 2, 2, 1), (2, 3, 3, 2), (1, 2, 4, 4, 2, 1)):
   out = None
   ts = []
   for _ in range(4):
@@ -21,4 +21,4 @@ for nc in (1, 2, 4, 6, 8, 12, 16, 24):
     out = fe.run_host_packed(pinned, off, sr, want=("feat", "sad"), n_chunks=nc, out=out)
     torch.cuda.synchronize(); ts.append(time.perf_counter() - t0)
   T = int(out["frame_offsets"][-1])
-  print("chunks %2d: %.2f ms  %.1f M frames/s" % (nc, min(ts[1:]) * 1e3, T / min(ts[1:]) / 1e6), flush=True)
+  print("chunks %s: %.2f ms  %.1f M frames/s" % (str(nc), min(ts[1:]) * 1e3, T / min(ts[1:]) / 1e6), flush=True)
