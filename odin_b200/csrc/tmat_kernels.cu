@@ -450,6 +450,98 @@ __global__ void __launch_bounds__(JT) tmat_jacobi_kernel(double* __restrict__ W,
   }
 }
 
+// Eigen-decomposition of the tv x tv Gram matrix G = T T^T = U S^2 U^T by two-sided cyclic Jacobi, one CTA, A and V
+// in shared memory (tv <= TMAT_GRAM_MAX).  Used as a PRE-ROTATION: T <- U^T T makes the rows of T orthogonal up to
+// eps * cond(T)^2, after which the one-sided sweeps on T itself (which do not square the condition number) converge in
+// one or two passes instead of eight.  Vout [tv][tv]: column i = eigenvector of the i-th LARGEST eigenvalue.
+constexpr int TMAT_GRAM_MAX = 96;
+
+constexpr int ET = 1024;   // threads of the eigen-solver CTA (a round is ~n^2 / 2 independent updates between barriers)
+
+__global__ void __launch_bounds__(ET) tmat_eig_kernel(const double* __restrict__ G, int n, double* __restrict__ Vout) {
+  extern __shared__ double dyn_sm[];
+  const int P = n + 1, tid = threadIdx.x;
+  double* A = dyn_sm;            // [n][P]
+  double* V = A + n * P;         // [n][P]
+  double* cs = V + n * P;        // [n/2 + 1][2]
+  __shared__ int s_rot;
+  __shared__ short s_pq[TMAT_GRAM_MAX + 2];   // (p, q) of every pair of the current round, p < q, -1 = bye
+  for (int e = tid; e < n * n; e += ET) {
+    const int i = e / n, j = e - i * n;
+    A[i * P + j] = G[e];
+    V[i * P + j] = (i == j) ? 1.0 : 0.0;
+  }
+  const int np = n + (n & 1), half = np / 2;
+  for (int sweep = 0; sweep < 40; ++sweep) {
+    __syncthreads();
+    if (tid == 0) s_rot = 0;
+    for (int r = 0; r < np - 1; ++r) {
+      __syncthreads();
+      // rotation of every pair of this round
+      if (tid < half) {
+        const int i = tid;
+        int p, q;
+        if (i == 0) { p = np - 1; q = r; }
+        else { p = (r + i) % (np - 1); q = (r - i + (np - 1)) % (np - 1); }
+        double c = 1.0, s = 0.0;
+        if (p < n && q < n) {
+          if (p > q) { const int t = p; p = q; q = t; }
+          const double apq = A[p * P + q], app = A[p * P + p], aqq = A[q * P + q];
+          if (fabs(apq) > 1e-17 * sqrt(fabs(app * aqq)) && apq != 0.0) {
+            const double tau = (aqq - app) / (2.0 * apq);
+            const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+            c = 1.0 / sqrt(1.0 + t * t);
+            s = t * c;
+            atomicAdd(&s_rot, 1);
+          }
+        } else {
+          p = q = -1;
+        }
+        cs[2 * i] = c; cs[2 * i + 1] = s;
+        s_pq[2 * i] = (short)p; s_pq[2 * i + 1] = (short)q;
+      }
+      __syncthreads();
+      // rows: A <- J^T A
+      for (int e = tid; e < half * n; e += ET) {
+        const int i = e / n, k = e - i * n;
+        const int p = s_pq[2 * i], q = s_pq[2 * i + 1];
+        const double c = cs[2 * i], s = cs[2 * i + 1];
+        if (p < 0 || s == 0.0) continue;
+        const double x = A[p * P + k], y = A[q * P + k];
+        A[p * P + k] = c * x - s * y;
+        A[q * P + k] = s * x + c * y;
+      }
+      __syncthreads();
+      // columns: A <- A J, V <- V J
+      for (int e = tid; e < half * n; e += ET) {
+        const int i = e / n, k = e - i * n;
+        const int p = s_pq[2 * i], q = s_pq[2 * i + 1];
+        const double c = cs[2 * i], s = cs[2 * i + 1];
+        if (p < 0 || s == 0.0) continue;
+        double x = A[k * P + p], y = A[k * P + q];
+        A[k * P + p] = c * x - s * y;
+        A[k * P + q] = s * x + c * y;
+        x = V[k * P + p]; y = V[k * P + q];
+        V[k * P + p] = c * x - s * y;
+        V[k * P + q] = s * x + c * y;
+      }
+    }
+    __syncthreads();
+    if (s_rot == 0) break;
+  }
+  __syncthreads();
+  // eigenvalues descending (ties: lower index first) -> column order of Vout
+  for (int q = tid; q < n; q += ET) {
+    const double aq = A[q * P + q];
+    int rank = 0;
+    for (int p = 0; p < n; ++p) {
+      const double ap = A[p * P + p];
+      rank += (ap > aq) || (ap == aq && p < q);
+    }
+    for (int k = 0; k < n; ++k) Vout[k * n + rank] = V[k * P + q];
+  }
+}
+
 // singular values (row norms) -> descending order (stable), one CTA
 __global__ void __launch_bounds__(256) tmat_order_kernel(const double* __restrict__ W, int tv, int64_t MD,
                                                          int* __restrict__ perm) {
@@ -666,6 +758,23 @@ int tmat_mstep(odin_tmat* t, const double* d_acc, int min_div, int orthogonalize
     // Tm <- U Tm (through the T_invS buffer, which is rebuilt by the refresh below)
     if ((rc = gemm(t->tv, (int)t->MD, t->tv, t->d_U, t->tv, 1, t->d_Tm, t->MD, 1, t->d_TinvS, t->MD, 0.0, st))) return rc;
     ODIN_CUDA_CHECK(cudaMemcpyAsync(t->d_Tm, t->d_TinvS, sizeof(double) * (size_t)t->tv * t->MD, cudaMemcpyDeviceToDevice, st));
+  }
+  if (orthogonalize && t->tv > 1 && t->tv <= TMAT_GRAM_MAX) {
+    // pre-rotation through the Gram matrix (three passes over T) -- see tmat_eig_kernel
+    const int tv = t->tv;
+    const size_t need = (size_t)33 * tv * tv;   // G | 32 split-K slices
+    if ((rc = reserve_gws(t, need, 1))) return rc;
+    double* G = t->d_gws;
+    if ((rc = gemm(tv, tv, (int)t->MD, t->d_Tm, t->MD, 1, t->d_Tm, 1, t->MD, G, tv, 0.0, st, G + (size_t)tv * tv,
+                   (int64_t)32 * tv * tv)))
+      return rc;
+    const size_t smem = sizeof(double) * (2 * (size_t)tv * (tv + 1) + tv + 4);
+    ODIN_CUDA_CHECK(cudaFuncSetAttribute(tmat_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tmat_eig_kernel<<<1, ET, smem, st>>>(G, tv, t->d_U);
+    ODIN_LAUNCH_CHECK("tmat_eig_kernel");
+    // T <- U^T T (through the T_invS buffer, rebuilt by the refresh at the end)
+    if ((rc = gemm(tv, (int)t->MD, tv, t->d_U, 1, tv, t->d_Tm, t->MD, 1, t->d_TinvS, t->MD, 0.0, st))) return rc;
+    ODIN_CUDA_CHECK(cudaMemcpyAsync(t->d_Tm, t->d_TinvS, sizeof(double) * (size_t)tv * t->MD, cudaMemcpyDeviceToDevice, st));
   }
   if (orthogonalize && t->tv > 1) {
     const int np = t->tv + (t->tv & 1);
