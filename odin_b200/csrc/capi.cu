@@ -770,6 +770,7 @@ int odin_tmat_create(int32_t tv_dim, int32_t nmix, int32_t feat_dim, odin_tmat_t
   if ((e = cudaMalloc(&t->d_TinvSTt, sizeof(double) * (size_t)t->M * t->t2)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&t->d_U, sizeof(double) * (size_t)t->tv * t->tv)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&t->d_perm, sizeof(int) * t->tv)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&t->d_small, sizeof(double) * (size_t)std::max(t->t2, t->tv))) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&t->d_flag, 2 * sizeof(int))) != cudaSuccess) return fail(e);   // status | Jacobi rotation counter
   if ((e = cudaMemset(t->d_flag, 0, 2 * sizeof(int))) != cudaSuccess) return fail(e);
   *out = t;
@@ -780,7 +781,7 @@ void odin_tmat_destroy(odin_tmat_t* t) {
   if (!t) return;
   cudaFree(t->d_Tm); cudaFree(t->d_TinvS); cudaFree(t->d_Sigma); cudaFree(t->d_TinvSTt); cudaFree(t->d_U);
   cudaFree(t->d_perm); cudaFree(t->d_flag); cudaFree(t->d_L1); cudaFree(t->d_B1); cudaFree(t->d_Ex); cudaFree(t->d_llk);
-  cudaFree(t->d_ws); cudaFree(t->d_gws);
+  cudaFree(t->d_ws); cudaFree(t->d_gws); cudaFree(t->d_small);
   if (t->sweep_graph) cudaGraphExecDestroy((cudaGraphExec_t)t->sweep_graph);
   delete t;
 }

@@ -16,6 +16,7 @@ struct odin_tmat {
   double* d_TinvSTt = nullptr; // [M, t2]
   double* d_U = nullptr;       // [tv, tv] minimum-divergence factor
   int* d_perm = nullptr;       // [tv]
+  double* d_small = nullptr;   // [t2]: LU.sum(0) for the min-div step, later the squared row norms
   void* sweep_graph = nullptr; // cudaGraphExec_t: one Jacobi sweep (tv - 1 rounds), captured on first use
   int* d_flag = nullptr;       // 0 ok; 1 E-step system / 2 M-step system / 3 min-div matrix not positive definite
   // per-call scratch (capacity in files)

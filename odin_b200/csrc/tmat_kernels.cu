@@ -365,6 +365,17 @@ __global__ void __launch_bounds__(256) tmat_solve_kernel(int tv, int D, int64_t 
 }
 
 // minimum-divergence factor: U upper with sym(sum_m LU_m / nframes) = U^T U (scipy.linalg.cholesky default)
+// LU.sum(0): one thread per column, mixtures in ascending order (a single CTA doing this inside the min-div kernel
+// took 0.95 ms of a 9 ms EM iteration)
+__global__ void __launch_bounds__(256) tmat_colsum_kernel(const double* __restrict__ LU, int nmix, int t2,
+                                                          double* __restrict__ out) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= t2) return;
+  double acc = 0.0;
+  for (int m = 0; m < nmix; ++m) acc += LU[(int64_t)m * t2 + j];
+  out[j] = acc;
+}
+
 __global__ void __launch_bounds__(1024) tmat_mindiv_kernel(int tv, int nmix, const double* __restrict__ LU,
                                                           const double* __restrict__ nframes, double* __restrict__ U,
                                                           int* flag, double* __restrict__ gws) {
@@ -378,9 +389,7 @@ __global__ void __launch_bounds__(1024) tmat_mindiv_kernel(int tv, int nmix, con
   for (int e = tid; e < n * n; e += blockDim.x) {
     const int i = e / n, j = e - i * n;
     if (j > i) continue;
-    double acc = 0.0;
-    for (int m = 0; m < nmix; ++m) acc += LU[(int64_t)m * t2 + tril_idx(i, j)];   // LU.sum(0), mixture order
-    S[i * P + j] = acc / nf;
+    S[i * P + j] = LU[tril_idx(i, j)] / nf;   // LU = LU.sum(0) here (tmat_colsum_kernel)
   }
   if (!chol_lower(S, n, P, &s_flag)) {
     if (tid == 0) atomicExch(flag, 3);
@@ -542,19 +551,26 @@ __global__ void __launch_bounds__(ET) tmat_eig_kernel(const double* __restrict__
   }
 }
 
-// singular values (row norms) -> descending order (stable), one CTA
-__global__ void __launch_bounds__(256) tmat_order_kernel(const double* __restrict__ W, int tv, int64_t MD,
-                                                         int* __restrict__ perm) {
-  __shared__ double nrm[TMAT_MAX_TV];   // (8 KB)
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int p = warp; p < tv; p += 8) {
-    double a = 0.0;
-    for (int64_t j = lane; j < MD; j += 32) { const double x = W[(int64_t)p * MD + j]; a = fma(x, x, a); }
-    a = warp_sum(a);
-    if (lane == 0) nrm[p] = a;
-  }
+// singular values: squared row norms, one CTA per row (fixed reduction order) ...
+__global__ void __launch_bounds__(256) tmat_rownorm_kernel(const double* __restrict__ W, int64_t MD, double* __restrict__ nrm) {
+  __shared__ double red[8];
+  const int tid = threadIdx.x;
+  const double* w = W + (int64_t)blockIdx.x * MD;
+  double a = 0.0;
+  for (int64_t j = tid; j < MD; j += 256) { const double x = w[j]; a = fma(x, x, a); }
+  a = warp_sum(a);
+  if ((tid & 31) == 0) red[tid >> 5] = a;
   __syncthreads();
-  for (int q = tid; q < tv; q += 256) {   // rank of row q = #rows with a larger norm (ties: lower index first)
+  if (tid == 0) {
+    double t = 0.0;
+    for (int k = 0; k < 8; ++k) t += red[k];
+    nrm[blockIdx.x] = t;
+  }
+}
+
+// ... -> descending order (stable)
+__global__ void __launch_bounds__(256) tmat_order_kernel(const double* __restrict__ nrm, int tv, int* __restrict__ perm) {
+  for (int q = threadIdx.x; q < tv; q += 256) {   // rank of row q = #rows with a larger norm (ties: lower index first)
     int rank = 0;
     for (int p = 0; p < tv; ++p) rank += (nrm[p] > nrm[q]) || (nrm[p] == nrm[q] && p < q);
     perm[rank] = q;
@@ -572,10 +588,11 @@ __global__ void __launch_bounds__(256) tmat_gather_rows_kernel(const double* __r
 // The reference takes nframes = ceil(sum Z) PER BATCH of its expectation() (gmm_tmat.py:1695, batches of
 // 64 MiB / ((D M + M) itemsize) files, :1444-1449) and adds the batches up, so the ceil is applied per
 // `rows_per_batch` files here as well.
-__global__ void __launch_bounds__(256) tmat_totals_kernel(const double* __restrict__ Z, int64_t n, int M,
-                                                          int64_t rows_per_batch, const double* __restrict__ llk,
-                                                          double* __restrict__ acc_llk, double* __restrict__ acc_nframes) {
-  __shared__ double red[8];
+__global__ void __launch_bounds__(1024) tmat_totals_kernel(const double* __restrict__ Z, int64_t n, int M,
+                                                           int64_t rows_per_batch, const double* __restrict__ llk,
+                                                           double* __restrict__ acc_llk, double* __restrict__ acc_nframes) {
+  constexpr int NT = 1024;
+  __shared__ double red[NT / 32];
   __shared__ double total;
   const int tid = threadIdx.x;
   auto block_sum = [&](double v) -> double {
@@ -585,7 +602,7 @@ __global__ void __launch_bounds__(256) tmat_totals_kernel(const double* __restri
     __syncthreads();
     if (tid == 0) {
       double t = 0.0;
-      for (int w = 0; w < 8; ++w) t += red[w];
+      for (int w = 0; w < NT / 32; ++w) t += red[w];
       total = t;
     }
     __syncthreads();
@@ -594,12 +611,15 @@ __global__ void __launch_bounds__(256) tmat_totals_kernel(const double* __restri
   double nfr = 0.0;
   for (int64_t s = 0; s < n; s += rows_per_batch) {
     const int64_t e = min(n, s + rows_per_batch);
-    double a = 0.0;
-    for (int64_t i = s * M + tid; i < e * M; i += 256) a += Z[i];
-    nfr += ceil(block_sum(a));
+    const int64_t lo = s * M, hi = e * M;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;   // four independent chains per thread (the loads are the latency)
+    int64_t i = lo + tid;
+    for (; i + 3 * NT < hi; i += 4 * NT) { a0 += Z[i]; a1 += Z[i + NT]; a2 += Z[i + 2 * NT]; a3 += Z[i + 3 * NT]; }
+    for (; i < hi; i += NT) a0 += Z[i];
+    nfr += ceil(block_sum((a0 + a1) + (a2 + a3)));
   }
   double b = 0.0;
-  for (int64_t i = tid; i < n; i += 256) b += llk[i];
+  for (int64_t i = tid; i < n; i += NT) b += llk[i];
   b = block_sum(b);
   if (tid == 0) {
     *acc_nframes += nfr;
@@ -711,7 +731,7 @@ int tmat_estep(odin_tmat* t, const double* d_Z, const double* d_F, int64_t n_fil
     // RU += Ex^T F  [tv, MD];  LU += Z^T Exx  [M, t2]
     if ((rc = gemm(t->tv, (int)t->MD, (int)n, t->d_Ex, 1, t->tv, F, t->MD, 1, d_RU, t->MD, 1.0, st))) return rc;
     if ((rc = gemm(t->M, t->t2, (int)n, Z, 1, t->M, t->d_L1, t->t2, 1, d_LU, t->t2, 1.0, st))) return rc;
-    tmat_totals_kernel<<<1, 256, 0, st>>>(Z, n, t->M, ref_batch, t->d_llk, d_llk, d_nframes);
+    tmat_totals_kernel<<<1, 1024, 0, st>>>(Z, n, t->M, ref_batch, t->d_llk, d_llk, d_nframes);
     ODIN_LAUNCH_CHECK("tmat_totals_kernel");
   }
   return ODIN_OK;
@@ -747,12 +767,14 @@ int tmat_mstep(odin_tmat* t, const double* d_acc, int min_div, int orthogonalize
   }
   if (min_div) {
     const size_t smem = square_smem(t->tv, 0);
+    tmat_colsum_kernel<<<ceil_div(t->t2, 256), 256, 0, st>>>(d_LU, t->M, t->t2, t->d_small);
+    ODIN_LAUNCH_CHECK("tmat_colsum_kernel");
     if (smem <= SMEM_LIMIT) {
       ODIN_CUDA_CHECK(cudaFuncSetAttribute(tmat_mindiv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      tmat_mindiv_kernel<<<1, 256, smem, st>>>(t->tv, t->M, d_LU, d_nframes, t->d_U, t->d_flag, nullptr);
+      tmat_mindiv_kernel<<<1, 256, smem, st>>>(t->tv, t->M, t->d_small, d_nframes, t->d_U, t->d_flag, nullptr);
     } else {
       if ((rc = reserve_gws(t, smem / sizeof(double), 1))) return rc;
-      tmat_mindiv_kernel<<<1, 1024, 0, st>>>(t->tv, t->M, d_LU, d_nframes, t->d_U, t->d_flag, t->d_gws);
+      tmat_mindiv_kernel<<<1, 1024, 0, st>>>(t->tv, t->M, t->d_small, d_nframes, t->d_U, t->d_flag, t->d_gws);
     }
     ODIN_LAUNCH_CHECK("tmat_mindiv_kernel");
     // Tm <- U Tm (through the T_invS buffer, which is rebuilt by the refresh below)
@@ -825,7 +847,9 @@ int tmat_mstep(odin_tmat* t, const double* d_acc, int min_div, int orthogonalize
       ODIN_CUDA_CHECK(cudaStreamSynchronize(st));
       if (h_rot == 0) break;
     }
-    tmat_order_kernel<<<1, 256, 0, st>>>(t->d_Tm, t->tv, t->MD, t->d_perm);
+    tmat_rownorm_kernel<<<t->tv, 256, 0, st>>>(t->d_Tm, t->MD, t->d_small);
+    ODIN_LAUNCH_CHECK("tmat_rownorm_kernel");
+    tmat_order_kernel<<<1, 256, 0, st>>>(t->d_small, t->tv, t->d_perm);
     ODIN_LAUNCH_CHECK("tmat_order_kernel");
     dim3 grid((unsigned)std::min<int64_t>(ceil_div<int64_t>(t->MD, 256), 64), (unsigned)t->tv);
     tmat_gather_rows_kernel<<<grid, 256, 0, st>>>(t->d_Tm, t->d_TinvS, t->d_perm, t->MD);
