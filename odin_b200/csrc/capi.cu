@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "fe.cuh"
+#include "fe_frame.cuh"
 #include "tmat.cuh"
 #include "fe_logic.cuh"
 #include "gmm.cuh"
@@ -194,6 +195,63 @@ int fe_build_tables(odin_fe* fe) {
     fe->mel_chunks = (int)chunks.size();
     if (nb > 0x7fff || chunks.size() > 0xffff) return set_error(ODIN_EINVAL, "filterbank too large for the packed table");
   }
+  // Segment form for fe_frame5_kernel (n_fft <= 1024).  With centres p_0 .. p_(nm+1), a bin in segment s =
+  // [p_s, p_(s+1)) lies on the falling side of filter s-1 and on the rising side of filter s and nowhere else;
+  // lane l of a warp owns the NK = N/64 contiguous bins NK l .. NK l + NK-1, keeps one falling and one rising
+  // accumulator and drops them into the next partial-sum slot whenever its next bin belongs to another segment
+  // (and after its last bin).  Slots are therefore in bin order and segment s owns slots [sstart[s], sstart[s+1]);
+  // filter m = rising sums of segment m + falling sums of segment m+1.
+  std::vector<Win5> win5(L);
+  for (int k = 0; k < L; ++k) {
+    win5[k].w = fe->h_win[k];
+    win5[k].ws = (float)(fe->h_win[k] * 0.5 * scale);
+    win5[k].pad_ = 0.f;
+  }
+  std::vector<float2> m5w;
+  std::vector<uint32_t> m5flags(32, 0u);
+  std::vector<int> m5sstart(nm + 2, 0);
+  fe->mel5_ok = false;
+  fe->mel5_nslots = 0;
+  if (N <= 1024) {
+    const int NK = N / 64, nhalf = N / 2;
+    bool ok = true;
+    std::vector<int> seg(nhalf, 0);
+    m5w.assign((size_t)NK * 32, make_float2(0.f, 0.f));
+    for (int k = 0; k < nhalf && ok; ++k) {
+      int s = 0;
+      for (int i = 1; i <= nm; ++i) s += edges[i] <= binhz[k];
+      seg[k] = s;
+      for (int m = 0; m < nm; ++m)
+        if (fe->h_mel[(size_t)m * nb + k] != 0.0 && m != s && m != s - 1) ok = false;
+      const float wdn = s >= 1 ? (float)fe->h_mel[(size_t)(s - 1) * nb + k] : 0.f;
+      const float wup = s < nm ? (float)fe->h_mel[(size_t)s * nb + k] : 0.f;
+      m5w[(size_t)(k % NK) * 32 + k / NK] = make_float2(wdn, wup);
+    }
+    for (int m = 0; m < nm; ++m) ok = ok && fe->h_mel[(size_t)m * nb + nhalf] == 0.0;   // Nyquist bin: never weighted
+    if (ok) {
+      std::vector<int> slot_seg;
+      for (int l = 0; l < 32; ++l) {
+        uint32_t fl = 0;
+        const uint32_t first = (uint32_t)slot_seg.size();
+        for (int j = 0; j < NK; ++j) {
+          const int k = NK * l + j;
+          if (j == NK - 1) slot_seg.push_back(seg[k]);
+          else if (seg[k + 1] != seg[k]) { fl |= 1u << j; slot_seg.push_back(seg[k]); }
+        }
+        m5flags[l] = fl | (first << 16);
+      }
+      // (slot_seg is non-decreasing; segments without bins own no slot)
+      size_t p = 0;
+      for (int s = 0; s <= nm + 1; ++s) {
+        while (p < slot_seg.size() && slot_seg[p] < s) ++p;
+        m5sstart[s] = (int)p;
+      }
+      fe->mel5_nslots = (int)slot_seg.size();
+      // the slots (16 B each) reuse a pair region of the kernel: 8 * f5_region<N>() bytes >= 8 * (N + 65)
+      ok = (size_t)fe->mel5_nslots * 16 <= (size_t)(N + 65) * 8;
+    }
+    fe->mel5_ok = ok;
+  }
   // DCT-II orthonormal rows (signal.py:682-733)
   const int nc1 = fe->n_c1;
   fe->h_dct.assign((size_t)std::max(1, nc1) * nm, 0.0);
@@ -223,6 +281,10 @@ int fe_build_tables(odin_fe* fe) {
   if ((rc = upload(&fe->d_mel_w, mw))) return rc;
   if ((rc = upload(&fe->d_mel_tab, mtab))) return rc;
   if ((rc = upload(&fe->d_mel_ps, mps))) return rc;
+  if ((rc = upload(reinterpret_cast<Win5**>(&fe->d_win5), win5))) return rc;
+  if ((rc = upload(&fe->d_mel5_w, m5w))) return rc;
+  if ((rc = upload(&fe->d_mel5_flags, m5flags))) return rc;
+  if ((rc = upload(&fe->d_mel5_sstart, m5sstart))) return rc;
   if ((rc = upload(&fe->d_dct, dct32))) return rc;
   if ((rc = upload(&fe->d_taps, taps))) return rc;
   return ODIN_OK;
@@ -309,6 +371,7 @@ void odin_fe_destroy(odin_fe_t* fe) {
   cudaFree(fe->d_win32); cudaFree(fe->d_win64); cudaFree(fe->d_tw); cudaFree(fe->d_tw4); cudaFree(fe->d_mel_start);
   cudaFree(fe->d_mel_cnt); cudaFree(fe->d_mel_off); cudaFree(fe->d_mel_w); cudaFree(fe->d_dct);
   cudaFree(fe->d_mel_tab); cudaFree(fe->d_mel_ps);
+  cudaFree(fe->d_win5); cudaFree(fe->d_mel5_w); cudaFree(fe->d_mel5_flags); cudaFree(fe->d_mel5_sstart);
   cudaFree(fe->d_taps); cudaFree(fe->d_sample_off); cudaFree(fe->d_dcsum); cudaFree(fe->d_umax);
   cudaFree(fe->d_cnt); cudaFree(fe->d_vad_scratch);
   if (fe->h_stage) cudaFreeHost(fe->h_stage);

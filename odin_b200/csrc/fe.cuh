@@ -30,6 +30,14 @@ struct odin_fe {
   float2* d_mel_tab = nullptr; // [mel_trips][32] {weight, bin | flush << 15 | slot << 16}
   int* d_mel_ps = nullptr;     // [n_mels + 1] partial-sum slots of filter m: [ps[m], ps[m+1])
   int mel_trips = 0, mel_chunks = 0;
+  // segment form of the filterbank + scaled window for fe_frame5_kernel (fe_frame5.cu); mel5_ok = the bank has
+  // the triangular structure that kernel assumes (every bin feeds at most the two filters around it)
+  void* d_win5 = nullptr;          // Win5[L]
+  float2* d_mel5_w = nullptr;      // [N/64][32]
+  uint32_t* d_mel5_flags = nullptr;// [32]
+  int* d_mel5_sstart = nullptr;    // [n_mels + 2]
+  int mel5_nslots = 0;
+  bool mel5_ok = false;
   // per-run scratch (capacity in utterances)
   int cap_utt = 0;
   int64_t* h_stage = nullptr;  // pinned [5*(cap+1)]: sample_off, frame_off, tile_off, tile2_off, vad order

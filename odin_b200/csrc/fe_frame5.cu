@@ -1,0 +1,327 @@
+// fe_frame5_kernel: the frame kernel of the speech front-end on packed fp32 pairs (sm_100a FADD2 / FMUL2 / FFMA2).
+//
+// Same contract as fe_frame4_kernel (fe_kernels.cu; reference arithmetic: odin/preprocessing/signal.py:1442-1562
+// framing / window / rfft / scale, :1421-1440 frame energy, :1623-1648 power spectrum, :1650-1691 mel projection,
+// :636-680 power2db) and the same four-step decomposition N = G * 32 with two real frames packed as re / im of one
+// complex transform, but written for the instruction-issue roofline that bounds it (ncu of fe_frame4_kernel:
+// 1 451 warp-instructions per frame, 59 % of the issue slots, FMA pipe 27 %):
+//
+//   * a complex value lives in one 64-bit register pair and every butterfly is add.f32x2 / sub.f32x2 /
+//     mul.f32x2 / fma.f32x2: a complex add is ONE issue slot instead of two, a complex multiply two instead of
+//     four (ptxas folds the re <-> im swap and the alternating sign into the operand modifiers of FFMA2, and
+//     the multiplication by -i of a radix-4 step into those of FADD2).  tools/f32x2_bench.cu: FFMA2 / FADD2 keep
+//     the FP32 lanes as busy as scalar code (72.8 vs 67.4 TFLOP/s) at half the issue slots.
+//   * conjugate-symmetric split in 4 packed instructions per bin: with s = Z[k] + Z[N-k], d = Z[k] - Z[N-k] the
+//     two power spectra are (|A|^2, |B|^2) = s*s + swap(d)*swap(d); the 1/4 and the 1/sum(w)^2 are folded
+//     into the fp32 window.
+//   * mel projection on the power values while they are in registers.  A lane owns N/64 CONTIGUOUS bins; a
+//     bin between the centres p_s and p_(s+1) ("segment" s) only feeds the falling side of filter s-1 and the
+//     rising side of filter s, so a lane keeps two packed accumulators (falling | rising, frames A | B), and
+//     drops them into a slot whenever its bins cross a centre.  Filter m = rising sum of segment m + falling sum
+//     of segment m+1, a handful of slots.  This replaces the table walk of fe_frame4_kernel (random shared-memory
+//     reads: 25 % of its instructions and all of its bank conflicts).
+//   * the rows of step A that are zero padding (L <= n_fft / 2 and the tail of the last live row) are template
+//     parameters: no predicated-off instructions are issued for them.
+//
+// Shared memory per warp is ONE region per frame pair, used three times: exchange tile [k1][l] of the four-step
+// FFT -> natural-order spectrum (one pad element per lane chunk: conflict-free for the contiguous reads) ->
+// partial-sum slots of the mel projection (the spectrum is pulled into registers first).
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+
+#include "fe.cuh"
+#include "fe_frame.cuh"
+
+namespace odin {
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 pk2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float lo32(u64 v) { float a, b; asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
+__device__ __forceinline__ float hi32(u64 v) { float a, b; asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+// (re, im) * (wr + i wi) = (re wr, im wr) + (im, re) * (-wi, wi)
+__device__ __forceinline__ u64 cmulw(u64 a, float wr, float wi) {
+  return fma2(pk2(hi32(a), lo32(a)), pk2(-wi, wi), mul2(a, pk2(wr, wr)));
+}
+
+// cos / -sin of 2 pi q / 32
+__device__ __forceinline__ constexpr float c32(int q) {
+  constexpr float t[9] = {1.0f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+                          0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f,
+                          0.19509032201612826785f, 0.0f};
+  return q <= 8 ? t[q] : -t[16 - q];
+}
+__device__ __forceinline__ constexpr float s32(int q) { return q <= 8 ? -c32(8 - q) : -c32(q - 8); }
+
+// In-register forward DFT of size R (power of two <= 32) over packed complex values, natural order in / out.
+// NZ < R declares v[NZ..R) to be zero: the even / odd halves inherit the zero tail and a sub-transform with a
+// single live input is a broadcast.
+template <int R, int NZ = R> struct Dft5 {
+  static __device__ __forceinline__ void run(u64 (&v)[R]) {
+    if constexpr (NZ <= 1) {
+#pragma unroll
+      for (int q = 1; q < R; ++q) v[q] = v[0];
+    } else {
+      u64 e[R / 2], o[R / 2];
+#pragma unroll
+      for (int q = 0; q < R / 2; ++q) { e[q] = v[2 * q]; o[q] = v[2 * q + 1]; }
+      Dft5<R / 2, (NZ + 1) / 2>::run(e);
+      Dft5<R / 2, NZ / 2>::run(o);
+#pragma unroll
+      for (int q = 0; q < R / 2; ++q) {
+        u64 t;
+        if (q == 0) t = o[q];
+        else if (4 * q == R) t = pk2(hi32(o[q]), -lo32(o[q]));   // * (-i)
+        else t = cmulw(o[q], c32(q * (32 / R)), s32(q * (32 / R)));
+        v[q] = add2(e[q], t);
+        v[q + R / 2] = sub2(e[q], t);
+      }
+    }
+  }
+};
+template <int NZ> struct Dft5<1, NZ> {
+  static __device__ __forceinline__ void run(u64 (&)[1]) {}
+};
+
+// float2 elements of one pair region: the exchange tile (32 rows of G + 1), then the natural-order spectrum with
+// one pad element behind every chunk of N / 64 bins (+ the copy of X[0] that stands in for X[N]); even, and
+// = 8 mod 16 at G = 8 so that the two pair regions of a half-warp fall on different banks.
+template <int N> constexpr int f5_region() {
+  constexpr int tile = 32 * (N / 32 + 1), nat = N + 64 + 1;
+  constexpr int r = (tile > nat ? tile : nat);
+  return N == 256 ? ((r + 15) / 16) * 16 + 8 : (r + 1) & ~1;
+}
+
+// NZ live rows in step A (rows r >= NZ are zero padding); EXACT: (NZ - 1) * G <= L, so only the last live row
+// needs the i < L test.
+template <int N, typename PCM, int NZ, bool EXACT>
+__global__ void __launch_bounds__(FE_THREADS, 2) fe_frame5_kernel(FrameArgs a) {
+  constexpr int G = N / 32, NP = 32 / G, RS = G + 1, REG = f5_region<N>(), NK = N / 64;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: win5 [L] | pair regions [FE_WARPS][NP * REG] float2 | tw4 [N] float2 | mel weights [NK][32] float2 |
+  //         sstart [n_mels + 2] | sbuf [(FT-1)*hop + L + 16]
+  Win5* win5 = reinterpret_cast<Win5*>(smem_raw);
+  u64* bufs = reinterpret_cast<u64*>(win5 + a.L);
+  u64* tw4 = bufs + FE_WARPS * NP * REG;
+  float2* melw = reinterpret_cast<float2*>(tw4 + N);
+  int* sstart = reinterpret_cast<int*>(melw + NK * 32);
+  float* sbuf = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sstart + a.n_mels + 2) + 15) & ~uintptr_t(15));
+  __shared__ int cta_max;
+  __shared__ double s_en[FT];   // frame energies of the tile; their logs are taken by one warp at the end
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane / G, l = lane % G;
+  const int L = a.L, hop = a.hop;
+  for (int i = tid; i < L; i += FE_THREADS) win5[i] = a.win5[i];
+  for (int i = tid; i < N; i += FE_THREADS) tw4[i] = reinterpret_cast<const u64*>(a.tw)[i];
+  for (int i = tid; i < NK * 32; i += FE_THREADS) melw[i] = a.mel5_w[i];
+  for (int i = tid; i < a.n_mels + 2; i += FE_THREADS) sstart[i] = a.mel5_sstart[i];
+  const uint32_t mflags = a.mel5_flags[lane];   // bits 0..NK-2: flush after bin j; bits 16..: the lane's first slot
+  u64* wbuf = bufs + warp * (NP * REG);
+  const PCM* __restrict__ pcm = reinterpret_cast<const PCM*>(a.pcm);
+  const float coef = a.preemph;
+
+  // contiguous range of tiles per CTA: one binary search, then the utterance index walks forward
+  const int64_t per = (a.n_tiles + gridDim.x - 1) / gridDim.x;
+  const int64_t tile_lo = per * blockIdx.x, tile_hi = min(a.n_tiles, tile_lo + per);
+  if (tile_lo >= tile_hi) return;
+  int u = find_segment(a.tile_off, a.n_utt, tile_lo);
+  int64_t u_end = a.tile_off[u + 1];
+  for (int64_t tile = tile_lo; tile < tile_hi; ++tile) {
+    while (tile >= u_end) { ++u; u_end = a.tile_off[u + 1]; }
+    const int64_t s0 = a.sample_off[u];
+    const int64_t n_u = a.sample_off[u + 1] - s0;
+    const int64_t fbase = a.frame_off[u];
+    const int T_u = (int)(a.frame_off[u + 1] - fbase);
+    const int t0 = (int)(tile - a.tile_off[u]) * FT;
+    const int nf = min(FT, T_u - t0);
+    float mean = 0.f;
+    if (a.remove_dc) {
+      double s = (sizeof(PCM) == 2) ? (double)reinterpret_cast<const long long*>(a.dcsum)[u] : a.dcsum[u];
+      mean = (float)(s / (double)n_u);
+    }
+    __syncthreads();  // previous tile done with sbuf / cta_max / s_en (and the table fill on the first trip)
+    if (tid == 0) cta_max = float_to_ordered(-FLT_MAX);
+    const float* stile = stage_pcm<PCM>(sbuf, pcm + s0, n_u, (int64_t)t0 * hop, (nf - 1) * hop + L, mean, coef, a.pad,
+                                        tid, FE_THREADS);
+    __syncthreads();
+
+    float wmax = -FLT_MAX;
+    const int npairs = (nf + 1) >> 1;
+    for (int base = warp * NP; base < npairs; base += FE_WARPS * NP) {
+      u64* reg = wbuf + g * REG;
+      // ---------------- step A: load + window + energy, 32-point DFT over r, twiddle
+      {
+        const int pr = base + g;
+        const int fA = 2 * pr, fB = fA + 1;
+        // frames past the end of the tile are computed on the tile's last frame and never stored
+        const float* sA = stile + min(fA, nf - 1) * hop + l;
+        const float* sB = stile + min(fB, nf - 1) * hop + l;
+        const Win5* wp = win5 + l;
+        double eA = 0.0, eB = 0.0;
+        u64 v[32];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          u64 z = 0ull;
+          if (r < NZ) {
+            const bool live = (EXACT && r < NZ - 1) ? true : (l + G * r < L);
+            if (live) {
+              const float xa = sA[G * r], xb = sB[G * r];
+              const Win5 w = wp[G * r];
+              const double wa = w.w * (double)xa, wb = w.w * (double)xb;
+              eA = fma(wa, wa, eA);
+              eB = fma(wb, wb, eB);
+              z = mul2(pk2(xa, xb), pk2(w.ws, w.ws));
+            }
+          }
+          v[r] = z;
+        }
+        if (a.energy != nullptr) {
+#pragma unroll
+          for (int o = G / 2; o > 0; o >>= 1) {
+            eA += __shfl_xor_sync(0xffffffffu, eA, o);
+            eB += __shfl_xor_sync(0xffffffffu, eB, o);
+          }
+          if (l == 0 && fA < nf) {
+            s_en[fA] = eA;
+            if (fB < nf) s_en[fB] = eB;
+          }
+        }
+        Dft5<32, NZ>::run(v);
+#pragma unroll
+        for (int k1 = 1; k1 < 32; ++k1) {
+          const u64 w = tw4[k1 * G + l];
+          v[k1] = cmulw(v[k1], lo32(w), hi32(w));
+        }
+        __syncwarp();  // the previous pass' mel stage has finished reading its slots in the regions
+#pragma unroll
+        for (int k1 = 0; k1 < 32; ++k1) reg[k1 * RS + l] = v[k1];
+      }
+      __syncwarp();
+      // ---------------- step B: G-point DFT over l for k1 = l + G t, natural-order store (chunk-padded)
+      {
+        u64 x[NP][G];
+#pragma unroll
+        for (int t = 0; t < NP; ++t) {
+          const int k1 = l + G * t;
+#pragma unroll
+          for (int i = 0; i < G; ++i) x[t][i] = reg[k1 * RS + i];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < NP; ++t) {
+          Dft5<G>::run(x[t]);
+          // k = k1 + 32 k2 -> k + k / NK; k1 = l + G t < 32, so k / NK = (32 / NK) k2 + k1 / NK
+          u64* dst = reg + (l + G * t) + (l + G * t) / NK;
+#pragma unroll
+          for (int k2 = 0; k2 < G; ++k2) dst[32 * k2 + (32 / NK) * k2] = x[t][k2];
+        }
+        if (l == 0) reg[N + 64] = x[0][0];   // X[N] = X[0]: the mirror of the DC bin
+      }
+      __syncwarp();
+      // ---------------- split + |.|^2 + mel + dB, the whole warp on one pair at a time
+#pragma unroll 1
+      for (int pp = 0; pp < NP; ++pp) {
+        const int fA = 2 * (base + pp), fB = fA + 1;
+        if (fA >= nf) break;
+        const bool hasB = fB < nf;
+        u64* buf = wbuf + pp * REG;
+        // lane owns bins k = NK lane + j; mirror N - k sits in chunk 63 - lane at offset NK - j (j >= 1), or at
+        // the head of chunk 64 - lane (j = 0)
+        const u64* p1 = buf + (NK + 1) * lane;
+        const u64* p2 = buf + (NK + 1) * (63 - lane) + NK;
+        u64 z1[NK], z2[NK];
+#pragma unroll
+        for (int j = 0; j < NK; ++j) { z1[j] = p1[j]; z2[j] = (j == 0) ? p2[1] : p2[-j]; }
+        __syncwarp();   // the spectrum is in registers: the region now takes the partial-sum slots
+        float4* slots = reinterpret_cast<float4*>(buf);
+        int slot = (int)(mflags >> 16);
+        u64 accD = 0ull, accU = 0ull;
+#pragma unroll
+        for (int j = 0; j < NK; ++j) {
+          const u64 s = add2(z1[j], z2[j]), d = sub2(z1[j], z2[j]);
+          const u64 ds = pk2(hi32(d), lo32(d));
+          const u64 P = fma2(ds, ds, mul2(s, s));   // (|A_k|^2, |B_k|^2) * scale^2
+          const float2 w = melw[j * 32 + lane];
+          accD = fma2(P, pk2(w.x, w.x), accD);
+          accU = fma2(P, pk2(w.y, w.y), accU);
+          if (j == NK - 1 || ((mflags >> j) & 1u)) {
+            slots[slot] = make_float4(lo32(accD), hi32(accD), lo32(accU), hi32(accU));
+            ++slot;
+            accD = 0ull; accU = 0ull;
+          }
+        }
+        __syncwarp();
+        float* rowA = a.mspec + (fbase + t0 + fA) * a.n_mels;
+        for (int m = lane; m < a.n_mels; m += 32) {
+          const int s0 = sstart[m], s1 = sstart[m + 1], s2 = sstart[m + 2];
+          float accA = 0.f, accB = 0.f;
+          for (int i = s0; i < s1; ++i) { const float4 q = slots[i]; accA += q.z; accB += q.w; }   // rising side
+          for (int i = s1; i < s2; ++i) { const float4 q = slots[i]; accA += q.x; accB += q.y; }   // falling side
+          const float dA = db10<float>(accA);
+          rowA[m] = dA;
+          wmax = fmaxf(wmax, dA);
+          if (hasB) {
+            const float dB = db10<float>(accB);
+            rowA[a.n_mels + m] = dB;
+            wmax = fmaxf(wmax, dB);
+          }
+        }
+      }
+    }
+    wmax = warp_max(wmax);
+    if (lane == 0) atomicMax(&cta_max, float_to_ordered(wmax));
+    __syncthreads();
+    if (tid == 0) atomicMax(a.umax + u, cta_max);
+    if (a.energy != nullptr && tid < nf) {
+      double e = s_en[tid];
+      if (e == 0.0) e = (double)FLT_EPSILON;  // signal.py:1436
+      a.energy[fbase + t0 + tid] = (float)log(e);
+    }
+  }
+}
+
+template <int N, typename PCM, int NZ, bool EXACT>
+static int launch5(const FrameArgs& a, cudaStream_t st) {
+  constexpr int NP = 32 / (N / 32), NK = N / 64;
+  size_t smem = (size_t)a.L * sizeof(Win5) + (size_t)FE_WARPS * NP * f5_region<N>() * sizeof(float2) +
+                (size_t)N * sizeof(float2) + (size_t)NK * 32 * sizeof(float2) + (size_t)(a.n_mels + 2) * sizeof(int) +
+                16 + (size_t)((FT - 1) * a.hop + a.L + 16 + 4) * sizeof(float);
+  if (smem > 227 * 1024) return set_error(ODIN_EINVAL, "frame kernel needs %zu B smem (hop too large)", smem);
+  auto k = fe_frame5_kernel<N, PCM, NZ, EXACT>;
+  ODIN_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (227 * 1024) / (smem + 1024)));
+  int64_t grid = std::min<int64_t>(a.n_tiles, (int64_t)sm_count() * per_sm);
+  k<<<(unsigned)grid, FE_THREADS, smem, st>>>(a);
+  ODIN_LAUNCH_CHECK("fe_frame5_kernel");
+  return ODIN_OK;
+}
+
+template <int N, typename PCM>
+static int dispatch5(const FrameArgs& a, cudaStream_t st) {
+  constexpr int G = N / 32;
+  const int rows = (a.L + G - 1) / G;   // live rows of step A
+  if constexpr (N == 1024) {
+    if (rows <= 13 && 12 * G <= a.L) return launch5<N, PCM, 13, true>(a, st);
+  } else {
+    if (rows <= 25 && 24 * G <= a.L) return launch5<N, PCM, 25, true>(a, st);
+  }
+  if (rows <= 16) return launch5<N, PCM, 16, false>(a, st);
+  return launch5<N, PCM, 32, false>(a, st);
+}
+
+int fe_frame5_launch(int N, int pcm_dtype, const FrameArgs& a, cudaStream_t st) {
+  switch (N) {
+    case 256: return pcm_dtype == 0 ? dispatch5<256, int16_t>(a, st) : dispatch5<256, float>(a, st);
+    case 512: return pcm_dtype == 0 ? dispatch5<512, int16_t>(a, st) : dispatch5<512, float>(a, st);
+    case 1024: return pcm_dtype == 0 ? dispatch5<1024, int16_t>(a, st) : dispatch5<1024, float>(a, st);
+  }
+  return set_error(ODIN_EINVAL, "n_fft %d unsupported by fe_frame5_kernel", N);
+}
+
+}  // namespace odin

@@ -38,16 +38,14 @@
 #include <cooperative_groups.h>
 
 #include "fe.cuh"
+#include "fe_frame.cuh"
 #include "fe_logic.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace odin {
 
-constexpr int FT = ODIN_FE_TILE;
 constexpr int PT = ODIN_FE_POST_TILE;
-constexpr int FE_WARPS = 8;
-constexpr int FE_THREADS = FE_WARPS * 32;
 
 // ---------------------------------------------------------------------------
 // small complex helpers
@@ -197,105 +195,6 @@ fe_dc_kernel(const PCM* __restrict__ pcm, const int64_t* __restrict__ sample_off
 // ---------------------------------------------------------------------------
 // fe_frame_kernel
 // ---------------------------------------------------------------------------
-struct FrameArgs {
-  const void* pcm;
-  const int64_t* sample_off;
-  const int64_t* frame_off;
-  const int64_t* tile_off;
-  int n_utt;
-  int64_t n_tiles;
-  const double* dcsum;
-  int L, hop, remove_dc;
-  float preemph;
-  const float* win32;
-  const double* win64;
-  const void* tw;  // C2<T>[N]: Stockham table exp(-2 pi i k / N), or the four-step table for fe_frame4_kernel
-  int mel_nnz;
-  const int* mel_start;
-  const int* mel_cnt;
-  const int* mel_off;
-  const float* mel_w;
-  const float2* mel_tab;   // lane-balanced filterbank (fe_frame4_kernel)
-  const int* mel_ps;
-  int mel_trips, mel_chunks;
-  int n_mels;
-  float scale2;
-  float* mspec;   // [T, n_mels] unclipped dB
-  float* energy;  // [T] nullable
-  int* umax;      // [n_utt]
-  int pad;        // zeros virtually prepended / appended to every utterance (stft(padding=True), signal.py:1529-1530)
-  float* spec;    // [T, N/2+1] nullable: power spectrum (SpectraExtractor, signal.py:1718-1832), dB when spec_log
-  int spec_log;
-  int* umax_spec; // [n_utt] ordered-int max of the dB spectrum
-};
-
-// PCM tile -> shared memory with DC removal and pre-emphasis fused (speech.py:472-473, signal.py:955-967);
-// virtual sample v of the (padded) utterance is real sample v - pad, zeros outside (signal.py:1529-1530:
-// the padding is applied to the processed signal, so padded samples are exact zeros).
-//
-// ncu put 31 % of the frame kernel's stall samples on the scalar 2-byte loads of the first version, so the
-// tile is read as 16-byte vectors aligned in GLOBAL memory (8 int16 / 4 float samples per load) and written as
-// 16-byte shared-memory stores: element i of the tile lands at sbase[i + mis], where mis (0..7) is the
-// misalignment of the tile's first sample; the function returns sbase + mis, the tile origin for the readers.
-// sbase must be 32-byte aligned and hold cnt + 16 floats.
-template <typename PCM>
-__device__ __forceinline__ float* stage_pcm(float* __restrict__ sbase, const PCM* __restrict__ pu, int64_t n_u,
-                                            int64_t v0, int cnt, float mean, float coef, int pad, int tid, int nthr) {
-  constexpr int V = 16 / (int)sizeof(PCM);
-  const int64_t gstart = v0 - pad;   // utterance index of tile element 0 (negative inside the left padding)
-  const int mis = (int)((reinterpret_cast<uintptr_t>(pu + gstart) & 15) / sizeof(PCM));
-  const int n_chunks = (cnt + mis + V - 1) / V;
-  for (int c = tid; c < n_chunks; c += nthr) {
-    const int64_t g0 = gstart + (int64_t)c * V - mis;   // utterance index of the chunk's first sample
-    float x[V], prev0 = 0.f;
-    if (g0 >= 0 && g0 + V <= n_u) {
-      union { uint4 u; PCM e[V]; } raw;
-      raw.u = *reinterpret_cast<const uint4*>(pu + g0);
-#pragma unroll
-      for (int e = 0; e < V; ++e) x[e] = __fsub_rn((float)raw.e[e], mean);
-      if (g0 > 0) prev0 = __fsub_rn((float)pu[g0 - 1], mean);
-    } else {
-#pragma unroll
-      for (int e = 0; e < V; ++e) {
-        const int64_t g = g0 + e;
-        x[e] = (g >= 0 && g < n_u) ? __fsub_rn((float)pu[g], mean) : 0.f;
-      }
-      if (g0 > 0 && g0 - 1 < n_u) prev0 = __fsub_rn((float)pu[g0 - 1], mean);
-    }
-    float y[V];
-#pragma unroll
-    for (int e = 0; e < V; ++e) {
-      const int64_t g = g0 + e;
-      float cur = x[e];
-      if (coef != 0.f && g > 0) cur = __fsub_rn(cur, __fmul_rn(coef, e == 0 ? prev0 : x[e - 1]));  // two roundings, like numpy (signal.py:965)
-      y[e] = (g >= 0 && g < n_u) ? cur : 0.f;
-    }
-    float4* dst = reinterpret_cast<float4*>(sbase + c * V);
-#pragma unroll
-    for (int q = 0; q < V / 4; ++q) dst[q] = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
-  }
-  return sbase + mis;
-}
-
-__device__ __forceinline__ int find_segment(const int64_t* __restrict__ off, int n, int64_t v) {
-  // largest u in [0, n) with off[u] <= v   (off is non-decreasing, off[0] = 0)
-  int lo = 0, hi = n;
-  while (hi - lo > 1) {
-    int mid = (lo + hi) >> 1;
-    if (off[mid] <= v) lo = mid; else hi = mid;
-  }
-  return lo;
-}
-
-template <typename T> __device__ __forceinline__ T db10(T v);
-// 10 log10(max(v, 1e-10)) (signal.py:636-680) through the SFU: MUFU.LG2 is within 2 ulp of log2 (absolute error
-// < 1e-5 dB over the range of a log-mel value, against a 1e-4 x 80 dB tolerance) and replaces ~20 instructions
-// of log10f by two -- it was 4 % of the frame kernel's instructions.
-template <> __device__ __forceinline__ float db10<float>(float v) {
-  return 3.0102999566398120f * __log2f(fmaxf(v, 1e-10f));
-}
-template <> __device__ __forceinline__ double db10<double>(double v) { return 10.0 * log10(fmax(v, 1e-10)); }
-
 template <int N, typename T, typename PCM>
 __global__ void __launch_bounds__(FE_THREADS) fe_frame_kernel(FrameArgs a) {
   using P = FftPlan<N>;
@@ -1754,8 +1653,17 @@ int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t 
     // (the chunk slots of the balanced filterbank sit behind the two power spectra in a pair region)
     const bool slots_fit = fe->N + 2 + 2 * fe->mel_chunks <= 2 * 32 * (fe->N / 32 + 1);
     const bool four = fe->N <= 1024 && slots_fit && !(force && force[0] == '1');
+    // packed-f32x2 kernel (fe_frame5.cu) whenever the filterbank has the plain triangular structure and the
+    // power spectrum itself is not an output (ODIN_FE_FRAME4=1 keeps the scalar four-step kernel, for A/B runs)
+    const char* keep4 = getenv("ODIN_FE_FRAME4");
+    const bool five = four && fe->mel5_ok && d_spec == nullptr && !(keep4 && keep4[0] == '1');
     int rc;
-    if (four) {
+    if (five) {
+      a.tw = fe->d_tw4;
+      a.win5 = reinterpret_cast<const Win5*>(fe->d_win5); a.mel5_w = fe->d_mel5_w; a.mel5_flags = fe->d_mel5_flags;
+      a.mel5_sstart = fe->d_mel5_sstart; a.mel5_nslots = fe->mel5_nslots;
+      rc = fe_frame5_launch(fe->N, pcm_dtype, a, st);
+    } else if (four) {
       a.tw = fe->d_tw4;
       rc = (pcm_dtype == 0) ? dispatch_frame4<int16_t>(fe->N, a, st) : dispatch_frame4<float>(fe->N, a, st);
     } else {

@@ -58,6 +58,11 @@ class Tmatrix(object):
     self._device = device
     self.ncpu = int(ncpu) if ncpu is not None else 1
     self.gpu_factor = int(gpu_factor)
+    # gmm_tmat.py:1452-1461 (kept for the pickle tuple; the device path sizes its own batches)
+    self.batch_size_cpu = int(Tmatrix.STANDARD_CPU_BATCH_SIZE / (self.feat_dim * self.nmix * self._dtype.itemsize)) \
+        if isinstance(batch_size_cpu, str) else int(batch_size_cpu)
+    self.batch_size_gpu = int(Tmatrix.STANDARD_GPU_BATCH_SIZE / (self.feat_dim * self.nmix * self._dtype.itemsize)) \
+        if isinstance(batch_size_gpu, str) else int(batch_size_gpu)
     # gmm_tmat.py:1466-1471 (host: the numpy generator is part of the contract)
     self.Sigma = np.array(np.asarray(gmm.sigma).reshape((1, self.feat_dim * self.nmix), order='F'), dtype=self.dtype)
     np.random.seed(self._seed)
@@ -102,16 +107,27 @@ class Tmatrix(object):
     except Exception:
       pass
 
+  Im = property(lambda self: np.eye(self.tv_dim, dtype=self.dtype))   # gmm_tmat.py:1463
+
   def __getstate__(self):
-    return (self.niter, self._tv_dim, self._gmm, self._path, self._seed, self._llk_hist, self._name,
-            self.cache_path, self._dtype, self._is_fitted, self.Sigma, self.Tm)
+    """The reference's 21-tuple (gmm_tmat.py:1483-1499), so a tmat.pkl moves between the two in either direction
+    (given a GMM class importable under the pickled name)."""
+    return (self.Im, self.Sigma, self.Tm, self._gmm,
+            self._tv_dim, self._t2_dim, self._feat_dim, self._nmix,
+            self._seed, self._llk_hist,
+            self.batch_size_cpu, self.batch_size_gpu,
+            self.niter, self.ncpu, self._device, self.gpu_factor,
+            self.cache_path, self._dtype,
+            self._is_fitted, self._path, self._name)
 
   def __setstate__(self, s):
-    (self.niter, self._tv_dim, self._gmm, self._path, self._seed, self._llk_hist, self._name, self.cache_path,
-     self._dtype, self._is_fitted, self.Sigma, Tm) = s
-    self._t2_dim = self._tv_dim * (self._tv_dim + 1) // 2
-    self._feat_dim, self._nmix = self._gmm.feat_dim, self._gmm.nmix
-    self._device, self.ncpu, self.gpu_factor = 'gpu', 1, 3
+    (_, self.Sigma, Tm, self._gmm,
+     self._tv_dim, self._t2_dim, self._feat_dim, self._nmix,
+     self._seed, self._llk_hist,
+     self.batch_size_cpu, self.batch_size_gpu,
+     self.niter, self.ncpu, self._device, self.gpu_factor,
+     self.cache_path, self._dtype,
+     self._is_fitted, self._path, self._name) = s
     self._h = None
     self._create()
     self._upload(Tm, self.Sigma)
@@ -210,10 +226,18 @@ class Tmatrix(object):
     llk = float(acc[-2])
     self._mstep_device(acc, True, True)
     self._llk_hist.append(llk / nfiles)
-    if self.path is not None:
-      with open(self.path, 'wb') as f:
-        pickle.dump(self, f)
+    self._checkpoint()
     return self
+
+  def _checkpoint(self):
+    """Rank 0 only, through a temporary file (concurrent writers on a shared file system would corrupt it)."""
+    if self.path is not None:
+      td = _dist()
+      if td is None or td.get_rank() == 0:
+        tmp = "%s.tmp%d" % (self.path, os.getpid())
+        with open(tmp, 'wb') as f:
+          pickle.dump(self, f)
+        os.replace(tmp, self.path)
 
   # ---- sklearn surface ------------------------------------------------------
   def _stats_of(self, X):

@@ -52,13 +52,18 @@ def _no_cpu(cls):
 
 
 def read_wav(path):
-  """16-bit PCM wav -> (int16 array [n] or [n, ch], sr).  (The reference decodes
-  through soundfile/sox, speech.py:127-170; only plain PCM is handled here.)"""
+  """16-bit PCM wav -> (float32 array [n] or [n, ch] in [-1, 1), sr).
+
+  The reference decodes files through ``soundfile.read`` (speech.py:127-170), which returns float64 samples
+  normalised by 32768, and then casts to float32 (speech.py:453); int16 / 32768 is exact in float32, so the
+  values here are bit-identical to that route.  Only array / dict inputs stay unscaled.
+  Only plain PCM is handled here (no sox / sphere fall-backs)."""
   with wave.open(path, 'rb') as f:
     if f.getsampwidth() != 2:
       raise ValueError("only 16-bit PCM wav is supported: %s" % path)
     sr, ch, n = f.getframerate(), f.getnchannels(), f.getnframes()
     raw = np.frombuffer(f.readframes(n), dtype='<i2')
+  raw = raw.astype(np.float32) * np.float32(1.0 / 32768.0)
   return (raw.reshape(-1, ch) if ch > 1 else raw), sr
 
 
@@ -744,63 +749,58 @@ def plan_fusion(extractors):
   speech_types = (PreEmphasis, STFTExtractor, PowerSpecExtractor, MelsSpecExtractor, MFCCsExtractor,
                   SADgmm, SADthreshold, ApplyingSAD)
   transparent = (Converter, RenameFeatures, DuplicateFeatures)
+  def scan(j, alias):
+    """Pure look-ahead over a run of transparent steps from position j: (position after the run, the steps,
+    the alias map with their renames applied).  Nothing is committed: the caller adopts the result only when
+    the extractor after the run joins the fused step, so every user step is emitted exactly once."""
+    col, al = [], dict(alias)
+    while j < n and isinstance(extractors[j], transparent):
+      t = extractors[j]
+      if isinstance(t, (RenameFeatures, DuplicateFeatures)):
+        for x, y in zip(t.input_name, t.output_name):
+          al[y] = al.get(x, x)
+      col.append(t)
+      j += 1
+    return j, col, al
+
   while i < n:
     e = extractors[i]
     j = i
     reader = preemph = None
     deferred, alias = [], {}
-
-    def skip(j):
-      while j < n and isinstance(extractors[j], transparent):
-        t = extractors[j]
-        if isinstance(t, RenameFeatures):
-          for a, b in zip(t.input_name, t.output_name):
-            alias[b] = alias.get(a, a)
-        elif isinstance(t, DuplicateFeatures):
-          for a, b in zip(t.input_name, t.output_name):
-            alias[b] = alias.get(a, a)
-        deferred.append(t)
-        j += 1
-      return j
-
     if isinstance(extractors[j], AudioReader):
-      k = skip(j + 1)
+      k, col, al = scan(j + 1, alias)
       if k < n and isinstance(extractors[k], (PreEmphasis, STFTExtractor)):
         reader = extractors[j]
-        j = k
-      else:
-        deferred, alias = [], {}
+        deferred, alias, j = deferred + col, al, k
     if j < n and isinstance(extractors[j], PreEmphasis):
-      k = skip(j + 1)
+      k, col, al = scan(j + 1, alias)
       if k < n and isinstance(extractors[k], STFTExtractor):
         preemph = extractors[j]
-        j = k
+        deferred, alias, j = deferred + col, al, k
     if j + 2 < n and isinstance(extractors[j], STFTExtractor) and \
         isinstance(extractors[j + 1], PowerSpecExtractor) and isinstance(extractors[j + 2], MelsSpecExtractor):
       stft, power, mels = extractors[j:j + 3]
       j += 3
       mfcc = delta = sad = apply_sad = None
-      k = skip(j)
+      k, col, al = scan(j, alias)
       if k < n and isinstance(extractors[k], MFCCsExtractor):
         mfcc = extractors[k]
-        j = k + 1
+        deferred, alias, j = deferred + col, al, k + 1
       # Delta and SAD may come in either order
       for _ in range(2):
-        k = skip(j)
+        k, col, al = scan(j, alias)
         if k < n and delta is None and mfcc is not None and isinstance(extractors[k], DeltaExtractor):
           delta = extractors[k]
-          j = k + 1
+          deferred, alias, j = deferred + col, al, k + 1
         elif k < n and sad is None and isinstance(extractors[k], (SADgmm, SADthreshold)):
           sad = extractors[k]
-          j = k + 1
-      k = skip(j)
+          deferred, alias, j = deferred + col, al, k + 1
+      k, col, al = scan(j, alias)
       if k < n and sad is not None and isinstance(extractors[k], ApplyingSAD):
         apply_sad = extractors[k]
-        j = k + 1
-      # transparent steps collected past the last fused extractor stay where they are
-      n_after = sum(1 for t in extractors[j:k] if isinstance(t, transparent)) if k > j else 0
-      if n_after:
-        deferred = deferred[:len(deferred) - n_after]
+        deferred, alias, j = deferred + col, al, k + 1
+      # transparent steps past the last fused extractor were only looked at: the main loop emits them in place
       plan.append(FusedSpeechFrontEnd(reader, preemph, stft, power, mels, mfcc, delta, sad, apply_sad,
                                       alias=dict(alias)))
       plan.extend(deferred)
@@ -809,11 +809,15 @@ def plan_fusion(extractors):
     # [AudioReader] [PreEmphasis] SpectraExtractor | Framing: the extractor takes the reader's DC removal
     # and the pre-emphasis into its own fused run
     if isinstance(e, (AudioReader, PreEmphasis, SpectraExtractor, Framing)):
-      j, rd, pe, deferred, alias = i, None, None, [], {}
+      j, rd, pe, deferred = i, None, None, []
       if isinstance(extractors[j], AudioReader):
-        rd, j = extractors[j], skip(j + 1)
+        k, col, _ = scan(j + 1, {})
+        if k < n and isinstance(extractors[k], (PreEmphasis, SpectraExtractor, Framing)):
+          rd, deferred, j = extractors[j], deferred + col, k
       if j < n and isinstance(extractors[j], PreEmphasis):
-        pe, j = extractors[j], skip(j + 1)
+        k, col, _ = scan(j + 1, {})
+        if k < n and isinstance(extractors[k], (SpectraExtractor, Framing)):
+          pe, deferred, j = extractors[j], deferred + col, k
       if j < n and isinstance(extractors[j], (SpectraExtractor, Framing)):
         extractors[j].bind(rd, pe)
         plan.append(extractors[j])

@@ -241,6 +241,56 @@ def test_fusion_plan_of_the_fsdd_recipe():
     pp.AcousticNorm('mfcc', win_length=300)
 
 
+def test_plan_fusion_emits_every_transparent_step_exactly_once():
+  """Transparent steps (Converter / RenameFeatures / DuplicateFeatures) behind MFCC, SAD or Delta are looked at
+  while the planner searches for the next fusable extractor; whether or not one follows, each user step must
+  appear exactly once in the plan (a non-idempotent Converter or an in-place rename must not run twice)."""
+  head = [pp.AudioReader(), pp.STFTExtractor(0.025, 0.01), pp.PowerSpecExtractor(), pp.MelsSpecExtractor(24),
+          pp.MFCCsExtractor(20, first_coef_energy=True)]
+  names = lambda pipe: [type(e).__name__ for e in pipe.plan]
+  # nothing fusable after the rename: it stays in place, once
+  p = pp.make_pipeline(head + [pp.RenameFeatures('mfcc', 'cep'), pp.AcousticNorm(input_name='cep')])
+  assert names(p) == ['FusedSpeechFrontEnd', 'RenameFeatures', 'AcousticNorm']
+  assert p.plan[0].alias == {}                      # the rename was not taken into the fused step
+  # rename in front of the SAD (fused), duplicate in front of ApplyingSAD (fused): both deferred, once each
+  p = pp.make_pipeline(head + [pp.RenameFeatures('mfcc_energy', 'energy'), pp.SADthreshold(input_name='energy'),
+                               pp.DuplicateFeatures('mfcc', 'mfcc2'), pp.ApplyingSAD(input_name='mfcc')])
+  assert names(p) == ['FusedSpeechFrontEnd', 'RenameFeatures', 'DuplicateFeatures']
+  assert p.plan[0].sad is not None and p.plan[0].apply_sad is not None
+  # ... and when no ApplyingSAD follows, the duplicate is emitted in place, once
+  p = pp.make_pipeline(head + [pp.RenameFeatures('mfcc_energy', 'energy'), pp.SADthreshold(input_name='energy'),
+                               pp.DuplicateFeatures('mfcc', 'mfcc2'), pp.AsType('float16')])
+  assert names(p) == ['FusedSpeechFrontEnd', 'RenameFeatures', 'DuplicateFeatures', 'AsType']
+  # a converter between Delta and nothing
+  calls = []
+  conv = pp.Converter(converter=lambda x: calls.append(x) or x, input_name='path', output_name='path2')
+  p = pp.make_pipeline(head + [pp.DeltaExtractor('mfcc', order=(0, 1)), conv, pp.DeleteFeatures('stft')])
+  assert names(p) == ['FusedSpeechFrontEnd', 'Converter', 'DeleteFeatures']
+  for pipe in (p,):
+    user = [e for _, e in pipe.steps]
+    flat = [id(e) for e in pipe.plan]
+    assert len(flat) == len(set(flat)) and all(id(e) in [id(u) for u in user] or type(e).__name__ == 'FusedSpeechFrontEnd'
+                                               for e in pipe.plan)
+
+
+def test_audio_reader_file_input_is_normalised_like_soundfile(tmp_path):
+  """speech.py:127-170, 453: files go through soundfile.read (float64 in [-1, 1)) then astype(float32); arrays and
+  dicts are NOT rescaled.  int16 / 32768 is exact in float32."""
+  import wave
+  x = (np.random.RandomState(3).randn(4000) * 8000).astype(np.int16)
+  path = str(tmp_path / "a.wav")
+  with wave.open(path, "wb") as f:
+    f.setnchannels(1); f.setsampwidth(2); f.setframerate(16000)
+    f.writeframes(x.astype("<i2").tobytes())
+  rd = pp.AudioReader()
+  for inp in (path, {"path": path}, (path, None)):
+    d = rd.transform(inp)
+    assert d["sr"] == 16000 and d["raw"].dtype == np.float32 and d["path"] == os.path.abspath(path)
+    assert np.array_equal(d["raw"], (x.astype(np.float64) / 32768.0).astype(np.float32))
+  d = rd.transform({"raw": x, "sr": 16000})
+  assert d["raw"].dtype == np.int16 and np.array_equal(d["raw"], x)          # arrays stay unscaled
+
+
 def test_plan_fusion_variants():
   """Planning is host logic: which extractor runs take the reader's DC removal / the pre-emphasis into their kernels."""
   from odin_b200 import preprocessing as pp
