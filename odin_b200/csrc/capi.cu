@@ -195,23 +195,19 @@ int fe_build_tables(odin_fe* fe) {
     fe->mel_chunks = (int)chunks.size();
     if (nb > 0x7fff || chunks.size() > 0xffff) return set_error(ODIN_EINVAL, "filterbank too large for the packed table");
   }
-  // Segment form for fe_frame5_kernel (n_fft <= 1024).  With centres p_0 .. p_(nm+1), a bin in segment s =
-  // [p_s, p_(s+1)) lies on the falling side of filter s-1 and on the rising side of filter s and nowhere else;
-  // lane l of a warp owns the NK = N/64 contiguous bins NK l .. NK l + NK-1, keeps one falling and one rising
-  // accumulator and drops them into the next partial-sum slot whenever its next bin belongs to another segment
-  // (and after its last bin).  Slots are therefore in bin order and segment s owns slots [sstart[s], sstart[s+1]);
-  // filter m = rising sums of segment m + falling sums of segment m+1.
-  std::vector<Win5> win5(L);
-  for (int k = 0; k < L; ++k) {
-    win5[k].w = fe->h_win[k];
-    win5[k].ws = (float)(fe->h_win[k] * 0.5 * scale);
-    win5[k].pad_ = 0.f;
-  }
+  // Lane-chunk form for fe_frame5_kernel (n_fft <= 1024).  With centres p_0 .. p_(nm+1), a bin in segment s =
+  // [p_s, p_(s+1)) lies on the falling side of filter s-1 and on the rising side of filter s and nowhere else.
+  // Lane l of a warp owns the NK = N/64 contiguous bins NK l .. NK l + NK-1 and keeps two accumulators, one for
+  // the filter it is on the falling side of and one for the filter it is on the rising side of.  When its next
+  // bin lies in the next segment the falling filter is complete for this lane: it is dropped into the next
+  // partial-sum slot, the rising accumulator takes the falling role and a new rising one starts at zero; after
+  // its last bin the lane drops both.  Filter m then adds its K or fewer slots (listed in bin order in `refs`).
+  fe->win_c = (float)(0.5 * scale);
   std::vector<float2> m5w;
   std::vector<uint32_t> m5flags(32, 0u);
-  std::vector<int> m5sstart(nm + 2, 0);
+  std::vector<uint16_t> m5refs;
   fe->mel5_ok = false;
-  fe->mel5_nslots = 0;
+  fe->mel5_nslots = fe->mel5_k = 0;
   if (N <= 1024) {
     const int NK = N / 64, nhalf = N / 2;
     bool ok = true;
@@ -223,32 +219,40 @@ int fe_build_tables(odin_fe* fe) {
       seg[k] = s;
       for (int m = 0; m < nm; ++m)
         if (fe->h_mel[(size_t)m * nb + k] != 0.0 && m != s && m != s - 1) ok = false;
-      const float wdn = s >= 1 ? (float)fe->h_mel[(size_t)(s - 1) * nb + k] : 0.f;
-      const float wup = s < nm ? (float)fe->h_mel[(size_t)s * nb + k] : 0.f;
-      m5w[(size_t)(k % NK) * 32 + k / NK] = make_float2(wdn, wup);
+      if (k > 0 && seg[k] - seg[k - 1] > 1) ok = false;   // a centre pair without a bin between: not this kernel's case
+      const float wfall = s >= 1 ? (float)fe->h_mel[(size_t)(s - 1) * nb + k] : 0.f;
+      const float wrise = s < nm ? (float)fe->h_mel[(size_t)s * nb + k] : 0.f;
+      m5w[(size_t)(k % NK) * 32 + k / NK] = make_float2(wfall, wrise);
     }
     for (int m = 0; m < nm; ++m) ok = ok && fe->h_mel[(size_t)m * nb + nhalf] == 0.0;   // Nyquist bin: never weighted
     if (ok) {
-      std::vector<int> slot_seg;
+      std::vector<int> slot_filter;   // filter fed by slot i (-1 / nm: none)
       for (int l = 0; l < 32; ++l) {
         uint32_t fl = 0;
-        const uint32_t first = (uint32_t)slot_seg.size();
+        const uint32_t first = (uint32_t)slot_filter.size();
         for (int j = 0; j < NK; ++j) {
           const int k = NK * l + j;
-          if (j == NK - 1) slot_seg.push_back(seg[k]);
-          else if (seg[k + 1] != seg[k]) { fl |= 1u << j; slot_seg.push_back(seg[k]); }
+          if (j == NK - 1) { slot_filter.push_back(seg[k] - 1); slot_filter.push_back(seg[k]); }
+          else if (seg[k + 1] != seg[k]) { fl |= 1u << j; slot_filter.push_back(seg[k] - 1); }
         }
         m5flags[l] = fl | (first << 16);
       }
-      // (slot_seg is non-decreasing; segments without bins own no slot)
-      size_t p = 0;
-      for (int s = 0; s <= nm + 1; ++s) {
-        while (p < slot_seg.size() && slot_seg[p] < s) ++p;
-        m5sstart[s] = (int)p;
-      }
-      fe->mel5_nslots = (int)slot_seg.size();
-      // the slots (16 B each) reuse a pair region of the kernel: 8 * f5_region<N>() bytes >= 8 * (N + 65)
-      ok = (size_t)fe->mel5_nslots * 16 <= (size_t)(N + 65) * 8;
+      const int nslots = (int)slot_filter.size();
+      std::vector<std::vector<int>> of(nm);
+      for (int i = 0; i < nslots; ++i)
+        if (slot_filter[i] >= 0 && slot_filter[i] < nm) of[slot_filter[i]].push_back(i);
+      size_t K = 1;
+      for (int m = 0; m < nm; ++m) K = std::max(K, of[m].size());
+      const int rounds = (nm + 31) / 32;
+      K = (K + 3) & ~size_t(3);   // four 16-bit slot indices per 8-byte word: [rounds][K / 4][32][4]
+      m5refs.assign((size_t)rounds * K * 32, (uint16_t)nslots);   // padding: the zero slot
+      for (int m = 0; m < nm; ++m)
+        for (size_t i = 0; i < of[m].size(); ++i)
+          m5refs[((((size_t)(m / 32) * (K / 4) + i / 4) * 32) + m % 32) * 4 + i % 4] = (uint16_t)of[m][i];
+      fe->mel5_nslots = nslots;
+      fe->mel5_k = (int)K;
+      // the slots (8 B each, + the zero slot) reuse a pair region of the kernel: 8 * f5_region<N>() bytes >= 8 * (N + 65)
+      ok = nslots + 1 <= N + 65 && K <= 16;
     }
     fe->mel5_ok = ok;
   }
@@ -281,10 +285,9 @@ int fe_build_tables(odin_fe* fe) {
   if ((rc = upload(&fe->d_mel_w, mw))) return rc;
   if ((rc = upload(&fe->d_mel_tab, mtab))) return rc;
   if ((rc = upload(&fe->d_mel_ps, mps))) return rc;
-  if ((rc = upload(reinterpret_cast<Win5**>(&fe->d_win5), win5))) return rc;
   if ((rc = upload(&fe->d_mel5_w, m5w))) return rc;
   if ((rc = upload(&fe->d_mel5_flags, m5flags))) return rc;
-  if ((rc = upload(&fe->d_mel5_sstart, m5sstart))) return rc;
+  if ((rc = upload(&fe->d_mel5_refs, m5refs))) return rc;
   if ((rc = upload(&fe->d_dct, dct32))) return rc;
   if ((rc = upload(&fe->d_taps, taps))) return rc;
   return ODIN_OK;
@@ -371,7 +374,7 @@ void odin_fe_destroy(odin_fe_t* fe) {
   cudaFree(fe->d_win32); cudaFree(fe->d_win64); cudaFree(fe->d_tw); cudaFree(fe->d_tw4); cudaFree(fe->d_mel_start);
   cudaFree(fe->d_mel_cnt); cudaFree(fe->d_mel_off); cudaFree(fe->d_mel_w); cudaFree(fe->d_dct);
   cudaFree(fe->d_mel_tab); cudaFree(fe->d_mel_ps);
-  cudaFree(fe->d_win5); cudaFree(fe->d_mel5_w); cudaFree(fe->d_mel5_flags); cudaFree(fe->d_mel5_sstart);
+  cudaFree(fe->d_mel5_w); cudaFree(fe->d_mel5_flags); cudaFree(fe->d_mel5_refs);
   cudaFree(fe->d_taps); cudaFree(fe->d_sample_off); cudaFree(fe->d_dcsum); cudaFree(fe->d_umax);
   cudaFree(fe->d_cnt); cudaFree(fe->d_vad_scratch);
   if (fe->h_stage) cudaFreeHost(fe->h_stage);

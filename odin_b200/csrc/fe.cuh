@@ -32,11 +32,11 @@ struct odin_fe {
   int mel_trips = 0, mel_chunks = 0;
   // segment form of the filterbank + scaled window for fe_frame5_kernel (fe_frame5.cu); mel5_ok = the bank has
   // the triangular structure that kernel assumes (every bin feeds at most the two filters around it)
-  void* d_win5 = nullptr;          // Win5[L]
+  float win_c = 0.f;               // 1/2 * 1/sum(w)
   float2* d_mel5_w = nullptr;      // [N/64][32]
   uint32_t* d_mel5_flags = nullptr;// [32]
-  int* d_mel5_sstart = nullptr;    // [n_mels + 2]
-  int mel5_nslots = 0;
+  uint16_t* d_mel5_refs = nullptr; // [ceil(n_mels/32)][mel5_k][32]
+  int mel5_nslots = 0, mel5_k = 0;
   bool mel5_ok = false;
   // per-run scratch (capacity in utterances)
   int cap_utt = 0;

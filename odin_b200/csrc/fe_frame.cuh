@@ -12,8 +12,6 @@ constexpr int FT = ODIN_FE_TILE;
 constexpr int FE_WARPS = 8;
 constexpr int FE_THREADS = FE_WARPS * 32;
 
-struct Win5 { double w; float ws; float pad_; };   // window value (fp64) | (float)(w * 0.5 / sum w)
-
 struct FrameArgs {
   const void* pcm;
   const int64_t* sample_off;
@@ -44,12 +42,12 @@ struct FrameArgs {
   float* spec;    // [T, N/2+1] nullable: power spectrum (SpectraExtractor, signal.py:1718-1832), dB when spec_log
   int spec_log;
   int* umax_spec; // [n_utt] ordered-int max of the dB spectrum
-  // fe_frame5_kernel (fe_frame5.cu): window with the 1/2 * 1/sum(w) scale folded in, segment form of the filterbank
-  const Win5* win5;          // [L]
-  const float2* mel5_w;      // [N/64][32] {falling weight, rising weight} of bin (N/64) * lane + j
-  const uint32_t* mel5_flags;// [32] bit j: a mel-centre lies between bins j and j + 1 of the lane's chunk
-  const int* mel5_sstart;    // [n_mels + 3] partial-sum slots of segment s: [sstart[s], sstart[s+1])
-  int mel5_nslots;
+  // fe_frame5_kernel (fe_frame5.cu): 1/2 * 1/sum(w) (folded into the fp32 samples), lane-chunk form of the filterbank
+  float win_c;
+  const float2* mel5_w;      // [N/64][32] {falling-side weight, rising-side weight} of bin (N/64) * lane + j
+  const uint32_t* mel5_flags;// [32] bit j: a mel centre lies between bins j and j + 1 of the lane's chunk | first slot << 16
+  const uint16_t* mel5_refs; // [rounds][K][32] partial-sum slots of filter 32 round + lane (padded with the zero slot)
+  int mel5_nslots, mel5_k;   // slots written per pair (the zero slot is index nslots); refs per filter
 };
 
 // PCM tile -> shared memory with DC removal and pre-emphasis fused (speech.py:472-473, signal.py:955-967);

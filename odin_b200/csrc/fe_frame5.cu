@@ -16,10 +16,12 @@
 //     into the fp32 window.
 //   * mel projection on the power values while they are in registers.  A lane owns N/64 CONTIGUOUS bins; a
 //     bin between the centres p_s and p_(s+1) ("segment" s) only feeds the falling side of filter s-1 and the
-//     rising side of filter s, so a lane keeps two packed accumulators (falling | rising, frames A | B), and
-//     drops them into a slot whenever its bins cross a centre.  Filter m = rising sum of segment m + falling sum
-//     of segment m+1, a handful of slots.  This replaces the table walk of fe_frame4_kernel (random shared-memory
-//     reads: 25 % of its instructions and all of its bank conflicts).
+//     rising side of filter s, so a lane keeps two packed accumulators (frames A | B) -- the filter it is on
+//     the falling side of and the one it is on the rising side of -- drops the first into a slot when its bins
+//     cross a centre and hands the second over.  Filter m adds its <= K slots (K = 2..4).  This replaces the
+//     table walk of fe_frame4_kernel (random shared-memory reads: 25 % of its instructions and all of its bank
+//     conflicts).
+//   * the PCM staging copy takes 4 samples per thread with a bounds-free interior path (stage_pcm5).
 //   * the rows of step A that are zero padding (L <= n_fft / 2 and the tail of the last live row) are template
 //     parameters: no predicated-off instructions are issued for them.
 //
@@ -29,6 +31,8 @@
 #include <float.h>
 #include <math.h>
 #include <stdlib.h>
+
+#include <type_traits>
 
 #include "fe.cuh"
 #include "fe_frame.cuh"
@@ -97,31 +101,112 @@ template <int N> constexpr int f5_region() {
   return N == 256 ? ((r + 15) / 16) * 16 + 8 : (r + 1) & ~1;
 }
 
+// PCM tile -> shared memory with DC removal and pre-emphasis fused: the arithmetic of stage_pcm (fe_frame.cuh;
+// speech.py:472-473, signal.py:955-967, two roundings per stage), arranged for this kernel: a thread takes FOUR
+// samples (8-byte loads of int16 / 16-byte loads of float32, aligned in global memory) and writes ONE 16-byte
+// shared store, so consecutive lanes fill consecutive banks (the 8-sample chunks of stage_pcm stored two 16-byte
+// words at a 32-byte lane stride: 2-way conflicts), and a chunk inside the utterance takes a path without any
+// per-sample bounds test (ncu of the first version of this kernel: the staging copy was 12 % of its
+// instructions, most of them 64-bit index compares and selects).  Returns the tile origin (sbase + 0..3).
+template <typename PCM>
+__device__ __forceinline__ float* stage_pcm5(float* __restrict__ sbase, const PCM* __restrict__ pu, int64_t n_u,
+                                             int64_t v0, int cnt, float mean, float coef, int pad, int tid, int next) {
+  using Vec = typename std::conditional<sizeof(PCM) == 2, uint2, float4>::type;   // four samples
+  const int64_t gstart = v0 - pad;   // utterance index of tile element 0 (negative inside the left padding)
+  const int mis = (int)((reinterpret_cast<uintptr_t>(pu + gstart) / sizeof(PCM)) & 3);
+  const int n_chunks = (cnt + mis + 3) >> 2;
+  const int64_t gbase = gstart - mis;                    // utterance index of chunk 0 (4-sample aligned in memory)
+  const PCM* __restrict__ pbase = pu + gbase;
+  // chunks [c_lo, c_hi) lie inside the utterance with a predecessor sample: no bounds tests
+  const int c_lo = (int)max((int64_t)0, (4 - gbase) >> 2), c_hi = (int)min((int64_t)n_chunks, (n_u - gbase) >> 2);
+  constexpr int U = 4;   // chunks in flight per thread: the loads of a batch are issued before the first use
+  for (int c0 = tid; c0 < n_chunks; c0 += U * FE_THREADS) {
+    Vec raw[U];
+    PCM prv[U];
+#pragma unroll
+    for (int q = 0; q < U; ++q) {
+      const int c = c0 + q * FE_THREADS;
+      if (c >= c_lo && c < c_hi) {
+        raw[q] = *reinterpret_cast<const Vec*>(pbase + 4 * c);
+        prv[q] = pbase[4 * c - 1];
+        // the CTA's next tile reads the samples `next` further on (same utterance, or the head of the following
+        // one): pull them into L2 now, so that its staging loads wait for L2 instead of HBM
+        if ((c & 7) == 0) asm volatile("prefetch.global.L2 [%0];" :: "l"(pbase + 4 * c + next));
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < U; ++q) {
+      const int c = c0 + q * FE_THREADS;
+      if (c >= n_chunks) break;
+      float y[4];
+      if (c >= c_lo && c < c_hi) {
+        float x[4];
+        if constexpr (sizeof(PCM) == 2) {
+          union { uint2 u; short e[4]; } r;
+          r.u = *reinterpret_cast<const uint2*>(&raw[q]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) x[e] = __fsub_rn((float)r.e[e], mean);
+        } else {
+          const float4 r = *reinterpret_cast<const float4*>(&raw[q]);
+          x[0] = __fsub_rn(r.x, mean); x[1] = __fsub_rn(r.y, mean);
+          x[2] = __fsub_rn(r.z, mean); x[3] = __fsub_rn(r.w, mean);
+        }
+        if (coef != 0.f) {
+          y[0] = __fsub_rn(x[0], __fmul_rn(coef, __fsub_rn((float)prv[q], mean)));
+#pragma unroll
+          for (int e = 1; e < 4; ++e) y[e] = __fsub_rn(x[e], __fmul_rn(coef, x[e - 1]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) y[e] = x[e];
+        }
+      } else {   // chunk touching an end of the utterance (or the virtual padding): sample by sample
+        const int64_t g0 = gbase + 4 * c;
+        float prev = (g0 >= 1 && g0 - 1 < n_u) ? __fsub_rn((float)pu[g0 - 1], mean) : 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int64_t g = g0 + e;
+          const bool in = g >= 0 && g < n_u;
+          const float x = in ? __fsub_rn((float)pu[in ? g : 0], mean) : 0.f;
+          float cur = x;
+          if (coef != 0.f && g > 0) cur = __fsub_rn(cur, __fmul_rn(coef, prev));
+          y[e] = in ? cur : 0.f;
+          prev = x;
+        }
+      }
+      *reinterpret_cast<float4*>(sbase + 4 * c) = make_float4(y[0], y[1], y[2], y[3]);
+    }
+  }
+  return sbase + mis;
+}
+
 // NZ live rows in step A (rows r >= NZ are zero padding); EXACT: (NZ - 1) * G <= L, so only the last live row
 // needs the i < L test.
 template <int N, typename PCM, int NZ, bool EXACT>
 __global__ void __launch_bounds__(FE_THREADS, 2) fe_frame5_kernel(FrameArgs a) {
   constexpr int G = N / 32, NP = 32 / G, RS = G + 1, REG = f5_region<N>(), NK = N / 64;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: win5 [L] | pair regions [FE_WARPS][NP * REG] float2 | tw4 [N] float2 | mel weights [NK][32] float2 |
-  //         sstart [n_mels + 2] | sbuf [(FT-1)*hop + L + 16]
-  Win5* win5 = reinterpret_cast<Win5*>(smem_raw);
-  u64* bufs = reinterpret_cast<u64*>(win5 + a.L);
+  // layout: win64 [L] | pair regions [FE_WARPS][NP * REG] float2 | tw4 [N] float2 | mel weights [NK][32] float2 |
+  //         refs [rounds][K][32] u16 | sbuf [(FT-1)*hop + L + 8]
+  double* win64 = reinterpret_cast<double*>(smem_raw);
+  u64* bufs = reinterpret_cast<u64*>(win64 + a.L + (a.L & 1));
   u64* tw4 = bufs + FE_WARPS * NP * REG;
   float2* melw = reinterpret_cast<float2*>(tw4 + N);
-  int* sstart = reinterpret_cast<int*>(melw + NK * 32);
-  float* sbuf = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sstart + a.n_mels + 2) + 15) & ~uintptr_t(15));
+  uint16_t* refs = reinterpret_cast<uint16_t*>(melw + NK * 32);
+  const int rounds = (a.n_mels + 31) >> 5, K = a.mel5_k;
+  float* sbuf = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(refs + rounds * K * 32) + 15) & ~uintptr_t(15));
   __shared__ int cta_max;
   __shared__ double s_en[FT];   // frame energies of the tile; their logs are taken by one warp at the end
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane / G, l = lane % G;
   const int L = a.L, hop = a.hop;
-  for (int i = tid; i < L; i += FE_THREADS) win5[i] = a.win5[i];
+  for (int i = tid; i < L; i += FE_THREADS) win64[i] = a.win64[i];
   for (int i = tid; i < N; i += FE_THREADS) tw4[i] = reinterpret_cast<const u64*>(a.tw)[i];
   for (int i = tid; i < NK * 32; i += FE_THREADS) melw[i] = a.mel5_w[i];
-  for (int i = tid; i < a.n_mels + 2; i += FE_THREADS) sstart[i] = a.mel5_sstart[i];
-  const uint32_t mflags = a.mel5_flags[lane];   // bits 0..NK-2: flush after bin j; bits 16..: the lane's first slot
+  for (int i = tid; i < rounds * K * 32; i += FE_THREADS) refs[i] = a.mel5_refs[i];
+  const uint32_t mflags = a.mel5_flags[lane];   // bits 0..NK-2: a centre lies behind bin j; bits 16..: the lane's first slot
+  const int zero_slot = a.mel5_nslots;
+  const float win_c = a.win_c;
   u64* wbuf = bufs + warp * (NP * REG);
   const PCM* __restrict__ pcm = reinterpret_cast<const PCM*>(a.pcm);
   const float coef = a.preemph;
@@ -132,6 +217,18 @@ __global__ void __launch_bounds__(FE_THREADS, 2) fe_frame5_kernel(FrameArgs a) {
   if (tile_lo >= tile_hi) return;
   int u = find_segment(a.tile_off, a.n_utt, tile_lo);
   int64_t u_end = a.tile_off[u + 1];
+  // The logs of a tile's frame energies (fp64 log: a long dependent sequence on one lane per frame) are taken
+  // while the NEXT tile is being staged, between its two barriers, where they overlap the global-memory latency
+  // of the staging loads instead of extending the tile by a serial tail.
+  float* en_dst = nullptr;
+  int en_n = 0;
+  auto flush_energies = [&]() {
+    if (tid < en_n) {
+      double e = s_en[tid];
+      if (e == 0.0) e = (double)FLT_EPSILON;  // signal.py:1436
+      en_dst[tid] = (float)log(e);
+    }
+  };
   for (int64_t tile = tile_lo; tile < tile_hi; ++tile) {
     while (tile >= u_end) { ++u; u_end = a.tile_off[u + 1]; }
     const int64_t s0 = a.sample_off[u];
@@ -147,9 +244,11 @@ __global__ void __launch_bounds__(FE_THREADS, 2) fe_frame5_kernel(FrameArgs a) {
     }
     __syncthreads();  // previous tile done with sbuf / cta_max / s_en (and the table fill on the first trip)
     if (tid == 0) cta_max = float_to_ordered(-FLT_MAX);
-    const float* stile = stage_pcm<PCM>(sbuf, pcm + s0, n_u, (int64_t)t0 * hop, (nf - 1) * hop + L, mean, coef, a.pad,
-                                        tid, FE_THREADS);
+    const float* stile = stage_pcm5<PCM>(sbuf, pcm + s0, n_u, (int64_t)t0 * hop, (nf - 1) * hop + L, mean, coef, a.pad, tid,
+                                         tile + 1 < tile_hi ? FT * hop : 0);
+    flush_energies();
     __syncthreads();
+    if (a.energy != nullptr) { en_dst = a.energy + fbase + t0; en_n = nf; }
 
     float wmax = -FLT_MAX;
     const int npairs = (nf + 1) >> 1;
@@ -162,7 +261,7 @@ __global__ void __launch_bounds__(FE_THREADS, 2) fe_frame5_kernel(FrameArgs a) {
         // frames past the end of the tile are computed on the tile's last frame and never stored
         const float* sA = stile + min(fA, nf - 1) * hop + l;
         const float* sB = stile + min(fB, nf - 1) * hop + l;
-        const Win5* wp = win5 + l;
+        const double* wp = win64 + l;
         double eA = 0.0, eB = 0.0;
         u64 v[32];
 #pragma unroll
@@ -171,12 +270,13 @@ __global__ void __launch_bounds__(FE_THREADS, 2) fe_frame5_kernel(FrameArgs a) {
           if (r < NZ) {
             const bool live = (EXACT && r < NZ - 1) ? true : (l + G * r < L);
             if (live) {
-              const float xa = sA[G * r], xb = sB[G * r];
-              const Win5 w = wp[G * r];
-              const double wa = w.w * (double)xa, wb = w.w * (double)xb;
+              // the window multiply in fp64 (signal.py:1543-1545) serves the frame energy; its rounding to fp32,
+              // times 1/2 * 1/sum(w), is the FFT input -- one 8-byte table read per sample pair
+              const double w = wp[G * r];
+              const double wa = w * (double)sA[G * r], wb = w * (double)sB[G * r];
               eA = fma(wa, wa, eA);
               eB = fma(wb, wb, eB);
-              z = mul2(pk2(xa, xb), pk2(w.ws, w.ws));
+              z = mul2(pk2((float)wa, (float)wb), pk2(win_c, win_c));
             }
           }
           v[r] = z;
@@ -239,37 +339,45 @@ __global__ void __launch_bounds__(FE_THREADS, 2) fe_frame5_kernel(FrameArgs a) {
 #pragma unroll
         for (int j = 0; j < NK; ++j) { z1[j] = p1[j]; z2[j] = (j == 0) ? p2[1] : p2[-j]; }
         __syncwarp();   // the spectrum is in registers: the region now takes the partial-sum slots
-        float4* slots = reinterpret_cast<float4*>(buf);
-        int slot = (int)(mflags >> 16);
-        u64 accD = 0ull, accU = 0ull;
+        u64* slot = buf + (mflags >> 16);
+        if (lane == 0) buf[zero_slot] = 0ull;
+        u64 accF = 0ull, accR = 0ull;   // filter on whose falling / rising side the current bin lies: (frame A, frame B)
 #pragma unroll
         for (int j = 0; j < NK; ++j) {
           const u64 s = add2(z1[j], z2[j]), d = sub2(z1[j], z2[j]);
           const u64 ds = pk2(hi32(d), lo32(d));
-          const u64 P = fma2(ds, ds, mul2(s, s));   // (|A_k|^2, |B_k|^2) * scale^2
+          const u64 P = fma2(ds, ds, mul2(s, s));   // (|A_k|^2, |B_k|^2) / sum(w)^2
           const float2 w = melw[j * 32 + lane];
-          accD = fma2(P, pk2(w.x, w.x), accD);
-          accU = fma2(P, pk2(w.y, w.y), accU);
-          if (j == NK - 1 || ((mflags >> j) & 1u)) {
-            slots[slot] = make_float4(lo32(accD), hi32(accD), lo32(accU), hi32(accU));
-            ++slot;
-            accD = 0ull; accU = 0ull;
+          accF = fma2(P, pk2(w.x, w.x), accF);
+          accR = fma2(P, pk2(w.y, w.y), accR);
+          if (j < NK - 1) {
+            if ((mflags >> j) & 1u) { *slot++ = accF; accF = accR; accR = 0ull; }
+          } else {
+            slot[0] = accF; slot[1] = accR;
           }
         }
         __syncwarp();
         float* rowA = a.mspec + (fbase + t0 + fA) * a.n_mels;
-        for (int m = lane; m < a.n_mels; m += 32) {
-          const int s0 = sstart[m], s1 = sstart[m + 1], s2 = sstart[m + 2];
-          float accA = 0.f, accB = 0.f;
-          for (int i = s0; i < s1; ++i) { const float4 q = slots[i]; accA += q.z; accB += q.w; }   // rising side
-          for (int i = s1; i < s2; ++i) { const float4 q = slots[i]; accA += q.x; accB += q.y; }   // falling side
-          const float dA = db10<float>(accA);
-          rowA[m] = dA;
-          wmax = fmaxf(wmax, dA);
-          if (hasB) {
-            const float dB = db10<float>(accB);
-            rowA[a.n_mels + m] = dB;
-            wmax = fmaxf(wmax, dB);
+        for (int r = 0; r < rounds; ++r) {
+          // the filter's slots in bin order, four 16-bit indices per word: four independent loads, then a tree
+          const u64* rp = reinterpret_cast<const u64*>(refs) + r * (K >> 2) * 32 + lane;
+          u64 acc = 0ull;
+          for (int i = 0; i < (K >> 2); ++i) {
+            const u64 ix = rp[i * 32];
+            const u64 q0 = buf[ix & 0xffffu], q1 = buf[(ix >> 16) & 0xffffu];
+            const u64 q2 = buf[(ix >> 32) & 0xffffu], q3 = buf[ix >> 48];
+            acc = add2(acc, add2(add2(q0, q1), add2(q2, q3)));
+          }
+          const int m = 32 * r + lane;
+          if (m < a.n_mels) {
+            const float dA = db10<float>(lo32(acc));
+            rowA[m] = dA;
+            wmax = fmaxf(wmax, dA);
+            if (hasB) {
+              const float dB = db10<float>(hi32(acc));
+              rowA[a.n_mels + m] = dB;
+              wmax = fmaxf(wmax, dB);
+            }
           }
         }
       }
@@ -278,20 +386,17 @@ __global__ void __launch_bounds__(FE_THREADS, 2) fe_frame5_kernel(FrameArgs a) {
     if (lane == 0) atomicMax(&cta_max, float_to_ordered(wmax));
     __syncthreads();
     if (tid == 0) atomicMax(a.umax + u, cta_max);
-    if (a.energy != nullptr && tid < nf) {
-      double e = s_en[tid];
-      if (e == 0.0) e = (double)FLT_EPSILON;  // signal.py:1436
-      a.energy[fbase + t0 + tid] = (float)log(e);
-    }
   }
+  flush_energies();   // (the last tile's s_en is complete: the __syncthreads above)
 }
 
 template <int N, typename PCM, int NZ, bool EXACT>
 static int launch5(const FrameArgs& a, cudaStream_t st) {
   constexpr int NP = 32 / (N / 32), NK = N / 64;
-  size_t smem = (size_t)a.L * sizeof(Win5) + (size_t)FE_WARPS * NP * f5_region<N>() * sizeof(float2) +
-                (size_t)N * sizeof(float2) + (size_t)NK * 32 * sizeof(float2) + (size_t)(a.n_mels + 2) * sizeof(int) +
-                16 + (size_t)((FT - 1) * a.hop + a.L + 16 + 4) * sizeof(float);
+  size_t smem = (size_t)(a.L + (a.L & 1)) * sizeof(double) + (size_t)FE_WARPS * NP * f5_region<N>() * sizeof(float2) +
+                (size_t)N * sizeof(float2) + (size_t)NK * 32 * sizeof(float2) +
+                (size_t)((a.n_mels + 31) / 32) * a.mel5_k * 32 * sizeof(uint16_t) +
+                16 + (size_t)((FT - 1) * a.hop + a.L + 8 + 4) * sizeof(float);
   if (smem > 227 * 1024) return set_error(ODIN_EINVAL, "frame kernel needs %zu B smem (hop too large)", smem);
   auto k = fe_frame5_kernel<N, PCM, NZ, EXACT>;
   ODIN_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -1660,8 +1660,8 @@ int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t 
     int rc;
     if (five) {
       a.tw = fe->d_tw4;
-      a.win5 = reinterpret_cast<const Win5*>(fe->d_win5); a.mel5_w = fe->d_mel5_w; a.mel5_flags = fe->d_mel5_flags;
-      a.mel5_sstart = fe->d_mel5_sstart; a.mel5_nslots = fe->mel5_nslots;
+      a.win_c = fe->win_c; a.mel5_w = fe->d_mel5_w; a.mel5_flags = fe->d_mel5_flags;
+      a.mel5_refs = fe->d_mel5_refs; a.mel5_nslots = fe->mel5_nslots; a.mel5_k = fe->mel5_k;
       rc = fe_frame5_launch(fe->N, pcm_dtype, a, st);
     } else if (four) {
       a.tw = fe->d_tw4;

@@ -180,3 +180,39 @@ def ref_gmm_initialize(g, X):
   if getattr(g, "_float32_mode", False):
     g._feat_const = float(g._feat_const)
   return g
+
+
+def load_scoring(root=DEFAULT_ROOT):
+  """Returns (scoring, plda): the reference's ``odin/ml/scoring.py`` and ``odin/ml/plda.py`` loaded by path.
+
+  Their two helpers from ``odin.backend`` are TensorFlow one-liners (maths.py:110-135) and TensorFlow is not
+  installed here; the shim supplies the same expressions in numpy / scipy -- ``cholesky(inv(X))`` (lower) and
+  ``x / sqrt(max(sum(x**2), eps))`` -- which is the only arithmetic in this loader that is not the reference's own
+  code.  ``Evaluable`` (reporting only) is an empty mixin."""
+  if "SC" in _STATE:
+    return _STATE["SC"], _STATE["PL"]
+  if not available(root):
+    raise RuntimeError("reference checkout not found at %s" % root)
+  load_gmm(root)   # brings in odin.utils and the odin.ml / odin.backend stubs
+  from scipy.linalg import cholesky, inv
+  from sklearn.base import BaseEstimator, TransformerMixin
+  be = sys.modules["odin.backend"]
+  be.calc_white_mat = lambda X: cholesky(inv(X), lower=True)
+
+  def length_norm(x, axis=-1, epsilon=1e-12, ord=2):
+    assert int(ord) == 2
+    return x / np.sqrt(np.maximum(np.sum(x ** 2, axis=axis, keepdims=True), epsilon))
+
+  be.length_norm = length_norm
+  sys.modules["odin.ml.base"].Evaluable = type("Evaluable", (object,), {})
+  sys.modules["odin.ml.base"].BaseEstimator = BaseEstimator
+  sys.modules["odin.ml.base"].TransformerMixin = TransformerMixin
+  mods = []
+  for name in ("scoring", "plda"):
+    spec = importlib.util.spec_from_file_location("odin.ml." + name, os.path.join(root, "odin", "ml", name + ".py"))
+    m = importlib.util.module_from_spec(spec)
+    sys.modules["odin.ml." + name] = m
+    spec.loader.exec_module(m)
+    mods.append(m)
+  _STATE["SC"], _STATE["PL"] = mods
+  return mods[0], mods[1]
