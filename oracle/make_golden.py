@@ -300,6 +300,48 @@ def tmat_fixtures():
   print("wrote tmat.npz")
 
 
+def _scoring_problem(seed=5, ncls=10, per=30, d=24):
+  """Synthetic i-vector-like vectors: class means + within-class noise, ragged class sizes."""
+  rng = np.random.RandomState(seed)
+  mu = rng.randn(ncls, d) * 1.5
+  y = np.concatenate([np.full(per + 3 * (c % 3), c) for c in range(ncls)])
+  X = mu[y] + rng.randn(len(y), d)
+  yt = np.repeat(np.arange(ncls), 7)
+  Xt = mu[yt] + rng.randn(len(yt), d)
+  return X, y, Xt, yt
+
+
+def scoring_fixtures():
+  """PLDA (plda.py:215-423) and Scorer / VectorNormalizer (scoring.py:95-364) of the REAL reference."""
+  SC, PL = ref_shim.load_scoring()
+  X, y, Xt, yt = _scoring_problem()
+  blob = dict(X=X, y=y, Xt=Xt, yt=yt)
+  p = PL.PLDA(n_phi=8, n_iter=12, centering=True, wccn=True, unit_length=True, random_state=1234)
+  p.fit(X, y)
+  blob.update(plda_scores=p.predict_log_proba(Xt), plda_Phi=p.Phi_, plda_Sigma=p.Sigma_, plda_Uk=p.Uk_,
+              plda_Lambda=p.Lambda_, plda_Qhat=p.Q_hat_, plda_Xmodel=p.X_model_, plda_proj=p.transform(Xt),
+              plda_llk=np.float64(p.compute_llk(p.normalizer.transform(X))))
+  # (n_iter='auto' evaluates compute_llk every iteration, whose Cholesky fails on the non-symmetric Sigma_ of the
+  #  first M-steps for every seed tried here: the reference raises LinAlgError; tests/test_scoring.py expects the same)
+  try:
+    PL.PLDA(n_phi=8, n_iter='auto', improve_threshold=1e-1, random_state=7).fit(X, y)
+    blob["plda_auto_raises"] = np.int64(0)
+  except np.linalg.LinAlgError:
+    blob["plda_auto_raises"] = np.int64(1)
+  pm = PL.PLDA(n_phi=8, random_state=3).fit_maximum_likelihood(X, y)
+  blob["plda_ml_scores"] = pm.predict_log_proba(Xt)
+  blob["plda_enroll_scores"] = p.predict_log_proba(Xt, X_model=SC.compute_class_avg(Xt, yt, np.unique(yt)))
+  for lda in (True, False):
+    s = SC.Scorer(centering=True, wccn=True, lda=lda, method='cosine').fit(X, y)
+    blob["cos_scores_lda%d" % lda] = s.transform(Xt)
+    blob["cos_enroll_lda%d" % lda] = s.normalizer.enroll_vecs
+  vn = SC.VectorNormalizer(centering=True, wccn=True, unit_length=True, lda=True, concat=True).fit(X, y)
+  blob["vn_concat"] = vn.transform(Xt)
+  blob["vn_W"], blob["vn_mean"], blob["vn_vmin"], blob["vn_vmax"] = vn.W, vn.mean, vn.vmin, vn.vmax
+  np.savez_compressed(os.path.join(OUT, "scoring.npz"), **blob)
+  print("wrote scoring.npz")
+
+
 if __name__ == "__main__":
   warnings.filterwarnings("ignore")
   os.makedirs(OUT, exist_ok=True)
@@ -311,7 +353,10 @@ if __name__ == "__main__":
     tmat_fixtures()
   elif len(sys.argv) > 1 and sys.argv[1] == "variants":
     variants_fixtures()
+  elif len(sys.argv) > 1 and sys.argv[1] == "scoring":
+    scoring_fixtures()
   else:
+    scoring_fixtures()
     variants_fixtures()
     tmat_fixtures()
     spectra_fixtures()
