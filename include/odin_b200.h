@@ -149,6 +149,10 @@ int odin_feat_rasta_sdc(const float* d_x, float* d_y, int32_t dim, const int64_t
                         int32_t rasta, int32_t sdc, void* stream);
 int odin_feat_energy(const float* d_frames, float* d_energy, int64_t n_frames, int32_t frame_len, int32_t take_log,
                      void* stream);
+/* AsType (base.py:616-665) on device buffers: n elements, dtype codes 0 float16, 1 float32, 2 float64 (one side must be
+ * float32; narrowing rounds to nearest even like ndarray.astype).  Lets float16 feature stores (the recipes'
+ * AsType('float16') tail, examples/fsdd_ivec.py:105) cross PCIe at their stored width in both directions. */
+int odin_feat_convert(const void* d_src, int32_t src_dtype, void* d_dst, int32_t dst_dtype, int64_t n, void* stream);
 /* signal.smooth(x, win, window='flat') of a 0/1 vector (signal.py:969-1000), float64 out; win >= 3, n >= win. */
 int odin_feat_smooth(const uint8_t* d_x, double* d_y, int64_t n, int32_t win, void* stream);
 

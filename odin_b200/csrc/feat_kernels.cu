@@ -6,6 +6,7 @@
 //   CalculateEnergy speech.py:623-649 -> signal.get_energy (signal.py:1421-1440)
 // All are HBM-bound copies / short recurrences; the arithmetic that the reference does in float64 (RASTA,
 // deltas, energy sums) is done in fp64 here and cast to float32 where the reference casts.
+#include <cuda_fp16.h>
 #include <algorithm>
 
 #include "common.cuh"
@@ -197,11 +198,65 @@ static int upload_offsets(const int64_t* h_off, int n_utt, int64_t** d_off, cuda
   return ODIN_OK;
 }
 
+// AsType (base.py:616-665) on the device: features stored as float16 (the recipes' AsType('float16') tail,
+// examples/fsdd_ivec.py:105) cross PCIe at their stored width and are widened here, and feature rows leaving for
+// a float16 store are narrowed (round to nearest even, like ndarray.astype) before the copy out.  HBM-bound:
+// 16 bytes per thread and trip on the wider side.
+template <typename S, typename D> __device__ __forceinline__ D cvt1(S v);
+template <> __device__ __forceinline__ float cvt1<__half, float>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float cvt1<double, float>(double v) { return (float)v; }
+template <> __device__ __forceinline__ __half cvt1<float, __half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ double cvt1<float, double>(float v) { return (double)v; }
+template <> __device__ __forceinline__ float cvt1<float, float>(float v) { return v; }
+
+template <typename S, typename D>
+__global__ void __launch_bounds__(256) feat_convert_kernel(const S* __restrict__ src, D* __restrict__ dst, int64_t n) {
+  constexpr int V = 4;
+  const int64_t nv = n / V;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(src) % (V * sizeof(S))) | (reinterpret_cast<uintptr_t>(dst) % (V * sizeof(D)))) == 0;
+  struct alignas(V * sizeof(S)) SV { S e[V]; };
+  struct alignas(V * sizeof(D)) DV { D e[V]; };
+  if (aligned) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+      const SV a = reinterpret_cast<const SV*>(src)[i];
+      DV b;
+#pragma unroll
+      for (int e = 0; e < V; ++e) b.e[e] = cvt1<S, D>(a.e[e]);
+      reinterpret_cast<DV*>(dst)[i] = b;
+    }
+    for (int64_t i = nv * V + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = cvt1<S, D>(src[i]);
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = cvt1<S, D>(src[i]);
+  }
+}
+
+template <typename S, typename D>
+static int feat_convert_launch(const void* src, void* dst, int64_t n, cudaStream_t st) {
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div<int64_t>(n, 4 * 256), (int64_t)sm_count() * 8);
+  feat_convert_kernel<S, D><<<grid, 256, 0, st>>>(reinterpret_cast<const S*>(src), reinterpret_cast<D*>(dst), n);
+  ODIN_LAUNCH_CHECK("feat_convert_kernel");
+  return ODIN_OK;
+}
+
 }  // namespace odin
 
 using namespace odin;
 
 extern "C" {
+
+int odin_feat_convert(const void* d_src, int32_t src_dtype, void* d_dst, int32_t dst_dtype, int64_t n, void* stream) {
+  if (!d_src || !d_dst || n < 0) return set_error(ODIN_EINVAL, "bad argument");
+  int rc = require_device();
+  if (rc) return rc;
+  if (n == 0) return ODIN_OK;
+  cudaStream_t st = as_stream(stream);
+  if (src_dtype == 0 && dst_dtype == 1) return feat_convert_launch<__half, float>(d_src, d_dst, n, st);
+  if (src_dtype == 2 && dst_dtype == 1) return feat_convert_launch<double, float>(d_src, d_dst, n, st);
+  if (src_dtype == 1 && dst_dtype == 0) return feat_convert_launch<float, __half>(d_src, d_dst, n, st);
+  if (src_dtype == 1 && dst_dtype == 2) return feat_convert_launch<float, double>(d_src, d_dst, n, st);
+  return set_error(ODIN_EINVAL, "odin_feat_convert: dtypes are 0 float16, 1 float32, 2 float64; one side must be float32");
+}
 
 int odin_feat_stack(const float* d_x, float* d_y, int32_t dim, const int64_t* h_frame_offsets, int32_t n_utt,
                     int32_t n_context, void* stream) {

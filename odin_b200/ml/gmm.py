@@ -49,7 +49,11 @@ def minibatch(n, batch_size):
 class _DeviceFrames(object):
   """Feeds [N, D] float32 frames to the kernels: a CUDA tensor is used in place,
   a host array is streamed through two pinned buffers on a copy stream so the
-  H2D copy of chunk i+1 overlaps the E-step of chunk i."""
+  H2D copy of chunk i+1 overlaps the E-step of chunk i.
+
+  float16 host data -- what the recipes store (AsType('float16'), examples/fsdd_ivec.py:105,197)
+  -- crosses PCIe at its stored width and is widened on the device (odin_feat_convert): half the bytes of the
+  host-side up-cast this class used to do, on a path that is PCIe / host-DRAM bound."""
 
   def __init__(self, X, chunk_frames=1 << 18):
     _lib.require_cuda()
@@ -60,7 +64,7 @@ class _DeviceFrames(object):
     self.host_pinned = None
     if isinstance(X, torch.Tensor):
       if not X.is_cuda:
-        if X.is_pinned() and X.dtype == torch.float32 and X.is_contiguous() and X.dim() == 2:
+        if X.is_pinned() and X.dtype in (torch.float32, torch.float16) and X.is_contiguous() and X.dim() == 2:
           self.host_pinned = X
         X = X.numpy()
       else:
@@ -130,9 +134,13 @@ class _DeviceFrames(object):
     if n == 0:
       return
     ch = min(self.chunk, n)
-    direct = self.host_pinned is not None  # pinned float32 tensor: DMA straight from the caller's buffer
-    pinned = None if direct else [torch.empty((ch, D), dtype=torch.float32).pin_memory() for _ in range(2)]
+    direct = self.host_pinned is not None  # pinned float32 / float16 tensor: DMA straight from the caller's buffer
+    half = np.dtype(self.host.dtype) == np.float16   # stored width on the wire, widened on the device
+    wire = torch.float16 if half else torch.float32
+    pinned = None if direct else [torch.empty((ch, D), dtype=wire).pin_memory() for _ in range(2)]
     dev = [torch.empty((ch, D), dtype=torch.float32, device="cuda") for _ in range(2)]
+    dev_wire = [torch.empty((ch, D), dtype=wire, device="cuda") for _ in range(2)] if half else dev
+    lib = _lib.load()
     copy_stream = torch.cuda.Stream()
     copied = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
@@ -152,7 +160,7 @@ class _DeviceFrames(object):
         src = pinned[b][:e - s]
       with torch.cuda.stream(copy_stream):
         copy_stream.wait_event(consumed[b])  # kernels of chunk i-2 are done with dev[b]
-        dev[b][:e - s].copy_(src, non_blocking=True)
+        dev_wire[b][:e - s].copy_(src, non_blocking=True)
         copied[b].record(copy_stream)
 
     for b in range(2):
@@ -164,6 +172,8 @@ class _DeviceFrames(object):
         stage(i + 1)
       b = i & 1
       torch.cuda.current_stream().wait_event(copied[b])
+      if half:
+        _lib.check(lib.odin_feat_convert(_lib.ptr(dev_wire[b]), 0, _lib.ptr(dev[b]), 1, (e - s) * D, _lib.current_stream()))
       yield dev[b][:e - s], s, e
       consumed[b].record()
 
@@ -172,7 +182,14 @@ class GMM(object):
   r"""Gaussian Mixture Model with diagonal covariance (see module docstring).
 
   Parameters follow gmm_tmat.py:341-346.  Extra keyword ``impl`` selects the
-  kernel family: 0 auto, 1 fp32 CUDA cores, 2 3xTF32 tcgen05.
+  kernel family: 0 auto, 1 fp32 CUDA cores, 2 3xTF32 tcgen05, 3 3xFP16 tcgen05.
+
+  Multi-GPU (one process per GPU under ``torch.distributed``): by default every rank is handed the SAME global
+  ``X`` / ``indices`` / ``sad`` -- exactly what a recipe written for the reference passes -- and takes its own
+  share of the utterances (``sharding.rank_frame_ranges``, the device-side form of ``_split_jobs``,
+  gmm_tmat.py:102-133); the packed statistics meet in one all-reduce per EM iteration and the M-step is
+  replicated.  ``local_shard=True`` says the caller already holds only this rank's frames (the front-end keeps
+  features on the GPU that extracted them).
   """
 
   STANDARD_CPU_BATCH_SIZE = 12 * 1024 * 1024  # gmm_tmat.py:338-339
@@ -183,7 +200,8 @@ class GMM(object):
                batch_size_cpu='auto', batch_size_gpu='auto',
                downsample=1, stochastic_downsample=True,
                device='gpu', ncpu=1, gpu_factor=80,
-               seed=1234, path=None, name=None, impl=0):
+               seed=1234, path=None, name=None, impl=0, local_shard=False):
+    self.local_shard = bool(local_shard)
     self._path = path if isinstance(path, str) else None
     nmix = int(nmix)
     if nmix < 1:
@@ -240,6 +258,7 @@ class GMM(object):
      self._dtype, self._path, self._name) = states
     self._stop_fitting = False
     self.impl = 0
+    self.local_shard = False
     self._feat_const = self._feat_dim * np.log(2 * np.pi)
     self._init_device_state()
 
@@ -419,6 +438,27 @@ class GMM(object):
       mask = sad if mask is None else (mask & sad)
     return mask
 
+  def _shard(self, X, sad, indices):
+    """Global (X, sad, indices) -> this rank's (X_local, ranges); `ranges` is None when nothing is cut (single
+    process, `local_shard`, or data that already lives on this rank's GPU)."""
+    td = _dist()
+    if td is None or self.local_shard or isinstance(X, _DeviceFrames):
+      return X, None
+    torch = _torch()
+    if isinstance(X, torch.Tensor) and X.is_cuda:
+      return X, None   # a CUDA tensor is this rank's own data by construction
+    ranges = sharding.rank_frame_ranges(X.shape[0], indices, td.get_rank(), td.get_world_size())
+    return sharding.take_ranges(X, ranges), ranges
+
+  def _local_mask(self, n_global, sad, indices, ranges):
+    """Selection mask over this rank's frames.  The selection itself (SAD, `indices`, down-sampling picks) is
+    made over the GLOBAL frame axis with the reference's seeded draws, so it does not depend on the number of
+    ranks; each rank then keeps the part that falls into its ranges."""
+    mask = self._selected_mask(n_global, sad, indices)
+    if mask is None or ranges is None:
+      return mask
+    return np.ascontiguousarray(sharding.take_ranges(mask, ranges))
+
   def _estep_device(self, frames, mask, second=True):
     """Runs the E-step kernels over `frames` (a _DeviceFrames); returns the packed
     fp64 statistics tensor on device, all-reduced over ranks."""
@@ -461,12 +501,14 @@ class GMM(object):
                   device=None, print_progress=True):
     """gmm_tmat.py:1043-1231 -> Z [1,M], F [D,M], S [D,M], L (mean log-likelihood)."""
     X, indices = self.initialize(X)
-    frames = X if isinstance(X, _DeviceFrames) else _DeviceFrames(X)
-    frames.reuse = frames.reuse or isinstance(X, _DeviceFrames)
+    n_global = X.shape[0]
     if sad is not None:
-      assert sad.shape[0] == frames.n, \
-          "Number of samples for X and sad mismatch X.shape=%s and sad.shape=%s" % ((frames.n, frames.dim), sad.shape)
-    mask = self._selected_mask(frames.n, sad, indices)
+      assert sad.shape[0] == n_global, \
+          "Number of samples for X and sad mismatch X.shape=%s and sad.shape=%s" % (tuple(X.shape), sad.shape)
+    Xl, ranges = self._shard(X, sad, indices)
+    frames = Xl if isinstance(Xl, _DeviceFrames) else _DeviceFrames(Xl)
+    frames.reuse = frames.reuse or isinstance(Xl, _DeviceFrames)
+    mask = self._local_mask(n_global, sad, indices, ranges)
     stats = self._estep_device(frames, mask, second).cpu().numpy()
     return self._unpack_stats(stats, zero, first, second, llk)
 
@@ -486,14 +528,24 @@ class GMM(object):
 
   def _maximization_device(self, stats, floor_const=None):
     lib = self._ensure_handle()
+    if floor_const is not None:
+      # gmm_tmat.py:1255-1257 floors the new variances at (sigma w^T) * floor_const BEFORE the negative-variance
+      # test (:1259-1272), so a positive floor prevents the rollback.  The M-step kernel computes
+      # sigma = S / (Z + EPS) - mu^2; flooring is the same as raising S to (floor + mu^2) (Z + EPS), which is done
+      # here on the packed statistics (O(D M) host work; not used by `fit`).
+      D, M = self._feat_dim, self._curr_nmix
+      st = stats.cpu().numpy().copy()
+      Z, F, S = st[:M].reshape(1, M), st[M:M + D * M].reshape(D, M), st[M + D * M:M + 2 * D * M].reshape(D, M)
+      iN = 1.0 / (Z + EPS)
+      mu = F * iN
+      sig = S * iN - mu * mu
+      vfloor = sig.dot((Z / Z.sum()).T) * floor_const
+      S[...] = np.maximum(sig, vfloor) / iN + mu * mu / iN
+      stats.copy_(_torch().from_numpy(st))
     _lib.check(lib.odin_gmm_mstep(self._handle, _lib.ptr(stats), 1 if self.allow_rollback else 0,
                                   _lib.ptr(self._d_mean), _lib.ptr(self._d_var), _lib.ptr(self._d_w),
                                   _lib.ptr(self._d_flag), _lib.current_stream()))
     self._download_params()
-    if floor_const is not None:  # gmm_tmat.py:1255-1257 (not used by fit)
-      vfloor = self.sigma.dot(self.w.T) * floor_const
-      self.sigma = self.sigma.clip(vfloor)
-      self._upload_params(force=True)
     if int(self._d_flag.item()) != 0 and self.exit_on_error:
       self._stop_fitting = True
     return self
@@ -501,10 +553,12 @@ class GMM(object):
   def expectation_maximization(self, X, sad=None, device=None, print_progress=True):
     """gmm_tmat.py:1278-1306."""
     X, indices = self.initialize(X)
-    frames = X if isinstance(X, _DeviceFrames) else _DeviceFrames(X)
-    frames.reuse = frames.reuse or isinstance(X, _DeviceFrames)
+    n_global = X.shape[0]
+    Xl, ranges = self._shard(X, sad, indices)
+    frames = Xl if isinstance(Xl, _DeviceFrames) else _DeviceFrames(Xl)
+    frames.reuse = frames.reuse or isinstance(Xl, _DeviceFrames)
     curr_nmix = self._curr_nmix
-    mask = self._selected_mask(frames.n, sad, indices)
+    mask = self._local_mask(n_global, sad, indices, ranges)
     stats = self._estep_device(frames, mask, True)
     tail = stats[-2:].cpu().numpy()
     L = float(tail[0] / tail[1]) if tail[1] > 0 else 0.0
@@ -561,10 +615,11 @@ class GMM(object):
         indices = list(indices.items())
       indices = sorted(indices, key=lambda x: x[1][0])
     self.initialize(data)
-    frames = _DeviceFrames(data)
+    n_global = data.shape[0]
+    local, ranges = self._shard(data, sad, indices)   # multi-GPU: this rank's utterances (gmm_tmat.py:102-133)
+    frames = _DeviceFrames(local)
     frames.cache_on_device()
     frames.reuse = True
-    arg = frames if indices is None else (frames, indices)
     niter = list(_NITER_SCHEDULE)
     niter[int(np.log2(self._nmix))] = self._niter
     self._stop_fitting = False
@@ -572,7 +627,7 @@ class GMM(object):
       curr_nmix = self._curr_nmix
       curr_niter = niter[int(np.log2(curr_nmix))] - len(self._llk_hist[curr_nmix])
       for _ in range(max(curr_niter, 0)):
-        self._em_frames(frames, sad, indices, print_progress)
+        self._em_frames(frames, sad, indices, print_progress, n_global, ranges)
         if self._stop_fitting:
           return self
       if curr_nmix < self._nmix:
@@ -581,9 +636,9 @@ class GMM(object):
         break
     return self
 
-  def _em_frames(self, frames, sad, indices, print_progress):
+  def _em_frames(self, frames, sad, indices, print_progress, n_global=None, ranges=None):
     curr_nmix = self._curr_nmix
-    mask = self._selected_mask(frames.n, sad, indices)
+    mask = self._local_mask(frames.n if n_global is None else n_global, sad, indices, ranges)
     stats = self._estep_device(frames, mask, True)
     tail = stats[-2:].cpu().numpy()
     L = float(tail[0] / tail[1]) if tail[1] > 0 else 0.0
@@ -668,63 +723,83 @@ class GMM(object):
     """gmm_tmat.py:769-913.  Z [n_utt, M] and Fhat [n_utt, M*D] are written as
     .npy files (the reference's bigarray.MmapArray container is a third-party
     format outside this path); returns the utterance names in processing order
-    (sorted by start, like the reference)."""
+    (sorted by start, like the reference).
+
+    Multi-GPU: the utterances are dealt to the ranks (`sharding.shard_utterances`), every rank writes the rows
+    of its own utterances into the shared files (rank 0 creates them) -- no collective on the data path
+    (SURVEY 8e); `local_shard=True` keeps everything on the calling rank."""
     if isinstance(indices, Mapping):
       indices = list(indices.items())
     indices = sorted(indices, key=lambda x: x[1][0])
     self.initialize(X)
     torch = _torch()
-    frames = _DeviceFrames(X)
-    resident = frames.cache_on_device()
     n_utt = len(indices)
-    D, M = self._feat_dim, self._nmix
-    for p in (pathZ, pathF):
-      if p is not None and os.path.exists(p) and override:
-        os.remove(p)
-    z_dat = np.lib.format.open_memmap(pathZ, mode='w+', dtype=np.dtype(dtype), shape=(n_utt, M)) \
-        if pathZ is not None else None
-    f_dat = np.lib.format.open_memmap(pathF, mode='w+', dtype=np.dtype(dtype), shape=(n_utt, M * D)) \
-        if pathF is not None else None
-    d_sad = None
+    td = None if self.local_shard else _dist()
+    rank = td.get_rank() if td is not None else 0
+    mine = list(range(n_utt)) if td is None else \
+        sharding.shard_utterances([int(e) - int(s) for _, (s, e) in indices], td.get_world_size())[rank]
+    frames = _DeviceFrames(X)
+    resident = frames.cache_on_device() if td is None else frames.resident is not None
+    D, M = self._feat_dim, self._curr_nmix   # (a partially fitted model emits _curr_nmix columns)
+    z_dat = f_dat = None
+    if rank == 0:
+      for p in (pathZ, pathF):
+        if p is not None and os.path.exists(p) and override:
+          os.remove(p)
+      if pathZ is not None:
+        z_dat = np.lib.format.open_memmap(pathZ, mode='w+', dtype=np.dtype(dtype), shape=(n_utt, M))
+      if pathF is not None:
+        f_dat = np.lib.format.open_memmap(pathF, mode='w+', dtype=np.dtype(dtype), shape=(n_utt, M * D))
+    if td is not None:
+      td.barrier()
+      if rank != 0:
+        z_dat = np.load(pathZ, mmap_mode='r+') if pathZ is not None else None
+        f_dat = np.load(pathF, mmap_mode='r+') if pathF is not None else None
+    d_sad_all = None
     if sad is not None:
       assert sad.shape[0] == frames.n
-      d_sad_all = torch.from_numpy((np.asarray(sad).reshape(-1) != 0).astype(np.uint8)).cuda()
-    names = []
-    Zs, Fs = [], []
-    for b0 in range(0, n_utt, utt_batch):
-      batch = indices[b0:b0 + utt_batch]
-      lo, hi = int(batch[0][1][0]), max(int(e) for _, (_, e) in batch)
+      sad = (np.asarray(sad).reshape(-1) != 0).astype(np.uint8)
       if resident:
-        dev = frames.resident[lo:hi]
+        d_sad_all = torch.from_numpy(sad).cuda()
+    Zs, Fs = [], []
+    for b0 in range(0, len(mine), utt_batch):
+      rows = mine[b0:b0 + utt_batch]
+      spans = [(int(indices[i][1][0]), int(indices[i][1][1])) for i in rows]
+      lens = np.array([e - s for s, e in spans], dtype=np.int64)
+      off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+      contiguous = all(spans[k][1] == spans[k + 1][0] for k in range(len(spans) - 1))
+      lo, hi = spans[0][0], spans[-1][1]
+      d_sad = None
+      if resident:   # one ragged batch per launch: the utterances of the batch back to back
+        dev = frames.resident[lo:hi] if contiguous else torch.cat([frames.resident[s:e] for s, e in spans], 0)
+        if sad is not None:
+          d_sad = d_sad_all[lo:hi] if contiguous else torch.cat([d_sad_all[s:e] for s, e in spans], 0)
       else:
-        dev = torch.from_numpy(np.ascontiguousarray(frames.host[lo:hi], dtype=np.float32)).cuda()
-      # utterances may leave gaps: build offsets per utterance pair (start,end) via a mask
-      starts = np.array([int(s) - lo for _, (s, _) in batch], dtype=np.int64)
-      ends = np.array([int(e) - lo for _, (_, e) in batch], dtype=np.int64)
-      contiguous = np.all(starts[1:] == ends[:-1])
-      if sad is not None:
-        d_sad = d_sad_all[lo:hi]
-      if contiguous:
-        off = np.concatenate([starts, ends[-1:]])
-        Z, Fh = self._utt_stats_device(dev, d_sad, off)
-      else:
-        zs, fs = zip(*[self._utt_stats_device(dev, d_sad, np.array([s, e], dtype=np.int64))
-                       for s, e in zip(starts, ends)])
-        Z, Fh = torch.cat(zs, 0), torch.cat(fs, 0)
+        host = frames.host[lo:hi] if contiguous else np.concatenate([frames.host[s:e] for s, e in spans], 0)
+        dev = torch.from_numpy(np.ascontiguousarray(host, dtype=np.float32)).cuda()
+        if sad is not None:
+          d_sad = torch.from_numpy(np.ascontiguousarray(
+              sad[lo:hi] if contiguous else np.concatenate([sad[s:e] for s, e in spans]))).cuda()
+      Z, Fh = self._utt_stats_device(dev, d_sad, off)
       Z, Fh = Z.cpu().numpy(), Fh.cpu().numpy()
       if z_dat is not None:
-        z_dat[b0:b0 + len(batch)] = Z
+        z_dat[rows] = Z
       if f_dat is not None:
-        f_dat[b0:b0 + len(batch)] = Fh
+        f_dat[rows] = Fh
       if z_dat is None and f_dat is None:
         Zs.append(Z)
         Fs.append(Fh)
-      names += [n for n, _ in batch]
     for d in (z_dat, f_dat):
       if d is not None:
         d.flush()
-    if isinstance(name_path, str):
+    if td is not None:
+      td.barrier()
+    names = [n for n, _ in indices]
+    if isinstance(name_path, str) and rank == 0:
       np.savetxt(fname=name_path, X=names, fmt='%s')
     if z_dat is None and f_dat is None:
-      self.last_utt_stats_ = (np.concatenate(Zs, 0), np.concatenate(Fs, 0))
+      Zl = np.concatenate(Zs, 0) if Zs else np.zeros((0, M), np.float32)
+      Fl = np.concatenate(Fs, 0) if Fs else np.zeros((0, M * D), np.float32)
+      self.last_utt_stats_ = (Zl, Fl) if td is None else \
+          (sharding.gather_rows(Zl, mine, n_utt), sharding.gather_rows(Fl, mine, n_utt))
     return names

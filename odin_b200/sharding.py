@@ -33,6 +33,40 @@ def shard_utterances(n_frames, world_size):
   return [sorted(ix) for ix in out]
 
 
+def rank_frame_ranges(n_frames_total, indices, rank, world_size):
+  """The frame ranges [(start, end), ...] (ascending) of a GLOBAL [N, D] feature matrix that rank `rank` owns.
+
+  This is the device-side stand-in for the reference's job fan-out (gmm_tmat.py:102-133 `_split_jobs`,
+  :1165-1220): with `indices` (name -> (start, end), or a list of such pairs) whole utterances are dealt to the
+  ranks longest-first (`shard_utterances`); without, the frames are cut into `world_size` contiguous
+  ranges.  Every frame belongs to exactly one rank, so summing the ranks' statistics gives the whole-set
+  statistics."""
+  rank, world_size = int(rank), int(world_size)
+  if indices is None:
+    n = int(n_frames_total)
+    return [((n * rank) // world_size, (n * (rank + 1)) // world_size)]
+  items = list(indices.items()) if hasattr(indices, "items") else list(indices)
+  spans = sorted(((int(s), int(e)) for _, (s, e) in items), key=lambda x: x[0])
+  mine = shard_utterances([e - s for s, e in spans], world_size)[rank]
+  out = []
+  for i in mine:   # ascending job order; merge neighbours
+    s, e = spans[i]
+    if out and out[-1][1] == s:
+      out[-1] = (out[-1][0], e)
+    elif e > s:
+      out.append((s, e))
+  return out
+
+
+def take_ranges(a, ranges):
+  """Rows of `a` (numpy array / memmap, or None) in the given frame ranges, concatenated."""
+  if a is None:
+    return None
+  if len(ranges) == 1:
+    return a[ranges[0][0]:ranges[0][1]]
+  return np.concatenate([a[s:e] for s, e in ranges], axis=0)
+
+
 def pack_stats(Z, F, S, L, n):
   """Z [1,M] | F [D,M] | S [D,M] | sum-LLK | nframes -> the packed fp64 vector the kernels use."""
   return np.concatenate([np.asarray(Z, np.float64).reshape(-1), np.asarray(F, np.float64).reshape(-1),

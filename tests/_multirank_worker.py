@@ -1,0 +1,67 @@
+"""Worker of tests/test_gpu_multirank.py: launched by torch.distributed.run with one rank per GPU (NCCL).
+
+Each rank first computes the whole-set answer alone on its own GPU (no process group yet), then joins the group
+and repeats the computation the way a recipe would under torchrun: every rank passes the SAME global arrays and
+GMM / Tmatrix take their share (sharding.rank_frame_ranges / shard_utterances).  Results go to
+<outdir>/rank<k>.npz for the parent test to compare."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main(outdir):
+  import torch
+  rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+  torch.cuda.set_device(local)
+  from odin_b200 import synth
+  from odin_b200.ml import GMM, Tmatrix
+  D, M = 60, 256
+  rng = np.random.RandomState(11)
+  lens = rng.randint(200, 3000, size=40)
+  off = np.concatenate([[0], np.cumsum(lens)])
+  X = synth.gmm_features(int(off[-1]), D, 16, seed=12)
+  sad = (rng.rand(int(off[-1])) > 0.2).astype(np.uint8)
+  indices = [("utt%03d" % i, (int(off[i]), int(off[i + 1]))) for i in range(len(lens))]
+  mean, sigma, w = synth.gmm_params(D, M, seed=13)
+
+  def model():
+    g = GMM(nmix=M, nmix_start=M, niter=2)
+    g.initialize(X)
+    g.mean, g.sigma, g.w = mean.copy(), sigma.copy(), w.copy()
+    return g
+
+  # ---- alone (no process group): whole-set statistics, two EM iterations, per-utterance statistics
+  g1 = model()
+  Z1, F1, S1, L1 = g1.expectation((X, indices), sad=sad)
+  g1.expectation_maximization((X, indices), sad=sad, print_progress=False)
+  g1.expectation_maximization((X, indices), sad=sad, print_progress=False)
+  g1.transform_to_disk(X, indices, sad=sad)
+  zu1, fu1 = g1.last_utt_stats_
+  t1 = Tmatrix(8, g1, niter=1)
+  t1.expectation_maximization(zu1.astype(np.float64), fu1.astype(np.float64))
+  T1 = t1.Tm
+  # ---- the same calls under NCCL
+  import torch.distributed as td
+  td.init_process_group("nccl", device_id=torch.device("cuda", local))
+  g2 = model()
+  Z2, F2, S2, L2 = g2.expectation((X, indices), sad=sad)
+  g2.expectation_maximization((X, indices), sad=sad, print_progress=False)
+  g2.expectation_maximization((X, indices), sad=sad, print_progress=False)
+  zp, fp = os.path.join(outdir, "Z.npy"), os.path.join(outdir, "F.npy")
+  names = g2.transform_to_disk(X, indices, sad=sad, pathZ=zp, pathF=fp)
+  zu2, fu2 = np.load(zp), np.load(fp)
+  t2 = Tmatrix(8, g2, niter=1)
+  t2.expectation_maximization(zu2.astype(np.float64), fu2.astype(np.float64))
+  np.savez(os.path.join(outdir, "rank%d.npz" % rank), Z1=Z1, F1=F1, S1=S1, L1=L1, Z2=Z2, F2=F2, S2=S2, L2=L2,
+           mean1=g1.mean, sigma1=g1.sigma, w1=g1.w, mean2=g2.mean, sigma2=g2.sigma, w2=g2.w,
+           zu1=zu1, fu1=fu1, zu2=zu2, fu2=fu2, T1=T1, T2=t2.Tm, names=np.array(names), world=world)
+  td.barrier()
+  td.destroy_process_group()
+
+
+if __name__ == "__main__":
+  main(sys.argv[1])

@@ -168,6 +168,16 @@ def test_applying_sad_compaction_and_processor():
     assert s == pos and e - s == o["mfcc"].shape[0]                      # job order
     assert np.array_equal(feats["mfcc"][s:e], o["mfcc"])
     pos = e
+  # the streaming on-disk store holds the same rows (appended batch by batch, never the whole corpus in memory)
+  import tempfile
+  with tempfile.TemporaryDirectory() as d:
+    disk, ind2 = pp.FeatureProcessor(jobs, path=d, extractor=pipe, batch_utts=5).run()
+    assert ind2 == indices and sorted(disk) == sorted(feats)
+    for k in feats:
+      assert isinstance(disk[k], np.memmap) and disk[k].dtype == feats[k].dtype
+      assert np.array_equal(np.load(os.path.join(d, k + ".npy")), feats[k])
+    rows = [l.strip().split(",") for l in open(os.path.join(d, "indices_mfcc.csv"))]
+    assert [(r[0], (int(r[1]), int(r[2]))) for r in rows] == list(indices["mfcc"].items())
 
 
 def test_device_tables_match_oracle():

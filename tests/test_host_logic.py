@@ -291,6 +291,22 @@ def test_audio_reader_file_input_is_normalised_like_soundfile(tmp_path):
   assert d["raw"].dtype == np.int16 and np.array_equal(d["raw"], x)          # arrays stay unscaled
 
 
+def test_streaming_npy_store(tmp_path):
+  """FeatureProcessor's store appends batches to <feat>.npy without knowing the final length (the header is patched on
+  close): np.load / mmap must read back exactly the appended rows, for every dtype / trailing shape it is used with."""
+  from odin_b200.preprocessing.processor import _NpyAppender
+  for dt, tail in ((np.float16, (60,)), (np.uint8, ()), (np.float64, (3, 2)), (np.float32, (80,))):
+    path = str(tmp_path / ("a_%s.npy" % np.dtype(dt).name))
+    ap = _NpyAppender(path, dt, tail)
+    blocks = [np.random.RandomState(i).rand(*((n,) + tail)).astype(dt) for i, n in enumerate((5, 0, 17, 1))]
+    for b in blocks:
+      ap.append(b)
+    ap.close()
+    a, m = np.load(path), np.load(path, mmap_mode='r')
+    assert a.dtype == dt and a.shape == (23,) + tail
+    assert np.array_equal(a, np.concatenate(blocks)) and np.array_equal(m, a)
+
+
 def test_plan_fusion_variants():
   """Planning is host logic: which extractor runs take the reader's DC removal / the pre-emphasis into their kernels."""
   from odin_b200 import preprocessing as pp

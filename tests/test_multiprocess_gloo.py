@@ -182,3 +182,32 @@ def test_two_ranks_tmatrix_estep_matches_single_process():
     assert np.allclose(stats, whole, rtol=1e-11, atol=1e-11)
   assert np.array_equal(got[0][2], got[1][2])                    # bit-identical replicated M-step
   assert got[0][3][1] == got[1][3][0] and got[1][3][1] == Z.shape[0]
+
+
+def test_rank_frame_ranges_partition_the_global_frame_axis():
+  """sharding.rank_frame_ranges is what GMM.fit / expectation use under torch.distributed to take a rank's share of a
+  GLOBAL (X, indices): every frame of every utterance belongs to exactly one rank, frames outside `indices` to none."""
+  rng = np.random.RandomState(4)
+  lens = rng.randint(1, 500, size=57)
+  gaps = rng.randint(0, 3, size=57)            # some utterances leave holes between them
+  starts = np.cumsum(np.concatenate([[5], lens[:-1] + gaps[:-1]]))
+  indices = {"u%d" % i: (int(s), int(s + n)) for i, (s, n) in enumerate(zip(starts, lens))}
+  n_total = int(starts[-1] + lens[-1] + 7)
+  covered = np.zeros(n_total, dtype=np.int32)
+  for s, e in indices.values():
+    covered[s:e] += 1
+  for world in (1, 2, 3, 8):
+    seen = np.zeros(n_total, dtype=np.int32)
+    for rank in range(world):
+      rr = sharding.rank_frame_ranges(n_total, indices, rank, world)
+      assert rr == sorted(rr) and all(e > s for s, e in rr)
+      for s, e in rr:
+        seen[s:e] += 1
+      x = np.arange(n_total)
+      assert np.array_equal(sharding.take_ranges(x, rr), np.concatenate([x[s:e] for s, e in rr]) if rr else x[:0]) or not rr
+    assert np.array_equal(seen, covered)
+    seen = np.zeros(n_total, dtype=np.int32)
+    for rank in range(world):
+      (s, e), = sharding.rank_frame_ranges(n_total, None, rank, world)
+      seen[s:e] += 1
+    assert np.all(seen == 1)
