@@ -7,7 +7,11 @@ Metric (BASELINE.json): 2048-mix UBM Baum-Welch frames/s (+ MFCC frames/s in the
 One step = one EM iteration of the 2048-mix diagonal UBM over this rank's
 resident shard of frames: zero the statistics, E-step kernels (log-sum-exp +
 N/F/S accumulation), ONE all-reduce of the packed fp64 statistics over ranks
-(NCCL, N > 1), M-step kernel.  Weak scaling: every rank holds `--frames` frames.
+(NCCL, N > 1), M-step kernel.  Weak scaling: every rank holds `--frames` frames
+(default 15 M = config 4's shard per GPU).  The MFCC leg runs config 3 at its
+real size: 100 h of 16 kHz audio, divided over the ranks (strong scaling); its
+figures are also promoted to top-level keys (`mfcc_value`, `mfcc_e2e`,
+`mfcc_frac`) so that they appear in every record of the driver.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
@@ -43,17 +47,37 @@ def parse():
   p.add_argument("--steps", type=int, default=20)
   p.add_argument("--warmup", type=int, default=3)
   p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-  p.add_argument("--frames", type=int, default=6_000_000, help="frames per GPU (60-dim fp32)")
+  p.add_argument("--frames", type=int, default=15_000_000, help="frames per GPU (60-dim fp32); config 4: 15 M")
   p.add_argument("--nmix", type=int, default=NMIX)
   p.add_argument("--kernel-impl", type=int, default=0, help="0 auto, 1 fp32 CUDA cores, 2 tcgen05 3xTF32, 3 tcgen05 3xFP16")
-  p.add_argument("--mfcc-hours", type=float, default=2.0, help="hours of 16 kHz audio per GPU for the MFCC leg")
+  p.add_argument("--mfcc-hours", type=float, default=100.0,
+                 help="hours of 16 kHz audio of the MFCC leg, TOTAL over all GPUs (config 3: 100 h)")
   p.add_argument("--no-mfcc", action="store_true")
-  p.add_argument("--mfcc-chunks", type=int, default=4, help="pipeline depth of the MFCC end-to-end call")
+  p.add_argument("--mfcc-chunks", type=int, default=0, help="chunks of the MFCC end-to-end call (0: one per ~1.5 h of audio)")
   p.add_argument("--no-tmat", action="store_true")
   p.add_argument("--tmat-files", type=int, default=3000, help="files per GPU in the T-matrix leg")
   p.add_argument("--no-cpu-baseline", action="store_true")
   p.add_argument("--cpu-sample", type=int, default=131072, help="frames in the CPU-baseline sample")
+  p.add_argument("--cpu-seconds", type=float, default=20.0, help="wall time of each MFCC CPU-baseline arm")
   return p.parse_args()
+
+
+def blas_threads(n=None):
+  """Pins the BLAS / OpenMP pools of THIS process to n threads (default: every core it may run on).
+  torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, which silently turned the CPU arm of the N >= 2
+  runs of round 1 into a single-threaded one (7.2 k instead of 32.6 k frames/s): the count is set explicitly here."""
+  n = len(os.sched_getaffinity(0)) if n is None else int(n)
+  try:
+    import threadpoolctl
+    threadpoolctl.threadpool_limits(limits=n)
+  except Exception:
+    pass
+  try:
+    import torch
+    torch.set_num_threads(n)
+  except Exception:
+    pass
+  return n
 
 
 # ---------------------------------------------------------------------------
@@ -170,7 +194,7 @@ def run_reference(args):
   n = min(args.cpu_sample, args.frames)
   X, mean, sigma, w = make_ubm_and_frames(torch, n, args.nmix, 7, "cpu")
   X = X.numpy()
-  cores = os.cpu_count()
+  cores = blas_threads()
   for _ in range(args.warmup):
     cpu_em_step(X[:8192], mean, sigma, w, args.nmix)
   t0 = time.perf_counter()
@@ -178,7 +202,8 @@ def run_reference(args):
     cpu_em_step(X, mean, sigma, w, args.nmix)
   dt = time.perf_counter() - t0
   val = n * args.steps / dt
-  sample = "%d frames x %d-mix x %d steps, numpy float32 (numpy-1 semantics), BLAS threads" % (n, args.nmix, args.steps)
+  sample = "%d frames x %d-mix x %d steps, numpy float32 (numpy-1 semantics), %d BLAS threads (set explicitly)" % (
+      n, args.nmix, args.steps, cores)
   line = {
       "impl": "reference", "metric": "ubm%d_baum_welch_frames_per_s" % args.nmix, "value": val, "unit": "frames/s",
       "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
@@ -190,12 +215,60 @@ def run_reference(args):
       "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
       "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
   }
+  if not args.no_mfcc:
+    try:
+      cpu = mfcc_cpu_baseline(args.cpu_seconds)
+      line["mfcc_value"] = line["mfcc_e2e"] = cpu["value"]
+      line["mfcc"] = {"metric": "mfcc_frames_per_s", "value": cpu["value"], "unit": "frames/s", "cpu_baseline": cpu}
+    except Exception as e:
+      line["mfcc"] = {"error": "%s: %s" % (type(e).__name__, e)}
   print(json.dumps(line))
 
 
 # ---------------------------------------------------------------------------
 # MFCC leg
 # ---------------------------------------------------------------------------
+MFCC_FLOP_PER_FRAME = 35.0e3   # FFT-1024 25.6 k + mel 2.05 k + DCT 3.36 k + rest 3.7 k
+MFCC_BYTES_PER_FRAME = 320 + 240 + 320 + 5  # PCM in, feat, log-mel, energy + sad
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # nominal: 148 SMs x 128 FP32 lanes x 2 x max SM clock
+
+
+def _mfcc_cpu_worker(args):
+  seed, seconds = args
+  blas_threads(1)
+  from odin_b200 import synth
+  from oracle import frontend as F
+  pool = synth.utterance_batch(24, 5.0, 60.0, sr=16000, seed=seed)
+  t0 = time.perf_counter()
+  nfr = 0
+  while True:
+    for u in pool:
+      r = F.extract(u, 16000, 0.025, 0.010, 1024, n_mels=80, fmin=64, fmax=8000, vad="gmm")
+      nfr += r["mfcc"].shape[0]
+      if time.perf_counter() - t0 > seconds:
+        return nfr, time.perf_counter() - t0
+
+
+def mfcc_cpu_baseline(seconds):
+  """The reference's front-end arithmetic (numpy port, oracle/frontend.py) on the host cores the way
+  FeatureProcessor runs it (processor.py:674-679): (a) one process, (b) ncpu = cores - 1 forked workers, one
+  utterance at a time each; the faster of the two is quoted."""
+  import multiprocessing as mp
+  cores = len(os.sched_getaffinity(0))
+  n1, t1 = _mfcc_cpu_worker((4000, seconds))
+  one = n1 / t1
+  many, nw = 0.0, max(1, cores - 1)
+  if nw > 1:
+    with mp.get_context("fork").Pool(nw) as pool:
+      res = pool.map(_mfcc_cpu_worker, [(4000 + i, seconds) for i in range(nw)])
+    many = sum(n for n, _ in res) / max(t for _, t in res)
+  best = max(one, many)
+  return {"value": best, "unit": "frames/s", "cores": 1 if one >= many else nw, "kind": "port",
+          "one_process": one, "mpi_workers": nw, "mpi_value": many,
+          "sample": "config-3 utterances (U[5,60] s) through oracle/frontend.py for %.0f s per arm: 1 process %.0f frames/s, "
+                    "%d forked workers %.0f frames/s" % (seconds, one, nw, many)}
+
+
 def mfcc_leg(torch, args, rank, world, dist, peaks, do_cpu):
   from odin_b200 import _lib, synth
   from odin_b200 import preprocessing as pp
@@ -206,12 +279,18 @@ def mfcc_leg(torch, args, rank, world, dist, peaks, do_cpu):
       pp.MFCCsExtractor(20, first_coef_energy=True), pp.DeltaExtractor("mfcc", order=(0, 1, 2)),
       pp.SADgmm(input_name="stft_energy")])
   fe = pipe.plan[0]
+  hours = args.mfcc_hours / world                                         # strong scaling: the corpus is divided
   pool = synth.utterance_batch(24, 5.0, 60.0, sr=sr, seed=4000 + rank)  # U[5,60] s utterances
-  pool_s = sum(len(u) for u in pool) / sr
-  reps = max(1, int(round(args.mfcc_hours * 3600.0 / pool_s)))
-  utts = [pool[i % len(pool)] for i in range(reps * len(pool))]
-  pcm_h, off = synth.pack_utterances(utts)
-  pcm_pinned = torch.from_numpy(pcm_h).pin_memory()
+  lens = np.array([len(u) for u in pool], dtype=np.int64)
+  reps = max(1, int(round(hours * 3600.0 * sr / lens.sum())))
+  n_utt = reps * len(pool)
+  off = np.zeros(n_utt + 1, dtype=np.int64)
+  np.cumsum(np.tile(lens, reps), out=off[1:])
+  pcm_pinned = torch.empty(int(off[-1]), dtype=torch.int16, pin_memory=True)   # the corpus in pinned host memory
+  one = np.concatenate(pool)
+  view = pcm_pinned.numpy()
+  for r in range(reps):
+    view[r * len(one):(r + 1) * len(one)] = one
   pcm = pcm_pinned.cuda()
   lib = _lib.load()
   h, _cfg = fe._handle(sr)
@@ -227,77 +306,88 @@ def mfcc_leg(torch, args, rank, world, dist, peaks, do_cpu):
   if dist is not None:
     dist.barrier()
   ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-  kms = np.zeros(4)
+  steps = max(3, min(args.steps, int(2.0e9 / max(T, 1)) + 1))   # ~2 G frames of timed work at most
+  l0 = lib.odin_launch_count()
   torch.cuda.synchronize()
   ev0.record()
-  for _ in range(args.steps):
+  for _ in range(steps):
     out = step()
     del out
   ev1.record()
   torch.cuda.synchronize()
   ms = ev0.elapsed_time(ev1)
-  # per-kernel share of the last step
+  launches = (lib.odin_launch_count() - l0) // steps
+  # per-kernel share of the last step (events recorded by the library on the launch stream)
   out = step()
   buf = (C.c_float * 4)()
   _lib.check(lib.odin_fe_last_run_ms(h, buf))
   kms = np.array(list(buf))
-  # e2e: pinned host PCM -> device, features + VAD back to pinned host memory, through the public host-buffer
-  # call (chunks of whole utterances pipelined over copy-in / kernel / copy-out streams)
-  t_e2e = []
   del out
-  host_out = None
-  for _ in range(4):
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    host_out = fe.run_host_packed(pcm_pinned, off, sr, want=("feat", "sad"), n_chunks=args.mfcc_chunks, out=host_out)
-    torch.cuda.synchronize()
-    t_e2e.append(time.perf_counter() - t0)
-  feat_h, sad_h = host_out["feat"], host_out["sad"]
+  torch.cuda.empty_cache()
+  # e2e: pinned host PCM -> device, features + VAD back to pinned host memory, through the public host-buffer
+  # call (chunks of whole utterances pipelined over copy-in / kernel / copy-out streams); float32 features, and
+  # the float16 store of the recipes' AsType('float16') tail (narrowed on the device)
+  n_chunks = args.mfcc_chunks if args.mfcc_chunks > 0 else max(4, int(round(hours / 1.5)))
+  e2e = {}
+  for tag, sd in (("f32", None), ("f16", "float16")):
+    host_out, ts = None, []
+    for _ in range(3):
+      torch.cuda.synchronize()
+      if dist is not None:
+        dist.barrier()
+      t0 = time.perf_counter()
+      host_out = fe.run_host_packed(pcm_pinned, off, sr, want=("feat", "sad"), n_chunks=n_chunks, out=host_out, store_dtype=sd)
+      torch.cuda.synchronize()
+      ts.append(time.perf_counter() - t0)
+    e2e[tag] = (min(ts[1:]), host_out["feat"].numel() * host_out["feat"].element_size() + host_out["sad"].numel())
+    del host_out
   h2d = pcm_pinned.numel() * 2
-  d2h = feat_h.numel() * 4 + sad_h.numel()
-  t = torch.tensor([ms / 1e3 / args.steps, min(t_e2e[1:])], dtype=torch.float64, device="cuda")
+  t = torch.tensor([ms / 1e3 / steps, e2e["f32"][0], e2e["f16"][0], float(T)], dtype=torch.float64, device="cuda")
   if dist is not None:
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-  step_s, e2e_s = float(t[0]), float(t[1])
-  total_T = T * world
-  bytes_per_frame = 320 + 240 + 320 + 5  # SURVEY.md 8d front-end cfg3: PCM in, feat, log-mel, energy+sad
-  frame_kernel_s = kms[1] / 1e3
+    tmax = t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    total_T = int(t[3])
+    t = tmax
+  else:
+    total_T = T
+  step_s, e2e_s, e2e16_s = float(t[0]), float(t[1]), float(t[2])
+  frame_s = kms[1] / 1e3
   res = {
-      "metric": "mfcc_frames_per_s", "value": total_T / step_s, "unit": "frames/s",
-      "ms_per_step": step_s * 1e3, "frames_per_gpu": T, "audio_hours_per_gpu": pcm_h.shape[0] / sr / 3600.0,
-      "config": {"workload": "config 3: 16 kHz, 25/10 ms, n_fft=1024, 80 mel + 20 MFCC + d/dd + SADgmm, U[5,60] s utterances",
-                 "n_utt_per_gpu": len(utts)},
+      "metric": "mfcc_frames_per_s", "value": total_T / step_s, "unit": "frames/s", "scaling": "strong",
+      "ms_per_step": step_s * 1e3, "steps": steps, "frames_per_gpu": T, "frames_total": total_T,
+      "audio_hours_total": args.mfcc_hours, "audio_hours_per_gpu": pcm_pinned.numel() / sr / 3600.0,
+      "config": {"workload": "config 3: %g h of 16 kHz audio over %d GPU(s), 25/10 ms, n_fft=1024, 80 mel + 20 MFCC + d/dd + SADgmm, "
+                             "U[5,60] s utterances; PCM (%.1f GB/GPU) exceeds L2" % (args.mfcc_hours, world, h2d / 1e9),
+                 "n_utt_per_gpu": n_utt},
       "kernel_ms": {"dc": float(kms[0]), "frame": float(kms[1]), "post": float(kms[2]), "vad": float(kms[3])},
-      "roofline": {"bound": "hbm", "achieved": bytes_per_frame * T / frame_kernel_s / 1e9, "peak": peaks["hbm_gbs"],
-                   "unit": "GB/s", "frac": bytes_per_frame * T / frame_kernel_s / 1e9 / peaks["hbm_gbs"],
-                   "traffic": 408.5e6 / 696132 * T, "kernel": "fe_frame4_kernel", "peak_source": peaks["source"],
-                   "note": "algorithmic 885 B/frame; traffic from profiles/r01_fe_ncu_s10_keymetrics.csv (223.2 MB read + 185.3 MB written per 696 132-frame launch: PCM in, unclipped log-mel + energies out; the utterance pass writes the rest); the kernel is issue / FP32 bound (SURVEY 8d), see roofline_fp32 and DESIGN.md"},
-      # the binding resource is the SM, not HBM: algorithmic 35 kFLOP per frame against the
-      # FP32 pipe peak 148 SM x 128 lanes x 2 x max SM clock
-      "roofline_fp32": {"bound": "fp32", "achieved": 35.0e3 * T / frame_kernel_s / 1e12,
-                        "peak": 148 * 128 * 2 * 1.965e9 / 1e12, "unit": "TFLOP/s",
-                        "frac": 35.0e3 * T / frame_kernel_s / (148 * 128 * 2 * 1.965e9),
-                        "kernel": "fe_frame4_kernel", "peak_source": "nominal: 148 SMs x 128 FP32 lanes x 2 x 1.965 GHz"},
-      # what actually binds the frame kernel: warp-instruction issue slots (4 per SM per cycle).  Not measurable
-      # without a profiler, so the figures of the committed capture are quoted, not re-measured per run.
-      "roofline_issue": {"bound": "issue", "frac": 0.591, "warp_instructions_per_frame": 1451, "kernel": "fe_frame4_kernel",
-                         "peak_source": "ncu smsp__issue_active / smsp__inst_executed of profiles/r01_fe_ncu_s10_keymetrics.csv "
-                                        "(same workload); utterance pass 0.62, SADgmm 0.31 (latency / barrier bound)"},
+      "gpu_launches": int(launches),
+      # the binding resource is the SM, not HBM (35 kFLOP over 885 B per frame): algorithmic FLOPs of
+      # the WHOLE step (all four kernels) over the FP32 pipe peak; the frame kernel alone as a sub-key
+      "roofline": {"bound": "fp32", "achieved": MFCC_FLOP_PER_FRAME * T / step_s / 1e12, "peak": FP32_PEAK_TFLOPS,
+                   "unit": "TFLOP/s", "frac": MFCC_FLOP_PER_FRAME * T / step_s / 1e12 / FP32_PEAK_TFLOPS,
+                   "peak_source": "nominal: 148 SMs x 128 FP32 lanes x 2 x 1.965 GHz (MEASURED_PEAKS.json has no fp32 figure)",
+                   "algorithmic_flops_per_frame": MFCC_FLOP_PER_FRAME,
+                   "frame_kernel": {"name": "fe_frame5_kernel", "ms": float(kms[1]),
+                                    "achieved": MFCC_FLOP_PER_FRAME * T / frame_s / 1e12,
+                                    "frac": MFCC_FLOP_PER_FRAME * T / frame_s / 1e12 / FP32_PEAK_TFLOPS},
+                   "hbm": {"achieved": MFCC_BYTES_PER_FRAME * T / step_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                           "frac": MFCC_BYTES_PER_FRAME * T / step_s / 1e9 / peaks["hbm_gbs"],
+                           "algorithmic_bytes_per_frame": MFCC_BYTES_PER_FRAME},
+                   # dram__bytes of the frame kernel from the committed capture (profiles/r02_fe_frame5_keymetrics.csv:
+                   # 224.0 MB read + 186.4 MB written per 696 132-frame launch = PCM in, log-mel + energy out), per frame
+                   "traffic": 410.4e6 / 696132 * T},
       "e2e": {"value": total_T / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d * world,
-              "d2h_bytes_per_step": d2h * world, "call": "FusedSpeechFrontEnd.run_host_packed (%d chunks)" % args.mfcc_chunks},
+              "d2h_bytes_per_step": e2e["f32"][1] * world,
+              "call": "FusedSpeechFrontEnd.run_host_packed (%d chunks), float32 features + sad to pinned host memory" % n_chunks},
+      "e2e_f16_store": {"value": total_T / e2e16_s, "unit": "frames/s", "h2d_bytes_per_step": h2d * world,
+                        "d2h_bytes_per_step": e2e["f16"][1] * world,
+                        "call": "the same with store_dtype='float16' (the recipes' AsType('float16') tail, narrowed on the device)"},
   }
+  del pcm, pcm_pinned
+  torch.cuda.empty_cache()
   if do_cpu:
-    from oracle import frontend as F
-    t0 = time.perf_counter()
-    nfr = 0
-    for u in pool:
-      r = F.extract(u, sr, 0.025, 0.010, 1024, n_mels=80, fmin=64, fmax=8000, vad="gmm")
-      nfr += r["mfcc"].shape[0]
-      if time.perf_counter() - t0 > 15.0:
-        break
-    dt = time.perf_counter() - t0
-    res["cpu_baseline"] = {"value": nfr / dt, "unit": "frames/s", "cores": 1, "kind": "port",
-                           "sample": "%d frames of the same utterance pool, oracle/frontend.py, 1 process" % nfr}
+    res["cpu_baseline"] = mfcc_cpu_baseline(args.cpu_seconds)
   return res
 
 
@@ -371,6 +461,7 @@ def tmat_leg(torch, args, rank, world, dist, do_cpu):
   }
   if do_cpu:
     from oracle import tmatrix as OT
+    cores = blas_threads()
     ns = min(n, 512)
     Zc, Fc = Z[:ns].cpu().numpy(), F[:ns].cpu().numpy()
     Sigma = OT.sigma_row(sigma)
@@ -383,7 +474,7 @@ def tmat_leg(torch, args, rank, world, dist, do_cpu):
       t0 = time.perf_counter()
       OT.maximization(LU, RU, nfr, Dm)
       t_m = min(t_m, time.perf_counter() - t0)
-    res["cpu_baseline"] = {"value": n / (t_e * n / ns + t_m), "unit": "files/s", "cores": os.cpu_count(), "kind": "port",
+    res["cpu_baseline"] = {"value": n / (t_e * n / ns + t_m), "unit": "files/s", "cores": cores, "kind": "port",
                            "sample": "oracle/tmatrix.py: E-step on %d files (%.2f s, scaled to %d files) + one M-step (%.2f s), "
                                      "numpy/scipy with BLAS threads" % (ns, t_e, n, t_m)}
   del Z, F, acc, t
@@ -461,25 +552,68 @@ def run_ours(args):
   n_timed = int(lib.odin_gmm_last_estep_frames(g._handle))   # frames covered by lse_ms / stats_ms (read before the
                                                              # end-to-end runs below issue their own E-steps)
 
+  # ---- N > 1: the all-reduced statistics against a one-GPU recomputation (untimed).  Every rank contributes a
+  # slice of its shard; rank 0 gathers the slices and recomputes the E-step on them alone.
+  multi_check = None
+  if dist is not None:
+    ns = min(N, 1 << 16)
+    reset_model()
+    part = _DeviceFrames(X[:ns].contiguous())
+    sharded = g._estep_device(part, None, True).clone()          # E-step on the slice + NCCL all-reduce
+    gathered = [torch.empty_like(part.resident) for _ in range(world)] if rank == 0 else None
+    dist.gather(part.resident, gathered, dst=0)
+    if rank == 0:
+      sharding_mod = __import__("odin_b200.sharding", fromlist=["x"])
+      keep = sharding_mod.allreduce_stats
+      sharding_mod.allreduce_stats = lambda st: st              # rank 0 alone: no collective
+      try:
+        alone = g._estep_device(_DeviceFrames(torch.cat(gathered, 0)), None, True).clone()
+      finally:
+        sharding_mod.allreduce_stats = keep
+      err = float((sharded - alone).abs().max() / alone.abs().max())
+      multi_check = {"what": "all-reduced packed N/F/S/llk of %d ranks x %d frames vs rank 0 alone on the gathered frames" % (world, ns),
+                     "max_rel_err": err, "ok": bool(err < 1e-5)}
+      assert multi_check["ok"], multi_check
+    del part
+    dist.barrier()
+    reset_model()
+
   # ---- e2e: public API, pinned host frames -> device every step, parameters read back ----
-  Xh = torch.empty((N, D), dtype=torch.float32).pin_memory()
+  g.local_shard = True     # every rank holds its own shard: nothing to cut
+  def timed_e2e(Xhost, calls=1):
+    times = []
+    for i in range(3):
+      reset_model()
+      torch.cuda.synchronize()
+      if dist is not None:
+        dist.barrier()
+      t0 = time.perf_counter()
+      if calls == 1:
+        g.expectation_maximization(Xhost, print_progress=False)   # H2D chunks overlap the kernels; mean/var/w D2H
+      else:   # the config-4 protocol: ONE upload, `calls` EM iterations on the resident frames, parameters read back
+        fr = _DeviceFrames(Xhost)
+        fr.cache_on_device()
+        fr.reuse = True
+        for _ in range(calls):
+          g.expectation_maximization(fr, print_progress=False)
+        del fr
+      torch.cuda.synchronize()
+      times.append((time.perf_counter() - t0) / calls)
+    return min(times[1:])
+
+  Xh = torch.empty((N, D), dtype=torch.float32, pin_memory=True)
   Xh.copy_(X)
-  reset_model()
-  e2e_times = []
-  for i in range(3):
-    torch.cuda.synchronize()
-    if dist is not None:
-      dist.barrier()
-    t0 = time.perf_counter()
-    g.expectation_maximization(Xh, print_progress=False)   # H2D chunks overlap the kernels; mean/var/w D2H
-    torch.cuda.synchronize()
-    e2e_times.append(time.perf_counter() - t0)
-  e2e_s = min(e2e_times[1:])
-  t = torch.tensor([ms / 1e3 / args.steps, e2e_s], dtype=torch.float64, device="cuda")
+  e2e_s = timed_e2e(Xh)
+  e2e_fit_s = timed_e2e(Xh, calls=10)
+  del Xh
+  Xh16 = torch.empty((N, D), dtype=torch.float16, pin_memory=True)   # the recipes' float16 store
+  Xh16.copy_(X)
+  e2e16_s = timed_e2e(Xh16)
+  del Xh16
+  t = torch.tensor([ms / 1e3 / args.steps, e2e_s, e2e_fit_s, e2e16_s], dtype=torch.float64, device="cuda")
   if dist is not None:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-  step_s, e2e_s = float(t[0]), float(t[1])
-  del Xh
+  step_s, e2e_s, e2e_fit_s, e2e16_s = (float(v) for v in t)
 
   total_frames = N * world
   value = total_frames / step_s
@@ -492,9 +626,14 @@ def run_ours(args):
   achieved = stats_useful / (stats_ms / 1e3) / 1e12
   names = {1: "gmm_stats_kernel (fp32 CUDA cores)", 2: "gmm_tc_stats_kernel (3xTF32 tcgen05)",
            3: "gmm_h_stats_kernel (3xFP16 tcgen05)"}
+  step_tflops = useful / step_s / 1e12
   roofline = {
-      "bound": "tensor", "achieved": achieved, "peak": kind_peak / 3.0, "unit": "TFLOP/s",
-      "frac": achieved / (kind_peak / 3.0),
+      # headline: useful FLOPs of the WHOLE EM iteration (both passes, M-step, all-reduce) over the split-precision
+      # ceiling of the MMA kind; the statistics kernel alone (the dominant kernel) under "stats_kernel"
+      "bound": "tensor", "achieved": step_tflops, "peak": kind_peak / 3.0, "unit": "TFLOP/s",
+      "frac": step_tflops / (kind_peak / 3.0),
+      "stats_kernel": {"achieved": achieved, "frac": achieved / (kind_peak / 3.0),
+                       "note": "timed on the last sub-batch of the step (%d of %d frames)" % (n_timed, N)},
       # DRAM bytes of one launch from the committed ncu capture (profiles/r01_gmm_f16x3_ncu_full_keymetrics.csv:
       # 1.043 GB read + 17.4 MB written for a 1 M-frame launch = the 1 KB/frame operand images), scaled to this launch
       "traffic": (1060.4 * n_timed) if impl_used == 3 else None,
@@ -503,7 +642,7 @@ def run_ours(args):
       "peak_source": "%s bf16_tflops_sustained%s / 3 (split precision)" % (
           peaks["source"], " (= fp16 dense)" if impl_used == 3 else " / 2 (TF32 dense)"),
       "algorithmic_flops_per_frame": (240 + 240) * M,
-      "step_useful_tflops": useful / step_s / 1e12,
+      "step_useful_tflops": step_tflops,
   }
   line = {
       "metric": "ubm%d_baum_welch_frames_per_s" % M, "value": value, "unit": "frames/s", "n_gpus": world,
@@ -518,7 +657,15 @@ def run_ours(args):
                                    "reused by every EM iteration" if impl_used == 3 else "n/a"},
       "roofline": roofline,
       "e2e": {"value": total_frames / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": N * D * 4 * world,
-              "d2h_bytes_per_step": ((2 * D + 1) * M * 4 + 16) * world},
+              "d2h_bytes_per_step": ((2 * D + 1) * M * 4 + 16) * world,
+              "call": "GMM.expectation_maximization(float32 pinned host frames): every iteration uploads its frames"},
+      # the same through a float16 host store (what the recipes keep: AsType('float16'); widened on the device)
+      "e2e_f16_store": {"value": total_frames / e2e16_s, "unit": "frames/s", "h2d_bytes_per_step": N * D * 2 * world,
+                        "d2h_bytes_per_step": ((2 * D + 1) * M * 4 + 16) * world},
+      # config 4's protocol: one upload, 10 EM iterations on the resident frames, parameters read back each iteration
+      "e2e_fit10": {"value": total_frames / e2e_fit_s, "unit": "frames/s", "h2d_bytes_per_step": N * D * 4 * world // 10,
+                    "d2h_bytes_per_step": ((2 * D + 1) * M * 4 + 16) * world},
+      "multi_gpu_check": multi_check,
       "gpu_launches": int(launches),
       "clocks": clocks,
   }
@@ -526,18 +673,22 @@ def run_ours(args):
   if do_cpu:
     n = min(args.cpu_sample, N)
     Xc = X[:n].cpu().numpy()
+    cores = blas_threads()
     cpu_em_step(Xc[:8192], mean, sigma, w, M)
     t0 = time.perf_counter()
     cpu_em_step(Xc, mean, sigma, w, M)
     dt = time.perf_counter() - t0
-    line["cpu_baseline"] = {"value": n / dt, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+    line["cpu_baseline"] = {"value": n / dt, "unit": "frames/s", "cores": cores, "kind": "port",
                             "sample": "%d frames of the same shard, one EM iteration, oracle/gmm.py in "
-                                      "float32 (numpy-1 semantics), BLAS threads" % n}
+                                      "float32 (numpy-1 semantics), %d BLAS threads" % (n, cores)}
   del X, X_frames
   torch.cuda.empty_cache()
   if not args.no_mfcc:
     try:
       line["mfcc"] = mfcc_leg(torch, args, rank, world, dist, peaks, do_cpu)
+      m = line["mfcc"]
+      line["mfcc_value"], line["mfcc_e2e"] = m["value"], m["e2e"]["value"]
+      line["mfcc_frac"], line["mfcc_ms_per_step"] = m["roofline"]["frac"], m["ms_per_step"]
     except Exception as e:  # the headline line must still be printed
       line["mfcc"] = {"error": "%s: %s" % (type(e).__name__, e)}
   if not args.no_tmat:

@@ -130,6 +130,33 @@ int odin_fe_run_spectra(odin_fe_t* fe, const void* d_pcm, int32_t pcm_dtype, con
                         int32_t n_utt, float* d_mspec, float* d_feat, float* d_energy, float* d_c0,
                         uint8_t* d_sad, double* d_sad_thr, float* d_spec, int32_t spec_log, void* stream);
 
+/* The chain one stage at a time (sig_kernels.cu) -- what `pp.signal.*` and the `_transform` of a single extractor call.
+ *   odin_fe_stft      signal.stft (signal.py:1442-1562) / STFTExtractor (speech.py:655-745): d_stft [T, n_fft/2+1] complex64
+ *                     (interleaved re, im), scaled by 1 / sum(window); d_energy [T] log frame energy or NULL.  DC removal,
+ *                     pre-emphasis and padding follow the handle, like odin_fe_run (use a handle with preemph = 0,
+ *                     remove_dc = 0 for the bare function).
+ *   odin_sig_preemph  signal.pre_emphasis (signal.py:955-967) over 1-D signals back to back (h_offsets [n_seg+1], HOST,
+ *                     starting at 0); rows2d != 0 selects the reference's 2-D form (first column s[:,0] * (1 - coeff)).
+ *   odin_sig_power    signal.power_spectrogram (signal.py:1623-1648): |S| ** power; is_complex: d_s holds n (re, im) pairs.
+ *   odin_fe_mels      signal.mels_spectrogram (signal.py:1650-1691) / MelsSpecExtractor (speech.py:766-802): d_spec
+ *                     [T, n_fft/2+1] power spectrum -> d_mspec [T, n_mels] through the handle's filterbank; log_db != 0
+ *                     applies power2db with the handle's top_db against the maximum of each utterance's matrix.
+ *   odin_fe_ceps      signal.ceps_spectrogram (signal.py:1693-1716) / MFCCsExtractor (speech.py:805-831): rows
+ *                     [first_row, first_row + n_rows) of the handle's DCT basis (n_ceps + 1 rows) applied to d_mspec.
+ *   odin_sig_delta    signal.delta (signal.py:1002-1066) along time for every utterance of a ragged [T, dim] batch:
+ *                     order 1 -> d_delta1, order 2 -> d_delta1 and d_delta2 (with the lfilter delay of SURVEY 8.1-Q1). */
+int odin_fe_stft(odin_fe_t* fe, const void* d_pcm, int32_t pcm_dtype, const int64_t* h_sample_offsets, int32_t n_utt,
+                 void* d_stft, float* d_energy, void* stream);
+int odin_sig_preemph(const float* d_x, float* d_y, const int64_t* h_offsets, int32_t n_seg, float coeff, int32_t rows2d,
+                     void* stream);
+int odin_sig_power(const float* d_s, int32_t is_complex, int32_t power, float* d_out, int64_t n, void* stream);
+int odin_fe_mels(odin_fe_t* fe, const float* d_spec, const int64_t* h_frame_offsets, int32_t n_utt, float* d_mspec,
+                 int32_t log_db, void* stream);
+int odin_fe_ceps(odin_fe_t* fe, const float* d_mspec, int64_t n_frames, int32_t first_row, int32_t n_rows, float* d_out,
+                 void* stream);
+int odin_sig_delta(const float* d_x, int32_t dim, const int64_t* h_frame_offsets, int32_t n_utt, int32_t width, int32_t order,
+                   float* d_delta1, float* d_delta2, void* stream);
+
 /* Framing (speech.py:569-620) [+ CalculateEnergy, speech.py:623-649]: d_frames [T, frame_len] = window * signal
  * (float32; the reference keeps float64), d_energy [T] = log sum (windowed frame)^2; either may be NULL.  DC removal,
  * pre-emphasis and padding follow the handle's configuration, like odin_fe_run. */

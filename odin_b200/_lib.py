@@ -67,6 +67,12 @@ SIGNATURES = {
     "odin_feat_energy": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp]),
     "odin_feat_smooth": (C.c_int, [_vp, _vp, _i64, _i32, _vp]),
     "odin_feat_convert": (C.c_int, [_vp, _i32, _vp, _i32, _i64, _vp]),
+    "odin_fe_stft": (C.c_int, [_vp, _vp, _i32, _pi64, _i32, _vp, _vp, _vp]),
+    "odin_sig_preemph": (C.c_int, [_vp, _vp, _pi64, _i32, C.c_float, _i32, _vp]),
+    "odin_sig_power": (C.c_int, [_vp, _i32, _i32, _vp, _i64, _vp]),
+    "odin_fe_mels": (C.c_int, [_vp, _vp, _pi64, _i32, _vp, _i32, _vp]),
+    "odin_fe_ceps": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "odin_sig_delta": (C.c_int, [_vp, _i32, _pi64, _i32, _i32, _i32, _vp, _vp, _vp]),
     "odin_vad_gmm": (C.c_int, [_vp, _pi64, _i32, _i32, _i32, _i32, C.c_float, _vp, _vp, _vp]),
     "odin_vad_threshold": (C.c_int, [_vp, _pi64, _i32, C.c_float, C.c_float, _i32, C.c_float, _i32, _vp, _vp, _vp]),
     "odin_fe_compact": (C.c_int, [_vp, _vp, _pi64, _i32, _vp, _i32, _i32, _vp, _vp, _vp]),

@@ -374,7 +374,7 @@ void odin_fe_destroy(odin_fe_t* fe) {
   cudaFree(fe->d_win32); cudaFree(fe->d_win64); cudaFree(fe->d_tw); cudaFree(fe->d_tw4); cudaFree(fe->d_mel_start);
   cudaFree(fe->d_mel_cnt); cudaFree(fe->d_mel_off); cudaFree(fe->d_mel_w); cudaFree(fe->d_dct);
   cudaFree(fe->d_mel_tab); cudaFree(fe->d_mel_ps);
-  cudaFree(fe->d_mel5_w); cudaFree(fe->d_mel5_flags); cudaFree(fe->d_mel5_refs);
+  cudaFree(fe->d_dct64); cudaFree(fe->d_mel5_w); cudaFree(fe->d_mel5_flags); cudaFree(fe->d_mel5_refs);
   cudaFree(fe->d_taps); cudaFree(fe->d_sample_off); cudaFree(fe->d_dcsum); cudaFree(fe->d_umax);
   cudaFree(fe->d_cnt); cudaFree(fe->d_vad_scratch);
   if (fe->h_stage) cudaFreeHost(fe->h_stage);
@@ -502,6 +502,25 @@ int odin_fe_run_spectra(odin_fe_t* fe, const void* d_pcm, int32_t pcm_dtype, con
   if (rc) return rc;
   return fe_launch(fe, d_pcm, pcm_dtype, n_utt, T, nt1, nt2, d_mspec, d_feat, d_energy, d_c0, d_sad, d_sad_thr, d_spec,
                    spec_log, st);
+}
+
+int odin_fe_stft(odin_fe_t* fe, const void* d_pcm, int32_t pcm_dtype, const int64_t* h_sample_offsets, int32_t n_utt,
+                 void* d_stft, float* d_energy, void* stream) {
+  if (!fe || !d_pcm || !h_sample_offsets || n_utt < 0 || !d_stft) return set_error(ODIN_EINVAL, "bad argument");
+  if (pcm_dtype != 0 && pcm_dtype != 1) return set_error(ODIN_EINVAL, "pcm_dtype must be 0 (int16) or 1 (float32)");
+  if (n_utt == 0) return ODIN_OK;
+  cudaStream_t st = as_stream(stream);
+  int64_t T = 0, nt1 = 0, nt2 = 0;
+  int rc = fe_prepare(fe, h_sample_offsets, n_utt, st, &T, &nt1, &nt2);
+  if (rc) return rc;
+  if (T == 0) return ODIN_OK;
+  // the frame kernels always project onto the handle's filterbank: give them a scratch for the rows nobody asked for
+  float* d_mspec = nullptr;
+  ODIN_CUDA_CHECK(cudaMallocAsync(&d_mspec, sizeof(float) * (size_t)T * fe->n_mels, st));
+  rc = fe_launch(fe, d_pcm, pcm_dtype, n_utt, T, nt1, nt2, d_mspec, nullptr, d_energy, nullptr, nullptr, nullptr, nullptr, 0, st,
+                 reinterpret_cast<float2*>(d_stft));
+  cudaFreeAsync(d_mspec, st);
+  return rc;
 }
 
 int odin_fe_frames(odin_fe_t* fe, const void* d_pcm, int32_t pcm_dtype, const int64_t* h_sample_offsets, int32_t n_utt,

@@ -24,6 +24,7 @@ struct odin_fe {
   int* d_mel_off = nullptr;    // [n_mels] offset into d_mel_w
   float* d_mel_w = nullptr;    // [nnz]
   float* d_dct = nullptr;      // [n_c1, n_mels]
+  double* d_dct64 = nullptr;   // the same in fp64, uploaded on first use by odin_fe_ceps (sig_kernels.cu)
   float* d_taps = nullptr;     // [delta_width]
   int mel_nnz = 0;
   // lane-balanced form of the same filterbank for fe_frame4_kernel (see capi.cu: fe_build_tables)
@@ -68,7 +69,7 @@ int fe_build_tables(odin_fe* fe);           // host fp64 -> device
 int fe_reserve(odin_fe* fe, int n_utt);
 int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t total_frames,
               int64_t n_tiles, int64_t n_tiles2, float* d_mspec, float* d_feat, float* d_energy, float* d_c0,
-              uint8_t* d_sad, double* d_sad_thr, float* d_spec, int spec_log, cudaStream_t st);
+              uint8_t* d_sad, double* d_sad_thr, float* d_spec, int spec_log, cudaStream_t st, float2* d_cspec = nullptr);
 int fe_frames_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t total_frames, int64_t n_tiles,
                      float* d_frames, float* d_energy, cudaStream_t st);
 int fe_vad_standalone(int kind, const float* d_x, const int64_t* h_fo, int n_utt, int nmix, int iters, int smooth,

@@ -42,6 +42,8 @@ struct FrameArgs {
   float* spec;    // [T, N/2+1] nullable: power spectrum (SpectraExtractor, signal.py:1718-1832), dB when spec_log
   int spec_log;
   int* umax_spec; // [n_utt] ordered-int max of the dB spectrum
+  float2* cspec;  // [T, N/2+1] nullable: the complex STFT itself (signal.stft, signal.py:1442-1562), scaled by 1 / sum(w)
+  float scale1;   // 1 / sum(w)
   // fe_frame5_kernel (fe_frame5.cu): 1/2 * 1/sum(w) (folded into the fp32 samples), lane-chunk form of the filterbank
   float win_c;
   const float2* mel5_w;      // [N/64][32] {falling-side weight, rising-side weight} of bin (N/64) * lane + j

@@ -302,11 +302,22 @@ __global__ void __launch_bounds__(FE_THREADS) fe_frame_kernel(FrameArgs a) {
         const T br = z1.y + z2.y, bi = z2.x - z1.x;
         pa[i] = (ar * ar + ai * ai) * q;
         pb[i] = (br * br + bi * bi) * q;
+        if (a.cspec != nullptr) {   // signal.stft: the complex spectra themselves
+          const float hs = 0.5f * a.scale1;
+          float2* cA = a.cspec + (fbase + t0 + fA) * (N / 2 + 1);
+          cA[k] = make_float2((float)ar * hs, (float)ai * hs);
+          if (hasB) cA[(N / 2 + 1) + k] = make_float2((float)br * hs, (float)bi * hs);
+        }
       }
       {
         const C2<T> zn = buf[padi(N / 2)];
         pa[NK] = (zn.x * zn.x) * (T)a.scale2;
         pb[NK] = (zn.y * zn.y) * (T)a.scale2;
+        if (a.cspec != nullptr && lane == 0) {
+          float2* cA = a.cspec + (fbase + t0 + fA) * (N / 2 + 1);
+          cA[N / 2] = make_float2((float)zn.x * a.scale1, 0.f);
+          if (hasB) cA[(N / 2 + 1) + N / 2] = make_float2((float)zn.y * a.scale1, 0.f);
+        }
       }
       if (a.spec != nullptr) {   // SpectraExtractor: the power spectrum itself is an output
         constexpr int NBIN = N / 2 + 1;
@@ -522,11 +533,22 @@ __global__ void __launch_bounds__(FE_THREADS, 2) fe_frame4_kernel(FrameArgs a) {
           const T br = z1.y + z2.y, bi = z2.x - z1.x;
           pa[i] = (ar * ar + ai * ai) * q;
           pb[i] = (br * br + bi * bi) * q;
+          if (a.cspec != nullptr) {   // signal.stft: the complex spectra themselves
+            const float hs = 0.5f * a.scale1;
+            float2* cA = a.cspec + (fbase + t0 + fA) * (N / 2 + 1);
+            cA[k] = make_float2(ar * hs, ai * hs);
+            if (hasB) cA[(N / 2 + 1) + k] = make_float2(br * hs, bi * hs);
+          }
         }
         {
           const C2<T> zn = buf[N / 2];
           pa[NK] = (zn.x * zn.x) * (T)a.scale2;
           pb[NK] = (zn.y * zn.y) * (T)a.scale2;
+          if (a.cspec != nullptr && lane == 0) {
+            float2* cA = a.cspec + (fbase + t0 + fA) * (N / 2 + 1);
+            cA[N / 2] = make_float2(zn.x * a.scale1, 0.f);
+            if (hasB) cA[(N / 2 + 1) + N / 2] = make_float2(zn.y * a.scale1, 0.f);
+          }
         }
         if (a.spec != nullptr) {   // SpectraExtractor: the power spectrum itself is an output
           constexpr int NBIN = N / 2 + 1;
@@ -1608,7 +1630,7 @@ int fe_vad_standalone(int kind, const float* d_x, const int64_t* h_fo, int n_utt
 
 int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t total_frames, int64_t n_tiles,
               int64_t n_tiles2, float* d_mspec, float* d_feat, float* d_energy, float* d_c0, uint8_t* d_sad,
-              double* d_sad_thr, float* d_spec, int spec_log, cudaStream_t st) {
+              double* d_sad_thr, float* d_spec, int spec_log, cudaStream_t st, float2* d_cspec) {
   const odin_fe_config& c = fe->cfg;
   if (total_frames <= 0) return ODIN_OK;
   if (fe->ev[0] == nullptr) {
@@ -1645,6 +1667,7 @@ int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t 
     a.mel_w = fe->d_mel_w; a.n_mels = fe->n_mels; a.scale2 = fe->scale2; a.mspec = d_mspec;
     a.energy = d_energy; a.umax = fe->d_umax;
     a.pad = fe->pad; a.spec = d_spec; a.spec_log = spec_log; a.umax_spec = fe->d_umax + fe->cap_utt + 1;
+    a.cspec = d_cspec; a.scale1 = sqrtf(fe->scale2);
     a.mel_nnz = fe->mel_nnz;
     a.mel_tab = fe->d_mel_tab; a.mel_ps = fe->d_mel_ps; a.mel_trips = fe->mel_trips; a.mel_chunks = fe->mel_chunks;
     // four-step FFT kernel up to n_fft = 1024; the Stockham kernel keeps n_fft = 2048
@@ -1656,7 +1679,7 @@ int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t 
     // packed-f32x2 kernel (fe_frame5.cu) whenever the filterbank has the plain triangular structure and the
     // power spectrum itself is not an output (ODIN_FE_FRAME4=1 keeps the scalar four-step kernel, for A/B runs)
     const char* keep4 = getenv("ODIN_FE_FRAME4");
-    const bool five = four && fe->mel5_ok && d_spec == nullptr && !(keep4 && keep4[0] == '1');
+    const bool five = four && fe->mel5_ok && d_spec == nullptr && d_cspec == nullptr && !(keep4 && keep4[0] == '1');
     int rc;
     if (five) {
       a.tw = fe->d_tw4;

@@ -412,7 +412,11 @@ class GMM(object):
 
   # ---------------------------------------------------------------- E-step
   def _selected_mask(self, n, sad, indices):
-    """Frame selection of gmm_tmat.py:135-232 as a uint8 mask (None = all)."""
+    """Frame selection of gmm_tmat.py:135-232 as a uint8 mask (None = all).  With `downsample > 1` the picks are
+    those of the reference's default single-job fan-out (ncpu=1; gmm_tmat.py:102-133 splits the frame axis into
+    `ncpu` jobs that each re-seed and shuffle their own batches, so its picks depend on `ncpu`): batches of
+    int(batch_size_cpu / floor(2 ** (curr_nmix / 1024))) frames -- or whole files with `indices` -- shuffled with
+    `random.seed(seed + curr_nmix + curr_niter)`, the first always kept, the others with probability 1 / downsample."""
     mask = None
     if indices is not None:
       mask = np.zeros(n, dtype=np.uint8)
@@ -426,7 +430,9 @@ class GMM(object):
         reduction = np.floor(np.power(2, self._curr_nmix / 1024))
         units = minibatch(n, int(self.batch_size_cpu / reduction))
       else:
-        units = [(int(s), int(e)) for _, (s, e) in indices]
+        # the reference hands its (single) job the files popped from the END of the list (gmm_tmat.py:1171-1181),
+        # i.e. in reverse order, and shuffles that list (gmm_tmat.py:185)
+        units = [(int(s), int(e)) for _, (s, e) in indices][::-1]
       random.shuffle(units)
       keep = np.zeros(n, dtype=np.uint8)
       for i, (s, e) in enumerate(units):

@@ -197,9 +197,8 @@ class Converter(Extractor):
 
 
 class DeltaExtractor(Extractor):
-  """base.py:433-484.  Arithmetic runs inside the fused front-end (it must sit
-  directly after MFCCsExtractor on the MFCC feature); a stand-alone instance has
-  no CUDA path in this version and raises."""
+  """base.py:433-484.  Directly behind MFCCsExtractor the deltas are computed inside the fused front-end;
+  anywhere else (any feature, any position) `_transform` runs signal.delta on the device (odin_sig_delta)."""
 
   def __init__(self, input_name, output_name=None, width=9, order=(0, 1), axis=0):
     super(DeltaExtractor, self).__init__(input_name=as_tuple(input_name, t=str), output_name=output_name)
@@ -210,9 +209,17 @@ class DeltaExtractor(Extractor):
     self.order = as_tuple(order, t=int)
     self.axis = axis
 
+  def _calc_deltas(self, X):   # base.py:470-481
+    from . import signal
+    import numpy as np
+    X = np.asarray(X)
+    top = max(self.order)
+    deltas = signal.delta(data=X, width=self.width, order=top, axis=self.axis) if top >= 1 else ()
+    deltas = (X,) + (tuple(deltas) if isinstance(deltas, (tuple, list)) else (deltas,))
+    return np.concatenate([d for i, d in enumerate(deltas) if i in self.order], axis=-1)
+
   def _transform(self, feat):
-    raise NotImplementedError(
-        "DeltaExtractor only runs fused behind MFCCsExtractor (make_pipeline); no CPU fallback")
+    return [self._calc_deltas(feat[name]) for name in self.input_name]
 
 
 class AsType(Extractor):

@@ -143,7 +143,12 @@ class PreEmphasis(Extractor):
     self.coeff = float(coeff)
 
   def _transform(self, X):
-    _no_cpu(self)
+    """Stand-alone use (outside a fusable run): signal.pre_emphasis on the device (speech.py:555-561)."""
+    from . import signal
+    raw = np.asarray(X[self.input_name])
+    if not 0 < raw.ndim <= 2:
+      raise ValueError("Only supper 1 or 2 channel audio but given shape: %s" % str(raw.shape))
+    return {self.output_name: signal.pre_emphasis(raw, coeff=self.coeff)}
 
 
 class STFTExtractor(Extractor):
@@ -165,7 +170,18 @@ class STFTExtractor(Extractor):
     self.scale = scale
 
   def _transform(self, X):
-    _no_cpu(self)
+    """Stand-alone use: signal.stft on the device (speech.py:715-745) -> complex64 `stft` (+ `stft_energy`)."""
+    from . import signal
+    y, sr = [X[name] for name in self.input_name]
+    scale = X[self.scale] if isinstance(self.scale, str) else self.scale
+    if self.frame_length is None:
+      raise NotImplementedError("framed input (frame_length=None) is not accelerated: run Framing inside the chain")
+    frame_length, step_length = _extract_frame_step_length(sr, self.frame_length, self.step_length)
+    res = signal.stft(y, frame_length=frame_length, step_length=step_length, n_fft=self.n_fft, window=self.window,
+                      scale=scale, padding=self.padding, energy=self.energy)
+    if self.energy:
+      return {self.output_name: res[0], '%s_energy' % self.output_name: res[1]}
+    return {self.output_name: res}
 
 
 class PowerSpecExtractor(Extractor):
@@ -176,7 +192,8 @@ class PowerSpecExtractor(Extractor):
     self.power = float(power)
 
   def _transform(self, X):
-    _no_cpu(self)
+    from . import signal
+    return signal.power_spectrogram(S=X[self.input_name], power=self.power)   # speech.py:762-763
 
 
 class MelsSpecExtractor(Extractor):
@@ -193,7 +210,9 @@ class MelsSpecExtractor(Extractor):
     self.top_db = top_db
 
   def _transform(self, X):
-    _no_cpu(self)
+    from . import signal
+    return signal.mels_spectrogram(spec=X[self.input_name[0]], sr=X[self.input_name[1]], n_mels=self.n_mels,
+                                   fmin=self.fmin, fmax=self.fmax, top_db=self.top_db)   # speech.py:796-802
 
 
 class MFCCsExtractor(Extractor):
@@ -207,7 +226,13 @@ class MFCCsExtractor(Extractor):
     self.first_coef_energy = bool(first_coef_energy)
 
   def _transform(self, X):
-    _no_cpu(self)
+    from . import signal
+    n_ceps = self.n_ceps + (1 if self.remove_first_coef else 0)   # speech.py:821-831
+    mfcc = signal.ceps_spectrogram(mspec=X[self.input_name], n_ceps=n_ceps, remove_first_coef=False)
+    ret = {self.output_name: mfcc[:, 1:] if self.remove_first_coef else mfcc}
+    if self.first_coef_energy:
+      ret['%s_energy' % self.output_name] = mfcc[:, 0]
+    return ret
 
 
 class SADthreshold(Extractor):
@@ -306,7 +331,31 @@ class ApplyingSAD(Extractor):
     self.keep_unvoiced = bool(keep_unvoiced)
 
   def _transform(self, X):
-    _no_cpu(self)
+    """Stand-alone use (speech.py:1732-1756): rows of every input feature where `sad` is set, compacted on the
+    device (odin_fe_compact); None -- the file is dropped -- when no frame is voiced and not `keep_unvoiced`."""
+    import torch
+    from . import signal
+    sad = np.asarray(X[self.sad_name]).reshape(-1)
+    if not np.any(sad) and not self.keep_unvoiced:
+      return None
+    lib = _lib.load()
+    h = signal._fe_handle(16000, 400, 160, 512)
+    d_sad = torch.from_numpy(np.ascontiguousarray(sad != 0, dtype=np.uint8)).cuda()
+    fo = np.array([0, sad.shape[0]], dtype=np.int64)
+    out = []
+    for name in self.input_name:
+      x = np.asarray(X[name])
+      assert len(sad) == max(x.shape), \
+          "Feature with name: %s, length of sad labels is: %d, but number of sample is: %s" % (name, len(sad), max(x.shape))
+      x2 = x.reshape(x.shape[0], -1)
+      d_x = torch.from_numpy(np.ascontiguousarray(x2, dtype=np.float32)).cuda()
+      d_y = torch.empty_like(d_x)
+      d_off = torch.empty(2, dtype=torch.int64, device='cuda')
+      _lib.check(lib.odin_fe_compact(h, _lib.ptr(d_sad), _lib.as_i64_ptr(fo), 1, _lib.ptr(d_x), int(d_x.shape[1]),
+                                     1 if self.keep_unvoiced else 0, _lib.ptr(d_y), _lib.ptr(d_off), _lib.current_stream()))
+      n = int(d_off[1].item())
+      out.append(d_y[:n].cpu().numpy().reshape((n,) + x.shape[1:]).astype(x.dtype, copy=False))
+    return out
 
 
 # ---------------------------------------------------------------------------
@@ -534,7 +583,8 @@ class FusedSpeechFrontEnd(Extractor):
                                        _lib.ptr(out['spec']), 1 if spec_log else 0, _lib.current_stream()))
     return out
 
-  def run_host_packed(self, pcm_pinned, sample_offsets, sr, want=("feat", "sad"), n_chunks=4, out=None):
+  def run_host_packed(self, pcm_pinned, sample_offsets, sr, want=("feat", "sad"), n_chunks=4, out=None,
+                      store_dtype=None):
     """End-to-end variant of `run_packed` for HOST buffers: `pcm_pinned` is a pinned CPU tensor (int16 /
     float32) of concatenated utterances; the batch is cut into `n_chunks` groups of whole utterances and
     pipelined over three streams -- H2D copy of chunk i+1, kernels of chunk i and D2H copy of chunk i-1 run
@@ -542,17 +592,25 @@ class FusedSpeechFrontEnd(Extractor):
     for the names in `want` (from 'mspec', 'feat', 'energy', 'c0', 'sad') + 'frame_offsets'; valid after
     the call returns (it synchronises).  Measured on the config-3 shard of bench.py (223 MB in, 168 MB out):
     1 chunk 9.5 ms, 2 -> 7.2, 4 -> 6.1, 8 -> 6.7, 16 -> 8.9 (every chunk pays the SADgmm critical path of its
-    longest utterance once; tools/fe_e2e_sweep.py)."""
+    longest utterance once; tools/fe_e2e_sweep.py).
+
+    `store_dtype='float16'` narrows the float32 features ON THE DEVICE (odin_feat_convert, round to nearest even like
+    the `AsType('float16')` tail of the recipes, examples/fsdd_ivec.py:105) before they are copied out: half the
+    device-to-host bytes of a path that is PCIe / host-DRAM bound."""
     import torch
     lib = _lib.load()
     h, cfg = self._handle(int(sr))
+    half = store_dtype is not None and np.dtype(store_dtype) == np.float16
+    if store_dtype is not None and not half and np.dtype(store_dtype) != np.float32:
+      raise ValueError("store_dtype must be float32 or float16")
+    fdt = torch.float16 if half else torch.float32
     so = np.ascontiguousarray(sample_offsets, dtype=np.int64)
     n_utt = len(so) - 1
     fo = np.zeros(n_utt + 1, dtype=np.int64)
     _lib.check(lib.odin_fe_frame_offsets(h, _lib.as_i64_ptr(so), n_utt, _lib.as_i64_ptr(fo)))
     T = int(fo[-1])
     fd = cfg.n_ceps * (1 + cfg.delta_order)
-    widths = {'mspec': (cfg.n_mels, torch.float32), 'feat': (fd, torch.float32), 'energy': (0, torch.float32),
+    widths = {'mspec': (cfg.n_mels, fdt), 'feat': (fd, fdt), 'energy': (0, torch.float32),
               'c0': (0, torch.float32), 'sad': (0, torch.uint8)}
     want = tuple(w for w in want if w in widths)
     if out is None:
@@ -560,7 +618,7 @@ class FusedSpeechFrontEnd(Extractor):
     for name in want:
       wd, dt = widths[name]
       if name not in out:
-        out[name] = torch.empty((T, wd) if wd else (T,), dtype=dt).pin_memory()
+        out[name] = torch.empty((T, wd) if wd else (T,), dtype=dt, pin_memory=True)
     out['frame_offsets'] = fo
     # chunk boundaries: whole utterances, about equal numbers of samples
     if isinstance(n_chunks, (tuple, list)):   # explicit fractions of the samples per chunk (they are normalised)
@@ -606,6 +664,13 @@ class FusedSpeechFrontEnd(Extractor):
       with torch.cuda.stream(s_run):
         s_run.wait_event(ev_in[i])
         o = self.run_packed(d_pcm[i % 2][:int(so[b] - so[a])], so[a:b + 1] - so[a], sr, want=dev_want)
+        if half:
+          for name in ('mspec', 'feat'):
+            if name in want:
+              h16 = torch.empty(o[name].shape, dtype=torch.float16, device=dev)
+              _lib.check(lib.odin_feat_convert(_lib.ptr(o[name]), 1, _lib.ptr(h16), 0, o[name].numel(),
+                                               _lib.current_stream()))
+              o[name] = h16
         ev_run[i].record(s_run)
       with torch.cuda.stream(s_out):
         s_out.wait_event(ev_run[i])
@@ -828,11 +893,8 @@ def plan_fusion(extractors):
         raise NotImplementedError(
             "AudioReader(remove_dc=True) at position %d is not followed by a fusable speech step: DC removal "
             "runs inside the fused kernels; odin_b200 has no CPU fallback" % i)
-    if (isinstance(e, speech_types) and not isinstance(e, (SADgmm, SADthreshold))) or isinstance(e, DeltaExtractor):
-      raise NotImplementedError(
-          "%s at position %d is not part of a fusable run "
-          "([AudioReader] [PreEmphasis] STFT PowerSpec MelsSpec [MFCCs [Delta]] [SAD] [ApplyingSAD]); "
-          "odin_b200 has no CPU fallback" % (e.__class__.__name__, i))
+    # a speech extractor outside a fusable run executes on its own: one stage of the chain per call
+    # (signal.pre_emphasis / stft / power_spectrogram / mels_spectrogram / ceps_spectrogram / delta on the device)
     plan.append(e)
     i += 1
   return plan

@@ -300,6 +300,105 @@ def tmat_fixtures():
   print("wrote tmat.npz")
 
 
+class _IdArray(np.ndarray):
+  __ne__ = lambda self, other: self is not other
+  __eq__ = lambda self, other: self is other
+  __hash__ = None
+
+
+def downsample_fixtures():
+  """Which frames GMM.expectation visits with downsample > 1 (gmm_tmat.py:135-232, 1043-1231), observed by running
+  the REAL reference on a data matrix whose first column is the frame number, and the statistics it returns."""
+  G = ref_shim.load_gmm()
+  rng = np.random.RandomState(21)
+  D, M, N = 6, 4, 12000
+  X = rng.randn(N, D).astype(np.float32)
+  lens = rng.randint(100, 1000, size=20)
+  starts = np.concatenate([[0], np.cumsum(lens)[:-1]])
+  indices = [("u%02d" % i, (int(s), int(s + n))) for i, (s, n) in enumerate(zip(starts, lens))]
+  sad = (rng.rand(N) > 0.3).astype(np.uint8)
+  mean, sigma, w = synth.gmm_params(D, M, seed=5)
+  blob = dict(X=X, sad=sad, starts=starts, lens=lens, mean=mean, sigma=sigma, w=w)
+  for tag, kw in (("ds4", dict(downsample=4, stochastic_downsample=True)),
+                  ("ds3det", dict(downsample=3, stochastic_downsample=False))):
+    for use_idx in (0, 1):
+      g = ref_shim.make_ref_gmm(M, niter=1, batch_size_cpu=700, seed=77, **kw)
+      ref_shim.ref_gmm_initialize(g, X)
+      g.mean, g.sigma, g.w = mean.copy(), sigma.copy(), w.copy()
+      g._resfresh_cpu_posterior()
+      g._llk_hist[M] = [0.0, 0.0]           # pretend two EM iterations were done: curr_niter = 2 enters the seed
+      # The workers of `expectation` are forked processes, so the picks are observed by driving the reference's own
+      # batch generators the way its single default job does (gmm_tmat.py:1165-1181: the job takes the files popped
+      # from the end of the list) on a matrix whose first column is the frame number ...
+      Xn = X.copy()
+      Xn[:, 0] = np.arange(N)
+      bs = int(g.batch_size_cpu / np.floor(np.power(2, M / 1024)))
+      common = dict(batch_size=bs, downsample=g.downsample, stochastic=g.stochastic_downsample, seed=g._seed,
+                    curr_nmix=M, curr_niter=2)
+      if use_idx:
+        it = G._create_batch_indices(Xn, sad, list(indices)[::-1], **common)
+      else:
+        it = G._create_batch(Xn, sad, 0, N, **common)
+      rows = np.concatenate([y[:, 0] for y, _, _ in it if y is not None]).astype(np.int64)
+      picked = np.zeros(N, dtype=np.uint8)
+      picked[rows] = 1
+      blob["%s_idx%d_mask" % (tag, use_idx)] = picked
+      # ... and confirmed against the real call: its statistics are those of exactly these frames
+      # (GMM.initialize picks the index list out of the tuple with `i != tmp` (gmm_tmat.py:566), which is ambiguous for a
+      #  plain ndarray; the reference feeds its own MmapData there.  An ndarray view with identity comparison stands in.)
+      Z, F, S, L = g.expectation((X.view(_IdArray), list(indices)) if use_idx else X, sad=sad, print_progress=True)
+      z2, f2, s2, l2 = g._fast_expectation(X[picked.astype(bool)], True, True, True, True, on_gpu=False)
+      assert np.allclose(Z, z2, rtol=1e-5) and np.allclose(F, f2, rtol=1e-4, atol=1e-3) and np.allclose(S, s2, rtol=1e-4, atol=1e-3)
+      assert abs(float(L) - float(l2) / int(picked.sum())) < 1e-5 * abs(float(L))
+      blob["%s_idx%d_Z" % (tag, use_idx)], blob["%s_idx%d_F" % (tag, use_idx)] = Z, F
+      blob["%s_idx%d_S" % (tag, use_idx)], blob["%s_idx%d_L" % (tag, use_idx)] = S, L
+  np.savez_compressed(os.path.join(OUT, "gmm_downsample.npz"), **blob)
+  print("wrote gmm_downsample.npz")
+
+
+def stages_fixtures():
+  """The chain one stage at a time through the reference's free functions (signal.py:955-967, 1002-1066,
+  1421-1562, 1623-1716): what `odin_b200.preprocessing.signal.*` and the stand-alone extractors must return."""
+  pp, S = ref_shim.load_frontend()
+  sr = 16000
+  raw = synth.speech_like(4242, 0.6, sr, seed=977).astype(np.float32)
+  blob = {"pcm": raw}
+  pre = S.pre_emphasis(raw, 0.97)
+  blob["pre"] = pre
+  blob["pre2d"] = S.pre_emphasis(np.stack([raw[:4000], raw[4000:8000]]), 0.95)
+  st, en = S.stft(pre, frame_length=400, step_length=160, n_fft=512, window='hamm', energy=True)
+  blob["stft"], blob["stft_energy"] = st, en
+  blob["stft_pad"] = S.stft(raw, frame_length=400, step_length=240, n_fft=1024, window='hann', padding=True)
+  blob["stft_scale"] = S.stft(raw, frame_length=200, step_length=80, n_fft=256, window='hann', scale=0.5)
+  spec = S.power_spectrogram(st, 2.0)
+  blob["spec"], blob["spec_mag"] = spec, S.power_spectrogram(st, 1.0)
+  blob["spec_real3"] = S.power_spectrogram(np.abs(st)[:5], 3.0)
+  mspec = S.mels_spectrogram(spec, sr, 40, fmin=64, fmax=8000, top_db=80.0)
+  blob["mspec"] = mspec
+  blob["mspec_top20"] = S.mels_spectrogram(spec, sr, 24, fmin=100, fmax=None, top_db=20.0)
+  blob["mfcc"] = S.ceps_spectrogram(mspec, 20, remove_first_coef=True)
+  blob["mfcc_keep0"] = S.ceps_spectrogram(mspec, 13, remove_first_coef=False)
+  d1, d2 = S.delta(blob["mfcc"], width=9, order=2, axis=0)
+  blob["d1"], blob["d2"] = d1, d2
+  blob["d1_w5"] = S.delta(blob["mfcc"], width=5, order=1, axis=0)
+  blob["d1_vec"] = S.delta(blob["mfcc"][:, 3], width=9, order=1, axis=0)
+  blob["energy_frames"] = S.get_energy(np.lib.stride_tricks.sliding_window_view(pre, 400)[::160], log=True)
+  # the same stages as stand-alone extractors (speech.py:540-563, 655-831; base.py:433-484)
+  sp, base = pp.speech, pp.base
+  X = {"raw": raw, "sr": sr}
+  X = sp.PreEmphasis(0.97).transform(X)
+  X = sp.STFTExtractor(0.025, 0.010, n_fft=512, window='hamm', energy=True).transform(X)
+  X = sp.PowerSpecExtractor(2.0).transform(X)
+  X = sp.MelsSpecExtractor(40, fmin=64, fmax=8000).transform(X)
+  X = sp.MFCCsExtractor(20, remove_first_coef=True, first_coef_energy=True).transform(X)
+  X = base.DeltaExtractor('mfcc', order=(0, 1, 2)).transform(X)
+  blob["x_mfcc"], blob["x_mfcc_energy"], blob["x_stft_energy"] = X["mfcc"], X["mfcc_energy"], X["stft_energy"]
+  # stored at single precision (the tolerances are 1e-4 of the matrix maximum): keeps the fixture small
+  blob = {k: (v.astype(np.complex64) if np.iscomplexobj(v) else v.astype(np.float32)) for k, v in blob.items()}
+  np.savez_compressed(os.path.join(OUT, "stages.npz"), **blob)
+  print("wrote stages.npz")
+
+
 def _scoring_problem(seed=5, ncls=10, per=30, d=24):
   """Synthetic i-vector-like vectors: class means + within-class noise, ragged class sizes."""
   rng = np.random.RandomState(seed)
@@ -355,7 +454,13 @@ if __name__ == "__main__":
     variants_fixtures()
   elif len(sys.argv) > 1 and sys.argv[1] == "scoring":
     scoring_fixtures()
+  elif len(sys.argv) > 1 and sys.argv[1] == "stages":
+    stages_fixtures()
+  elif len(sys.argv) > 1 and sys.argv[1] == "downsample":
+    downsample_fixtures()
   else:
+    downsample_fixtures()
+    stages_fixtures()
     scoring_fixtures()
     variants_fixtures()
     tmat_fixtures()

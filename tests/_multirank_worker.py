@@ -19,14 +19,19 @@ def main(outdir):
   torch.cuda.set_device(local)
   from odin_b200 import synth
   from odin_b200.ml import GMM, Tmatrix
-  D, M = 60, 256
+  D, M = 60, 64
   rng = np.random.RandomState(11)
   lens = rng.randint(200, 3000, size=40)
   off = np.concatenate([[0], np.cumsum(lens)])
-  X = synth.gmm_features(int(off[-1]), D, 16, seed=12)
+  # frames from 16 well separated components; the 64-mixture model starts at perturbed copies of the true means, so
+  # every mixture keeps occupancy (the T-matrix M-step needs every per-mixture system to be positive definite)
+  mu = rng.randn(16, D) * 3.0
+  X = (mu[rng.randint(0, 16, size=int(off[-1]))] + rng.randn(int(off[-1]), D)).astype(np.float32)
   sad = (rng.rand(int(off[-1])) > 0.2).astype(np.uint8)
   indices = [("utt%03d" % i, (int(off[i]), int(off[i + 1]))) for i in range(len(lens))]
-  mean, sigma, w = synth.gmm_params(D, M, seed=13)
+  mean = (np.tile(mu, (4, 1)) + 0.5 * rng.randn(M, D)).T.astype(np.float32).copy()
+  sigma = np.full((D, M), 1.5, dtype=np.float32)
+  w = np.full((1, M), 1.0 / M, dtype=np.float32)
 
   def model():
     g = GMM(nmix=M, nmix_start=M, niter=2)
@@ -41,7 +46,7 @@ def main(outdir):
   g1.expectation_maximization((X, indices), sad=sad, print_progress=False)
   g1.transform_to_disk(X, indices, sad=sad)
   zu1, fu1 = g1.last_utt_stats_
-  t1 = Tmatrix(8, g1, niter=1)
+  t1 = Tmatrix(4, g1, niter=1)
   t1.expectation_maximization(zu1.astype(np.float64), fu1.astype(np.float64))
   T1 = t1.Tm
   # ---- the same calls under NCCL
@@ -54,7 +59,7 @@ def main(outdir):
   zp, fp = os.path.join(outdir, "Z.npy"), os.path.join(outdir, "F.npy")
   names = g2.transform_to_disk(X, indices, sad=sad, pathZ=zp, pathF=fp)
   zu2, fu2 = np.load(zp), np.load(fp)
-  t2 = Tmatrix(8, g2, niter=1)
+  t2 = Tmatrix(4, g2, niter=1)
   t2.expectation_maximization(zu2.astype(np.float64), fu2.astype(np.float64))
   np.savez(os.path.join(outdir, "rank%d.npz" % rank), Z1=Z1, F1=F1, S1=S1, L1=L1, Z2=Z2, F2=F2, S2=S2, L2=L2,
            mean1=g1.mean, sigma1=g1.sigma, w1=g1.w, mean2=g2.mean, sigma2=g2.sigma, w2=g2.w,

@@ -47,7 +47,8 @@ def test_two_ranks_equal_one_rank(tmp_path):
     assert abs(float(r[k]["L2"]) - float(r[k]["L1"])) < 1e-6 * abs(float(r[k]["L1"]))
     for a, b in (("mean2", "mean1"), ("sigma2", "sigma1"), ("w2", "w1")):
       assert relmax(r[k][a], r[k][b]) < 1e-4, a
-    assert relmax(r[k]["zu2"], r[k]["zu1"]) < 1e-5 and relmax(r[k]["fu2"], r[k]["fu1"]) < 1e-5
+    # per-utterance statistics under the two fitted models (which differ at the 1e-5 level after two EM iterations)
+    assert relmax(r[k]["zu2"], r[k]["zu1"]) < 1e-4 and relmax(r[k]["fu2"], r[k]["fu1"]) < 1e-4
     sgn = np.sign(np.sum(r[k]["T2"] * r[k]["T1"], axis=1, keepdims=True))
     assert relmax(r[k]["T2"] * sgn, r[k]["T1"]) < 1e-4
   # replicated M-step / T-matrix update: bit-identical on both ranks

@@ -171,10 +171,15 @@ def test_make_pipeline_and_fusion_plan():
   assert (cfg.delta_order, cfg.vad_kind, cfg.vad_smooth, cfg.window, cfg.remove_dc) == (2, 1, 3, 1, 1)
   with pytest.raises(ValueError):
     pp.make_pipeline([1, 2])
-  with pytest.raises(NotImplementedError):      # a lone speech extractor cannot run (no CPU fallback)
-    pp.make_pipeline([pp.PreEmphasis()])
-  with pytest.raises(NotImplementedError):
-    pp.PreEmphasis().transform({"raw": np.zeros(4)})
+  # a lone speech extractor is planned as its own stage (signal.* on the device) ...
+  assert [type(s).__name__ for s in pp.make_pipeline([pp.PreEmphasis(), pp.DeltaExtractor("raw")]).plan] == \
+      ["PreEmphasis", "DeltaExtractor"]
+  # ... and there is no CPU fallback behind it: without a CUDA device it fails loudly
+  import torch
+  if not torch.cuda.is_available():
+    from odin_b200._lib import OdinError
+    with pytest.raises(OdinError):
+      pp.PreEmphasis().transform({"raw": np.zeros(4, np.float32)})
   # FSDD recipe wiring (examples/fsdd_ivec.py:80-106): SADthreshold on the first cepstral coefficient
   pipe = pp.make_pipeline([pp.AudioReader(), pp.PreEmphasis(), pp.STFTExtractor(0.025, 0.005, n_fft=512),
                            pp.PowerSpecExtractor(), pp.MelsSpecExtractor(24, fmin=64, fmax=4000),
@@ -206,6 +211,25 @@ def test_gmm_host_surface():
   m = g._selected_mask(200000, None, None)
   assert 0 < int(m.sum()) < 200000 and m[:1].dtype == np.uint8
   assert np.array_equal(m, g._selected_mask(200000, None, None))             # seeded => reproducible
+
+
+def test_downsample_picks_match_the_reference():
+  """g4 (gmm_tmat.py:135-232): with downsample > 1 the frames the E-step visits must be the reference's own picks --
+  observed from the real reference's batch generators (oracle/make_golden.py: downsample_fixtures), with and without
+  `indices`, stochastic (seed + curr_nmix + curr_niter) and deterministic seeding, SAD applied."""
+  g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gmm_downsample.npz"))
+  N = g["X"].shape[0]
+  indices = [("u%02d" % i, (int(s), int(s + n))) for i, (s, n) in enumerate(zip(g["starts"], g["lens"]))]
+  for tag, kw in (("ds4", dict(downsample=4, stochastic_downsample=True)),
+                  ("ds3det", dict(downsample=3, stochastic_downsample=False))):
+    for use_idx in (0, 1):
+      m = GMM(nmix=4, nmix_start=4, niter=1, batch_size_cpu=700, seed=77, **kw)
+      m.initialize(g["X"])
+      m._llk_hist[4] = [0.0, 0.0]     # two iterations done at this mixture count: enters the stochastic seed
+      mask = m._selected_mask(N, g["sad"], indices if use_idx else None)
+      ref = g["%s_idx%d_mask" % (tag, use_idx)]
+      assert 0 < int(ref.sum()) < int(g["sad"].sum())
+      assert np.array_equal(mask, ref), (tag, use_idx)
 
 
 def test_fusion_plan_of_the_fsdd_recipe():
