@@ -53,7 +53,7 @@ def parse():
   p.add_argument("--mfcc-hours", type=float, default=100.0,
                  help="hours of 16 kHz audio of the MFCC leg, TOTAL over all GPUs (config 3: 100 h)")
   p.add_argument("--no-mfcc", action="store_true")
-  p.add_argument("--mfcc-chunks", type=int, default=0, help="chunks of the MFCC end-to-end call (0: one per ~1.5 h of audio)")
+  p.add_argument("--mfcc-chunks", type=int, default=0, help="chunks of the MFCC end-to-end call (0: one per ~0.75 h of audio)")
   p.add_argument("--no-tmat", action="store_true")
   p.add_argument("--tmat-files", type=int, default=3000, help="files per GPU in the T-matrix leg")
   p.add_argument("--no-cpu-baseline", action="store_true")
@@ -327,7 +327,10 @@ def mfcc_leg(torch, args, rank, world, dist, peaks, do_cpu):
   # e2e: pinned host PCM -> device, features + VAD back to pinned host memory, through the public host-buffer
   # call (chunks of whole utterances pipelined over copy-in / kernel / copy-out streams); float32 features, and
   # the float16 store of the recipes' AsType('float16') tail (narrowed on the device)
-  n_chunks = args.mfcc_chunks if args.mfcc_chunks > 0 else max(4, int(round(hours / 1.5)))
+  # chunks of about 0.75 h: long enough that the per-chunk latency of the SADgmm kernel (its longest utterance's EM,
+  # ~0.5 ms whatever the chunk) stays below the chunk's PCIe time, short enough to expose little at both ends
+  # (tools/fe_e2e_scale.py: 100 h at 128 or 256 chunks 158 M frames/s = 51 GB/s H2D; 50 h at 256 chunks 105 M)
+  n_chunks = args.mfcc_chunks if args.mfcc_chunks > 0 else max(4, min(128, int(round(hours / 0.75))))
   e2e = {}
   for tag, sd in (("f32", None), ("f16", "float16")):
     host_out, ts = None, []

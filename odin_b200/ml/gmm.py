@@ -77,10 +77,23 @@ class _DeviceFrames(object):
         raise ValueError("`X` must be a 2-D matrix [n_samples, feat_dim]")
       self.host = X
     self.n, self.dim = (self.resident.shape if self.resident is not None else self.host.shape)
+    self.kdim = int(self.dim)   # row width handed to the kernels (GMM._kdim: zero columns appended), see set_kdim
     self.chunk = int(os.environ.get('ODIN_GMM_CHUNK_FRAMES', chunk_frames))   # (env: A/B runs of the streaming depth)
 
   shape = property(lambda self: (self.n, self.dim))
   ndim = 2
+
+  def set_kdim(self, k):
+    """Rows are delivered `k` >= dim wide, the extra columns zero (GMM._kdim)."""
+    k = int(k)
+    if k != self.kdim:
+      assert k >= self.dim and self._prepared is None
+      if self.resident is not None:
+        out = self.torch.zeros((self.n, k), dtype=self.torch.float32, device=self.resident.device)
+        out[:, :self.dim] = self.resident[:, :self.dim]
+        self.resident = out
+      self.kdim = k
+    return self
   _prepared = None
   _prepared_failed = False
   reuse = False   # set by callers that keep this object across EM iterations (fit, bench)
@@ -114,11 +127,11 @@ class _DeviceFrames(object):
     if self.resident is not None:
       return True
     torch = self.torch
-    need = self.n * self.dim * 4
+    need = self.n * self.kdim * 4
     free, _ = torch.cuda.mem_get_info()
     if need + reserve_bytes > free:
       return False
-    out = torch.empty((self.n, self.dim), dtype=torch.float32, device="cuda")
+    out = torch.empty((self.n, self.kdim), dtype=torch.float32, device="cuda")
     for dev, s, e in self.chunks():
       out[s:e].copy_(dev)
     self.resident, self.host, self.host_pinned = out, None, None
@@ -130,7 +143,7 @@ class _DeviceFrames(object):
     if self.resident is not None:
       yield self.resident, 0, self.n
       return
-    n, D = self.n, self.dim
+    n, D, K = self.n, self.dim, self.kdim
     if n == 0:
       return
     ch = min(self.chunk, n)
@@ -138,8 +151,8 @@ class _DeviceFrames(object):
     half = np.dtype(self.host.dtype) == np.float16   # stored width on the wire, widened on the device
     wire = torch.float16 if half else torch.float32
     pinned = None if direct else [torch.empty((ch, D), dtype=wire).pin_memory() for _ in range(2)]
-    dev = [torch.empty((ch, D), dtype=torch.float32, device="cuda") for _ in range(2)]
-    dev_wire = [torch.empty((ch, D), dtype=wire, device="cuda") for _ in range(2)] if half else dev
+    dev = [torch.zeros((ch, K), dtype=torch.float32, device="cuda") for _ in range(2)]   # pad columns stay zero
+    dev_wire = [torch.empty((ch, D), dtype=wire, device="cuda") for _ in range(2)] if (half or K != D) else dev
     lib = _lib.load()
     copy_stream = torch.cuda.Stream()
     copied = [torch.cuda.Event() for _ in range(2)]
@@ -172,7 +185,9 @@ class _DeviceFrames(object):
         stage(i + 1)
       b = i & 1
       torch.cuda.current_stream().wait_event(copied[b])
-      if half:
+      if K != D:     # widen (if float16) and place into the first D columns of the padded rows
+        dev[b][:e - s, :D].copy_(dev_wire[b][:e - s])
+      elif half:
         _lib.check(lib.odin_feat_convert(_lib.ptr(dev_wire[b]), 0, _lib.ptr(dev[b]), 1, (e - s) * D, _lib.current_stream()))
       yield dev[b][:e - s], s, e
       consumed[b].record()
@@ -228,6 +243,44 @@ class GMM(object):
     self._init_device_state()
 
   # ------------------------------------------------------------------ state
+  @property
+  def _kdim(self):
+    """Feature dimension the KERNELS see.  The tensor-core E-step needs D % 4 == 0 (16-byte frame rows); any
+    other D up to 60 (e.g. 39 = 13 MFCC + deltas) is carried with zero columns up to the next multiple of four and a
+    unit-variance, zero-mean model in those columns: they add exactly zero to every Mahalanobis term and the same
+    constant to every mixture's log-likelihood (removed again in `_unpack_stats` / the scoring calls), so posteriors
+    and statistics are unchanged -- and the frames run on tcgen05 instead of the 13x slower fp32 kernels."""
+    D = self._feat_dim
+    if D % 4 == 0 or D > 60 or self.impl not in (0, 3) or os.environ.get("ODIN_GMM_NO_PAD", "0") == "1":
+      return D
+    return (D + 3) & ~3
+
+  def _pad_frames(self, dev):
+    """[n, D] CUDA float32 -> [n, kdim] with zero columns appended (no-op when kdim == D)."""
+    k = self._kdim
+    if k == self._feat_dim:
+      return dev
+    out = _torch().zeros((dev.shape[0], k), dtype=dev.dtype, device=dev.device)
+    out[:, :self._feat_dim] = dev
+    return out
+
+  def _fix_pad_model(self, var_value):
+    """Pad rows of the device model: mean 0, variance `var_value` (1 - EPS for the E-step: precision exactly 1 and
+    log(var + EPS) = 0; 0 around the mix-up so that a pad column is never the split direction)."""
+    D, k, M = self._feat_dim, self._kdim, self._curr_nmix
+    if k == D:
+      return
+    self._d_mean[:k * M].view(k, M)[D:] = 0.0
+    self._d_var[:k * M].view(k, M)[D:] = var_value
+    _lib.check(_lib.load().odin_gmm_set_params(self._handle, M, _lib.ptr(self._d_mean), _lib.ptr(self._d_var),
+                                               _lib.ptr(self._d_w), _lib.current_stream()))
+
+  def _frames(self, X):
+    """X (array / tensor / _DeviceFrames) -> _DeviceFrames delivering rows of the kernel width."""
+    fr = X if isinstance(X, _DeviceFrames) else _DeviceFrames(X)
+    fr.reuse = fr.reuse or isinstance(X, _DeviceFrames)
+    return fr.set_kdim(self._kdim)
+
   def _init_device_state(self):
     self._handle = None
     self._d_mean = self._d_var = self._d_w = None
@@ -315,9 +368,9 @@ class GMM(object):
     if self._handle is None:
       import ctypes as C
       h = C.c_void_p()
-      _lib.check(lib.odin_gmm_create(self._feat_dim, self._nmix, C.byref(h)))
+      _lib.check(lib.odin_gmm_create(self._kdim, self._nmix, C.byref(h)))
       self._handle = h
-      D, M = self._feat_dim, self._nmix
+      D, M = self._kdim, self._nmix
       self._d_mean = torch.empty(D * M, dtype=torch.float32, device="cuda")
       self._d_var = torch.empty(D * M, dtype=torch.float32, device="cuda")
       self._d_w = torch.empty(M, dtype=torch.float32, device="cuda")
@@ -339,13 +392,16 @@ class GMM(object):
       if a.shape[0] != n:
         raise ValueError("parameter has %d elements, expected %d" % (a.shape[0], n))
       dst[:n].copy_(torch.from_numpy(a))
-    _lib.check(lib.odin_gmm_set_params(self._handle, M, _lib.ptr(self._d_mean), _lib.ptr(self._d_var),
-                                       _lib.ptr(self._d_w), _lib.current_stream()))
+    if self._kdim != D:
+      self._fix_pad_model(1.0 - EPS)   # (also calls odin_gmm_set_params)
+    else:
+      _lib.check(lib.odin_gmm_set_params(self._handle, M, _lib.ptr(self._d_mean), _lib.ptr(self._d_var),
+                                         _lib.ptr(self._d_w), _lib.current_stream()))
     self._synced = (self.mean, self.sigma, self.w)
     return lib
 
   def _download_params(self):
-    D, M = self._feat_dim, self._curr_nmix
+    D, M = self._feat_dim, self._curr_nmix   # (the first D of the kdim rows)
     self.mean = self._d_mean[:D * M].cpu().numpy().reshape(D, M).astype(self._dtype, copy=False)
     self.sigma = self._d_var[:D * M].cpu().numpy().reshape(D, M).astype(self._dtype, copy=False)
     self.w = self._d_w[:M].cpu().numpy().reshape(1, M).astype(self._dtype, copy=False)
@@ -360,17 +416,21 @@ class GMM(object):
 
   def _stats_buffer(self):
     torch = _torch()
-    n = (2 * self._feat_dim + 1) * self._curr_nmix + 2
+    n = (2 * self._kdim + 1) * self._curr_nmix + 2
     if self._d_stats is None or self._d_stats.shape[0] != n:
       self._d_stats = torch.zeros(n, dtype=torch.float64, device="cuda")
     return self._d_stats
 
+  def _llk_pad_const(self):
+    """What the pad columns take off every frame's log-likelihood: 1/2 (kdim - D) log 2 pi."""
+    return 0.5 * (self._kdim - self._feat_dim) * np.log(2 * np.pi)
+
   def _unpack_stats(self, stats_host, zero, first, second, llk):
-    D, M = self._feat_dim, self._curr_nmix
+    D, K, M = self._feat_dim, self._kdim, self._curr_nmix
     Z = stats_host[:M].reshape(1, M)
-    F = stats_host[M:M + D * M].reshape(D, M)
-    S = stats_host[M + D * M:M + 2 * D * M].reshape(D, M)
-    L, nfr = stats_host[-2], stats_host[-1]
+    F = stats_host[M:M + K * M].reshape(K, M)[:D]
+    S = stats_host[M + K * M:M + 2 * K * M].reshape(K, M)[:D]
+    L, nfr = stats_host[-2] + self._llk_pad_const() * stats_host[-1], stats_host[-1]
     out = []
     if zero:
       out.append(Z)
@@ -478,8 +538,9 @@ class GMM(object):
         d_mask = mask.to(device="cuda", dtype=torch.uint8).contiguous()
       else:
         d_mask = torch.from_numpy(np.ascontiguousarray(mask)).cuda()
+    frames.set_kdim(self._kdim)
     prep = None
-    if self.impl in (0, 3) and self._feat_dim % 4 == 0 and self._feat_dim <= 60 \
+    if self.impl in (0, 3) and self._kdim % 4 == 0 and self._kdim <= 60 \
         and os.environ.get("ODIN_H_NO_PREPARED", "0") != "1":   # (the images depend on the data only: every stage of fit)
       prep = frames.prepared(self._handle) if frames.reuse else None
     if prep is not None:
@@ -496,7 +557,7 @@ class GMM(object):
   def _fast_expectation(self, X, zero=True, first=True, second=True, llk=True, on_gpu=True):
     """gmm_tmat.py:997-1041 (L is the SUM of frame log-likelihoods here, as in the reference)."""
     self.initialize(X)
-    stats = self._estep_device(_DeviceFrames(X), None, second).cpu().numpy()
+    stats = self._estep_device(self._frames(X), None, second).cpu().numpy()
     out = self._unpack_stats(stats, zero, first, second, False)
     out = [out] if not isinstance(out, list) else out
     if llk:
@@ -512,8 +573,7 @@ class GMM(object):
       assert sad.shape[0] == n_global, \
           "Number of samples for X and sad mismatch X.shape=%s and sad.shape=%s" % (tuple(X.shape), sad.shape)
     Xl, ranges = self._shard(X, sad, indices)
-    frames = Xl if isinstance(Xl, _DeviceFrames) else _DeviceFrames(Xl)
-    frames.reuse = frames.reuse or isinstance(Xl, _DeviceFrames)
+    frames = self._frames(Xl)
     mask = self._local_mask(n_global, sad, indices, ranges)
     stats = self._estep_device(frames, mask, second).cpu().numpy()
     return self._unpack_stats(stats, zero, first, second, llk)
@@ -522,11 +582,12 @@ class GMM(object):
   def maximization(self, Z, F, S, floor_const=None):
     """gmm_tmat.py:1233-1276 on device (fp64) from host statistics."""
     torch = _torch()
-    D, M = self._feat_dim, self._curr_nmix
+    D, K, M = self._feat_dim, self._kdim, self._curr_nmix
+    pad = np.zeros(((K - D), M), dtype=np.float64)
     packed = np.concatenate([np.asarray(Z, dtype=np.float64).reshape(-1),
-                             np.asarray(F, dtype=np.float64).reshape(-1),
-                             np.asarray(S, dtype=np.float64).reshape(-1), [0.0, 0.0]])
-    assert packed.shape[0] == (2 * D + 1) * M + 2
+                             np.asarray(F, dtype=np.float64).reshape(D, M).reshape(-1), pad.reshape(-1),
+                             np.asarray(S, dtype=np.float64).reshape(D, M).reshape(-1), pad.reshape(-1), [0.0, 0.0]])
+    assert packed.shape[0] == (2 * K + 1) * M + 2
     self._upload_params()
     stats = self._stats_buffer()
     stats.copy_(torch.from_numpy(packed))
@@ -539,7 +600,7 @@ class GMM(object):
       # test (:1259-1272), so a positive floor prevents the rollback.  The M-step kernel computes
       # sigma = S / (Z + EPS) - mu^2; flooring is the same as raising S to (floor + mu^2) (Z + EPS), which is done
       # here on the packed statistics (O(D M) host work; not used by `fit`).
-      D, M = self._feat_dim, self._curr_nmix
+      D, M = self._kdim, self._curr_nmix
       st = stats.cpu().numpy().copy()
       Z, F, S = st[:M].reshape(1, M), st[M:M + D * M].reshape(D, M), st[M + D * M:M + 2 * D * M].reshape(D, M)
       iN = 1.0 / (Z + EPS)
@@ -551,6 +612,7 @@ class GMM(object):
     _lib.check(lib.odin_gmm_mstep(self._handle, _lib.ptr(stats), 1 if self.allow_rollback else 0,
                                   _lib.ptr(self._d_mean), _lib.ptr(self._d_var), _lib.ptr(self._d_w),
                                   _lib.ptr(self._d_flag), _lib.current_stream()))
+    self._fix_pad_model(1.0 - EPS)
     self._download_params()
     if int(self._d_flag.item()) != 0 and self.exit_on_error:
       self._stop_fitting = True
@@ -561,8 +623,7 @@ class GMM(object):
     X, indices = self.initialize(X)
     n_global = X.shape[0]
     Xl, ranges = self._shard(X, sad, indices)
-    frames = Xl if isinstance(Xl, _DeviceFrames) else _DeviceFrames(Xl)
-    frames.reuse = frames.reuse or isinstance(Xl, _DeviceFrames)
+    frames = self._frames(Xl)
     curr_nmix = self._curr_nmix
     mask = self._local_mask(n_global, sad, indices, ranges)
     stats = self._estep_device(frames, mask, True)
@@ -581,9 +642,11 @@ class GMM(object):
       return
     lib = self._upload_params()
     new_m = min(2 * self._curr_nmix, self._nmix)
+    self._fix_pad_model(0.0)           # a pad column must never be the direction of the split
     _lib.check(lib.odin_gmm_mixup(self._handle, new_m, _lib.ptr(self._d_mean), _lib.ptr(self._d_var),
                                   _lib.ptr(self._d_w), _lib.current_stream()))
     self._curr_nmix = new_m
+    self._fix_pad_model(1.0 - EPS)
     self._download_params()
     self._checkpoint()
     return self
@@ -623,7 +686,7 @@ class GMM(object):
     self.initialize(data)
     n_global = data.shape[0]
     local, ranges = self._shard(data, sad, indices)   # multi-GPU: this rank's utterances (gmm_tmat.py:102-133)
-    frames = _DeviceFrames(local)
+    frames = self._frames(local)
     frames.cache_on_device()
     frames.reuse = True
     niter = list(_NITER_SCHEDULE)
@@ -659,7 +722,7 @@ class GMM(object):
     torch = _torch()
     self.initialize(X)
     lib = self._upload_params()
-    frames = _DeviceFrames(X)
+    frames = self._frames(X)
     M = self._curr_nmix
     llk = np.empty((frames.n, 1), dtype=np.float32)
     post = np.empty((frames.n, M), dtype=np.float32) if want_post else None
@@ -676,6 +739,11 @@ class GMM(object):
         post[s:e] = d_post.cpu().numpy()
       if want_logprob:
         logp[s:e] = d_logp.cpu().numpy()
+    c = np.float32(self._llk_pad_const())
+    if c != 0:
+      llk += c
+      if want_logprob:
+        logp += c
     return llk, post, logp
 
   def logprob(self, X):
@@ -700,12 +768,16 @@ class GMM(object):
     torch = _torch()
     lib = self._upload_params()
     n_utt = len(offsets) - 1
-    D, M = self._feat_dim, self._curr_nmix
+    D, K, M = self._feat_dim, self._kdim, self._curr_nmix
+    if frames_dev.shape[1] != K:
+      frames_dev = self._pad_frames(frames_dev)
     Z = torch.empty((n_utt, M), dtype=torch.float32, device="cuda")
-    Fh = torch.empty((n_utt, M * D), dtype=torch.float32, device="cuda")
+    Fh = torch.empty((n_utt, M * K), dtype=torch.float32, device="cuda")
     off = np.ascontiguousarray(offsets, dtype=np.int64)
     _lib.check(lib.odin_gmm_utt_stats(self._handle, _lib.ptr(frames_dev), _lib.ptr(d_sad), _lib.as_i64_ptr(off),
                                       n_utt, _lib.ptr(Z), _lib.ptr(Fh), self.impl, _lib.current_stream()))
+    if K != D:   # drop the pad columns: index m * D + d (gmm_tmat.py:754-757)
+      Fh = Fh.view(n_utt, M, K)[:, :, :D].reshape(n_utt, M * D)
     return Z, Fh
 
   def transform(self, X, zero=True, first=True, device=None):
@@ -716,7 +788,7 @@ class GMM(object):
     self.initialize(X)
     assert X.ndim == 2 and X.shape[1] == self.feat_dim, \
         "`X` must be 2-D matrix, with `X.shape[1]=%d`; but given: %s" % (self.feat_dim, str(X.shape))
-    frames = _DeviceFrames(X)
+    frames = self._frames(X)
     frames.cache_on_device(0)
     Z, Fh = self._utt_stats_device(frames.resident, None, np.array([0, frames.n], dtype=np.int64))
     Z, Fh = Z.cpu().numpy(), Fh.cpu().numpy()
@@ -744,7 +816,7 @@ class GMM(object):
     rank = td.get_rank() if td is not None else 0
     mine = list(range(n_utt)) if td is None else \
         sharding.shard_utterances([int(e) - int(s) for _, (s, e) in indices], td.get_world_size())[rank]
-    frames = _DeviceFrames(X)
+    frames = self._frames(X)
     resident = frames.cache_on_device() if td is None else frames.resident is not None
     D, M = self._feat_dim, self._curr_nmix   # (a partially fitted model emits _curr_nmix columns)
     z_dat = f_dat = None

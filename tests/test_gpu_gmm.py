@@ -217,3 +217,32 @@ def test_host_array_streaming_equals_resident():
   Z16, F16, S16, L16 = gm.expectation(X16)
   z, f, s, l, _ = OG.expectation(X16.astype(np.float32), mean, sigma, w, compute_dtype=np.float64)
   assert relmax(Z16, z) < TOL_STATS and relmax(S16, s) < TOL_STATS
+
+
+def test_maximization_floor_const_prevents_rollback():
+  """gmm_tmat.py:1254-1268: the variance floor is applied BEFORE the negative-variance test, so a positive
+  `floor_const` keeps the update where the unfloored one would have been rolled back."""
+  from odin_b200.ml import GMM
+  D, M = 8, 4
+  rng = np.random.RandomState(2)
+  Z = rng.rand(1, M) * 50 + 10
+  F = rng.randn(D, M) * Z
+  S = (F / Z) ** 2 * Z + rng.rand(D, M) * Z            # variances in (0, 1)
+  S[3, 1] = (F[3, 1] / Z[0, 1]) ** 2 * Z[0, 1] - 5.0   # one negative variance
+  prev = (rng.randn(D, M).astype(np.float32), np.ones((D, M), np.float32), np.full((1, M), 0.25, np.float32))
+
+  def run(floor):
+    g = GMM(nmix=M, nmix_start=M, impl=1)
+    g.initialize(np.zeros((1, D), np.float32))
+    g.mean, g.sigma, g.w = [a.copy() for a in prev]
+    g.maximization(Z, F, S, floor_const=floor)
+    return g
+
+  g0 = run(None)
+  assert np.array_equal(g0.mean, prev[0]) and np.array_equal(g0.sigma, prev[1])     # rolled back (allow_rollback)
+  g1 = run(0.1)
+  iN = 1.0 / (Z + 1e-6)
+  mu, sig = F * iN, S * iN - (F * iN) ** 2
+  wgt = Z / Z.sum()
+  ref = sig.clip(sig.dot(wgt.T) * 0.1)
+  assert relmax(g1.mean, mu) < 1e-5 and relmax(g1.sigma, ref) < 1e-5 and relmax(g1.w, wgt) < 1e-5

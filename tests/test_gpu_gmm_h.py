@@ -185,3 +185,105 @@ def test_h_per_utterance_statistics():
                                     compute_dtype=np.float64)
     assert nr == names and Zu.shape == zr.shape and Fu.shape == fr.shape
     assert relmax(Zu, zr) < 5e-5 and relmax(Fu, fr) < 5e-5, (relmax(Zu, zr), relmax(Fu, fr))
+
+
+@pytest.mark.parametrize("D,M", [(39, 256), (13, 64), (57, 512)])
+def test_h_feature_dims_not_multiple_of_four(D, M):
+  """D = 39 (13 MFCC + deltas) and friends: the frames are carried with zero columns up to the next multiple of four
+  (GMM._kdim) so they run on the tcgen05 kernels; statistics, log-likelihood, scores, per-utterance statistics, the
+  M-step and the mix-up must be those of the D-dimensional model."""
+  from odin_b200 import _lib
+  from odin_b200.ml import GMM
+  N = 6000
+  X = synth.gmm_features(N, D, 8, seed=D)
+  mean, sigma, w = synth.gmm_params(D, M, seed=M + 1)
+  g = _gmm(M, mean, sigma, w, 0)
+  assert g._kdim == (D + 3) // 4 * 4 and g._kdim != D
+  sad = (np.random.RandomState(1).rand(N) > 0.25).astype(np.uint8)
+  Z, F, S, L = g.expectation(X, sad=sad)
+  z, f, s, l, n = OG.expectation(X, mean, sigma, w, sad=sad, compute_dtype=np.float64)
+  assert F.shape == (D, M) and S.shape == (D, M)
+  assert max(relmax(Z, z), relmax(F, f), relmax(S, s)) < TIGHT
+  assert abs(float(L) - float(l)) < 1e-4 * abs(float(l))
+  im = _lib.C.c_int32()
+  a, b = _lib.C.c_float(), _lib.C.c_float()
+  _lib.check(_lib.load().odin_gmm_last_estep_ms(g._handle, _lib.C.byref(a), _lib.C.byref(b), _lib.C.byref(im)))
+  assert im.value == 3                                   # it did run on the 3xFP16 tensor-core kernels
+  # scoring surface: same constant correction
+  prec, mup, Cc = OG.posterior_constants(mean.astype(np.float64), sigma.astype(np.float64), w.astype(np.float64))
+  X64 = X[:500].astype(np.float64)
+  lp = -0.5 * (Cc + X64**2 @ prec - 2 * X64 @ mup + D * np.log(2 * np.pi))
+  assert np.max(np.abs(g.logprob(X[:500]) - lp)) < 2e-3 * max(1.0, np.max(np.abs(lp)) / 100)
+  assert np.max(np.abs(g.llk(X[:500]) - OG._lse(lp))) < 2e-3 and np.allclose(g.postprob(X[:500]).sum(1), 1.0, atol=1e-4)
+  # per-utterance statistics: F-hat index m * D + d
+  idx = [("a", (0, 2500)), ("b", (2500, 6000))]
+  g.transform_to_disk(X, idx, sad=None)
+  Zu, Fu = g.last_utt_stats_
+  nr, zr, fr = OG.utterance_stats(X, idx, mean, sigma, w, compute_dtype=np.float64)
+  assert Fu.shape == (2, M * D) and relmax(Zu, zr) < TIGHT and relmax(Fu, fr) < 2e-4
+  # EM iterations and a mix-up follow the oracle (model started on data points: no empty mixtures, whose
+  # variances of exactly zero +- rounding would make the roll-back decision a coin toss)
+  M0 = M // 2
+  rng = np.random.RandomState(D)
+  g2 = GMM(nmix=M, nmix_start=M0, niter=3)
+  g2.initialize(X)
+  g2.mean = X[rng.choice(N, M0, replace=False)].T.copy()
+  g2.sigma = np.tile(X.var(0)[:, None], (1, M0)).astype(np.float32)
+  g2.w = np.full((1, M0), 1.0 / M0, dtype=np.float32)
+  om, os_, ow = [a.astype(np.float64) for a in (g2.mean, g2.sigma, g2.w)]
+  for _ in range(2):
+    g2.expectation_maximization(X, print_progress=False)
+    zz, ff, ss, ll, _ = OG.expectation(X, om, os_, ow, compute_dtype=np.float64)
+    om, os_, ow, rb = OG.maximization(zz, ff, ss, (om, os_, ow))
+    assert not rb
+  assert relmax(g2.mean, om) < TOL_STATS and relmax(g2.sigma, os_) < TOL_STATS and relmax(g2.w, ow) < TOL_STATS
+  g2.gmm_mixup()
+  m2, s2, w2 = OG.mixup(om, os_, ow, M)
+  assert g2.mean.shape == (D, M) and relmax(g2.mean, m2) < TOL_STATS and relmax(g2.sigma, s2) < TOL_STATS
+  g2.expectation_maximization(X, print_progress=False)
+  zz, ff, ss, ll, _ = OG.expectation(X, m2, s2, w2, compute_dtype=np.float64)
+  m3, s3, w3, rb = OG.maximization(zz, ff, ss, (m2, s2, w2))
+  assert not rb and relmax(g2.mean, m3) < TOL_STATS and relmax(g2.sigma, s3) < TOL_STATS
+
+
+def test_h_float16_store_is_widened_on_the_device():
+  """Frames kept as float16 (AsType('float16')) cross PCIe as float16 and are widened by
+  odin_feat_convert: the statistics equal those of the same values handed over as float32, bit for bit."""
+  import torch
+  D, M, N = 60, 256, 300000
+  X16 = synth.gmm_features(N, D, 8, seed=3).astype(np.float16)
+  mean, sigma, w = synth.gmm_params(D, M, seed=4)
+  a = _gmm(M, mean, sigma, w, 3).expectation(X16)
+  b = _gmm(M, mean, sigma, w, 3).expectation(X16.astype(np.float32))
+  for x, y in zip(a, b):
+    assert np.array_equal(np.asarray(x), np.asarray(y))
+  c = _gmm(M, mean, sigma, w, 3).expectation(torch.from_numpy(X16).pin_memory())
+  for x, y in zip(a, c):
+    assert np.array_equal(np.asarray(x), np.asarray(y))
+  z, f, s, l, n = OG.expectation(X16.astype(np.float64), mean, sigma, w, compute_dtype=np.float64)
+  assert max(relmax(a[0], z), relmax(a[1], f), relmax(a[2], s)) < TIGHT
+
+
+def test_h_config4_protocol_ten_iterations_2048():
+  """Config 4's protocol at reduced frame count: TEN EM iterations of a 2048-mixture UBM (resident frames, operand
+  images built once) against ten iterations of the fp64 oracle; parameters within the north star's 1e-3."""
+  D, M, N = 60, 2048, 120000
+  X = synth.gmm_features(N, D, 64, seed=31)
+  rng = np.random.RandomState(6)
+  mean = X[rng.choice(N, M, replace=False)].T.copy()
+  sigma = np.tile(X.var(0)[:, None], (1, M)).astype(np.float32)
+  w = np.full((1, M), 1.0 / M, dtype=np.float32)
+  gm = _gmm(M, mean, sigma, w, 3)
+  from odin_b200.ml.gmm import _DeviceFrames
+  fr = _DeviceFrames(X)
+  fr.cache_on_device()
+  fr.reuse = True
+  om, os_, ow = mean.astype(np.float64), sigma.astype(np.float64), w.astype(np.float64)
+  for it in range(10):
+    gm.expectation_maximization(fr, print_progress=False)
+    z, f, s, l, _ = OG.expectation(X, om, os_, ow, compute_dtype=np.float64)
+    om, os_, ow, rb = OG.maximization(z, f, s, (om, os_, ow))
+    assert not rb
+  assert relmax(gm.mean, om) < TOL_STATS and relmax(gm.sigma, os_) < TOL_STATS and relmax(gm.w, ow) < TOL_STATS
+  assert len(gm._llk_hist[M]) == 10 and abs(gm._llk_hist[M][-1] - l) < 1e-3 * abs(l)
+  assert all(b >= a - 1e-6 * abs(a) for a, b in zip(gm._llk_hist[M], gm._llk_hist[M][1:]))   # EM never decreases the llk
