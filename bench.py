@@ -486,6 +486,67 @@ def tmat_leg(torch, args, rank, world, dist, do_cpu):
 
 
 # ---------------------------------------------------------------------------
+# config 5: FSDD-style digits -> MFCC -> 512-mix per-utterance statistics (the i-vector extractor's input)
+# ---------------------------------------------------------------------------
+def cfg5_leg(torch, args, rank, world, dist):
+  """3 000 synthetic digits of U[0.3, 1.0] s at 8 kHz per GPU through the recipe's chain (examples/fsdd_ivec.py:80-106:
+  25 ms / 5 ms, n_fft 512, 24 mel, 20 MFCC + c0 + d/dd, SADthreshold) and GMM.transform_to_disk's kernels at M = 512:
+  per-utterance Z [n, 512] and F-hat [n, 30 720]; PCM and features stay resident."""
+  from odin_b200 import _lib, synth
+  from odin_b200 import preprocessing as pp
+  from odin_b200.ml import GMM
+  sr, n_utt, M = 8000, 3000, 512
+  pipe = pp.make_pipeline([
+      pp.AudioReader(), pp.PreEmphasis(0.97), pp.STFTExtractor(0.025, 0.005, n_fft=512, window="hamm", energy=False),
+      pp.PowerSpecExtractor(), pp.MelsSpecExtractor(24, fmin=64, fmax=4000),
+      pp.MFCCsExtractor(20, first_coef_energy=True), pp.DeltaExtractor("mfcc", order=(0, 1, 2)),
+      pp.RenameFeatures("mfcc_energy", "energy"), pp.SADthreshold(input_name="energy")])
+  fe = pipe.plan[0]
+  pool = synth.utterance_batch(100, 0.3, 1.0, sr=sr, seed=50 + rank)
+  utts = [pool[i % 100] for i in range(n_utt)]
+  pcm_h, off = synth.pack_utterances(utts)
+  pcm = torch.from_numpy(pcm_h).cuda()
+  out = fe.run_packed(pcm, off, sr)
+  fo = out["frame_offsets"]
+  T = int(fo[-1])
+  X = out["feat"]
+  rng = np.random.RandomState(3)
+  g = GMM(nmix=M, nmix_start=M)
+  g.initialize(np.zeros((1, 60), np.float32))
+  pick = torch.from_numpy(rng.choice(T, M, replace=False)).cuda()
+  g.mean = X[pick].t().contiguous().cpu().numpy()
+  g.sigma = np.tile(X.var(0).cpu().numpy()[:, None], (1, M)).astype(np.float32)
+  g.w = np.full((1, M), 1.0 / M, dtype=np.float32)
+
+  def timed(fn, reps):
+    for _ in range(3):
+      fn()
+    torch.cuda.synchronize()
+    if dist is not None:
+      dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+      fn()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / reps / 1e3], dtype=torch.float64, device="cuda")
+    if dist is not None:
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+  reps = max(3, min(args.steps, 20))
+  fe_s = timed(lambda: fe.run_packed(pcm, off, sr), reps)
+  st_s = timed(lambda: g._utt_stats_device(X, out["sad"], fo), reps)
+  return {"metric": "cfg5_utterances_per_s", "value": n_utt * world / (fe_s + st_s), "unit": "utterances/s",
+          "config": {"workload": "config 5: %d digits of U[0.3,1.0] s at 8 kHz per GPU -> MFCC(20)+c0+d/dd+SADthreshold -> "
+                                 "512-mix per-utterance Z / F-hat" % n_utt, "frames_per_gpu": T, "nmix": M},
+          "frontend": {"ms": fe_s * 1e3, "frames_per_s": T * world / fe_s},
+          "utt_stats": {"ms": st_s * 1e3, "frames_per_s": T * world / st_s, "utterances_per_s": n_utt * world / st_s,
+                        "kernels": "fp32 CUDA-core route of odin_gmm_utt_stats (short utterances: one launch per batch)"}}
+
+
+# ---------------------------------------------------------------------------
 # main arm
 # ---------------------------------------------------------------------------
 def run_ours(args):
@@ -699,6 +760,10 @@ def run_ours(args):
       line["tmatrix"] = tmat_leg(torch, args, rank, world, dist, do_cpu)
     except Exception as e:
       line["tmatrix"] = {"error": "%s: %s" % (type(e).__name__, e)}
+    try:
+      line["cfg5"] = cfg5_leg(torch, args, rank, world, dist)
+    except Exception as e:
+      line["cfg5"] = {"error": "%s: %s" % (type(e).__name__, e)}
   if rank == 0:
     print(json.dumps(line))
   if dist is not None:

@@ -1,5 +1,5 @@
 """The recipe of the reference's examples/fsdd_ivec.py (feature extraction -> UBM -> Baum-Welch statistics ->
-T-matrix -> i-vectors) with the imports switched to odin_b200, on synthetic "digits" (there is no dataset or
+T-matrix -> i-vectors -> cosine / PLDA scoring) with the imports switched to odin_b200, on synthetic "digits" (there is no dataset or
 network here): 8 kHz, 25 ms / 5 ms frames, 24 mel bands, 20 MFCC + c0 energy + deltas, SADthreshold, mean /
 windowed-mean normalisation, float16 store (fsdd_ivec.py:80-106); 128-mixture UBM, tv_dim 64 (its defaults).
 
@@ -16,6 +16,19 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from odin_b200 import preprocessing as pp   # reference: from odin import preprocessing as pp
 from odin_b200 import ml                     # reference: from odin import ml
 from odin_b200 import synth
+
+
+def eer(scores, labels):
+  """Equal error rate of the target / non-target trials of a [n_trials, n_classes] score matrix."""
+  tgt = np.zeros(scores.shape, dtype=bool)
+  tgt[np.arange(len(labels)), labels] = True
+  s, t = scores.ravel(), tgt.ravel()
+  order = np.argsort(-s)
+  t = t[order]
+  fa = np.cumsum(~t) / max(1, int((~t).sum()))        # false accepts above each threshold
+  miss = 1.0 - np.cumsum(t) / max(1, int(t.sum()))    # misses below it
+  i = int(np.argmin(np.abs(fa - miss)))
+  return float(0.5 * (fa[i] + miss[i]))
 
 
 def main(n_files=600, nmix=128, tv_dim=64):
@@ -68,6 +81,18 @@ def main(n_files=600, nmix=128, tv_dim=64):
     diff = cos[spk[:, None] != spk[None, :]].mean()
     print("mean cosine: same speaker %.3f, different speaker %.3f" % (same, diff))
     assert same > diff
+    # scoring back-end (fsdd_ivec.py:270-330): even files enrol / train, odd files are the trials
+    tr, te = np.arange(0, len(spk), 2), np.arange(1, len(spk), 2)
+    X_train, X_test = np.asarray(ivecs[tr], np.float64), np.asarray(ivecs[te], np.float64)
+    for tag, scorer in (("cosine (centering + WCCN + LDA)", ml.Scorer(centering=True, wccn=True, lda=True, method="cosine")),
+                        ("PLDA (n_phi %d, 12 iterations)" % (tv_dim // 2),
+                         ml.PLDA(n_phi=tv_dim // 2, n_iter=12, centering=True, wccn=True, unit_length=True, random_state=1234))):
+      t5 = time.perf_counter()
+      scorer.fit(X_train, spk[tr])
+      scores = scorer.predict_log_proba(X_test)
+      acc = float(np.mean(np.argmax(scores, 1) == spk[te]))
+      print("%s: accuracy %.3f, EER %.3f  (fit + score %.1f ms)" % (tag, acc, eer(scores, spk[te]), 1e3 * (time.perf_counter() - t5)))
+      assert acc > 0.9
   print("total %.2f s" % (time.perf_counter() - t0))
 
 

@@ -257,6 +257,12 @@ void odin_gmm_frames_destroy(odin_gmm_frames_t* f);
 int odin_gmm_estep_frames(odin_gmm_t* g, const odin_gmm_frames_t* f, const uint8_t* d_sad, int32_t want_second,
                           double* d_stats, void* stream);
 
+/* The exchange step of SURVEY 8e for a binder that owns an NCCL communicator (replaces _ExpectationResults.update +
+ * the multiprocessing queue, gmm_tmat.py:249-265, 1199-1220): in-place, in-stream ncclAllReduce(sum, double) of the packed
+ * statistics of the current model size.  `nccl_comm` is an ncclComm_t; libnccl is resolved at run time (no link-time
+ * dependency).  The Python binding performs the same all-reduce through torch.distributed (odin_b200/sharding.py). */
+int odin_gmm_allreduce(odin_gmm_t* g, double* d_stats, void* nccl_comm, void* stream);
+
 /* M-step (gmm_tmat.py:1233-1276) from packed stats, in fp64 on device; writes the
  * new model into the handle AND to d_mean/d_var/d_w (fp32, reference layout).
  * If any variance < 0: allow_rollback = 1 keeps the previous model, 0 clips at 0;

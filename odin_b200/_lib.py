@@ -85,6 +85,7 @@ SIGNATURES = {
     "odin_gmm_frames_create": (C.c_int, [_vp, _vp, _i64, C.POINTER(_vp), _vp]),
     "odin_gmm_frames_destroy": (None, [_vp]),
     "odin_gmm_estep_frames": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp]),
+    "odin_gmm_allreduce": (C.c_int, [_vp, _vp, _vp, _vp]),
     "odin_gmm_mstep": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "odin_gmm_mixup": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp]),
     "odin_gmm_utt_stats": (C.c_int, [_vp, _vp, _vp, _pi64, _i32, _vp, _vp, _i32, _vp]),

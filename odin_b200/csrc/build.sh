@@ -16,5 +16,5 @@ for f in capi fe_kernels fe_frame5 cmvn_kernels gmm_kernels gmm_tc gmm_h tmat_ke
   fi
 done
 for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
-"$NVCC" -shared -o "$OUT/libodin_b200.so" "$HERE"/.obj/{capi,fe_kernels,fe_frame5,cmvn_kernels,gmm_kernels,gmm_tc,gmm_h,tmat_kernels,feat_kernels,sig_kernels}.o -lcudart
+"$NVCC" -shared -o "$OUT/libodin_b200.so" "$HERE"/.obj/{capi,fe_kernels,fe_frame5,cmvn_kernels,gmm_kernels,gmm_tc,gmm_h,tmat_kernels,feat_kernels,sig_kernels}.o -lcudart -ldl
 echo "built $OUT/libodin_b200.so"

@@ -1,5 +1,6 @@
 // extern "C" entry points of libodin_b200.so (see include/odin_b200.h) and the
 // host-side table construction for the front-end.
+#include <dlfcn.h>
 #include <math.h>
 #include <string.h>
 
@@ -725,6 +726,31 @@ int odin_gmm_estep_frames(odin_gmm_t* g, const odin_gmm_frames_t* f, const uint8
 }
 
 int64_t odin_gmm_last_estep_frames(const odin_gmm_t* g) { return g ? g->last_frames : ODIN_EINVAL; }
+
+// The one exchange step of the multi-GPU path for a C / C++ binder that owns an NCCL communicator:
+// ncclAllReduce(sum, double) of the packed statistics, in place and in stream.  NCCL is not linked: it is looked
+// up at run time (the library the host application -- e.g. torch -- has already loaded), so the shared object has no
+// NCCL dependency when the caller does its collectives elsewhere (the Python binding uses torch.distributed).
+int odin_gmm_allreduce(odin_gmm_t* g, double* d_stats, void* nccl_comm, void* stream) {
+  if (!g || !d_stats || !nccl_comm) return set_error(ODIN_EINVAL, "bad argument");
+  if (g->M <= 0) return set_error(ODIN_EINVAL, "odin_gmm_set_params has not been called");
+  typedef int (*allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+  typedef const char* (*errstr_fn)(int);
+  static allreduce_fn fn = nullptr;
+  static errstr_fn es = nullptr;
+  if (fn == nullptr) {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return set_error(ODIN_ENODEVICE, "odin_gmm_allreduce: libnccl.so.2 cannot be loaded (%s)", dlerror());
+    fn = reinterpret_cast<allreduce_fn>(dlsym(h, "ncclAllReduce"));
+    es = reinterpret_cast<errstr_fn>(dlsym(h, "ncclGetErrorString"));
+    if (!fn) return set_error(ODIN_ENODEVICE, "odin_gmm_allreduce: ncclAllReduce not found in libnccl");
+  }
+  const size_t n = (size_t)stats_size(g->D, g->M);
+  const int rc = fn(d_stats, d_stats, n, /*ncclFloat64*/ 8, /*ncclSum*/ 0, nccl_comm, as_stream(stream));
+  if (rc != 0) return set_error(ODIN_ECUDA, "ncclAllReduce: %s", es ? es(rc) : "error");
+  return ODIN_OK;
+}
 
 int odin_gmm_last_estep_ms(odin_gmm_t* g, float* lse_ms, float* stats_ms, int32_t* impl_used) {
   if (!g || !lse_ms || !stats_ms) return set_error(ODIN_EINVAL, "null argument");

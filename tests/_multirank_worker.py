@@ -61,7 +61,32 @@ def main(outdir):
   zu2, fu2 = np.load(zp), np.load(fp)
   t2 = Tmatrix(4, g2, niter=1)
   t2.expectation_maximization(zu2.astype(np.float64), fu2.astype(np.float64))
-  np.savez(os.path.join(outdir, "rank%d.npz" % rank), Z1=Z1, F1=F1, S1=S1, L1=L1, Z2=Z2, F2=F2, S2=S2, L2=L2,
+  # ---- the C-ABI collective (odin_gmm_allreduce) on an NCCL communicator of its own, against torch.distributed
+  import ctypes as C
+  from odin_b200 import _lib
+  nccl = C.CDLL("libnccl.so.2")          # the library torch has already loaded
+
+  class UniqueId(C.Structure):
+    _fields_ = [("internal", C.c_byte * 128)]
+
+  uid = UniqueId()
+  if rank == 0:
+    assert nccl.ncclGetUniqueId(C.byref(uid)) == 0
+  t = torch.tensor(list(bytes(uid)), dtype=torch.uint8, device="cuda")
+  td.broadcast(t, 0)
+  C.memmove(C.byref(uid), bytes(t.cpu().numpy().tolist()), 128)
+  comm = C.c_void_p()
+  nccl.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, UniqueId, C.c_int]
+  assert nccl.ncclCommInitRank(C.byref(comm), world, uid, rank) == 0
+  nst = (2 * g2._kdim + 1) * M + 2
+  mine = torch.arange(nst, dtype=torch.float64, device="cuda") * (rank + 1) + 0.25 * rank
+  want = mine.clone()
+  td.all_reduce(want)
+  _lib.check(_lib.load().odin_gmm_allreduce(g2._handle, _lib.ptr(mine), comm, _lib.current_stream()))
+  torch.cuda.synchronize()
+  ar_equal = bool(torch.equal(mine, want))
+  nccl.ncclCommDestroy(comm)
+  np.savez(os.path.join(outdir, "rank%d.npz" % rank), ar_equal=ar_equal, Z1=Z1, F1=F1, S1=S1, L1=L1, Z2=Z2, F2=F2, S2=S2, L2=L2,
            mean1=g1.mean, sigma1=g1.sigma, w1=g1.w, mean2=g2.mean, sigma2=g2.sigma, w2=g2.w,
            zu1=zu1, fu1=fu1, zu2=zu2, fu2=fu2, T1=T1, T2=t2.Tm, names=np.array(names), world=world)
   td.barrier()

@@ -55,3 +55,5 @@ def test_two_ranks_equal_one_rank(tmp_path):
   for name in ("Z2", "F2", "S2", "mean2", "sigma2", "w2", "T2", "zu2", "fu2"):
     assert np.array_equal(r[0][name], r[1][name]), name
   assert list(r[0]["names"]) == ["utt%03d" % i for i in range(40)]
+  # odin_gmm_allreduce (C-ABI, its own NCCL communicator) == torch.distributed.all_reduce, bit for bit
+  assert bool(r[0]["ar_equal"]) and bool(r[1]["ar_equal"])
