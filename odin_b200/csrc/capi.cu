@@ -375,7 +375,7 @@ void odin_fe_destroy(odin_fe_t* fe) {
   cudaFree(fe->d_win32); cudaFree(fe->d_win64); cudaFree(fe->d_tw); cudaFree(fe->d_tw4); cudaFree(fe->d_mel_start);
   cudaFree(fe->d_mel_cnt); cudaFree(fe->d_mel_off); cudaFree(fe->d_mel_w); cudaFree(fe->d_dct);
   cudaFree(fe->d_mel_tab); cudaFree(fe->d_mel_ps);
-  cudaFree(fe->d_dct64); cudaFree(fe->d_mel5_w); cudaFree(fe->d_mel5_flags); cudaFree(fe->d_mel5_refs);
+  cudaFree(fe->d_dct64); cudaFree(fe->d_tile_ctr); cudaFree(fe->d_mel5_w); cudaFree(fe->d_mel5_flags); cudaFree(fe->d_mel5_refs);
   cudaFree(fe->d_taps); cudaFree(fe->d_sample_off); cudaFree(fe->d_dcsum); cudaFree(fe->d_umax);
   cudaFree(fe->d_cnt); cudaFree(fe->d_vad_scratch);
   if (fe->h_stage) cudaFreeHost(fe->h_stage);

@@ -39,6 +39,7 @@ struct odin_fe {
   uint16_t* d_mel5_refs = nullptr; // [ceil(n_mels/32)][mel5_k][32]
   int mel5_nslots = 0, mel5_k = 0;
   bool mel5_ok = false;
+  int* d_tile_ctr = nullptr;       // work counter of fe_frame5_kernel
   // per-run scratch (capacity in utterances)
   int cap_utt = 0;
   int64_t* h_stage = nullptr;  // pinned [5*(cap+1)]: sample_off, frame_off, tile_off, tile2_off, vad order

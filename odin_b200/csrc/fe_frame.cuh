@@ -50,6 +50,8 @@ struct FrameArgs {
   const uint32_t* mel5_flags;// [32] bit j: a mel centre lies between bins j and j + 1 of the lane's chunk | first slot << 16
   const uint16_t* mel5_refs; // [rounds][K][32] partial-sum slots of filter 32 round + lane (padded with the zero slot)
   int mel5_nslots, mel5_k;   // slots written per pair (the zero slot is index nslots); refs per filter
+  int64_t n_samples;         // length of the whole PCM buffer (bounds of the 16-byte async copies)
+  int* tile_ctr;             // zeroed per launch: the next tile to hand out (fe_frame5_kernel)
 };
 
 // PCM tile -> shared memory with DC removal and pre-emphasis fused (speech.py:472-473, signal.py:955-967);

@@ -179,27 +179,117 @@ __device__ __forceinline__ float* stage_pcm5(float* __restrict__ sbase, const PC
   return sbase + mis;
 }
 
+// ---- per-warp staging of one PASS (the 2 * NP frames a warp transforms together) --------------------------------
+// What a lane needs to know about a tile of FT frames (a tile never crosses an utterance).
+struct F5Tile {
+  int u;
+  int64_t s0, n_u, fbase;
+  int t0, nf;
+  float mean;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem)
+               : "memory");
+}
+
+// int16 PCM: the raw samples of a pass -- one sample before its first frame (pre-emphasis) up to the end of its last
+// frame -- are fetched by the warp with 16-byte asynchronous copies while it still computes the PREVIOUS pass;
+// chunks that stick out of the PCM buffer are filled sample by sample.  raw[j] = buffer sample (s0 + g0 - 1 - mis + j),
+// g0 = (t0 + f0) * hop - pad the utterance index of the pass' first sample, mis = 0..7 the 16-byte misalignment.
+__device__ __forceinline__ int f5_raw_mis(const int16_t* pcm, const F5Tile& t, int f0, int hop, int pad) {
+  return (int)((reinterpret_cast<uintptr_t>(pcm + t.s0 + ((int64_t)(t.t0 + f0) * hop - pad - 1)) >> 1) & 7);
+}
+__device__ __forceinline__ void f5_issue_raw(int16_t* raw, const int16_t* __restrict__ pcm, int64_t n_samples,
+                                             const F5Tile& t, int f0, int fl, int L, int hop, int pad, int lane) {
+  const int mis = f5_raw_mis(pcm, t, f0, hop, pad);
+  const int64_t e0 = t.s0 + ((int64_t)(t.t0 + f0) * hop - pad - 1) - mis;   // buffer index of raw[0]: 16-byte aligned address
+  const int nch = ((fl - 1) * hop + L + 1 + mis + 7) >> 3;
+  for (int c = lane; c < nch; c += 32) {
+    const int64_t ea = e0 + 8 * c;
+    if (ea >= 0 && ea + 8 <= n_samples) {
+      cp_async16(raw + 8 * c, pcm + ea);
+    } else {
+      for (int e = 0; e < 8; ++e) raw[8 * c + e] = (ea + e >= 0 && ea + e < n_samples) ? pcm[ea + e] : (int16_t)0;
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+// raw -> dst (float32, DC removed, pre-emphasised; speech.py:472-473, signal.py:955-967: two roundings per stage;
+// zeros in the virtual padding).  Four outputs per lane and trip, one 16-byte store; a pass inside its utterance
+// takes the path without bounds tests.
+__device__ __forceinline__ void f5_convert_raw(float* __restrict__ dst, const int16_t* __restrict__ raw, int mis,
+                                               const F5Tile& t, int f0, int fl, int L, int hop, int pad, float coef, int lane) {
+  const int cnt = (fl - 1) * hop + L;
+  const int64_t g0 = (int64_t)(t.t0 + f0) * hop - pad;   // utterance index of output 0
+  const int16_t* __restrict__ r0 = raw + mis;             // r0[o] = sample g0 + o - 1
+  const float mean = t.mean;
+  const bool interior = g0 >= 1 && g0 + cnt <= t.n_u;
+  for (int c = lane; 4 * c < cnt; c += 32) {
+    float y[4];
+    if (interior) {
+      float x[5];
+#pragma unroll
+      for (int e = 0; e < 5; ++e) x[e] = __fsub_rn((float)r0[4 * c + e], mean);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) y[e] = (coef != 0.f) ? __fsub_rn(x[e + 1], __fmul_rn(coef, x[e])) : x[e + 1];
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int64_t g = g0 + 4 * c + e;
+        const bool in = g >= 0 && g < t.n_u;
+        float cur = in ? __fsub_rn((float)r0[4 * c + e + 1], mean) : 0.f;
+        if (in && coef != 0.f && g > 0) cur = __fsub_rn(cur, __fmul_rn(coef, __fsub_rn((float)r0[4 * c + e], mean)));
+        y[e] = cur;
+      }
+    }
+    *reinterpret_cast<float4*>(dst + 4 * c) = make_float4(y[0], y[1], y[2], y[3]);
+  }
+}
+// float32 PCM: straight from global memory (no look-ahead; the rare input type)
+__device__ __forceinline__ void f5_convert_f32(float* __restrict__ dst, const float* __restrict__ pu, const F5Tile& t, int f0,
+                                               int fl, int L, int hop, int pad, float coef, int lane) {
+  const int cnt = (fl - 1) * hop + L;
+  const int64_t g0 = (int64_t)(t.t0 + f0) * hop - pad;
+  const float mean = t.mean;
+  for (int o = lane; o < cnt; o += 32) {
+    const int64_t g = g0 + o;
+    const bool in = g >= 0 && g < t.n_u;
+    float cur = in ? __fsub_rn(pu[in ? g : 0], mean) : 0.f;
+    if (in && coef != 0.f && g > 0) cur = __fsub_rn(cur, __fmul_rn(coef, __fsub_rn(pu[g - 1], mean)));
+    dst[o] = cur;
+  }
+}
+
 // NZ live rows in step A (rows r >= NZ are zero padding); EXACT: (NZ - 1) * G <= L, so only the last live row
 // needs the i < L test.
+//
+// Every WARP runs on its own: it owns a contiguous range of 32-frame tiles, walks their passes (2 * NP frames
+// each), and there is no block-level barrier after the table fill.  Per pass: the raw int16 samples were fetched
+// into a per-warp buffer by cp.async during the previous pass; they are converted (DC, pre-emphasis) into the
+// warp's pair region as float32, the next pass' samples are requested, and the region is then reused -- as before --
+// as exchange tile, natural-order spectrum and partial-sum slots.  (The block-wide staging of the first version
+// cost two barriers per tile and left all eight warps waiting for HBM together: 17 % of the stall samples.)
 template <int N, typename PCM, int NZ, bool EXACT>
 __global__ void __launch_bounds__(FE_THREADS, 2) fe_frame5_kernel(FrameArgs a) {
   constexpr int G = N / 32, NP = 32 / G, RS = G + 1, REG = f5_region<N>(), NK = N / 64;
+  constexpr bool ASYNC = sizeof(PCM) == 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // layout: win64 [L] | pair regions [FE_WARPS][NP * REG] float2 | tw4 [N] float2 | mel weights [NK][32] float2 |
-  //         refs [rounds][K][32] u16 | sbuf [(FT-1)*hop + L + 8]
+  //         refs [rounds][K/4][32] 4 x u16 | raw int16 [FE_WARPS][2][rawlen] (int16 PCM)
   double* win64 = reinterpret_cast<double*>(smem_raw);
   u64* bufs = reinterpret_cast<u64*>(win64 + a.L + (a.L & 1));
   u64* tw4 = bufs + FE_WARPS * NP * REG;
   float2* melw = reinterpret_cast<float2*>(tw4 + N);
   uint16_t* refs = reinterpret_cast<uint16_t*>(melw + NK * 32);
   const int rounds = (a.n_mels + 31) >> 5, K = a.mel5_k;
-  float* sbuf = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(refs + rounds * K * 32) + 15) & ~uintptr_t(15));
-  __shared__ int cta_max;
-  __shared__ double s_en[FT];   // frame energies of the tile; their logs are taken by one warp at the end
+  const int L = a.L, hop = a.hop;
+  const int rawlen = ((2 * NP - 1) * hop + L + 1 + 8 + 7) & ~7;   // int16 per buffer (multiple of 8: 16-byte slots)
+  int16_t* raws = reinterpret_cast<int16_t*>((reinterpret_cast<uintptr_t>(refs + rounds * K * 32) + 15) & ~uintptr_t(15));
+  __shared__ double s_en[FE_WARPS][FT];   // frame energies of a warp's tile; logs taken by the warp at the tile's end
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane / G, l = lane % G;
-  const int L = a.L, hop = a.hop;
   for (int i = tid; i < L; i += FE_THREADS) win64[i] = a.win64[i];
   for (int i = tid; i < N; i += FE_THREADS) tw4[i] = reinterpret_cast<const u64*>(a.tw)[i];
   for (int i = tid; i < NK * 32; i += FE_THREADS) melw[i] = a.mel5_w[i];
@@ -208,59 +298,77 @@ __global__ void __launch_bounds__(FE_THREADS, 2) fe_frame5_kernel(FrameArgs a) {
   const int zero_slot = a.mel5_nslots;
   const float win_c = a.win_c;
   u64* wbuf = bufs + warp * (NP * REG);
+  float* stile = reinterpret_cast<float*>(wbuf);           // float32 samples of the pass (before the region is reused)
+  int16_t* raw = raws + warp * 2 * rawlen;
   const PCM* __restrict__ pcm = reinterpret_cast<const PCM*>(a.pcm);
   const float coef = a.preemph;
+  __syncthreads();   // tables are in place: from here on the warps never meet again
 
-  // contiguous range of tiles per CTA: one binary search, then the utterance index walks forward
-  const int64_t per = (a.n_tiles + gridDim.x - 1) / gridDim.x;
-  const int64_t tile_lo = per * blockIdx.x, tile_hi = min(a.n_tiles, tile_lo + per);
-  if (tile_lo >= tile_hi) return;
-  int u = find_segment(a.tile_off, a.n_utt, tile_lo);
-  int64_t u_end = a.tile_off[u + 1];
-  // The logs of a tile's frame energies (fp64 log: a long dependent sequence on one lane per frame) are taken
-  // while the NEXT tile is being staged, between its two barriers, where they overlap the global-memory latency
-  // of the staging loads instead of extending the tile by a serial tail.
-  float* en_dst = nullptr;
-  int en_n = 0;
-  auto flush_energies = [&]() {
-    if (tid < en_n) {
-      double e = s_en[tid];
-      if (e == 0.0) e = (double)FLT_EPSILON;  // signal.py:1436
-      en_dst[tid] = (float)log(e);
-    }
+  // Tiles are handed out one at a time from a global counter (lane 0 draws, the warp follows): with ~9 tiles per warp
+  // a static split leaves 8 % of the warps idle through the last tile.  A warp always holds the tile it works on and
+  // the one after it, so that the next tile's first samples can be requested a pass ahead.
+  auto draw = [&]() -> int64_t {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(a.tile_ctr, 1);
+    return (int64_t)__shfl_sync(0xffffffffu, t, 0);
   };
-  for (int64_t tile = tile_lo; tile < tile_hi; ++tile) {
-    while (tile >= u_end) { ++u; u_end = a.tile_off[u + 1]; }
-    const int64_t s0 = a.sample_off[u];
-    const int64_t n_u = a.sample_off[u + 1] - s0;
-    const int64_t fbase = a.frame_off[u];
-    const int T_u = (int)(a.frame_off[u + 1] - fbase);
-    const int t0 = (int)(tile - a.tile_off[u]) * FT;
-    const int nf = min(FT, T_u - t0);
-    float mean = 0.f;
+  auto tile_info = [&](int64_t tile) -> F5Tile {
+    const int u = find_segment(a.tile_off, a.n_utt, tile);
+    F5Tile t;
+    t.u = u;
+    t.s0 = a.sample_off[u];
+    t.n_u = a.sample_off[u + 1] - t.s0;
+    t.fbase = a.frame_off[u];
+    t.t0 = (int)(tile - a.tile_off[u]) * FT;
+    t.nf = min(FT, (int)(a.frame_off[u + 1] - t.fbase) - t.t0);
+    t.mean = 0.f;
     if (a.remove_dc) {
       double s = (sizeof(PCM) == 2) ? (double)reinterpret_cast<const long long*>(a.dcsum)[u] : a.dcsum[u];
-      mean = (float)(s / (double)n_u);
+      t.mean = (float)(s / (double)t.n_u);
     }
-    __syncthreads();  // previous tile done with sbuf / cta_max / s_en (and the table fill on the first trip)
-    if (tid == 0) cta_max = float_to_ordered(-FLT_MAX);
-    const float* stile = stage_pcm5<PCM>(sbuf, pcm + s0, n_u, (int64_t)t0 * hop, (nf - 1) * hop + L, mean, coef, a.pad, tid,
-                                         tile + 1 < tile_hi ? FT * hop : 0);
-    flush_energies();
-    __syncthreads();
-    if (a.energy != nullptr) { en_dst = a.energy + fbase + t0; en_n = nf; }
+    return t;
+  };
+  int64_t tile = draw();
+  if (tile >= a.n_tiles) return;
+  int64_t tile_next = draw();
+  F5Tile cur = tile_info(tile);
+  int f0 = 0, b = 0;                         // first frame of the pass inside its tile; raw buffer in use
+  if constexpr (ASYNC)
+    f5_issue_raw(raw, reinterpret_cast<const int16_t*>(pcm), a.n_samples, cur, 0, min(2 * NP, cur.nf), L, hop, a.pad, lane);
+  while (true) {
+    const int nf = cur.nf;
+    const int fl = min(2 * NP, nf - f0);     // frames of this pass
+    // the pass after this one: same tile, or the first of the next tile
+    F5Tile nxt = cur;
+    int nf0 = f0 + 2 * NP;
+    bool has_next = true;
+    if (nf0 >= nf) {
+      nf0 = 0;
+      if (tile_next < a.n_tiles) nxt = tile_info(tile_next); else has_next = false;
+    }
+    if constexpr (ASYNC) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();   // every lane's copies of this pass have landed; the previous pass is done with the region
+      f5_convert_raw(stile, raw + b * rawlen, f5_raw_mis(reinterpret_cast<const int16_t*>(pcm), cur, f0, hop, a.pad), cur, f0, fl,
+                     L, hop, a.pad, coef, lane);
+      if (has_next)
+        f5_issue_raw(raw + (b ^ 1) * rawlen, reinterpret_cast<const int16_t*>(pcm), a.n_samples, nxt, nf0,
+                     min(2 * NP, nxt.nf - nf0), L, hop, a.pad, lane);
+    } else {
+      __syncwarp();
+      f5_convert_f32(stile, reinterpret_cast<const float*>(pcm) + cur.s0, cur, f0, fl, L, hop, a.pad, coef, lane);
+    }
+    __syncwarp();
 
     float wmax = -FLT_MAX;
-    const int npairs = (nf + 1) >> 1;
-    for (int base = warp * NP; base < npairs; base += FE_WARPS * NP) {
+    {
       u64* reg = wbuf + g * REG;
       // ---------------- step A: load + window + energy, 32-point DFT over r, twiddle
       {
-        const int pr = base + g;
-        const int fA = 2 * pr, fB = fA + 1;
-        // frames past the end of the tile are computed on the tile's last frame and never stored
-        const float* sA = stile + min(fA, nf - 1) * hop + l;
-        const float* sB = stile + min(fB, nf - 1) * hop + l;
+        const int fA = f0 + 2 * g, fB = fA + 1;
+        // frames past the end of the tile are computed on the pass' last frame and never stored
+        const float* sA = stile + min(2 * g, fl - 1) * hop + l;
+        const float* sB = stile + min(2 * g + 1, fl - 1) * hop + l;
         const double* wp = win64 + l;
         double eA = 0.0, eB = 0.0;
         u64 v[32];
@@ -288,8 +396,8 @@ __global__ void __launch_bounds__(FE_THREADS, 2) fe_frame5_kernel(FrameArgs a) {
             eB += __shfl_xor_sync(0xffffffffu, eB, o);
           }
           if (l == 0 && fA < nf) {
-            s_en[fA] = eA;
-            if (fB < nf) s_en[fB] = eB;
+            s_en[warp][fA] = eA;
+            if (fB < nf) s_en[warp][fB] = eB;
           }
         }
         Dft5<32, NZ>::run(v);
@@ -298,7 +406,7 @@ __global__ void __launch_bounds__(FE_THREADS, 2) fe_frame5_kernel(FrameArgs a) {
           const u64 w = tw4[k1 * G + l];
           v[k1] = cmulw(v[k1], lo32(w), hi32(w));
         }
-        __syncwarp();  // the previous pass' mel stage has finished reading its slots in the regions
+        __syncwarp();  // every lane has its samples in registers: the region becomes the exchange tile
 #pragma unroll
         for (int k1 = 0; k1 < 32; ++k1) reg[k1 * RS + l] = v[k1];
       }
@@ -327,7 +435,7 @@ __global__ void __launch_bounds__(FE_THREADS, 2) fe_frame5_kernel(FrameArgs a) {
       // ---------------- split + |.|^2 + mel + dB, the whole warp on one pair at a time
 #pragma unroll 1
       for (int pp = 0; pp < NP; ++pp) {
-        const int fA = 2 * (base + pp), fB = fA + 1;
+        const int fA = f0 + 2 * pp, fB = fA + 1;
         if (fA >= nf) break;
         const bool hasB = fB < nf;
         u64* buf = wbuf + pp * REG;
@@ -357,7 +465,7 @@ __global__ void __launch_bounds__(FE_THREADS, 2) fe_frame5_kernel(FrameArgs a) {
           }
         }
         __syncwarp();
-        float* rowA = a.mspec + (fbase + t0 + fA) * a.n_mels;
+        float* rowA = a.mspec + (cur.fbase + cur.t0 + fA) * a.n_mels;
         for (int r = 0; r < rounds; ++r) {
           // the filter's slots in bin order, four 16-bit indices per word: four independent loads, then a tree
           const u64* rp = reinterpret_cast<const u64*>(refs) + r * (K >> 2) * 32 + lane;
@@ -381,22 +489,37 @@ __global__ void __launch_bounds__(FE_THREADS, 2) fe_frame5_kernel(FrameArgs a) {
           }
         }
       }
+      wmax = warp_max(wmax);
+      if (lane == 0) atomicMax(a.umax + cur.u, float_to_ordered(wmax));
     }
-    wmax = warp_max(wmax);
-    if (lane == 0) atomicMax(&cta_max, float_to_ordered(wmax));
-    __syncthreads();
-    if (tid == 0) atomicMax(a.umax + u, cta_max);
+    if (f0 + 2 * NP >= nf && a.energy != nullptr) {   // last pass of the tile: the logs of its frame energies
+      __syncwarp();
+      if (lane < nf) {
+        double e = s_en[warp][lane];
+        if (e == 0.0) e = (double)FLT_EPSILON;  // signal.py:1436
+        a.energy[cur.fbase + cur.t0 + lane] = (float)log(e);
+      }
+      __syncwarp();
+    }
+    if (!has_next) break;
+    if (nf0 == 0) { tile = tile_next; tile_next = draw(); }
+    cur = nxt;
+    f0 = nf0;
+    b ^= 1;
   }
-  flush_energies();   // (the last tile's s_en is complete: the __syncthreads above)
 }
 
 template <int N, typename PCM, int NZ, bool EXACT>
 static int launch5(const FrameArgs& a, cudaStream_t st) {
   constexpr int NP = 32 / (N / 32), NK = N / 64;
+  const size_t rawlen = ((size_t)(2 * NP - 1) * a.hop + a.L + 1 + 8 + 7) & ~size_t(7);
   size_t smem = (size_t)(a.L + (a.L & 1)) * sizeof(double) + (size_t)FE_WARPS * NP * f5_region<N>() * sizeof(float2) +
                 (size_t)N * sizeof(float2) + (size_t)NK * 32 * sizeof(float2) +
-                (size_t)((a.n_mels + 31) / 32) * a.mel5_k * 32 * sizeof(uint16_t) +
-                16 + (size_t)((FT - 1) * a.hop + a.L + 8 + 4) * sizeof(float);
+                (size_t)((a.n_mels + 31) / 32) * a.mel5_k * 32 * sizeof(uint16_t) + 16 +
+                (sizeof(PCM) == 2 ? (size_t)FE_WARPS * 2 * rawlen * sizeof(int16_t) : 0);
+  // the float32 samples of a pass are staged in the warp's pair region before it becomes the exchange tile
+  if (((size_t)(2 * NP - 1) * a.hop + a.L + 4) * sizeof(float) > (size_t)NP * f5_region<N>() * sizeof(float2))
+    return set_error(ODIN_EINVAL, "frame kernel: hop %d / frame %d too long for the pass staging", a.hop, a.L);
   if (smem > 227 * 1024) return set_error(ODIN_EINVAL, "frame kernel needs %zu B smem (hop too large)", smem);
   auto k = fe_frame5_kernel<N, PCM, NZ, EXACT>;
   ODIN_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

