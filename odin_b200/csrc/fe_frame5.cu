@@ -270,36 +270,39 @@ __device__ __forceinline__ void f5_convert_f32(float* __restrict__ dst, const fl
 // warp's pair region as float32, the next pass' samples are requested, and the region is then reused -- as before --
 // as exchange tile, natural-order spectrum and partial-sum slots.  (The block-wide staging of the first version
 // cost two barriers per tile and left all eight warps waiting for HBM together: 17 % of the stall samples.)
+constexpr int F5_MAX_WARPS = 20;          // one CTA per SM: 5 warps per scheduler at 96 registers (a sixth would leave 80 and spill)
+constexpr int F5_MAX_THREADS = 32 * F5_MAX_WARPS;
+
 template <int N, typename PCM, int NZ, bool EXACT>
-__global__ void __launch_bounds__(FE_THREADS, 2) fe_frame5_kernel(FrameArgs a) {
+__global__ void __launch_bounds__(F5_MAX_THREADS, 1) fe_frame5_kernel(FrameArgs a) {
   constexpr int G = N / 32, NP = 32 / G, RS = G + 1, REG = f5_region<N>(), NK = N / 64;
   constexpr bool ASYNC = sizeof(PCM) == 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: win64 [L] | pair regions [FE_WARPS][NP * REG] float2 | tw4 [N] float2 | mel weights [NK][32] float2 |
-  //         refs [rounds][K/4][32] 4 x u16 | raw int16 [FE_WARPS][2][rawlen] (int16 PCM)
+  // layout: win64 [L] | pair regions [warps][NP * REG] float2 | tw4 [N] float2 | mel weights [NK][32] float2 |
+  //         refs [rounds][K/4][32] 4 x u16 | raw int16 [warps][rawlen] (int16 PCM)
   double* win64 = reinterpret_cast<double*>(smem_raw);
   u64* bufs = reinterpret_cast<u64*>(win64 + a.L + (a.L & 1));
-  u64* tw4 = bufs + FE_WARPS * NP * REG;
+  const int nthr = blockDim.x, nwarps = nthr >> 5;
+  u64* tw4 = bufs + nwarps * NP * REG;
   float2* melw = reinterpret_cast<float2*>(tw4 + N);
   uint16_t* refs = reinterpret_cast<uint16_t*>(melw + NK * 32);
   const int rounds = (a.n_mels + 31) >> 5, K = a.mel5_k;
   const int L = a.L, hop = a.hop;
   const int rawlen = ((2 * NP - 1) * hop + L + 1 + 8 + 7) & ~7;   // int16 per buffer (multiple of 8: 16-byte slots)
   int16_t* raws = reinterpret_cast<int16_t*>((reinterpret_cast<uintptr_t>(refs + rounds * K * 32) + 15) & ~uintptr_t(15));
-  __shared__ double s_en[FE_WARPS][FT];   // frame energies of a warp's tile; logs taken by the warp at the tile's end
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane / G, l = lane % G;
-  for (int i = tid; i < L; i += FE_THREADS) win64[i] = a.win64[i];
-  for (int i = tid; i < N; i += FE_THREADS) tw4[i] = reinterpret_cast<const u64*>(a.tw)[i];
-  for (int i = tid; i < NK * 32; i += FE_THREADS) melw[i] = a.mel5_w[i];
-  for (int i = tid; i < rounds * K * 32; i += FE_THREADS) refs[i] = a.mel5_refs[i];
+  for (int i = tid; i < L; i += nthr) win64[i] = a.win64[i];
+  for (int i = tid; i < N; i += nthr) tw4[i] = reinterpret_cast<const u64*>(a.tw)[i];
+  for (int i = tid; i < NK * 32; i += nthr) melw[i] = a.mel5_w[i];
+  for (int i = tid; i < rounds * K * 32; i += nthr) refs[i] = a.mel5_refs[i];
   const uint32_t mflags = a.mel5_flags[lane];   // bits 0..NK-2: a centre lies behind bin j; bits 16..: the lane's first slot
   const int zero_slot = a.mel5_nslots;
   const float win_c = a.win_c;
   u64* wbuf = bufs + warp * (NP * REG);
   float* stile = reinterpret_cast<float*>(wbuf);           // float32 samples of the pass (before the region is reused)
-  int16_t* raw = raws + warp * 2 * rawlen;
+  int16_t* raw = raws + warp * rawlen;
   const PCM* __restrict__ pcm = reinterpret_cast<const PCM*>(a.pcm);
   const float coef = a.preemph;
   __syncthreads();   // tables are in place: from here on the warps never meet again
@@ -332,7 +335,8 @@ __global__ void __launch_bounds__(FE_THREADS, 2) fe_frame5_kernel(FrameArgs a) {
   if (tile >= a.n_tiles) return;
   int64_t tile_next = draw();
   F5Tile cur = tile_info(tile);
-  int f0 = 0, b = 0;                         // first frame of the pass inside its tile; raw buffer in use
+  int f0 = 0;                                // first frame of the pass inside its tile
+  double my_e = 0.0;                         // energy of frame `lane` of the current tile
   if constexpr (ASYNC)
     f5_issue_raw(raw, reinterpret_cast<const int16_t*>(pcm), a.n_samples, cur, 0, min(2 * NP, cur.nf), L, hop, a.pad, lane);
   while (true) {
@@ -349,16 +353,17 @@ __global__ void __launch_bounds__(FE_THREADS, 2) fe_frame5_kernel(FrameArgs a) {
     if constexpr (ASYNC) {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncwarp();   // every lane's copies of this pass have landed; the previous pass is done with the region
-      f5_convert_raw(stile, raw + b * rawlen, f5_raw_mis(reinterpret_cast<const int16_t*>(pcm), cur, f0, hop, a.pad), cur, f0, fl,
-                     L, hop, a.pad, coef, lane);
+      f5_convert_raw(stile, raw, f5_raw_mis(reinterpret_cast<const int16_t*>(pcm), cur, f0, hop, a.pad), cur, f0, fl, L, hop,
+                     a.pad, coef, lane);
+      __syncwarp();   // the float32 samples are in place and the raw buffer is free: it takes the next pass' samples
       if (has_next)
-        f5_issue_raw(raw + (b ^ 1) * rawlen, reinterpret_cast<const int16_t*>(pcm), a.n_samples, nxt, nf0,
-                     min(2 * NP, nxt.nf - nf0), L, hop, a.pad, lane);
+        f5_issue_raw(raw, reinterpret_cast<const int16_t*>(pcm), a.n_samples, nxt, nf0, min(2 * NP, nxt.nf - nf0), L, hop,
+                     a.pad, lane);
     } else {
       __syncwarp();
       f5_convert_f32(stile, reinterpret_cast<const float*>(pcm) + cur.s0, cur, f0, fl, L, hop, a.pad, coef, lane);
+      __syncwarp();
     }
-    __syncwarp();
 
     float wmax = -FLT_MAX;
     {
@@ -395,10 +400,12 @@ __global__ void __launch_bounds__(FE_THREADS, 2) fe_frame5_kernel(FrameArgs a) {
             eA += __shfl_xor_sync(0xffffffffu, eA, o);
             eB += __shfl_xor_sync(0xffffffffu, eB, o);
           }
-          if (l == 0 && fA < nf) {
-            s_en[warp][fA] = eA;
-            if (fB < nf) s_en[warp][fB] = eB;
-          }
+          // lane j of the warp keeps the energy of frame j of the tile until the tile's last pass (fp64 log there):
+          // frame f0 + i of this pass sits in every lane of group i / 2 as eA (i even) or eB (i odd)
+          const int i = lane - f0;
+          const int src = ((i >> 1) * G) & 31;
+          const double ea = __shfl_sync(0xffffffffu, eA, src), eb = __shfl_sync(0xffffffffu, eB, src);
+          if (i >= 0 && i < 2 * NP) my_e = (i & 1) ? eb : ea;
         }
         Dft5<32, NZ>::run(v);
 #pragma unroll
@@ -493,19 +500,16 @@ __global__ void __launch_bounds__(FE_THREADS, 2) fe_frame5_kernel(FrameArgs a) {
       if (lane == 0) atomicMax(a.umax + cur.u, float_to_ordered(wmax));
     }
     if (f0 + 2 * NP >= nf && a.energy != nullptr) {   // last pass of the tile: the logs of its frame energies
-      __syncwarp();
       if (lane < nf) {
-        double e = s_en[warp][lane];
+        double e = my_e;
         if (e == 0.0) e = (double)FLT_EPSILON;  // signal.py:1436
         a.energy[cur.fbase + cur.t0 + lane] = (float)log(e);
       }
-      __syncwarp();
     }
     if (!has_next) break;
     if (nf0 == 0) { tile = tile_next; tile_next = draw(); }
     cur = nxt;
     f0 = nf0;
-    b ^= 1;
   }
 }
 
@@ -513,19 +517,20 @@ template <int N, typename PCM, int NZ, bool EXACT>
 static int launch5(const FrameArgs& a, cudaStream_t st) {
   constexpr int NP = 32 / (N / 32), NK = N / 64;
   const size_t rawlen = ((size_t)(2 * NP - 1) * a.hop + a.L + 1 + 8 + 7) & ~size_t(7);
-  size_t smem = (size_t)(a.L + (a.L & 1)) * sizeof(double) + (size_t)FE_WARPS * NP * f5_region<N>() * sizeof(float2) +
-                (size_t)N * sizeof(float2) + (size_t)NK * 32 * sizeof(float2) +
-                (size_t)((a.n_mels + 31) / 32) * a.mel5_k * 32 * sizeof(uint16_t) + 16 +
-                (sizeof(PCM) == 2 ? (size_t)FE_WARPS * 2 * rawlen * sizeof(int16_t) : 0);
+  const size_t fixed = (size_t)(a.L + (a.L & 1)) * sizeof(double) + (size_t)N * sizeof(float2) + (size_t)NK * 32 * sizeof(float2) +
+                       (size_t)((a.n_mels + 31) / 32) * a.mel5_k * 32 * sizeof(uint16_t) + 16;
+  const size_t per_warp = (size_t)NP * f5_region<N>() * sizeof(float2) + (sizeof(PCM) == 2 ? rawlen * sizeof(int16_t) : 0);
   // the float32 samples of a pass are staged in the warp's pair region before it becomes the exchange tile
   if (((size_t)(2 * NP - 1) * a.hop + a.L + 4) * sizeof(float) > (size_t)NP * f5_region<N>() * sizeof(float2))
     return set_error(ODIN_EINVAL, "frame kernel: hop %d / frame %d too long for the pass staging", a.hop, a.L);
-  if (smem > 227 * 1024) return set_error(ODIN_EINVAL, "frame kernel needs %zu B smem (hop too large)", smem);
+  // ONE CTA per SM with as many independent warps as its shared memory holds (the tables are stored once)
+  const int warps = (int)std::min<size_t>(F5_MAX_WARPS, (227 * 1024 - fixed) / per_warp);
+  if (warps < 1) return set_error(ODIN_EINVAL, "frame kernel: tables of %zu B leave no room for a warp", fixed);
+  const size_t smem = fixed + warps * per_warp;
   auto k = fe_frame5_kernel<N, PCM, NZ, EXACT>;
   ODIN_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2, (227 * 1024) / (smem + 1024)));
-  int64_t grid = std::min<int64_t>(a.n_tiles, (int64_t)sm_count() * per_sm);
-  k<<<(unsigned)grid, FE_THREADS, smem, st>>>(a);
+  const int64_t grid = std::min<int64_t>(ceil_div<int64_t>(a.n_tiles, warps), (int64_t)sm_count());
+  k<<<(unsigned)grid, 32 * warps, smem, st>>>(a);
   ODIN_LAUNCH_CHECK("fe_frame5_kernel");
   return ODIN_OK;
 }
