@@ -377,9 +377,9 @@ def mfcc_leg(torch, args, rank, world, dist, peaks, do_cpu):
                    "hbm": {"achieved": MFCC_BYTES_PER_FRAME * T / step_s / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                            "frac": MFCC_BYTES_PER_FRAME * T / step_s / 1e9 / peaks["hbm_gbs"],
                            "algorithmic_bytes_per_frame": MFCC_BYTES_PER_FRAME},
-                   # dram__bytes of the frame kernel from the committed capture (profiles/r02_fe_frame5_keymetrics.csv:
-                   # 224.0 MB read + 186.4 MB written per 696 132-frame launch = PCM in, log-mel + energy out), per frame
-                   "traffic": 410.4e6 / 696132 * T},
+                   # dram__bytes of the frame kernel from the committed capture (profiles/r02_fe_frame5_ncu_keymetrics.csv:
+                   # 223.2 MB read + 185.3 MB written per 696 132-frame launch = PCM in, log-mel + energy out), per frame
+                   "traffic": 408.5e6 / 696132 * T},
       "e2e": {"value": total_T / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d * world,
               "d2h_bytes_per_step": e2e["f32"][1] * world,
               "call": "FusedSpeechFrontEnd.run_host_packed (%d chunks), float32 features + sad to pinned host memory" % n_chunks},

@@ -21,11 +21,13 @@
 //     cross a centre and hands the second over.  Filter m adds its <= K slots (K = 2..4).  This replaces the
 //     table walk of fe_frame4_kernel (random shared-memory reads: 25 % of its instructions and all of its bank
 //     conflicts).
-//   * the PCM staging copy takes 4 samples per thread with a bounds-free interior path (stage_pcm5).
+//   * every warp runs on its own (no block barrier after the table fill): the raw int16 samples of its next pass arrive by
+//     cp.async while it computes, are converted (DC removal, pre-emphasis) into its pair region, and tiles are drawn
+//     from a global counter; one CTA of 20 warps per SM stores the tables once.
 //   * the rows of step A that are zero padding (L <= n_fft / 2 and the tail of the last live row) are template
 //     parameters: no predicated-off instructions are issued for them.
 //
-// Shared memory per warp is ONE region per frame pair, used three times: exchange tile [k1][l] of the four-step
+// Shared memory per warp is ONE region per frame pair, used four times: float32 samples of the pass -> exchange tile [k1][l] of the four-step
 // FFT -> natural-order spectrum (one pad element per lane chunk: conflict-free for the contiguous reads) ->
 // partial-sum slots of the mel projection (the spectrum is pulled into registers first).
 #include <float.h>
@@ -99,84 +101,6 @@ template <int N> constexpr int f5_region() {
   constexpr int tile = 32 * (N / 32 + 1), nat = N + 64 + 1;
   constexpr int r = (tile > nat ? tile : nat);
   return N == 256 ? ((r + 15) / 16) * 16 + 8 : (r + 1) & ~1;
-}
-
-// PCM tile -> shared memory with DC removal and pre-emphasis fused: the arithmetic of stage_pcm (fe_frame.cuh;
-// speech.py:472-473, signal.py:955-967, two roundings per stage), arranged for this kernel: a thread takes FOUR
-// samples (8-byte loads of int16 / 16-byte loads of float32, aligned in global memory) and writes ONE 16-byte
-// shared store, so consecutive lanes fill consecutive banks (the 8-sample chunks of stage_pcm stored two 16-byte
-// words at a 32-byte lane stride: 2-way conflicts), and a chunk inside the utterance takes a path without any
-// per-sample bounds test (ncu of the first version of this kernel: the staging copy was 12 % of its
-// instructions, most of them 64-bit index compares and selects).  Returns the tile origin (sbase + 0..3).
-template <typename PCM>
-__device__ __forceinline__ float* stage_pcm5(float* __restrict__ sbase, const PCM* __restrict__ pu, int64_t n_u,
-                                             int64_t v0, int cnt, float mean, float coef, int pad, int tid, int next) {
-  using Vec = typename std::conditional<sizeof(PCM) == 2, uint2, float4>::type;   // four samples
-  const int64_t gstart = v0 - pad;   // utterance index of tile element 0 (negative inside the left padding)
-  const int mis = (int)((reinterpret_cast<uintptr_t>(pu + gstart) / sizeof(PCM)) & 3);
-  const int n_chunks = (cnt + mis + 3) >> 2;
-  const int64_t gbase = gstart - mis;                    // utterance index of chunk 0 (4-sample aligned in memory)
-  const PCM* __restrict__ pbase = pu + gbase;
-  // chunks [c_lo, c_hi) lie inside the utterance with a predecessor sample: no bounds tests
-  const int c_lo = (int)max((int64_t)0, (4 - gbase) >> 2), c_hi = (int)min((int64_t)n_chunks, (n_u - gbase) >> 2);
-  constexpr int U = 4;   // chunks in flight per thread: the loads of a batch are issued before the first use
-  for (int c0 = tid; c0 < n_chunks; c0 += U * FE_THREADS) {
-    Vec raw[U];
-    PCM prv[U];
-#pragma unroll
-    for (int q = 0; q < U; ++q) {
-      const int c = c0 + q * FE_THREADS;
-      if (c >= c_lo && c < c_hi) {
-        raw[q] = *reinterpret_cast<const Vec*>(pbase + 4 * c);
-        prv[q] = pbase[4 * c - 1];
-        // the CTA's next tile reads the samples `next` further on (same utterance, or the head of the following
-        // one): pull them into L2 now, so that its staging loads wait for L2 instead of HBM
-        if ((c & 7) == 0) asm volatile("prefetch.global.L2 [%0];" :: "l"(pbase + 4 * c + next));
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < U; ++q) {
-      const int c = c0 + q * FE_THREADS;
-      if (c >= n_chunks) break;
-      float y[4];
-      if (c >= c_lo && c < c_hi) {
-        float x[4];
-        if constexpr (sizeof(PCM) == 2) {
-          union { uint2 u; short e[4]; } r;
-          r.u = *reinterpret_cast<const uint2*>(&raw[q]);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) x[e] = __fsub_rn((float)r.e[e], mean);
-        } else {
-          const float4 r = *reinterpret_cast<const float4*>(&raw[q]);
-          x[0] = __fsub_rn(r.x, mean); x[1] = __fsub_rn(r.y, mean);
-          x[2] = __fsub_rn(r.z, mean); x[3] = __fsub_rn(r.w, mean);
-        }
-        if (coef != 0.f) {
-          y[0] = __fsub_rn(x[0], __fmul_rn(coef, __fsub_rn((float)prv[q], mean)));
-#pragma unroll
-          for (int e = 1; e < 4; ++e) y[e] = __fsub_rn(x[e], __fmul_rn(coef, x[e - 1]));
-        } else {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) y[e] = x[e];
-        }
-      } else {   // chunk touching an end of the utterance (or the virtual padding): sample by sample
-        const int64_t g0 = gbase + 4 * c;
-        float prev = (g0 >= 1 && g0 - 1 < n_u) ? __fsub_rn((float)pu[g0 - 1], mean) : 0.f;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int64_t g = g0 + e;
-          const bool in = g >= 0 && g < n_u;
-          const float x = in ? __fsub_rn((float)pu[in ? g : 0], mean) : 0.f;
-          float cur = x;
-          if (coef != 0.f && g > 0) cur = __fsub_rn(cur, __fmul_rn(coef, prev));
-          y[e] = in ? cur : 0.f;
-          prev = x;
-        }
-      }
-      *reinterpret_cast<float4*>(sbase + 4 * c) = make_float4(y[0], y[1], y[2], y[3]);
-    }
-  }
-  return sbase + mis;
 }
 
 // ---- per-warp staging of one PASS (the 2 * NP frames a warp transforms together) --------------------------------
