@@ -93,6 +93,28 @@ def measured_peaks():
   return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback")
 
 
+class PinnedArena(object):
+  """ONE pinned host allocation made at process start, carved up by the end-to-end legs (the UBM frames in float32
+  and float16, the MFCC corpus and its outputs): pinning ~20 GB takes seconds, so it is done once, not per leg."""
+
+  def __init__(self, torch, nbytes):
+    self.torch = torch
+    self.buf = torch.empty(int(nbytes) + 4096, dtype=torch.uint8, pin_memory=True)
+    self.buf.zero_()   # touch every page now
+    self.pos = 0
+
+  def reset(self):
+    self.pos = 0
+
+  def take(self, shape, dtype):
+    n = int(np.prod(shape)) * self.torch.empty((), dtype=dtype).element_size()
+    start = (self.pos + 255) & ~255
+    if start + n > self.buf.numel():
+      return self.torch.empty(shape, dtype=dtype, pin_memory=True)   # (arena too small: plain pinned tensor)
+    self.pos = start + n
+    return self.buf[start:start + n].view(dtype).view(shape)
+
+
 class ClockSampler(object):
   """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
   Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -269,7 +291,15 @@ def mfcc_cpu_baseline(seconds):
                     "%d forked workers %.0f frames/s" % (seconds, one, nw, many)}
 
 
-def mfcc_leg(torch, args, rank, world, dist, peaks, do_cpu):
+def mfcc_sizes(args, world):
+  """(hours per GPU, pinned bytes the leg wants): PCM + float32 features + sad of its corpus."""
+  hours = args.mfcc_hours / world
+  samples = hours * 3600.0 * 16000
+  frames = samples / 160.0
+  return hours, int(samples * 2 + frames * (60 * 4 + 1) * 1.02) + (1 << 20)
+
+
+def mfcc_leg(torch, args, rank, world, dist, peaks, do_cpu, arena):
   from odin_b200 import _lib, synth
   from odin_b200 import preprocessing as pp
   sr = 16000
@@ -286,7 +316,8 @@ def mfcc_leg(torch, args, rank, world, dist, peaks, do_cpu):
   n_utt = reps * len(pool)
   off = np.zeros(n_utt + 1, dtype=np.int64)
   np.cumsum(np.tile(lens, reps), out=off[1:])
-  pcm_pinned = torch.empty(int(off[-1]), dtype=torch.int16, pin_memory=True)   # the corpus in pinned host memory
+  arena.reset()
+  pcm_pinned = arena.take((int(off[-1]),), torch.int16)   # the corpus in pinned host memory
   one = np.concatenate(pool)
   view = pcm_pinned.numpy()
   for r in range(reps):
@@ -332,8 +363,11 @@ def mfcc_leg(torch, args, rank, world, dist, peaks, do_cpu):
   # (tools/fe_e2e_scale.py: 100 h at 128 or 256 chunks 158 M frames/s = 51 GB/s H2D; 50 h at 256 chunks 105 M)
   n_chunks = args.mfcc_chunks if args.mfcc_chunks > 0 else max(4, min(128, int(round(hours / 0.75))))
   e2e = {}
+  mark = arena.pos
   for tag, sd in (("f32", None), ("f16", "float16")):
-    host_out, ts = None, []
+    arena.pos = mark
+    fdt = torch.float16 if sd else torch.float32
+    host_out, ts = {"feat": arena.take((T, 60), fdt), "sad": arena.take((T,), torch.uint8)}, []
     for _ in range(3):
       torch.cuda.synchronize()
       if dist is not None:
@@ -580,6 +614,8 @@ def run_ours(args):
   lib = _lib.load()
   peaks = measured_peaks()
   N, M = args.frames, args.nmix
+  # every pinned host buffer of the end-to-end legs comes out of one allocation made now (see PinnedArena)
+  arena = PinnedArena(torch, max(N * D * 4, 0 if args.no_mfcc else mfcc_sizes(args, world)[1]))
   X, mean, sigma, w = make_ubm_and_frames(torch, N, M, 1000 + rank, "cuda")
   g = GMM(nmix=M, nmix_start=M, impl=args.kernel_impl)
   g.initialize(X)
@@ -680,12 +716,14 @@ def run_ours(args):
       times.append((time.perf_counter() - t0) / calls)
     return min(times[1:])
 
-  Xh = torch.empty((N, D), dtype=torch.float32, pin_memory=True)
+  arena.reset()
+  Xh = arena.take((N, D), torch.float32)
   Xh.copy_(X)
   e2e_s = timed_e2e(Xh)
   e2e_fit_s = timed_e2e(Xh, calls=10)
   del Xh
-  Xh16 = torch.empty((N, D), dtype=torch.float16, pin_memory=True)   # the recipes' float16 store
+  arena.reset()
+  Xh16 = arena.take((N, D), torch.float16)   # the recipes' float16 store
   Xh16.copy_(X)
   e2e16_s = timed_e2e(Xh16)
   del Xh16
@@ -764,7 +802,7 @@ def run_ours(args):
   torch.cuda.empty_cache()
   if not args.no_mfcc:
     try:
-      line["mfcc"] = mfcc_leg(torch, args, rank, world, dist, peaks, do_cpu)
+      line["mfcc"] = mfcc_leg(torch, args, rank, world, dist, peaks, do_cpu, arena)
       m = line["mfcc"]
       line["mfcc_value"], line["mfcc_e2e"] = m["value"], m["e2e"]["value"]
       line["mfcc_frac"], line["mfcc_ms_per_step"] = m["roofline"]["frac"], m["ms_per_step"]

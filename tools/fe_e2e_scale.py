@@ -17,7 +17,8 @@ fe = pipe.plan[0]
 pool = synth.utterance_batch(24, 5.0, 60.0, sr=16000, seed=4000)
 lens = np.array([len(u) for u in pool])
 one = np.concatenate(pool)
-for hours, chunk_list in ((12.5, (16, 32)), (50.0, (32, 64, 128, 256)), (100.0, (128, 256))):
+CASES = ((12.5, (16, 32)), (50.0, (32, 64, 128, 256)), (100.0, (128, 256))) if len(sys.argv) < 2 else ((float(sys.argv[1]), tuple(int(x) for x in sys.argv[2:])),)
+for hours, chunk_list in CASES:
   reps = int(round(hours * 3600 * 16000 / lens.sum()))
   off = np.zeros(reps * 24 + 1, np.int64)
   np.cumsum(np.tile(lens, reps), out=off[1:])
