@@ -2,11 +2,12 @@
 
 SURVEY 8f-4.  The model works on a few thousand i-vectors of <= 600 dimensions: the EM iteration is two
 [n_phi x n_phi] inverses per distinct class size, one [n_classes, feat_dim] x [feat_dim, n_phi] product and two
-linear solves; scoring is two small GEMMs.  That is milliseconds of LAPACK on the host and nothing the device
+linear solves; scoring is two small GEMMs.  That is a fraction of a second of LAPACK on the host and nothing the device
 would speed up, so -- unlike everything upstream of the i-vectors -- it runs in numpy / scipy float64, in the
 reference's operation order (same `solve` / `inv` / `svd` calls, same random initialisation from
-`RandomState(random_state)`), which keeps scores comparable to the reference's to rounding.  Measured on the FSDD
-recipe (`examples/fsdd_style_ivec.py`, 2 400 x 64-dim i-vectors, n_phi 32, 12 iterations): about 30 ms.
+`RandomState(random_state)`), which keeps scores comparable to the reference's to rounding.  Measured at the FSDD
+recipe's scale (2 400 x 64-dim i-vectors, n_phi 32, 12 iterations, 8 host cores): 0.25 s for fit + scoring, once per
+experiment.
 """
 import warnings
 from numbers import Number
