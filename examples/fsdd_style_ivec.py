@@ -81,8 +81,9 @@ def main(n_files=600, nmix=128, tv_dim=64):
     diff = cos[spk[:, None] != spk[None, :]].mean()
     print("mean cosine: same speaker %.3f, different speaker %.3f" % (same, diff))
     assert same > diff
-    # scoring back-end (fsdd_ivec.py:270-330): even files enrol / train, odd files are the trials
-    tr, te = np.arange(0, len(spk), 2), np.arange(1, len(spk), 2)
+    # scoring back-end (fsdd_ivec.py:270-330): alternate blocks of ten files (every speaker once) enrol / are trials
+    blk = (np.arange(len(spk)) // 10) % 2
+    tr, te = np.where(blk == 0)[0], np.where(blk == 1)[0]
     X_train, X_test = np.asarray(ivecs[tr], np.float64), np.asarray(ivecs[te], np.float64)
     for tag, scorer in (("cosine (centering + WCCN + LDA)", ml.Scorer(centering=True, wccn=True, lda=True, method="cosine")),
                         ("PLDA (n_phi %d, 12 iterations)" % (tv_dim // 2),

@@ -61,6 +61,22 @@ def main(outdir):
   zu2, fu2 = np.load(zp), np.load(fp)
   t2 = Tmatrix(4, g2, niter=1)
   t2.expectation_maximization(zu2.astype(np.float64), fu2.astype(np.float64))
+  # ---- features stay with the GPU that extracted them: FeatureProcessor shards the jobs, GMM(local_shard=True) fits on
+  # each rank's own store; the model must be the one a single process gets from the whole job list
+  from odin_b200 import preprocessing as pp
+  pool = synth.utterance_batch(12, 0.6, 1.6, sr=8000, seed=5)
+  jobs = [{"raw": pool[i], "sr": 8000, "name": "j%02d" % i} for i in range(12)]
+  chain = lambda: pp.make_pipeline([pp.AudioReader(), pp.PreEmphasis(0.97), pp.STFTExtractor(0.025, 0.010, n_fft=256, window="hamm"),
+                                    pp.PowerSpecExtractor(), pp.MelsSpecExtractor(24, fmin=64, fmax=4000), pp.MFCCsExtractor(12)])
+  fdir = os.path.join(outdir, "feats")
+  feats, idx = pp.FeatureProcessor(jobs, path=fdir, extractor=chain(), batch_utts=4).run()      # this rank's share
+  gl = GMM(nmix=4, nmix_start=1, niter=2, local_shard=True)
+  gl.fit((np.ascontiguousarray(feats["mfcc"], dtype=np.float32), idx["mfcc"]))
+  local_names = sorted(idx["mfcc"])
+  td.barrier()
+  full, idx_all = pp.FeatureProcessor(jobs, extractor=chain(), batch_utts=4, shard=False).run()  # every job, in memory
+  g_all = GMM(nmix=4, nmix_start=1, niter=2)                       # global input: the GMM takes its own share
+  g_all.fit((np.ascontiguousarray(full["mfcc"], dtype=np.float32), idx_all["mfcc"]))
   # ---- the C-ABI collective (odin_gmm_allreduce) on an NCCL communicator of its own, against torch.distributed
   import ctypes as C
   from odin_b200 import _lib
@@ -86,7 +102,8 @@ def main(outdir):
   torch.cuda.synchronize()
   ar_equal = bool(torch.equal(mine, want))
   nccl.ncclCommDestroy(comm)
-  np.savez(os.path.join(outdir, "rank%d.npz" % rank), ar_equal=ar_equal, Z1=Z1, F1=F1, S1=S1, L1=L1, Z2=Z2, F2=F2, S2=S2, L2=L2,
+  np.savez(os.path.join(outdir, "rank%d.npz" % rank), ar_equal=ar_equal, fp_names=np.array(local_names),
+           fp_mean_local=gl.mean, fp_mean_global=g_all.mean, fp_sigma_local=gl.sigma, fp_sigma_global=g_all.sigma, Z1=Z1, F1=F1, S1=S1, L1=L1, Z2=Z2, F2=F2, S2=S2, L2=L2,
            mean1=g1.mean, sigma1=g1.sigma, w1=g1.w, mean2=g2.mean, sigma2=g2.sigma, w2=g2.w,
            zu1=zu1, fu1=fu1, zu2=zu2, fu2=fu2, T1=T1, T2=t2.Tm, names=np.array(names), world=world)
   td.barrier()

@@ -55,5 +55,13 @@ def test_two_ranks_equal_one_rank(tmp_path):
   for name in ("Z2", "F2", "S2", "mean2", "sigma2", "w2", "T2", "zu2", "fu2"):
     assert np.array_equal(r[0][name], r[1][name]), name
   assert list(r[0]["names"]) == ["utt%03d" % i for i in range(40)]
+  # FeatureProcessor(shard=True): the two ranks split the 12 jobs, each wrote its own store; fitting on the rank-local
+  # stores (local_shard) gives the model of fitting on the whole job list
+  names = sorted(list(r[0]["fp_names"]) + list(r[1]["fp_names"]))
+  assert names == ["j%02d" % i for i in range(12)] and len(r[0]["fp_names"]) > 0 and len(r[1]["fp_names"]) > 0
+  for k in range(2):
+    assert relmax(r[k]["fp_mean_local"], r[k]["fp_mean_global"]) < 1e-4
+    assert relmax(r[k]["fp_sigma_local"], r[k]["fp_sigma_global"]) < 1e-3
+  assert np.array_equal(r[0]["fp_mean_local"], r[1]["fp_mean_local"])
   # odin_gmm_allreduce (C-ABI, its own NCCL communicator) == torch.distributed.all_reduce, bit for bit
   assert bool(r[0]["ar_equal"]) and bool(r[1]["ar_equal"])
