@@ -33,8 +33,9 @@ def eer(scores, labels):
 
 def main(n_files=600, nmix=128, tv_dim=64):
   sr = 8000
-  pool = synth.utterance_batch(60, 0.3, 1.0, sr=sr, seed=1)
-  jobs = [{"raw": pool[i % 60], "sr": sr, "name": "spk%02d_%04d" % (i % 10, i)} for i in range(n_files)]
+  rng = np.random.RandomState(1)
+  jobs = [{"raw": synth.speech_like(i, rng.uniform(0.3, 1.0), sr=sr, seed=1, speaker=i % 10), "sr": sr,
+           "name": "spk%02d_%04d" % (i % 10, i)} for i in range(n_files)]   # ten synthetic "speakers"
   extractors = pp.make_pipeline(steps=[
       pp.AudioReader(sr=sr, remove_dc=True),
       pp.PreEmphasis(coeff=0.97),
@@ -72,7 +73,7 @@ def main(n_files=600, nmix=128, tv_dim=64):
     t4 = time.perf_counter()
     print("T-matrix: tv_dim %d, llk %.4f -> %.4f; i-vectors %s in %.2f s" %
           (tv_dim, tmat._llk_hist[0], tmat._llk_hist[-1], ivecs.shape, t4 - t3))
-    # the ten synthetic "speakers" reuse their waveforms: same-speaker i-vectors must be closer than different ones
+    # ten synthetic "speakers" (own pitch and formants): same-speaker i-vectors must be closer than different ones
     spk = np.array([int(n[3:5]) for n in names])
     iv = np.asarray(ivecs, dtype=np.float64)
     iv = iv / np.linalg.norm(iv, axis=1, keepdims=True)
@@ -93,7 +94,7 @@ def main(n_files=600, nmix=128, tv_dim=64):
       scores = scorer.predict_log_proba(X_test)
       acc = float(np.mean(np.argmax(scores, 1) == spk[te]))
       print("%s: accuracy %.3f, EER %.3f  (fit + score %.1f ms)" % (tag, acc, eer(scores, spk[te]), 1e3 * (time.perf_counter() - t5)))
-      assert acc > 0.9
+      assert acc > 0.3   # chance is 0.1: the synthetic "speakers" differ in pitch and formants only, utterances are < 1 s
   print("total %.2f s" % (time.perf_counter() - t0))
 
 

@@ -7,12 +7,15 @@ checked on these generated signals.  Pure numpy, deterministic per
 import numpy as np
 
 
-def speech_like(index, duration_s, sr=16000, seed=1234):
+def speech_like(index, duration_s, sr=16000, seed=1234, speaker=None):
   """int16 PCM: harmonics of f0 in U[90,250] Hz with 1/k roll-off, shaped by 3
   random formant resonances, gated by a random on/off envelope (segments
   0.1-0.6 s, about 55 % on) over -45 dB white noise plus a small DC offset;
   peak about 0.5 * 32767.  The gating makes the energy VAD, the top_db clip
-  and the DC pre-pass all do real work."""
+  and the DC pre-pass all do real work.  `speaker` (int) ties pitch and formants to a
+  speaker (with a few per cent of per-utterance jitter) while envelope, phases and
+  noise stay per utterance -- for the scoring end of the recipe example; the default
+  (None) draws everything per utterance, as all fixtures do."""
   rng = np.random.RandomState(seed + int(index))
   n = int(round(duration_s * sr))
   t = np.arange(n, dtype=np.float64) / sr
@@ -21,6 +24,13 @@ def speech_like(index, duration_s, sr=16000, seed=1234):
   phase = 2 * np.pi * np.cumsum(f0 * vib) / sr
   formants = rng.uniform([300.0, 900.0, 2200.0], [900.0, 2200.0, min(3600.0, 0.45 * sr)])
   bw = rng.uniform(60.0, 200.0, size=3)
+  if speaker is not None:   # (after the per-utterance draws, so the default stream is untouched)
+    srng = np.random.RandomState(100003 + int(speaker))
+    jit = np.random.RandomState(seed + 31 * int(index) + 7)
+    f0 = srng.uniform(90.0, 250.0) * (1.0 + 0.03 * jit.randn())
+    formants = srng.uniform([300.0, 900.0, 2200.0], [900.0, 2200.0, min(3600.0, 0.45 * sr)]) * (1.0 + 0.02 * jit.randn(3))
+    bw = srng.uniform(60.0, 200.0, size=3)
+    phase = 2 * np.pi * np.cumsum(f0 * vib) / sr
   nharm = int(min(0.45 * sr, 5000.0) // f0)
   y = np.zeros(n)
   for k in range(1, nharm + 1):
