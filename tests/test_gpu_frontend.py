@@ -106,6 +106,39 @@ def test_fresh_audio_vs_oracle(name, n_utt):
     assert flips == 0, "%d of %d VAD decisions differ" % (flips, total)
 
 
+def test_config3_full_length_utterances_vs_oracle():
+  """Config 3 at the utterance lengths the benchmark runs (U[5, 60] s): a 60 s and a 37.3 s utterance (6 000 and 3 729
+  frames: many tiles per utterance, utterance-global top_db and SADgmm over thousands of frames), n_fft 1024, 80 mel,
+  both SADs, int16 PCM, against the oracle; and the WAV-file route (soundfile-style float32 in [-1, 1))."""
+  import wave
+  import tempfile
+  cfg = FE_CONFIGS["cfg3"]
+  sr = cfg["sr"]
+  utts = [synth.speech_like(700, 60.0, sr=sr, seed=99), synth.speech_like(701, 37.3, sr=sr, seed=99)]
+  for vad in ("gmm", "threshold"):
+    outs = _pipeline(cfg, vad).transform_batch([{"raw": u, "sr": sr} for u in utts])
+    for u, o in zip(utts, outs):
+      r = F.extract(u, sr, cfg["frame_length"], cfg["step_length"], cfg["n_fft"], n_mels=cfg["n_mels"], fmin=cfg["fmin"],
+                    fmax=cfg["fmax"], n_ceps=cfg["n_ceps"], vad=vad, vad_smooth=3 if vad == "gmm" else 5)
+      assert o["mfcc"].shape == r["mfcc"].shape == (1 + (len(u) - 400) // 160, 60)
+      assert relmax(o["mspec"], r["mspec"]) < TOL_FEAT and relmax(o["mfcc"], r["mfcc"]) < TOL_FEAT
+      assert relmax(o["mfcc"][:, 20:40], r["mfcc"][:, 20:40]) < TOL_FEAT and relmax(o["mfcc"][:, 40:], r["mfcc"][:, 40:]) < TOL_FEAT
+      assert np.array_equal(o["sad"].astype(np.uint8), r["sad"].astype(np.uint8)), "VAD mask differs (%s)" % vad
+  # the same audio as a 16-bit WAV file: AudioReader normalises like soundfile (int16 / 32768 as float32, ADVICE r1)
+  with tempfile.TemporaryDirectory() as d:
+    path = os.path.join(d, "u.wav")
+    with wave.open(path, "wb") as f:
+      f.setnchannels(1); f.setsampwidth(2); f.setframerate(sr)
+      f.writeframes(utts[1][:sr * 8].astype("<i2").tobytes())
+    o = _pipeline(cfg, "gmm").transform(path)
+    xf = (utts[1][:sr * 8].astype(np.float64) / 32768.0).astype(np.float32)
+    r = F.extract(xf, sr, cfg["frame_length"], cfg["step_length"], cfg["n_fft"], n_mels=cfg["n_mels"], fmin=cfg["fmin"],
+                  fmax=cfg["fmax"], n_ceps=cfg["n_ceps"], vad="gmm", vad_smooth=3)
+    assert o["path"] == os.path.abspath(path) and o["sr"] == sr
+    assert relmax(o["mspec"], r["mspec"]) < TOL_FEAT and relmax(o["mfcc"], r["mfcc"]) < TOL_FEAT
+    assert np.array_equal(o["sad"].astype(np.uint8), r["sad"].astype(np.uint8))
+
+
 def test_ragged_edge_cases():
   cfg = FE_CONFIGS["cfg1"]
   L, hop = 400, 160
