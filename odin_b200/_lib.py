@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libodin_b200.so")
+# ODIN_B200_LIB selects another build of the same library (A/B timing of two builds in tools/)
+LIB_PATH = os.environ.get("ODIN_B200_LIB") or os.path.join(_HERE, "lib", "libodin_b200.so")
 
 ODIN_OK, ODIN_EINVAL, ODIN_ENODEVICE, ODIN_ECUDA, ODIN_ENOMEM, ODIN_ESHORT = 0, -1, -2, -3, -4, -5
 

@@ -944,6 +944,8 @@ struct VadShared {
   int leaf_lo[VAD_MAXLEAF];
   int leaf_cnt[VAD_MAXLEAF];
   float leaf_sum[VAD_MAXLEAF];
+  int stk_a[40], stk_b[40];                 // thread 0's explicit recursion stack (kept out of local memory)
+  float stk_f[40];
 };
 
 // cluster-wide sums of v[0..VAD_NRED) -> sh.tot (same bits in every CTA; visible after the caller's next
@@ -982,7 +984,7 @@ template <class F>
 __device__ float block_np_pairwise_sum_f32(F f, int n, VadShared& sh, bool reuse_leaves = false) {
   const int tid = threadIdx.x;
   if (tid == 0 && !reuse_leaves) {   // (the table depends on n only)
-    int s_lo[40], s_n[40], sp = 0, nl = 0;
+    int *s_lo = sh.stk_a, *s_n = sh.stk_b, sp = 0, nl = 0;
     s_lo[0] = 0; s_n[0] = n; sp = 1;
     while (sp > 0 && nl >= 0) {
       const int lo = s_lo[sp - 1], cnt = s_n[sp - 1];
@@ -1040,8 +1042,8 @@ __device__ float block_np_pairwise_sum_f32(F f, int n, VadShared& sh, bool reuse
   __syncthreads();
   if (tid == 0) {
     // fold: post-order evaluation of the same recursion, leaves consumed left to right
-    int s_n[40], s_stage[40], sp = 1, next = 0;
-    float s_left[40], ret = 0.f;
+    int *s_n = sh.stk_a, *s_stage = sh.stk_b, sp = 1, next = 0;
+    float *s_left = sh.stk_f, ret = 0.f;
     s_n[0] = n; s_stage[0] = 0; s_left[0] = 0.f;
     while (sp > 0) {
       const int t = sp - 1, cnt = s_n[t];
@@ -1083,24 +1085,27 @@ __device__ __forceinline__ void vad_store_params(VadShared& sh, int k, double mu
   sh.par[k][VP_W] = w;
 }
 
-// E-step of one frame (sklearn _estimate_log_prob_resp, 1-D) accumulated into acc[] = lsum | nk | sx | sxx | #non-finite
-__device__ __forceinline__ void vad_frame(const float xf, const int nc, const double (&prec)[VAD_KMAX],
-                                          const double (&a0)[VAD_KMAX], const double (&b0)[VAD_KMAX],
-                                          const double (&ld)[VAD_KMAX], const double (&lw)[VAD_KMAX],
+// E-step of one frame (sklearn _estimate_log_prob_resp, 1-D) accumulated into acc[] = lsum | nk | sx | sxx | #non-finite.
+// The component count is a template parameter: with a run-time count the parameter and accumulator arrays were
+// indexed dynamically and lived in local memory (314 LDL / 285 STL in the kernel, a 1 376-byte stack frame).
+template <int NC>
+__device__ __forceinline__ void vad_frame(const float xf, const double (&prec)[NC], const double (&a0)[NC],
+                                          const double (&b0)[NC], const double (&ld)[NC], const double (&lw)[NC],
                                           double (&acc)[VAD_NRED], double& sprod, int& nprod) {
   constexpr int KMAX = VAD_KMAX;
   const double LOG2PI = 1.8378770664093454835606594728112;
   if (!isfinite(xf)) acc[VAD_NRED - 1] += 1.0;
   const double xd = (double)xf, x2 = (double)__fmul_rn(xf, xf);  // x*x is float32 in sklearn
-  double wl[KMAX], mx = -INFINITY;
-  for (int k = 0; k < nc; ++k) {
+  double wl[NC], mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
     double lp = dadd(dadd(a0[k], -dmul(2.0, dmul(xd, b0[k]))), dmul(x2, prec[k]));
     lp = dadd(dmul(-0.5, dadd(LOG2PI, lp)), ld[k]);
     wl[k] = dadd(lp, lw[k]);
     mx = fmax(mx, wl[k]);
   }
-  double ek[KMAX], s = 0.0;
-  if (nc == 3) {
+  double ek[NC], s = 0.0;
+  if constexpr (NC == 3) {
     const bool am = wl[0] == mx, bm = wl[1] == mx, cm = wl[2] == mx;
     const double dA = wl[0] - mx, dB = wl[1] - mx, dC = wl[2] - mx;
     const double e1 = exp(am ? dB : dA), e2 = exp(cm ? dB : dC);
@@ -1109,18 +1114,46 @@ __device__ __forceinline__ void vad_frame(const float xf, const int nc, const do
     ek[1] = bm ? 1.0 : (am ? e1 : e2);
     s = (ek[0] + ek[1]) + ek[2];
   } else {
-    for (int k = 0; k < nc; ++k) { ek[k] = exp(wl[k] - mx); s += ek[k]; }
+#pragma unroll
+    for (int k = 0; k < NC; ++k) { ek[k] = exp(wl[k] - mx); s += ek[k]; }
   }
   const double inv = 1.0 / s;
   acc[0] += mx;
   sprod *= s;
   if (++nprod == 256) { acc[0] += log(sprod); sprod = 1.0; nprod = 0; }   // nc^256 stays finite
-  for (int k = 0; k < nc; ++k) {
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
     const double r = ek[k] * inv;
     acc[1 + k] += r;
     acc[1 + KMAX + k] = fma(r, xd, acc[1 + KMAX + k]);
     acc[1 + 2 * KMAX + k] = fma(r, x2, acc[1 + 2 * KMAX + k]);
   }
+}
+
+// The E-step of one EM iteration over the frames get(0), get(1), ... of this thread; par[k] as vad_store_params left it.
+template <int NC, class Get>
+__device__ __forceinline__ void vad_estep(const double (*par)[8], int count, Get get, double (&acc)[VAD_NRED]) {
+  double prec[NC], a0[NC], b0[NC], ld[NC], lw[NC];
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    prec[k] = par[k][VP_PREC]; a0[k] = par[k][VP_A0]; b0[k] = par[k][VP_B0];
+    ld[k] = par[k][VP_LD]; lw[k] = par[k][VP_LW];
+  }
+#pragma unroll
+  for (int k = 0; k < VAD_NRED; ++k) acc[k] = 0.0;
+  // The per-frame work is ~all fp64 transcendental code, so it is trimmed to what the sums need:
+  //  * exp(wl[k] - max) of the maximal component is exactly 1: with three components the two other
+  //    differences are picked with selects and only TWO exponentials are evaluated;
+  //  * log(s) only feeds the running sum of log-likelihoods: the s of a thread's frames are
+  //    multiplied (s in [1, nc], <= a few dozen frames per thread and iteration) and ONE log is
+  //    taken at the end;
+  //  * the responsibilities exp(wl - norm) are formed as exp(wl - max) / s.
+  // Each step differs from sklearn's expression by <= 1 ulp of a double.
+  double sprod = 1.0;
+  int nprod = 0;
+#pragma unroll 2
+  for (int j = 0; j < count; ++j) vad_frame<NC>(get(j), prec, a0, b0, ld, lw, acc, sprod, nprod);
+  acc[0] += log(sprod);
 }
 
 __device__ bool vad_em(const float* __restrict__ x, int n, int nc, int max_iter, VadShared& sh, cg::cluster_group& cl,
@@ -1141,47 +1174,39 @@ __device__ bool vad_em(const float* __restrict__ x, int n, int nc, int max_iter,
   __syncthreads();
   double lower = -INFINITY;
   for (int it = 0; it < max_iter; ++it) {
-    double prec[KMAX], a0[KMAX], b0[KMAX], ld[KMAX], lw[KMAX];
-    for (int k = 0; k < nc; ++k) {
-      prec[k] = sh.par[k][VP_PREC]; a0[k] = sh.par[k][VP_A0]; b0[k] = sh.par[k][VP_B0];
-      ld[k] = sh.par[k][VP_LD]; lw[k] = sh.par[k][VP_LW];
-    }
     double acc[VAD_NRED];
-#pragma unroll
-    for (int k = 0; k < VAD_NRED; ++k) acc[k] = 0.0;
-    // The per-frame work is ~all fp64 transcendental code, so it is trimmed to what the sums need:
-    //  * exp(wl[k] - max) of the maximal component is exactly 1: with three components the two other
-    //    differences are picked with selects and only TWO exponentials are evaluated;
-    //  * log(s) only feeds the running sum of log-likelihoods: the s of a thread's frames are
-    //    multiplied (s in [1, nc], <= a few dozen frames per thread and iteration) and ONE log is
-    //    taken at the end;
-    //  * the responsibilities exp(wl - norm) are formed as exp(wl - max) / s.
-    // Each step differs from sklearn's expression by <= 1 ulp of a double.
-    double sprod = 1.0;
-    int nprod = 0;
-    auto frame = [&](const float xf) { vad_frame(xf, nc, prec, a0, b0, ld, lw, acc, sprod, nprod); };
-    if (staged) {
-      for (int j = 0, i = gt; i < n; ++j, i += gstride) frame(sh.xs[j * VAD_THREADS + tid]);
-    } else {
-      for (int i = gt; i < n; i += gstride) frame(x[i]);
+    {
+      const int count = gt < n ? (n - gt + gstride - 1) / gstride : 0;   // frames gt, gt + gstride, ... of this thread
+      const float* xcol = sh.xs + tid;
+      const float* xg = x + gt;
+      auto run = [&](auto nc_tag) {
+        constexpr int NC = decltype(nc_tag)::value;
+        if (staged) vad_estep<NC>(sh.par, count, [xcol](int j) { return xcol[j * VAD_THREADS]; }, acc);
+        else vad_estep<NC>(sh.par, count, [xg, gstride](int j) { return xg[(size_t)j * gstride]; }, acc);
+      };
+      if (nc == 3) run(std::integral_constant<int, 3>());
+      else if (nc == 2) run(std::integral_constant<int, 2>());
+      else run(std::integral_constant<int, 4>());
     }
-    acc[0] += log(sprod);
     vad_cluster_reduce(acc, sh, cl);
     // M-step (sklearn _estimate_gaussian_parameters, 1-D): component k by lane k of warp 0 -- the same warp
     // that wrote sh.tot, so a warp barrier orders the two
     if (tid < 32) {
       __syncwarp();
       if (tid < nc) {
-        double nk[KMAX], nksum = 0.0;
-        for (int k = 0; k < nc; ++k) {
-          nk[k] = sh.tot[1 + k] + 10.0 * DBL_EPSILON;
-          nksum += nk[k];
-        }
+        double nkk = 0.0, nksum = 0.0;   // (static indexing: no local-memory arrays)
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+          if (k < nc) {
+            const double v = sh.tot[1 + k] + 10.0 * DBL_EPSILON;
+            nksum += v;
+            if (k == tid) nkk = v;
+          }
         const int k = tid;
-        const double mu = sh.tot[1 + KMAX + k] / nk[k];
-        const double var = dadd(dadd(sh.tot[1 + 2 * KMAX + k] / nk[k], -dmul(mu, mu)), 1e-6);
+        const double mu = sh.tot[1 + KMAX + k] / nkk;
+        const double var = dadd(dadd(sh.tot[1 + 2 * KMAX + k] / nkk, -dmul(mu, mu)), 1e-6);
         sh.bad[k] = !(var > 0.0);
-        vad_store_params(sh, k, mu, 1.0 / sqrt(var), nk[k] / nksum);
+        vad_store_params(sh, k, mu, 1.0 / sqrt(var), nkk / nksum);
       }
     }
     __syncthreads();
@@ -1194,10 +1219,11 @@ __device__ bool vad_em(const float* __restrict__ x, int n, int nc, int max_iter,
     lower = new_lower;
     if (fabs(change) < 1e-3) break;
   }
-  for (int k = 0; k < nc; ++k) {
-    mu_out[k] = sh.par[k][VP_MU];
-    prec_out[k] = dmul(sh.par[k][VP_PCH], sh.par[k][VP_PCH]);
-  }
+  // the component with the largest mean (first one on ties, like np.argmax)
+  int kb = 0;
+  for (int k = 1; k < nc; ++k) if (sh.par[k][VP_MU] > sh.par[kb][VP_MU]) kb = k;
+  *mu_out = sh.par[kb][VP_MU];
+  *prec_out = dmul(sh.par[kb][VP_PCH], sh.par[kb][VP_PCH]);
   return true;
 }
 
@@ -1237,11 +1263,9 @@ __global__ void __launch_bounds__(VAD_THREADS, 2) fe_vad_gmm_kernel(VadArgs a) {
       __threadfence();
       cl.sync();
       src = xs;
-      double mu[4], prec[4];
-      if (vad_em(xs, n, nc, a.iters, sh, cl, mu, prec)) {
-        int kb = 0;
-        for (int k = 1; k < nc; ++k) if (mu[k] > mu[kb]) kb = k;
-        thr = dadd(mu[kb], -dmul(a.mode, sqrt(1.0 / prec[kb])));
+      double mu_b, prec_b;
+      if (vad_em(xs, n, nc, a.iters, sh, cl, &mu_b, &prec_b)) {
+        thr = dadd(mu_b, -dmul(a.mode, sqrt(1.0 / prec_b)));
         ok = true;
         break;
       }
@@ -1259,6 +1283,58 @@ __global__ void __launch_bounds__(VAD_THREADS, 2) fe_vad_gmm_kernel(VadArgs a) {
     }
     cl.sync();  // xs / sh are reused by the cluster's next utterance
   }
+}
+
+// EM of one utterance by one warp (fe_vad_gmm_warp_kernel): returns false where sklearn would raise; mu / precision
+// Cholesky factor of the component with the largest mean.
+template <int NC>
+__device__ bool vad_warp_em(const float* __restrict__ xs, int n, int max_iter, int lane, double& mu_b, double& pch_b) {
+  constexpr int KMAX = VAD_KMAX;
+  if (n < (NC > 2 ? NC : 2)) return false;
+  double w[NC], mu[NC], pch[NC];
+#pragma unroll
+  for (int k = 0; k < NC; ++k) { w[k] = 1.0 / NC; mu[k] = -2.0 + 4.0 * k / (double)(NC - 1); pch[k] = 1.0; }
+  double lower = -INFINITY;
+  const int count = lane < n ? (n - lane + 31) / 32 : 0;
+  const float* xl = xs + lane;
+  for (int it = 0; it < max_iter; ++it) {
+    double par[NC][8];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      const double prec = dmul(pch[k], pch[k]);
+      par[k][VP_PREC] = prec;
+      par[k][VP_A0] = dmul(dmul(mu[k], mu[k]), prec);
+      par[k][VP_B0] = dmul(mu[k], prec);
+      par[k][VP_LD] = log(pch[k]);
+      par[k][VP_LW] = log(w[k]);
+    }
+    double acc[VAD_NRED];
+    vad_estep<NC>(par, count, [xl](int j) { return xl[32 * j]; }, acc);
+#pragma unroll
+    for (int k = 0; k < VAD_NRED; ++k) acc[k] = warp_sum(acc[k]);
+    if (acc[VAD_NRED - 1] != 0.0) return false;   // sklearn rejects non-finite input
+    double nk[NC], nksum = 0.0;
+    bool collapsed = false;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) { nk[k] = acc[1 + k] + 10.0 * DBL_EPSILON; nksum += nk[k]; }
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      mu[k] = acc[1 + KMAX + k] / nk[k];
+      const double var = dadd(dadd(acc[1 + 2 * KMAX + k] / nk[k], -dmul(mu[k], mu[k])), 1e-6);
+      if (!(var > 0.0)) collapsed = true;
+      pch[k] = 1.0 / sqrt(var);
+      w[k] = nk[k] / nksum;
+    }
+    if (collapsed) return false;
+    const double new_lower = acc[0] / (double)n;
+    const double change = new_lower - lower;
+    lower = new_lower;
+    if (fabs(change) < 1e-3) break;
+  }
+  mu_b = mu[0]; pch_b = pch[0];
+#pragma unroll
+  for (int k = 1; k < NC; ++k) if (mu[k] > mu_b) { mu_b = mu[k]; pch_b = pch[k]; }
+  return true;
 }
 
 // SADgmm for SHORT utterances: one WARP per utterance, eight independent utterances per CTA, no block or cluster
@@ -1297,49 +1373,12 @@ __global__ void __launch_bounds__(VAD_THREADS, 2) fe_vad_gmm_warp_kernel(VadArgs
       __syncwarp();
       src = xs;
       // ---- EM (same arithmetic as vad_em; reductions by butterfly) ----
-      bool fitted = n >= max(nc, 2);
-      double w[KMAX], mu[KMAX], pch[KMAX];
-      for (int k = 0; k < nc; ++k) { w[k] = 1.0 / nc; mu[k] = -2.0 + 4.0 * k / (double)(nc - 1); pch[k] = 1.0; }
-      double lower = -INFINITY;
-      for (int it = 0; fitted && it < a.iters; ++it) {
-        double prec[KMAX], a0[KMAX], b0[KMAX], ld[KMAX], lw[KMAX];
-        for (int k = 0; k < nc; ++k) {
-          prec[k] = dmul(pch[k], pch[k]);
-          a0[k] = dmul(dmul(mu[k], mu[k]), prec[k]);
-          b0[k] = dmul(mu[k], prec[k]);
-          ld[k] = log(pch[k]);
-          lw[k] = log(w[k]);
-        }
-        double acc[VAD_NRED];
-#pragma unroll
-        for (int k = 0; k < VAD_NRED; ++k) acc[k] = 0.0;
-        double sprod = 1.0;
-        int nprod = 0;
-        for (int i = lane; i < n; i += 32) vad_frame(xs[i], nc, prec, a0, b0, ld, lw, acc, sprod, nprod);
-        acc[0] += log(sprod);
-#pragma unroll
-        for (int k = 0; k < VAD_NRED; ++k) acc[k] = warp_sum(acc[k]);
-        if (acc[VAD_NRED - 1] != 0.0) { fitted = false; break; }   // sklearn rejects non-finite input
-        double nk[KMAX], nksum = 0.0;
-        bool collapsed = false;
-        for (int k = 0; k < nc; ++k) { nk[k] = acc[1 + k] + 10.0 * DBL_EPSILON; nksum += nk[k]; }
-        for (int k = 0; k < nc; ++k) {
-          mu[k] = acc[1 + KMAX + k] / nk[k];
-          const double var = dadd(dadd(acc[1 + 2 * KMAX + k] / nk[k], -dmul(mu[k], mu[k])), 1e-6);
-          if (!(var > 0.0)) collapsed = true;
-          pch[k] = 1.0 / sqrt(var);
-          w[k] = nk[k] / nksum;
-        }
-        if (collapsed) { fitted = false; break; }
-        const double new_lower = acc[0] / (double)n;
-        const double change = new_lower - lower;
-        lower = new_lower;
-        if (fabs(change) < 1e-3) break;
-      }
+      double mu_b = 0.0, pch_b = 1.0;
+      const bool fitted = nc == 3 ? vad_warp_em<3>(xs, n, a.iters, lane, mu_b, pch_b)
+                        : nc == 2 ? vad_warp_em<2>(xs, n, a.iters, lane, mu_b, pch_b)
+                                  : vad_warp_em<4>(xs, n, a.iters, lane, mu_b, pch_b);
       if (fitted) {
-        int kb = 0;
-        for (int k = 1; k < nc; ++k) if (mu[k] > mu[kb]) kb = k;
-        thr = dadd(mu[kb], -dmul(a.mode, sqrt(1.0 / dmul(pch[kb], pch[kb]))));
+        thr = dadd(mu_b, -dmul(a.mode, sqrt(1.0 / dmul(pch_b, pch_b))));
         ok = true;
         break;
       }
