@@ -122,6 +122,21 @@ template <> __device__ __forceinline__ float db10<float>(float v) {
 template <> __device__ __forceinline__ double db10<double>(double v) { return 10.0 * log10(fmax(v, 1e-10)); }
 
 
+// ---- packed fp32 pairs (sm_100a FADD2 / FMUL2 / FFMA2): one 64-bit register holds (lo, hi) ----
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 pk2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float lo32(u64 v) { float a, b; asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
+__device__ __forceinline__ float hi32(u64 v) { float a, b; asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+// (re, im) * (wr + i wi) = (re wr, im wr) + (im, re) * (-wi, wi)
+__device__ __forceinline__ u64 cmulw(u64 a, float wr, float wi) {
+  return fma2(pk2(hi32(a), lo32(a)), pk2(-wi, wi), mul2(a, pk2(wr, wr)));
+}
+
 // fe_frame5.cu: packed-f32x2 four-step kernel (n_fft <= 1024, conforming filterbank, no spectrum output)
 int fe_frame5_launch(int N, int pcm_dtype, const FrameArgs& a, cudaStream_t st);
 

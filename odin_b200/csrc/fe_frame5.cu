@@ -41,20 +41,6 @@
 
 namespace odin {
 
-typedef unsigned long long u64;
-
-__device__ __forceinline__ u64 pk2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ float lo32(u64 v) { float a, b; asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
-__device__ __forceinline__ float hi32(u64 v) { float a, b; asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
-__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-// (re, im) * (wr + i wi) = (re wr, im wr) + (im, re) * (-wi, wi)
-__device__ __forceinline__ u64 cmulw(u64 a, float wr, float wi) {
-  return fma2(pk2(hi32(a), lo32(a)), pk2(-wi, wi), mul2(a, pk2(wr, wr)));
-}
-
 // cos / -sin of 2 pi q / 32
 __device__ __forceinline__ constexpr float c32(int q) {
   constexpr float t[9] = {1.0f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
@@ -332,10 +318,26 @@ __global__ void __launch_bounds__(F5_MAX_THREADS, 1) fe_frame5_kernel(FrameArgs 
           if (i >= 0 && i < 2 * NP) my_e = (i & 1) ? eb : ea;
         }
         Dft5<32, NZ>::run(v);
+        // twiddles W_N^(k1 l), k1 = 8 a + b: ten table reads (b = 1..7, 8 a = 8, 16, 24) and 21 complex products instead
+        // of 31 reads -- a packed complex multiply is two issue slots, a 64-bit shared-memory read two wavefronts of
+        // the crossbar that bounds this kernel
+        {
+          u64 wa[4];
 #pragma unroll
-        for (int k1 = 1; k1 < 32; ++k1) {
-          const u64 w = tw4[k1 * G + l];
-          v[k1] = cmulw(v[k1], lo32(w), hi32(w));
+          for (int q = 1; q < 4; ++q) {
+            wa[q] = tw4[8 * q * G + l];
+            v[8 * q] = cmulw(v[8 * q], lo32(wa[q]), hi32(wa[q]));
+          }
+#pragma unroll
+          for (int b = 1; b < 8; ++b) {
+            const u64 wb = tw4[b * G + l];
+            v[b] = cmulw(v[b], lo32(wb), hi32(wb));
+#pragma unroll
+            for (int q = 1; q < 4; ++q) {
+              const u64 w = cmulw(wa[q], lo32(wb), hi32(wb));
+              v[8 * q + b] = cmulw(v[8 * q + b], lo32(w), hi32(w));
+            }
+          }
         }
         __syncwarp();  // every lane has its samples in registers: the region becomes the exchange tile
 #pragma unroll

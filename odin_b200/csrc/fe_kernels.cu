@@ -689,6 +689,22 @@ __device__ __forceinline__ void fir4(const float* __restrict__ x, int stride, co
   }
 }
 
+// The same for TWO adjacent columns at once on packed fp32 pairs: out[j] = (column c, column c + 1) of row j.  Each
+// lane of an FFMA2 is the IEEE fma of the scalar loop, so the results are bit-identical to fir4's.
+template <int W>
+__device__ __forceinline__ void fir4x2(const float* __restrict__ x, int stride, const float (&tp)[W], u64 (&out)[4]) {
+  u64 v[W + 3];
+#pragma unroll
+  for (int q = 0; q < W + 3; ++q) v[q] = pk2(x[q * stride], x[q * stride + 1]);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    u64 acc = 0ull;
+#pragma unroll
+    for (int k = 0; k < W; ++k) acc = fma2(pk2(tp[k], tp[k]), v[j + W - 1 - k], acc);
+    out[j] = acc;
+  }
+}
+
 // Utterance pass.  Issue-bound (ncu: 72 % of issue slots at 728 warp-instructions per frame in its first
 // version), so the work is arranged to cost few instructions: runtime divisors go through fdiv, the DCT is
 // register-blocked 2 rows x 8 coefficients with the basis transposed and zero-padded to a multiple of 8
@@ -705,7 +721,7 @@ __global__ void __launch_bounds__(256, 3) fe_post_kernel(PostArgs a) {
   float* sdct = sm;                         // [n_mels][C8]  transposed basis, 16-byte aligned rows
   float* staps = sdct + a.n_mels * C8;      // [W] (+ pad to 4)
   float* scep = staps + ((a.W + 3) & ~3);   // [NR][n_c1]
-  float* smel = scep + NR * a.n_c1;         // [NR][MS]
+  float* smel = scep + ((NR * a.n_c1 + 3) & ~3);   // [NR][MS]
   float* sd1 = smel;                        // [ND][n_ceps] first-order deltas: the mel rows are dead by then
   const uint32_t mg_c8 = fdiv_magic(C8), mg_ceps = fdiv_magic(max(a.n_ceps, 1));
 
@@ -716,6 +732,9 @@ __global__ void __launch_bounds__(256, 3) fe_post_kernel(PostArgs a) {
     sdct[i] = (c < a.n_c1) ? a.dct[c * a.n_mels + m] : 0.f;
   }
   for (int i = tid; i < a.W; i += 256) staps[i] = a.taps[i];
+  float tp9[9];   // the taps of the usual 9-wide delta window, in registers
+#pragma unroll
+  for (int k = 0; k < 9; ++k) tp9[k] = a.taps[min(k, a.W - 1)];
   const int64_t per = (a.n_tiles + gridDim.x - 1) / gridDim.x;
   const int64_t tile_lo = per * blockIdx.x, tile_hi = min(a.n_tiles, tile_lo + per);
   if (tile_lo >= tile_hi) return;
@@ -789,19 +808,25 @@ __global__ void __launch_bounds__(256, 3) fe_post_kernel(PostArgs a) {
       const float* m1 = smel + r1 * MS;
       const float4* dq = reinterpret_cast<const float4*>(sdct + 8 * g);
       const int dstride = C8 >> 2;
-      float acc0[8], acc1[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc0[j] = acc1[j] = 0.f;
+      // (coefficient 2p, coefficient 2p + 1) per 64-bit accumulator: 8 FFMA2 per mel for the 2 x 8 block; each lane
+      // of an FFMA2 is the fmaf of the scalar loop (m ascending from a zero accumulator), so the bits are unchanged
+      u64 pa0[4] = {0ull, 0ull, 0ull, 0ull}, pa1[4] = {0ull, 0ull, 0ull, 0ull};
+      const ulonglong2* dq2 = reinterpret_cast<const ulonglong2*>(dq);
 #pragma unroll 4
       for (int m = 0; m < a.n_mels; ++m) {
         const float x0 = m0[m], x1 = m1[m];
-        const float4 da = dq[m * dstride], db = dq[m * dstride + 1];
-        const float dv[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+        const ulonglong2 da = dq2[m * dstride], db = dq2[m * dstride + 1];
+        const u64 xx0 = pk2(x0, x0), xx1 = pk2(x1, x1);
+        pa0[0] = fma2(da.x, xx0, pa0[0]); pa1[0] = fma2(da.x, xx1, pa1[0]);
+        pa0[1] = fma2(da.y, xx0, pa0[1]); pa1[1] = fma2(da.y, xx1, pa1[1]);
+        pa0[2] = fma2(db.x, xx0, pa0[2]); pa1[2] = fma2(db.x, xx1, pa1[2]);
+        pa0[3] = fma2(db.y, xx0, pa0[3]); pa1[3] = fma2(db.y, xx1, pa1[3]);
+      }
+      float acc0[8], acc1[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          acc0[j] = fmaf(dv[j], x0, acc0[j]);
-          acc1[j] = fmaf(dv[j], x1, acc1[j]);
-        }
+      for (int q = 0; q < 4; ++q) {
+        acc0[2 * q] = lo32(pa0[q]); acc0[2 * q + 1] = hi32(pa0[q]);
+        acc1[2 * q] = lo32(pa1[q]); acc1[2 * q + 1] = hi32(pa1[q]);
       }
       const int c0i = 8 * g;
 #pragma unroll
@@ -825,36 +850,47 @@ __global__ void __launch_bounds__(256, 3) fe_post_kernel(PostArgs a) {
   const int ulo = t0 - ((a.order >= 2) ? a.W - 1 : 0);
   const int nd = t0 + nf - ulo;
   float* sd2 = sd1 + nd * a.n_ceps;   // [nf][n_ceps] second-order deltas
+  const bool pairs = a.W == 9 && (a.n_ceps & 1) == 0;   // packed route: a thread takes 4 rows x 2 adjacent coefficients
   if (a.order >= 1) {
     const int ng = (nd + 3) >> 2;
-    for (int i = tid; i < ng * a.n_ceps; i += 256) {
-      const int rg = fdiv(i, mg_ceps), c = i - rg * a.n_ceps;
+    const int ncol = pairs ? a.n_ceps >> 1 : a.n_ceps, cw = pairs ? 2 : 1;
+    const uint32_t mg_col = fdiv_magic(ncol);
+    for (int i = tid; i < ng * ncol; i += 256) {
+      const int rg = fdiv(i, mg_col), c = (i - rg * ncol) * cw;
       const int r0 = 4 * rg, uu0 = ulo + r0;
       if (a.W == 9 && r0 + 3 < nd && uu0 - h >= 0 && uu0 + 3 + h <= T - 1) {
-        float o4[4];
-        fir4<9>(scep + (uu0 - h - lo) * a.n_c1 + 1 + c, a.n_c1, staps, o4);
+        if (pairs) {
+          u64 o4[4];
+          fir4x2<9>(scep + (uu0 - h - lo) * a.n_c1 + 1 + c, a.n_c1, tp9, o4);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) sd1[(r0 + j) * a.n_ceps + c] = o4[j];
+          for (int j = 0; j < 4; ++j) *reinterpret_cast<u64*>(sd1 + (r0 + j) * a.n_ceps + c) = o4[j];
+        } else {
+          float o4[4];
+          fir4<9>(scep + (uu0 - h - lo) * a.n_c1 + 1 + c, a.n_c1, staps, o4);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) sd1[(r0 + j) * a.n_ceps + c] = o4[j];
+        }
         continue;
       }
+      for (int cc = c; cc < c + cw; ++cc)
       for (int r = r0; r < min(r0 + 4, nd); ++r) {
         const int uu = ulo + r;
         float acc = 0.f;
         if (uu - h >= 0 && uu + h <= T - 1) {   // interior: no clamping
-          const float* p = scep + (uu + h - lo) * a.n_c1 + 1 + c;
+          const float* p = scep + (uu + h - lo) * a.n_c1 + 1 + cc;
           for (int k = 0; k < a.W; ++k) acc = fmaf(staps[k], p[-k * a.n_c1], acc);
         } else if (uu >= -(h + 1)) {
           for (int k = 0; k < a.W; ++k) {
             int t = min(max(uu + h - k, 0), T - 1);
-            acc = fmaf(staps[k], scep[(t - lo) * a.n_c1 + 1 + c], acc);
+            acc = fmaf(staps[k], scep[(t - lo) * a.n_c1 + 1 + cc], acc);
           }
         } else {  // zero initial state of the causal filter
           const int j = uu + 2 * a.W - h - 1;
           float ts = 0.f;
           for (int k = 0; k <= j; ++k) ts += staps[k];
-          acc = ts * scep[(0 - lo) * a.n_c1 + 1 + c];
+          acc = ts * scep[(0 - lo) * a.n_c1 + 1 + cc];
         }
-        sd1[r * a.n_ceps + c] = acc;
+        sd1[r * a.n_ceps + cc] = acc;
       }
     }
   }
@@ -862,34 +898,270 @@ __global__ void __launch_bounds__(256, 3) fe_post_kernel(PostArgs a) {
     __syncthreads();
     // second-order deltas: DD(t) = sum_k taps[k] D(t - k), every input row is held (no edges)
     const int ng = (nf + 3) >> 2;
-    for (int i = tid; i < ng * a.n_ceps; i += 256) {
-      const int rg = fdiv(i, mg_ceps), c = i - rg * a.n_ceps;
+    const int ncol = pairs ? a.n_ceps >> 1 : a.n_ceps, cw = pairs ? 2 : 1;
+    const uint32_t mg_col = fdiv_magic(ncol);
+    for (int i = tid; i < ng * ncol; i += 256) {
+      const int rg = fdiv(i, mg_col), c = (i - rg * ncol) * cw;
       const int r0 = 4 * rg;   // row t = t0 + r0, its D row index is t - ulo = r0 + W - 1
       if (a.W == 9 && r0 + 3 < nf) {
-        float o4[4];
-        fir4<9>(sd1 + r0 * a.n_ceps + c, a.n_ceps, staps, o4);
+        if (pairs) {
+          u64 o4[4];
+          fir4x2<9>(sd1 + r0 * a.n_ceps + c, a.n_ceps, tp9, o4);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) sd2[(r0 + j) * a.n_ceps + c] = o4[j];
+          for (int j = 0; j < 4; ++j) *reinterpret_cast<u64*>(sd2 + (r0 + j) * a.n_ceps + c) = o4[j];
+        } else {
+          float o4[4];
+          fir4<9>(sd1 + r0 * a.n_ceps + c, a.n_ceps, staps, o4);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) sd2[(r0 + j) * a.n_ceps + c] = o4[j];
+        }
         continue;
       }
+      for (int cc = c; cc < c + cw; ++cc)
       for (int r = r0; r < min(r0 + 4, nf); ++r) {
         float acc = 0.f;
-        const float* p = sd1 + (r + a.W - 1) * a.n_ceps + c;
+        const float* p = sd1 + (r + a.W - 1) * a.n_ceps + cc;
         for (int k = 0; k < a.W; ++k) acc = fmaf(staps[k], p[-k * a.n_ceps], acc);
-        sd2[r * a.n_ceps + c] = acc;
+        sd2[r * a.n_ceps + cc] = acc;
       }
     }
   }
   __syncthreads();
-  const uint32_t mg_fd = fdiv_magic(fd);
   float* fout = a.feat + (base + t0) * fd;
-  for (int i = tid; i < nf * fd; i += 256) {
-    const int r = fdiv(i, mg_fd), j = i - r * fd;
-    const int o = fdiv(j, mg_ceps), c = j - o * a.n_ceps;
-    const float* src = (o == 0) ? scep + (t0 + r - lo) * a.n_c1 + 1 + c
-                                : (o == 1 ? sd1 + (t0 + r - ulo) * a.n_ceps + c : sd2 + r * a.n_ceps + c);
-    fout[i] = *src;
+  if ((a.n_ceps & 3) == 0 && (reinterpret_cast<uintptr_t>(a.feat) & 15) == 0) {
+    // 16 bytes per store: a quad never straddles the static / delta / delta-delta blocks of a row
+    const int qrow = fd >> 2, qblk = a.n_ceps >> 2;
+    const uint32_t mg_qrow = fdiv_magic(qrow), mg_qblk = fdiv_magic(qblk);
+    float4* fout4 = reinterpret_cast<float4*>(fout);
+    for (int i = tid; i < nf * qrow; i += 256) {
+      const int r = fdiv(i, mg_qrow), q = i - r * qrow;
+      const int o = fdiv(q, mg_qblk), c = 4 * (q - o * qblk);
+      const float* src = (o == 0) ? scep + (t0 + r - lo) * a.n_c1 + 1 + c
+                                  : (o == 1 ? sd1 + (t0 + r - ulo) * a.n_ceps + c : sd2 + r * a.n_ceps + c);
+      fout4[i] = make_float4(src[0], src[1], src[2], src[3]);
+    }
+  } else {
+    const uint32_t mg_fd = fdiv_magic(fd);
+    for (int i = tid; i < nf * fd; i += 256) {
+      const int r = fdiv(i, mg_fd), j = i - r * fd;
+      const int o = fdiv(j, mg_ceps), c = j - o * a.n_ceps;
+      const float* src = (o == 0) ? scep + (t0 + r - lo) * a.n_c1 + 1 + c
+                                  : (o == 1 ? sd1 + (t0 + r - ulo) * a.n_ceps + c : sd2 + r * a.n_ceps + c);
+      fout[i] = *src;
+    }
   }
+  }  // tile loop
+}
+
+// ---------------------------------------------------------------------------
+// fe_post9_kernel: the utterance pass for the usual shape -- 9-tap deltas of order 2, n_mels and n_ceps multiples of 4,
+// 16-byte aligned buffers.  Same arithmetic, in the same order, as fe_post_kernel (outputs are bit-identical); what
+// changes is how the data moves.  ncu of fe_post_kernel on 25 h of config 3: shared-memory pipe 67 % busy with 38 % of
+// its wavefronts bank conflicts (scalar stores of the mel rows 4-way, delta inputs at an odd row stride, scalar reads of
+// the output phase 4-way), 51 % of the issue slots.  Here every shared-memory access of the hot phases is a 16- or
+// 8-byte access at a row stride of 4 (mod 8) words, which is conflict-free per quarter warp:
+//   * mel rows [NR][MS] stored and read as float4 (lanes walk rows in the DCT);
+//   * cepstra [NR][CS] without c0 (the DCT basis is permuted: slots 0..n_ceps-1 the cepstra, slot n_ceps c0, which goes
+//     straight to global memory), so a thread stores its 8 coefficients as two float4 and the deltas read (c, c + 1) as one
+//     64-bit word;
+//   * deltas as 6-row x 2-coefficient FIR blocks on packed pairs (14 reads for 12 outputs; 230 / 220 work items fill the
+//     256 threads in one round);
+//   * the output phase moves one float4 per load and store.
+// ---------------------------------------------------------------------------
+constexpr int P9_R = 6;
+__host__ __device__ __forceinline__ int pad4odd(int n) { return ((n >> 2) & 1) ? n : n + 4; }
+
+template <int R>
+__device__ __forceinline__ void fir9x2(const float* __restrict__ x, int stride, const float (&tp)[9], float* __restrict__ y) {
+  u64 v[R + 8];
+#pragma unroll
+  for (int q = 0; q < R + 8; ++q) v[q] = *reinterpret_cast<const u64*>(x + q * stride);
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    u64 acc = 0ull;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc = fma2(pk2(tp[k], tp[k]), v[j + 8 - k], acc);
+    *reinterpret_cast<u64*>(y + j * stride) = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256, 3) fe_post9_kernel(PostArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const int tid = threadIdx.x;
+  constexpr int W = 9, h = 4, HL = W - 1 + h, HR = h, NR = PT + HL + HR;
+  const int MS = pad4odd(a.n_mels), CS = pad4odd(a.n_ceps);
+  const int C8 = (a.n_c1 + 7) & ~7;
+  float* sdct = sm;                        // [n_mels][C8] transposed, permuted basis
+  float* scep = sdct + a.n_mels * C8;      // [NR][CS]
+  float* smel = scep + NR * CS;            // [NR][MS]
+  float* sd1 = smel;                       // [nd][CS] first-order deltas: the mel rows are dead by then
+  const int nq = a.n_mels >> 2, qblk = a.n_ceps >> 2, qrow = 3 * qblk, ncol = a.n_ceps >> 1;
+  const uint32_t mg_c8 = fdiv_magic(C8), mg_nq = fdiv_magic(nq), mg_col = fdiv_magic(ncol);
+  const uint32_t mg_qrow = fdiv_magic(qrow), mg_qblk = fdiv_magic(qblk);
+  for (int i = tid; i < a.n_mels * C8; i += 256) {
+    const int m = fdiv(i, mg_c8), sl = i - m * C8;
+    sdct[i] = (sl < a.n_ceps) ? a.dct[(sl + 1) * a.n_mels + m] : (sl == a.n_ceps ? a.dct[m] : 0.f);
+  }
+  float tp[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) tp[k] = a.taps[k];
+  const int64_t per = (a.n_tiles + gridDim.x - 1) / gridDim.x;
+  const int64_t tile_lo = per * blockIdx.x, tile_hi = min(a.n_tiles, tile_lo + per);
+  if (tile_lo >= tile_hi) return;
+  int u = find_segment(a.tile2_off, a.n_utt, tile_lo);
+  int64_t u_end = a.tile2_off[u + 1];
+  for (int64_t tile = tile_lo; tile < tile_hi; ++tile) {
+    while (tile >= u_end) { ++u; u_end = a.tile2_off[u + 1]; }
+    const int64_t base = a.frame_off[u];
+    const int T = (int)(a.frame_off[u + 1] - base);
+    const int t0 = (int)(tile - a.tile2_off[u]) * PT;
+    const int nf = min(PT, T - t0);
+    const int lo = max(0, t0 - HL), hi = min(T, t0 + nf + HR);
+    const int nrows = hi - lo;
+    const float floor_db = (a.top_db >= 0.f) ? ordered_to_float(a.umax[u]) - a.top_db : -FLT_MAX;
+    __syncthreads();   // the previous tile is done with the buffers (and the table fill on the first trip)
+    {
+      float4* g4 = reinterpret_cast<float4*>(a.mspec + (base + lo) * a.n_mels);
+      const int n4 = nrows * nq;
+      for (int i0 = tid; i0 < n4; i0 += 4 * 256) {
+        float4 vv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = i0 + k * 256;
+          vv[k] = (i < n4) ? g4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int i = i0 + k * 256;
+          if (i < n4) {
+            const int r = fdiv(i, mg_nq), q = i - r * nq;
+            float4 v = vv[k];
+            const bool clip = fminf(fminf(v.x, v.y), fminf(v.z, v.w)) < floor_db;
+            v.x = fmaxf(v.x, floor_db); v.y = fmaxf(v.y, floor_db);
+            v.z = fmaxf(v.z, floor_db); v.w = fmaxf(v.w, floor_db);
+            *reinterpret_cast<float4*>(smel + r * MS + 4 * q) = v;
+            const int t = lo + r;
+            if (clip && a.write_mspec && t >= t0 && t < t0 + nf) g4[i] = v;   // unclipped rows are already final
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // DCT (signal.py:1711), 2 rows x 8 slots per thread, m ascending from a zero accumulator
+    {
+      const int half = (nrows + 1) >> 1;
+      const int ncg = C8 >> 3, dstride = C8 >> 2;
+      const uint32_t mg_half = fdiv_magic(half);
+      for (int i = tid; i < half * ncg; i += 256) {
+        const int g = fdiv(i, mg_half), r0 = i - g * half;
+        const bool two = r0 + half < nrows;
+        const int r1 = two ? r0 + half : r0;
+        const float4* m0 = reinterpret_cast<const float4*>(smel + r0 * MS);
+        const float4* m1 = reinterpret_cast<const float4*>(smel + r1 * MS);
+        const ulonglong2* dq = reinterpret_cast<const ulonglong2*>(sdct + 8 * g);
+        u64 pa0[4] = {0ull, 0ull, 0ull, 0ull}, pa1[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll 2
+        for (int m4 = 0; m4 < nq; ++m4) {
+          const float4 xa = m0[m4], xb = m1[m4];
+          const float x0[4] = {xa.x, xa.y, xa.z, xa.w}, x1[4] = {xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const ulonglong2 da = dq[(4 * m4 + e) * dstride], db = dq[(4 * m4 + e) * dstride + 1];
+            const u64 xx0 = pk2(x0[e], x0[e]), xx1 = pk2(x1[e], x1[e]);
+            pa0[0] = fma2(da.x, xx0, pa0[0]); pa1[0] = fma2(da.x, xx1, pa1[0]);
+            pa0[1] = fma2(da.y, xx0, pa0[1]); pa1[1] = fma2(da.y, xx1, pa1[1]);
+            pa0[2] = fma2(db.x, xx0, pa0[2]); pa1[2] = fma2(db.x, xx1, pa1[2]);
+            pa0[3] = fma2(db.y, xx0, pa0[3]); pa1[3] = fma2(db.y, xx1, pa1[3]);
+          }
+        }
+        const int s0 = 8 * g;
+        if (s0 + 3 < a.n_ceps) {
+          *reinterpret_cast<ulonglong2*>(scep + r0 * CS + s0) = make_ulonglong2(pa0[0], pa0[1]);
+          if (two) *reinterpret_cast<ulonglong2*>(scep + r1 * CS + s0) = make_ulonglong2(pa1[0], pa1[1]);
+        }
+        if (s0 + 7 < a.n_ceps) {
+          *reinterpret_cast<ulonglong2*>(scep + r0 * CS + s0 + 4) = make_ulonglong2(pa0[2], pa0[3]);
+          if (two) *reinterpret_cast<ulonglong2*>(scep + r1 * CS + s0 + 4) = make_ulonglong2(pa1[2], pa1[3]);
+        }
+        if (a.c0 != nullptr && (s0 == a.n_ceps || s0 + 4 == a.n_ceps)) {
+          const bool first = s0 == a.n_ceps;
+          const int ta = lo + r0, tb = lo + r1;
+          if (ta >= t0 && ta < t0 + nf) a.c0[base + ta] = lo32(first ? pa0[0] : pa0[2]);
+          if (two && tb >= t0 && tb < t0 + nf) a.c0[base + tb] = lo32(first ? pa1[0] : pa1[2]);
+        }
+      }
+    }
+    __syncthreads();   // scep complete; smel may now be overwritten by sd1
+    // first-order deltas D(uu) for uu in [ulo, t0 + nf): blocks of P9_R rows x 2 coefficients; rows that touch an
+    // utterance edge go one by one
+    const int ulo = t0 - (W - 1);
+    const int nd = t0 + nf - ulo;
+    float* sd2 = sd1 + nd * CS;   // [nf][CS] second-order deltas
+    {
+      const int ng = (nd + P9_R - 1) / P9_R;
+      for (int i = tid; i < ng * ncol; i += 256) {
+        const int rg = fdiv(i, mg_col), c = (i - rg * ncol) * 2;
+        const int r0 = P9_R * rg, uu0 = ulo + r0;
+        if (r0 + P9_R - 1 < nd && uu0 - h >= 0 && uu0 + P9_R - 1 + h <= T - 1) {
+          fir9x2<P9_R>(scep + (uu0 - h - lo) * CS + c, CS, tp, sd1 + r0 * CS + c);
+          continue;
+        }
+        for (int cc = c; cc < c + 2; ++cc)
+          for (int r = r0; r < min(r0 + P9_R, nd); ++r) {
+            const int uu = ulo + r;
+            float acc = 0.f;
+            if (uu - h >= 0 && uu + h <= T - 1) {   // interior: no clamping
+              const float* p = scep + (uu + h - lo) * CS + cc;
+#pragma unroll
+              for (int k = 0; k < W; ++k) acc = fmaf(tp[k], p[-k * CS], acc);
+            } else if (uu >= -(h + 1)) {
+#pragma unroll
+              for (int k = 0; k < W; ++k) {
+                const int t = min(max(uu + h - k, 0), T - 1);
+                acc = fmaf(tp[k], scep[(t - lo) * CS + cc], acc);
+              }
+            } else {  // zero initial state of the causal filter
+              const int j = uu + 2 * W - h - 1;
+              float ts = 0.f;
+#pragma unroll
+              for (int k = 0; k < W; ++k) if (k <= j) ts += tp[k];
+              acc = ts * scep[(0 - lo) * CS + cc];
+            }
+            sd1[r * CS + cc] = acc;
+          }
+      }
+    }
+    __syncthreads();
+    // second-order deltas: DD(t) = sum_k taps[k] D(t - k), every input row is held (no edges)
+    {
+      const int ng = (nf + P9_R - 1) / P9_R;
+      for (int i = tid; i < ng * ncol; i += 256) {
+        const int rg = fdiv(i, mg_col), c = (i - rg * ncol) * 2;
+        const int r0 = P9_R * rg;   // row t = t0 + r0, its D row index is t - ulo = r0 + W - 1
+        if (r0 + P9_R - 1 < nf) {
+          fir9x2<P9_R>(sd1 + r0 * CS + c, CS, tp, sd2 + r0 * CS + c);
+          continue;
+        }
+        for (int cc = c; cc < c + 2; ++cc)
+          for (int r = r0; r < min(r0 + P9_R, nf); ++r) {
+            float acc = 0.f;
+            const float* p = sd1 + (r + W - 1) * CS + cc;
+#pragma unroll
+            for (int k = 0; k < W; ++k) acc = fmaf(tp[k], p[-k * CS], acc);
+            sd2[r * CS + cc] = acc;
+          }
+      }
+    }
+    __syncthreads();
+    // rows [static | delta | delta-delta], one float4 per load and store
+    float4* fout4 = reinterpret_cast<float4*>(a.feat + (base + t0) * (3 * a.n_ceps));
+    for (int i = tid; i < nf * qrow; i += 256) {
+      const int r = fdiv(i, mg_qrow), q = i - r * qrow;
+      const int o = fdiv(q, mg_qblk), c = 4 * (q - o * qblk);
+      const float* src = (o == 0) ? scep + (t0 + r - lo) * CS + c
+                                  : (o == 1 ? sd1 + (t0 + r - ulo) * CS + c : sd2 + r * CS + c);
+      fout4[i] = *reinterpret_cast<const float4*>(src);
+    }
   }  // tile loop
 }
 
@@ -1796,16 +2068,24 @@ int fe_launch(odin_fe* fe, const void* d_pcm, int pcm_dtype, int n_utt, int64_t 
     const int HL = (c.delta_order >= 2) ? (c.delta_width - 1 + h) : (c.delta_order == 1 ? h : 0);
     const int HR = (c.delta_order >= 1) ? h : 0;
     const int NR = PT + HL + HR, ND = PT + ((c.delta_order >= 2) ? c.delta_width - 1 : 0);
+    const bool post9 = c.delta_width == 9 && c.delta_order == 2 && c.n_ceps > 0 && (c.n_ceps & 3) == 0 && (fe->n_mels & 3) == 0 &&
+                       d_feat != nullptr && ((reinterpret_cast<uintptr_t>(d_feat) | reinterpret_cast<uintptr_t>(d_mspec)) & 15) == 0 &&
+                       getenv("ODIN_FE_POST_GENERIC") == nullptr;
     // sd1 ([ND][n_ceps]) and sd2 ([PT][n_ceps]) alias the mel rows
     const size_t mel_or_d1 = std::max((size_t)NR * (fe->n_mels | 1), (size_t)(ND + PT) * c.n_ceps);
-    size_t smem = sizeof(float) * (mel_or_d1 + (size_t)NR * fe->n_c1 + (size_t)((fe->n_c1 + 7) & ~7) * fe->n_mels +
+    size_t smem = sizeof(float) * (mel_or_d1 + (((size_t)NR * fe->n_c1 + 3) & ~size_t(3)) + (size_t)((fe->n_c1 + 7) & ~7) * fe->n_mels +
                                    ((c.delta_width + 3) & ~3) + 4);
+    if (post9) {
+      const size_t CS = pad4odd(c.n_ceps), MS = pad4odd(fe->n_mels);
+      smem = sizeof(float) * ((size_t)((fe->n_c1 + 7) & ~7) * fe->n_mels + (size_t)NR * CS + std::max((size_t)NR * MS, (size_t)(ND + PT) * CS));
+    }
     if (smem > 227 * 1024) return set_error(ODIN_EINVAL, "post kernel needs %zu B smem", smem);
-    ODIN_CUDA_CHECK(cudaFuncSetAttribute(fe_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kpost = post9 ? fe_post9_kernel : fe_post_kernel;
+    ODIN_CUDA_CHECK(cudaFuncSetAttribute(kpost, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     p.n_tiles = n_tiles2;
     const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(3, (227 * 1024) / (smem + 1024)));
     const int64_t pgrid = std::min<int64_t>(n_tiles2, (int64_t)sm_count() * per_sm);
-    fe_post_kernel<<<(unsigned)pgrid, 256, smem, st>>>(p);
+    kpost<<<(unsigned)pgrid, 256, smem, st>>>(p);
     ODIN_LAUNCH_CHECK("fe_post_kernel");
   }
   ODIN_CUDA_CHECK(cudaEventRecord(fe->ev[3], st));
