@@ -25,7 +25,11 @@
 //                         orthogonal yields U^T T = diag(s) V^T directly, without forming T T^T or U; one launch
 //                         per round of a round-robin tournament (tv / 2 disjoint pairs per round, a 4-CTA
 //                         cluster per pair with the dot products reduced through distributed shared memory)
+#include <dlfcn.h>
+#include <stdlib.h>
+
 #include <algorithm>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -639,6 +643,55 @@ constexpr size_t SMEM_LIMIT = 200 * 1024;   // beyond this a kernel's matrices m
 // per-CTA global slabs for the sizes whose systems do not fit shared memory (tv > ~150): `ctas` slabs of
 // `doubles_per_cta`; the data stay L2-resident while a CTA works on them, but the factorisations are not blocked,
 // so this route is much slower per FLOP than the shared-memory one
+// ---- symmetric eigen-solver for tv > TMAT_GRAM_MAX: cuSOLVER's Dsyevd, bound at run time ------------------------------
+// The Gram pre-rotation needs the eigenvectors of ONE tv x tv matrix per M-step (tv 400-600 at the NIST-SRE recipe's
+// scale).  That is a plain LAPACK call outside any hot loop, so beyond the size tmat_eig_kernel holds in shared memory it
+// goes to the CUDA toolkit's library -- loaded with dlopen so that libodin_b200.so does not depend on it; when the
+// library cannot be loaded the pre-rotation is skipped and the one-sided sweeps do all the work (slower, same result).
+namespace {
+struct Cusolver {
+  bool tried = false;
+  void* lib = nullptr;
+  void* handle = nullptr;
+  int (*create)(void**) = nullptr;
+  int (*set_stream)(void*, cudaStream_t) = nullptr;
+  int (*bufsize)(void*, int, int, int, const double*, int, const double*, int*) = nullptr;
+  int (*syevd)(void*, int, int, int, double*, int, double*, double*, int, int*) = nullptr;
+};
+Cusolver g_cusolver;
+std::mutex g_cusolver_mu;
+
+bool cusolver_ready() {
+  std::lock_guard<std::mutex> lock(g_cusolver_mu);
+  Cusolver& c = g_cusolver;
+  if (c.tried) return c.handle != nullptr;
+  c.tried = true;
+  const char* names[] = {"libcusolver.so.11", "libcusolver.so", "/usr/local/cuda/lib64/libcusolver.so.11",
+                         "/usr/local/cuda/targets/x86_64-linux/lib/libcusolver.so.11"};
+  for (const char* n : names)
+    if ((c.lib = dlopen(n, RTLD_NOW | RTLD_LOCAL)) != nullptr) break;
+  if (c.lib == nullptr) return false;
+  c.create = reinterpret_cast<decltype(c.create)>(dlsym(c.lib, "cusolverDnCreate"));
+  c.set_stream = reinterpret_cast<decltype(c.set_stream)>(dlsym(c.lib, "cusolverDnSetStream"));
+  c.bufsize = reinterpret_cast<decltype(c.bufsize)>(dlsym(c.lib, "cusolverDnDsyevd_bufferSize"));
+  c.syevd = reinterpret_cast<decltype(c.syevd)>(dlsym(c.lib, "cusolverDnDsyevd"));
+  if (!c.create || !c.set_stream || !c.bufsize || !c.syevd) return false;
+  if (c.create(&c.handle) != 0) c.handle = nullptr;
+  return c.handle != nullptr;
+}
+}  // namespace
+
+// Dsyevd leaves the eigenvectors in the columns of a column-major matrix, eigenvalues ascending; the pre-rotation wants
+// Vout [tv][tv] row-major with column i = eigenvector of the i-th LARGEST eigenvalue.  A failed factorisation (info != 0)
+// yields the identity: the one-sided sweeps then start from the unrotated T.
+__global__ void tmat_eigperm_kernel(const double* __restrict__ A, const int* __restrict__ info, int n, double* __restrict__ Vout) {
+  const bool ok = *info == 0;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n * n; e += gridDim.x * blockDim.x) {
+    const int r = e / n, i = e - r * n;
+    Vout[e] = ok ? A[r + (size_t)(n - 1 - i) * n] : (r == i ? 1.0 : 0.0);
+  }
+}
+
 static int reserve_gws(odin_tmat* t, size_t doubles_per_cta, int ctas) {
   const size_t need = doubles_per_cta * (size_t)ctas;
   if (need <= t->gws_cap) return ODIN_OK;
@@ -797,6 +850,31 @@ int tmat_mstep(odin_tmat* t, const double* d_acc, int min_div, int orthogonalize
     // T <- U^T T (through the T_invS buffer, rebuilt by the refresh at the end)
     if ((rc = gemm(tv, (int)t->MD, tv, t->d_U, 1, tv, t->d_Tm, t->MD, 1, t->d_TinvS, t->MD, 0.0, st))) return rc;
     ODIN_CUDA_CHECK(cudaMemcpyAsync(t->d_Tm, t->d_TinvS, sizeof(double) * (size_t)tv * t->MD, cudaMemcpyDeviceToDevice, st));
+  }
+  if (orthogonalize && t->tv > TMAT_GRAM_MAX && getenv("ODIN_TMAT_NO_PREROT") == nullptr && cusolver_ready()) {
+    // the same pre-rotation beyond the shared-memory eigen-solver: at tv 400, 2048 x 60 the one-sided sweeps alone took
+    // 11 passes over the 393 MB matrix (4 389 launches, 0.97 s of a 1.24 s M-step; tools/tmat_scale.py)
+    const int tv = t->tv;
+    const size_t need = (size_t)33 * tv * tv;   // G | 32 split-K slices, reused as eigenvalues | info | Dsyevd workspace
+    if ((rc = reserve_gws(t, need, 1))) return rc;
+    double* G = t->d_gws;
+    double* W = G + (size_t)tv * tv;
+    int* info = reinterpret_cast<int*>(W + tv);
+    double* work = W + tv + 2;
+    int lwork = 0;
+    Cusolver& cs = g_cusolver;
+    const int CUSOLVER_EIG_MODE_VECTOR = 1, CUBLAS_FILL_MODE_LOWER = 0;
+    if (cs.set_stream(cs.handle, st) == 0 &&
+        cs.bufsize(cs.handle, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, tv, G, tv, W, &lwork) == 0 &&
+        (size_t)lwork + tv + 2 <= (size_t)32 * tv * tv) {
+      if ((rc = gemm(tv, tv, (int)t->MD, t->d_Tm, t->MD, 1, t->d_Tm, 1, t->MD, G, tv, 0.0, st, W, (int64_t)32 * tv * tv))) return rc;
+      if (cs.syevd(cs.handle, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, tv, G, tv, W, work, lwork, info) != 0)
+        return set_error(ODIN_ECUDA, "cusolverDnDsyevd failed (tv %d)", tv);
+      tmat_eigperm_kernel<<<std::min(sm_count() * 4, ceil_div(tv * tv, 256)), 256, 0, st>>>(G, info, tv, t->d_U);
+      ODIN_LAUNCH_CHECK("tmat_eigperm_kernel");
+      if ((rc = gemm(tv, (int)t->MD, tv, t->d_U, 1, tv, t->d_Tm, t->MD, 1, t->d_TinvS, t->MD, 0.0, st))) return rc;
+      ODIN_CUDA_CHECK(cudaMemcpyAsync(t->d_Tm, t->d_TinvS, sizeof(double) * (size_t)tv * t->MD, cudaMemcpyDeviceToDevice, st));
+    }
   }
   if (orthogonalize && t->tv > 1) {
     const int np = t->tv + (t->tv & 1);

@@ -60,11 +60,11 @@ def test_golden_reference_run():
 
 
 @pytest.mark.parametrize("tv,D,M,n_files", [(16, 12, 20, 150), (64, 60, 32, 300), (128, 20, 8, 90), (33, 7, 5, 70),
-                                            (176, 24, 10, 230)])
+                                            (176, 24, 10, 230), (400, 24, 20, 450)])
 def test_em_iteration_vs_oracle(tv, D, M, n_files):
   """One full EM iteration and i-vector extraction on fresh statistics, including tv_dim 128 (the largest whose
   systems fit shared memory next to the M-step's right-hand sides), an odd one (a bye in the Jacobi tournament) and
-  176 (every factorisation on the global-memory route)."""
+  176 (every factorisation on the global-memory route) and 400 (the NIST-SRE recipe's tv_dim)."""
   from odin_b200.ml import Tmatrix
   sigma, Z, F = _problem(tv + D, D, M, n_files)
   t = Tmatrix(tv, _gmm_stub(sigma), niter=1)
