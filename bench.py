@@ -592,7 +592,7 @@ def cfg5_leg(torch, args, rank, world, dist):
                                  "512-mix per-utterance Z / F-hat" % n_utt, "frames_per_gpu": T, "nmix": M},
           "frontend": {"ms": fe_s * 1e3, "frames_per_s": T * world / fe_s},
           "utt_stats": {"ms": st_s * 1e3, "frames_per_s": T * world / st_s, "utterances_per_s": n_utt * world / st_s,
-                        "kernels": "fp32 CUDA-core route of odin_gmm_utt_stats (short utterances: one launch per batch)"}}
+                        "kernels": "tcgen05 3xFP16 kernels in segmented mode (odin_gmm_utt_stats -> gmm_utt_stats_hseg: utterances padded to 64-frame tiles, accumulator drained per utterance)"}}
 
 
 # ---------------------------------------------------------------------------

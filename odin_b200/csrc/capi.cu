@@ -640,7 +640,7 @@ int odin_gmm_create(int32_t feat_dim, int32_t max_nmix, odin_gmm_t** out) {
 void odin_gmm_destroy(odin_gmm_t* g) {
   if (!g) return;
   cudaFree(g->d_mean); cudaFree(g->d_var); cudaFree(g->d_w); cudaFree(g->d_Wk); cudaFree(g->d_cst);
-  cudaFree(g->d_Whi); cudaFree(g->d_Whs); cudaFree(g->d_Wlo); cudaFree(g->d_part); cudaFree(g->d_utt_acc); cudaFree(g->d_lse); cudaFree(g->d_prev); cudaFree(g->d_off);
+  cudaFree(g->d_Whi); cudaFree(g->d_Whs); cudaFree(g->d_Wlo); cudaFree(g->d_part); cudaFree(g->d_utt_acc); cudaFree(g->d_segX); cudaFree(g->d_segmask); cudaFree(g->d_segtile); cudaFree(g->d_segoff); cudaFree(g->d_lse); cudaFree(g->d_prev); cudaFree(g->d_off);
   gmm_h_free(g);
   if (g->h_off) cudaFreeHost(g->h_off);
   for (int i = 0; i < 3; ++i) if (g->ev[i]) cudaEventDestroy(g->ev[i]);
@@ -824,10 +824,19 @@ int odin_gmm_utt_stats(odin_gmm_t* g, const float* d_X, const uint8_t* d_sad, co
       if (rc) return rc;
     }
     const int64_t total = h_frame_offsets[n_utt] - h_frame_offsets[0];
-    if (use == 3 && (impl == 3 || total >= (int64_t)1024 * n_utt)) {
+    if (use == 3 && total >= (int64_t)1024 * n_utt) {
       ODIN_CUDA_CHECK(cudaStreamSynchronize(st));
       return gmm_utt_stats_h(g, d_X + h_frame_offsets[0] * g->D, d_sad ? d_sad + h_frame_offsets[0] : nullptr,
                              h_frame_offsets, n_utt, d_Z, d_Fhat, st);
+    }
+    // ... and batches of SHORT utterances through the same kernels in segmented mode (every utterance padded to whole
+    // 64-frame tiles, the accumulator drained at utterance boundaries): config 5, 3 000 digits at M = 512, 5.7 -> ~1 ms.
+    // Tiny batches stay on the fp32 kernels (the tensor route's fixed cost is five extra launches).
+    static const int seg_env = [] { const char* e = getenv("ODIN_GMM_UTT_SEG"); return e ? atoi(e) : -1; }();
+    if (use == 3 && seg_env != 0 && (impl == 3 || seg_env == 1 || total >= 16384)) {
+      ODIN_CUDA_CHECK(cudaStreamSynchronize(st));
+      return gmm_utt_stats_hseg(g, d_X + h_frame_offsets[0] * g->D, d_sad ? d_sad + h_frame_offsets[0] : nullptr, h_frame_offsets,
+                                n_utt, d_Z, d_Fhat, st);
     }
   }
   if (g->off_cap < n_utt + 1) {

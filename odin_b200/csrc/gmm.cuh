@@ -31,6 +31,12 @@ struct odin_gmm {
   int64_t part_cap = 0;  // float2 elements
   double* d_utt_acc = nullptr;   // per-utterance statistics of a group of utterances (gmm_utt_stats_h)
   int64_t utt_acc_cap = 0;
+  // segmented route (gmm_utt_stats_hseg): utterances padded to whole 64-frame tiles
+  float* d_segX = nullptr;       // [seg_cap, D]
+  uint8_t* d_segmask = nullptr;  // [seg_cap]
+  int* d_segtile = nullptr;      // [seg_cap / 64] utterance of every tile
+  int64_t* d_segoff = nullptr;   // [2][seg_utt_cap] frame offsets | padded offsets
+  int64_t seg_cap = 0, seg_utt_cap = 0;
   // 3xFP16 tcgen05 path (gmm_h.cu): column scales, scaled model images, per-sub-batch frame
   // operand images (A: rows = frames, T: rows = [x^2|x|1] transposed) and 14 - lse2 per frame
   void* d_hscale = nullptr;
@@ -91,6 +97,8 @@ int gmm_frames_create(odin_gmm* g, const float* X, int64_t N, void** out, cudaSt
 void gmm_frames_destroy(void* f);
 int gmm_utt_stats_h(odin_gmm* g, const float* X, const uint8_t* sad, const int64_t* h_off, int n_utt, float* d_Z,
                     float* d_Fhat, cudaStream_t st);
+int gmm_utt_stats_hseg(odin_gmm* g, const float* X, const uint8_t* sad, const int64_t* h_off, int n_utt, float* d_Z,
+                       float* d_Fhat, cudaStream_t st);
 int gmm_estep_frames(odin_gmm* g, const void* f, const uint8_t* sad, int want_second, double* stats,
                      cudaStream_t st);
 

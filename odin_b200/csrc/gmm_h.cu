@@ -43,6 +43,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "gmm.cuh"
 #include "tc_ptx.cuh"
@@ -279,6 +280,10 @@ struct HArgs {
   double* stats;
   int want_second;
   int flush_tiles;
+  // segmented mode (gmm_utt_stats_hseg): per-utterance outputs, the accumulator is flushed where the utterance changes
+  const int* tile_utt;    // [tiles64 + 1] utterance of every 64-frame tile (-1: padding), one sentinel behind the last
+  float* uZ;              // [n_utt, M]      zeroed by the caller
+  float* uF;              // [n_utt, M * D]  raw first-order sums (centred afterwards)
 };
 
 // ---------------------------------------------------------------------------
@@ -457,6 +462,11 @@ gmm_h_combine_kernel(const float2* __restrict__ part, int nparts, int64_t stride
 // ---------------------------------------------------------------------------
 // pass 2: posteriors and statistics
 // ---------------------------------------------------------------------------
+// SEG: the tiles of a CTA are CONTIGUOUS, every tile belongs to one utterance (the caller pads utterances to whole
+// tiles) and the accumulator is drained into that utterance's float32 rows whenever the next tile starts another one --
+// the per-utterance statistics of thousands of short utterances in one launch (the i-vector extractor's
+// input).  !SEG: tiles strided over the CTAs, periodic flush into the packed fp64 statistics of the whole call.
+template <bool SEG>
 __global__ void __launch_bounds__(hk::THREADS, 1) gmm_h_stats_kernel(HArgs a) {
   using namespace hk;
   using namespace ptx;
@@ -469,7 +479,12 @@ __global__ void __launch_bounds__(hk::THREADS, 1) gmm_h_stats_kernel(HArgs a) {
   const int chunk = blockIdx.x;
   const int D = a.D;
   const int64_t n_tiles = 2 * ((a.N + TF1 - 1) / TF1);   // the images are padded to whole super-tiles
-  const int64_t my_tiles = (n_tiles > (int64_t)blockIdx.y) ? (n_tiles - blockIdx.y + gridDim.y - 1) / gridDim.y : 0;
+  const int64_t seg_per = (n_tiles + gridDim.y - 1) / gridDim.y;
+  const int64_t seg_lo = seg_per * blockIdx.y;
+  const int64_t seg_left = n_tiles - seg_lo;
+  const int64_t my_tiles = SEG ? (seg_left <= 0 ? 0 : (seg_left < seg_per ? seg_left : seg_per))
+                               : ((n_tiles > (int64_t)blockIdx.y) ? (n_tiles - blockIdx.y + gridDim.y - 1) / gridDim.y : 0);
+  auto tile_of = [&](int64_t it) -> int64_t { return SEG ? seg_lo + it : (int64_t)blockIdx.y + it * gridDim.y; };
   auto bar = [&](int i) -> uint32_t { return sbase + S_BAR + 8u * i; };
   volatile uint32_t* tmem_ptr_s = reinterpret_cast<volatile uint32_t*>(smem + S_BAR + 8 * SB_TMEM);
 
@@ -518,7 +533,7 @@ __global__ void __launch_bounds__(hk::THREADS, 1) gmm_h_stats_kernel(HArgs a) {
     // ============================================== bulk-copy producer (one lane)
     if (lane == 0) {
       for (int64_t it = 0; it < my_tiles; ++it) {
-        const int64_t tile = blockIdx.y + it * gridDim.y;
+        const int64_t tile = tile_of(it);
         const int64_t st = tile >> 1;
         const int half = (int)(tile & 1);
         {
@@ -552,6 +567,10 @@ __global__ void __launch_bounds__(hk::THREADS, 1) gmm_h_stats_kernel(HArgs a) {
       uint32_t g2_b = 0, g2_bpar = 0, g2_t = 0, g2_tpar = 0;     // cursors of GEMM 2: P' buffer, T slot
       uint32_t flush_left = (uint32_t)a.flush_tiles, d2_phase = 0;
       bool acc = false, need_d2_empty = false;
+      // SEG: utterance of the current tile and of the next two (read two tiles ahead: the load is off the critical path)
+      int u_cur = 0, u_n1 = 0;
+      uint32_t seg_it = 0;
+      if (SEG) { u_cur = __ldg(a.tile_utt + seg_lo); u_n1 = nt > 1 ? __ldg(a.tile_utt + seg_lo + 1) : -2; }
       auto issue_g1 = [&]() {
         mbar_wait_fast(bar0 + 8u * (SB_BUFEMPTY + g1_b), g1_bpar);
         mbar_wait_fast(bar0 + 8u * (SB_AFULL + g1_a), g1_apar);
@@ -584,7 +603,14 @@ __global__ void __launch_bounds__(hk::THREADS, 1) gmm_h_stats_kernel(HArgs a) {
           need_d2_empty = false;
         }
         tc_fence_after();
-        const bool flush = (--flush_left == 0u) || last;
+        bool flush;
+        if (SEG) {
+          const int u_n2 = (seg_it + 2 < nt) ? __ldg(a.tile_utt + seg_lo + seg_it + 2) : -2;
+          flush = last || u_n1 != u_cur;
+          u_cur = u_n1; u_n1 = u_n2; ++seg_it;
+        } else {
+          flush = (--flush_left == 0u) || last;
+        }
         if (elect_one()) {
           const uint32_t d = tmem + TM_D2;
           const uint32_t p0 = tmem + TM_BUF + 64u * g2_b;
@@ -622,13 +648,17 @@ __global__ void __launch_bounds__(hk::THREADS, 1) gmm_h_stats_kernel(HArgs a) {
     const float dsc = a.dsc[chunk * CM2 + row];
     const double* dsj = reinterpret_cast<const double*>(smem + S_DSJ);
     uint32_t d2_phase = 0, flush_left = (uint32_t)a.flush_tiles;
+    int u_cur = 0, u_n1 = 0;
+    if (SEG && my_tiles > 0) { u_cur = __ldg(a.tile_utt + seg_lo); u_n1 = my_tiles > 1 ? __ldg(a.tile_utt + seg_lo + 1) : -2; }
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int b = (int)(it % NBUF);
+      int u_n2 = -2;
+      if (SEG && it + 2 < my_tiles) u_n2 = __ldg(a.tile_utt + seg_lo + it + 2);
       // 14 - lse2[b] of this warp's 32 frames (warp-uniform addresses: one broadcast line per load),
       // issued before the wait so the latency hides behind GEMM 1
       float cbv[32];
       {
-        const int64_t tile = blockIdx.y + it * gridDim.y;
+        const int64_t tile = tile_of(it);
         const float4* cb4 = reinterpret_cast<const float4*>(a.cb + (size_t)tile * TF2) + h * 8;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -654,7 +684,11 @@ __global__ void __launch_bounds__(hk::THREADS, 1) gmm_h_stats_kernel(HArgs a) {
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(bar(SB_PFULL + b));
-      if ((--flush_left == 0u) || it + 1 == my_tiles) {
+      const int u_here = u_cur;
+      bool flush_now;
+      if (SEG) { flush_now = it + 1 == my_tiles || u_n1 != u_cur; u_cur = u_n1; u_n1 = u_n2; }
+      else flush_now = (--flush_left == 0u) || it + 1 == my_tiles;
+      if (flush_now) {
         flush_left = (uint32_t)a.flush_tiles;
         // drain D2[mixture = row, j] into the fp64 statistics (64 columns per warp)
         mbar_wait(bar(SB_D2FULL), d2_phase);
@@ -663,17 +697,26 @@ __global__ void __launch_bounds__(hk::THREADS, 1) gmm_h_stats_kernel(HArgs a) {
         const int m = chunk * CM2 + row;
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
+          const int j0 = 64 * h + 32 * c;
+          if (SEG && (j0 + 32 <= D || (j0 >= 2 * D && !(j0 <= K_ONE && K_ONE < j0 + 32)))) continue;   // S columns / padding only
           float s[32];
           tmem_ld32(tmem + TM_D2 + 64u * h + 32u * c + lane_field, s);
-          if (m < a.M) {
+          if (m < a.M && (!SEG || u_here >= 0)) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              const int j = 64 * h + 32 * c + i;
-              double* dst = nullptr;
-              if (j < D) { if (a.want_second) dst = a.stats + a.M + (size_t)D * a.M + (size_t)j * a.M; }
-              else if (j < 2 * D) dst = a.stats + a.M + (size_t)(j - D) * a.M;
-              else if (j == K_ONE) dst = a.stats;
-              if (dst != nullptr) atomicAdd(dst + m, (double)s[i] * dsj[j]);
+              const int j = j0 + i;
+              if (SEG) {
+                // float32 rows of utterance u_here (red.global.add.f32: an utterance that straddles two CTAs' tile ranges
+                // receives two partial sums); 2^(-14 - ea[j]) is an exact scaling
+                if (j >= D && j < 2 * D) atomicAdd(a.uF + ((size_t)u_here * a.M + m) * D + (j - D), s[i] * (float)dsj[j]);
+                else if (j == K_ONE) atomicAdd(a.uZ + (size_t)u_here * a.M + m, s[i] * (float)dsj[j]);
+              } else {
+                double* dst = nullptr;
+                if (j < D) { if (a.want_second) dst = a.stats + a.M + (size_t)D * a.M + (size_t)j * a.M; }
+                else if (j < 2 * D) dst = a.stats + a.M + (size_t)(j - D) * a.M;
+                else if (j == K_ONE) dst = a.stats;
+                if (dst != nullptr) atomicAdd(dst + m, (double)s[i] * dsj[j]);
+              }
             }
           }
         }
@@ -768,20 +811,23 @@ static int h_launch_prepare(odin_gmm* g, const HScale* sc, cudaStream_t st) {
                                                           reinterpret_cast<uint32_t*>(g->d_hWimg), g->d_hdsc);
   ODIN_LAUNCH_CHECK("gmm_h_prepare_kernel");
   ODIN_CUDA_CHECK(cudaFuncSetAttribute(gmm_h_lse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hk::L_SMEM));
-  ODIN_CUDA_CHECK(cudaFuncSetAttribute(gmm_h_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hk::S_SMEM));
+  ODIN_CUDA_CHECK(cudaFuncSetAttribute(gmm_h_stats_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hk::S_SMEM));
+  ODIN_CUDA_CHECK(cudaFuncSetAttribute(gmm_h_stats_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hk::S_SMEM));
   return ODIN_OK;
 }
 
 // pass 1 + combine + pass 2 over n frames whose operand images start at imgA / imgT
 static int h_launch_passes(odin_gmm* g, const HScale* sc, const unsigned char* imgA, const unsigned char* imgT,
                            int64_t n, int64_t part_stride, const uint8_t* sad, int want_second, double* stats,
-                           bool record, cudaStream_t st) {
+                           bool record, cudaStream_t st, const int* tile_utt = nullptr, float* uZ = nullptr,
+                           float* uF = nullptr) {
   const int D = g->D, M = g->M;
   const int mpad = ceil_div(M, hk::CM1) * hk::CM1;
   const int nch1 = mpad / hk::CM1, nch2 = mpad / hk::CM2;
   const int64_t nsuper = ceil_div<int64_t>(n, hk::TF1);
-  double* statL = stats + (stats_size(D, M) - 2);
+  double* statL = stats ? stats + (stats_size(D, M) - 2) : nullptr;
   HArgs a{};
+  a.tile_utt = tile_utt; a.uZ = uZ; a.uF = uF;
   a.N = n; a.D = D; a.M = M;
   a.imgA = imgA;
   a.imgT = imgT;
@@ -807,7 +853,8 @@ static int h_launch_passes(odin_gmm* g, const HScale* sc, const unsigned char* i
   if (record) ODIN_CUDA_CHECK(cudaEventRecord(g->ev[1], st));
   {
     const int64_t splits = std::max<int64_t>(1, std::min<int64_t>(sm_count() / nch2, nsuper * 2));
-    gmm_h_stats_kernel<<<dim3(nch2, (unsigned)splits), hk::THREADS, hk::S_SMEM, st>>>(a);
+    if (tile_utt != nullptr) gmm_h_stats_kernel<true><<<dim3(nch2, (unsigned)splits), hk::THREADS, hk::S_SMEM, st>>>(a);
+    else gmm_h_stats_kernel<false><<<dim3(nch2, (unsigned)splits), hk::THREADS, hk::S_SMEM, st>>>(a);
     ODIN_LAUNCH_CHECK("gmm_h_stats_kernel");
   }
   if (record) {
@@ -910,6 +957,118 @@ int gmm_utt_stats_h(odin_gmm* g, const float* X, const uint8_t* sad, const int64
                                              d_Fhat + (int64_t)u0 * M * D);
     ODIN_LAUNCH_CHECK("gmm_h_centre_kernel");
   }
+  return ODIN_OK;
+}
+
+// ---- per-utterance statistics of MANY SHORT utterances in one tensor-core launch sequence -----------------------------
+// The utterances of a group are laid out back to back, each padded to whole 64-frame tiles (zero rows, masked out of the
+// posteriors through cb = -1e30 like SAD-rejected frames), so that a tile of pass 2 belongs to ONE utterance; pass 1 and the
+// images do not care about the boundaries.  gmm_h_stats_kernel<true> then drains its accumulator at every utterance change.
+__global__ void __launch_bounds__(256) gmm_h_segpad_kernel(const float* __restrict__ X, const uint8_t* __restrict__ sad, int D,
+                                                           const int* __restrict__ tile_utt, const int64_t* __restrict__ off,
+                                                           const int64_t* __restrict__ poff, int u0, int64_t p0,
+                                                           float* __restrict__ Xp, uint8_t* __restrict__ mask) {
+  const int64_t tile = blockIdx.x;
+  const int u = tile_utt[tile];
+  const int d4 = D >> 2;
+  float4* dst = reinterpret_cast<float4*>(Xp + tile * hk::TF2 * D);
+  int64_t src0 = 0, live = 0;
+  if (u >= 0) {
+    const int64_t li0 = p0 + tile * hk::TF2 - poff[u0 + u];   // index of the tile's first frame inside its utterance
+    src0 = off[u0 + u] + li0;
+    live = off[u0 + u + 1] - src0;                             // frames of the utterance from there on (may exceed the tile)
+  }
+  const float4* src = reinterpret_cast<const float4*>(X + src0 * D);
+  for (int i = threadIdx.x; i < hk::TF2 * d4; i += 256) {
+    const int r = i / d4;
+    dst[i] = r < live ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (threadIdx.x < hk::TF2) {
+    const int r = threadIdx.x;
+    mask[tile * hk::TF2 + r] = (r < live && (sad == nullptr || sad[src0 + r] != 0)) ? 1 : 0;
+  }
+}
+
+// F-hat[u, m * D + d] = F[u, m, d] - mean[d, m] Z[u, m], in place
+__global__ void __launch_bounds__(256) gmm_h_segcentre_kernel(const float* __restrict__ Z, const float* __restrict__ mean, int D,
+                                                              int M, int64_t total, float* __restrict__ F) {
+  const int64_t md = (int64_t)M * D;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int64_t u = i / md, r = i - u * md;
+    const int m = (int)(r / D), d = (int)(r - (int64_t)m * D);
+    F[i] = F[i] - mean[(int64_t)d * M + m] * Z[u * M + m];
+  }
+}
+
+int gmm_utt_stats_hseg(odin_gmm* g, const float* X, const uint8_t* sad, const int64_t* h_off, int n_utt, float* d_Z,
+                       float* d_Fhat, cudaStream_t st) {
+  const int D = g->D, M = g->M;
+  const int64_t base = h_off[0], N = h_off[n_utt] - base;
+  ODIN_CUDA_CHECK(cudaMemsetAsync(d_Z, 0, sizeof(float) * (size_t)n_utt * M, st));
+  ODIN_CUDA_CHECK(cudaMemsetAsync(d_Fhat, 0, sizeof(float) * (size_t)n_utt * M * D, st));
+  if (N <= 0) return ODIN_OK;
+  // padded offsets and groups of whole utterances of at most `cap` padded frames
+  std::vector<int64_t> off(n_utt + 1), poff(n_utt + 1);
+  int64_t maxpad = 0;
+  poff[0] = 0;
+  for (int u = 0; u <= n_utt; ++u) off[u] = h_off[u] - base;
+  for (int u = 0; u < n_utt; ++u) {
+    const int64_t pl = ceil_div<int64_t>(off[u + 1] - off[u], hk::TF2) * hk::TF2;
+    poff[u + 1] = poff[u] + pl;
+    maxpad = std::max(maxpad, pl);
+  }
+  const int64_t cap = std::max<int64_t>(h_sub_batch(), ceil_div<int64_t>(maxpad, hk::TF1) * hk::TF1);
+  const int64_t sub = std::min<int64_t>(cap, ceil_div<int64_t>(poff[n_utt], hk::TF1) * hk::TF1);
+  int rc = h_reserve(g, sub, true);
+  if (rc) return rc;
+  const int64_t tiles_cap = sub / hk::TF2;
+  if (g->seg_cap < sub || g->seg_utt_cap < n_utt + 1) {
+    cudaFree(g->d_segX); cudaFree(g->d_segmask); cudaFree(g->d_segtile); cudaFree(g->d_segoff);
+    g->d_segX = nullptr; g->d_segmask = nullptr; g->d_segtile = nullptr; g->d_segoff = nullptr;
+    g->seg_cap = 0; g->seg_utt_cap = 0;
+    ODIN_CUDA_CHECK(cudaMalloc(&g->d_segX, sizeof(float) * (size_t)sub * D));
+    ODIN_CUDA_CHECK(cudaMalloc(&g->d_segmask, (size_t)sub));
+    ODIN_CUDA_CHECK(cudaMalloc(&g->d_segtile, sizeof(int) * (size_t)tiles_cap));
+    ODIN_CUDA_CHECK(cudaMalloc(&g->d_segoff, sizeof(int64_t) * 2 * (size_t)(n_utt + 1)));
+    g->seg_cap = sub; g->seg_utt_cap = n_utt + 1;
+  }
+  int64_t* d_off = g->d_segoff;
+  int64_t* d_poff = d_off + (n_utt + 1);
+  ODIN_CUDA_CHECK(cudaMemcpyAsync(d_off, off.data(), sizeof(int64_t) * (n_utt + 1), cudaMemcpyHostToDevice, st));
+  ODIN_CUDA_CHECK(cudaMemcpyAsync(d_poff, poff.data(), sizeof(int64_t) * (n_utt + 1), cudaMemcpyHostToDevice, st));
+  HScale* sc = reinterpret_cast<HScale*>(g->d_hscale);
+  // one data range (-> exact power-of-two scales) and one set of scaled model images for the whole batch
+  if ((rc = h_launch_range(X, N, D, sc, st))) return rc;
+  if ((rc = h_launch_prepare(g, sc, st))) return rc;
+  std::vector<int> tile_utt;
+  for (int u0 = 0; u0 < n_utt;) {
+    int u1 = u0;
+    while (u1 < n_utt && poff[u1 + 1] - poff[u0] <= sub) ++u1;   // (a single utterance always fits: sub >= maxpad)
+    const int64_t np = poff[u1] - poff[u0];                        // padded frames of the group: a multiple of 64
+    const int64_t nsuper = ceil_div<int64_t>(np, hk::TF1);
+    const int64_t nt = nsuper * 2;
+    tile_utt.assign((size_t)nt, -1);
+    for (int u = u0; u < u1; ++u)
+      for (int64_t t = (poff[u] - poff[u0]) / hk::TF2; t < (poff[u + 1] - poff[u0]) / hk::TF2; ++t) tile_utt[(size_t)t] = u - u0;
+    ODIN_CUDA_CHECK(cudaMemcpyAsync(g->d_segtile, tile_utt.data(), sizeof(int) * (size_t)nt, cudaMemcpyHostToDevice, st));
+    gmm_h_segpad_kernel<<<(unsigned)nt, 256, 0, st>>>(X, sad, D, g->d_segtile, d_off, d_poff, u0, poff[u0], g->d_segX,
+                                                     g->d_segmask);
+    ODIN_LAUNCH_CHECK("gmm_h_segpad_kernel");
+    const int64_t n = nsuper * hk::TF1;
+    gmm_h_image_kernel<<<(unsigned)nsuper, 256, 0, st>>>(g->d_segX, n, D, sc, reinterpret_cast<unsigned char*>(g->d_himgA),
+                                                          reinterpret_cast<unsigned char*>(g->d_himgT));
+    ODIN_LAUNCH_CHECK("gmm_h_image_kernel");
+    rc = h_launch_passes(g, sc, reinterpret_cast<const unsigned char*>(g->d_himgA),
+                         reinterpret_cast<const unsigned char*>(g->d_himgT), n, sub, g->d_segmask, 0, nullptr, false, st,
+                         g->d_segtile, d_Z + (int64_t)u0 * M, d_Fhat + (int64_t)u0 * M * D);
+    if (rc) return rc;
+    u0 = u1;
+  }
+  const int64_t total = (int64_t)n_utt * M * D;
+  gmm_h_segcentre_kernel<<<(unsigned)std::min<int64_t>(ceil_div<int64_t>(total, 256 * 8), (int64_t)sm_count() * 16), 256, 0, st>>>(
+      d_Z, g->d_mean, D, M, total, d_Fhat);
+  ODIN_LAUNCH_CHECK("gmm_h_segcentre_kernel");
+  ODIN_CUDA_CHECK(cudaStreamSynchronize(st));   // the pageable staging vectors of this call go out of scope
   return ODIN_OK;
 }
 

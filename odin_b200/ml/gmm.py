@@ -797,7 +797,7 @@ class GMM(object):
     return Z if zero else Fh
 
   def transform_to_disk(self, X, indices, sad=None, pathZ=None, pathF=None, name_path=None,
-                        dtype='float32', device='gpu', ncpu=None, override=True, utt_batch=256):
+                        dtype='float32', device='gpu', ncpu=None, override=True, utt_batch=2048):
     """gmm_tmat.py:769-913.  Z [n_utt, M] and Fhat [n_utt, M*D] are written as
     .npy files (the reference's bigarray.MmapArray container is a third-party
     format outside this path); returns the utterance names in processing order
@@ -840,6 +840,7 @@ class GMM(object):
       if resident:
         d_sad_all = torch.from_numpy(sad).cuda()
     Zs, Fs = [], []
+    utt_batch = max(1, min(int(utt_batch), (1 << 31) // (4 * M * (self._kdim + 1))))   # <= 2 GiB of statistics per launch
     for b0 in range(0, len(mine), utt_batch):
       rows = mine[b0:b0 + utt_batch]
       spans = [(int(indices[i][1][0]), int(indices[i][1][1])) for i in rows]

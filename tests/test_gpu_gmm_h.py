@@ -187,6 +187,48 @@ def test_h_per_utterance_statistics():
     assert relmax(Zu, zr) < 5e-5 and relmax(Fu, fr) < 5e-5, (relmax(Zu, zr), relmax(Fu, fr))
 
 
+def test_h_per_utterance_statistics_short_utterances_segmented():
+  """Thousands of SHORT utterances (the digits of config 5) through the tcgen05 kernels in segmented mode
+  (odin_gmm_utt_stats -> gmm_utt_stats_hseg: utterances padded to whole 64-frame tiles, the accumulator drained at
+  every utterance change): lengths around the tile size (1, 63, 64, 65, 128, 129 frames), an empty utterance, a SAD mask,
+  a long utterance in the middle, M not a multiple of the 128-mixture chunk; against the oracle and the fp32 route."""
+  import tempfile
+  from odin_b200.ml import GMM
+  from oracle import gmm as OG
+  rng = np.random.RandomState(5)
+  D, M = 60, 320
+  lens = [1, 63, 64, 65, 128, 129, 0, 700, 2] + list(rng.randint(30, 200, size=400))
+  off = np.concatenate([[0], np.cumsum(lens)])
+  cents = rng.randn(M, D).astype(np.float32) * 2
+  X = (cents[rng.randint(0, M, size=off[-1])] + rng.randn(off[-1], D)).astype(np.float32)
+  mean = cents.T.copy()
+  sigma = (0.6 + rng.rand(D, M)).astype(np.float32)
+  w = (rng.rand(1, M) + 0.5).astype(np.float32)
+  w /= w.sum()
+  sad = (rng.rand(off[-1]) > 0.3).astype(np.uint8)
+  indices = [("u%d" % i, (int(off[i]), int(off[i + 1]))) for i in range(len(lens)) if lens[i] > 0]
+  res = {}
+  for impl in (0, 1):   # 0: auto -> segmented tensor-core route (>= 16 384 frames); 1: fp32 CUDA-core kernels
+    g = GMM(nmix=M, nmix_start=M)
+    g.initialize(X)
+    g.mean, g.sigma, g.w = mean, sigma, w
+    g.impl = impl
+    for tag, mask in (("all", None), ("sad", sad)):
+      names = g.transform_to_disk(X, indices, sad=mask)
+      res[impl, tag] = (names,) + tuple(np.array(a) for a in g.last_utt_stats_)
+  for tag, mask in (("all", None), ("sad", sad)):
+    names, Zu, Fu = res[0, tag]
+    nr, zr, fr = OG.utterance_stats(X, [(n, dict(indices)[n]) for n in names], mean, sigma, w, sad=mask,
+                                    compute_dtype=np.float64)
+    assert nr == names and Zu.shape == zr.shape and Fu.shape == fr.shape
+    assert relmax(Zu, zr) < 5e-5 and relmax(Fu, fr) < 5e-5, (tag, relmax(Zu, zr), relmax(Fu, fr))
+    # row by row (a short utterance's row is tiny next to the matrix maximum)
+    rowmax = np.abs(zr).max(1)
+    assert np.all(np.abs(Zu - zr).max(1) <= 1e-4 * np.maximum(rowmax, 1e-3)), tag
+    assert res[1, tag][0] == names
+    assert relmax(res[1, tag][1], Zu) < 5e-5 and relmax(res[1, tag][2], Fu) < 5e-5
+
+
 @pytest.mark.parametrize("D,M", [(39, 256), (13, 64), (57, 512)])
 def test_h_feature_dims_not_multiple_of_four(D, M):
   """D = 39 (13 MFCC + deltas) and friends: the frames are carried with zero columns up to the next multiple of four
