@@ -815,24 +815,25 @@ int odin_gmm_utt_stats(odin_gmm_t* g, const float* d_X, const uint8_t* d_sad, co
   if (n_utt == 0) return ODIN_OK;
   cudaStream_t st = as_stream(stream);
   {
-    // Long utterances at tensor-core-sized models go through the tcgen05 3xFP16 E-step, one accumulator per
-    // utterance (gmm_utt_stats_h); short ones stay on the batched fp32 kernels, where a launch covers every
-    // utterance at once (a 100-frame digit does not fill one tensor-core launch).
+    // Tensor-core-sized models (D % 4 == 0, D <= 60) go through the tcgen05 3xFP16 kernels in SEGMENTED mode: the
+    // utterances of the batch back to back, each padded to whole 64-frame tiles, one launch sequence for all of them, the
+    // accumulator drained into the utterance's rows wherever the utterance changes (gmm_utt_stats_hseg).  Measured on
+    // B200 against the fp32 CUDA-core kernels / the earlier one-launch-sequence-per-utterance route (gmm_utt_stats_h, kept
+    // behind ODIN_GMM_UTT_SEG=0): 3 000 digits of 60-200 frames at M = 512: 6.1 -> 1.6 ms; 1 000 utterances of 500-6 000
+    // frames at M = 2048: 153.7 / 56.5 -> 12.3 ms; 200 of 6 000-18 000 frames: 115.5 / 17.0 -> 8.5 ms.
+    // Tiny batches stay on the fp32 kernels (the tensor route's fixed cost is a handful of extra launches).
     int use = 1;
     if (impl == 0 || impl == 3) {
       int rc = pick_impl(g, impl, &use);
       if (rc) return rc;
     }
     const int64_t total = h_frame_offsets[n_utt] - h_frame_offsets[0];
-    if (use == 3 && total >= (int64_t)1024 * n_utt) {
+    static const int seg_env = [] { const char* e = getenv("ODIN_GMM_UTT_SEG"); return e ? atoi(e) : -1; }();
+    if (use == 3 && seg_env == 0 && total >= (int64_t)1024 * n_utt) {
       ODIN_CUDA_CHECK(cudaStreamSynchronize(st));
       return gmm_utt_stats_h(g, d_X + h_frame_offsets[0] * g->D, d_sad ? d_sad + h_frame_offsets[0] : nullptr,
                              h_frame_offsets, n_utt, d_Z, d_Fhat, st);
     }
-    // ... and batches of SHORT utterances through the same kernels in segmented mode (every utterance padded to whole
-    // 64-frame tiles, the accumulator drained at utterance boundaries): config 5, 3 000 digits at M = 512, 5.7 -> ~1 ms.
-    // Tiny batches stay on the fp32 kernels (the tensor route's fixed cost is five extra launches).
-    static const int seg_env = [] { const char* e = getenv("ODIN_GMM_UTT_SEG"); return e ? atoi(e) : -1; }();
     if (use == 3 && seg_env != 0 && (impl == 3 || seg_env == 1 || total >= 16384)) {
       ODIN_CUDA_CHECK(cudaStreamSynchronize(st));
       return gmm_utt_stats_hseg(g, d_X + h_frame_offsets[0] * g->D, d_sad ? d_sad + h_frame_offsets[0] : nullptr, h_frame_offsets,
