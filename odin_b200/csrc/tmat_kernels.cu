@@ -155,6 +155,157 @@ __global__ void __launch_bounds__(256, 2) tmat_gemm_kernel(int M, int N, int K, 
   }
 }
 
+// ---------------------------------------------------------------------------
+// The same product on the fp64 TENSOR instruction (mma.sync m8n8k4 f64, SASS DMMA).  tools/f64_bench.cu on the box: DMMA
+// sustains 37.0 TFLOP/s at 0.25 warp-instructions per clock and SM, DFMA 31.7 TFLOP/s at 1.70 -- the register-blocked
+// kernel above spends its issue slots on the multiply-adds themselves (8.9 TFLOP/s over the four products of the
+// E-step), here they are free for the operand traffic.  CTA tile BM x BN x 16, eight warps of (BM / WM) x (BN / WN),
+// three cp.async stages (16-byte copies when the operand's unit-stride dimension allows it, 8-byte otherwise, zero fill
+// at the edges).  An operand tile is stored the way it arrives -- unit stride along k: [rows][16 + 4], unit stride along
+// the tile dimension: [16][rows + 4]; both row strides are 4 (mod 16) doubles, which makes the fragment reads of a half
+// warp (4 k x 4 rows) fall on 16 distinct 8-byte banks.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async_zfill(void* smem, const void* gmem, int bytes, int src_bytes) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem);
+  if (bytes == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(d), "l"(gmem), "r"(src_bytes) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(d), "l"(gmem), "r"(src_bytes) : "memory");
+}
+
+// one operand tile (ROWS x 16) of stage memory `dst`: element (r, k) of the tile is X[(r0 + r) sr + (k0 + k) sk]
+template <int ROWS>
+__device__ __forceinline__ void dgemm_load_tile(double* dst, const double* __restrict__ X, int64_t sr, int64_t sk, int r0, int nrows,
+                                                int k0, int kend, bool vec, int tid) {
+  constexpr int BK = 16;
+  if (sk == 1) {            // unit stride along k: [ROWS][20]
+    if (vec) {
+      for (int idx = tid; idx < ROWS * (BK / 2); idx += 256) {
+        const int r = idx >> 3, k = (idx & 7) * 2;
+        const int left = (r0 + r < nrows) ? min(2, max(0, kend - (k0 + k))) : 0;
+        const double* src = left > 0 ? X + (int64_t)(r0 + r) * sr + (k0 + k) : X;
+        cp_async_zfill(dst + r * 20 + k, src, 16, 8 * left);
+      }
+    } else {
+      for (int idx = tid; idx < ROWS * BK; idx += 256) {
+        const int r = idx >> 4, k = idx & 15;
+        const bool in = r0 + r < nrows && k0 + k < kend;
+        cp_async_zfill(dst + r * 20 + k, in ? X + (int64_t)(r0 + r) * sr + (k0 + k) : X, 8, in ? 8 : 0);
+      }
+    }
+  } else {                  // unit stride along the tile dimension: [16][ROWS + 4]
+    if (vec) {
+      for (int idx = tid; idx < BK * (ROWS / 2); idx += 256) {
+        const int k = idx / (ROWS / 2), r = (idx - k * (ROWS / 2)) * 2;
+        const int left = (k0 + k < kend) ? min(2, max(0, nrows - (r0 + r))) : 0;
+        const double* src = left > 0 ? X + (int64_t)(k0 + k) * sk + (r0 + r) : X;
+        cp_async_zfill(dst + k * (ROWS + 4) + r, src, 16, 8 * left);
+      }
+    } else {
+      for (int idx = tid; idx < BK * ROWS; idx += 256) {
+        const int k = idx / ROWS, r = idx - k * ROWS;
+        const bool in = r0 + r < nrows && k0 + k < kend;
+        cp_async_zfill(dst + k * (ROWS + 4) + r, in ? X + (int64_t)(k0 + k) * sk + (int64_t)(r0 + r) * sr : X, 8, in ? 8 : 0);
+      }
+    }
+  }
+}
+
+template <int BM, int BN, int WM, int WN>
+__global__ void __launch_bounds__(256, 1) tmat_dgemm_kernel(int M, int N, int K, const double* __restrict__ A, int64_t sai,
+                                                            int64_t sak, const double* __restrict__ B, int64_t sbk, int64_t sbj,
+                                                            double* __restrict__ C, int64_t ldc, double beta) {
+  static_assert(WM * WN == 8, "eight warps");
+  constexpr int BK = 16, STAGES = 3;
+  constexpr int TM = BM / WM, TN = BN / WN, FM = TM / 8, FN = TN / 8;
+  constexpr int SZA = BM * 20, SZB = BN * 20;   // doubles per stage (>= 16 * (rows + 4) for rows >= 16)
+  extern __shared__ __align__(16) double dsm[];
+  double* sA = dsm;
+  double* sB = dsm + STAGES * SZA;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm0 = (warp / WN) * TM, wn0 = (warp % WN) * TN;
+  const int i0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
+  int kbeg = 0, kend = K;
+  if (gridDim.z > 1) {
+    const int per = ((K + (int)gridDim.z - 1) / (int)gridDim.z + BK - 1) / BK * BK;
+    kbeg = (int)blockIdx.z * per;
+    kend = min(K, kbeg + per);
+    C += (int64_t)blockIdx.z * M * ldc;
+    beta = 0.0;
+  }
+  // 16-byte copies need even element offsets: the operand's non-unit stride even, its base 16-byte aligned (tile and
+  // k origins are multiples of 16)
+  const bool vecA = (sak == 1 || sai == 1) && (((sak == 1 ? sai : sak) & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+  const bool vecB = (sbk == 1 || sbj == 1) && (((sbk == 1 ? sbj : sbk) & 1) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+  const int a_m = sak == 1 ? 20 : 1, a_k = sak == 1 ? 1 : BM + 4;   // smem strides of element (m, k)
+  const int b_n = sbk == 1 ? 20 : 1, b_k = sbk == 1 ? 1 : BN + 4;
+  const int nk = (kend - kbeg + BK - 1) / BK;
+  auto load_stage = [&](int kt) {
+    const int st = kt % STAGES, k0 = kbeg + kt * BK;
+    dgemm_load_tile<BM>(sA + st * SZA, A, sai, sak, i0, M, k0, kend, vecA, tid);
+    dgemm_load_tile<BN>(sB + st * SZB, B, sbj, sbk, j0, N, k0, kend, vecB, tid);
+  };
+  double acc[FM][FN][2];
+#pragma unroll
+  for (int a = 0; a < FM; ++a)
+#pragma unroll
+    for (int b = 0; b < FN; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < nk) load_stage(s);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  const int fr = lane >> 2, fk = lane & 3;   // fragment row (m or n) and k of this lane
+  for (int kt = 0; kt < nk; ++kt) {
+    asm volatile("cp.async.wait_group %0;" :: "n"(STAGES - 2) : "memory");
+    __syncthreads();   // stage kt has landed for everybody; everybody is done with stage kt - 1, which is refilled now
+    if (kt + STAGES - 1 < nk) load_stage(kt + STAGES - 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const double* pa = sA + (kt % STAGES) * SZA + (wm0 + fr) * a_m + fk * a_k;
+    const double* pb = sB + (kt % STAGES) * SZB + (wn0 + fr) * b_n + fk * b_k;
+#pragma unroll
+    for (int ks = 0; ks < BK / 4; ++ks) {
+      double av[FM], bv[FN];
+#pragma unroll
+      for (int a = 0; a < FM; ++a) av[a] = pa[8 * a * a_m + 4 * ks * a_k];
+#pragma unroll
+      for (int b = 0; b < FN; ++b) bv[b] = pb[8 * b * b_n + 4 * ks * b_k];
+#pragma unroll
+      for (int a = 0; a < FM; ++a)
+#pragma unroll
+        for (int b = 0; b < FN; ++b)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(acc[a][b][0]), "+d"(acc[a][b][1]) : "d"(av[a]), "d"(bv[b]));
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  // C fragment: row lane / 4, columns 2 (lane % 4), + 1
+#pragma unroll
+  for (int a = 0; a < FM; ++a) {
+    const int gi = i0 + wm0 + 8 * a + fr;
+    if (gi >= M) continue;
+#pragma unroll
+    for (int b = 0; b < FN; ++b) {
+      const int gj = j0 + wn0 + 8 * b + 2 * fk;
+      double* c = C + (int64_t)gi * ldc + gj;
+      if (gj < N) c[0] = (beta == 0.0) ? acc[a][b][0] : fma(beta, c[0], acc[a][b][0]);
+      if (gj + 1 < N) c[1] = (beta == 0.0) ? acc[a][b][1] : fma(beta, c[1], acc[a][b][1]);
+    }
+  }
+}
+
+template <int BM, int BN, int WM, int WN>
+static int launch_dgemm(dim3 grid, int M, int N, int K, const double* A, int64_t sai, int64_t sak, const double* B, int64_t sbk,
+                        int64_t sbj, double* C, int64_t ldc, double beta, cudaStream_t st) {
+  constexpr size_t smem = sizeof(double) * 3 * (BM * 20 + BN * 20);
+  auto k = tmat_dgemm_kernel<BM, BN, WM, WN>;
+  static bool attr_set = false;   // (per instantiation)
+  if (!attr_set) {
+    ODIN_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  k<<<grid, 256, smem, st>>>(M, N, K, A, sai, sak, B, sbk, sbj, C, ldc, beta);
+  ODIN_LAUNCH_CHECK("tmat_dgemm_kernel");
+  return ODIN_OK;
+}
+
 __global__ void __launch_bounds__(256) tmat_splitk_reduce_kernel(const double* __restrict__ ws, int splits, int64_t MN,
                                                                  int N, double* __restrict__ C, int64_t ldc, double beta) {
   for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < MN; e += (int64_t)gridDim.x * 256) {
@@ -170,21 +321,44 @@ __global__ void __launch_bounds__(256) tmat_splitk_reduce_kernel(const double* _
 static int gemm(int M, int N, int K, const double* A, int64_t sai, int64_t sak, const double* B, int64_t sbk, int64_t sbj,
                 double* C, int64_t ldc, double beta, cudaStream_t st, double* ws = nullptr, int64_t ws_cap = 0) {
   if (M <= 0 || N <= 0) return ODIN_OK;
-  dim3 grid((unsigned)ceil_div(N, GBN), (unsigned)ceil_div(M, GBM));
+  static const bool ffma = [] { const char* e = getenv("ODIN_TMAT_GEMM_DFMA"); return e && e[0] == '1'; }();   // A/B runs
+  // tile shape by the output's aspect: 128 x 128, or a 64-wide side for the skinny products (tv = 64 rows / columns)
+  const int bm = ffma ? GBM : (M <= 64 ? 64 : 128), bn = ffma ? GBN : (N <= 64 ? 64 : 128);
+  dim3 grid((unsigned)ceil_div(N, bn), (unsigned)ceil_div(M, bm));
   const int64_t tiles = (int64_t)grid.x * grid.y;
   int splits = 1;
-  if (ws != nullptr && tiles < 2 * sm_count() && K >= 1024) {
-    splits = (int)std::min<int64_t>(std::min<int64_t>(4 * sm_count() / tiles, K / 256), 32);
+  if (ws != nullptr && K >= 1024) {
+    if (ffma) {
+      if (tiles < 2 * sm_count()) splits = (int)std::min<int64_t>(std::min<int64_t>(4 * sm_count() / tiles, K / 256), 32);
+    } else if (tiles < 4 * sm_count()) {
+      // one CTA per SM: the smallest split-K factor that fills >= 92 % of its last wave (slices of >= 512 columns of K)
+      const int sms = sm_count();
+      double best = 0.0;
+      for (int sp = 1; sp <= 32 && K / sp >= 512; ++sp) {
+        const int64_t ctas = tiles * sp;
+        const double eff = (double)ctas / (double)(ceil_div<int64_t>(ctas, sms) * sms);
+        if (eff > best + 1e-9) { best = eff; splits = sp; }
+        if (eff >= 0.92) break;
+      }
+    }
     while (splits > 1 && (int64_t)splits * M * N > ws_cap) --splits;
   }
-  if (splits <= 1) {
-    tmat_gemm_kernel<<<grid, 256, 0, st>>>(M, N, K, A, sai, sak, B, sbk, sbj, C, ldc, beta);
+  grid.z = (unsigned)std::max(splits, 1);
+  double* out = splits > 1 ? ws : C;
+  const int64_t ldo = splits > 1 ? N : ldc;
+  const double b0 = splits > 1 ? 0.0 : beta;
+  if (ffma) {
+    tmat_gemm_kernel<<<grid, 256, 0, st>>>(M, N, K, A, sai, sak, B, sbk, sbj, out, ldo, b0);
     ODIN_LAUNCH_CHECK("tmat_gemm_kernel");
-    return ODIN_OK;
+  } else {
+    int rc;
+    if (bm == 128 && bn == 128) rc = launch_dgemm<128, 128, 4, 2>(grid, M, N, K, A, sai, sak, B, sbk, sbj, out, ldo, b0, st);
+    else if (bm == 128) rc = launch_dgemm<128, 64, 4, 2>(grid, M, N, K, A, sai, sak, B, sbk, sbj, out, ldo, b0, st);
+    else if (bn == 128) rc = launch_dgemm<64, 128, 2, 4>(grid, M, N, K, A, sai, sak, B, sbk, sbj, out, ldo, b0, st);
+    else rc = launch_dgemm<64, 64, 2, 4>(grid, M, N, K, A, sai, sak, B, sbk, sbj, out, ldo, b0, st);
+    if (rc) return rc;
   }
-  grid.z = (unsigned)splits;
-  tmat_gemm_kernel<<<grid, 256, 0, st>>>(M, N, K, A, sai, sak, B, sbk, sbj, ws, N, 0.0);
-  ODIN_LAUNCH_CHECK("tmat_gemm_kernel");
+  if (splits <= 1) return ODIN_OK;
   const int64_t MN = (int64_t)M * N;
   tmat_splitk_reduce_kernel<<<(unsigned)std::min<int64_t>(ceil_div<int64_t>(MN, 256), sm_count() * 8), 256, 0, st>>>(
       ws, splits, MN, N, C, ldc, beta);
@@ -588,46 +762,41 @@ __global__ void __launch_bounds__(256) tmat_gather_rows_kernel(const double* __r
   for (int64_t j = blockIdx.x * 256 + threadIdx.x; j < MD; j += (int64_t)gridDim.x * 256) out[(int64_t)r * MD + j] = src[j];
 }
 
-// nframes and llk totals of a chunk, one CTA, fixed order, accumulated into the packed statistics.
+// nframes and llk totals of a chunk, accumulated into the packed statistics.
 // The reference takes nframes = ceil(sum Z) PER BATCH of its expectation() (gmm_tmat.py:1695, batches of
 // 64 MiB / ((D M + M) itemsize) files, :1444-1449) and adds the batches up, so the ceil is applied per
-// `rows_per_batch` files here as well.
+// `rows_per_batch` files here as well: CTA b sums batch b (the integers it adds are exact in any order), the last CTA
+// sums the likelihoods in a fixed order.  (One CTA for everything was 0.29 ms of a 5 ms E-step.)
 __global__ void __launch_bounds__(1024) tmat_totals_kernel(const double* __restrict__ Z, int64_t n, int M,
                                                            int64_t rows_per_batch, const double* __restrict__ llk,
                                                            double* __restrict__ acc_llk, double* __restrict__ acc_nframes) {
   constexpr int NT = 1024;
   __shared__ double red[NT / 32];
-  __shared__ double total;
   const int tid = threadIdx.x;
-  auto block_sum = [&](double v) -> double {
+  auto block_sum = [&](double v) -> double {   // valid in thread 0
     v = warp_sum(v);
-    __syncthreads();
     if ((tid & 31) == 0) red[tid >> 5] = v;
     __syncthreads();
-    if (tid == 0) {
-      double t = 0.0;
+    double t = 0.0;
+    if (tid == 0)
       for (int w = 0; w < NT / 32; ++w) t += red[w];
-      total = t;
-    }
-    __syncthreads();
-    return total;
+    return t;
   };
-  double nfr = 0.0;
-  for (int64_t s = 0; s < n; s += rows_per_batch) {
+  if (blockIdx.x + 1 < gridDim.x) {
+    const int64_t s = (int64_t)blockIdx.x * rows_per_batch;
     const int64_t e = min(n, s + rows_per_batch);
     const int64_t lo = s * M, hi = e * M;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;   // four independent chains per thread (the loads are the latency)
     int64_t i = lo + tid;
     for (; i + 3 * NT < hi; i += 4 * NT) { a0 += Z[i]; a1 += Z[i + NT]; a2 += Z[i + 2 * NT]; a3 += Z[i + 3 * NT]; }
     for (; i < hi; i += NT) a0 += Z[i];
-    nfr += ceil(block_sum((a0 + a1) + (a2 + a3)));
-  }
-  double b = 0.0;
-  for (int64_t i = tid; i < n; i += NT) b += llk[i];
-  b = block_sum(b);
-  if (tid == 0) {
-    *acc_nframes += nfr;
-    *acc_llk += b;
+    const double t = block_sum((a0 + a1) + (a2 + a3));
+    if (tid == 0) atomicAdd(acc_nframes, ceil(t));
+  } else {
+    double b = 0.0;
+    for (int64_t i = tid; i < n; i += NT) b += llk[i];
+    b = block_sum(b);
+    if (tid == 0) *acc_llk += b;
   }
 }
 
@@ -730,7 +899,10 @@ static int reserve_files(odin_tmat* t, int64_t n) {
   ODIN_CUDA_CHECK(cudaMalloc(&t->d_B1, sizeof(double) * (size_t)n * t->tv));
   ODIN_CUDA_CHECK(cudaMalloc(&t->d_Ex, sizeof(double) * (size_t)n * t->tv));
   ODIN_CUDA_CHECK(cudaMalloc(&t->d_llk, sizeof(double) * (size_t)n));
-  t->ws_cap = (int64_t)16 * n * t->tv;
+  // split-K workspace: slices of B1 [n, tv] and of the accumulating products RU [tv, MD] / LU [M, t2] (at most 512 MiB)
+  t->ws_cap = std::max<int64_t>((int64_t)16 * n * t->tv,
+                                std::min<int64_t>((int64_t)4 * std::max<int64_t>((int64_t)t->tv * t->MD, (int64_t)t->M * t->t2),
+                                                  (int64_t)64 << 20));
   ODIN_CUDA_CHECK(cudaMalloc(&t->d_ws, sizeof(double) * (size_t)t->ws_cap));
   t->cap_files = n;
   return ODIN_OK;
@@ -782,9 +954,10 @@ int tmat_estep(odin_tmat* t, const double* d_Z, const double* d_F, int64_t n_fil
     const double* F = d_F + s * t->MD;
     if ((rc = posterior_chunk(t, Z, F, n, true, t->d_Ex, st))) return rc;
     // RU += Ex^T F  [tv, MD];  LU += Z^T Exx  [M, t2]
-    if ((rc = gemm(t->tv, (int)t->MD, (int)n, t->d_Ex, 1, t->tv, F, t->MD, 1, d_RU, t->MD, 1.0, st))) return rc;
-    if ((rc = gemm(t->M, t->t2, (int)n, Z, 1, t->M, t->d_L1, t->t2, 1, d_LU, t->t2, 1.0, st))) return rc;
-    tmat_totals_kernel<<<1, 1024, 0, st>>>(Z, n, t->M, ref_batch, t->d_llk, d_llk, d_nframes);
+    if ((rc = gemm(t->tv, (int)t->MD, (int)n, t->d_Ex, 1, t->tv, F, t->MD, 1, d_RU, t->MD, 1.0, st, t->d_ws, t->ws_cap))) return rc;
+    if ((rc = gemm(t->M, t->t2, (int)n, Z, 1, t->M, t->d_L1, t->t2, 1, d_LU, t->t2, 1.0, st, t->d_ws, t->ws_cap))) return rc;
+    tmat_totals_kernel<<<(unsigned)(ceil_div<int64_t>(n, ref_batch) + 1), 1024, 0, st>>>(Z, n, t->M, ref_batch, t->d_llk, d_llk,
+                                                                                        d_nframes);
     ODIN_LAUNCH_CHECK("tmat_totals_kernel");
   }
   return ODIN_OK;
