@@ -507,7 +507,7 @@ def tmat_leg(torch, args, rank, world, dist, do_cpu):
       "kernel_ms": {"estep": te / reps, "mstep": tm / reps}, "gpu_launches": int(launches // reps),
       "roofline": {"bound": "fp64", "achieved": flops_file * n / (te / reps / 1e3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                    "frac": flops_file * n / (te / reps / 1e3) / 1e12 / fp64_peak, "traffic": None,
-                   "kernel": "E-step (tmat_gemm_kernel x4 + tmat_file_kernel)",
+                   "kernel": "E-step (tmat_dgemm_kernel x4: fp64 tensor instruction DMMA + tmat_file_kernel)",
                    "peak_source": "measured in this run: cuBLAS DGEMM 4096^3 (nominal B200 fp64: 40 TFLOP/s)",
                    "algorithmic_flops_per_file": flops_file},
   }
