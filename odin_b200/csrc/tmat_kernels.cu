@@ -367,10 +367,18 @@ static int gemm(int M, int N, int K, const double* A, int64_t sai, int64_t sak, 
 }
 
 // ---------------------------------------------------------------------------
-// in-place Cholesky of the lower triangle of S [n][P] (A = G G^T); returns false on a non-positive pivot
+// in-place Cholesky of the lower triangle of S [n][P] (A = G G^T), P >= n + 1; returns false on a non-positive pivot.
+//
+// Right-looking on UNSCALED columns: step k subtracts (S[i][k] / S[k][k]) S[j][k] from the trailing triangle, so a step
+// is ONE barrier (the pivot of step k + 1 is final when step k's updates are) with neither a square root nor a column
+// scaling on the critical path; the columns are divided by the square roots of their pivots in one pass at the end
+// (pivots parked in the pad column S[k][n]).  Threads form a 16 x (nt / 16) grid over (j, i): no index divisions.
+// The first version (scale column, barrier, update through e -> (e / r, e % r), three barriers per column) took
+// ~130 us of the ~200 us a 64 x 64 file spent in tmat_file_kernel.
 // ---------------------------------------------------------------------------
 __device__ bool chol_lower(double* S, int n, int P, int* s_flag) {
   const int tid = threadIdx.x, nt = blockDim.x;
+  const int tx = tid & 15, ty = tid >> 4, ny = nt >> 4;
   for (int k = 0; k < n; ++k) {
     __syncthreads();
     const double akk = S[k * P + k];
@@ -378,18 +386,18 @@ __device__ bool chol_lower(double* S, int n, int P, int* s_flag) {
       if (tid == 0) *s_flag = 1;
       return false;
     }
-    const double g = sqrt(akk);
-    __syncthreads();
-    if (tid == 0) S[k * P + k] = g;
-    for (int i = k + 1 + tid; i < n; i += nt) S[i * P + k] /= g;
-    __syncthreads();
-    const int r = n - k - 1;
-    for (int e = tid; e < r * r; e += nt) {
-      const int ii = e / r, jj = e - ii * r;
-      if (jj > ii) continue;
-      const int i = k + 1 + ii, j = k + 1 + jj;
-      S[i * P + j] = fma(-S[i * P + k], S[j * P + k], S[i * P + j]);
+    const double inv = 1.0 / akk;
+    for (int i = k + 1 + ty; i < n; i += ny) {
+      const double lik = S[i * P + k] * inv;
+      for (int j = k + 1 + tx; j <= i; j += 16) S[i * P + j] = fma(-lik, S[j * P + k], S[i * P + j]);
     }
+  }
+  __syncthreads();
+  for (int k = tid; k < n; k += nt) S[k * P + n] = sqrt(S[k * P + k]);
+  __syncthreads();
+  for (int k = tx; k < n; k += 16) {
+    const double g = S[k * P + n], rg = 1.0 / g;
+    for (int i = k + ty; i < n; i += ny) S[i * P + k] = (i == k) ? g : S[i * P + k] * rg;
   }
   __syncthreads();
   return true;
@@ -439,12 +447,22 @@ __global__ void __launch_bounds__(256) tmat_file_kernel(FileArgs a) {
     // (strict upper triangle), the diagonal of G moves to dg[] and 1 / G[j][j] takes its place
     for (int i = tid; i < n; i += 256) dg[i] = S[i * P + i];
     __syncthreads();
-    for (int j = tid; j < n; j += 256) {
-      S[j * P + j] = 1.0 / dg[j];
-      for (int i = j + 1; i < n; ++i) {
-        double acc = 0.0;
-        for (int k = j; k < i; ++k) acc = fma(S[i * P + k], S[j * P + k], acc);   // G[i][k] * Ginv[k][j]
-        S[j * P + i] = -acc / dg[i];
+    {
+      // four lanes per column j: each forms a quarter of the dot product, the quarters meet by shuffle (fixed order),
+      // lane 0 of the group writes; __syncwarp orders the group's write before its next reads
+      const int q = tid & 3;
+      const unsigned gmask = 0xFu << (threadIdx.x & 28);
+      for (int j = tid >> 2; j < n; j += 64) {
+        if (q == 0) S[j * P + j] = 1.0 / dg[j];
+        __syncwarp(gmask);
+        for (int i = j + 1; i < n; ++i) {
+          double acc = 0.0;
+          for (int k = j + q; k < i; k += 4) acc = fma(S[i * P + k], S[j * P + k], acc);   // G[i][k] * Ginv[k][j]
+          acc += __shfl_xor_sync(gmask, acc, 1);
+          acc += __shfl_xor_sync(gmask, acc, 2);
+          if (q == 0) S[j * P + i] = -acc / dg[i];
+          __syncwarp(gmask);
+        }
       }
     }
     // careful: thread j reads G[i][k] for k in [j, i) -- strictly lower entries and never the diagonal slot of
@@ -522,16 +540,28 @@ __global__ void __launch_bounds__(256) tmat_solve_kernel(int tv, int D, int64_t 
     if (tid == 0) atomicExch(flag, 2);
     continue;
   }
-  for (int d = tid; d < D; d += 256) {
-    for (int i = 0; i < n; ++i) {            // G y = r
-      double acc = R[i * Q + d];
-      for (int k = 0; k < i; ++k) acc = fma(-S[i * P + k], R[k * Q + d], acc);
-      R[i * Q + d] = acc / S[i * P + i];
-    }
-    for (int i = n - 1; i >= 0; --i) {       // G^T x = y
-      double acc = R[i * Q + d];
-      for (int k = i + 1; k < n; ++k) acc = fma(-S[k * P + i], R[k * Q + d], acc);
-      R[i * Q + d] = acc / S[i * P + i];
+  {
+    // four lanes per right-hand side: quarter dot products joined by shuffle in a fixed order (one thread per column
+    // left 60 of 256 threads walking 2 n^2 dependent multiply-adds)
+    const int q = tid & 3;
+    const unsigned gmask = 0xFu << (threadIdx.x & 28);
+    for (int d = tid >> 2; d < D; d += 64) {
+      for (int i = 0; i < n; ++i) {            // G y = r
+        double acc = 0.0;
+        for (int k = q; k < i; k += 4) acc = fma(S[i * P + k], R[k * Q + d], acc);
+        acc += __shfl_xor_sync(gmask, acc, 1);
+        acc += __shfl_xor_sync(gmask, acc, 2);
+        if (q == 0) R[i * Q + d] = (R[i * Q + d] - acc) / S[i * P + i];
+        __syncwarp(gmask);
+      }
+      for (int i = n - 1; i >= 0; --i) {       // G^T x = y
+        double acc = 0.0;
+        for (int k = i + 1 + q; k < n; k += 4) acc = fma(S[k * P + i], R[k * Q + d], acc);
+        acc += __shfl_xor_sync(gmask, acc, 1);
+        acc += __shfl_xor_sync(gmask, acc, 2);
+        if (q == 0) R[i * Q + d] = (R[i * Q + d] - acc) / S[i * P + i];
+        __syncwarp(gmask);
+      }
     }
   }
   __syncthreads();
