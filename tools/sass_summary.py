@@ -8,7 +8,7 @@ import re
 import subprocess
 import sys
 
-KEYS = ["UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UBLKCP", "UTMALDG", "SYNCS", "LDGSTS", "FFMA2", "FADD2", "FMUL2",
+KEYS = ["UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UBLKCP", "UTMALDG", "SYNCS", "LDGSTS", "DMMA", "FFMA2", "FADD2", "FMUL2",
         "FFMA", "DFMA", "HMMA", "LDS", "STS", "SHFL", "RED", "ATOM", "BAR", "MUFU"]
 
 
