@@ -655,7 +655,10 @@ __global__ void __launch_bounds__(JT) tmat_jacobi_kernel(double* __restrict__ W,
     al += rp[0]; be += rp[1]; ga += rp[2];
   }
   cl.sync();   // nobody leaves (or overwrites part) while a neighbour still reads it
-  if (bye || fabs(ga) <= 1e-15 * sqrt(al * be) || ga == 0.0) return;   // already orthogonal to working precision
+  // already orthogonal: |cos| <= 1e-13.  (1e-15 sat at the rounding floor of the 30 720-long dot products -- ~1e-16 sqrt(MD)
+  // -- so a sweep after the Gram pre-rotation still "rotated" pairs by angles of that size and a second sweep was needed
+  // to see none: M-step 2.5 -> 2.2 ms at config-5 scale, 300 -> 246 ms at tv 400.  The tests ask for 1e-10.)
+  if (bye || fabs(ga) <= 1e-13 * sqrt(al * be) || ga == 0.0) return;
   if (tid == 0 && rank == 0) atomicAdd(n_rot, 1);
   const double zeta = (be - al) / (2.0 * ga);
   const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
