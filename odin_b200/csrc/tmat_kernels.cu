@@ -1040,7 +1040,9 @@ int tmat_mstep(odin_tmat* t, const double* d_acc, int min_div, int orthogonalize
     if ((rc = gemm(t->tv, (int)t->MD, t->tv, t->d_U, t->tv, 1, t->d_Tm, t->MD, 1, t->d_TinvS, t->MD, 0.0, st))) return rc;
     ODIN_CUDA_CHECK(cudaMemcpyAsync(t->d_Tm, t->d_TinvS, sizeof(double) * (size_t)t->tv * t->MD, cudaMemcpyDeviceToDevice, st));
   }
-  if (orthogonalize && t->tv > 1 && t->tv <= TMAT_GRAM_MAX) {
+  static const int eig_lib_min = [] { const char* e = getenv("ODIN_TMAT_EIG_LIB_MIN"); return e ? atoi(e) : 64; }();   // measured: own solver 0.8 / 2.2 / 5.9 ms M-step at tv 32 / 64 / 96, Dsyevd 2.5 / 2.0 / 4.3
+  const bool eig_lib = t->tv >= eig_lib_min && getenv("ODIN_TMAT_NO_PREROT") == nullptr && cusolver_ready();
+  if (orthogonalize && t->tv > 1 && t->tv <= TMAT_GRAM_MAX && !eig_lib) {
     // pre-rotation through the Gram matrix (three passes over T) -- see tmat_eig_kernel
     const int tv = t->tv;
     const size_t need = (size_t)33 * tv * tv;   // G | 32 split-K slices
@@ -1057,7 +1059,7 @@ int tmat_mstep(odin_tmat* t, const double* d_acc, int min_div, int orthogonalize
     if ((rc = gemm(tv, (int)t->MD, tv, t->d_U, 1, tv, t->d_Tm, t->MD, 1, t->d_TinvS, t->MD, 0.0, st))) return rc;
     ODIN_CUDA_CHECK(cudaMemcpyAsync(t->d_Tm, t->d_TinvS, sizeof(double) * (size_t)tv * t->MD, cudaMemcpyDeviceToDevice, st));
   }
-  if (orthogonalize && t->tv > TMAT_GRAM_MAX && getenv("ODIN_TMAT_NO_PREROT") == nullptr && cusolver_ready()) {
+  if (orthogonalize && t->tv > 1 && eig_lib) {
     // the same pre-rotation beyond the shared-memory eigen-solver: at tv 400, 2048 x 60 the one-sided sweeps alone took
     // 11 passes over the 393 MB matrix (4 389 launches, 0.97 s of a 1.24 s M-step; tools/tmat_scale.py)
     const int tv = t->tv;
