@@ -14,19 +14,19 @@
 //
 // Kernel plan (one ragged batch of utterances per call):
 //   fe_dc_kernel     per-utterance sample sums (exact int64 for int16 PCM)
-//   fe_frame_kernel  one CTA per tile of 32 consecutive frames of ONE utterance:
-//                    PCM -> smem (DC removal + pre-emphasis fused into the
-//                    staging copy), then one warp per PAIR of frames: the two
-//                    real frames are packed as re/im of one complex n_fft-point
-//                    Stockham FFT held in shared memory (radix 8/16 butterflies
-//                    in registers, window multiply and the fp64 frame energy
-//                    fused into the first pass), spectra are split by symmetry,
-//                    |.|^2, sparse mel triangles, 10 log10 -> unclipped log-mel
-//                    rows + an atomic per-utterance max.  Spectra never touch HBM.
-//   fe_post_kernel   utterance pass: utterance-global top_db clip, DCT, c0,
-//                    delta / delta-delta with the reference's edge/latency quirks.
-//   fe_vad_*_kernel  one warp per utterance: standardise (numpy-exact float32
-//                    mean/std), 1-D EM in fp64, threshold, smoothing.
+//   frame kernels    PCM -> unclipped log-mel rows, frame energies and an atomic per-utterance max; the two real frames
+//                    of a pair are the re / im of one complex FFT, spectra never touch HBM:
+//                      fe_frame5_kernel (fe_frame5.cu)  n_fft <= 1024: packed f32x2 four-step FFT in registers, every warp
+//                                       on its own (cp.async staging), mel projection in registers -- the default;
+//                      fe_frame4_kernel the scalar four-step kernel it replaced (spectrum / complex STFT outputs, unusual
+//                                       filterbanks);  fe_frame_kernel  Stockham FFT in shared memory (n_fft = 2048)
+//   fe_post9_kernel  utterance pass: utterance-global top_db clip, DCT, c0, delta / delta-delta with the reference's
+//                    edge / latency quirks, on 16-byte conflict-free shared-memory accesses and packed pairs
+//                    (9-tap deltas of order 2, widths divisible by 4); fe_post_kernel for every other shape
+//   fe_vad_gmm_kernel / fe_vad_gmm_warp_kernel / fe_vad_thr_kernel
+//                    SADgmm: a thread-block cluster (long utterances) or a warp (batches of short ones) per utterance:
+//                    standardise (numpy-exact float32 mean / std), 1-D EM in fp64 with the component count as a template
+//                    parameter, threshold, smoothing;  SADthreshold: one warp per utterance
 //   fe_compact_*     ApplyingSAD row compaction.
 #include <float.h>
 #include <math.h>

@@ -15,8 +15,11 @@
 //
 // Kernels
 //   tmat_refresh_kernel   one CTA per mixture (T2 block in smem)
-//   tmat_gemm_kernel      128x64x16 register-blocked (8x4 per thread) fp64 GEMM with generic strides (all products)
-//   tmat_file_kernel      one CTA per file: the tv x tv system lives in ONE padded smem square --
+//   tmat_dgemm_kernel     fp64 GEMM with generic strides on the tensor instruction (mma.sync m8n8k4 f64 = DMMA), 128x128x16
+//                         tiles (64-wide for skinny outputs), cp.async 3-stage, split-K (all products);
+//                         tmat_gemm_kernel: the register-blocked DFMA kernel it replaced (ODIN_TMAT_GEMM_DFMA=1)
+//   tmat_file_kernel      one CTA per file: the tv x tv system lives in ONE padded smem square (one-barrier-per-column
+//                         Cholesky on unscaled columns, chol_lower) --
 //                         Cholesky factor in the lower triangle, its inverse written transposed into the
 //                         upper triangle, Cxx = G^-T G^-1 back into the lower triangle -- so tv = 128 fits
 //   tmat_solve_kernel     one CTA per mixture: Cholesky + forward / backward substitution, one thread per column
