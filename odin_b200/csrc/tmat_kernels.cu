@@ -848,6 +848,17 @@ constexpr size_t SMEM_LIMIT = 200 * 1024;   // beyond this a kernel's matrices m
 // per-CTA global slabs for the sizes whose systems do not fit shared memory (tv > ~150): `ctas` slabs of
 // `doubles_per_cta`; the data stay L2-resident while a CTA works on them, but the factorisations are not blocked,
 // so this route is much slower per FLOP than the shared-memory one
+// pairs of rows still not orthogonal after the Gram pre-rotation: |G[p][q]| > 1e-13 sqrt(G[p][p] G[q][q]) (the criterion of
+// tmat_jacobi_kernel), counted from ONE more Gram matrix -- when there is none, the verifying sweep (tv - 1 launches) is skipped
+__global__ void __launch_bounds__(256) tmat_gramcheck_kernel(const double* __restrict__ G, int n, int* __restrict__ count) {
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e >= n * n) return;
+  const int p = e / n, q = e - p * n;
+  if (q >= p) return;
+  const double g = G[e];
+  if (fabs(g) > 1e-13 * sqrt(G[p * n + p] * G[q * n + q]) && g != 0.0) atomicAdd(count, 1);
+}
+
 // ---- symmetric eigen-solver for tv > TMAT_GRAM_MAX: cuSOLVER's Dsyevd, bound at run time ------------------------------
 // The Gram pre-rotation needs the eigenvectors of ONE tv x tv matrix per M-step (tv 400-600 at the NIST-SRE recipe's
 // scale).  That is a plain LAPACK call outside any hot loop, so beyond the size tmat_eig_kernel holds in shared memory it
@@ -1045,7 +1056,9 @@ int tmat_mstep(odin_tmat* t, const double* d_acc, int min_div, int orthogonalize
   }
   static const int eig_lib_min = [] { const char* e = getenv("ODIN_TMAT_EIG_LIB_MIN"); return e ? atoi(e) : 64; }();   // measured: own solver 0.8 / 2.2 / 5.9 ms M-step at tv 32 / 64 / 96, Dsyevd 2.5 / 2.0 / 4.3
   const bool eig_lib = t->tv >= eig_lib_min && getenv("ODIN_TMAT_NO_PREROT") == nullptr && cusolver_ready();
+  bool prerot = false;
   if (orthogonalize && t->tv > 1 && t->tv <= TMAT_GRAM_MAX && !eig_lib) {
+    prerot = true;
     // pre-rotation through the Gram matrix (three passes over T) -- see tmat_eig_kernel
     const int tv = t->tv;
     const size_t need = (size_t)33 * tv * tv;   // G | 32 split-K slices
@@ -1085,7 +1098,25 @@ int tmat_mstep(odin_tmat* t, const double* d_acc, int min_div, int orthogonalize
       ODIN_LAUNCH_CHECK("tmat_eigperm_kernel");
       if ((rc = gemm(tv, (int)t->MD, tv, t->d_U, 1, tv, t->d_Tm, t->MD, 1, t->d_TinvS, t->MD, 0.0, st))) return rc;
       ODIN_CUDA_CHECK(cudaMemcpyAsync(t->d_Tm, t->d_TinvS, sizeof(double) * (size_t)tv * t->MD, cudaMemcpyDeviceToDevice, st));
+      prerot = true;
     }
+  }
+  bool rows_orthogonal = false;
+  if (orthogonalize && prerot && getenv("ODIN_TMAT_NO_GRAMCHECK") == nullptr) {
+    // one more Gram matrix (a ~60 us GEMM at tv = 64) instead of a verifying sweep of tv - 1 launches
+    const int tv = t->tv;
+    double* G = t->d_gws;   // (33 tv^2 doubles reserved by the pre-rotation)
+    int* d_rot = t->d_flag + 1;
+    if ((rc = gemm(tv, tv, (int)t->MD, t->d_Tm, t->MD, 1, t->d_Tm, 1, t->MD, G, tv, 0.0, st, G + (size_t)tv * tv,
+                   (int64_t)32 * tv * tv)))
+      return rc;
+    ODIN_CUDA_CHECK(cudaMemsetAsync(d_rot, 0, sizeof(int), st));
+    tmat_gramcheck_kernel<<<ceil_div(tv * tv, 256), 256, 0, st>>>(G, tv, d_rot);
+    ODIN_LAUNCH_CHECK("tmat_gramcheck_kernel");
+    int h_rot = 1;
+    ODIN_CUDA_CHECK(cudaMemcpyAsync(&h_rot, d_rot, sizeof(int), cudaMemcpyDeviceToHost, st));
+    ODIN_CUDA_CHECK(cudaStreamSynchronize(st));
+    rows_orthogonal = h_rot == 0;
   }
   if (orthogonalize && t->tv > 1) {
     const int np = t->tv + (t->tv & 1);
@@ -1128,7 +1159,7 @@ int tmat_mstep(odin_tmat* t, const double* d_acc, int min_div, int orthogonalize
       if (e_inst != cudaSuccess) return set_error(ODIN_ECUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e_inst));
       t->sweep_graph = exec;
     }
-    for (int sweep = 0; sweep < sweeps; ++sweep) {
+    for (int sweep = 0; sweep < sweeps && !rows_orthogonal; ++sweep) {
       ODIN_CUDA_CHECK(cudaGraphLaunch((cudaGraphExec_t)t->sweep_graph, st));
       g_launches.fetch_add(np - 1, std::memory_order_relaxed);
       int h_rot = 0;
