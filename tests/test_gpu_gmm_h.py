@@ -187,12 +187,16 @@ def test_h_per_utterance_statistics():
     assert relmax(Zu, zr) < 5e-5 and relmax(Fu, fr) < 5e-5, (relmax(Zu, zr), relmax(Fu, fr))
 
 
-def test_h_per_utterance_statistics_short_utterances_segmented():
+@pytest.mark.parametrize("sub_batch", [None, "1024"])
+def test_h_per_utterance_statistics_short_utterances_segmented(sub_batch, monkeypatch):
   """Thousands of SHORT utterances (the digits of config 5) through the tcgen05 kernels in segmented mode
   (odin_gmm_utt_stats -> gmm_utt_stats_hseg: utterances padded to whole 64-frame tiles, the accumulator drained at
   every utterance change): lengths around the tile size (1, 63, 64, 65, 128, 129 frames), an empty utterance, a SAD mask,
-  a long utterance in the middle, M not a multiple of the 128-mixture chunk; against the oracle and the fp32 route."""
+  a long utterance in the middle, M not a multiple of the 128-mixture chunk; against the oracle and the fp32 route.
+  With ODIN_H_SUB_BATCH=1024 the batch is cut into many groups of whole utterances (the 700-frame one alone in its)."""
   import tempfile
+  if sub_batch is not None:
+    monkeypatch.setenv("ODIN_H_SUB_BATCH", sub_batch)
   from odin_b200.ml import GMM
   from oracle import gmm as OG
   rng = np.random.RandomState(5)
