@@ -233,6 +233,33 @@ def test_h_per_utterance_statistics_short_utterances_segmented(sub_batch, monkey
     assert relmax(res[1, tag][1], Zu) < 5e-5 and relmax(res[1, tag][2], Fu) < 5e-5
 
 
+def test_h_segmented_statistics_add_up_at_config5_scale():
+  """size-independent property of the segmented route at config 5's size (3 000 utterances of 60-200 frames, 512
+  mixtures) and with utterances of config 3's lengths at 2048 mixtures: the per-utterance statistics add up to the
+  statistics of the whole call (Z, and F after un-centring F-hat + Z mean), every row sums to its utterance's length.
+  Tolerance 1e-4: the whole-call kernel drains its fp32 TMEM accumulator every 256 tiles (16 384 frames), whose
+  truncating accumulation leaves its totals 2-4e-5 low (sum Z = N (1 - 2e-5) here); the per-utterance rows, drained every
+  <= 32 tiles, agree with the fp32 CUDA-core kernels to 3e-6."""
+  import torch
+  for M, lo, hi, n_utt in ((512, 60, 200, 3000), (2048, 500, 6000, 300)):
+    D = 60
+    rng = np.random.RandomState(M)
+    lens = rng.randint(lo, hi, size=n_utt)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(M)
+    X = torch.randn(int(off[-1]), D, generator=gen, device="cuda") * 2.0
+    mean, sigma, w = synth.gmm_params(D, M, seed=M + 3)
+    gm = _gmm(M, mean, sigma * 4.0, w, 0)
+    Z, F, S, L = gm.expectation(X)
+    Zu, Fu = gm._utt_stats_device(X, None, off)
+    Zu, Fu = Zu.double().cpu().numpy(), Fu.double().cpu().numpy().reshape(n_utt, M, D)
+    assert np.abs(Zu.sum(1) - lens).max() < 1e-4 * lens.max()
+    assert relmax(Zu.sum(0)[None, :], np.asarray(Z, dtype=np.float64).reshape(1, M)) < 1e-4
+    Ftot = (Fu + Zu[:, :, None] * mean.T.astype(np.float64)[None]).sum(0)       # [M, D]
+    assert relmax(Ftot.T, np.asarray(F, dtype=np.float64)) < 1e-4
+
+
 @pytest.mark.parametrize("D,M", [(39, 256), (13, 64), (57, 512)])
 def test_h_feature_dims_not_multiple_of_four(D, M):
   """D = 39 (13 MFCC + deltas) and friends: the frames are carried with zero columns up to the next multiple of four
