@@ -43,6 +43,23 @@ def test_frontend_matches_reference(seed):
   assert np.array_equal(s2, R["sad_thr"]) and abs(t2 - R["sad_thr_threshold"]) < 1e-9
 
 
+def test_frontend_long_utterance_matches_reference():
+  """Config 3 at the benchmark's utterance lengths (60 s: 5 998 frames, utterance-global top_db and SADgmm over thousands
+  of frames) and on the float32 samples soundfile would hand over -- pins the oracle the GPU test
+  `test_config3_full_length_utterances_vs_oracle` compares against."""
+  from oracle.make_golden import FE_CONFIGS
+  cfg = FE_CONFIGS["cfg3"]
+  raw = synth.speech_like(700, 60.0, cfg["sr"], seed=99)
+  for x in (raw, (raw[:cfg["sr"] * 8].astype(np.float64) / 32768.0).astype(np.float32)):
+    R = _ref_chain(x, cfg["sr"], cfg)
+    o = F.extract(x, cfg["sr"], cfg["frame_length"], cfg["step_length"], cfg["n_fft"],
+                  n_mels=cfg["n_mels"], fmin=cfg["fmin"], fmax=cfg["fmax"], vad="gmm")
+    assert o["mfcc"].shape == R["mfcc"].shape
+    assert np.array_equal(o["stft_energy"], R["stft_energy"])
+    assert relmax(o["mspec"], R["mspec"]) < 1e-12 and relmax(o["mfcc"], R["mfcc"]) < 1e-12
+    assert np.array_equal(o["sad"], R["sad_gmm"])
+
+
 def test_mel_and_dct_tables():
   _, S = ref_shim.load_frontend()
   for sr, n_fft, n_mels, fmin, fmax in [(16000, 512, 40, 64, 8000), (16000, 1024, 80, 64, 8000),
